@@ -1,0 +1,268 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. ctypes binding of oracle/_build/liboracle.so (built by oracle/Makefile)."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
+            for f in os.listdir(_HERE) if f.endswith((".hpp", ".cpp", ".h"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("min_base_call_quality", "min_map_quality", "remove_duplicates", "only_proper_pairs")] + \
+        [(n, C.c_float) for n in ("min_frequency", "min_frequency_filter", "target_lod_frequency")] + \
+        [(n, C.c_int32) for n in ("max_vq", "min_vq", "vq_filter", "max_gq", "min_gq", "low_gq_filter", "min_coverage", "low_depth_filter",
+                                  "indel_repeat_filter", "rmxn_max_repeat_len", "rmxn_min_repetitions")] + \
+        [("rmxn_freq_limit", C.c_float)] + \
+        [(n, C.c_int32) for n in ("ploidy", "forced_noise_level", "noise_model")] + \
+        [("sb_acceptance", C.c_float)] + \
+        [(n, C.c_int32) for n in ("sb_model", "filter_single_strand")] + \
+        [("no_call_filter", C.c_float)] + \
+        [(n, C.c_int32) for n in ("call_mnvs", "max_size_mnv", "max_gap_mnv", "collapse")] + \
+        [(n, C.c_float) for n in ("collapse_freq_threshold", "collapse_freq_ratio_threshold")] + \
+        [(n, C.c_int32) for n in ("exclude_mnvs_from_collapsing", "tracked_anchor_size", "output_gvcf", "source_is_stitched", "source_is_collapsed")]
+
+
+class ReadStruct(C.Structure):
+    _fields_ = [("pos0", C.c_int32), ("flag", C.c_int32), ("mapq", C.c_int32), ("n_cigar", C.c_int32), ("cigar", C.POINTER(C.c_uint32)),
+                ("l_seq", C.c_int32), ("seq", C.c_char_p), ("qual", C.POINTER(C.c_uint8)), ("has_tags", C.c_int32), ("xd", C.c_char_p),
+                ("xr", C.c_char_p), ("has_xv", C.c_int32), ("xv", C.c_int32), ("has_xw", C.c_int32), ("xw", C.c_int32)]
+
+
+class Record(C.Structure):
+    _fields_ = [("pos", C.c_int32), ("type", C.c_int32), ("genotype", C.c_int32), ("gq", C.c_int32), ("vq", C.c_int32),
+                ("filter_mask", C.c_uint32), ("n_filters", C.c_int32), ("filters", C.c_int32 * 8),
+                ("noise_level", C.c_int32), ("total_coverage", C.c_int32), ("sum_base_quality", C.c_double),
+                ("cov", C.c_int32 * 3), ("support", C.c_int32 * 3), ("well_anchored", C.c_int32 * 3),
+                ("allele_support", C.c_int32), ("ref_support", C.c_int32), ("num_no_calls", C.c_int32),
+                ("fraction_no_calls", C.c_float), ("frequency", C.c_float), ("bias_score", C.c_double), ("gatk_bias_score", C.c_double),
+                ("bias_acceptable", C.c_int32), ("var_both_strands", C.c_int32), ("cov_both_strands", C.c_int32), ("forced", C.c_int32),
+                ("collapsed_mut", C.c_int32 * 8), ("collapsed_total", C.c_int32 * 8), ("ref_len", C.c_int32), ("alt_len", C.c_int32)]
+
+
+# enums (src/lib/Pisces.Domain/Types/*.cs)
+A, G, Cc, T, N, DEL = 0, 1, 2, 3, 4, 5
+FWD, REV, STITCHED = 0, 1, 2
+SNV, INSERTION, DELETION, MNV, REFERENCE = 0, 1, 2, 3, 4
+FILTERS = ["StrandBias", "PoolBias", "AmpliconBias", "LowVariantQscore", "LowDepth", "LowVariantFrequency", "LowGenotypeQuality",
+           "IndelRepeatLength", "MultiAllelicSite", "RMxN", "ForcedReport", "OffTarget", "NoCall", "Unknown"]
+GENOTYPES = ["HeterozygousAlt1Alt2", "Alt12LikeNoCall", "HeterozygousAltRef", "HomozygousAlt", "HomozygousRef", "RefLikeNoCall",
+             "AltLikeNoCall", "RefAndNoCall", "AltAndNoCall", "HemizygousRef", "HemizygousAlt", "HemizygousNoCall", "Others"]
+_CIGAR_OPS = "MIDNSHP=X"
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.po_last_error.restype = C.c_char_p
+        L.po_caller_create.restype = C.c_void_p
+        L.po_caller_create.argtypes = [C.POINTER(Config), C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]
+        L.po_caller_destroy.argtypes = [C.c_void_p]
+        L.po_caller_add_forced.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p]
+        for f in ("po_caller_add_read", "po_caller_add_read_counts_only", "po_caller_add_read_candidates_only"):
+            getattr(L, f).argtypes = [C.c_void_p, C.POINTER(ReadStruct)]
+        L.po_caller_finish.argtypes = [C.c_void_p]
+        L.po_caller_num_records.argtypes = [C.c_void_p]
+        L.po_caller_get_record.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Record)]
+        for f in ("po_caller_record_ref", "po_caller_record_alt"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int32]
+            getattr(L, f).restype = C.c_char_p
+        L.po_caller_num_write_batches.argtypes = [C.c_void_p]
+        L.po_caller_write_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.po_caller_total_called.argtypes = [C.c_void_p]
+        L.po_caller_total_collapsed.argtypes = [C.c_void_p]
+        L.po_get_allele_count.argtypes = [C.c_void_p] + [C.c_int32] * 7
+        L.po_get_sum_base_quality.argtypes = [C.c_void_p] + [C.c_int32] * 6
+        L.po_get_sum_base_quality.restype = C.c_double
+        L.po_get_collapsed_count.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.po_set_allele_count.argtypes = [C.c_void_p] + [C.c_int32] * 5
+        L.po_add_gapped_ref_count.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.po_dump_counts.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        L.po_num_candidates_at.argtypes = [C.c_void_p, C.c_int32]
+        L.po_get_candidate_at.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_int32)]
+        L.po_process_allele.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(Record)]
+        L.po_raw_vq.argtypes = [C.c_int32] * 3
+        L.po_raw_vq.restype = C.c_double
+        L.po_vq.argtypes = [C.c_int32] * 4
+        L.po_pvalue.argtypes = [C.c_int32] * 3
+        L.po_pvalue.restype = C.c_double
+        L.po_poisson_cdf.argtypes = [C.c_double, C.c_double]
+        L.po_poisson_cdf.restype = C.c_double
+        L.po_mathnet_gamma_lower_regularized.argtypes = [C.c_double, C.c_double]
+        L.po_mathnet_gamma_lower_regularized.restype = C.c_double
+        L.po_mathnet_gamma_ln.argtypes = [C.c_double]
+        L.po_mathnet_gamma_ln.restype = C.c_double
+        L.po_strand_bias.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_double, C.c_double, C.c_int32, C.POINTER(C.c_double)]
+        L.po_somatic_gq.argtypes = [C.c_int32] * 5 + [C.c_float, C.c_int32, C.c_int32]
+        L.po_somatic_genotype.argtypes = [C.c_int32] * 4 + [C.c_float, C.c_int32]
+        L.po_anchor_adjusted_count.argtypes = [C.POINTER(C.c_int32)] + [C.c_int32] * 5
+        _lib = L
+    return _lib
+
+
+def default_config(**kw):
+    c = Config()
+    lib().po_default_config(C.byref(c))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+def parse_cigar(s):
+    out, num = [], ""
+    for ch in s:
+        if ch.isdigit():
+            num += ch
+        else:
+            out.append((int(num) << 4) | _CIGAR_OPS.index(ch))
+            num = ""
+    return out
+
+
+class SimpleRead:
+    """A read as the reference's tests build them (ReadTestHelper.CreateRead, TestUtilities/ReadTestHelper.cs:72)."""
+
+    def __init__(self, pos, seq, cigar, quals=30, flag=0, mapq=10, xd=None, xr=None, xv=None, xw=None, has_tags=None):
+        """pos is the 1-based Read.Position."""
+        self.pos0 = pos - 1
+        self.seq = seq
+        self.cigar = parse_cigar(cigar) if isinstance(cigar, str) else list(cigar)
+        self.quals = [quals] * len(seq) if isinstance(quals, int) else list(quals)
+        self.flag, self.mapq, self.xd, self.xr, self.xv, self.xw = flag, mapq, xd, xr, xv, xw
+        self.has_tags = has_tags if has_tags is not None else any(v is not None for v in (xd, xr, xv, xw))
+
+    def to_struct(self):
+        r = ReadStruct()
+        r.pos0, r.flag, r.mapq = self.pos0, self.flag, self.mapq
+        self._cig = (C.c_uint32 * max(1, len(self.cigar)))(*self.cigar)
+        r.n_cigar, r.cigar = len(self.cigar), self._cig
+        self._seq = self.seq.encode()
+        r.l_seq, r.seq = len(self.seq), self._seq
+        self._q = (C.c_uint8 * max(1, len(self.quals)))(*self.quals)
+        r.qual = self._q
+        r.has_tags = int(self.has_tags)
+        r.xd = self.xd.encode() if self.xd is not None else None
+        r.xr = self.xr.encode() if self.xr is not None else None
+        r.has_xv, r.xv = int(self.xv is not None), self.xv or 0
+        r.has_xw, r.xw = int(self.xw is not None), self.xw or 0
+        return r
+
+
+class Caller:
+    def __init__(self, cfg=None, chr_name="chr1", seq="", intervals=None):
+        self.L = lib()
+        cfg = cfg or default_config()
+        self.cfg = cfg
+        seqb = seq.encode() if isinstance(seq, str) else bytes(seq)
+        if intervals is None:
+            h = self.L.po_caller_create(C.byref(cfg), chr_name.encode(), seqb, len(seqb), None, None, -1)
+        else:
+            s = (C.c_int32 * max(1, len(intervals)))(*[a for a, _ in intervals])
+            e = (C.c_int32 * max(1, len(intervals)))(*[b for _, b in intervals])
+            h = self.L.po_caller_create(C.byref(cfg), chr_name.encode(), seqb, len(seqb), s, e, len(intervals))
+        if not h:
+            raise RuntimeError(self.L.po_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.po_caller_destroy(self.h)
+            self.h = None
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.po_last_error().decode())
+
+    def add_read(self, r, mode="full"):
+        st = r.to_struct()
+        f = {"full": self.L.po_caller_add_read, "counts": self.L.po_caller_add_read_counts_only,
+             "candidates": self.L.po_caller_add_read_candidates_only}[mode]
+        self._chk(f(self.h, C.byref(st)))
+
+    def add_forced(self, pos, ref, alt):
+        self.L.po_caller_add_forced(self.h, pos, ref.encode(), alt.encode())
+
+    def finish(self):
+        self._chk(self.L.po_caller_finish(self.h))
+
+    def records(self):
+        out = []
+        for i in range(self.L.po_caller_num_records(self.h)):
+            r = Record()
+            self._chk(self.L.po_caller_get_record(self.h, i, C.byref(r)))
+            r.ref = self.L.po_caller_record_ref(self.h, i).decode()
+            r.alt = self.L.po_caller_record_alt(self.h, i).decode()
+            out.append(r)
+        return out
+
+    def write_batches(self):
+        out = []
+        b, e = C.c_int32(), C.c_int32()
+        for i in range(self.L.po_caller_num_write_batches(self.h)):
+            self.L.po_caller_write_batch(self.h, i, C.byref(b), C.byref(e))
+            out.append((b.value, e.value))
+        return out
+
+    def count(self, pos, allele, direction, min_anchor=0, max_anchor=None, from_end=False, symmetric=False):
+        return self.L.po_get_allele_count(self.h, pos, allele, direction, min_anchor, -1 if max_anchor is None else max_anchor, int(from_end), int(symmetric))
+
+    def qsum(self, pos, allele, direction, min_anchor=0, max_anchor=None, from_end=False):
+        return self.L.po_get_sum_base_quality(self.h, pos, allele, direction, min_anchor, -1 if max_anchor is None else max_anchor, int(from_end))
+
+    def collapsed_count(self, pos, t):
+        return self.L.po_get_collapsed_count(self.h, pos, t)
+
+    def set_count(self, pos, allele, direction, anchor, value):
+        self.L.po_set_allele_count(self.h, pos, allele, direction, anchor, value)
+
+    def add_gapped_ref_count(self, pos, count):
+        self.L.po_add_gapped_ref_count(self.h, pos, count)
+
+    def dump_counts(self, pos0, n):
+        import numpy as np
+        na = 2 * self.cfg.tracked_anchor_size + 1
+        out = np.zeros((n, 6, 3, na), dtype=np.int32)
+        self._chk(self.L.po_dump_counts(self.h, pos0, n, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def candidates_at(self, pos):
+        out = []
+        for i in range(self.L.po_num_candidates_at(self.h, pos)):
+            t, ol, orr = C.c_int32(), C.c_int32(), C.c_int32()
+            sup, wa, cm = (C.c_int32 * 3)(), (C.c_int32 * 3)(), (C.c_int32 * 8)()
+            rb, ab = C.create_string_buffer(512), C.create_string_buffer(512)
+            self._chk(self.L.po_get_candidate_at(self.h, pos, i, C.byref(t), sup, wa, C.byref(ol), C.byref(orr), rb, ab, 512, cm))
+            out.append(dict(type=t.value, pos=pos, ref=rb.value.decode(), alt=ab.value.decode(), support=list(sup), well_anchored=list(wa),
+                            open_left=bool(ol.value), open_right=bool(orr.value), collapsed_mut=list(cm)))
+        return out
+
+    def process_allele(self, type_, pos, ref, alt, support=(0, 0, 0), well_anchored=(0, 0, 0), coverage_only=False):
+        r = Record()
+        s = (C.c_int32 * 3)(*support)
+        w = (C.c_int32 * 3)(*well_anchored)
+        self._chk(self.L.po_process_allele(self.h, type_, pos, ref.encode(), alt.encode(), s, w, int(coverage_only), C.byref(r)))
+        return r
+
+
+def strand_bias(cov, sup, q_noise, min_vf=0.01, acceptance=0.5, model=1):
+    out = (C.c_double * 29)()
+    lib().po_strand_bias((C.c_int32 * 3)(*cov), (C.c_int32 * 3)(*sup), q_noise, min_vf, acceptance, model, out)
+    names = ["overall", "fwd", "rev", "stitched"]
+    res = dict(bias=out[0], gatk=out[1], acceptable=bool(out[2]), var_both=bool(out[3]), cov_both=bool(out[4]))
+    for i, n in enumerate(names):
+        o = out[5 + 6 * i: 11 + 6 * i]
+        res[n] = dict(fn=o[0], fp=o[1], vg=o[2], coverage=o[3], frequency=o[4], support=o[5])
+    return res
