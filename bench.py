@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — candidate loci scored per second on synthetic pileups of the BASELINE.json shape.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--loci L] [--depth D] [--gvcf 0|1]
+
+A step = one pass of the hot path (pileup count + score + record compaction) over one batch of `loci` synthetic pileup columns per GPU.
+Default workload = BASELINE.json configs[1]: 1 M loci x depth ~Poisson(500), SNV (1 % of loci) + deletion entries, flat Poisson noise model
+NL 20, gVCF off, one B200. N>1 (torchrun): loci are sharded by interval across ranks (weak scaling: `loci` per GPU), no data-path
+collective; each step ends with the single all-gather of the per-rank call records (NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "candidate loci scored/sec"
+UNIT = "loci/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--loci", type=int, default=1_000_000, help="loci per GPU")
+    ap.add_argument("--depth", type=int, default=500)
+    ap.add_argument("--depth-dist", default="poisson", choices=["poisson", "fixed"])
+    ap.add_argument("--gvcf", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--cpu-sample-loci", type=int, default=200_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def workload_name(a):
+    return (f"synthetic {a.loci} loci x depth {'~Poisson' if a.depth_dist == 'poisson' else '='}({a.depth}) per GPU, SNV 1% + deletion entries, "
+            f"Poisson noise model NL20, gvcf={a.gvcf} (BASELINE.json configs[1] shape)")
+
+
+def oracle_config(a):
+    from oracle import binding as ob
+    return ob.default_config(output_gvcf=a.gvcf, collapse=1)
+
+
+def run_oracle_slices(a, d, n_threads, loci_per_thread):
+    """Times the CPU restatement (count + call, no I/O) on n_threads disjoint slices, one thread each. Returns (seconds, loci)."""
+    import numpy as np
+    from oracle import binding as ob
+    off = d["offsets"].cpu().numpy()
+    slices = []
+    for t in range(n_threads):
+        l0, l1 = t * loci_per_thread, (t + 1) * loci_per_thread
+        e0, e1 = int(off[l0]), int(off[l1])
+        ref = bytes(d["ref_bases"][l0:l1].cpu().numpy()).decode()
+        slices.append((ob.Caller(oracle_config(a), "chr1", ref), (off[l0:l1 + 1] - e0).astype(np.int64), d["code"][e0:e1].cpu().numpy(),
+                       d["qual"][e0:e1].cpu().numpy(), d["anchor"][e0:e1].cpu().numpy()))
+
+    def work(s):
+        c, o, co, q, an = s
+        c.add_pileup(o, co, q, an, 1, call_every=1)
+        c.finish()
+    ths = [threading.Thread(target=work, args=(s,)) for s in slices]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    return time.perf_counter() - t0, n_threads * loci_per_thread
+
+
+def main_reference(a):
+    """Reference arm: the reference's CPU implementation of the path. The C# cannot run here (no dotnet runtime in the image), so this is
+    the oracle port (oracle/) on all host threads, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from pisces_b200 import synth
+    cores = os.cpu_count() or 1
+    per_thread = max(1000, min(20_000, a.loci // cores))
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    d = synth.make_pileup(cores * per_thread, a.depth, seed=a.seed, device=dev, depth_dist=a.depth_dist)
+    d = {k: (v.cpu() if hasattr(v, "cpu") else v) for k, v in d.items()}
+    times = []
+    for i in range(a.warmup + a.steps):
+        dt, loci = run_oracle_slices(a, d, cores, per_thread)
+        if i >= a.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = a.steps * cores * per_thread / total
+    sample = f"{cores} threads x {per_thread} loci per step ({cores * per_thread} loci, depth {a.depth}) of the same synthetic workload"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "oracle port of the C# path (dotnet runtime absent); count+call only, no I/O"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main_ours(a):
+    import torch
+    import torch.distributed as dist
+    import pisces_b200 as pb
+    from pisces_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; pisces_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = f"cuda:{local}"
+
+    # ---- synthetic shard for this rank, resident in HBM (interval shard `rank` of `world`)
+    d = synth.make_pileup(a.loci, a.depth, seed=a.seed + 1000 * rank, device=dev, depth_dist=a.depth_dist)
+    n_entries = d["n_entries"]
+    ref = bytes(d["ref_bases"].cpu().numpy())
+    cfg = pb.make_config(device=local, output_gvcf=a.gvcf)
+    sm = pb.GpuStateManager(cfg, "chr1", ref)
+    sm.AddPileup(d["offsets"], d["code"], d["qual"], d["anchor"], first_position=1, ref_bases=d["ref_bases"], device=True)
+    torch.cuda.synchronize()
+
+    import ctypes as C
+    from pisces_b200 import _native as N
+
+    class DevBuf:   # torch view of a device buffer owned by the library
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    cap_records = 1 << 16
+    gather_in = torch.zeros(cap_records * 96 + 8, dtype=torch.uint8, device=dev)
+    gather_out = torch.zeros(world * (cap_records * 96 + 8), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step():
+        n = sm.call_resident()
+        if world > 1:   # the single all-gather of per-interval call records (variant stream; the dense gVCF stream stays sharded)
+            vr, nv = C.c_void_p(), C.c_int64()
+            sm._chk(sm._L.pb2_resident_results(sm._h, None, None, None, C.byref(vr), C.byref(nv)))
+            k = min(nv.value, cap_records)
+            if k:
+                gather_in[8:8 + k * 96].copy_(torch.as_tensor(DevBuf(vr.value, k * 96), device=dev))
+            gather_in[:8].copy_(torch.tensor([k], dtype=torch.int64, device=dev).view(torch.uint8))
+            dist.all_gather_into_tensor(gather_out, gather_in)
+        return n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        n_records = step()
+    sm.stats()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        n_records = step()
+    barrier()
+    dt = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    st = sm.stats()
+    tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax.item())
+    value = world * a.loci * a.steps / dt
+
+    # ---- roofline of the dominant (only) kernel: algorithmic bytes / CUDA-event duration on the launching stream
+    n_ref_records = a.loci if a.gvcf else 0
+    algo_bytes = synth.algorithmic_bytes(a.loci, n_entries, n_records + n_ref_records)
+    hot_ms = st["hot_ms"] / max(1, st["hot_launches"])
+    achieved = algo_bytes / (hot_ms * 1e-3) / 1e9
+    peak, peak_src = 6650.0, "fallback"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_src = "measured"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": 1e3 * dt / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "loci_per_gpu": a.loci, "entries_per_gpu": n_entries, "records_per_step": n_records + n_ref_records,
+                       "l2": "inputs (%.2f GB per GPU) larger than L2, no flush needed" % (3 * n_entries / 1e9), "parallelism": f"interval-sharded x{world}"},
+            "gpu_launches": st["total_launches"],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "pileup_count_score_kernel", "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": hot_ms},
+            "clocks": sampler.summary()}
+
+    # ---- end to end through the C ABI with HOST buffers: pinned H2D of the step's pileup, tile staging, call, D2H of the records
+    if not a.no_e2e:
+        h = {k: d[k].cpu().pin_memory() for k in ("offsets", "code", "qual", "anchor", "ref_bases")}
+        sm2 = pb.GpuStateManager(cfg, "chr1", ref)
+        caller = pb.GpuAlleleCaller()
+        e2e_steps = max(2, min(a.steps, 4))
+
+        def e2e_step():
+            sm2.AddPileup(h["offsets"].numpy(), h["code"].numpy(), h["qual"].numpy(), h["anchor"].numpy(), first_position=1, ref_bases=h["ref_bases"].numpy())
+            recs = caller.Call(sm2, raw=True)
+            sm2.DoneProcessing()
+            return len(recs)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            nrec = e2e_step()
+        barrier()
+        edt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(edt, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": world * a.loci * e2e_steps / float(edt.item()), "unit": UNIT, "h2d_bytes_per_step": 3 * n_entries + 8 * (a.loci + 1) + a.loci,
+                       "d2h_bytes_per_step": 96 * nrec, "steps": e2e_steps}
+        sm2.close()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample, single thread like one Pisces (BAM x chr) job
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        s_loci = min(a.cpu_sample_loci, a.loci)
+        dd = {k: (v[: int(d["offsets"][s_loci]) if k in ("code", "qual", "anchor") else s_loci + 1 if k == "offsets" else s_loci].cpu() if hasattr(v, "cpu") else v)
+              for k, v in d.items()}
+        cdt, cl = run_oracle_slices(a, dd, 1, s_loci)
+        line["cpu_baseline"] = {"value": cl / cdt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"first {s_loci} loci of the same workload, single thread (count + call, no I/O)"}
+    sm.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)

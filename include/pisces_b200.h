@@ -1,0 +1,183 @@
+/* pisces_b200 — C ABI of the B200-native per-locus variant-calling hot path.
+ *
+ * Drop-in boundary for Illumina/Pisces (reference @ becd35f). A .NET host P/Invokes these entry points
+ * (CallingConvention.Cdecl, the same convention as the reference's only native binding,
+ * src/lib/Common.IO/FileCompression.cs:10-35) from implementations of the reference's own seams:
+ *
+ *   IStateManager.AddAlleleCounts(Read)            src/lib/Pisces.Processing/Interfaces/IStateManager.cs:8-15     -> pb2_push_reads
+ *   IStateManager.AddCandidates(candidates)        src/lib/Pisces.Domain/Interfaces/IAlleleSource.cs:10            -> pb2_push_candidates
+ *   IStateManager.GetCandidatesToProcess/DoneProcessing + IAlleleCaller.Call(batch, source)
+ *                                                  src/exe/Pisces/Interfaces/IAlleleCaller.cs:8-13                 -> pb2_flush
+ *   IAlleleSource.GetAlleleCount(pos, allele, dir, ...)   IAlleleSource.cs:12                                      -> pb2_get_counts
+ *   Factory.CreateStateManager / CreateVariantCaller      src/exe/Pisces/Logic/Factory.cs:128,209                  -> pb2_create (+ pb2_config)
+ *   ChrReference / ChrIntervalSet handed to the caller    Factory.cs:253-269                                       -> pb2_set_reference / pb2_set_intervals
+ *
+ * Conventions: every call returns 0 on success, <0 on error (message: pb2_last_error); nothing throws across the
+ * boundary. The caller owns all input buffers (they are consumed before the call returns). Output buffers belong to the
+ * handle and stay valid until the next pb2_flush / pb2_destroy on it. One handle per (BAM, chromosome) job, one CUDA stream per
+ * handle, no global mutable state: N concurrent handles are safe. There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with PB2_ERR_CUDA.
+ *
+ * Enum values are the reference's: AlleleType A=0,G=1,C=2,T=3,N=4,Deletion=5 (Types/AlleleType.cs:5-10);
+ * DirectionType Forward=0,Reverse=1,Stitched=2; AlleleCategory Snv=0,Insertion=1,Deletion=2,Mnv=3,Reference=4;
+ * FilterType / Genotype ordinals as in Types/FilterType.cs, Types/Genotype.cs.
+ */
+#ifndef PISCES_B200_H
+#define PISCES_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_OK 0
+#define PB2_ERR_ARG (-1)
+#define PB2_ERR_CUDA (-2)
+#define PB2_ERR_STATE (-3)
+#define PB2_ERR_NOMEM (-4)
+#define PB2_ERR_UNSUPPORTED (-5)
+
+typedef struct pb2_handle pb2_handle;
+
+/* The complete parameter set of the path: VariantCallerConfig (src/exe/Pisces/Logic/VariantCalling/AlleleCaller.cs:266-291, filled at
+ * Factory.cs:149-179) + the ctor arguments of RegionStateManager (RegionStateManager.cs:36-53) and CandidateVariantFinder
+ * (CandidateVariantFinder.cs:20-29). Nullable C# options use -1 for null. Defaults: pb2_default_config. */
+typedef struct pb2_config {
+    int32_t device;                      /* CUDA device ordinal */
+    int32_t min_base_call_quality;       /* BamFilterParameters.MinimumBaseCallQuality (20) */
+    float   min_frequency;               /* VariantCallingParameters.MinimumFrequency (0.01) */
+    float   min_frequency_filter;        /* MinimumFrequencyFilter (-1 -> raised to min_frequency) */
+    float   target_lod_frequency;        /* TargetLODFrequency (-1 -> raised to min_frequency_filter) */
+    int32_t max_variant_qscore;          /* 100 */
+    int32_t min_variant_qscore;          /* 20 */
+    int32_t variant_qscore_filter;       /* MinimumVariantQScoreFilter 30 */
+    int32_t max_genotype_qscore;         /* 100 */
+    int32_t min_genotype_qscore;         /* 0 */
+    int32_t low_genotype_quality_filter; /* null */
+    int32_t min_coverage;                /* 10 */
+    int32_t low_depth_filter;            /* null -> min_coverage */
+    int32_t rmxn_max_repeat_len;         /* 5 */
+    int32_t rmxn_min_repetitions;        /* 9 */
+    float   rmxn_frequency_limit;        /* 0.35 */
+    int32_t forced_noise_level;          /* -1 -> noise level = min_base_call_quality (VariantCallingParameters.cs:109-118) */
+    int32_t noise_model;                 /* 0 Flat, 1 Window */
+    float   strand_bias_acceptance;      /* 0.5 */
+    int32_t strand_bias_model;           /* 0 Poisson, 1 Extended (default); 2 Diploid -> PB2_ERR_UNSUPPORTED */
+    int32_t filter_single_strand;        /* FilterOutVariantsPresentOnlyOneStrand */
+    float   no_call_filter;              /* 0.6 */
+    int32_t ploidy;                      /* 0 Somatic; others -> PB2_ERR_UNSUPPORTED */
+    int32_t tracked_anchor_size;         /* TrackedAnchorSize 5 -> 11 anchor bins; only 5 is built */
+    int32_t output_gvcf;                 /* VcfWritingParameters.OutputGvcfFile (1) = IncludeReferenceCalls */
+    int32_t expect_stitched;             /* IAlleleSource.ExpectStitchedReads */
+    int32_t expect_collapsed;            /* CollapsedRegionStateManager in use */
+    int32_t want_sum_base_quality;       /* fill pb2_call_record.sum_base_quality (always on when noise_model == Window) */
+    int32_t collapse;                    /* PiscesApplicationOptions.Collapse (1): candidates are tracked per open-end state (trackOpenEnded) */
+    int32_t call_mnvs;                   /* CallMNVs (0); 1 -> PB2_ERR_UNSUPPORTED until the MNV path lands */
+    int32_t reserved[2];
+} pb2_config;
+
+/* Reads for IStateManager.AddAlleleCounts(Read) / ICandidateVariantFinder.FindCandidates(Read, ...), as a struct of arrays. Only
+ * reads that passed AlignmentSource.ShouldSkipRead (src/exe/Pisces/Logic/Alignment/AlignmentsSource.cs:84-92) are pushed; they must
+ * arrive in position order like the BAM. Bases are upper-case ASCII (BamReader.cs:185-201). */
+typedef struct pb2_read_batch {
+    int32_t n_reads;
+    const int32_t*  pos0;        /* [n] BamAlignment.Position (0-based) */
+    const uint16_t* flag;        /* [n] SAM flag (0x10 reverse, 0x2 proper pair, 0x40 first mate) */
+    const int64_t*  cigar_off;   /* [n+1] into cigar */
+    const uint32_t* cigar;       /* BAM encoding len<<4|op, ops MIDNSHP=X */
+    const int64_t*  seq_off;     /* [n+1] into bases / quals / base_dirs */
+    const uint8_t*  bases;
+    const uint8_t*  quals;
+    const uint8_t*  base_dirs;   /* optional: Read.SequencedBaseDirectionMap per base (XD tag projected, Read.cs:390-421,664-682); NULL -> from flag 0x10 */
+    const uint8_t*  collapsed;   /* optional [n]: bit0 IsCollapsedRead (XV/XW present), bit1 IsDuplex, bits2-3 ReadPairDirection 1=FR 2=RF 0=other (Read.cs:17-71,311-349) */
+} pb2_read_batch;
+
+/* Locus-major pileup ("pileup columns") in CSR form: locus i covers reference position first_position + i (or positions[i]),
+ * its entries are [offsets[i], offsets[i+1]) in the three byte planes. One entry = one call to RegionState.AddAlleleCount
+ * (RegionStateManager.cs:155,174,183,206) before minimum-base-quality is applied:
+ *   code  : bits 0-2 AlleleType of the read base (Deletion for gap entries), bits 3-4 DirectionType,
+ *           bit 5 PB2_ENTRY_OPEN_LEFT, bit 6 PB2_ENTRY_OPEN_RIGHT (CandidateAllele.OpenOnLeft/Right of the SNV this base would
+ *           raise, CandidateVariantFinder.cs:112-117,496-553), bit 7 PB2_ENTRY_NO_CANDIDATE (base sits in an '='/'X' op or
+ *           outside the chromosome: counted, but never an SNV candidate, CandidateVariantFinder.cs:46-64,102-103)
+ *   qual  : base-call quality byte (for Deletion entries: min of the two flanking qualities, CandidateVariantFinder.cs:294-320)
+ *   anchor: bits 0-3 anchor bin 0..10 (RegionStateManager.GetAnchorType :83-116), bits 4-7 ReadCollapsedType+1 (0 = none). */
+#define PB2_ENTRY_OPEN_LEFT 0x20
+#define PB2_ENTRY_OPEN_RIGHT 0x40
+#define PB2_ENTRY_NO_CANDIDATE 0x80
+typedef struct pb2_pileup_csr {
+    int64_t n_loci;
+    int32_t first_position;      /* 1-based; used when positions == NULL */
+    const int32_t* positions;    /* optional [n_loci], strictly increasing */
+    const int64_t* offsets;      /* [n_loci + 1] */
+    const uint8_t* code;         /* [offsets[n_loci]] */
+    const uint8_t* qual;
+    const uint8_t* anchor;
+    const uint8_t* ref_bases;    /* optional [n_loci] ASCII; NULL -> taken from pb2_set_reference */
+} pb2_pileup_csr;
+
+/* One called allele: the POD image of CalledAllele (src/lib/Pisces.Domain/Models/Alleles/CalledAllele.cs:7-140). 96 bytes. */
+typedef struct pb2_call_record {
+    int32_t  position;                 /* ReferencePosition, 1-based */
+    uint8_t  type;                     /* AlleleCategory */
+    uint8_t  genotype;                 /* Genotype */
+    uint8_t  sb_flags;                 /* bit0 BiasAcceptable, bit1 VarPresentOnBothStrands, bit2 CovPresentOnBothStrands, bit3 IsForcedToReport */
+    uint8_t  open_flags;               /* bit0 OpenOnLeft, bit1 OpenOnRight of the source candidate (diagnostic) */
+    uint16_t filters;                  /* bit i = FilterType i */
+    uint16_t noise_level;              /* NoiseLevelApplied */
+    int32_t  variant_qscore;
+    int32_t  genotype_qscore;
+    int32_t  total_coverage;
+    int32_t  coverage_by_direction[3]; /* EstimatedCoverageByDirection */
+    int32_t  support_by_direction[3];
+    int32_t  allele_support;
+    int32_t  reference_support;
+    int32_t  num_no_calls;
+    float    fraction_no_calls;
+    uint32_t allele_bytes;             /* ref_len + alt_len <= 4: the ASCII bases inline (ref then alt, little-endian); else offset into the flush arena */
+    uint16_t ref_len, alt_len;
+    double   sum_base_quality;
+    double   bias_score;               /* StrandBiasResults.BiasScore */
+    double   gatk_bias_score;          /* StrandBiasResults.GATKBiasScore */
+} pb2_call_record;
+
+void pb2_default_config(pb2_config* cfg);
+int pb2_create(const pb2_config* cfg, pb2_handle** out);
+void pb2_destroy(pb2_handle* h);
+const char* pb2_last_error(pb2_handle* h);      /* h may be NULL: last error of a failed pb2_create on this thread */
+int pb2_device_count(void);
+
+int pb2_set_reference(pb2_handle* h, const char* chr_name, const uint8_t* seq, int64_t len);
+int pb2_set_intervals(pb2_handle* h, const int32_t* start, const int32_t* end, int32_t n);
+
+/* Stage a locus-major pileup. Host pointers: copied through pinned staging with cudaMemcpyAsync. */
+int pb2_push_pileup(pb2_handle* h, const pb2_pileup_csr* p);
+/* Same, but every pointer in *p is a device pointer (data already resident in HBM). */
+int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p);
+
+/* IStateManager.AddAlleleCounts + FindCandidates for a batch of reads: the reads are kept by the handle until a pb2_flush clears the
+ * positions they cover; the pileup is built on the device (read expansion, bucketing to loci, tile interleave). */
+int pb2_push_reads(pb2_handle* h, const pb2_read_batch* batch);
+
+/* Count + score everything staged; records stay on the device (bench / multi-GPU gather use this). */
+int pb2_call_resident(pb2_handle* h, int64_t* n_records);
+/* Device pointers to the results of the last pb2_call_resident: the dense per-locus reference stream (gVCF), its validity bytes,
+ * and the compacted variant stream. Any may be NULL. */
+int pb2_resident_results(pb2_handle* h, const pb2_call_record** ref_records, const uint8_t** ref_valid, int64_t* n_loci,
+                         const pb2_call_record** variant_records, int64_t* n_variants);
+/* IAlleleCaller.Call for everything staged up to up_to_position (-1 = all): runs pb2_call_resident if needed, copies the
+ * records to the host ordered by (position, ref, alt) as AlleleCaller.cs:96-140,172-176 orders them. */
+int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n);
+/* Parity hook = IAlleleSource.GetAlleleCount over a position range: out[n][6][3][11] int32 (RegionState._alleleCounts). */
+int pb2_get_counts(pb2_handle* h, int32_t position0, int32_t n, int32_t* out);
+/* Drop staged pileups and results (IStateManager.DoneProcessing). */
+int pb2_reset(pb2_handle* h);
+
+/* Timing/diagnostics for bench.py: kernel launches and device milliseconds of the hot kernel since the last call, measured with
+ * CUDA events on the handle's stream. */
+int pb2_stats(pb2_handle* h, int64_t* hot_kernel_launches, double* hot_kernel_ms, int64_t* total_kernel_launches);
+/* The handle's cudaStream_t (as void*) so the host can order its own work against it. */
+void* pb2_stream(pb2_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -71,6 +71,7 @@ def lib():
         L.po_caller_add_forced.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p]
         for f in ("po_caller_add_read", "po_caller_add_read_counts_only", "po_caller_add_read_candidates_only"):
             getattr(L, f).argtypes = [C.c_void_p, C.POINTER(ReadStruct)]
+        L.po_caller_add_pileup.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.po_caller_finish.argtypes = [C.c_void_p]
         L.po_caller_num_records.argtypes = [C.c_void_p]
         L.po_caller_get_record.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Record)]
@@ -191,6 +192,23 @@ class Caller:
         f = {"full": self.L.po_caller_add_read, "counts": self.L.po_caller_add_read_counts_only,
              "candidates": self.L.po_caller_add_read_candidates_only}[mode]
         self._chk(f(self.h, C.byref(st)))
+
+    def add_pileup(self, offsets, code, qual, anchor, first_position=1, call_every=1):
+        """Locus-major entries (pb2_pileup_csr semantics) through the reference's per-base operations."""
+        import numpy as np
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        code, qual, anchor = (np.ascontiguousarray(x, dtype=np.uint8) for x in (code, qual, anchor))
+        self._chk(self.L.po_caller_add_pileup(self.h, len(offsets) - 1, first_position, offsets.ctypes.data, code.ctypes.data, qual.ctypes.data,
+                                              anchor.ctypes.data, call_every))
+
+    def records_array(self):
+        """All records as a numpy structured array (fast path for large outputs)."""
+        import numpy as np
+        n = self.L.po_caller_num_records(self.h)
+        arr = (Record * n)()
+        for i in range(n):
+            self._chk(self.L.po_caller_get_record(self.h, i, C.byref(arr[i])))
+        return np.ctypeslib.as_array(arr) if n else np.zeros(0)
 
     def add_forced(self, pos, ref, alt):
         self.L.po_caller_add_forced(self.h, pos, ref.encode(), alt.encode())

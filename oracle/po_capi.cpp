@@ -81,6 +81,48 @@ int po_caller_add_read_candidates_only(void* h, const po_read* r) {
     auto* s = (SmallVariantCaller*)h;
     GUARD(s->state->AddCandidates(s->finder->FindCandidates(ToRead(r), s->chrSeq, s->chrName)))
 }
+// Locus-major pileup entries (the staging format of include/pisces_b200.h, pb2_pileup_csr) pushed through the SAME per-base operations
+// the reference performs in RegionStateManager.AddAlleleCounts (:161-192) and CandidateVariantFinder (SNV candidates, CallMNVs=false),
+// followed by Call(upTo) as positions clear. Used for parity of the locus-major path and as the CPU baseline of bench.py.
+int po_caller_add_pileup(void* h, int64_t n_loci, int32_t first_pos, const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int32_t call_every) {
+    auto* s = (SmallVariantCaller*)h;
+    try {
+        auto& st = *s->state;
+        const int minBQ = s->cfg.MinimumBaseCallQuality;
+        for (int64_t i = 0; i < n_loci; i++) {
+            const int p = first_pos + (int)i;
+            const char refc = (p >= 1 && p <= (int)s->chrSeq.size()) ? s->chrSeq[(size_t)p - 1] : 'N';
+            const AlleleType refA = GetAlleleType(refc);
+            std::vector<CandPtr> cands;
+            for (int64_t e = off[i]; e < off[i + 1]; e++) {
+                const int allele = code[e] & 7, dir = (code[e] >> 3) & 3, q = qual[e], anchor = anch[e] & 15, ct = anch[e] >> 4;
+                if (allele == AT_Del) {
+                    if (q >= minBQ) {
+                        st.GetBlock(p)->AddAlleleCount(p, AT_Del, (DirectionType)dir, anchor);
+                        if (ct && st.expectCollapsed) st.GetBlock(p)->AddCollapsedReadCount(p, (ReadCollapsedType)(ct - 1));
+                    }
+                    continue;
+                }
+                AlleleType a2 = q < minBQ ? AT_N : (AlleleType)allele;
+                st.GetBlock(p)->AddAlleleCount(p, a2, (DirectionType)dir, anchor);
+                if (a2 != AT_N && ct && st.expectCollapsed) st.GetBlock(p)->AddCollapsedReadCount(p, (ReadCollapsedType)(ct - 1));
+                float expo = (float)(-1 * q) / 10.0f;
+                st.GetBlock(p)->AddBaseQualites(p, a2, (DirectionType)dir, std::pow(10.0, (double)expo), anchor);
+                if (a2 != AT_N && !(code[e] & 0x80) && refA != AT_N && a2 != refA) {
+                    static const char b[4] = {'A', 'G', 'C', 'T'};
+                    auto c = std::make_shared<CandidateAllele>(s->chrName, p, std::string(1, refc), std::string(1, b[a2]), Snv);
+                    c->SupportByDirection[dir] = 1;
+                    c->OpenOnLeft = (code[e] & 0x20) != 0;
+                    c->OpenOnRight = (code[e] & 0x40) != 0;
+                    cands.push_back(c);
+                }
+            }
+            st.AddCandidates(cands);
+            if (call_every > 0 && (i % call_every) == (call_every - 1)) s->Call(p);
+        }
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 int po_caller_finish(void* h) { GUARD(((SmallVariantCaller*)h)->Finish()) }
 int32_t po_caller_num_records(void* h) { return (int32_t)((SmallVariantCaller*)h)->output.size(); }
 

@@ -62,6 +62,7 @@ void po_caller_add_forced(void* h, int32_t pos, const char* ref, const char* alt
 int po_caller_add_read(void* h, const po_read* r);           /* find candidates + counts + call(upTo) */
 int po_caller_add_read_counts_only(void* h, const po_read* r); /* RegionStateManager.AddAlleleCounts only */
 int po_caller_add_read_candidates_only(void* h, const po_read* r); /* FindCandidates + AddCandidates only */
+int po_caller_add_pileup(void* h, int64_t n_loci, int32_t first_pos, const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int32_t call_every);
 int po_caller_finish(void* h);
 int32_t po_caller_num_records(void* h);
 int po_caller_get_record(void* h, int32_t i, po_record* out);

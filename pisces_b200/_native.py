@@ -1,0 +1,88 @@
+"""ctypes binding of libpisces_b200.so (C ABI in include/pisces_b200.h). Fails loudly if the library is missing: there is no
+Python or CPU implementation of the path behind it."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpisces_b200.so")
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("min_base_call_quality", C.c_int32), ("min_frequency", C.c_float), ("min_frequency_filter", C.c_float),
+        ("target_lod_frequency", C.c_float), ("max_variant_qscore", C.c_int32), ("min_variant_qscore", C.c_int32),
+        ("variant_qscore_filter", C.c_int32), ("max_genotype_qscore", C.c_int32), ("min_genotype_qscore", C.c_int32),
+        ("low_genotype_quality_filter", C.c_int32), ("min_coverage", C.c_int32), ("low_depth_filter", C.c_int32),
+        ("rmxn_max_repeat_len", C.c_int32), ("rmxn_min_repetitions", C.c_int32), ("rmxn_frequency_limit", C.c_float),
+        ("forced_noise_level", C.c_int32), ("noise_model", C.c_int32), ("strand_bias_acceptance", C.c_float),
+        ("strand_bias_model", C.c_int32), ("filter_single_strand", C.c_int32), ("no_call_filter", C.c_float), ("ploidy", C.c_int32),
+        ("tracked_anchor_size", C.c_int32), ("output_gvcf", C.c_int32), ("expect_stitched", C.c_int32), ("expect_collapsed", C.c_int32),
+        ("want_sum_base_quality", C.c_int32), ("collapse", C.c_int32), ("call_mnvs", C.c_int32), ("reserved", C.c_int32 * 2)]
+
+
+class PileupCsr(C.Structure):
+    _fields_ = [("n_loci", C.c_int64), ("first_position", C.c_int32), ("positions", C.c_void_p), ("offsets", C.c_void_p),
+                ("code", C.c_void_p), ("qual", C.c_void_p), ("anchor", C.c_void_p), ("ref_bases", C.c_void_p)]
+
+
+class ReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("pos0", C.c_void_p), ("flag", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p),
+                ("seq_off", C.c_void_p), ("bases", C.c_void_p), ("quals", C.c_void_p), ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p)]
+
+
+class CallRecord(C.Structure):
+    _fields_ = [("position", C.c_int32), ("type", C.c_uint8), ("genotype", C.c_uint8), ("sb_flags", C.c_uint8), ("open_flags", C.c_uint8),
+                ("filters", C.c_uint16), ("noise_level", C.c_uint16), ("variant_qscore", C.c_int32), ("genotype_qscore", C.c_int32),
+                ("total_coverage", C.c_int32), ("coverage_by_direction", C.c_int32 * 3), ("support_by_direction", C.c_int32 * 3),
+                ("allele_support", C.c_int32), ("reference_support", C.c_int32), ("num_no_calls", C.c_int32),
+                ("fraction_no_calls", C.c_float), ("allele_bytes", C.c_uint32), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16),
+                ("sum_base_quality", C.c_double), ("bias_score", C.c_double), ("gatk_bias_score", C.c_double)]
+
+
+assert C.sizeof(CallRecord) == 96
+
+# numpy view of pb2_call_record
+RECORD_DTYPE = [("position", "<i4"), ("type", "u1"), ("genotype", "u1"), ("sb_flags", "u1"), ("open_flags", "u1"), ("filters", "<u2"),
+                ("noise_level", "<u2"), ("variant_qscore", "<i4"), ("genotype_qscore", "<i4"), ("total_coverage", "<i4"),
+                ("coverage_by_direction", "<i4", (3,)), ("support_by_direction", "<i4", (3,)), ("allele_support", "<i4"),
+                ("reference_support", "<i4"), ("num_no_calls", "<i4"), ("fraction_no_calls", "<f4"), ("allele_bytes", "<u4"),
+                ("ref_len", "<u2"), ("alt_len", "<u2"), ("sum_base_quality", "<f8"), ("bias_score", "<f8"), ("gatk_bias_score", "<f8")]
+
+EXPORTS = ["pb2_default_config", "pb2_create", "pb2_destroy", "pb2_last_error", "pb2_device_count", "pb2_set_reference", "pb2_set_intervals",
+           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_call_resident", "pb2_resident_results", "pb2_flush",
+           "pb2_get_counts", "pb2_reset", "pb2_stats", "pb2_stream"]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C pisces_b200/csrc). pisces_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    L.pb2_default_config.argtypes = [C.POINTER(Config)]
+    L.pb2_default_config.restype = None
+    L.pb2_create.argtypes = [C.POINTER(Config), C.POINTER(H)]
+    L.pb2_destroy.argtypes = [H]
+    L.pb2_destroy.restype = None
+    L.pb2_last_error.argtypes = [H]
+    L.pb2_last_error.restype = C.c_char_p
+    L.pb2_set_reference.argtypes = [H, C.c_char_p, C.c_char_p, C.c_int64]
+    L.pb2_set_intervals.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int32]
+    L.pb2_push_pileup.argtypes = [H, C.POINTER(PileupCsr)]
+    L.pb2_push_pileup_device.argtypes = [H, C.POINTER(PileupCsr)]
+    L.pb2_push_reads.argtypes = [H, C.POINTER(ReadBatch)]
+    L.pb2_call_resident.argtypes = [H, C.POINTER(C.c_int64)]
+    L.pb2_resident_results.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.pb2_flush.argtypes = [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.pb2_get_counts.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
+    L.pb2_reset.argtypes = [H]
+    L.pb2_stats.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.pb2_stream.argtypes = [H]
+    L.pb2_stream.restype = C.c_void_p
+    _lib = L
+    return L

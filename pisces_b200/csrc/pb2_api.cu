@@ -1,0 +1,721 @@
+// C ABI of libpisces_b200.so (include/pisces_b200.h): handle, staging, launches. No CPU compute path exists here: every
+// entry point that produces counts or calls runs the CUDA kernels in pb2_kernels.cu and fails with PB2_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "pb2_kernels.cuh"
+#include "pb2_math.cuh"
+
+using namespace pb2;
+
+namespace pb2 {
+struct ReadsView {
+    int32_t n_reads;
+    const int32_t* pos0;
+    const uint16_t* flag;
+    const int64_t* cigar_off;
+    const uint32_t* cigar;
+    const int64_t* seq_off;
+    const uint8_t* bases;
+    const uint8_t* quals;
+    const uint8_t* base_dirs;
+    const uint8_t* collapsed;
+};
+struct RegionView {
+    int32_t lo, hi;
+    const int32_t* index_of_pos;
+    const uint8_t* chr;
+    int64_t chr_len;
+    int min_bq;
+    int expect_collapsed;
+};
+cudaError_t launch_reads_count(const ReadsView& rv, const RegionView& rg, unsigned int* depth, cudaStream_t st);
+cudaError_t launch_reads_emit(const ReadsView& rv, const RegionView& rg, const int64_t* offsets, unsigned int* cursor, uint8_t* code, uint8_t* qual, uint8_t* anch,
+                              cudaStream_t st);
+cudaError_t launch_depth_to_i64(const unsigned int* depth, int64_t* out, int64_t n, cudaStream_t st);
+}  // namespace pb2
+
+namespace {
+
+struct HostReads {   // reads staged by pb2_push_reads, kept until a flush clears the positions they cover
+    std::vector<int32_t> pos0, end_pos;
+    std::vector<uint16_t> flag;
+    std::vector<int64_t> cigar_off{0}, seq_off{0};
+    std::vector<uint32_t> cigar;
+    std::vector<uint8_t> bases, quals, base_dirs, collapsed;
+    bool has_dirs = false, has_collapsed = false;
+    size_t size() const { return pos0.size(); }
+    void clear() { *this = HostReads(); }
+};
+
+thread_local std::string g_create_error;
+
+struct Segment {   // one staged pileup (pb2_push_pileup*)
+    int64_t n_loci = 0;
+    int32_t n_tiles = 0;
+    int32_t first_position = 0;
+    bool has_positions = false;
+    int64_t plane_bytes = 0;
+    int64_t n_entries = 0;
+    // device
+    int32_t* depth = nullptr;
+    int64_t* tile_base = nullptr;
+    uint8_t *code = nullptr, *qual = nullptr, *anch = nullptr, *ref_base = nullptr;
+    int32_t* positions = nullptr;
+    pb2_call_record* ref_records = nullptr;
+    uint8_t* ref_valid = nullptr;
+    pb2_call_record* var_records = nullptr;
+    int64_t var_capacity = 0;
+    uint32_t* exc_entries = nullptr;
+    int64_t exc_capacity = 0;
+    unsigned long long* counters = nullptr;   // [0] var_count, [1] exc_count
+    // host copies needed for ordering / lookups
+    std::vector<int32_t> h_positions;
+    bool called = false;
+    bool temporary = false;   // built inside pb2_flush from staged reads; freed when the flush returns
+    unsigned long long h_var_count = 0, h_exc_count = 0;
+};
+
+}  // namespace
+
+struct pb2_handle {
+    pb2_config cfg;
+    DeviceConfig dcfg;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string error;
+    std::string chr_name;
+    uint8_t* d_chr = nullptr;
+    int64_t chr_len = 0;
+    std::vector<uint8_t> h_chr;
+    std::vector<int32_t> iv_start, iv_end;
+    bool have_intervals = false;
+    std::vector<Segment> segs;
+    HostReads reads;
+    int32_t cleared_through = 0;   // positions <= this were called by an earlier pb2_flush(up_to >= 0)
+    int* d_tile_counter = nullptr;
+    std::vector<pb2_call_record> h_out;
+    int64_t hot_launches = 0, total_launches = 0;
+    double hot_ms = 0;
+};
+
+#define CU(h, expr)                                                                                      \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            (h)->error = std::string(#expr) + ": " + cudaGetErrorString(_e);                             \
+            return PB2_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+static int fail(pb2_handle* h, int code, const std::string& msg) {
+    if (h) h->error = msg; else g_create_error = msg;
+    return code;
+}
+
+extern "C" void pb2_default_config(pb2_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->device = 0;
+    c->min_base_call_quality = 20;      // BamFilterParameters.cs:8
+    c->min_frequency = 0.01f;           // VariantCallingParameters.cs:59
+    c->min_frequency_filter = -1;
+    c->target_lod_frequency = -1;
+    c->max_variant_qscore = 100; c->min_variant_qscore = 20; c->variant_qscore_filter = 30;
+    c->max_genotype_qscore = 100; c->min_genotype_qscore = 0; c->low_genotype_quality_filter = -1;
+    c->min_coverage = 10; c->low_depth_filter = -1;
+    c->rmxn_max_repeat_len = 5; c->rmxn_min_repetitions = 9; c->rmxn_frequency_limit = 0.35f;
+    c->forced_noise_level = -1; c->noise_model = 0;
+    c->strand_bias_acceptance = 0.5f; c->strand_bias_model = 1; c->filter_single_strand = 0;
+    c->no_call_filter = 0.6f; c->ploidy = 0; c->tracked_anchor_size = 5; c->output_gvcf = 1;
+    c->expect_stitched = 0; c->expect_collapsed = 0; c->want_sum_base_quality = 0; c->collapse = 1; c->call_mnvs = 0;
+}
+
+extern "C" int pb2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* pb2_last_error(pb2_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+static void derive_config(pb2_handle* h) {
+    const pb2_config& c = h->cfg;
+    DeviceConfig& d = h->dcfg;
+    d.min_bq = c.min_base_call_quality;
+    d.noise_level = c.forced_noise_level == -1 ? c.min_base_call_quality : c.forced_noise_level;  // VariantCallingParameters.cs:109-118
+    d.noise_model = c.noise_model;
+    d.min_frequency = c.min_frequency;
+    d.min_frequency_filter = c.min_frequency_filter < c.min_frequency ? c.min_frequency : c.min_frequency_filter;  // Validate :144-147
+    d.target_lod = c.target_lod_frequency < d.min_frequency_filter ? d.min_frequency_filter : c.target_lod_frequency;  // :152-155
+    d.variant_freq_filter = d.min_frequency_filter > c.min_frequency ? d.min_frequency_filter : c.min_frequency;  // SomaticGenotyper.SetMinFreqFilter
+    d.max_vq = c.max_variant_qscore; d.min_vq = c.min_variant_qscore; d.vq_filter = c.variant_qscore_filter;
+    d.max_gq = c.max_genotype_qscore; d.min_gq = c.min_genotype_qscore; d.low_gq_filter = c.low_genotype_quality_filter;
+    d.min_coverage = c.min_coverage;
+    d.low_depth_filter = c.low_depth_filter < c.min_coverage ? c.min_coverage : c.low_depth_filter;  // :137-141
+    d.rmxn_max_len = c.rmxn_max_repeat_len; d.rmxn_min_reps = c.rmxn_min_repetitions; d.rmxn_freq_limit = c.rmxn_frequency_limit;
+    d.sb_acceptance = c.strand_bias_acceptance; d.sb_model = c.strand_bias_model; d.filter_single_strand = c.filter_single_strand;
+    d.no_call_filter = c.no_call_filter;
+    d.output_gvcf = c.output_gvcf; d.expect_stitched = c.expect_stitched; d.expect_collapsed = c.expect_collapsed;
+    d.have_intervals = h->have_intervals ? 1 : 0;
+    d.want_qsum = c.want_sum_base_quality;
+}
+
+extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
+    if (!cfg || !out) return fail(nullptr, PB2_ERR_ARG, "pb2_create: null argument");
+    *out = nullptr;
+    if (cfg->ploidy != 0) return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: only the Somatic ploidy model is built (SURVEY 8f rank 3)");
+    if (cfg->strand_bias_model == 2) return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: Diploid strand-bias model not built (SURVEY 8f rank 3)");
+    if (cfg->tracked_anchor_size != 5) return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: tracked_anchor_size must be 5");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PB2_ERR_CUDA, std::string("pb2_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    }
+    if (cfg->device < 0 || cfg->device >= n) return fail(nullptr, PB2_ERR_ARG, "pb2_create: bad device ordinal");
+    pb2_handle* h = new pb2_handle();
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    derive_config(h);
+    auto bail = [&](const char* what, cudaError_t err) { g_create_error = std::string(what) + ": " + cudaGetErrorString(err); delete h; return PB2_ERR_CUDA; };
+    if ((e = cudaSetDevice(h->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    h->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&h->d_tile_counter, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    *out = h;
+    return PB2_OK;
+}
+
+static void free_segment(pb2_handle* h, Segment& s) {
+    void* ptrs[] = {s.depth, s.tile_base, s.code, s.qual, s.anch, s.ref_base, s.positions, s.ref_records, s.ref_valid, s.var_records, s.exc_entries, s.counters};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    s = Segment();
+}
+
+extern "C" int pb2_reset(pb2_handle* h) {
+    if (!h) return PB2_ERR_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& s : h->segs) free_segment(h, s);
+    h->segs.clear();
+    h->h_out.clear();
+    h->reads.clear();
+    return PB2_OK;
+}
+
+extern "C" void pb2_destroy(pb2_handle* h) {
+    if (!h) return;
+    pb2_reset(h);
+    if (h->d_chr) cudaFree(h->d_chr);
+    if (h->d_tile_counter) cudaFree(h->d_tile_counter);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" void* pb2_stream(pb2_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+extern "C" int pb2_set_reference(pb2_handle* h, const char* chr_name, const uint8_t* seq, int64_t len) {
+    if (!h || !chr_name || (!seq && len > 0) || len < 0) return fail(h, PB2_ERR_ARG, "pb2_set_reference: bad argument");
+    CU(h, cudaSetDevice(h->device));
+    h->chr_name = chr_name;
+    h->h_chr.assign(seq, seq + len);
+    for (auto& b : h->h_chr) if (b >= 'a' && b <= 'z') b = (uint8_t)(b - 32);   // Genome.cs:81-96 upper-cases on load
+    if (h->d_chr) { cudaFree(h->d_chr); h->d_chr = nullptr; }
+    h->chr_len = len;
+    if (len > 0) {
+        CU(h, cudaMalloc(&h->d_chr, (size_t)len));
+        CU(h, cudaMemcpyAsync(h->d_chr, h->h_chr.data(), (size_t)len, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    return PB2_OK;
+}
+
+extern "C" int pb2_set_intervals(pb2_handle* h, const int32_t* start, const int32_t* end, int32_t n) {
+    if (!h || n < 0 || (n > 0 && (!start || !end))) return fail(h, PB2_ERR_ARG, "pb2_set_intervals: bad argument");
+    h->iv_start.assign(start, start + n);
+    h->iv_end.assign(end, end + n);
+    h->have_intervals = true;   // an empty set still means "intervals applied" (Factory.cs:229-245)
+    derive_config(h);
+    return PB2_OK;
+}
+
+static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs) {
+    if (!h || !p || p->n_loci < 0 || (p->n_loci > 0 && (!p->offsets || !p->code || !p->qual || !p->anchor)))
+        return fail(h, PB2_ERR_ARG, "pb2_push_pileup: bad argument");
+    if (p->n_loci == 0) return PB2_OK;
+    if (p->n_loci > (int64_t)1 << 31) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: more than 2^31 loci in one push");
+    if (!p->ref_bases && !p->positions && (h->chr_len == 0)) return fail(h, PB2_ERR_STATE, "pb2_push_pileup: no ref_bases given and no reference set");
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Segment s;
+    s.n_loci = p->n_loci;
+    s.n_tiles = (int32_t)((p->n_loci + kTileLoci - 1) / kTileLoci);
+    s.first_position = p->first_position;
+    s.has_positions = p->positions != nullptr;
+
+    // CSR on the device
+    const int64_t* d_off = nullptr;
+    const uint8_t *d_code = nullptr, *d_qual = nullptr, *d_anch = nullptr;
+    int64_t* tmp_off = nullptr;
+    uint8_t *tmp_code = nullptr, *tmp_qual = nullptr, *tmp_anch = nullptr;
+    int64_t n_entries = 0;
+    if (device_ptrs) {
+        d_off = p->offsets; d_code = p->code; d_qual = p->qual; d_anch = p->anchor;
+        CU(h, cudaMemcpyAsync(&n_entries, p->offsets + p->n_loci, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+    } else {
+        n_entries = p->offsets[p->n_loci];
+        if (n_entries < 0) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: negative entry count");
+        CU(h, cudaMalloc(&tmp_off, sizeof(int64_t) * (size_t)(p->n_loci + 1)));
+        CU(h, cudaMalloc(&tmp_code, (size_t)std::max<int64_t>(n_entries, 1)));
+        CU(h, cudaMalloc(&tmp_qual, (size_t)std::max<int64_t>(n_entries, 1)));
+        CU(h, cudaMalloc(&tmp_anch, (size_t)std::max<int64_t>(n_entries, 1)));
+        CU(h, cudaMemcpyAsync(tmp_off, p->offsets, sizeof(int64_t) * (size_t)(p->n_loci + 1), cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(tmp_code, p->code, (size_t)n_entries, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(tmp_qual, p->qual, (size_t)n_entries, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(tmp_anch, p->anchor, (size_t)n_entries, cudaMemcpyHostToDevice, st));
+        d_off = tmp_off; d_code = tmp_code; d_qual = tmp_qual; d_anch = tmp_anch;
+    }
+    s.n_entries = n_entries;
+
+    // per-locus side arrays
+    CU(h, cudaMalloc(&s.depth, sizeof(int32_t) * (size_t)p->n_loci));
+    CU(h, cudaMalloc(&s.tile_base, sizeof(int64_t) * (size_t)(s.n_tiles + 1)));
+    CU(h, cudaMalloc(&s.ref_base, (size_t)p->n_loci));
+    const cudaMemcpyKind kind = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (p->positions) {
+        CU(h, cudaMalloc(&s.positions, sizeof(int32_t) * (size_t)p->n_loci));
+        CU(h, cudaMemcpyAsync(s.positions, p->positions, sizeof(int32_t) * (size_t)p->n_loci, kind, st));
+        s.h_positions.resize((size_t)p->n_loci);
+        CU(h, cudaMemcpyAsync(s.h_positions.data(), p->positions, sizeof(int32_t) * (size_t)p->n_loci, device_ptrs ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost, st));
+    }
+    if (p->ref_bases) {
+        CU(h, cudaMemcpyAsync(s.ref_base, p->ref_bases, (size_t)p->n_loci, kind, st));
+    } else {
+        // contiguous positions: slice of the chromosome already on the device
+        if (p->positions) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: ref_bases is required together with positions");
+        const int64_t a = (int64_t)p->first_position - 1;
+        if (a < 0 || a + p->n_loci > h->chr_len) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: loci outside the reference");
+        CU(h, cudaMemcpyAsync(s.ref_base, h->d_chr + a, (size_t)p->n_loci, cudaMemcpyDeviceToDevice, st));
+    }
+
+    // layout: depths, per-tile sizes, exclusive scan -> tile_base, then the interleaving scatter
+    int64_t* tile_bytes = nullptr;
+    CU(h, cudaMalloc(&tile_bytes, sizeof(int64_t) * (size_t)(s.n_tiles + 1)));
+    CU(h, cudaMemsetAsync(tile_bytes, 0, sizeof(int64_t) * (size_t)(s.n_tiles + 1), st));
+    CU(h, launch_tile_layout(d_off, p->n_loci, s.depth, tile_bytes, st));
+    size_t temp_bytes = 0;
+    CU(h, exclusive_scan_i64(tile_bytes, s.tile_base, s.n_tiles + 1, nullptr, 0, &temp_bytes, st));
+    void* temp = nullptr;
+    CU(h, cudaMalloc(&temp, std::max<size_t>(temp_bytes, 16)));
+    CU(h, exclusive_scan_i64(tile_bytes, s.tile_base, s.n_tiles + 1, temp, temp_bytes, nullptr, st));
+    CU(h, cudaMemcpyAsync(&s.plane_bytes, s.tile_base + s.n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    const size_t pb = (size_t)std::max<int64_t>(s.plane_bytes, 16);
+    CU(h, cudaMalloc(&s.code, pb));
+    CU(h, cudaMalloc(&s.qual, pb));
+    CU(h, cudaMalloc(&s.anch, pb));
+    CU(h, launch_tile_scatter(d_off, d_code, d_qual, d_anch, p->n_loci, s.tile_base, s.code, s.qual, s.anch, st));
+    h->total_launches += 4;
+
+    // outputs
+    if (h->cfg.output_gvcf) {
+        CU(h, cudaMalloc(&s.ref_records, sizeof(pb2_call_record) * (size_t)p->n_loci));
+        CU(h, cudaMalloc(&s.ref_valid, (size_t)p->n_loci));
+    }
+    s.var_capacity = std::max<int64_t>(1024, p->n_loci);
+    CU(h, cudaMalloc(&s.var_records, sizeof(pb2_call_record) * (size_t)s.var_capacity));
+    s.exc_capacity = 1 << 20;
+    CU(h, cudaMalloc(&s.exc_entries, sizeof(uint32_t) * 2 * (size_t)s.exc_capacity));
+    CU(h, cudaMalloc(&s.counters, sizeof(unsigned long long) * 2));
+
+    CU(h, cudaStreamSynchronize(st));
+    cudaFree(tile_bytes);
+    cudaFree(temp);
+    if (tmp_off) { cudaFree(tmp_off); cudaFree(tmp_code); cudaFree(tmp_qual); cudaFree(tmp_anch); }
+    h->segs.push_back(std::move(s));
+    return PB2_OK;
+}
+
+extern "C" int pb2_push_pileup(pb2_handle* h, const pb2_pileup_csr* p) { return push_common(h, p, false); }
+extern "C" int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p) { return push_common(h, p, true); }
+
+static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out) {
+    cudaStream_t st = h->stream;
+    TilePileup in;
+    in.code = s.code; in.qual = s.qual; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.ref_base = s.ref_base;
+    in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles;
+    HotInputsExtra ex;
+    ex.gapped_ref = nullptr; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len;
+    HotOutputs out;
+    out.ref_records = s.ref_records; out.ref_valid = s.ref_valid; out.var_records = s.var_records; out.var_count = s.counters;
+    out.var_capacity = s.var_capacity; out.exc_entries = s.exc_entries; out.exc_count = s.counters + 1; out.exc_capacity = s.exc_capacity;
+    out.counts_out = counts_out; out.collapsed_out = collapsed_out;
+    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 2, st));
+    CU(h, cudaEventRecord(h->ev0, st));
+    CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, st));
+    CU(h, cudaEventRecord(h->ev1, st));
+    unsigned long long cnt[2];
+    CU(h, cudaMemcpyAsync(cnt, s.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    float ms = 0;
+    CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->hot_ms += ms;
+    h->hot_launches += 1;
+    h->total_launches += 1;
+    s.h_var_count = cnt[0];
+    s.h_exc_count = cnt[1];
+    s.called = true;
+    if ((int64_t)cnt[0] > s.var_capacity) return fail(h, PB2_ERR_NOMEM, "variant record buffer overflow");
+    if ((int64_t)cnt[1] > s.exc_capacity) return fail(h, PB2_ERR_NOMEM, "open-ended candidate side list overflow");
+    return PB2_OK;
+}
+
+extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
+    if (!h || !b || b->n_reads < 0) return fail(h, PB2_ERR_ARG, "pb2_push_reads: bad argument");
+    if (b->n_reads == 0) return PB2_OK;
+    if (!b->pos0 || !b->flag || !b->cigar_off || !b->cigar || !b->seq_off || !b->bases || !b->quals) return fail(h, PB2_ERR_ARG, "pb2_push_reads: null array");
+    if (h->cfg.call_mnvs) return fail(h, PB2_ERR_UNSUPPORTED, "pb2_push_reads: CallMNVs=true is not built yet");
+    HostReads& R = h->reads;
+    if (R.size() == 0) { R.has_dirs = b->base_dirs != nullptr; R.has_collapsed = b->collapsed != nullptr; }
+    else if (R.has_dirs != (b->base_dirs != nullptr) || R.has_collapsed != (b->collapsed != nullptr))
+        return fail(h, PB2_ERR_ARG, "pb2_push_reads: base_dirs / collapsed must be given for all batches or none");
+    static const bool ref_span[16] = {1, 0, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0}, read_span[16] = {1, 1, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < b->n_reads; i++) {
+        const int64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1], s0 = b->seq_off[i], s1 = b->seq_off[i + 1];
+        if (c1 < c0 || s1 < s0) return fail(h, PB2_ERR_ARG, "pb2_push_reads: offsets not monotone");
+        if (b->pos0[i] < 0) return fail(h, PB2_ERR_ARG, "Position must be greater than 0.");   // RegionStateManager.cs:363-364
+        int64_t rs = 0, fs = 0;
+        for (int64_t k = c0; k < c1; k++) {
+            const uint32_t c = b->cigar[k];
+            if ((c & 15) > 8) return fail(h, PB2_ERR_ARG, "pb2_push_reads: bad CIGAR operation");
+            if (read_span[c & 15]) rs += c >> 4;
+            if (ref_span[c & 15]) fs += c >> 4;
+        }
+        if (c1 > c0 && rs != s1 - s0) return fail(h, PB2_ERR_ARG, "Invalid cigar: does not match length of read");   // Read.cs:603-605
+        R.pos0.push_back(b->pos0[i]);
+        R.end_pos.push_back(b->pos0[i] + (int32_t)fs);
+        R.flag.push_back(b->flag[i]);
+        R.cigar.insert(R.cigar.end(), b->cigar + c0, b->cigar + c1);
+        R.cigar_off.push_back((int64_t)R.cigar.size());
+        R.bases.insert(R.bases.end(), b->bases + s0, b->bases + s1);
+        R.quals.insert(R.quals.end(), b->quals + s0, b->quals + s1);
+        if (R.has_dirs) R.base_dirs.insert(R.base_dirs.end(), b->base_dirs + s0, b->base_dirs + s1);
+        R.seq_off.push_back((int64_t)R.bases.size());
+        if (R.has_collapsed) R.collapsed.push_back(b->collapsed[i]);
+    }
+    return PB2_OK;
+}
+
+template <class T>
+static cudaError_t upload(T** d, const std::vector<T>& v, cudaStream_t st) {
+    cudaError_t e = cudaMalloc(d, std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+// Build a (temporary) segment from the staged reads for reference positions <= cleared_end (INT32_MAX = everything).
+static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t cleared_from) {
+    HostReads& R = h->reads;
+    if (R.size() == 0) return PB2_OK;
+    int32_t lo = INT32_MAX, hi = 0;
+    for (size_t i = 0; i < R.size(); i++) { lo = std::min(lo, R.pos0[i] + 1); hi = std::max(hi, R.end_pos[i]); }
+    lo = std::max(lo, cleared_from);
+    hi = std::min(hi, cleared_end);
+    if (hi < lo) return PB2_OK;
+    const int64_t span = (int64_t)hi - lo + 1;
+    // loci: the whole span, or — with intervals — the interval positions inside 1000-bp blocks some read touched
+    // (reference candidates are only generated for existing blocks: RegionStateManager.cs:295-314, RegionState.cs:393-399)
+    std::vector<int32_t> positions, index_of_pos;
+    if (h->have_intervals) {
+        std::vector<uint8_t> block_touched((size_t)((hi - 1) / 1000 - (lo - 1) / 1000 + 1), 0);
+        const int b0 = (lo - 1) / 1000;
+        for (size_t i = 0; i < R.size(); i++) {
+            const int a = std::max(R.pos0[i] + 1, lo), e = std::min(R.end_pos[i], hi);
+            for (int b = (a - 1) / 1000; a <= e && b <= (e - 1) / 1000; b++) block_touched[(size_t)(b - b0)] = 1;
+        }
+        index_of_pos.assign((size_t)span, -1);
+        std::vector<std::pair<int32_t, int32_t>> iv;
+        for (size_t i = 0; i < h->iv_start.size(); i++) iv.push_back({h->iv_start[i], h->iv_end[i]});
+        std::sort(iv.begin(), iv.end());
+        for (auto& v : iv)
+            for (int64_t p = std::max<int64_t>(v.first, lo); p <= std::min<int64_t>(v.second, hi); p++)
+                if (index_of_pos[(size_t)(p - lo)] < 0 && block_touched[(size_t)((p - 1) / 1000 - b0)]) index_of_pos[(size_t)(p - lo)] = 0;
+        for (int64_t k = 0; k < span; k++)
+            if (index_of_pos[(size_t)k] == 0) { index_of_pos[(size_t)k] = (int32_t)positions.size(); positions.push_back((int32_t)(lo + k)); }
+        if (positions.empty()) return PB2_OK;
+    }
+    const int64_t n_loci = h->have_intervals ? (int64_t)positions.size() : span;
+    if (!h->have_intervals && (h->chr_len < hi)) hi = hi;  // loci beyond the chromosome end keep ref base 'N' below
+
+    cudaStream_t st = h->stream;
+    int32_t *d_pos0 = nullptr, *d_index = nullptr, *d_positions = nullptr;
+    uint16_t* d_flag = nullptr;
+    int64_t *d_coff = nullptr, *d_soff = nullptr, *d_off = nullptr;
+    uint32_t* d_cigar = nullptr;
+    uint8_t *d_bases = nullptr, *d_quals = nullptr, *d_dirs = nullptr, *d_coll = nullptr, *d_code = nullptr, *d_qual = nullptr, *d_anch = nullptr, *d_ref = nullptr;
+    unsigned int *d_depth = nullptr, *d_cursor = nullptr;
+    void* temp = nullptr;
+    auto cleanup = [&]() {
+        void* ptrs[] = {d_pos0, d_index, d_positions, d_flag, d_coff, d_soff, d_off, d_cigar, d_bases, d_quals, d_dirs, d_coll, d_code, d_qual, d_anch, d_ref, d_depth, d_cursor, temp};
+        for (void* p : ptrs) if (p) cudaFree(p);
+    };
+#define CUC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->error = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return PB2_ERR_CUDA; } } while (0)
+    CUC(upload(&d_pos0, R.pos0, st)); CUC(upload(&d_flag, R.flag, st)); CUC(upload(&d_coff, R.cigar_off, st)); CUC(upload(&d_soff, R.seq_off, st));
+    CUC(upload(&d_cigar, R.cigar, st)); CUC(upload(&d_bases, R.bases, st)); CUC(upload(&d_quals, R.quals, st));
+    if (R.has_dirs) CUC(upload(&d_dirs, R.base_dirs, st));
+    if (R.has_collapsed) CUC(upload(&d_coll, R.collapsed, st));
+    if (h->have_intervals) { CUC(upload(&d_index, index_of_pos, st)); CUC(upload(&d_positions, positions, st)); }
+    ReadsView rv{(int32_t)R.size(), d_pos0, d_flag, d_coff, d_cigar, d_soff, d_bases, d_quals, d_dirs, d_coll};
+    RegionView rg{lo, hi, d_index, h->d_chr, h->chr_len, h->dcfg.min_bq, h->cfg.expect_collapsed};
+    CUC(cudaMalloc(&d_depth, sizeof(unsigned int) * (size_t)n_loci));
+    CUC(cudaMalloc(&d_cursor, sizeof(unsigned int) * (size_t)n_loci));
+    CUC(cudaMemsetAsync(d_depth, 0, sizeof(unsigned int) * (size_t)n_loci, st));
+    CUC(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int) * (size_t)n_loci, st));
+    CUC(launch_reads_count(rv, rg, d_depth, st));
+    int64_t* d_depth64 = nullptr;
+    CUC(cudaMalloc(&d_off, sizeof(int64_t) * (size_t)(n_loci + 1)));
+    CUC(cudaMalloc(&d_depth64, sizeof(int64_t) * (size_t)(n_loci + 1)));
+    cudaError_t e2 = launch_depth_to_i64(d_depth, d_depth64, n_loci, st);
+    size_t tb = 0;
+    if (e2 == cudaSuccess) e2 = exclusive_scan_i64(d_depth64, d_off, n_loci + 1, nullptr, 0, &tb, st);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&temp, std::max<size_t>(tb, 16));
+    if (e2 == cudaSuccess) e2 = exclusive_scan_i64(d_depth64, d_off, n_loci + 1, temp, tb, nullptr, st);
+    int64_t n_entries = 0;
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(&n_entries, d_off + n_loci, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+    cudaFree(d_depth64);
+    CUC(e2);
+    CUC(cudaMalloc(&d_code, (size_t)std::max<int64_t>(n_entries, 1)));
+    CUC(cudaMalloc(&d_qual, (size_t)std::max<int64_t>(n_entries, 1)));
+    CUC(cudaMalloc(&d_anch, (size_t)std::max<int64_t>(n_entries, 1)));
+    CUC(launch_reads_emit(rv, rg, d_off, d_cursor, d_code, d_qual, d_anch, st));
+    h->total_launches += 5;
+    // reference bases of the staged loci ('N' beyond the chromosome end or when no reference was set)
+    std::vector<uint8_t> refb((size_t)n_loci, (uint8_t)'N');
+    for (int64_t i = 0; i < n_loci; i++) {
+        const int64_t p = h->have_intervals ? positions[(size_t)i] : lo + i;
+        if (p >= 1 && p <= h->chr_len) refb[(size_t)i] = h->h_chr[(size_t)(p - 1)];
+    }
+    CUC(upload(&d_ref, refb, st));
+    CUC(cudaStreamSynchronize(st));
+    pb2_pileup_csr csr;
+    csr.n_loci = n_loci; csr.first_position = lo; csr.positions = h->have_intervals ? d_positions : nullptr; csr.offsets = d_off;
+    csr.code = d_code; csr.qual = d_qual; csr.anchor = d_anch; csr.ref_bases = d_ref;
+    const int rc = push_common(h, &csr, true);
+    cleanup();
+#undef CUC
+    if (rc != PB2_OK) return rc;
+    h->segs.back().temporary = true;
+    return PB2_OK;
+}
+
+extern "C" int pb2_call_resident(pb2_handle* h, int64_t* n_records) {
+    if (!h) return PB2_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    int64_t total = 0;
+    for (auto& s : h->segs) {
+        int rc = run_segment(h, s, nullptr, nullptr);
+        if (rc != PB2_OK) return rc;
+        total += (int64_t)s.h_var_count;
+    }
+    if (n_records) *n_records = total;
+    return PB2_OK;
+}
+
+extern "C" int pb2_resident_results(pb2_handle* h, const pb2_call_record** ref_records, const uint8_t** ref_valid, int64_t* n_loci,
+                                    const pb2_call_record** variant_records, int64_t* n_variants) {
+    if (!h) return PB2_ERR_ARG;
+    if (h->segs.empty() || !h->segs.back().called) return fail(h, PB2_ERR_STATE, "pb2_resident_results: nothing has been called");
+    const Segment& s = h->segs.back();
+    if (ref_records) *ref_records = s.ref_records;
+    if (ref_valid) *ref_valid = s.ref_valid;
+    if (n_loci) *n_loci = s.n_loci;
+    if (variant_records) *variant_records = s.var_records;
+    if (n_variants) *n_variants = (int64_t)s.h_var_count;
+    return PB2_OK;
+}
+
+static inline bool record_less(const pb2_call_record& a, const pb2_call_record& b) {
+    if (a.position != b.position) return a.position < b.position;
+    // (ReferenceAllele, AlternateAllele) string order (AlleleCaller.cs:172-176); inline alleles only so far
+    const uint32_t ra = a.allele_bytes & ((1u << (8 * a.ref_len)) - 1), rb = b.allele_bytes & ((1u << (8 * b.ref_len)) - 1);
+    auto bytes_less = [](uint32_t x, int nx, uint32_t y, int ny, bool& eq) {
+        for (int i = 0; i < std::min(nx, ny); i++) {
+            const uint8_t cx = (x >> (8 * i)) & 0xff, cy = (y >> (8 * i)) & 0xff;
+            if (cx != cy) { eq = false; return cx < cy; }
+        }
+        eq = nx == ny;
+        return nx < ny;
+    };
+    bool eq;
+    bool l = bytes_less(ra, a.ref_len, rb, b.ref_len, eq);
+    if (!eq) return l;
+    const uint32_t aa = a.allele_bytes >> (8 * a.ref_len), ab = b.allele_bytes >> (8 * b.ref_len);
+    l = bytes_less(aa, a.alt_len, ab, b.alt_len, eq);
+    return eq ? false : l;
+}
+
+// Flagged mismatching entries (side list of the hot kernel) against the SNV records it emitted.
+//  * PB2_ENTRY_NO_CANDIDATE: the base was counted but CandidateVariantFinder never sees it ('='/'X' operations, bases past the
+//    chromosome end: CandidateVariantFinder.cs:46-64,102-103) -> its support must come off the candidate.
+//  * open-ended entries (only tracked when Collapse is on, RegionState.cs:114-118): VariantCollapser merges an open-ended SNV into its
+//    fully anchored twin unconditionally (exact match, VariantCollapser.cs:213-215) and the smaller of two complementary open-ended
+//    twins into the larger (frequency ratio >= 1 > 0.5, :218); then the record built from the total support is exact. Anything else
+//    needs the explicit-candidate path.
+static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std::vector<uint32_t>& exc, std::vector<pb2_call_record>& vars) {
+    struct Key { uint32_t locus; int allele; bool operator<(const Key& o) const { return locus != o.locus ? locus < o.locus : allele < o.allele; } };
+    struct Acc { int nocand = 0; int open_l = 0, open_r = 0, open_lr = 0; };
+    std::vector<std::pair<Key, Acc>> groups;
+    {
+        std::vector<std::pair<Key, uint32_t>> items;
+        for (size_t i = 0; i + 1 < exc.size(); i += 2) items.push_back({Key{exc[i], (int)(exc[i + 1] & 7)}, exc[i + 1] & 0xffu});
+        std::sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        for (auto& it : items) {
+            if (groups.empty() || groups.back().first < it.first) groups.push_back({it.first, Acc()});
+            Acc& a = groups.back().second;
+            const bool l = it.second & PB2_ENTRY_OPEN_LEFT, r = it.second & PB2_ENTRY_OPEN_RIGHT;
+            if (it.second & PB2_ENTRY_NO_CANDIDATE) a.nocand++;
+            else if (l && r) a.open_lr++;
+            else if (l) a.open_l++;
+            else if (r) a.open_r++;
+        }
+    }
+    static const char base_of[4] = {'A', 'G', 'C', 'T'};
+    for (auto& g : groups) {
+        const int32_t pos = s.has_positions ? s.h_positions[g.first.locus] : s.first_position + (int32_t)g.first.locus;
+        for (auto& v : vars) {
+            if (v.position != pos || v.type != CAT_SNV || (char)((v.allele_bytes >> 8) & 0xff) != base_of[g.first.allele]) continue;
+            const Acc& a = g.second;
+            if (a.nocand > 0) return fail(h, PB2_ERR_UNSUPPORTED, "called SNV has support from '='/'X' operations: explicit-candidate path not built yet");
+            if (!h->cfg.collapse) continue;   // open ends are not tracked without the collapser
+            const int anchored = v.allele_support - (a.open_l + a.open_r + a.open_lr);
+            const int kinds = (a.open_l > 0) + (a.open_r > 0) + (a.open_lr > 0);
+            if (anchored > 0 || kinds <= 1) continue;                       // exact-match merge, or a single open-ended candidate on its own
+            if (kinds == 2 && a.open_lr == 0) continue;                     // complementary twins: smaller merges into larger
+            return fail(h, PB2_ERR_UNSUPPORTED, "open-ended SNV candidates without an anchored twin need the explicit-candidate path (not built yet)");
+        }
+    }
+    return PB2_OK;
+}
+
+extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n) {
+    if (!h || !out || !n) return fail(h, PB2_ERR_ARG, "pb2_flush: null argument");
+    CU(h, cudaSetDevice(h->device));
+    h->h_out.clear();
+    // reads staged through pb2_push_reads: positions in complete 1000-bp blocks <= up_to_position are callable (RegionStateManager.cs:283-314);
+    // locus-major pushes are complete by construction
+    const int32_t cleared_end = up_to_position < 0 ? INT32_MAX : (up_to_position / 1000) * 1000;
+    {
+        const int rc = stage_reads_segment(h, cleared_end, h->cleared_through + 1);
+        if (rc != PB2_OK) return rc;
+    }
+    for (auto& s : h->segs) {
+        if (!s.called) { int rc = run_segment(h, s, nullptr, nullptr); if (rc != PB2_OK) return rc; }
+        std::vector<pb2_call_record> vars((size_t)s.h_var_count);
+        std::vector<uint32_t> exc((size_t)s.h_exc_count * 2);
+        if (!exc.empty()) CU(h, cudaMemcpyAsync(exc.data(), s.exc_entries, sizeof(uint32_t) * exc.size(), cudaMemcpyDeviceToHost, h->stream));
+        if (!vars.empty()) CU(h, cudaMemcpyAsync(vars.data(), s.var_records, sizeof(pb2_call_record) * vars.size(), cudaMemcpyDeviceToHost, h->stream));
+        std::vector<pb2_call_record> refs;
+        std::vector<uint8_t> valid;
+        if (s.ref_records) {
+            refs.resize((size_t)s.n_loci);
+            valid.resize((size_t)s.n_loci);
+            CU(h, cudaMemcpyAsync(refs.data(), s.ref_records, sizeof(pb2_call_record) * refs.size(), cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaMemcpyAsync(valid.data(), s.ref_valid, valid.size(), cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (!exc.empty()) { const int rc = reconcile_flagged_entries(h, s, exc, vars); if (rc != PB2_OK) return rc; }
+        std::sort(vars.begin(), vars.end(), record_less);
+        // merge the dense reference stream (already in position order) with the sorted variant stream
+        size_t vi = 0;
+        for (int64_t i = 0; i < s.n_loci; i++) {
+            const int32_t pos = s.has_positions ? s.h_positions[(size_t)i] : s.first_position + (int32_t)i;
+            while (vi < vars.size() && vars[vi].position < pos) h->h_out.push_back(vars[vi++]);
+            while (vi < vars.size() && vars[vi].position == pos) h->h_out.push_back(vars[vi++]);
+            if (!refs.empty() && valid[(size_t)i]) h->h_out.push_back(refs[(size_t)i]);
+        }
+        while (vi < vars.size()) h->h_out.push_back(vars[vi++]);
+    }
+    // drop what this flush consumed: temporary segments, and reads that end inside the cleared positions
+    for (size_t i = 0; i < h->segs.size();) {
+        if (h->segs[i].temporary) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); } else i++;
+    }
+    if (up_to_position < 0) { h->reads.clear(); h->cleared_through = 0; }
+    else if (h->reads.size() != 0 && cleared_end > h->cleared_through) {
+        HostReads keep;
+        HostReads& R = h->reads;
+        keep.has_dirs = R.has_dirs; keep.has_collapsed = R.has_collapsed;
+        for (size_t i = 0; i < R.size(); i++) {
+            if (R.end_pos[i] <= cleared_end) continue;
+            keep.pos0.push_back(R.pos0[i]); keep.end_pos.push_back(R.end_pos[i]); keep.flag.push_back(R.flag[i]);
+            keep.cigar.insert(keep.cigar.end(), R.cigar.begin() + R.cigar_off[i], R.cigar.begin() + R.cigar_off[i + 1]);
+            keep.cigar_off.push_back((int64_t)keep.cigar.size());
+            keep.bases.insert(keep.bases.end(), R.bases.begin() + R.seq_off[i], R.bases.begin() + R.seq_off[i + 1]);
+            keep.quals.insert(keep.quals.end(), R.quals.begin() + R.seq_off[i], R.quals.begin() + R.seq_off[i + 1]);
+            if (R.has_dirs) keep.base_dirs.insert(keep.base_dirs.end(), R.base_dirs.begin() + R.seq_off[i], R.base_dirs.begin() + R.seq_off[i + 1]);
+            keep.seq_off.push_back((int64_t)keep.bases.size());
+            if (R.has_collapsed) keep.collapsed.push_back(R.collapsed[i]);
+        }
+        h->reads = std::move(keep);
+        h->cleared_through = cleared_end;
+    }
+    *out = h->h_out.data();
+    *n = (int64_t)h->h_out.size();
+    return PB2_OK;
+}
+
+extern "C" int pb2_get_counts(pb2_handle* h, int32_t position0, int32_t n, int32_t* out) {
+    if (!h || !out || n < 0) return fail(h, PB2_ERR_ARG, "pb2_get_counts: bad argument");
+    CU(h, cudaSetDevice(h->device));
+    memset(out, 0, sizeof(int32_t) * (size_t)n * kNumBins);   // positions nobody staged read as 0 (RegionStateManager.cs:224-225)
+    {
+        // staged reads are expanded over the requested window only (no intervals filter: counts exist for every position)
+        const bool iv = h->have_intervals;
+        h->have_intervals = false;
+        const int rc = stage_reads_segment(h, position0 + n - 1, position0);
+        h->have_intervals = iv;
+        if (rc != PB2_OK) return rc;
+    }
+    for (auto& s : h->segs) {
+        int32_t* d_counts = nullptr;
+        CU(h, cudaMalloc(&d_counts, sizeof(int32_t) * (size_t)s.n_loci * kNumBins));
+        const bool was_called = s.called;
+        const unsigned long long vc = s.h_var_count, ec = s.h_exc_count;
+        int rc = run_segment(h, s, d_counts, nullptr);
+        s.called = was_called; s.h_var_count = vc; s.h_exc_count = ec;
+        if (rc != PB2_OK) { cudaFree(d_counts); return rc; }
+        std::vector<int32_t> hc((size_t)s.n_loci * kNumBins);
+        CU(h, cudaMemcpy(hc.data(), d_counts, sizeof(int32_t) * hc.size(), cudaMemcpyDeviceToHost));
+        cudaFree(d_counts);
+        for (int64_t i = 0; i < s.n_loci; i++) {
+            const int32_t pos = s.has_positions ? s.h_positions[(size_t)i] : s.first_position + (int32_t)i;
+            const int64_t k = (int64_t)pos - position0;
+            if (k >= 0 && k < n) memcpy(out + k * kNumBins, hc.data() + i * kNumBins, sizeof(int32_t) * kNumBins);
+        }
+    }
+    for (size_t i = 0; i < h->segs.size();) {
+        if (h->segs[i].temporary) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); } else i++;
+    }
+    return PB2_OK;
+}
+
+extern "C" int pb2_stats(pb2_handle* h, int64_t* hot_kernel_launches, double* hot_kernel_ms, int64_t* total_kernel_launches) {
+    if (!h) return PB2_ERR_ARG;
+    if (hot_kernel_launches) *hot_kernel_launches = h->hot_launches;
+    if (hot_kernel_ms) *hot_kernel_ms = h->hot_ms;
+    if (total_kernel_launches) *total_kernel_launches = h->total_launches;
+    h->hot_launches = 0; h->hot_ms = 0; h->total_launches = 0;
+    return PB2_OK;
+}

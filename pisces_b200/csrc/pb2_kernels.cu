@@ -1,0 +1,425 @@
+// Hot-path kernels for sm_100a: tile staging and the fused pileup-count + score kernel.
+//
+// Replaces (reference @ /root/reference):
+//   RegionStateManager.AddAlleleCounts / RegionState.AddAlleleCount     src/lib/Pisces.Processing/RegionState/RegionStateManager.cs:118-220, RegionState.cs:225-239
+//   RegionState.GetAllCandidates (reference candidates)                 RegionState.cs:383-453
+//   CoverageCalculator.CalculateSinglePoint                             src/lib/Pisces.Calculators/CoverageCalculator.cs:49-98
+//   AlleleCaller.ProcessVariant / IsCallable / ComputeGenotypeAndFilterAllele   src/exe/Pisces/Logic/VariantCalling/AlleleCaller.cs:143-177,208-258
+//   AlleleProcessor.ApplyFilters, RMxNCalculator                        AlleleProcessor.cs:25-71, src/lib/Pisces.Calculators/RMxNCalculator.cs:19-133
+#include <cub/device/device_scan.cuh>
+#include "pb2_kernels.cuh"
+#include "pb2_math.cuh"
+
+namespace pb2 {
+
+// ------------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {  // 16-byte streaming load: read once, do not pollute L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int allele_of_base(uint8_t c) {  // AlleleHelper.GetAlleleType (Utility/AlleleHelper.cs:13-32)
+    switch (c) { case 'A': return AT_A; case 'C': return AT_C; case 'G': return AT_G; case 'T': return AT_T; default: return AT_N; }
+}
+__device__ __forceinline__ char base_of_allele(int a) { return a == AT_A ? 'A' : a == AT_C ? 'C' : a == AT_G ? 'G' : a == AT_T ? 'T' : 'N'; }
+
+// ------------------------------------------------------------------------------------------------ CSR -> PTILE32
+// depth[i] = off[i+1]-off[i];  tile_chunks[t] = bytes per plane of tile t = 16 * sum over the tile's loci of ceil(depth/16)
+__global__ void tile_layout_kernel(const int64_t* __restrict__ off, int64_t n_loci, int32_t* __restrict__ depth, int64_t* __restrict__ tile_chunks) {
+    const int64_t locus = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // blockDim multiple of 32, tiles are warp-aligned
+    int d = 0;
+    if (locus < n_loci) { d = (int)(off[locus + 1] - off[locus]); depth[locus] = d; }
+    int chunks = (d + kChunk - 1) / kChunk;
+    chunks = __reduce_add_sync(0xffffffffu, chunks);
+    if ((threadIdx.x & 31) == 0 && (locus / kTileLoci) * (int64_t)kTileLoci < n_loci) tile_chunks[locus / kTileLoci] = (int64_t)chunks * kChunk;
+}
+
+// one warp per tile: lane i copies locus i's entries chunk by chunk into the interleaved position; tail bytes of a locus' last chunk are 0xFF
+__global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8_t* __restrict__ code, const uint8_t* __restrict__ qual,
+                                    const uint8_t* __restrict__ anch, int64_t n_loci, const int64_t* __restrict__ tile_base, uint8_t* __restrict__ tcode,
+                                    uint8_t* __restrict__ tqual, uint8_t* __restrict__ tanch) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t locus = tile * kTileLoci + lane;
+    if (tile * kTileLoci >= n_loci) return;
+    int64_t src = 0;
+    int d = 0;
+    if (locus < n_loci) { src = off[locus]; d = (int)(off[locus + 1] - src); }
+    const int nchunks = (d + kChunk - 1) / kChunk;
+    const int max_chunks = __reduce_max_sync(0xffffffffu, nchunks);
+    int64_t base = tile_base[tile];
+    for (int c = 0; c < max_chunks; c++) {
+        const bool active = c < nchunks;
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const int slot = __popc(m & ((1u << lane) - 1));
+            const int64_t dst = base + (int64_t)slot * kChunk;
+            const int n = min(kChunk, d - c * kChunk);
+            const int64_t s = src + (int64_t)c * kChunk;
+            const uint8_t* planes_in[3] = {code, qual, anch};
+            uint8_t* planes_out[3] = {tcode, tqual, tanch};
+#pragma unroll
+            for (int p = 0; p < 3; p++) {
+                uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                for (int k = 0; k < n; k++) {
+                    const uint32_t b = planes_in[p][s + k];
+                    w[k >> 2] = (w[k >> 2] & ~(0xffu << ((k & 3) * 8))) | (b << ((k & 3) * 8));
+                }
+                *reinterpret_cast<uint4*>(planes_out[p] + dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        base += (int64_t)__popc(m) * kChunk;
+    }
+}
+
+cudaError_t launch_tile_layout(const int64_t* off, int64_t n_loci, int32_t* depth, int64_t* tile_chunks, cudaStream_t stream) {
+    const int threads = 256;
+    const int64_t n_pad = (n_loci + kTileLoci - 1) / kTileLoci * kTileLoci;
+    const unsigned blocks = (unsigned)((n_pad + threads - 1) / threads);
+    if (blocks) tile_layout_kernel<<<blocks, threads, 0, stream>>>(off, n_loci, depth, tile_chunks);
+    return cudaGetLastError();
+}
+cudaError_t launch_tile_scatter(const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci, const int64_t* tile_base,
+                                uint8_t* tcode, uint8_t* tqual, uint8_t* tanch, cudaStream_t stream) {
+    const int threads = 256;
+    const int64_t n_tiles = (n_loci + kTileLoci - 1) / kTileLoci;
+    const unsigned blocks = (unsigned)((n_tiles * 32 + threads - 1) / threads);
+    if (blocks) tile_scatter_kernel<<<blocks, threads, 0, stream>>>(off, code, qual, anch, n_loci, tile_base, tcode, tqual, tanch);
+    return cudaGetLastError();
+}
+
+// out[i] = sum_{j<i} in[j]   (staging step, not on the hot path: CUB device scan). tile_layout_kernel already scaled the input to bytes.
+cudaError_t exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* temp, size_t temp_bytes, size_t* temp_needed, cudaStream_t stream) {
+    size_t need = 0;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, stream);
+    if (e != cudaSuccess) return e;
+    if (temp_needed) *temp_needed = need;
+    if (temp == nullptr) return cudaSuccess;
+    if (temp_bytes < need) return cudaErrorInvalidValue;
+    return cub::DeviceScan::ExclusiveSum(temp, need, in, out, (int)n, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ the fused hot kernel
+// Thread-private histogram cell for (bin, thread): 16-bit counters interleaved so that the 32 lanes of a warp always hit 32 different
+// banks whatever bins they address: halfword index = bin * kHotThreads + (warp >> 1) * 64 + lane * 2 + (warp & 1).
+__device__ __forceinline__ int hist_slot(int warp, int lane) { return (warp >> 1) * 64 + lane * 2 + (warp & 1); }
+
+// RMxNCalculator.ComputeRMxNLengthForIndel (:49-95) on the device-resident chromosome; variant_bases has length <= 1 for point alleles
+__device__ int rmxn_length_for_indel(int variant_position, const char* vb, int length, const uint8_t* __restrict__ ref, int64_t ref_len, int max_unit) {
+    int best = 0;
+    const int first = length - min(max_unit, length);
+    for (int pass = 0; pass < 2; pass++) {          // prefixes, then suffixes (bookends)
+        for (int i = first; i < length; i++) {
+            const int blen = length - i;
+            const char* book = pass == 0 ? vb : vb + i;
+            int64_t back = variant_position;
+            while (true) {
+                const int64_t nb = back - blen;
+                if (nb < 0) break;
+                bool eq = true;
+                for (int k = 0; k < blen; k++) if (ref[nb + k] != (uint8_t)book[k]) { eq = false; break; }
+                if (!eq) break;
+                back = nb;
+            }
+            int reps = 0;
+            int64_t cur = back;
+            while (true) {
+                if (cur + blen > ref_len) break;
+                bool eq = true;
+                for (int k = 0; k < blen; k++) if (ref[cur + k] != (uint8_t)book[k]) { eq = false; break; }
+                if (!eq) break;
+                reps++;
+                cur += blen;
+            }
+            best = max(best, reps);
+        }
+    }
+    return best;
+}
+// RMxNCalculator.ShouldFilter for an SNV (:19-38,104-133)
+__device__ bool rmxn_should_filter_snv(int position, char ref_base, char alt_base, float freq, const DeviceConfig& cfg, const uint8_t* __restrict__ ref, int64_t ref_len) {
+    if (freq >= cfg.rmxn_freq_limit) return false;
+    if (cfg.rmxn_max_len < 0 || cfg.rmxn_min_reps < 0 || ref == nullptr) return false;
+    const int c1 = rmxn_length_for_indel(position - 1, &ref_base, 1, ref, ref_len, cfg.rmxn_max_len);
+    const int i1 = rmxn_length_for_indel(position + 1 - 1, &alt_base, 1, ref, ref_len, cfg.rmxn_max_len);
+    const int i2 = rmxn_length_for_indel(position - 1, &alt_base, 1, ref, ref_len, cfg.rmxn_max_len);
+    return min(c1, max(i1, i2)) >= cfg.rmxn_min_reps;
+}
+
+struct LocusCounts {
+    int c[kNumAlleles][kNumDirs];  // anchor-summed counts  (IAlleleSource.GetAlleleCount defaults: all 11 bins)
+    double qsum;                   // Σ over coverage-contributing alleles of the base-quality probabilities
+};
+
+// Fill one record for a point allele (Reference or Snv) exactly as ProcessVariant + SetGenotypes would. Returns false when a non-reference
+// allele is not callable (AlleleCaller.IsCallable) so nothing is emitted.
+__device__ bool score_point_allele(const LocusCounts& lc, int position, int ref_allele, int alt_allele /* == ref_allele for Reference */, int gapped,
+                                   const DeviceConfig& cfg, const uint8_t* __restrict__ chr_seq, int64_t chr_len, pb2_call_record& r) {
+    const bool is_ref = alt_allele == ref_allele;
+    int cov[3], sup[3];
+    int total = 0, nocalls = 0, ref_support = 0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        cov[d] = lc.c[AT_A][d] + lc.c[AT_C][d] + lc.c[AT_G][d] + lc.c[AT_T][d] + lc.c[AT_DEL][d];
+        total += cov[d];
+        nocalls += lc.c[AT_N][d];
+        sup[d] = lc.c[alt_allele][d];
+        if (ref_allele != AT_N) ref_support += lc.c[ref_allele][d];
+    }
+    int allele_support = sup[0] + sup[1] + sup[2];
+    if (is_ref) allele_support = max(0, allele_support - gapped);  // CoverageCalculator.cs:94-97
+    else ref_support = max(0, ref_support - gapped);               // :90-93
+    const float freq = allele_frequency(allele_support, total);
+
+    // cheap callability tests first (same outcome as evaluating Q/SB first, AlleleCaller.cs:236-258)
+    if (!is_ref) {
+        if (total < cfg.min_coverage && !cfg.output_gvcf) return false;
+        if (total != 0 && freq < cfg.min_frequency) return false;
+    }
+    int vq = 0, nl_applied = 0;
+    SbResult sb;
+    sb.bias = 0; sb.gatk = 0; sb.acceptable = false; sb.var_both = false; sb.cov_both = false;   // new BiasResults()
+    if (allele_support > 0) {
+        int nl = cfg.noise_level;
+        if (cfg.noise_model == 1) nl = (int)(-10 * log10(lc.qsum / total));   // NoiseModel.Window (AlleleCaller.cs:215-218)
+        nl_applied = nl;
+        vq = (total == 0) ? 0 : poisson_qscore(allele_support, total, nl, cfg.max_vq);
+    }
+    if (!is_ref && vq < cfg.min_vq) return false;
+    if (allele_support > 0) sb = strand_bias(cov, sup, cfg.noise_level, (double)cfg.sb_acceptance, cfg.sb_model);
+
+    // AlleleProcessor.Process / ApplyFilters
+    const float all_reads = (float)(total + nocalls);
+    const float frac_nc = all_reads == 0 ? 0.0f : ((float)nocalls / all_reads);
+    unsigned filters = 0;
+    if (cfg.low_depth_filter >= 0 && total < cfg.low_depth_filter) filters |= 1u << FLT_LOW_DEPTH;
+    if (vq < cfg.vq_filter && total != 0) filters |= 1u << FLT_LOW_VQ;
+    if (!is_ref) {
+        if (cfg.no_call_filter >= 0 && frac_nc > cfg.no_call_filter) filters |= 1u << FLT_NO_CALL;
+        if (!sb.acceptable || (cfg.filter_single_strand && !sb.var_both)) filters |= 1u << FLT_STRAND_BIAS;
+        if (rmxn_should_filter_snv(position, base_of_allele(ref_allele), base_of_allele(alt_allele), freq, cfg, chr_seq, chr_len)) filters |= 1u << FLT_RMXN;
+        if (freq < cfg.variant_freq_filter) filters |= 1u << FLT_LOW_VF;
+    }
+    // SomaticGenotyper + GQ (per allele)
+    const float ref_freq = allele_frequency(ref_support, total);
+    const int gt = somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
+    const int gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq);
+    if (cfg.low_gq_filter >= 0 && (float)gq < (float)cfg.low_gq_filter) filters |= 1u << FLT_LOW_GQ;
+
+    r.position = position;
+    r.type = is_ref ? CAT_REF : CAT_SNV;
+    r.genotype = (uint8_t)gt;
+    r.sb_flags = (sb.acceptable ? 1 : 0) | (sb.var_both ? 2 : 0) | (sb.cov_both ? 4 : 0);
+    r.open_flags = 0;
+    r.filters = (uint16_t)filters;
+    r.noise_level = (uint16_t)nl_applied;
+    r.variant_qscore = vq;
+    r.genotype_qscore = gq;
+    r.total_coverage = total;
+#pragma unroll
+    for (int d = 0; d < 3; d++) { r.coverage_by_direction[d] = cov[d]; r.support_by_direction[d] = sup[d]; }
+    r.allele_support = allele_support;
+    r.reference_support = ref_support;
+    r.num_no_calls = nocalls;
+    r.fraction_no_calls = frac_nc;
+    r.allele_bytes = (uint32_t)(uint8_t)base_of_allele(ref_allele) | ((uint32_t)(uint8_t)base_of_allele(alt_allele) << 8);
+    r.ref_len = 1;
+    r.alt_len = 1;
+    r.sum_base_quality = lc.qsum;
+    r.bias_score = sb.bias;
+    r.gatk_bias_score = sb.gatk;
+    return true;
+}
+
+__device__ __forceinline__ void store_record(pb2_call_record* dst, const pb2_call_record& r) {
+    const uint4* s = reinterpret_cast<const uint4*>(&r);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(pb2_call_record) / 16); i++) d[i] = s[i];
+}
+
+template <bool kWantQsum, bool kCollapsed>
+__global__ void __launch_bounds__(kHotThreads, 1)
+pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, DeviceConfig cfg, int* __restrict__ tile_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw);                                     // [rows][kHotThreads]
+    constexpr int kRows = kNumBins + (kCollapsed ? kNumCollapsed : 0);
+    double* q_lut = reinterpret_cast<double*>(smem_raw + (size_t)kRows * kHotThreads * sizeof(uint16_t));  // [256] 10^(-q/10f)
+    __shared__ int s_tile[kHotThreads / 32];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint16_t* my = hist + hist_slot(warp, lane);   // my[bin * kHotThreads]
+    for (int b = 0; b < kRows; b++) my[b * kHotThreads] = 0;
+    if (kWantQsum) {
+        for (int q = threadIdx.x; q < 256; q += kHotThreads) q_lut[q] = pow(10.0, (double)((float)(-q) / 10.0f));  // RegionStateManager.cs:191 (float exponent)
+        __syncthreads();
+    }
+
+    while (true) {
+        if (lane == 0) s_tile[warp] = atomicAdd(tile_counter, 1);
+        __syncwarp();
+        const int tile = s_tile[warp];
+        __syncwarp();
+        if (tile >= in.n_tiles) break;
+
+        const int64_t locus = (int64_t)tile * kTileLoci + lane;
+        const bool have_locus = locus < in.n_loci;
+        const int depth = have_locus ? in.depth[locus] : 0;
+        const int nchunks = (depth + kChunk - 1) / kChunk;
+        const int max_chunks = __reduce_max_sync(0xffffffffu, nchunks);
+        const int ref_allele = have_locus ? allele_of_base(in.ref_base[locus]) : AT_N;
+        int64_t base = in.tile_base[tile];
+        double qsum = 0.0;
+
+        // software pipeline: chunk c+1 is in flight while chunk c is histogrammed
+        uint4 nc = make_uint4(0, 0, 0, 0), nq = nc, na = nc;
+        {
+            const bool active = 0 < nchunks;
+            const unsigned m = __ballot_sync(0xffffffffu, active);
+            if (active) {
+                const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
+                nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o); na = ldg_stream(in.anch + o);
+            }
+            base += (int64_t)__popc(m) * kChunk;
+        }
+        for (int c = 0; c < max_chunks; c++) {
+            const uint4 wc = nc, wq = nq, wa = na;
+            {
+                const bool active = (c + 1) < nchunks;
+                const unsigned m = __ballot_sync(0xffffffffu, active);
+                if (active) {
+                    const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
+                    nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o); na = ldg_stream(in.anch + o);
+                }
+                base += (int64_t)__popc(m) * kChunk;
+            }
+            const int n_here = min(kChunk, depth - c * kChunk);   // <= 0 for lanes that ran out of chunks
+            const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w}, aw[4] = {wa.x, wa.y, wa.z, wa.w};
+#pragma unroll
+            for (int k = 0; k < kChunk; k++) {
+                if (k < n_here) {
+                    const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                    const uint32_t q = (qw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                    const uint32_t an = (aw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                    const int allele = code & 7;
+                    const int dir = (code >> 3) & 3;
+                    const bool lowq = (int)q < cfg.min_bq;
+                    // deletions below the quality bar are not counted at all (RegionStateManager.cs:170-177); bases become N (:180-181)
+                    if (!(allele == AT_DEL && lowq)) {
+                        const int a2 = lowq ? AT_N : allele;
+                        const int bin = (a2 * kNumDirs + dir) * kNumAnchors + (int)(an & 15u);
+                        my[bin * kHotThreads] += 1;
+                        if (kWantQsum) { if (allele != AT_DEL && a2 != AT_N) qsum += q_lut[q]; }
+                        if (kCollapsed) {
+                            const int ct = (int)(an >> 4);
+                            if (ct != 0 && a2 != AT_N) {   // CollapsedRegionState.AddCollapsedReadCount (:28-44)
+                                my[(kNumBins + ct - 1) * kHotThreads] += 1;
+                                if (ct - 1 == 4 || ct - 1 == 6) my[(kNumBins + 2) * kHotThreads] += 1;
+                                else if (ct - 1 == 5 || ct - 1 == 7) my[(kNumBins + 3) * kHotThreads] += 1;
+                            }
+                        }
+                        // flagged entries that would raise an SNV candidate need the candidate bookkeeping of CandidateVariantFinder: rare, side list
+                        if ((code & 0xe0u) != 0 && a2 < AT_N && a2 != ref_allele && ref_allele != AT_N) {
+                            const unsigned long long slot = atomicAdd(out.exc_count, 1ull);
+                            if ((int64_t)slot < out.exc_capacity) {
+                                out.exc_entries[2 * slot] = (uint32_t)locus;
+                                out.exc_entries[2 * slot + 1] = code | (q << 8) | (an << 16);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- read the histogram out (and clear it for the next tile)
+        LocusCounts lc;
+        lc.qsum = qsum;
+        int any = 0;
+#pragma unroll
+        for (int a = 0; a < kNumAlleles; a++)
+#pragma unroll
+            for (int d = 0; d < kNumDirs; d++) {
+                int s = 0;
+#pragma unroll
+                for (int an = 0; an < kNumAnchors; an++) {
+                    const int bin = (a * kNumDirs + d) * kNumAnchors + an;
+                    const int v = my[bin * kHotThreads];
+                    my[bin * kHotThreads] = 0;
+                    if (out.counts_out != nullptr && have_locus) out.counts_out[locus * kNumBins + bin] = v;
+                    s += v;
+                }
+                lc.c[a][d] = s;
+                any += s;
+            }
+        if (kCollapsed) {
+#pragma unroll
+            for (int t = 0; t < kNumCollapsed; t++) {
+                const int v = my[(kNumBins + t) * kHotThreads];
+                my[(kNumBins + t) * kHotThreads] = 0;
+                if (out.collapsed_out != nullptr && have_locus) out.collapsed_out[locus * kNumCollapsed + t] = v;
+            }
+        }
+        if (!have_locus) continue;
+
+        // ---- score: SNV candidates in (ref, alt) order = alphabetical alt (AlleleCaller.cs:172-176), then the reference allele
+        const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+        const int gapped = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
+        bool variant_called = ex.locus_has_variant ? (ex.locus_has_variant[locus] != 0) : false;
+        if (ref_allele != AT_N) {
+            const int order[4] = {AT_A, AT_C, AT_G, AT_T};
+#pragma unroll 1
+            for (int oi = 0; oi < 4; oi++) {
+                const int alt = order[oi];
+                if (alt == ref_allele) continue;
+                if (lc.c[alt][0] + lc.c[alt][1] + lc.c[alt][2] == 0) continue;
+                pb2_call_record r;
+                if (score_point_allele(lc, position, ref_allele, alt, gapped, cfg, ex.chr_seq, ex.chr_len, r)) {
+                    variant_called = true;
+                    const unsigned long long slot = atomicAdd(out.var_count, 1ull);
+                    if ((int64_t)slot < out.var_capacity) store_record(out.var_records + slot, r);
+                }
+            }
+        }
+        if (out.ref_records != nullptr) {
+            // RegionState.GetAllCandidates: a Reference candidate per position when gVCF; zero-coverage positions only with intervals (:446)
+            bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || any > 0);
+            if (emit) {
+                pb2_call_record r;
+                score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex.chr_seq, ex.chr_len, r);
+                store_record(out.ref_records + locus, r);
+            }
+            out.ref_valid[locus] = emit ? 1 : 0;
+        }
+    }
+}
+
+size_t hot_kernel_smem_bytes(bool collapsed) {
+    const int rows = kNumBins + (collapsed ? kNumCollapsed : 0);
+    return (size_t)rows * kHotThreads * sizeof(uint16_t) + 256 * sizeof(double);
+}
+
+cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
+                              cudaStream_t stream) {
+    if (in.n_tiles == 0) return cudaSuccess;
+    const bool want_q = cfg.want_qsum || cfg.noise_model == 1;
+    const bool coll = cfg.expect_collapsed != 0;
+    const size_t smem = hot_kernel_smem_bytes(coll);
+    const int grid = min(num_sms, (in.n_tiles + kHotThreads / 32 - 1) / (kHotThreads / 32));
+    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+#define PB2_LAUNCH(Q, C)                                                                                                         \
+    do {                                                                                                                         \
+        e = cudaFuncSetAttribute(pileup_count_score_kernel<Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        if (e != cudaSuccess) return e;                                                                                          \
+        pileup_count_score_kernel<Q, C><<<grid, kHotThreads, smem, stream>>>(in, ex, out, cfg, tile_counter);                     \
+    } while (0)
+    if (want_q && coll) PB2_LAUNCH(true, true);
+    else if (want_q) PB2_LAUNCH(true, false);
+    else if (coll) PB2_LAUNCH(false, true);
+    else PB2_LAUNCH(false, false);
+#undef PB2_LAUNCH
+    return cudaGetLastError();
+}
+
+}  // namespace pb2

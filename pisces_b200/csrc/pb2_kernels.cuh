@@ -1,0 +1,78 @@
+// Kernels of the per-locus hot path (sm_100a). See DESIGN.md for the data layout and the roofline of each kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pisces_b200.h"
+
+namespace pb2 {
+
+constexpr int kNumAlleles = 6;
+constexpr int kNumDirs = 3;
+constexpr int kAnchorK = 5;                 // TrackedAnchorSize
+constexpr int kNumAnchors = 2 * kAnchorK + 1;
+constexpr int kNumBins = kNumAlleles * kNumDirs * kNumAnchors;  // 198 = RegionState._alleleCounts[pos,...]
+constexpr int kNumCollapsed = 8;
+constexpr int kTileLoci = 32;               // loci per tile = lanes per warp
+constexpr int kChunk = 16;                  // entries per lane per step = one 16-byte load per plane
+constexpr int kHotThreads = 512;            // one persistent CTA per SM, thread-private histograms in shared memory
+
+// Scalars the kernels need from pb2_config (validated / derived on the host, Config semantics of VariantCallingParameters.Validate).
+struct DeviceConfig {
+    int min_bq;
+    int noise_level;
+    int noise_model;
+    float min_frequency, min_frequency_filter, target_lod, variant_freq_filter;
+    int max_vq, min_vq, vq_filter, max_gq, min_gq, low_gq_filter, min_coverage, low_depth_filter;
+    int rmxn_max_len, rmxn_min_reps;
+    float rmxn_freq_limit;
+    float sb_acceptance;
+    int sb_model, filter_single_strand;
+    float no_call_filter;
+    int output_gvcf, expect_stitched, expect_collapsed, have_intervals, want_qsum;
+};
+
+// Device-resident, tile-interleaved pileup ("PTILE32").
+struct TilePileup {
+    const uint8_t* code;
+    const uint8_t* qual;
+    const uint8_t* anch;
+    const int64_t* tile_base;   // [n_tiles] first byte of the tile in each plane (multiple of 16)
+    const int32_t* depth;       // [n_loci]
+    const uint8_t* ref_base;    // [n_loci] ASCII
+    const int32_t* positions;   // [n_loci] or nullptr
+    int32_t first_position;
+    int64_t n_loci;
+    int32_t n_tiles;
+};
+
+struct HotOutputs {
+    pb2_call_record* ref_records;   // [n_loci] dense reference stream (gVCF) or nullptr
+    uint8_t* ref_valid;             // [n_loci]
+    pb2_call_record* var_records;   // compacted variant stream
+    unsigned long long* var_count;
+    int64_t var_capacity;
+    uint32_t* exc_entries;          // flagged mismatching entries: {locus_index, code | qual<<8 | anchor<<16}
+    unsigned long long* exc_count;
+    int64_t exc_capacity;
+    int32_t* counts_out;            // optional [n_loci][198] parity dump (pb2_get_counts); nullptr on the hot path
+    int32_t* collapsed_out;         // optional [n_loci][8]
+};
+
+struct HotInputsExtra {
+    const int32_t* gapped_ref;      // [n_loci] or nullptr (RegionState._gappedMnvReferenceCounts)
+    const uint8_t* locus_has_variant;  // [n_loci] or nullptr: a non-point variant was called at this position (ref pruning, AlleleCaller.cs:146-147)
+    const uint8_t* chr_seq;         // upper-case chromosome (RMxN), or nullptr
+    int64_t chr_len;
+};
+
+size_t hot_kernel_smem_bytes(bool collapsed);
+cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
+                              cudaStream_t stream);
+
+// CSR -> PTILE32 staging
+cudaError_t launch_tile_layout(const int64_t* csr_offsets, int64_t n_loci, int32_t* depth, int64_t* tile_chunks /*[n_tiles]*/, cudaStream_t stream);
+cudaError_t launch_tile_scatter(const int64_t* csr_offsets, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci,
+                                const int64_t* tile_base, uint8_t* tcode, uint8_t* tqual, uint8_t* tanch, cudaStream_t stream);
+cudaError_t exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* temp, size_t temp_bytes, size_t* temp_needed, cudaStream_t stream);
+
+}  // namespace pb2

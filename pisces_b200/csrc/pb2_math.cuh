@@ -1,0 +1,253 @@
+// Device-side scoring arithmetic for the per-locus hot path. Compiled with --fmad=false: the reference's C# evaluates every
+// operation separately in IEEE double / single precision, and several steps are deliberately mixed-precision.
+//
+// What each block reproduces (reference @ /root/reference):
+//   incomplete gamma "Poisson.Cdf"                   src/lib/Pisces.Calculators/stats/Poisson.cs:16-128
+//   MathNet.Numerics 4.5.1 GammaLowerRegularized/GammaLn/FactorialLn (NuGet dep; arithmetic taken from the IL of the shipped
+//   MathNet.Numerics.dll, see oracle/tools/il_dump.py)  call sites src/lib/Pisces.Calculators/VariantQualityCalculator.cs:36-47
+//   variant q-score                                  VariantQualityCalculator.cs:11-65
+//   strand bias                                      src/lib/Pisces.Calculators/StrandBiasCalculator.cs:21-105,137-231
+//   somatic genotype + GQ                            src/lib/Pisces.Genotyping/Somatic/SomaticGenotyper.cs:65-100, SomaticGenotypeQualityCalculator.cs:10-48
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace pb2 {
+
+// ---- enums (values = reference ordinals)
+enum : int { AT_A = 0, AT_G = 1, AT_C = 2, AT_T = 3, AT_N = 4, AT_DEL = 5 };
+enum : int { DIR_F = 0, DIR_R = 1, DIR_S = 2 };
+enum : int { CAT_SNV = 0, CAT_INS = 1, CAT_DEL = 2, CAT_MNV = 3, CAT_REF = 4 };
+enum : int { FLT_STRAND_BIAS = 0, FLT_POOL_BIAS, FLT_AMPLICON_BIAS, FLT_LOW_VQ, FLT_LOW_DEPTH, FLT_LOW_VF, FLT_LOW_GQ, FLT_INDEL_REPEAT,
+             FLT_MULTI_ALLELIC, FLT_RMXN, FLT_FORCED_REPORT, FLT_OFF_TARGET, FLT_NO_CALL };
+enum : int { GT_HET_ALT12 = 0, GT_ALT12_NOCALL, GT_HET_ALT_REF, GT_HOM_ALT, GT_HOM_REF, GT_REF_NOCALL, GT_ALT_NOCALL, GT_REF_AND_NOCALL,
+             GT_ALT_AND_NOCALL };
+enum : int { SBM_POISSON = 0, SBM_EXTENDED = 1, SBM_DIPLOID = 2 };
+
+// ---------------------------------------------------------------- Pisces' own regularised upper incomplete gamma (Poisson.cs)
+__device__ __forceinline__ double pisces_lngamma(double a) {
+    if (a >= 700.0)  // LanczCutoff -> Stirling (:125-128)
+        return 0.5 * log(2.0 * 3.141592653589793) + (0.5 + a) * log(a) - a;
+    double tmp = a + 5.5;  // Lanczos (:106-120)
+    tmp = tmp - (a + 0.5) * log(tmp);
+    double ser = 1.000000000190015 + 76.18009172947146 / (a + 1.0);
+    ser -= 86.50532032941678 / (a + 2.0);
+    ser += 24.01409824083091 / (a + 3.0);
+    ser -= 1.231739572450155 / (a + 4.0);
+    ser += 0.001208650973866179 / (a + 5.0);
+    ser -= 5.395239384953E-06 / (a + 6.0);
+    return log(2.506628274631001 * ser / a) - tmp;
+}
+
+// Poisson.Cdf(numOccurrences, lambda) = IncompleteGammaFunction((int)(numOccurrences + 1.0), lambda)   (:26-44)
+static __device__ __noinline__ double pisces_poisson_cdf(double num_occurrences, double x) {
+    const double a = (double)(int)(num_occurrences + 1.0);
+    if ((x < 0) || (a <= 0)) return -1.0;
+    const double g = pisces_lngamma(a);
+    if (x >= a + 1.0) {  // Lentz continued fraction (:49-74), Itmax 300, Epsilon 1e-20, Fpmin 1e-50
+        double b = x + 1.0 - a;
+        double c = 1.0 / 1.0E-50;
+        double d = 1.0 / b;
+        double h = d;
+        int i;
+        for (i = 1; i <= 300; i++) {
+            double an = i * (a - i);
+            b += 2.0;
+            d = an * d + b;
+            if (fabs(d) < 1.0E-50) d = 1.0E-50;
+            c = b + an / c;
+            if (fabs(c) < 1.0E-50) c = 1.0E-50;
+            d = 1.0 / d;
+            double del = d * c;
+            h *= del;
+            if (fabs(del - 1.0) < 1.0E-20) break;
+        }
+        if (i > 300) return -1.0;
+        return exp(a * log(x) - x - g) * h;
+    }
+    // series (:76-101)
+    if (x == 0.0) return 1.0 - 0.0;
+    double ap = a;
+    double sum = 1.0 / a;
+    double del = sum;
+    double gs = -1.0;
+    for (int i = 1; i <= 300; i++) {
+        ap += 1.0;
+        del *= x / ap;
+        sum += del;
+        if (fabs(del) < fabs(sum) * 1.0E-20) {
+            gs = sum * exp(a * log(x) - x - g);
+            break;
+        }
+    }
+    if (gs < 0) return gs;
+    return 1.0 - gs;
+}
+
+// ---------------------------------------------------------------- MathNet.Numerics 4.5.1 (IL of the shipped dll)
+__device__ __forceinline__ double mathnet_gamma_ln(double z) {  // SpecialFunctions::GammaLn, z >= 0.5 branch only (callers pass z >= 1)
+    const double dk[11] = {2.4857408913875355e-05, 1.0514237858172197,   -3.4568709722201625,  4.512277094668948,
+                           -2.9828522532357664,    1.056397115771267,    -0.19542877319164587, 0.01709705434044412,
+                           -0.0005719261174043057, 4.633994733599057e-06, -2.7199490848860772e-09};
+    double s = dk[0];
+#pragma unroll
+    for (int i = 1; i <= 10; i++) s += dk[i] / (z + (double)i - 1.0);
+    return log(s) + 0.6207822376352452 + ((z - 0.5) * log((z - 0.5 + 10.900511) / 2.718281828459045));
+}
+
+__device__ __forceinline__ double mathnet_factorial_ln(int x) {  // SpecialFunctions::FactorialLn; cache f[i] = f[i-1]*i, 171 entries
+    if (x <= 1) return 0.0;
+    if (x < 171) {
+        double f = 1.0;
+        for (int i = 2; i <= x; i++) f = f * (double)i;  // same left-to-right product as the cache
+        return log(f);
+    }
+    return mathnet_gamma_ln((double)x + 1.0);
+}
+
+static __device__ __noinline__ double mathnet_gamma_lower_regularized(double a, double x) {  // SpecialFunctions::GammaLowerRegularized
+    if (fabs(a) < 10 * 1.1102230246251565e-16) return 1.0;
+    if (fabs(x) < 10 * 1.1102230246251565e-16) return 0.0;
+    const double ax = (a * log(x)) - x - mathnet_gamma_ln(a);
+    if (ax < -709.782712893384) return a < x ? 1.0 : 0.0;
+    if (x <= 1 || x <= a) {
+        double r2 = a, c2 = 1, ans2 = 1;
+        do {
+            r2 = r2 + 1;
+            c2 = c2 * x / r2;
+            ans2 += c2;
+        } while ((c2 / ans2) > 1e-15);
+        return exp(ax) * ans2 / a;
+    }
+    int c = 0;
+    double y = 1 - a;
+    double z = x + y + 1;
+    double p3 = 1, q3 = x, p2 = x + 1, q2 = z * x;
+    double ans = p2 / q2;
+    double error;
+    do {
+        c++;
+        y += 1;
+        z += 2;
+        double yc = y * c;
+        double p = (p2 * z) - (p3 * yc);
+        double q = (q2 * z) - (q3 * yc);
+        if (q != 0) {
+            double nextans = p / q;
+            error = fabs((ans - nextans) / nextans);
+            ans = nextans;
+        } else {
+            error = 1;
+        }
+        p3 = p2; p2 = p; q3 = q2; q2 = q;
+        if (fabs(p) > 4503599627370496.0) {
+            p3 *= 2.220446049250313e-16; p2 *= 2.220446049250313e-16; q3 *= 2.220446049250313e-16; q2 *= 2.220446049250313e-16;
+        }
+    } while (error > 1e-15);
+    return 1.0 - (exp(ax) * ans);
+}
+
+// ---------------------------------------------------------------- VariantQualityCalculator.cs
+// MathOperations.QtoP(double q) = Math.Pow(10, -1 * q / 10f): q is double there, so the division is in double (MathOperations.cs:7-10)
+__device__ __forceinline__ double q_to_p(double q) { return pow(10.0, -1 * q / 10.0); }
+
+__device__ __forceinline__ double raw_poisson_qscore(int call_count, int coverage, int noise_level) {  // :27-52
+    const double error_rate = q_to_p((double)noise_level);
+    const double k_minus_one = call_count - 1;
+    const double k = call_count;
+    const double lambda = error_rate * coverage;
+    // Poisson(lambda).CumulativeDistribution(k-1) = 1 - GammaLowerRegularized(k, lambda); keep the double cancellation
+    const double cdf = 1.0 - mathnet_gamma_lower_regularized(k_minus_one + 1.0, lambda);
+    const double p_value = 1 - cdf;
+    if (p_value > 0) return -10 * log10(p_value);
+    const double A = -lambda + (double)(int)k_minus_one * log(lambda) - mathnet_factorial_ln((int)k_minus_one);  // ProbabilityLn
+    const double correction = (k - lambda) / k;
+    return -10.0 * (A - log(2.0 * correction)) / log(10.0);
+}
+__device__ __forceinline__ int poisson_qscore(int call_count, int coverage, int noise_level, int max_q) {  // :54-65
+    if ((call_count <= 0) || (coverage <= 0)) return 0;
+    double q = fmin((double)max_q, raw_poisson_qscore(call_count, coverage, noise_level));
+    q = fmax(q, 0.0);
+    return (int)rint(q);  // Math.Round: half to even
+}
+
+// ---------------------------------------------------------------- StrandBiasCalculator.cs
+struct SbStats { double fn, fp, vg, coverage, support; };
+
+__device__ __forceinline__ SbStats sb_create_stats(double support, double coverage, double noise, int model) {  // :137-148,175-231 (non-diploid)
+    SbStats s;
+    s.support = support;
+    s.coverage = coverage;
+    const double min_detectable = noise;  // model != Diploid: minDetectableSNP = noiseFreq
+    if (support == 0) {
+        if (model == SBM_POISSON) { s.fp = 1; s.vg = 0; s.fn = 0; }
+        else { s.vg = pow(1 - min_detectable, coverage); s.fp = 1 - s.vg; s.fn = s.vg; }
+    } else {
+        s.vg = fmax(0.0, pisces_poisson_cdf(support - 1, coverage * noise));
+        s.fp = fmax(0.0, 1 - s.vg);
+        s.fn = 0.0;  // ChanceFalseNeg feeds nothing downstream of the record (StrandBiasStats only); computed on demand by the stats API
+    }
+    return s;
+}
+
+struct SbResult { double bias, gatk; bool acceptable, var_both, cov_both; };
+
+__device__ __forceinline__ SbResult strand_bias(const int cov[3], const int sup[3], int q_noise, double acceptance, int model) {  // :21-72,89-105
+    const double noise = pow(10.0, (double)((float)(-1 * q_noise) / 10.0f));  // float exponent (:32)
+    const SbStats o = sb_create_stats(sup[0] + sup[1] + sup[2], cov[0] + cov[1] + cov[2], noise, model);
+    const SbStats f = sb_create_stats(sup[0] + sup[2] / 2, cov[0] + cov[2] / 2, noise, model);
+    const SbStats r = sb_create_stats(sup[1] + sup[2] / 2, cov[1] + cov[2] / 2, noise, model);
+    double fb = (f.vg * r.fp) / o.vg;
+    double rb = (r.vg * f.fp) / o.vg;
+    if (o.vg == 0) { fb = 1; rb = 1; }
+    SbResult res;
+    double p = (isnan(fb) || isnan(rb)) ? nan("") : fmax(fb, rb);  // Math.Max propagates NaN
+    res.bias = p;
+    res.gatk = 10 * log10(p);
+    res.cov_both = (f.coverage > 0) && (r.coverage > 0);
+    res.var_both = (f.support > 0) && (r.support > 0);
+    if (!res.cov_both) { res.bias = 0; res.gatk = -INFINITY; }
+    res.acceptable = res.bias < acceptance;
+    return res;
+}
+
+// ---------------------------------------------------------------- CalledAllele.Frequency / RefFrequency (CalledAllele.cs:49-52,123-126): float
+__device__ __forceinline__ float allele_frequency(int support, int total) {
+    if (total == 0) return 0.0f;
+    return fminf((float)support / (float)total, 1.0f);
+}
+
+// ---------------------------------------------------------------- SomaticGenotyper.cs:65-100
+__device__ __forceinline__ int somatic_genotype(bool is_ref, int total_cov, float freq, float ref_freq, float min_freq_filter, int min_depth) {
+    if (total_cov < min_depth) return is_ref ? GT_REF_NOCALL : GT_ALT_NOCALL;
+    if (!is_ref) {
+        if (ref_freq < min_freq_filter) {
+            if ((1 - freq) > min_freq_filter) return GT_ALT_AND_NOCALL;
+            return GT_HOM_ALT;
+        }
+        return GT_HET_ALT_REF;
+    }
+    if (freq < min_freq_filter) return GT_REF_NOCALL;
+    if ((1 - freq) > min_freq_filter) return GT_REF_AND_NOCALL;
+    return GT_HOM_REF;
+}
+// SomaticGenotypeQualityCalculator.cs:10-48
+__device__ __forceinline__ int somatic_gq(int genotype, int vq, int total_cov, float freq, float target_lod, int min_gq, int max_gq) {
+    double raw = vq;
+    const bool nocall = genotype == GT_ALT12_NOCALL || genotype == GT_ALT_NOCALL || genotype == GT_REF_NOCALL;
+    if (total_cov == 0 || nocall) return min_gq;
+    if (genotype == GT_HOM_REF || genotype == GT_HOM_ALT) {
+        const double p1 = q_to_p((double)vq);
+        const float non_allele_obs = (1.0f - freq) * (float)total_cov;
+        const float expected = target_lod * (float)total_cov;
+        if (non_allele_obs >= expected) return min_gq;
+        const double p2 = pisces_poisson_cdf((double)non_allele_obs, (double)expected);
+        raw = -10 * log10(p1 + p2);
+    }
+    double q = fmin((double)max_gq, raw);
+    q = fmax(q, (double)min_gq);
+    return (int)rint(q);
+}
+
+}  // namespace pb2

@@ -1,0 +1,205 @@
+// Read expansion (K0): reads (struct of arrays) -> locus-major pileup entries in CSR form, on the device.
+// One thread walks one read's CIGAR exactly as RegionStateManager.AddAlleleCounts does
+// (src/lib/Pisces.Processing/RegionState/RegionStateManager.cs:118-220) and produces one entry per AddAlleleCount call; the SNV
+// candidate flags follow CandidateVariantFinder (src/lib/Pisces.Domain/Logic/CandidateVariantFinder.cs:90-203,496-553) for CallMNVs=false.
+#include "pb2_kernels.cuh"
+#include "pb2_math.cuh"
+
+namespace pb2 {
+
+struct ReadsView {
+    int32_t n_reads;
+    const int32_t* pos0;
+    const uint16_t* flag;
+    const int64_t* cigar_off;
+    const uint32_t* cigar;
+    const int64_t* seq_off;
+    const uint8_t* bases;
+    const uint8_t* quals;
+    const uint8_t* base_dirs;
+    const uint8_t* collapsed;
+};
+
+struct RegionView {
+    int32_t lo, hi;                 // staged reference positions [lo, hi] (1-based, inclusive)
+    const int32_t* index_of_pos;    // [hi-lo+1] locus index or -1 (nullptr: index = pos - lo)
+    const uint8_t* chr;             // chromosome, may be nullptr
+    int64_t chr_len;
+    int min_bq;
+    int expect_collapsed;
+};
+
+__device__ __forceinline__ bool op_ref_span(int op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }   // M D N = X  (BamCommon.cs:560-573)
+__device__ __forceinline__ bool op_read_span(int op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }  // M I S = X  (:575-588)
+
+// RegionStateManager.GetAnchorType (:83-116), K = 5
+__device__ __forceinline__ int anchor_type(int end_pos, int base_pos, int start_pos) {
+    const int left = base_pos - start_pos, right = end_pos - base_pos;
+    if (left >= right) return right >= kAnchorK ? kAnchorK : kNumAnchors - right - 1;
+    return left >= kAnchorK ? kAnchorK : left;
+}
+// ReadExtentions.GetReadCollapsedType (Read.cs:17-64) from the per-read summary byte; returns type+1 or 0
+__device__ __forceinline__ int collapsed_code(int cbyte, int dir) {
+    if (!(cbyte & 1)) return 0;
+    if (cbyte & 2) return (dir == DIR_S ? 0 : 1) + 1;                // DuplexStitched / DuplexNonStitched
+    const int pd = (cbyte >> 2) & 3;
+    if (pd == 1) return (dir == DIR_S ? 4 : 5) + 1;                  // SimplexForward(Non)Stitched
+    if (pd == 2) return (dir == DIR_S ? 6 : 7) + 1;                  // SimplexReverse(Non)Stitched
+    return 0;
+}
+
+// Walks one read; calls emit(position, code, qual, anchor_byte) once per pileup entry.
+template <class Emit>
+__device__ void walk_read(const ReadsView& rv, const RegionView& rg, int r, Emit emit) {
+    const int64_t c0 = rv.cigar_off[r], c1 = rv.cigar_off[r + 1];
+    const int64_t s0 = rv.seq_off[r];
+    const int read_len = (int)(rv.seq_off[r + 1] - s0);
+    const int n_ops = (int)(c1 - c0);
+    if (n_ops == 0) return;
+    const int start_pos = rv.pos0[r] + 1;                                  // Read.Position
+    int ref_span = 0;
+    for (int i = 0; i < n_ops; i++) { const uint32_t c = rv.cigar[c0 + i]; if (op_ref_span(c & 15)) ref_span += (int)(c >> 4); }
+    const int end_pos = rv.pos0[r] + ref_span;                             // Read.EndPosition (Read.cs:88-91)
+    const bool reverse = (rv.flag[r] & 0x10) != 0;
+    const int cbyte = (rg.expect_collapsed && rv.collapsed) ? rv.collapsed[r] : 0;
+    const uint8_t* bases = rv.bases + s0;
+    const uint8_t* quals = rv.quals + s0;
+    const uint8_t* dirs = rv.base_dirs ? rv.base_dirs + s0 : nullptr;
+    auto dir_at = [&](int i) -> int { return dirs ? dirs[i] : (reverse ? DIR_R : DIR_F); };
+    auto del_q = [&](int idx) -> int {  // CandidateVariantFinder.CheckDeletionQuality (:294-320): min of the flanking qualities
+        if (read_len == 0) return -1;
+        const int after = idx < read_len ? quals[idx] : quals[idx - 1];
+        const int before = idx > 0 ? quals[idx - 1] : after;
+        return min(before, after);
+    };
+    // terminal deletion bookkeeping (:127-137)
+    const int last_op = (int)(rv.cigar[c1 - 1] & 15);
+    const int prev_op = n_ops >= 2 ? (int)(rv.cigar[c1 - 2] & 15) : -1;
+    const bool ends_in_del = last_op == 2;
+    const bool ends_in_del_before_clip = prev_op == 2 && last_op == 4;
+    int del_len = 0, len_before_del = read_len;
+    if (ends_in_del || ends_in_del_before_clip) {
+        del_len = (int)(ends_in_del_before_clip ? (rv.cigar[c1 - 2] >> 4) : (rv.cigar[c1 - 1] >> 4));
+        len_before_del = ends_in_del_before_clip ? read_len - (int)(rv.cigar[c1 - 1] >> 4) : read_len;
+    }
+    // open-end annotation (:496-553): first / last non-soft-clip operation
+    int first_op = (int)(rv.cigar[c0] & 15);
+    if (first_op == 4 && n_ops >= 2) first_op = (int)(rv.cigar[c0 + 1] & 15);
+    int last_nonclip = last_op;
+    if (last_nonclip == 4 && n_ops >= 2) last_nonclip = prev_op;
+    int max_mapped = -1;
+    {
+        int rp = start_pos;
+        for (int i = 0; i < n_ops; i++) {
+            const uint32_t c = rv.cigar[c0 + i];
+            const int op = c & 15, len = (int)(c >> 4);
+            if (op_ref_span(op)) { if (op_read_span(op) && len > 0) max_mapped = rp + len - 1; rp += len; }
+        }
+    }
+
+    int read_idx = 0, ref_pos = start_pos, last_position = start_pos - 1;
+    for (int oi = 0; oi < n_ops; oi++) {
+        const uint32_t c = rv.cigar[c0 + oi];
+        const int op = c & 15, len = (int)(c >> 4);
+        const bool rs = op_read_span(op), fs = op_ref_span(op);
+        if (rs) {
+            for (int k = 0; k < len; k++, read_idx++) {
+                const int dir = dir_at(read_idx);
+                if (ends_in_del_before_clip && read_idx == len_before_del) {      // (:148-159)
+                    const int dq = del_q(read_idx);
+                    for (int j = 1; j < del_len + 1; j++)
+                        emit(j + last_position, AT_DEL | (dir << 3), dq, (kNumAnchors - 1) | (collapsed_code(cbyte, dir) << 4));
+                }
+                if (!fs) continue;                                               // I / S: not mapped to the reference
+                const int position = ref_pos++;
+                const int an = anchor_type(end_pos, position, start_pos);
+                const int cc = collapsed_code(cbyte, dir) << 4;
+                if (position > last_position + 1) {                              // deletion (or N skip) before this base (:170-177)
+                    const int dq = del_q(read_idx);
+                    for (int j = last_position + 1; j < position; j++) emit(j, AT_DEL | (dir << 3), dq, an | cc);
+                }
+                const uint8_t b = bases[read_idx];
+                const int allele = b == 'A' ? AT_A : b == 'C' ? AT_C : b == 'G' ? AT_G : b == 'T' ? AT_T : AT_N;
+                int code = allele | (dir << 3);
+                // SNV candidate flags for CallMNVs=false (CandidateVariantFinder.cs:90-168): only 'M' operations inside the chromosome raise candidates
+                const bool in_chr = rg.chr == nullptr || position <= rg.chr_len;
+                if (op != 0 || !in_chr) code |= PB2_ENTRY_NO_CANDIDATE;
+                else {
+                    // open on the right: the next base of this operation exists and is unusable (low quality, N, or reference N) -> FlushVariant(..., openRight=true)
+                    if (k + 1 < len) {
+                        const int nq = quals[read_idx + 1];
+                        const uint8_t nb = bases[read_idx + 1];
+                        const bool nb_n = !(nb == 'A' || nb == 'C' || nb == 'G' || nb == 'T');
+                        bool nref_n = false, n_in = true;
+                        if (rg.chr) {
+                            n_in = position + 1 <= rg.chr_len;
+                            if (n_in) { const uint8_t rb = rg.chr[position]; nref_n = !(rb == 'A' || rb == 'C' || rb == 'G' || rb == 'T'); }
+                        }
+                        if (n_in && (nq < rg.min_bq || nb_n || nref_n)) code |= PB2_ENTRY_OPEN_RIGHT;
+                    }
+                    if (first_op == 0 && position == start_pos) code |= PB2_ENTRY_OPEN_LEFT;
+                    if (last_nonclip == 0 && position == max_mapped) code |= PB2_ENTRY_OPEN_RIGHT;
+                }
+                emit(position, code, quals[read_idx], an | cc);
+                last_position = position;
+            }
+        } else if (fs) {
+            ref_pos += len;
+        }
+    }
+    if (ends_in_del) {                                                           // (:195-210)
+        const int dq = del_q(read_len - 1);
+        const int dir = read_len > 0 ? dir_at(read_len - 1) : DIR_F;
+        if (read_len > 0)
+            for (int j = 1; j < del_len + 1; j++) emit(j + last_position, AT_DEL | (dir << 3), dq, (kNumAnchors - 1) | (collapsed_code(cbyte, dir) << 4));
+    }
+}
+
+__device__ __forceinline__ int64_t locus_index(const RegionView& rg, int position) {
+    if (position < rg.lo || position > rg.hi) return -1;
+    return rg.index_of_pos ? (int64_t)rg.index_of_pos[position - rg.lo] : (int64_t)(position - rg.lo);
+}
+
+__global__ void reads_count_kernel(ReadsView rv, RegionView rg, unsigned int* __restrict__ depth) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rv.n_reads) return;
+    walk_read(rv, rg, r, [&](int position, int, int, int) {
+        const int64_t li = locus_index(rg, position);
+        if (li >= 0) atomicAdd(depth + li, 1u);
+    });
+}
+__global__ void reads_emit_kernel(ReadsView rv, RegionView rg, const int64_t* __restrict__ offsets, unsigned int* __restrict__ cursor, uint8_t* __restrict__ code,
+                                  uint8_t* __restrict__ qual, uint8_t* __restrict__ anch) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rv.n_reads) return;
+    walk_read(rv, rg, r, [&](int position, int c, int q, int a) {
+        const int64_t li = locus_index(rg, position);
+        if (li < 0) return;
+        const int64_t o = offsets[li] + (int64_t)atomicAdd(cursor + li, 1u);
+        code[o] = (uint8_t)c;
+        qual[o] = (uint8_t)max(q, 0);
+        anch[o] = (uint8_t)a;
+    });
+}
+__global__ void depth_to_i64_kernel(const unsigned int* __restrict__ depth, int64_t* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = depth[i]; else if (i == n) out[i] = 0;
+}
+
+cudaError_t launch_reads_count(const ReadsView& rv, const RegionView& rg, unsigned int* depth, cudaStream_t st) {
+    if (rv.n_reads == 0) return cudaSuccess;
+    reads_count_kernel<<<(rv.n_reads + 127) / 128, 128, 0, st>>>(rv, rg, depth);
+    return cudaGetLastError();
+}
+cudaError_t launch_reads_emit(const ReadsView& rv, const RegionView& rg, const int64_t* offsets, unsigned int* cursor, uint8_t* code, uint8_t* qual, uint8_t* anch,
+                              cudaStream_t st) {
+    if (rv.n_reads == 0) return cudaSuccess;
+    reads_emit_kernel<<<(rv.n_reads + 127) / 128, 128, 0, st>>>(rv, rg, offsets, cursor, code, qual, anch);
+    return cudaGetLastError();
+}
+cudaError_t launch_depth_to_i64(const unsigned int* depth, int64_t* out, int64_t n, cudaStream_t st) {
+    depth_to_i64_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(depth, out, n);
+    return cudaGetLastError();
+}
+
+}  // namespace pb2

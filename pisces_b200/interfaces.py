@@ -1,0 +1,313 @@
+"""Host-side mirror of the reference's plug-in interfaces for the hot path, over the C ABI.
+
+  GpuStateManager  ~ IStateManager : IAlleleSource   (src/lib/Pisces.Processing/Interfaces/IStateManager.cs:8-15,
+                                                      src/lib/Pisces.Domain/Interfaces/IAlleleSource.cs:8-26)
+  GpuAlleleCaller  ~ IAlleleCaller                   (src/exe/Pisces/Interfaces/IAlleleCaller.cs:8-13)
+  CalledAllele     ~ CalledAllele                    (src/lib/Pisces.Domain/Models/Alleles/CalledAllele.cs)
+  Read             ~ Read                            (src/lib/Pisces.Domain/Models/Read.cs), the fields the path consumes
+
+Method names and argument meaning follow the reference so that tests read like the reference's own tests. All compute happens in
+libpisces_b200.so on the GPU; this module only marshals.
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _native as N
+
+
+class PiscesB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pisces_b200 error {code}: {msg}")
+        self.code = code
+
+
+class AlleleType(enum.IntEnum):      # Types/AlleleType.cs:5-10
+    A = 0
+    G = 1
+    C = 2
+    T = 3
+    N = 4
+    Deletion = 5
+
+
+class DirectionType(enum.IntEnum):   # Types/DirectionType.cs
+    Forward = 0
+    Reverse = 1
+    Stitched = 2
+
+
+class AlleleCategory(enum.IntEnum):  # Types/AlleleCategory.cs
+    Snv = 0
+    Insertion = 1
+    Deletion = 2
+    Mnv = 3
+    Reference = 4
+
+
+class FilterType(enum.IntEnum):      # Types/FilterType.cs
+    StrandBias = 0
+    PoolBias = 1
+    AmpliconBias = 2
+    LowVariantQscore = 3
+    LowDepth = 4
+    LowVariantFrequency = 5
+    LowGenotypeQuality = 6
+    IndelRepeatLength = 7
+    MultiAllelicSite = 8
+    RMxN = 9
+    ForcedReport = 10
+    OffTarget = 11
+    NoCall = 12
+
+
+class Genotype(enum.IntEnum):        # Types/Genotype.cs
+    HeterozygousAlt1Alt2 = 0
+    Alt12LikeNoCall = 1
+    HeterozygousAltRef = 2
+    HomozygousAlt = 3
+    HomozygousRef = 4
+    RefLikeNoCall = 5
+    AltLikeNoCall = 6
+    RefAndNoCall = 7
+    AltAndNoCall = 8
+
+
+VariantCallerConfig = N.Config
+
+
+def make_config(**kw):
+    """pb2_default_config() + overrides (field names of pb2_config)."""
+    c = N.Config()
+    N.load().pb2_default_config(C.byref(c))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(f"pb2_config has no field {k}")
+        setattr(c, k, v)
+    return c
+
+
+_CIGAR_OPS = "MIDNSHP=X"
+
+
+class Read:
+    """The fields of Pisces.Domain.Models.Read the path consumes. position is the 1-based Read.Position."""
+
+    def __init__(self, position, sequence, cigar, qualities=30, flag=0, base_directions=None, collapsed=None):
+        self.position = position
+        self.sequence = sequence
+        if isinstance(cigar, str):
+            ops, num = [], ""
+            for ch in cigar:
+                if ch.isdigit():
+                    num += ch
+                else:
+                    ops.append((int(num) << 4) | _CIGAR_OPS.index(ch))
+                    num = ""
+            cigar = ops
+        self.cigar = list(cigar)
+        self.qualities = [qualities] * len(sequence) if isinstance(qualities, int) else list(qualities)
+        self.flag = flag
+        self.base_directions = base_directions   # Read.SequencedBaseDirectionMap or None
+        self.collapsed = collapsed               # summary byte (see pb2_read_batch.collapsed) or None
+
+
+class CalledAllele:
+    """View of one pb2_call_record with the reference's property names."""
+
+    def __init__(self, rec):
+        self._r = rec
+        self.ReferencePosition = int(rec["position"])
+        self.Type = AlleleCategory(int(rec["type"]))
+        self.Genotype = Genotype(int(rec["genotype"]))
+        self.GenotypeQscore = int(rec["genotype_qscore"])
+        self.VariantQscore = int(rec["variant_qscore"])
+        self.Filters = [FilterType(i) for i in range(13) if int(rec["filters"]) >> i & 1]
+        self.NoiseLevelApplied = int(rec["noise_level"])
+        self.TotalCoverage = int(rec["total_coverage"])
+        self.EstimatedCoverageByDirection = [int(x) for x in rec["coverage_by_direction"]]
+        self.SupportByDirection = [int(x) for x in rec["support_by_direction"]]
+        self.AlleleSupport = int(rec["allele_support"])
+        self.ReferenceSupport = int(rec["reference_support"])
+        self.NumNoCalls = int(rec["num_no_calls"])
+        self.FractionNoCalls = float(rec["fraction_no_calls"])
+        self.SumOfBaseQuality = float(rec["sum_base_quality"])
+        self.BiasScore = float(rec["bias_score"])
+        self.GATKBiasScore = float(rec["gatk_bias_score"])
+        f = int(rec["sb_flags"])
+        self.BiasAcceptable, self.VarPresentOnBothStrands, self.CovPresentOnBothStrands = bool(f & 1), bool(f & 2), bool(f & 4)
+        rl, al, ab = int(rec["ref_len"]), int(rec["alt_len"]), int(rec["allele_bytes"])
+        raw = ab.to_bytes(4, "little")
+        self.ReferenceAllele = raw[:rl].decode() if rl + al <= 4 else None
+        self.AlternateAllele = raw[rl:rl + al].decode() if rl + al <= 4 else None
+
+    @property
+    def Frequency(self):  # CalledAllele.cs:49-52 (float32 arithmetic)
+        if self.TotalCoverage == 0:
+            return np.float32(0)
+        return min(np.float32(self.AlleleSupport) / np.float32(self.TotalCoverage), np.float32(1))
+
+    def __repr__(self):
+        return (f"<{self.Type.name} {self.ReferencePosition} {self.ReferenceAllele}>{self.AlternateAllele} Q{self.VariantQscore} "
+                f"GQ{self.GenotypeQscore} {self.Genotype.name} DP{self.TotalCoverage} AD{self.AlleleSupport} {[x.name for x in self.Filters]}>")
+
+
+class GpuStateManager:
+    """IStateManager over libpisces_b200.so: buffers reads / pileups on the device; counts live in HBM until called."""
+
+    def __init__(self, config=None, chr_name="chr1", chr_sequence=None, intervals=None):
+        self._L = N.load()
+        self.config = config if config is not None else make_config()
+        h = C.c_void_p()
+        rc = self._L.pb2_create(C.byref(self.config), C.byref(h))
+        if rc != 0:
+            raise PiscesB200Error(rc, self._L.pb2_last_error(None).decode())
+        self._h = h
+        self._keep = []
+        if chr_sequence is not None:
+            seq = chr_sequence.encode() if isinstance(chr_sequence, str) else bytes(chr_sequence)
+            self._chk(self._L.pb2_set_reference(self._h, chr_name.encode(), seq, len(seq)))
+        if intervals is not None:
+            s = np.ascontiguousarray([a for a, _ in intervals], dtype=np.int32)
+            e = np.ascontiguousarray([b for _, b in intervals], dtype=np.int32)
+            self._chk(self._L.pb2_set_intervals(self._h, s.ctypes.data, e.ctypes.data, len(s)))
+
+    # -- plumbing
+    def _chk(self, rc):
+        if rc != 0:
+            raise PiscesB200Error(rc, self._L.pb2_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pb2_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def ExpectStitchedReads(self):
+        return bool(self.config.expect_stitched)
+
+    # -- IStateManager
+    def AddAlleleCounts(self, reads):
+        """IStateManager.AddAlleleCounts(Read) (+ the SNV part of ICandidateVariantFinder.FindCandidates); accepts one Read or a list."""
+        if isinstance(reads, Read):
+            reads = [reads]
+        if not reads:
+            return
+        n = len(reads)
+        pos0 = np.array([r.position - 1 for r in reads], dtype=np.int32)
+        flag = np.array([r.flag for r in reads], dtype=np.uint16)
+        cig_off = np.zeros(n + 1, dtype=np.int64)
+        seq_off = np.zeros(n + 1, dtype=np.int64)
+        for i, r in enumerate(reads):
+            cig_off[i + 1] = cig_off[i] + len(r.cigar)
+            seq_off[i + 1] = seq_off[i] + len(r.sequence)
+        cigar = np.array([c for r in reads for c in r.cigar], dtype=np.uint32)
+        bases = np.frombuffer("".join(r.sequence for r in reads).encode(), dtype=np.uint8)
+        quals = np.array([q for r in reads for q in r.qualities], dtype=np.uint8)
+        has_dirs = any(r.base_directions is not None for r in reads)
+        dirs = None
+        if has_dirs:
+            dirs = np.array([d for r in reads for d in (r.base_directions if r.base_directions is not None
+                                                        else [1 if r.flag & 0x10 else 0] * len(r.sequence))], dtype=np.uint8)
+        has_coll = any(r.collapsed is not None for r in reads)
+        coll = np.array([r.collapsed or 0 for r in reads], dtype=np.uint8) if has_coll else None
+        b = N.ReadBatch(n, pos0.ctypes.data, flag.ctypes.data, cig_off.ctypes.data, cigar.ctypes.data if len(cigar) else None,
+                        seq_off.ctypes.data, bases.ctypes.data if len(bases) else None, quals.ctypes.data if len(quals) else None,
+                        dirs.ctypes.data if dirs is not None else None, coll.ctypes.data if coll is not None else None)
+        if len(cigar) == 0 or len(bases) == 0:
+            raise PiscesB200Error(N_ERR_ARG, "reads without CIGAR or bases")
+        self._chk(self._L.pb2_push_reads(self._h, C.byref(b)))
+
+    def AddPileup(self, offsets, code, qual, anchor, first_position=1, positions=None, ref_bases=None, device=False):
+        """Stage a locus-major pileup (pb2_push_pileup / pb2_push_pileup_device). Arrays are numpy (host) or torch CUDA tensors (device)."""
+        def ptr(a):
+            if a is None:
+                return None
+            return a.data_ptr() if device else np.ascontiguousarray(a).ctypes.data
+        if not device:
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            code, qual, anchor = (np.ascontiguousarray(x, dtype=np.uint8) for x in (code, qual, anchor))
+            if positions is not None:
+                positions = np.ascontiguousarray(positions, dtype=np.int32)
+            if ref_bases is not None:
+                ref_bases = np.ascontiguousarray(ref_bases, dtype=np.uint8)
+        n_loci = (offsets.numel() if device else len(offsets)) - 1
+        p = N.PileupCsr(n_loci, int(first_position), ptr(positions), ptr(offsets), ptr(code), ptr(qual), ptr(anchor), ptr(ref_bases))
+        self._keep = [offsets, code, qual, anchor, positions, ref_bases]
+        self._chk((self._L.pb2_push_pileup_device if device else self._L.pb2_push_pileup)(self._h, C.byref(p)))
+
+    def GetAlleleCounts(self, position0, n):
+        """RegionState._alleleCounts over [position0, position0+n): int32 [n][6][3][11]."""
+        out = np.zeros((n, 6, 3, 11), dtype=np.int32)
+        self._chk(self._L.pb2_get_counts(self._h, position0, n, out.ctypes.data))
+        return out
+
+    def GetAlleleCount(self, position, alleleType, directionType, minAnchor=0, maxAnchor=None, fromEnd=False, symmetric=False):
+        """IAlleleSource.GetAlleleCount (anchor selection per AlleleCountHelper.cs:21-85, evaluated on the 11 device-computed bins)."""
+        bins = self.GetAlleleCounts(position, 1)[0, int(alleleType), int(directionType)]
+        K, NA = 5, 11
+        true_min = min(K, minAnchor)
+        init_max = K
+        if maxAnchor is not None:
+            init_max = K - 1 if maxAnchor >= K else maxAnchor
+        tot = 0
+        if fromEnd:
+            tot += sum(int(bins[NA - i - 1]) for i in range(true_min, init_max + 1))
+            if maxAnchor is None:
+                tot += sum(int(bins[i]) for i in range(true_min if symmetric else 0, init_max))
+        else:
+            tot += sum(int(bins[i]) for i in range(true_min, init_max + 1))
+            if maxAnchor is None:
+                tot += sum(int(bins[i]) for i in range(init_max + 1, NA - true_min if symmetric else NA))
+        return tot
+
+    def DoneProcessing(self):
+        self._chk(self._L.pb2_reset(self._h))
+
+    # -- used by GpuAlleleCaller
+    def _flush(self, up_to):
+        out = C.c_void_p()
+        n = C.c_int64()
+        self._chk(self._L.pb2_flush(self._h, -1 if up_to is None else int(up_to), C.byref(out), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=N.RECORD_DTYPE)
+        buf = (C.c_char * (96 * n.value)).from_address(out.value)
+        return np.frombuffer(buf, dtype=N.RECORD_DTYPE).copy()
+
+    def call_resident(self):
+        n = C.c_int64()
+        self._chk(self._L.pb2_call_resident(self._h, C.byref(n)))
+        return n.value
+
+    def stats(self):
+        a, b, c = C.c_int64(), C.c_double(), C.c_int64()
+        self._chk(self._L.pb2_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(hot_launches=a.value, hot_ms=b.value, total_launches=c.value)
+
+
+N_ERR_ARG = -1
+
+
+class GpuAlleleCaller:
+    """IAlleleCaller: Call(batch, source) -> {position: [CalledAllele, ...]} (SortedList<int, List<CalledAllele>>)."""
+
+    def __init__(self):
+        self.TotalNumCalled = 0
+        self.TotalNumCollapsed = 0
+
+    def Call(self, source, upToPosition=None, raw=False):
+        recs = source._flush(upToPosition)
+        self.TotalNumCalled += len(recs)
+        if raw:
+            return recs
+        out = {}
+        for r in recs:
+            out.setdefault(int(r["position"]), []).append(CalledAllele(r))
+        return out

@@ -1,0 +1,104 @@
+"""Seeded synthetic reads shared by the oracle and the CUDA path (test helper)."""
+import numpy as np
+
+from oracle import binding as ob
+
+BASES = "ACGT"
+
+
+def random_reference(rng, n, n_rate=0.0):
+    seq = rng.choice(list(BASES), size=n)
+    if n_rate > 0:
+        seq[rng.random(n) < n_rate] = "N"
+    return "".join(seq)
+
+
+def make_reads(rng, ref, n_reads, read_len=60, start=1, span=None, snv_rate=0.01, lowq_rate=0.08, n_base_rate=0.005, del_rate=0.05, ins_rate=0.05,
+               clip_rate=0.15, hotspots=None, stitched=False, collapsed=False, sorted_by_pos=True):
+    """Returns a list of dicts: pos (1-based), seq, cigar (string), quals, flag, dirs (or None), coll (or None), xd/xr/xv/xw for the oracle.
+
+    hotspots: {position: (alt_base, fraction)} real variants so that some calls pass the frequency / q-score bars."""
+    span = span or (len(ref) - read_len - 12)
+    reads = []
+    for _ in range(n_reads):
+        pos = int(rng.integers(start, start + span))
+        ops = []
+        r = rng.random()
+        body = read_len
+        lead_clip = int(rng.integers(1, 6)) if rng.random() < clip_rate else 0
+        tail_clip = int(rng.integers(1, 6)) if rng.random() < clip_rate else 0
+        body -= lead_clip + tail_clip
+        if lead_clip:
+            ops.append(("S", lead_clip))
+        if r < del_rate and body > 12:
+            a = int(rng.integers(3, body - 6))
+            ops += [("M", a), ("D", int(rng.integers(1, 4))), ("M", body - a)]
+        elif r < del_rate + ins_rate and body > 12:
+            a = int(rng.integers(3, body - 8))
+            il = int(rng.integers(1, 4))
+            ops += [("M", a), ("I", il), ("M", body - a - il)]
+        else:
+            ops.append(("M", body))
+        if tail_clip:
+            ops.append(("S", tail_clip))
+        seq, rp = [], pos - 1
+        for op, ln in ops:
+            if op == "M":
+                for k in range(ln):
+                    b = ref[rp + k] if rp + k < len(ref) else "A"
+                    p1 = rp + k + 1
+                    if hotspots and p1 in hotspots and rng.random() < hotspots[p1][1]:
+                        b = hotspots[p1][0]
+                    elif rng.random() < snv_rate:
+                        b = BASES[int(rng.integers(0, 4))]
+                    if rng.random() < n_base_rate:
+                        b = "N"
+                    seq.append(b)
+                rp += ln
+            elif op == "D":
+                rp += ln
+            else:  # I, S
+                seq += [BASES[int(rng.integers(0, 4))] for _ in range(ln)]
+        quals = np.where(rng.random(read_len) < lowq_rate, rng.integers(2, 20, read_len), rng.integers(20, 41, read_len)).astype(int).tolist()
+        reverse = bool(rng.random() < 0.5)
+        flag = (0x10 if reverse else 0) | 0x1 | 0x2 | (0x40 if rng.random() < 0.5 else 0x80)
+        rd = dict(pos=pos, seq="".join(seq), cigar="".join(f"{ln}{op}" for op, ln in ops), quals=quals, flag=flag, dirs=None, coll=None,
+                  xd=None, xr=None, xv=None, xw=None)
+        if stitched and rng.random() < 0.6:
+            # XD direction string over the cigar-expanded alignment: F.. S.. R..
+            total = sum(ln for _, ln in ops)
+            a = int(rng.integers(1, total // 2))
+            b = int(rng.integers(1, total - a))
+            rd["xd"] = f"{a}F{b}S{total - a - b}R" if total - a - b > 0 else f"{a}F{b}S"
+            exp = [0] * a + [2] * b + [1] * (total - a - b)
+            dirs, ci = [], 0
+            for op, ln in ops:
+                for _k in range(ln):
+                    if op in "MIS":
+                        dirs.append(exp[ci])
+                    ci += 1
+            rd["dirs"] = dirs
+        if collapsed:
+            xv, xw = int(rng.integers(0, 4)), int(rng.integers(0, 3))
+            xr = ["FR", "RF", "FF"][int(rng.integers(0, 3))]
+            rd.update(xv=xv, xw=xw, xr=xr)
+            rd["coll"] = 1 | (2 if (xv != 0 and xw != 0) else 0) | ({"FR": 1, "RF": 2}.get(xr, 0) << 2)
+        reads.append(rd)
+    if sorted_by_pos:
+        reads.sort(key=lambda r: r["pos"])
+    return reads
+
+
+def to_oracle(rd):
+    return ob.SimpleRead(rd["pos"], rd["seq"], rd["cigar"], rd["quals"], flag=rd["flag"], xd=rd["xd"], xr=rd["xr"], xv=rd["xv"], xw=rd["xw"],
+                         has_tags=any(rd[k] is not None for k in ("xd", "xr", "xv", "xw")))
+
+
+def to_product(rd):
+    import pisces_b200 as pb
+    return pb.Read(rd["pos"], rd["seq"], rd["cigar"], rd["quals"], flag=rd["flag"], base_directions=rd["dirs"], collapsed=rd["coll"])
+
+
+def oracle_cfg_from(**kw):
+    """Oracle config with the same knobs the product config takes (names of po_config)."""
+    return ob.default_config(**kw)
