@@ -61,6 +61,7 @@ struct Segment {   // one staged pileup (pb2_push_pileup*)
     int64_t n_entries = 0;
     // device
     int32_t* depth = nullptr;
+    int32_t* pad = nullptr;
     int64_t* tile_base = nullptr;
     uint8_t *code = nullptr, *qual = nullptr, *anch = nullptr, *ref_base = nullptr;
     int32_t* positions = nullptr;
@@ -170,6 +171,7 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
     if (cfg->ploidy != 0) return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: only the Somatic ploidy model is built (SURVEY 8f rank 3)");
     if (cfg->strand_bias_model == 2) return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: Diploid strand-bias model not built (SURVEY 8f rank 3)");
     if (cfg->tracked_anchor_size != 5) return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: tracked_anchor_size must be 5");
+    if (cfg->min_base_call_quality < 0 || cfg->min_base_call_quality > 127) return fail(nullptr, PB2_ERR_ARG, "pb2_create: min_base_call_quality must be in [0,127]");
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -195,7 +197,7 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
 }
 
 static void free_segment(pb2_handle* h, Segment& s) {
-    void* ptrs[] = {s.depth, s.tile_base, s.code, s.qual, s.anch, s.ref_base, s.positions, s.ref_records, s.ref_valid, s.var_records, s.exc_entries, s.counters};
+    void* ptrs[] = {s.depth, s.pad, s.tile_base, s.code, s.qual, s.anch, s.ref_base, s.positions, s.ref_records, s.ref_valid, s.var_records, s.exc_entries, s.counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     s = Segment();
 }
@@ -290,6 +292,7 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
 
     // per-locus side arrays
     CU(h, cudaMalloc(&s.depth, sizeof(int32_t) * (size_t)p->n_loci));
+    CU(h, cudaMalloc(&s.pad, sizeof(int32_t) * (size_t)p->n_loci));
     CU(h, cudaMalloc(&s.tile_base, sizeof(int64_t) * (size_t)(s.n_tiles + 1)));
     CU(h, cudaMalloc(&s.ref_base, (size_t)p->n_loci));
     const cudaMemcpyKind kind = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -325,7 +328,7 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     CU(h, cudaMalloc(&s.code, pb));
     CU(h, cudaMalloc(&s.qual, pb));
     CU(h, cudaMalloc(&s.anch, pb));
-    CU(h, launch_tile_scatter(d_off, d_code, d_qual, d_anch, p->n_loci, s.tile_base, s.code, s.qual, s.anch, st));
+    CU(h, launch_tile_scatter(d_off, d_code, d_qual, d_anch, p->n_loci, s.tile_base, s.ref_base, h->dcfg.min_bq, s.code, s.qual, s.anch, s.pad, st));
     h->total_launches += 4;
 
     // outputs
@@ -353,7 +356,7 @@ extern "C" int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p) { 
 static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out) {
     cudaStream_t st = h->stream;
     TilePileup in;
-    in.code = s.code; in.qual = s.qual; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.ref_base = s.ref_base;
+    in.code = s.code; in.qual = s.qual; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
     in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles;
     HotInputsExtra ex;
     ex.gapped_ref = nullptr; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len;
@@ -431,6 +434,10 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     if (R.size() == 0) return PB2_OK;
     int32_t lo = INT32_MAX, hi = 0;
     for (size_t i = 0; i < R.size(); i++) { lo = std::min(lo, R.pos0[i] + 1); hi = std::max(hi, R.end_pos[i]); }
+    if (h->have_intervals) {   // interval positions are reported for every position of a block some read touched, covered or not
+        lo = ((lo - 1) / 1000) * 1000 + 1;
+        hi = (int32_t)std::min<int64_t>(((int64_t)(hi - 1) / 1000 + 1) * 1000, INT32_MAX);
+    }
     lo = std::max(lo, cleared_from);
     hi = std::min(hi, cleared_end);
     if (hi < lo) return PB2_OK;

@@ -34,20 +34,28 @@ __global__ void tile_layout_kernel(const int64_t* __restrict__ off, int64_t n_lo
     if ((threadIdx.x & 31) == 0 && (locus / kTileLoci) * (int64_t)kTileLoci < n_loci) tile_chunks[locus / kTileLoci] = (int64_t)chunks * kChunk;
 }
 
-// one warp per tile: lane i copies locus i's entries chunk by chunk into the interleaved position; tail bytes of a locus' last chunk are 0xFF
+// one warp per tile: lane i copies locus i's entries chunk by chunk into the interleaved position. Entries are normalised on the way so
+// that the hot loop is branch-free:
+//   * a Deletion entry below the quality bar is never counted (RegionStateManager.cs:170-177) -> replaced by a PAD entry;
+//   * the tail of a locus' last 16-entry chunk is filled with PAD entries;
+//   * PAD = (code N|Forward, qual 255, anchor 0): it lands in bin [N][Forward][0] and pad[i] of them are subtracted at read-out;
+//   * candidate flags are kept only where they can matter: the base is a usable (q >= minBQ, A/C/G/T) mismatch against an A/C/G/T
+//     reference base. Every flagged entry the hot kernel meets is then a real SNV-candidate exception.
 __global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8_t* __restrict__ code, const uint8_t* __restrict__ qual,
-                                    const uint8_t* __restrict__ anch, int64_t n_loci, const int64_t* __restrict__ tile_base, uint8_t* __restrict__ tcode,
-                                    uint8_t* __restrict__ tqual, uint8_t* __restrict__ tanch) {
+                                    const uint8_t* __restrict__ anch, int64_t n_loci, const int64_t* __restrict__ tile_base, const uint8_t* __restrict__ ref_base,
+                                    int min_bq, uint8_t* __restrict__ tcode, uint8_t* __restrict__ tqual, uint8_t* __restrict__ tanch, int32_t* __restrict__ pad) {
     const int lane = threadIdx.x & 31;
     const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t locus = tile * kTileLoci + lane;
     if (tile * kTileLoci >= n_loci) return;
     int64_t src = 0;
     int d = 0;
-    if (locus < n_loci) { src = off[locus]; d = (int)(off[locus + 1] - src); }
+    int ref_allele = AT_N;
+    if (locus < n_loci) { src = off[locus]; d = (int)(off[locus + 1] - src); ref_allele = allele_of_base(ref_base[locus]); }
     const int nchunks = (d + kChunk - 1) / kChunk;
     const int max_chunks = __reduce_max_sync(0xffffffffu, nchunks);
     int64_t base = tile_base[tile];
+    int npad = nchunks * kChunk - d;
     for (int c = 0; c < max_chunks; c++) {
         const bool active = c < nchunks;
         const unsigned m = __ballot_sync(0xffffffffu, active);
@@ -56,20 +64,30 @@ __global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8
             const int64_t dst = base + (int64_t)slot * kChunk;
             const int n = min(kChunk, d - c * kChunk);
             const int64_t s = src + (int64_t)c * kChunk;
-            const uint8_t* planes_in[3] = {code, qual, anch};
-            uint8_t* planes_out[3] = {tcode, tqual, tanch};
-#pragma unroll
-            for (int p = 0; p < 3; p++) {
-                uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-                for (int k = 0; k < n; k++) {
-                    const uint32_t b = planes_in[p][s + k];
-                    w[k >> 2] = (w[k >> 2] & ~(0xffu << ((k & 3) * 8))) | (b << ((k & 3) * 8));
+            uint32_t wc[4] = {0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u};
+            uint32_t wq[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            uint32_t wa[4] = {0u, 0u, 0u, 0u};
+            for (int k = 0; k < n; k++) {
+                uint32_t cb = code[s + k], qb = qual[s + k], ab = anch[s + k];
+                const int allele = cb & 7;
+                const bool lowq = (int)qb < min_bq;
+                if (allele > AT_DEL || ((cb >> 3) & 3) > DIR_S || (ab & 15) >= kNumAnchors || (allele == AT_DEL && lowq)) {
+                    cb = 0x04; qb = 0xff; ab = 0; npad++;           // not countable: PAD
+                } else if (lowq || allele >= AT_N || ref_allele == AT_N || allele == ref_allele) {
+                    cb &= 0x1f;                                     // flags cannot matter here
                 }
-                *reinterpret_cast<uint4*>(planes_out[p] + dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                const int sh = (k & 3) * 8;
+                wc[k >> 2] = (wc[k >> 2] & ~(0xffu << sh)) | (cb << sh);
+                wq[k >> 2] = (wq[k >> 2] & ~(0xffu << sh)) | (qb << sh);
+                wa[k >> 2] = (wa[k >> 2] & ~(0xffu << sh)) | (ab << sh);
             }
+            *reinterpret_cast<uint4*>(tcode + dst) = make_uint4(wc[0], wc[1], wc[2], wc[3]);
+            *reinterpret_cast<uint4*>(tqual + dst) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+            *reinterpret_cast<uint4*>(tanch + dst) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
         }
         base += (int64_t)__popc(m) * kChunk;
     }
+    if (locus < n_loci) pad[locus] = npad;
 }
 
 cudaError_t launch_tile_layout(const int64_t* off, int64_t n_loci, int32_t* depth, int64_t* tile_chunks, cudaStream_t stream) {
@@ -80,11 +98,11 @@ cudaError_t launch_tile_layout(const int64_t* off, int64_t n_loci, int32_t* dept
     return cudaGetLastError();
 }
 cudaError_t launch_tile_scatter(const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci, const int64_t* tile_base,
-                                uint8_t* tcode, uint8_t* tqual, uint8_t* tanch, cudaStream_t stream) {
+                                const uint8_t* ref_base, int min_bq, uint8_t* tcode, uint8_t* tqual, uint8_t* tanch, int32_t* pad, cudaStream_t stream) {
     const int threads = 256;
     const int64_t n_tiles = (n_loci + kTileLoci - 1) / kTileLoci;
     const unsigned blocks = (unsigned)((n_tiles * 32 + threads - 1) / threads);
-    if (blocks) tile_scatter_kernel<<<blocks, threads, 0, stream>>>(off, code, qual, anch, n_loci, tile_base, tcode, tqual, tanch);
+    if (blocks) tile_scatter_kernel<<<blocks, threads, 0, stream>>>(off, code, qual, anch, n_loci, tile_base, ref_base, min_bq, tcode, tqual, tanch, pad);
     return cudaGetLastError();
 }
 
@@ -238,6 +256,50 @@ __device__ __forceinline__ void store_record(pb2_call_record* dst, const pb2_cal
     for (int i = 0; i < (int)(sizeof(pb2_call_record) / 16); i++) d[i] = s[i];
 }
 
+// Histogram rows are allele-minor: row = allele + 6 * direction, bin = row * 11 + anchor (0..197); [N][Forward][0] (bin 44) also absorbs PADs.
+constexpr int kPadBin = (AT_N + 6 * DIR_F) * kNumAnchors + 0;
+
+// Four entries at a time with byte-parallel arithmetic: quality test, N-forcing and the bin index never leave the packed word; only the
+// shared-memory read-modify-write is per entry.
+__device__ __forceinline__ uint32_t bins_of_word(uint32_t c4, uint32_t q4, uint32_t a4, uint32_t minbq4) {
+    const uint32_t al4 = c4 & 0x07070707u;
+    const uint32_t dr6 = ((c4 >> 3) & 0x03030303u) * 6u;            // per byte <= 12
+    const uint32_t row4 = al4 + dr6;                                  // <= 17
+    const uint32_t rowN4 = dr6 + 0x04040404u;                         // the N row of the same direction
+    const uint32_t g7 = ((q4 | 0x80808080u) - minbq4) & 0x80808080u;  // bit 7 of a byte set <=> q >= minBQ (no borrow crosses bytes: q | 0x80 >= 128 > minBQ)
+    const uint32_t m = (g7 - (g7 >> 7)) | g7;                         // 0xFF where q >= minBQ
+    const uint32_t rs4 = (row4 & m) | (rowN4 & ~m);                   // RegionStateManager.cs:180-181: low quality -> N
+    return rs4 * 11u + (a4 & 0x0f0f0f0fu);                            // per byte <= 197
+}
+
+template <bool kWantQsum, bool kCollapsed>
+__device__ __forceinline__ void count_word(uint32_t c4, uint32_t q4, uint32_t a4, uint32_t minbq4, uint16_t* __restrict__ my, const double* __restrict__ q_lut,
+                                           int min_bq, double& qsum) {
+    const uint32_t bin4 = bins_of_word(c4, q4, a4, minbq4);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t b = (bin4 >> (8 * k)) & 0xffu;
+        my[b * kHotThreads] += 1;
+    }
+    if (kWantQsum || kCollapsed) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t code = (c4 >> (8 * k)) & 0xffu, q = (q4 >> (8 * k)) & 0xffu, an = (a4 >> (8 * k)) & 0xffu;
+            const int allele = code & 7;
+            const bool usable = allele == AT_DEL || (allele < AT_N && (int)q >= min_bq);   // counted as something other than N (PADs are N)
+            if (kWantQsum) { if (usable && allele != AT_DEL) qsum += q_lut[q]; }   // Σ over A,C,G,T (Deletion entries carry no base quality, :191)
+            if (kCollapsed) {
+                const int ct = (int)(an >> 4);
+                if (ct != 0 && usable) {   // CollapsedRegionState.AddCollapsedReadCount (:28-44)
+                    my[(kNumBins + ct - 1) * kHotThreads] += 1;
+                    if (ct - 1 == 4 || ct - 1 == 6) my[(kNumBins + 2) * kHotThreads] += 1;
+                    else if (ct - 1 == 5 || ct - 1 == 7) my[(kNumBins + 3) * kHotThreads] += 1;
+                }
+            }
+        }
+    }
+}
+
 template <bool kWantQsum, bool kCollapsed>
 __global__ void __launch_bounds__(kHotThreads, 1)
 pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, DeviceConfig cfg, int* __restrict__ tile_counter) {
@@ -255,6 +317,7 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
         for (int q = threadIdx.x; q < 256; q += kHotThreads) q_lut[q] = pow(10.0, (double)((float)(-q) / 10.0f));  // RegionStateManager.cs:191 (float exponent)
         __syncthreads();
     }
+    const uint32_t minbq4 = (uint32_t)cfg.min_bq * 0x01010101u;
 
     while (true) {
         if (lane == 0) s_tile[warp] = atomicAdd(tile_counter, 1);
@@ -271,9 +334,11 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
         const int ref_allele = have_locus ? allele_of_base(in.ref_base[locus]) : AT_N;
         int64_t base = in.tile_base[tile];
         double qsum = 0.0;
+        int extra_pad = 0;   // whole PAD chunks counted by lanes that ran out of entries before the longest lane of the tile
 
-        // software pipeline: chunk c+1 is in flight while chunk c is histogrammed
-        uint4 nc = make_uint4(0, 0, 0, 0), nq = nc, na = nc;
+        // software pipeline: chunk c+1 is in flight while chunk c is histogrammed; lanes without a chunk process a PAD chunk
+        const uint4 pad_c = make_uint4(0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u), pad_q = make_uint4(~0u, ~0u, ~0u, ~0u), pad_a = make_uint4(0, 0, 0, 0);
+        uint4 nc = pad_c, nq = pad_q, na = pad_a;
         {
             const bool active = 0 < nchunks;
             const unsigned m = __ballot_sync(0xffffffffu, active);
@@ -285,6 +350,8 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
         }
         for (int c = 0; c < max_chunks; c++) {
             const uint4 wc = nc, wq = nq, wa = na;
+            if (c >= nchunks) extra_pad += kChunk;
+            nc = pad_c; nq = pad_q; na = pad_a;
             {
                 const bool active = (c + 1) < nchunks;
                 const unsigned m = __ballot_sync(0xffffffffu, active);
@@ -294,39 +361,20 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
                 }
                 base += (int64_t)__popc(m) * kChunk;
             }
-            const int n_here = min(kChunk, depth - c * kChunk);   // <= 0 for lanes that ran out of chunks
-            const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w}, aw[4] = {wa.x, wa.y, wa.z, wa.w};
-#pragma unroll
-            for (int k = 0; k < kChunk; k++) {
-                if (k < n_here) {
+            count_word<kWantQsum, kCollapsed>(wc.x, wq.x, wa.x, minbq4, my, q_lut, cfg.min_bq, qsum);
+            count_word<kWantQsum, kCollapsed>(wc.y, wq.y, wa.y, minbq4, my, q_lut, cfg.min_bq, qsum);
+            count_word<kWantQsum, kCollapsed>(wc.z, wq.z, wa.z, minbq4, my, q_lut, cfg.min_bq, qsum);
+            count_word<kWantQsum, kCollapsed>(wc.w, wq.w, wa.w, minbq4, my, q_lut, cfg.min_bq, qsum);
+            // flagged entries (rare after staging normalisation): SNV-candidate bookkeeping the counts cannot express -> side list
+            if (((wc.x | wc.y | wc.z | wc.w) & 0xe0e0e0e0u) != 0) {
+                const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w}, aw[4] = {wa.x, wa.y, wa.z, wa.w};
+                for (int k = 0; k < kChunk; k++) {
                     const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-                    const uint32_t q = (qw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-                    const uint32_t an = (aw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-                    const int allele = code & 7;
-                    const int dir = (code >> 3) & 3;
-                    const bool lowq = (int)q < cfg.min_bq;
-                    // deletions below the quality bar are not counted at all (RegionStateManager.cs:170-177); bases become N (:180-181)
-                    if (!(allele == AT_DEL && lowq)) {
-                        const int a2 = lowq ? AT_N : allele;
-                        const int bin = (a2 * kNumDirs + dir) * kNumAnchors + (int)(an & 15u);
-                        my[bin * kHotThreads] += 1;
-                        if (kWantQsum) { if (allele != AT_DEL && a2 != AT_N) qsum += q_lut[q]; }
-                        if (kCollapsed) {
-                            const int ct = (int)(an >> 4);
-                            if (ct != 0 && a2 != AT_N) {   // CollapsedRegionState.AddCollapsedReadCount (:28-44)
-                                my[(kNumBins + ct - 1) * kHotThreads] += 1;
-                                if (ct - 1 == 4 || ct - 1 == 6) my[(kNumBins + 2) * kHotThreads] += 1;
-                                else if (ct - 1 == 5 || ct - 1 == 7) my[(kNumBins + 3) * kHotThreads] += 1;
-                            }
-                        }
-                        // flagged entries that would raise an SNV candidate need the candidate bookkeeping of CandidateVariantFinder: rare, side list
-                        if ((code & 0xe0u) != 0 && a2 < AT_N && a2 != ref_allele && ref_allele != AT_N) {
-                            const unsigned long long slot = atomicAdd(out.exc_count, 1ull);
-                            if ((int64_t)slot < out.exc_capacity) {
-                                out.exc_entries[2 * slot] = (uint32_t)locus;
-                                out.exc_entries[2 * slot + 1] = code | (q << 8) | (an << 16);
-                            }
-                        }
+                    if ((code & 0xe0u) == 0) continue;
+                    const unsigned long long slot = atomicAdd(out.exc_count, 1ull);
+                    if ((int64_t)slot < out.exc_capacity) {
+                        out.exc_entries[2 * slot] = (uint32_t)locus;
+                        out.exc_entries[2 * slot + 1] = code | (((qw[k >> 2] >> ((k & 3) * 8)) & 0xffu) << 8) | (((aw[k >> 2] >> ((k & 3) * 8)) & 0xffu) << 16);
                     }
                 }
             }
@@ -336,6 +384,7 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
         LocusCounts lc;
         lc.qsum = qsum;
         int any = 0;
+        const int npad = (have_locus ? in.pad[locus] : 0) + extra_pad;
 #pragma unroll
         for (int a = 0; a < kNumAlleles; a++)
 #pragma unroll
@@ -343,10 +392,11 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
                 int s = 0;
 #pragma unroll
                 for (int an = 0; an < kNumAnchors; an++) {
-                    const int bin = (a * kNumDirs + d) * kNumAnchors + an;
-                    const int v = my[bin * kHotThreads];
-                    my[bin * kHotThreads] = 0;
-                    if (out.counts_out != nullptr && have_locus) out.counts_out[locus * kNumBins + bin] = v;
+                    const int hbin = (a + 6 * d) * kNumAnchors + an;            // shared-memory layout (allele-minor)
+                    int v = my[hbin * kHotThreads];
+                    my[hbin * kHotThreads] = 0;
+                    if (hbin == kPadBin) v -= npad;
+                    if (out.counts_out != nullptr && have_locus) out.counts_out[locus * kNumBins + (a * kNumDirs + d) * kNumAnchors + an] = v;   // RegionState order
                     s += v;
                 }
                 lc.c[a][d] = s;

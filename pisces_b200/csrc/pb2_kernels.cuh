@@ -37,7 +37,8 @@ struct TilePileup {
     const uint8_t* qual;
     const uint8_t* anch;
     const int64_t* tile_base;   // [n_tiles] first byte of the tile in each plane (multiple of 16)
-    const int32_t* depth;       // [n_loci]
+    const int32_t* depth;       // [n_loci] entries in the source pileup
+    const int32_t* pad;         // [n_loci] PAD entries the staged locus carries (chunk tail + dropped low-quality deletions)
     const uint8_t* ref_base;    // [n_loci] ASCII
     const int32_t* positions;   // [n_loci] or nullptr
     int32_t first_position;
@@ -72,7 +73,8 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
 // CSR -> PTILE32 staging
 cudaError_t launch_tile_layout(const int64_t* csr_offsets, int64_t n_loci, int32_t* depth, int64_t* tile_chunks /*[n_tiles]*/, cudaStream_t stream);
 cudaError_t launch_tile_scatter(const int64_t* csr_offsets, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci,
-                                const int64_t* tile_base, uint8_t* tcode, uint8_t* tqual, uint8_t* tanch, cudaStream_t stream);
+                                const int64_t* tile_base, const uint8_t* ref_base, int min_bq, uint8_t* tcode, uint8_t* tqual, uint8_t* tanch, int32_t* pad,
+                                cudaStream_t stream);
 cudaError_t exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* temp, size_t temp_bytes, size_t* temp_needed, cudaStream_t stream);
 
 }  // namespace pb2
