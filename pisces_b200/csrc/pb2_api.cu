@@ -71,7 +71,9 @@ struct Segment {   // one staged pileup (pb2_push_pileup*)
     int64_t var_capacity = 0;
     uint32_t* exc_entries = nullptr;
     int64_t exc_capacity = 0;
-    unsigned long long* counters = nullptr;   // [0] var_count, [1] exc_count
+    PendingLocus* pending = nullptr;
+    int64_t pending_capacity = 0;
+    unsigned long long* counters = nullptr;   // [0] var_count, [1] exc_count, [2] pending_count
     // host copies needed for ordering / lookups
     std::vector<int32_t> h_positions;
     bool called = false;
@@ -197,7 +199,7 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
 }
 
 static void free_segment(pb2_handle* h, Segment& s) {
-    void* ptrs[] = {s.depth, s.pad, s.tile_base, s.code, s.qual, s.anch, s.ref_base, s.positions, s.ref_records, s.ref_valid, s.var_records, s.exc_entries, s.counters};
+    void* ptrs[] = {s.depth, s.pad, s.tile_base, s.code, s.qual, s.anch, s.ref_base, s.positions, s.ref_records, s.ref_valid, s.var_records, s.exc_entries, s.counters, s.pending};
     for (void* p : ptrs) if (p) cudaFree(p);
     s = Segment();
 }
@@ -340,7 +342,9 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     CU(h, cudaMalloc(&s.var_records, sizeof(pb2_call_record) * (size_t)s.var_capacity));
     s.exc_capacity = 1 << 20;
     CU(h, cudaMalloc(&s.exc_entries, sizeof(uint32_t) * 2 * (size_t)s.exc_capacity));
-    CU(h, cudaMalloc(&s.counters, sizeof(unsigned long long) * 2));
+    CU(h, cudaMalloc(&s.counters, sizeof(unsigned long long) * 4));
+    s.pending_capacity = std::max<int64_t>(1024, p->n_loci);
+    CU(h, cudaMalloc(&s.pending, sizeof(PendingLocus) * (size_t)s.pending_capacity));
 
     CU(h, cudaStreamSynchronize(st));
     cudaFree(tile_bytes);
@@ -357,14 +361,15 @@ static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* 
     cudaStream_t st = h->stream;
     TilePileup in;
     in.code = s.code; in.qual = s.qual; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
-    in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles;
+    in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles; in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);
     HotInputsExtra ex;
     ex.gapped_ref = nullptr; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len;
     HotOutputs out;
     out.ref_records = s.ref_records; out.ref_valid = s.ref_valid; out.var_records = s.var_records; out.var_count = s.counters;
     out.var_capacity = s.var_capacity; out.exc_entries = s.exc_entries; out.exc_count = s.counters + 1; out.exc_capacity = s.exc_capacity;
     out.counts_out = counts_out; out.collapsed_out = collapsed_out;
-    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 2, st));
+    out.pending = s.pending; out.pending_count = s.counters + 2; out.pending_capacity = s.pending_capacity;
+    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
     CU(h, cudaEventRecord(h->ev0, st));
     CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, st));
     CU(h, cudaEventRecord(h->ev1, st));
@@ -375,7 +380,7 @@ static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* 
     CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->hot_ms += ms;
     h->hot_launches += 1;
-    h->total_launches += 1;
+    h->total_launches += 2;
     s.h_var_count = cnt[0];
     s.h_exc_count = cnt[1];
     s.called = true;

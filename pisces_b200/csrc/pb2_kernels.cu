@@ -18,6 +18,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {  // 16-byte stre
     asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ void prefetch_l2(const uint8_t* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int allele_of_base(uint8_t c) {  // AlleleHelper.GetAlleleType (Utility/AlleleHelper.cs:13-32)
     switch (c) { case 'A': return AT_A; case 'C': return AT_C; case 'G': return AT_G; case 'T': return AT_T; default: return AT_N; }
 }
@@ -171,7 +172,7 @@ struct LocusCounts {
 
 // Fill one record for a point allele (Reference or Snv) exactly as ProcessVariant + SetGenotypes would. Returns false when a non-reference
 // allele is not callable (AlleleCaller.IsCallable) so nothing is emitted.
-__device__ bool score_point_allele(const LocusCounts& lc, int position, int ref_allele, int alt_allele /* == ref_allele for Reference */, int gapped,
+__device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int position, int ref_allele, int alt_allele /* == ref_allele for Reference */, int gapped,
                                    const DeviceConfig& cfg, const uint8_t* __restrict__ chr_seq, int64_t chr_len, pb2_call_record& r) {
     const bool is_ref = alt_allele == ref_allele;
     int cov[3], sup[3];
@@ -353,6 +354,7 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
             if (c >= nchunks) extra_pad += kChunk;
             nc = pad_c; nq = pad_q; na = pad_a;
             {
+                // chunk c+1 into registers now, chunk c+2 into L2: both requests are in flight for the whole of this iteration
                 const bool active = (c + 1) < nchunks;
                 const unsigned m = __ballot_sync(0xffffffffu, active);
                 if (active) {
@@ -360,6 +362,9 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
                     nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o); na = ldg_stream(in.anch + o);
                 }
                 base += (int64_t)__popc(m) * kChunk;
+                const int64_t pf = min(base + lane * kChunk, in.plane_bytes - kChunk);
+                prefetch_l2(in.code + pf); prefetch_l2(in.qual + pf); prefetch_l2(in.anch + pf);
+                asm volatile("" ::: "memory");   // keep the histogram traffic below the loads
             }
             count_word<kWantQsum, kCollapsed>(wc.x, wq.x, wa.x, minbq4, my, q_lut, cfg.min_bq, qsum);
             count_word<kWantQsum, kCollapsed>(wc.y, wq.y, wa.y, minbq4, my, q_lut, cfg.min_bq, qsum);
@@ -412,31 +417,90 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
         }
         if (!have_locus) continue;
 
-        // ---- score: SNV candidates in (ref, alt) order = alphabetical alt (AlleleCaller.cs:172-176), then the reference allele
-        const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+        // ---- candidates. Cheap tests here (coverage / frequency bars of AlleleCaller.IsCallable, :246-251); a locus with a surviving SNV
+        // candidate is queued for score_pending_kernel, where lanes are dense, instead of being scored here at 1/32 lane utilisation.
         const int gapped = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
-        bool variant_called = ex.locus_has_variant ? (ex.locus_has_variant[locus] != 0) : false;
+        unsigned cand_mask = 0;
         if (ref_allele != AT_N) {
-            const int order[4] = {AT_A, AT_C, AT_G, AT_T};
-#pragma unroll 1
-            for (int oi = 0; oi < 4; oi++) {
-                const int alt = order[oi];
-                if (alt == ref_allele) continue;
-                if (lc.c[alt][0] + lc.c[alt][1] + lc.c[alt][2] == 0) continue;
+            int total = 0;
+#pragma unroll
+            for (int d = 0; d < 3; d++) total += lc.c[AT_A][d] + lc.c[AT_C][d] + lc.c[AT_G][d] + lc.c[AT_T][d] + lc.c[AT_DEL][d];
+#pragma unroll
+            for (int alt = 0; alt < 4; alt++) {
+                const int sup = lc.c[alt][0] + lc.c[alt][1] + lc.c[alt][2];
+                if (alt == ref_allele || sup == 0) continue;
+                if (total < cfg.min_coverage && !cfg.output_gvcf) continue;
+                if (total != 0 && allele_frequency(sup, total) < cfg.min_frequency) continue;
+                cand_mask |= 1u << alt;
+            }
+        }
+        const bool has_ext_variant = ex.locus_has_variant ? (ex.locus_has_variant[locus] != 0) : false;
+        if (cand_mask != 0) {
+            const unsigned long long slot = atomicAdd(out.pending_count, 1ull);
+            if ((int64_t)slot < out.pending_capacity) {
+                PendingLocus pl;
+                pl.locus = (int32_t)locus;
+                pl.cand_mask = (int32_t)cand_mask | (has_ext_variant ? 0x100 : 0) | (any > 0 ? 0x200 : 0);
+#pragma unroll
+                for (int a = 0; a < kNumAlleles; a++)
+#pragma unroll
+                    for (int d = 0; d < kNumDirs; d++) pl.c[a * kNumDirs + d] = lc.c[a][d];
+                pl.gapped = gapped;
+                pl.pad_ = 0;
+                pl.qsum = lc.qsum;
+                const uint4* sp = reinterpret_cast<const uint4*>(&pl);
+                uint4* dp = reinterpret_cast<uint4*>(out.pending + slot);
+#pragma unroll
+                for (int i = 0; i < (int)(sizeof(PendingLocus) / 16); i++) dp[i] = sp[i];
+            }
+            if (out.ref_records != nullptr) out.ref_valid[locus] = 0;   // decided by score_pending_kernel
+        } else if (out.ref_records != nullptr) {
+            // RegionState.GetAllCandidates: a Reference candidate per position when gVCF; zero-coverage positions only with intervals (:446)
+            const bool emit = cfg.output_gvcf && !has_ext_variant && (cfg.have_intervals || any > 0);
+            if (emit) {
+                const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
                 pb2_call_record r;
-                if (score_point_allele(lc, position, ref_allele, alt, gapped, cfg, ex.chr_seq, ex.chr_len, r)) {
-                    variant_called = true;
-                    const unsigned long long slot = atomicAdd(out.var_count, 1ull);
-                    if ((int64_t)slot < out.var_capacity) store_record(out.var_records + slot, r);
-                }
+                score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex.chr_seq, ex.chr_len, r);
+                store_record(out.ref_records + locus, r);
+            }
+            out.ref_valid[locus] = emit ? 1 : 0;
+        }
+    }
+}
+
+// One thread per queued locus: the full ProcessVariant + genotype chain for its SNV candidates in (ref, alt) order (AlleleCaller.cs:172-176),
+// then the reference allele if nothing was called there (:146-147).
+__global__ void __launch_bounds__(128) score_pending_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, DeviceConfig cfg) {
+    const unsigned long long n = min(*out.pending_count, (unsigned long long)out.pending_capacity);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const PendingLocus pl = out.pending[i];
+        const int64_t locus = pl.locus;
+        LocusCounts lc;
+#pragma unroll
+        for (int a = 0; a < kNumAlleles; a++)
+#pragma unroll
+            for (int d = 0; d < kNumDirs; d++) lc.c[a][d] = pl.c[a * kNumDirs + d];
+        lc.qsum = pl.qsum;
+        const int ref_allele = allele_of_base(in.ref_base[locus]);
+        const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+        bool variant_called = (pl.cand_mask & 0x100) != 0;
+        const int order[4] = {AT_A, AT_C, AT_G, AT_T};
+#pragma unroll 1
+        for (int oi = 0; oi < 4; oi++) {
+            const int alt = order[oi];
+            if (!((pl.cand_mask >> alt) & 1)) continue;
+            pb2_call_record r;
+            if (score_point_allele(lc, position, ref_allele, alt, pl.gapped, cfg, ex.chr_seq, ex.chr_len, r)) {
+                variant_called = true;
+                const unsigned long long slot = atomicAdd(out.var_count, 1ull);
+                if ((int64_t)slot < out.var_capacity) store_record(out.var_records + slot, r);
             }
         }
         if (out.ref_records != nullptr) {
-            // RegionState.GetAllCandidates: a Reference candidate per position when gVCF; zero-coverage positions only with intervals (:446)
-            bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || any > 0);
+            const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (pl.cand_mask & 0x200));
             if (emit) {
                 pb2_call_record r;
-                score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex.chr_seq, ex.chr_len, r);
+                score_point_allele(lc, position, ref_allele, ref_allele, pl.gapped, cfg, ex.chr_seq, ex.chr_len, r);
                 store_record(out.ref_records + locus, r);
             }
             out.ref_valid[locus] = emit ? 1 : 0;
@@ -469,6 +533,9 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
     else if (coll) PB2_LAUNCH(false, true);
     else PB2_LAUNCH(false, false);
 #undef PB2_LAUNCH
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    score_pending_kernel<<<num_sms * 4, 128, 0, stream>>>(in, ex, out, cfg);
     return cudaGetLastError();
 }
 

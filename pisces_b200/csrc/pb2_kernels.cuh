@@ -44,7 +44,19 @@ struct TilePileup {
     int32_t first_position;
     int64_t n_loci;
     int32_t n_tiles;
+    int64_t plane_bytes;        // size of each plane (multiple of 16, >= 16)
 };
+
+// A locus whose SNV candidates passed the cheap callability bars: scored by score_pending_kernel. 96 bytes.
+struct PendingLocus {
+    int32_t locus;
+    int32_t cand_mask;   // bit a: allele a is a candidate; 0x100: a non-point variant was called here; 0x200: any count at the locus
+    int32_t c[18];       // [allele][direction] anchor-summed counts
+    int32_t gapped;
+    int32_t pad_;
+    double qsum;
+};
+static_assert(sizeof(PendingLocus) == 96, "PendingLocus layout");
 
 struct HotOutputs {
     pb2_call_record* ref_records;   // [n_loci] dense reference stream (gVCF) or nullptr
@@ -52,6 +64,9 @@ struct HotOutputs {
     pb2_call_record* var_records;   // compacted variant stream
     unsigned long long* var_count;
     int64_t var_capacity;
+    PendingLocus* pending;          // queue of loci for score_pending_kernel
+    unsigned long long* pending_count;
+    int64_t pending_capacity;
     uint32_t* exc_entries;          // flagged mismatching entries: {locus_index, code | qual<<8 | anchor<<16}
     unsigned long long* exc_count;
     int64_t exc_capacity;
