@@ -59,6 +59,7 @@ struct Segment {   // one staged pileup (pb2_push_pileup*)
     bool has_positions = false;
     int64_t plane_bytes = 0;
     int64_t n_entries = 0;
+    int32_t max_depth = 0;
     // device
     int32_t* depth = nullptr;
     int32_t* pad = nullptr;
@@ -318,7 +319,10 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     int64_t* tile_bytes = nullptr;
     CU(h, cudaMalloc(&tile_bytes, sizeof(int64_t) * (size_t)(s.n_tiles + 1)));
     CU(h, cudaMemsetAsync(tile_bytes, 0, sizeof(int64_t) * (size_t)(s.n_tiles + 1), st));
-    CU(h, launch_tile_layout(d_off, p->n_loci, s.depth, tile_bytes, st));
+    int32_t* d_max_depth = reinterpret_cast<int32_t*>(h->d_tile_counter);   // scratch int of the handle (the hot kernel resets it before use)
+    CU(h, cudaMemsetAsync(d_max_depth, 0, sizeof(int32_t), st));
+    CU(h, launch_tile_layout(d_off, p->n_loci, s.depth, tile_bytes, d_max_depth, st));
+    CU(h, cudaMemcpyAsync(&s.max_depth, d_max_depth, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     size_t temp_bytes = 0;
     CU(h, exclusive_scan_i64(tile_bytes, s.tile_base, s.n_tiles + 1, nullptr, 0, &temp_bytes, st));
     void* temp = nullptr;
@@ -371,7 +375,7 @@ static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* 
     out.pending = s.pending; out.pending_count = s.counters + 2; out.pending_capacity = s.pending_capacity;
     CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
     CU(h, cudaEventRecord(h->ev0, st));
-    CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, st));
+    CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, s.max_depth < kNarrowMaxDepth, st));
     CU(h, cudaEventRecord(h->ev1, st));
     unsigned long long cnt[2];
     CU(h, cudaMemcpyAsync(cnt, s.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));

@@ -26,11 +26,14 @@ __device__ __forceinline__ char base_of_allele(int a) { return a == AT_A ? 'A' :
 
 // ------------------------------------------------------------------------------------------------ CSR -> PTILE32
 // depth[i] = off[i+1]-off[i];  tile_chunks[t] = bytes per plane of tile t = 16 * sum over the tile's loci of ceil(depth/16)
-__global__ void tile_layout_kernel(const int64_t* __restrict__ off, int64_t n_loci, int32_t* __restrict__ depth, int64_t* __restrict__ tile_chunks) {
+__global__ void tile_layout_kernel(const int64_t* __restrict__ off, int64_t n_loci, int32_t* __restrict__ depth, int64_t* __restrict__ tile_chunks,
+                                   int32_t* __restrict__ max_depth) {
     const int64_t locus = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // blockDim multiple of 32, tiles are warp-aligned
     int d = 0;
     if (locus < n_loci) { d = (int)(off[locus + 1] - off[locus]); depth[locus] = d; }
     int chunks = (d + kChunk - 1) / kChunk;
+    const int dmax = __reduce_max_sync(0xffffffffu, d);
+    if ((threadIdx.x & 31) == 0 && dmax > 0) atomicMax(max_depth, dmax);
     chunks = __reduce_add_sync(0xffffffffu, chunks);
     if ((threadIdx.x & 31) == 0 && (locus / kTileLoci) * (int64_t)kTileLoci < n_loci) tile_chunks[locus / kTileLoci] = (int64_t)chunks * kChunk;
 }
@@ -91,11 +94,11 @@ __global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8
     if (locus < n_loci) pad[locus] = npad;
 }
 
-cudaError_t launch_tile_layout(const int64_t* off, int64_t n_loci, int32_t* depth, int64_t* tile_chunks, cudaStream_t stream) {
+cudaError_t launch_tile_layout(const int64_t* off, int64_t n_loci, int32_t* depth, int64_t* tile_chunks, int32_t* max_depth, cudaStream_t stream) {
     const int threads = 256;
     const int64_t n_pad = (n_loci + kTileLoci - 1) / kTileLoci * kTileLoci;
     const unsigned blocks = (unsigned)((n_pad + threads - 1) / threads);
-    if (blocks) tile_layout_kernel<<<blocks, threads, 0, stream>>>(off, n_loci, depth, tile_chunks);
+    if (blocks) tile_layout_kernel<<<blocks, threads, 0, stream>>>(off, n_loci, depth, tile_chunks, max_depth);
     return cudaGetLastError();
 }
 cudaError_t launch_tile_scatter(const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci, const int64_t* tile_base,
@@ -121,7 +124,11 @@ cudaError_t exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void*
 // ------------------------------------------------------------------------------------------------ the fused hot kernel
 // Thread-private histogram cell for (bin, thread): 16-bit counters interleaved so that the 32 lanes of a warp always hit 32 different
 // banks whatever bins they address: halfword index = bin * kHotThreads + (warp >> 1) * 64 + lane * 2 + (warp & 1).
-__device__ __forceinline__ int hist_slot(int warp, int lane) { return (warp >> 1) * 64 + lane * 2 + (warp & 1); }
+template <typename Cnt>
+__device__ __forceinline__ int hist_slot(int warp, int lane) {
+    constexpr int kPerWord = 4 / (int)sizeof(Cnt);   // counters per 32-bit word: the warps sharing a word differ, the 32 lanes hit 32 banks
+    return (warp / kPerWord) * (32 * kPerWord) + lane * kPerWord + (warp % kPerWord);
+}
 
 // RMxNCalculator.ComputeRMxNLengthForIndel (:49-95) on the device-resident chromosome; variant_bases has length <= 1 for point alleles
 __device__ int rmxn_length_for_indel(int variant_position, const char* vb, int length, const uint8_t* __restrict__ ref, int64_t ref_len, int max_unit) {
@@ -273,14 +280,16 @@ __device__ __forceinline__ uint32_t bins_of_word(uint32_t c4, uint32_t q4, uint3
     return rs4 * 11u + (a4 & 0x0f0f0f0fu);                            // per byte <= 197
 }
 
-template <bool kWantQsum, bool kCollapsed>
-__device__ __forceinline__ void count_word(uint32_t c4, uint32_t q4, uint32_t a4, uint32_t minbq4, uint16_t* __restrict__ my, const double* __restrict__ q_lut,
-                                           int min_bq, double& qsum) {
+template <typename Cnt, int kThreads, bool kWantQsum, bool kCollapsed>
+__device__ __forceinline__ void count_word(uint32_t c4, uint32_t q4, uint32_t a4, uint32_t minbq4, Cnt* __restrict__ my, const double* __restrict__ q_lut,
+                                           int min_bq, double& qsum, uint32_t& wrap_acc) {
     const uint32_t bin4 = bins_of_word(c4, q4, a4, minbq4);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t b = (bin4 >> (8 * k)) & 0xffu;
-        my[b * kHotThreads] += 1;
+        const uint32_t v = (uint32_t)my[b * kThreads] + 1u;
+        my[b * kThreads] = (Cnt)v;
+        if (sizeof(Cnt) == 1) wrap_acc |= v;     // bit 8 set <=> an 8-bit counter wrapped somewhere in this chunk
     }
     if (kWantQsum || kCollapsed) {
 #pragma unroll
@@ -292,30 +301,55 @@ __device__ __forceinline__ void count_word(uint32_t c4, uint32_t q4, uint32_t a4
             if (kCollapsed) {
                 const int ct = (int)(an >> 4);
                 if (ct != 0 && usable) {   // CollapsedRegionState.AddCollapsedReadCount (:28-44)
-                    my[(kNumBins + ct - 1) * kHotThreads] += 1;
-                    if (ct - 1 == 4 || ct - 1 == 6) my[(kNumBins + 2) * kHotThreads] += 1;
-                    else if (ct - 1 == 5 || ct - 1 == 7) my[(kNumBins + 3) * kHotThreads] += 1;
+                    my[(kNumBins + ct - 1) * kThreads] += 1;
+                    if (ct - 1 == 4 || ct - 1 == 6) my[(kNumBins + 2) * kThreads] += 1;
+                    else if (ct - 1 == 5 || ct - 1 == 7) my[(kNumBins + 3) * kThreads] += 1;
                 }
             }
         }
     }
 }
 
-template <bool kWantQsum, bool kCollapsed>
-__global__ void __launch_bounds__(kHotThreads, 1)
+// Rare path of the 8-bit histogram: some counter wrapped while this chunk was added. A bin wrapped iff its value is now smaller than the
+// number of entries the chunk put into it; the wrap is recorded per histogram row (allele, direction), which is all the scoring needs.
+template <int kThreads>
+__device__ __noinline__ void note_wraps(const uint4 wc, const uint4 wq, const uint4 wa, uint32_t minbq4, const uint8_t* __restrict__ my, uint8_t* __restrict__ my_wraps) {
+    const uint32_t b4[4] = {bins_of_word(wc.x, wq.x, wa.x, minbq4), bins_of_word(wc.y, wq.y, wa.y, minbq4), bins_of_word(wc.z, wq.z, wa.z, minbq4),
+                            bins_of_word(wc.w, wq.w, wa.w, minbq4)};
+    for (int k = 0; k < kChunk; k++) {
+        const uint32_t b = (b4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+        int cnt = 0;
+        bool first = true;
+        for (int j = 0; j < kChunk; j++) {
+            const uint32_t bj = (b4[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+            if (bj == b) { cnt++; if (j < k) first = false; }
+        }
+        if (first && (int)my[b * kThreads] < cnt) my_wraps[(b / kNumAnchors) * kThreads] += 1;
+    }
+}
+
+// Cnt = uint16_t, 512 threads: general variant (any depth < 65536 per locus, collapsed-read counts, the full 198-bin dump).
+// Cnt = uint8_t, 1024 threads: twice the resident warps for the same shared memory; wraps are caught per chunk and kept per row.
+template <typename Cnt, int kThreads, bool kWantQsum, bool kCollapsed>
+__global__ void __launch_bounds__(kThreads, 1)
 pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, DeviceConfig cfg, int* __restrict__ tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw);                                     // [rows][kHotThreads]
-    constexpr int kRows = kNumBins + (kCollapsed ? kNumCollapsed : 0);
-    double* q_lut = reinterpret_cast<double*>(smem_raw + (size_t)kRows * kHotThreads * sizeof(uint16_t));  // [256] 10^(-q/10f)
-    __shared__ int s_tile[kHotThreads / 32];
+    constexpr bool kNarrow = sizeof(Cnt) == 1;
+    constexpr int kHotThreads = kThreads;
+    constexpr int kWrapRows = kNarrow ? kNumAlleles * kNumDirs : 0;
+    constexpr int kRows = kNumBins + (kCollapsed ? kNumCollapsed : 0) + kWrapRows;
+    Cnt* hist = reinterpret_cast<Cnt*>(smem_raw);                                               // [rows][kThreads]
+    double* q_lut = reinterpret_cast<double*>(smem_raw + (size_t)kRows * kThreads * sizeof(Cnt));   // [256] 10^(-q/10f)
+    __shared__ int s_tile[kThreads / 32];
+    static_assert(!(kNarrow && kCollapsed), "collapsed-read counts use the 16-bit variant");
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint16_t* my = hist + hist_slot(warp, lane);   // my[bin * kHotThreads]
-    for (int b = 0; b < kRows; b++) my[b * kHotThreads] = 0;
+    Cnt* my = hist + hist_slot<Cnt>(warp, lane);   // my[bin * kThreads]
+    uint8_t* my_wraps = reinterpret_cast<uint8_t*>(my) + (size_t)(kNumBins + (kCollapsed ? kNumCollapsed : 0)) * kThreads;   // [18 rows] (8-bit variant)
+    for (int b = 0; b < kRows; b++) my[b * kThreads] = 0;
     if (kWantQsum) {
-        for (int q = threadIdx.x; q < 256; q += kHotThreads) q_lut[q] = pow(10.0, (double)((float)(-q) / 10.0f));  // RegionStateManager.cs:191 (float exponent)
+        for (int q = threadIdx.x; q < 256; q += kThreads) q_lut[q] = pow(10.0, (double)((float)(-q) / 10.0f));  // RegionStateManager.cs:191 (float exponent)
         __syncthreads();
     }
     const uint32_t minbq4 = (uint32_t)cfg.min_bq * 0x01010101u;
@@ -366,10 +400,12 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
                 prefetch_l2(in.code + pf); prefetch_l2(in.qual + pf); prefetch_l2(in.anch + pf);
                 asm volatile("" ::: "memory");   // keep the histogram traffic below the loads
             }
-            count_word<kWantQsum, kCollapsed>(wc.x, wq.x, wa.x, minbq4, my, q_lut, cfg.min_bq, qsum);
-            count_word<kWantQsum, kCollapsed>(wc.y, wq.y, wa.y, minbq4, my, q_lut, cfg.min_bq, qsum);
-            count_word<kWantQsum, kCollapsed>(wc.z, wq.z, wa.z, minbq4, my, q_lut, cfg.min_bq, qsum);
-            count_word<kWantQsum, kCollapsed>(wc.w, wq.w, wa.w, minbq4, my, q_lut, cfg.min_bq, qsum);
+            uint32_t wrap_acc = 0;
+            count_word<Cnt, kThreads, kWantQsum, kCollapsed>(wc.x, wq.x, wa.x, minbq4, my, q_lut, cfg.min_bq, qsum, wrap_acc);
+            count_word<Cnt, kThreads, kWantQsum, kCollapsed>(wc.y, wq.y, wa.y, minbq4, my, q_lut, cfg.min_bq, qsum, wrap_acc);
+            count_word<Cnt, kThreads, kWantQsum, kCollapsed>(wc.z, wq.z, wa.z, minbq4, my, q_lut, cfg.min_bq, qsum, wrap_acc);
+            count_word<Cnt, kThreads, kWantQsum, kCollapsed>(wc.w, wq.w, wa.w, minbq4, my, q_lut, cfg.min_bq, qsum, wrap_acc);
+            if (kNarrow) { if (wrap_acc & 0x100u) note_wraps<kThreads>(wc, wq, wa, minbq4, reinterpret_cast<const uint8_t*>(my), my_wraps); }
             // flagged entries (rare after staging normalisation): SNV-candidate bookkeeping the counts cannot express -> side list
             if (((wc.x | wc.y | wc.z | wc.w) & 0xe0e0e0e0u) != 0) {
                 const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w}, aw[4] = {wa.x, wa.y, wa.z, wa.w};
@@ -401,9 +437,10 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
                     int v = my[hbin * kHotThreads];
                     my[hbin * kHotThreads] = 0;
                     if (hbin == kPadBin) v -= npad;
-                    if (out.counts_out != nullptr && have_locus) out.counts_out[locus * kNumBins + (a * kNumDirs + d) * kNumAnchors + an] = v;   // RegionState order
+                    if (!kNarrow) { if (out.counts_out != nullptr && have_locus) out.counts_out[locus * kNumBins + (a * kNumDirs + d) * kNumAnchors + an] = v; }   // RegionState order
                     s += v;
                 }
+                if (kNarrow) { s += 256 * (int)my_wraps[(a + 6 * d) * kThreads]; my_wraps[(a + 6 * d) * kThreads] = 0; }
                 lc.c[a][d] = s;
                 any += s;
             }
@@ -508,30 +545,36 @@ __global__ void __launch_bounds__(128) score_pending_kernel(TilePileup in, HotIn
     }
 }
 
-size_t hot_kernel_smem_bytes(bool collapsed) {
+size_t hot_kernel_smem_bytes(bool narrow, bool collapsed) {
+    if (narrow) return (size_t)(kNumBins + kNumAlleles * kNumDirs) * kNarrowThreads + 256 * sizeof(double);
     const int rows = kNumBins + (collapsed ? kNumCollapsed : 0);
     return (size_t)rows * kHotThreads * sizeof(uint16_t) + 256 * sizeof(double);
 }
 
 cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
-                              cudaStream_t stream) {
+                              bool allow_narrow, cudaStream_t stream) {
     if (in.n_tiles == 0) return cudaSuccess;
     const bool want_q = cfg.want_qsum || cfg.noise_model == 1;
     const bool coll = cfg.expect_collapsed != 0;
-    const size_t smem = hot_kernel_smem_bytes(coll);
-    const int grid = min(num_sms, (in.n_tiles + kHotThreads / 32 - 1) / (kHotThreads / 32));
+    const bool narrow = allow_narrow && !coll && out.counts_out == nullptr;
+    const size_t smem = hot_kernel_smem_bytes(narrow, coll);
+    const int threads = narrow ? kNarrowThreads : kHotThreads;
+    const int grid = min(num_sms, (in.n_tiles + threads / 32 - 1) / (threads / 32));
     cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
-#define PB2_LAUNCH(Q, C)                                                                                                         \
-    do {                                                                                                                         \
-        e = cudaFuncSetAttribute(pileup_count_score_kernel<Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-        if (e != cudaSuccess) return e;                                                                                          \
-        pileup_count_score_kernel<Q, C><<<grid, kHotThreads, smem, stream>>>(in, ex, out, cfg, tile_counter);                     \
+#define PB2_LAUNCH(CNT, THREADS, Q, C)                                                                                                       \
+    do {                                                                                                                                     \
+        e = cudaFuncSetAttribute(pileup_count_score_kernel<CNT, THREADS, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e != cudaSuccess) return e;                                                                                                      \
+        pileup_count_score_kernel<CNT, THREADS, Q, C><<<grid, THREADS, smem, stream>>>(in, ex, out, cfg, tile_counter);                      \
     } while (0)
-    if (want_q && coll) PB2_LAUNCH(true, true);
-    else if (want_q) PB2_LAUNCH(true, false);
-    else if (coll) PB2_LAUNCH(false, true);
-    else PB2_LAUNCH(false, false);
+    if (narrow) {
+        if (want_q) PB2_LAUNCH(uint8_t, kNarrowThreads, true, false);
+        else PB2_LAUNCH(uint8_t, kNarrowThreads, false, false);
+    } else if (want_q && coll) PB2_LAUNCH(uint16_t, kHotThreads, true, true);
+    else if (want_q) PB2_LAUNCH(uint16_t, kHotThreads, true, false);
+    else if (coll) PB2_LAUNCH(uint16_t, kHotThreads, false, true);
+    else PB2_LAUNCH(uint16_t, kHotThreads, false, false);
 #undef PB2_LAUNCH
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -14,7 +14,9 @@ constexpr int kNumBins = kNumAlleles * kNumDirs * kNumAnchors;  // 198 = RegionS
 constexpr int kNumCollapsed = 8;
 constexpr int kTileLoci = 32;               // loci per tile = lanes per warp
 constexpr int kChunk = 16;                  // entries per lane per step = one 16-byte load per plane
-constexpr int kHotThreads = 512;            // one persistent CTA per SM, thread-private histograms in shared memory
+constexpr int kHotThreads = 512;            // one persistent CTA per SM, thread-private 16-bit histograms in shared memory
+constexpr int kNarrowThreads = 1024;        // 8-bit histograms: twice the warps in the same shared memory (depth per locus < kNarrowMaxDepth)
+constexpr int kNarrowMaxDepth = 60000;      // 8-bit row-wrap counters hold 255 wraps of 256
 
 // Scalars the kernels need from pb2_config (validated / derived on the host, Config semantics of VariantCallingParameters.Validate).
 struct DeviceConfig {
@@ -81,12 +83,13 @@ struct HotInputsExtra {
     int64_t chr_len;
 };
 
-size_t hot_kernel_smem_bytes(bool collapsed);
+size_t hot_kernel_smem_bytes(bool narrow, bool collapsed);
 cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
-                              cudaStream_t stream);
+                              bool allow_narrow, cudaStream_t stream);
 
 // CSR -> PTILE32 staging
-cudaError_t launch_tile_layout(const int64_t* csr_offsets, int64_t n_loci, int32_t* depth, int64_t* tile_chunks /*[n_tiles]*/, cudaStream_t stream);
+cudaError_t launch_tile_layout(const int64_t* csr_offsets, int64_t n_loci, int32_t* depth, int64_t* tile_chunks /*[n_tiles]*/, int32_t* max_depth,
+                               cudaStream_t stream);
 cudaError_t launch_tile_scatter(const int64_t* csr_offsets, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci,
                                 const int64_t* tile_base, const uint8_t* ref_base, int min_bq, uint8_t* tcode, uint8_t* tqual, uint8_t* tanch, int32_t* pad,
                                 cudaStream_t stream);

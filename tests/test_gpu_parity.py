@@ -170,3 +170,42 @@ def test_empty_and_ragged_inputs():
     assert [int(got[i].sum()) for i in range(6)] == depths
     assert int(got[3, 0, 0, 5]) == 17
     sm.close()
+
+
+def _pileup_both(d, gvcf, **kw):
+    pb = _pb()
+    ref = bytes(d["ref_bases"].numpy()).decode()
+    off, code, qual, anch = (d[k].numpy() for k in ("offsets", "code", "qual", "anchor"))
+    oc = ob.Caller(ob.default_config(output_gvcf=gvcf, **kw), "chr1", ref)
+    oc.add_pileup(off, code, qual, anch, 1)
+    oc.finish()
+    pkw = dict(kw)
+    if pkw.get("noise_model") == 1:
+        pkw["want_sum_base_quality"] = 1
+    sm = pb.GpuStateManager(pb.make_config(output_gvcf=gvcf, **pkw), "chr1", ref)
+    sm.AddPileup(off, code, qual, anch, first_position=1)
+    precs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    counts = sm.GetAlleleCounts(1, len(off) - 1)
+    sm.close()
+    oc2 = ob.Caller(ob.default_config(output_gvcf=gvcf, **kw), "chr1", ref)
+    oc2.add_pileup(off, code, qual, anch, 1, call_every=0)
+    return oc.records(), precs, counts, oc2.dump_counts(1, len(off) - 1)
+
+
+@pytest.mark.parametrize("gvcf", [0, 1])
+@pytest.mark.parametrize("depth,n_loci", [(40, 3000), (500, 2500), (2000, 1500)])
+def test_locus_major_pileup_matches_oracle(depth, n_loci, gvcf):
+    """The bench data path (pb2_push_pileup) against the oracle fed the same entries; depth 2000 wraps the 8-bit histogram counters."""
+    from pisces_b200 import synth
+    d = synth.make_pileup(n_loci, depth, seed=depth + gvcf, snv_rate=0.05, del_rate=0.01)
+    orecs, precs, counts, ocounts = _pileup_both(d, gvcf)
+    np.testing.assert_array_equal(counts, ocounts)     # 16-bit variant (full bin dump)
+    assert len(orecs) > 50
+    _compare_records(orecs, precs)                      # 8-bit variant (scoring path)
+
+
+def test_window_noise_model_and_qsum():
+    from pisces_b200 import synth
+    d = synth.make_pileup(1500, 300, seed=5, snv_rate=0.05)
+    orecs, precs, _, _ = _pileup_both(d, 1, noise_model=1)
+    _compare_records(orecs, precs, check_qsum=True)
