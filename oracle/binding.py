@@ -27,7 +27,7 @@ class Config(C.Structure):
         [("no_call_filter", C.c_float)] + \
         [(n, C.c_int32) for n in ("call_mnvs", "max_size_mnv", "max_gap_mnv", "collapse")] + \
         [(n, C.c_float) for n in ("collapse_freq_threshold", "collapse_freq_ratio_threshold")] + \
-        [(n, C.c_int32) for n in ("exclude_mnvs_from_collapsing", "tracked_anchor_size", "output_gvcf", "source_is_stitched", "source_is_collapsed")]
+        [(n, C.c_int32) for n in ("exclude_mnvs_from_collapsing", "tracked_anchor_size", "output_gvcf", "source_is_stitched", "source_is_collapsed", "apply_validation")]
 
 
 class ReadStruct(C.Structure):

@@ -24,7 +24,7 @@ void po_default_config(po_config* c) {
     c->no_call_filter = d.NoCallFilterThreshold; c->call_mnvs = d.CallMNVs; c->max_size_mnv = d.MaxSizeMNV; c->max_gap_mnv = d.MaxGapBetweenMNV; c->collapse = d.Collapse;
     c->collapse_freq_threshold = d.CollapseFreqThreshold; c->collapse_freq_ratio_threshold = d.CollapseFreqRatioThreshold;
     c->exclude_mnvs_from_collapsing = d.ExcludeMNVsFromCollapsing; c->tracked_anchor_size = d.TrackedAnchorSize; c->output_gvcf = d.OutputGvcfFile;
-    c->source_is_stitched = d.SourceIsStitched; c->source_is_collapsed = d.SourceIsCollapsed;
+    c->source_is_stitched = d.SourceIsStitched; c->source_is_collapsed = d.SourceIsCollapsed; c->apply_validation = 1;
 }
 static Config FromC(const po_config* c) {
     Config d;
@@ -38,7 +38,7 @@ static Config FromC(const po_config* c) {
     d.NoCallFilterThreshold = c->no_call_filter; d.CallMNVs = c->call_mnvs; d.MaxSizeMNV = c->max_size_mnv; d.MaxGapBetweenMNV = c->max_gap_mnv; d.Collapse = c->collapse;
     d.CollapseFreqThreshold = c->collapse_freq_threshold; d.CollapseFreqRatioThreshold = c->collapse_freq_ratio_threshold;
     d.ExcludeMNVsFromCollapsing = c->exclude_mnvs_from_collapsing; d.TrackedAnchorSize = c->tracked_anchor_size; d.OutputGvcfFile = c->output_gvcf;
-    d.SourceIsStitched = c->source_is_stitched; d.SourceIsCollapsed = c->source_is_collapsed;
+    d.SourceIsStitched = c->source_is_stitched; d.SourceIsCollapsed = c->source_is_collapsed; d.ApplyValidation = c->apply_validation != 0;
     return d;
 }
 static Read ToRead(const po_read* r) {

@@ -20,6 +20,7 @@ typedef struct po_config {
     int32_t call_mnvs, max_size_mnv, max_gap_mnv, collapse;
     float collapse_freq_threshold, collapse_freq_ratio_threshold;
     int32_t exclude_mnvs_from_collapsing, tracked_anchor_size, output_gvcf, source_is_stitched, source_is_collapsed;
+    int32_t apply_validation;   /* 1: VariantCallingParameters.Validate() derived values (what Program.Main does); 0: raw options as some reference tests build them */
 } po_config;
 
 typedef struct po_read {

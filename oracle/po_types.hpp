@@ -227,9 +227,11 @@ struct Config {
     bool OutputGvcfFile = true;
     // source properties (BamFileAlignmentExtractor.cs:111-153)
     bool SourceIsStitched = false, SourceIsCollapsed = false;
+    bool ApplyValidation = true;   // false: options object built by hand without Validate() (e.g. SomaticVariantCallerFunctionalTests.cs:683-758)
 
     int NoiseLevelUsedForQScoring() const { return ForcedNoiseLevel == -1 ? MinimumBaseCallQuality : ForcedNoiseLevel; }
     void Validate() {
+        if (!ApplyValidation) return;
         if (MinimumFrequencyFilter < MinimumFrequency) MinimumFrequencyFilter = MinimumFrequency;
         if (TargetLODFrequency < MinimumFrequencyFilter) TargetLODFrequency = MinimumFrequencyFilter;
         if (LowDepthFilter < MinimumCoverage) LowDepthFilter = MinimumCoverage;  // checked against VariantCallingParameters.Validate below

@@ -36,7 +36,7 @@ def _fixed(x, decimals):
 
 
 class VcfText:
-    def __init__(self, cfg, filters_enum, genotypes_enum, debug=False, output_bias_files=False):
+    def __init__(self, cfg, filters_enum, genotypes_enum, debug=False, output_bias_files=False, report_rc_counts=False, report_ts_counts=False):
         self.cfg = cfg
         self.FILTERS, self.GENOTYPES = filters_enum, genotypes_enum
         min_freq_filter = cfg.min_frequency_filter if cfg.min_frequency_filter > cfg.min_frequency else None   # VcfFileWriter.cs:334-347
@@ -45,6 +45,7 @@ class VcfText:
             digits = max(digits, _sig_digits(_float_tostring(min_freq_filter)))
         self.vf_decimals = digits
         self.out_sb = debug or output_bias_files or cfg.sb_acceptance < 1   # VcfFileWriter.cs:353-356
+        self.rc, self.ts = report_rc_counts, report_ts_counts
 
     def filter_string(self, rec):
         names = []
@@ -79,4 +80,9 @@ class VcfText:
             sb = min(max(-100.0, rec.gatk_bias_score), 0.0)
             fmt += ":NL:SB"
             sample += f":{rec.noise_level}:{_fixed(sb, 4)}"
+        if self.rc:   # VcfFormatter.cs:283-316
+            m, t = list(rec.collapsed_mut), list(rec.collapsed_total)
+            idx = [0, 1, 4, 5, 6, 7] if self.ts else [0, 1, 2, 3]
+            fmt += ":US"
+            sample += ":" + ",".join(str(m[i]) for i in idx) + "," + ",".join(str(t[i]) for i in idx)
         return "\t".join([chrom, str(rec.pos), ".", rec.ref, alt, str(rec.vq), self.filter_string(rec), f"DP={depth}", fmt, sample])

@@ -41,6 +41,14 @@ def main():
             forced.append([int(t[1]), t[3], alt])
     json.dump(forced, open(os.path.join(HERE, "phix_forced_alleles.json"), "w"))
     print(f"{len(out)} reads, genome {len(fa['phix'])} bp, {len(forced)} forced alleles")
+    # collapsed + stitched golden: src/test/Pisces.Tests/FunctionalTests/SomaticVariantCallerFunctionalTests.cs:683-758
+    _, _, crecs = bamio.read_bam(f"{REF}/Pisces.Tests/TestData/collapsed.test.stitched.bam")
+    cout = [dict(pos0=r["pos0"], flag=r["flag"], mapq=r["mapq"], cigar=r["cigar"], seq=r["seq"], qual=r["qual"], xd=r["tags"].get("XD"),
+                 xr=r["tags"].get("XR"), xv=r["tags"].get("XV"), xw=r["tags"].get("XW")) for r in crecs]
+    json.dump(cout, open(os.path.join(HERE, "collapsed_stitched_reads.json"), "w"))
+    lines = [l for l in open(f"{REF}/Pisces.Tests/TestData/test_truth.stitched.genome.vcf") if not l.startswith("#")]
+    open(os.path.join(HERE, "collapsed_stitched.records.vcf"), "w").writelines(lines)
+    print(f"{len(cout)} collapsed/stitched reads, {len(lines)} golden records")
 
 
 if __name__ == "__main__":

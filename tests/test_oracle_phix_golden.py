@@ -48,3 +48,22 @@ def test_phix_full_text_golden(min_vq, forced, golden):
     assert len(got) == len(exp)
     for a, b in zip(got, exp):
         assert a == b
+
+
+def test_collapsed_stitched_full_text_golden():
+    """src/test/Pisces.Tests/FunctionalTests/SomaticVariantCallerFunctionalTests.cs:683-758: collapsed.test.stitched.bam against the mock chr1
+    built at :729-738 -> test_truth.stitched.genome.vcf (XD stitched directions, XV/XW/XR collapsed-read categories, the 12-field US tag).
+    That test fills PiscesApplicationOptions by hand, so VariantCallingParameters.Validate() never runs (LowDepthFilter stays null)."""
+    reads = json.load(open(os.path.join(G, "collapsed_stitched_reads.json")))
+    seq = "N" * (9770498 - 1) + ("GAAGTAACAACGCAGGATGCCCCCTGGGGTGGACTGCCCCATGGAATTCTGGACCAAGGAGGAGAATCAGAGCGTTGTGGTTGACTTCCTGCTGCCCACAGGGGTCTACCTGAACTTCCCTGTGTCCCGCAATGCCAACCTC"
+                                 "AGCACCATCAAGCAGGTATGGCCTCCATC")
+    kw = dict(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, source_is_stitched=1, source_is_collapsed=1, apply_validation=0)
+    c = ob.Caller(ob.default_config(**kw), "chr1", seq)
+    for r in reads:
+        c.add_read(ob.SimpleRead(r["pos0"] + 1, r["seq"], r["cigar"], r["qual"], flag=r["flag"], mapq=r["mapq"], has_tags=True, xd=r["xd"], xr=r["xr"],
+                                 xv=r["xv"], xw=r["xw"]))
+    c.finish()
+    vt = VcfText(ob.default_config(**kw), ob.FILTERS, ob.GENOTYPES, debug=True, output_bias_files=True, report_rc_counts=True, report_ts_counts=True)
+    got = [vt.line("chr1", r) for r in c.records()]
+    exp = [l.rstrip("\n") for l in open(os.path.join(G, "collapsed_stitched.records.vcf"))]
+    assert got == exp
