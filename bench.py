@@ -212,7 +212,10 @@ def main_ours(a):
 
     # ---- roofline of the dominant (only) kernel: algorithmic bytes / CUDA-event duration on the launching stream
     n_ref_records = a.loci if a.gvcf else 0
-    algo_bytes = synth.algorithmic_bytes(a.loci, n_entries, n_records + n_ref_records)
+    # point alleles (SNV / reference) never read the anchor/collapsed byte: without collapsed-read tracking the hot kernel skips that plane,
+    # and the algorithmic bytes are SURVEY 8d's 2*D + 8 + 96*E form
+    third_byte = bool(cfg.expect_collapsed)
+    algo_bytes = synth.algorithmic_bytes(a.loci, n_entries, n_records + n_ref_records, third_byte=third_byte)
     hot_ms = st["hot_ms"] / max(1, st["hot_launches"])
     achieved = algo_bytes / (hot_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback"
@@ -233,7 +236,8 @@ def main_ours(a):
                        "l2": "inputs (%.2f GB per GPU) larger than L2, no flush needed" % (3 * n_entries / 1e9), "parallelism": f"interval-sharded x{world}"},
             "gpu_launches": st["total_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "pileup_count_score_kernel", "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": hot_ms},
+                         "kernel": "pileup_vcount_score_kernel", "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_entry": 3 if third_byte else 2,
+                         "kernel_ms": hot_ms},
             "clocks": sampler.summary()}
 
     # ---- end to end through the C ABI with HOST buffers: pinned H2D of the step's pileup, tile staging, call, D2H of the records

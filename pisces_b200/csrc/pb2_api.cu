@@ -1,6 +1,7 @@
 // C ABI of libpisces_b200.so (include/pisces_b200.h): handle, staging, launches. No CPU compute path exists here: every
 // entry point that produces counts or calls runs the CUDA kernels in pb2_kernels.cu and fails with PB2_ERR_CUDA otherwise.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -166,6 +167,8 @@ static void derive_config(pb2_handle* h) {
     d.output_gvcf = c.output_gvcf; d.expect_stitched = c.expect_stitched; d.expect_collapsed = c.expect_collapsed;
     d.have_intervals = h->have_intervals ? 1 : 0;
     d.want_qsum = c.want_sum_base_quality;
+    d.vq_error_rate = std::pow(10.0, -1 * (double)d.noise_level / 10.0);                      // QtoP: double division (MathOperations.cs:7-10)
+    d.sb_noise = std::pow(10.0, (double)((float)(-1 * d.noise_level) / 10.0f));               // float exponent (StrandBiasCalculator.cs:32)
 }
 
 extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
@@ -330,6 +333,7 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     CU(h, exclusive_scan_i64(tile_bytes, s.tile_base, s.n_tiles + 1, temp, temp_bytes, nullptr, st));
     CU(h, cudaMemcpyAsync(&s.plane_bytes, s.tile_base + s.n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
+    if (s.max_depth >= 65000) return fail(h, PB2_ERR_UNSUPPORTED, "pb2_push_pileup: a locus with 65000 or more entries (16-bit counters)");
     const size_t pb = (size_t)std::max<int64_t>(s.plane_bytes, 16);
     CU(h, cudaMalloc(&s.code, pb));
     CU(h, cudaMalloc(&s.qual, pb));
@@ -375,7 +379,7 @@ static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* 
     out.pending = s.pending; out.pending_count = s.counters + 2; out.pending_capacity = s.pending_capacity;
     CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
     CU(h, cudaEventRecord(h->ev0, st));
-    CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, s.max_depth < kNarrowMaxDepth, st));
+    CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, s.max_depth, st));
     CU(h, cudaEventRecord(h->ev1, st));
     unsigned long long cnt[2];
     CU(h, cudaMemcpyAsync(cnt, s.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));

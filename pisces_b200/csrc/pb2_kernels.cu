@@ -12,6 +12,9 @@
 
 namespace pb2 {
 
+constexpr uint32_t kStagedN = 7;                 // staged allele code of N (the external pb2_pileup_csr code is AlleleType.N = 4)
+constexpr uint32_t kPadCode4 = 0x07070707u;      // four PAD code bytes: N | Forward
+
 // ------------------------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {  // 16-byte streaming load: read once, do not pollute L1
     uint4 r;
@@ -43,6 +46,7 @@ __global__ void tile_layout_kernel(const int64_t* __restrict__ off, int64_t n_lo
 //   * a Deletion entry below the quality bar is never counted (RegionStateManager.cs:170-177) -> replaced by a PAD entry;
 //   * the tail of a locus' last 16-entry chunk is filled with PAD entries;
 //   * PAD = (code N|Forward, qual 255, anchor 0): it lands in bin [N][Forward][0] and pad[i] of them are subtracted at read-out;
+//   * N is staged as allele code 7 (kStagedN) so that the quality rule `q < minBQ -> N` is a byte-parallel OR with 7 in the hot loop;
 //   * candidate flags are kept only where they can matter: the base is a usable (q >= minBQ, A/C/G/T) mismatch against an A/C/G/T
 //     reference base. Every flagged entry the hot kernel meets is then a real SNV-candidate exception.
 __global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8_t* __restrict__ code, const uint8_t* __restrict__ qual,
@@ -68,7 +72,7 @@ __global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8
             const int64_t dst = base + (int64_t)slot * kChunk;
             const int n = min(kChunk, d - c * kChunk);
             const int64_t s = src + (int64_t)c * kChunk;
-            uint32_t wc[4] = {0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u};
+            uint32_t wc[4] = {kPadCode4, kPadCode4, kPadCode4, kPadCode4};
             uint32_t wq[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
             uint32_t wa[4] = {0u, 0u, 0u, 0u};
             for (int k = 0; k < n; k++) {
@@ -76,10 +80,11 @@ __global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8
                 const int allele = cb & 7;
                 const bool lowq = (int)qb < min_bq;
                 if (allele > AT_DEL || ((cb >> 3) & 3) > DIR_S || (ab & 15) >= kNumAnchors || (allele == AT_DEL && lowq)) {
-                    cb = 0x04; qb = 0xff; ab = 0; npad++;           // not countable: PAD
+                    cb = kStagedN; qb = 0xff; ab = 0; npad++;       // not countable: PAD
                 } else if (lowq || allele >= AT_N || ref_allele == AT_N || allele == ref_allele) {
                     cb &= 0x1f;                                     // flags cannot matter here
                 }
+                if ((cb & 7) == AT_N) cb |= kStagedN;
                 const int sh = (k & 3) * 8;
                 wc[k >> 2] = (wc[k >> 2] & ~(0xffu << sh)) | (cb << sh);
                 wq[k >> 2] = (wq[k >> 2] & ~(0xffu << sh)) | (qb << sh);
@@ -131,7 +136,8 @@ __device__ __forceinline__ int hist_slot(int warp, int lane) {
 }
 
 // RMxNCalculator.ComputeRMxNLengthForIndel (:49-95) on the device-resident chromosome; variant_bases has length <= 1 for point alleles
-__device__ int rmxn_length_for_indel(int variant_position, const char* vb, int length, const uint8_t* __restrict__ ref, int64_t ref_len, int max_unit) {
+// `cap`: counting stops at cap repeats; callers only compare min/max of these counts against cap, which capping preserves.
+__device__ int rmxn_length_for_indel(int variant_position, const char* vb, int length, const uint8_t* __restrict__ ref, int64_t ref_len, int max_unit, int cap) {
     int best = 0;
     const int first = length - min(max_unit, length);
     for (int pass = 0; pass < 2; pass++) {          // prefixes, then suffixes (bookends)
@@ -139,7 +145,7 @@ __device__ int rmxn_length_for_indel(int variant_position, const char* vb, int l
             const int blen = length - i;
             const char* book = pass == 0 ? vb : vb + i;
             int64_t back = variant_position;
-            while (true) {
+            for (int steps = 0; steps < cap; steps++) {   // going back further than cap units cannot change a count that is capped at cap
                 const int64_t nb = back - blen;
                 if (nb < 0) break;
                 bool eq = true;
@@ -156,6 +162,7 @@ __device__ int rmxn_length_for_indel(int variant_position, const char* vb, int l
                 if (!eq) break;
                 reps++;
                 cur += blen;
+                if (reps >= cap) break;
             }
             best = max(best, reps);
         }
@@ -166,9 +173,10 @@ __device__ int rmxn_length_for_indel(int variant_position, const char* vb, int l
 __device__ bool rmxn_should_filter_snv(int position, char ref_base, char alt_base, float freq, const DeviceConfig& cfg, const uint8_t* __restrict__ ref, int64_t ref_len) {
     if (freq >= cfg.rmxn_freq_limit) return false;
     if (cfg.rmxn_max_len < 0 || cfg.rmxn_min_reps < 0 || ref == nullptr) return false;
-    const int c1 = rmxn_length_for_indel(position - 1, &ref_base, 1, ref, ref_len, cfg.rmxn_max_len);
-    const int i1 = rmxn_length_for_indel(position + 1 - 1, &alt_base, 1, ref, ref_len, cfg.rmxn_max_len);
-    const int i2 = rmxn_length_for_indel(position - 1, &alt_base, 1, ref, ref_len, cfg.rmxn_max_len);
+    const int cap = max(cfg.rmxn_min_reps, 1);
+    const int c1 = rmxn_length_for_indel(position - 1, &ref_base, 1, ref, ref_len, cfg.rmxn_max_len, cap);
+    const int i1 = rmxn_length_for_indel(position + 1 - 1, &alt_base, 1, ref, ref_len, cfg.rmxn_max_len, cap);
+    const int i2 = rmxn_length_for_indel(position - 1, &alt_base, 1, ref, ref_len, cfg.rmxn_max_len, cap);
     return min(c1, max(i1, i2)) >= cfg.rmxn_min_reps;
 }
 
@@ -207,12 +215,16 @@ __device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int posit
     sb.bias = 0; sb.gatk = 0; sb.acceptable = false; sb.var_both = false; sb.cov_both = false;   // new BiasResults()
     if (allele_support > 0) {
         int nl = cfg.noise_level;
-        if (cfg.noise_model == 1) nl = (int)(-10 * log10(lc.qsum / total));   // NoiseModel.Window (AlleleCaller.cs:215-218)
+        double error_rate = cfg.vq_error_rate;
+        if (cfg.noise_model == 1) {   // NoiseModel.Window (AlleleCaller.cs:215-218)
+            nl = (int)(-10 * log10(lc.qsum / total));
+            error_rate = q_to_p((double)nl);
+        }
         nl_applied = nl;
-        vq = (total == 0) ? 0 : poisson_qscore(allele_support, total, nl, cfg.max_vq);
+        vq = (total == 0) ? 0 : poisson_qscore(allele_support, total, error_rate, cfg.max_vq);
     }
     if (!is_ref && vq < cfg.min_vq) return false;
-    if (allele_support > 0) sb = strand_bias(cov, sup, cfg.noise_level, (double)cfg.sb_acceptance, cfg.sb_model);
+    if (allele_support > 0) sb = strand_bias(cov, sup, cfg.sb_noise, (double)cfg.sb_acceptance, cfg.sb_model);
 
     // AlleleProcessor.Process / ApplyFilters
     const float all_reads = (float)(total + nocalls);
@@ -264,13 +276,77 @@ __device__ __forceinline__ void store_record(pb2_call_record* dst, const pb2_cal
     for (int i = 0; i < (int)(sizeof(pb2_call_record) / 16); i++) d[i] = s[i];
 }
 
+// After a locus' counts are known: screen its SNV candidates with the cheap bars of AlleleCaller.IsCallable (:246-251) and queue the locus for
+// score_pending_kernel if any survives (the FP64 chain then runs lane-dense instead of at 1/32 lane utilisation); otherwise, in gVCF mode,
+// score and emit its reference allele in place.
+constexpr int kCtaPending = 64;   // per-CTA queue of the vertical-counter kernel: 64 loci x 4 alleles = one 256-thread scoring pass
+
+__device__ __forceinline__ void finish_locus(const LocusCounts& lc, int any, int64_t locus, int ref_allele, const TilePileup& in, const HotInputsExtra& ex,
+                                             const HotOutputs& out, const DeviceConfig& cfg, PendingLocus* cta_queue = nullptr, int* cta_count = nullptr) {
+    const int gapped = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
+    unsigned cand_mask = 0;
+    if (ref_allele != AT_N) {
+        int total = 0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) total += lc.c[AT_A][d] + lc.c[AT_C][d] + lc.c[AT_G][d] + lc.c[AT_T][d] + lc.c[AT_DEL][d];
+#pragma unroll
+        for (int alt = 0; alt < 4; alt++) {
+            const int sup = lc.c[alt][0] + lc.c[alt][1] + lc.c[alt][2];
+            if (alt == ref_allele || sup == 0) continue;
+            if (total < cfg.min_coverage && !cfg.output_gvcf) continue;
+            if (total != 0 && allele_frequency(sup, total) < cfg.min_frequency) continue;
+            cand_mask |= 1u << alt;
+        }
+    }
+    const bool has_ext_variant = ex.locus_has_variant ? (ex.locus_has_variant[locus] != 0) : false;
+    if (cand_mask != 0) {
+        PendingLocus* dst = nullptr;
+        if (cta_queue != nullptr) {
+            const int s = atomicAdd(cta_count, 1);
+            if (s < kCtaPending) dst = cta_queue + s;
+        }
+        if (dst == nullptr) {   // no CTA queue (198-bin kernel) or it is full: the global queue, scored by score_pending_kernel
+            const unsigned long long slot = atomicAdd(out.pending_count, 1ull);
+            if ((int64_t)slot < out.pending_capacity) dst = out.pending + slot;
+        }
+        if (dst != nullptr) {
+            PendingLocus pl;
+            pl.locus = (int32_t)locus;
+            pl.cand_mask = (int32_t)cand_mask | (has_ext_variant ? 0x100 : 0) | (any > 0 ? 0x200 : 0);
+#pragma unroll
+            for (int a = 0; a < kNumAlleles; a++)
+#pragma unroll
+                for (int d = 0; d < kNumDirs; d++) pl.c[a * kNumDirs + d] = lc.c[a][d];
+            pl.gapped = gapped;
+            pl.pad_ = 0;
+            pl.qsum = lc.qsum;
+            const uint4* sp = reinterpret_cast<const uint4*>(&pl);
+            uint4* dp = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(PendingLocus) / 16); i++) dp[i] = sp[i];
+        }
+        if (out.ref_records != nullptr) out.ref_valid[locus] = 0;   // decided when the queued locus is scored
+    } else if (out.ref_records != nullptr) {
+        // RegionState.GetAllCandidates: a Reference candidate per position when gVCF; zero-coverage positions only with intervals (:446)
+        const bool emit = cfg.output_gvcf && !has_ext_variant && (cfg.have_intervals || any > 0);
+        if (emit) {
+            const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+            pb2_call_record r;
+            score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex.chr_seq, ex.chr_len, r);
+            store_record(out.ref_records + locus, r);
+        }
+        out.ref_valid[locus] = emit ? 1 : 0;
+    }
+}
+
 // Histogram rows are allele-minor: row = allele + 6 * direction, bin = row * 11 + anchor (0..197); [N][Forward][0] (bin 44) also absorbs PADs.
 constexpr int kPadBin = (AT_N + 6 * DIR_F) * kNumAnchors + 0;
 
 // Four entries at a time with byte-parallel arithmetic: quality test, N-forcing and the bin index never leave the packed word; only the
 // shared-memory read-modify-write is per entry.
 __device__ __forceinline__ uint32_t bins_of_word(uint32_t c4, uint32_t q4, uint32_t a4, uint32_t minbq4) {
-    const uint32_t al4 = c4 & 0x07070707u;
+    uint32_t al4 = c4 & 0x07070707u;
+    al4 -= (al4 & (al4 >> 1) & (al4 >> 2) & 0x01010101u) * 3u;        // staged N (7) -> AlleleType.N (4)
     const uint32_t dr6 = ((c4 >> 3) & 0x03030303u) * 6u;            // per byte <= 12
     const uint32_t row4 = al4 + dr6;                                  // <= 17
     const uint32_t rowN4 = dr6 + 0x04040404u;                         // the N row of the same direction
@@ -295,7 +371,7 @@ __device__ __forceinline__ void count_word(uint32_t c4, uint32_t q4, uint32_t a4
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint32_t code = (c4 >> (8 * k)) & 0xffu, q = (q4 >> (8 * k)) & 0xffu, an = (a4 >> (8 * k)) & 0xffu;
-            const int allele = code & 7;
+            const int allele = code & 7;   // staged: A,G,C,T = 0..3, Del = 5, N = 7
             const bool usable = allele == AT_DEL || (allele < AT_N && (int)q >= min_bq);   // counted as something other than N (PADs are N)
             if (kWantQsum) { if (usable && allele != AT_DEL) qsum += q_lut[q]; }   // Σ over A,C,G,T (Deletion entries carry no base quality, :191)
             if (kCollapsed) {
@@ -372,7 +448,7 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
         int extra_pad = 0;   // whole PAD chunks counted by lanes that ran out of entries before the longest lane of the tile
 
         // software pipeline: chunk c+1 is in flight while chunk c is histogrammed; lanes without a chunk process a PAD chunk
-        const uint4 pad_c = make_uint4(0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u), pad_q = make_uint4(~0u, ~0u, ~0u, ~0u), pad_a = make_uint4(0, 0, 0, 0);
+        const uint4 pad_c = make_uint4(kPadCode4, kPadCode4, kPadCode4, kPadCode4), pad_q = make_uint4(~0u, ~0u, ~0u, ~0u), pad_a = make_uint4(0, 0, 0, 0);
         uint4 nc = pad_c, nq = pad_q, na = pad_a;
         {
             const bool active = 0 < nchunks;
@@ -454,54 +530,252 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
         }
         if (!have_locus) continue;
 
-        // ---- candidates. Cheap tests here (coverage / frequency bars of AlleleCaller.IsCallable, :246-251); a locus with a surviving SNV
-        // candidate is queued for score_pending_kernel, where lanes are dense, instead of being scored here at 1/32 lane utilisation.
-        const int gapped = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
-        unsigned cand_mask = 0;
-        if (ref_allele != AT_N) {
-            int total = 0;
+        finish_locus(lc, any, locus, ref_allele, in, ex, out, cfg);
+    }
+}
+
+// A queued locus scored by 4 adjacent lanes: lane j takes alternate allele j of (A, C, G, T) (the (ref, alt) order of AlleleCaller.cs:172-176 is
+// restored when the records are sorted), then lane 0 the reference allele if nothing was called there (:146-147). Must be called by full warps.
+__device__ __forceinline__ void score_queued_locus(const PendingLocus* item /* nullptr: idle group */, int j, const TilePileup& in, const HotInputsExtra& ex,
+                                                   const HotOutputs& out, const DeviceConfig& cfg) {
+    const int lane = threadIdx.x & 31;
+    bool called = false;
+    LocusCounts lc;
+    int64_t locus = 0;
+    int ref_allele = AT_N, position = 0, cand_mask = 0, gapped = 0;
+    if (item != nullptr) {
 #pragma unroll
-            for (int d = 0; d < 3; d++) total += lc.c[AT_A][d] + lc.c[AT_C][d] + lc.c[AT_G][d] + lc.c[AT_T][d] + lc.c[AT_DEL][d];
+        for (int a = 0; a < kNumAlleles; a++)
 #pragma unroll
-            for (int alt = 0; alt < 4; alt++) {
-                const int sup = lc.c[alt][0] + lc.c[alt][1] + lc.c[alt][2];
-                if (alt == ref_allele || sup == 0) continue;
-                if (total < cfg.min_coverage && !cfg.output_gvcf) continue;
-                if (total != 0 && allele_frequency(sup, total) < cfg.min_frequency) continue;
-                cand_mask |= 1u << alt;
+            for (int d = 0; d < kNumDirs; d++) lc.c[a][d] = item->c[a * kNumDirs + d];
+        lc.qsum = item->qsum;
+        locus = item->locus;
+        cand_mask = item->cand_mask;
+        gapped = item->gapped;
+        ref_allele = allele_of_base(in.ref_base[locus]);
+        position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+        const int order[4] = {AT_A, AT_C, AT_G, AT_T};
+        const int alt = order[j];
+        if ((cand_mask >> alt) & 1) {
+            pb2_call_record r;
+            if (score_point_allele(lc, position, ref_allele, alt, gapped, cfg, ex.chr_seq, ex.chr_len, r)) {
+                called = true;
+                const unsigned long long slot = atomicAdd(out.var_count, 1ull);
+                if ((int64_t)slot < out.var_capacity) store_record(out.var_records + slot, r);
             }
         }
-        const bool has_ext_variant = ex.locus_has_variant ? (ex.locus_has_variant[locus] != 0) : false;
-        if (cand_mask != 0) {
-            const unsigned long long slot = atomicAdd(out.pending_count, 1ull);
-            if ((int64_t)slot < out.pending_capacity) {
-                PendingLocus pl;
-                pl.locus = (int32_t)locus;
-                pl.cand_mask = (int32_t)cand_mask | (has_ext_variant ? 0x100 : 0) | (any > 0 ? 0x200 : 0);
-#pragma unroll
-                for (int a = 0; a < kNumAlleles; a++)
-#pragma unroll
-                    for (int d = 0; d < kNumDirs; d++) pl.c[a * kNumDirs + d] = lc.c[a][d];
-                pl.gapped = gapped;
-                pl.pad_ = 0;
-                pl.qsum = lc.qsum;
-                const uint4* sp = reinterpret_cast<const uint4*>(&pl);
-                uint4* dp = reinterpret_cast<uint4*>(out.pending + slot);
-#pragma unroll
-                for (int i = 0; i < (int)(sizeof(PendingLocus) / 16); i++) dp[i] = sp[i];
-            }
-            if (out.ref_records != nullptr) out.ref_valid[locus] = 0;   // decided by score_pending_kernel
-        } else if (out.ref_records != nullptr) {
-            // RegionState.GetAllCandidates: a Reference candidate per position when gVCF; zero-coverage positions only with intervals (:446)
-            const bool emit = cfg.output_gvcf && !has_ext_variant && (cfg.have_intervals || any > 0);
-            if (emit) {
-                const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
-                pb2_call_record r;
-                score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex.chr_seq, ex.chr_len, r);
-                store_record(out.ref_records + locus, r);
-            }
-            out.ref_valid[locus] = emit ? 1 : 0;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, called);
+    if (item != nullptr && j == 0 && out.ref_records != nullptr) {
+        const bool variant_called = ((cand_mask & 0x100) != 0) || (((b >> (lane & ~3)) & 0xfu) != 0);
+        const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (cand_mask & 0x200));
+        if (emit) {
+            pb2_call_record r;
+            score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex.chr_seq, ex.chr_len, r);
+            store_record(out.ref_records + locus, r);
         }
+        out.ref_valid[locus] = emit ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the hot kernel: vertical counters
+// Point alleles (Reference, SNV) only ever read anchor-summed counts (CoverageCalculator.CalculateSinglePoint, RegionState.GetAllCandidates), so
+// this kernel counts 18 rows (allele x direction) [+ 8 collapsed-read types] instead of 198 bins and keeps them in REGISTERS as bit-sliced
+// ("vertical") counters: plane P[i] holds bit i of all row counters, one row per bit position. An entry is a one-hot word 1 << row; sixteen
+// entries are added with a carry-save adder tree (two LOP3 per 3:2 compressor), the last carry ripples through the high planes. No shared
+// memory, no atomics, no read-modify-write chain — the loop is pure ALU work next to two (three with collapsed reads) coalesced 16-byte
+// loads per lane per step, and the anchor plane is not read at all. The 198-bin kernel above remains for pb2_get_counts (IAlleleSource).
+constexpr int kVRows = 24;   // bit (direction * 8 + staged allele) for the 18 used rows; bits 24..31 = ReadCollapsedType 0..7
+
+__device__ __forceinline__ void csa(uint32_t& sum, uint32_t& carry, uint32_t a, uint32_t b, uint32_t c) {
+    carry = (a & b) | (a & c) | (b & c);
+    sum = a ^ b ^ c;
+}
+// Rows of four entries after the quality rule, byte-parallel. Staged code bytes carry allele' | direction << 3 in their low 5 bits with N staged
+// as 7, so row = direction * 8 + allele' is the low 5 bits as they are and `q < minBQ -> N` (RegionStateManager.cs:180-181) is an OR with 7.
+// The ALU pipe (LOP3/SHF) is this kernel's bottleneck: the subtract and the x7 are written as multiplies to run on the FMA pipe.
+__device__ __forceinline__ uint32_t rows_of_word(uint32_t c4, uint32_t q4, uint32_t minbq4) {
+    const uint32_t d = (q4 | 0x80808080u) + (0u - minbq4);          // bit 7 of a byte set <=> q >= minBQ (no borrow crosses bytes)
+    const uint32_t low = ~(d >> 7) & 0x01010101u;                   // 1 where q < minBQ
+    return (c4 & 0x1f1f1f1fu) | (low * 7u);
+}
+template <bool kCollapsed>
+__device__ __forceinline__ uint32_t onehot(uint32_t rows4, uint32_t a4, int k) {
+    // byte k to the low bits with a high-multiply (FMA pipe) instead of a shift (ALU pipe); the variable shift uses the low 5 bits
+    const uint32_t sh = k == 0 ? rows4 : __umulhi(rows4, 1u << (32 - 8 * k));
+    uint32_t v = 1u << (sh & 31u);
+    if (kCollapsed) {
+        // CollapsedRegionState.AddCollapsedReadCount (:28-44): any entry not counted as N, typed reads only
+        const uint32_t ct = (a4 >> (8 * k + 4)) & 0xfu;
+        const bool usable = (sh & 7u) != kStagedN;
+        if (ct != 0 && usable) {
+            v |= 1u << (kVRows + ct - 1);
+            if (ct - 1 == 4 || ct - 1 == 6) v |= 1u << (kVRows + 2);
+            else if (ct - 1 == 5 || ct - 1 == 7) v |= 1u << (kVRows + 3);
+        }
+    }
+    return v;
+}
+// counter of row r out of the planes: Σ_i bit r of P[i] << i  (mask on the ALU pipe, the shift-accumulate as a multiply on the FMA pipe)
+template <int NP>
+__device__ __forceinline__ int vcount_row(const uint32_t (&P)[NP], int r) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        const uint32_t t = P[i] & (1u << r);
+        v += (i >= r) ? t * (1u << (i - r)) : __umulhi(t, 1u << (32 - (r - i)));
+    }
+    return (int)v;
+}
+
+template <int NP, bool kWantQsum, bool kCollapsed>
+__global__ void __launch_bounds__(256, 4)
+pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, DeviceConfig cfg, int* __restrict__ tile_counter) {
+    __shared__ int s_tile[8];
+    __shared__ double q_lut[kWantQsum ? 256 : 1];
+    __shared__ __align__(16) PendingLocus s_pend[kCtaPending];
+    __shared__ int s_pend_n;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_pend_n = 0;
+    if (kWantQsum) {
+        for (int q = threadIdx.x; q < 256; q += blockDim.x) q_lut[q] = pow(10.0, (double)((float)(-q) / 10.0f));  // RegionStateManager.cs:191 (float exponent)
+    }
+    __syncthreads();
+    const uint32_t minbq4 = (uint32_t)cfg.min_bq * 0x01010101u;
+
+    while (true) {
+        if (lane == 0) s_tile[warp] = atomicAdd(tile_counter, 1);
+        __syncwarp();
+        const int tile = s_tile[warp];
+        __syncwarp();
+        if (tile >= in.n_tiles) break;
+
+        const int64_t locus = (int64_t)tile * kTileLoci + lane;
+        const bool have_locus = locus < in.n_loci;
+        const int depth = have_locus ? in.depth[locus] : 0;
+        const int nchunks = (depth + kChunk - 1) / kChunk;
+        const int max_chunks = __reduce_max_sync(0xffffffffu, nchunks);
+        int64_t base = in.tile_base[tile];
+        double qsum = 0.0;
+        int extra_pad = 0;   // whole PAD chunks counted by lanes that ran out of entries before the longest lane of the tile
+        uint32_t P[NP];
+#pragma unroll
+        for (int i = 0; i < NP; i++) P[i] = 0;
+
+        // software pipeline: chunk c+1 is in flight (registers) and chunk c+2 is being prefetched into L2 while chunk c is counted
+        const uint4 pad_c = make_uint4(kPadCode4, kPadCode4, kPadCode4, kPadCode4), pad_q = make_uint4(~0u, ~0u, ~0u, ~0u), pad_a = make_uint4(0, 0, 0, 0);
+        uint4 nc = pad_c, nq = pad_q, na = pad_a;
+        {
+            const bool active = 0 < nchunks;
+            const unsigned m = __ballot_sync(0xffffffffu, active);
+            if (active) {
+                const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
+                nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o);
+                if (kCollapsed) na = ldg_stream(in.anch + o);
+            }
+            base += (int64_t)__popc(m) * kChunk;
+        }
+        for (int c = 0; c < max_chunks; c++) {
+            const uint4 wc = nc, wq = nq, wa = na;
+            if (c >= nchunks) extra_pad += kChunk;
+            nc = pad_c; nq = pad_q; na = pad_a;
+            {
+                const bool active = (c + 1) < nchunks;
+                const unsigned m = __ballot_sync(0xffffffffu, active);
+                if (active) {
+                    const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
+                    nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o);
+                    if (kCollapsed) na = ldg_stream(in.anch + o);
+                }
+                base += (int64_t)__popc(m) * kChunk;
+                const int64_t pf = min(base + lane * kChunk, in.plane_bytes - kChunk);
+                prefetch_l2(in.code + pf); prefetch_l2(in.qual + pf);
+                if (kCollapsed) prefetch_l2(in.anch + pf);
+            }
+            const uint32_t r0 = rows_of_word(wc.x, wq.x, minbq4), r1 = rows_of_word(wc.y, wq.y, minbq4), r2 = rows_of_word(wc.z, wq.z, minbq4),
+                           r3 = rows_of_word(wc.w, wq.w, minbq4);
+            // weight 1: P[0] + 16 one-hot words -> P[0] and eight weight-2 carries
+            uint32_t s0, s1, s2, s3, s4, t0, t1, k0, k1, k2, k3, k4, k5, k6, k7;
+            csa(s0, k0, onehot<kCollapsed>(r0, wa.x, 0), onehot<kCollapsed>(r0, wa.x, 1), onehot<kCollapsed>(r0, wa.x, 2));
+            csa(s1, k1, onehot<kCollapsed>(r0, wa.x, 3), onehot<kCollapsed>(r1, wa.y, 0), onehot<kCollapsed>(r1, wa.y, 1));
+            csa(s2, k2, onehot<kCollapsed>(r1, wa.y, 2), onehot<kCollapsed>(r1, wa.y, 3), onehot<kCollapsed>(r2, wa.z, 0));
+            csa(s3, k3, onehot<kCollapsed>(r2, wa.z, 1), onehot<kCollapsed>(r2, wa.z, 2), onehot<kCollapsed>(r2, wa.z, 3));
+            csa(s4, k4, onehot<kCollapsed>(r3, wa.w, 0), onehot<kCollapsed>(r3, wa.w, 1), onehot<kCollapsed>(r3, wa.w, 2));
+            csa(t0, k5, s0, s1, s2);
+            csa(t1, k6, s3, s4, onehot<kCollapsed>(r3, wa.w, 3));
+            csa(P[0], k7, P[0], t0, t1);
+            // weight 2: P[1] + 8 carries -> P[1] and four weight-4 carries
+            uint32_t u0, u1, u2, m0, m1, m2, m3;
+            csa(u0, m0, k0, k1, k2);
+            csa(u1, m1, k3, k4, k5);
+            csa(u2, m2, k6, k7, P[1]);
+            csa(P[1], m3, u0, u1, u2);
+            // weight 4: P[2] + 4 carries -> P[2] and two weight-8 carries
+            uint32_t w0, n0, n1;
+            csa(w0, n0, m0, m1, m2);
+            csa(P[2], n1, w0, m3, P[2]);
+            // weight 8: P[3] + 2 carries -> P[3] and one weight-16 carry, which ripples through the high planes
+            uint32_t carry;
+            csa(P[3], carry, n0, n1, P[3]);
+#pragma unroll
+            for (int i = 4; i < NP; i++) { const uint32_t t = P[i] & carry; P[i] ^= carry; carry = t; }
+
+            if (kWantQsum) {   // Σ 10^(-q/10f) over entries counted as A/C/G/T (Deletion entries carry no base quality, :191)
+                const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) {
+                    const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu, q = (qw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                    if ((code & 7) < AT_N && (int)q >= cfg.min_bq) qsum += q_lut[q];
+                }
+            }
+            // flagged entries (rare after staging normalisation): SNV-candidate bookkeeping the counts cannot express -> side list
+            if (((wc.x | wc.y | wc.z | wc.w) & 0xe0e0e0e0u) != 0) {
+                const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w};
+                for (int k = 0; k < kChunk; k++) {
+                    const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                    if ((code & 0xe0u) == 0) continue;
+                    const unsigned long long slot = atomicAdd(out.exc_count, 1ull);
+                    if ((int64_t)slot < out.exc_capacity) {
+                        out.exc_entries[2 * slot] = (uint32_t)locus;
+                        out.exc_entries[2 * slot + 1] = code | (((qw[k >> 2] >> ((k & 3) * 8)) & 0xffu) << 8);
+                    }
+                }
+            }
+        }
+
+        // ---- read the vertical counters out
+        LocusCounts lc;
+        lc.qsum = qsum;
+        int any = 0;
+        const int npad = (have_locus ? in.pad[locus] : 0) + extra_pad;
+#pragma unroll
+        for (int a = 0; a < kNumAlleles; a++)
+#pragma unroll
+            for (int d = 0; d < kNumDirs; d++) {
+                int cnt = vcount_row<NP>(P, d * 8 + (a == AT_N ? (int)kStagedN : a));
+                if (a == AT_N && d == DIR_F) cnt -= npad;
+                lc.c[a][d] = cnt;
+                any += cnt;
+            }
+        if (kCollapsed) {
+            if (out.collapsed_out != nullptr && have_locus) {
+#pragma unroll
+                for (int t = 0; t < kNumCollapsed; t++) out.collapsed_out[locus * kNumCollapsed + t] = vcount_row<NP>(P, kVRows + t);
+            }
+        }
+        if (!have_locus) continue;
+        const int ref_allele = allele_of_base(in.ref_base[locus]);
+        finish_locus(lc, any, locus, ref_allele, in, ex, out, cfg, s_pend, &s_pend_n);
+    }
+
+    // ---- the CTA's queued loci: 4 lanes per locus, all 256 threads at once. Other CTAs of this SM are still counting, so this FP64 latency
+    // chain overlaps their work; only the last CTAs' pass is exposed at the end of the kernel.
+    __syncthreads();
+    {
+        const int n = min(s_pend_n, kCtaPending);
+        const int item = threadIdx.x >> 2;
+        score_queued_locus(item < n ? &s_pend[item] : nullptr, threadIdx.x & 3, in, ex, out, cfg);
     }
 }
 
@@ -552,30 +826,43 @@ size_t hot_kernel_smem_bytes(bool narrow, bool collapsed) {
 }
 
 cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
-                              bool allow_narrow, cudaStream_t stream) {
+                              int max_depth, cudaStream_t stream) {
     if (in.n_tiles == 0) return cudaSuccess;
     const bool want_q = cfg.want_qsum || cfg.noise_model == 1;
     const bool coll = cfg.expect_collapsed != 0;
-    const bool narrow = allow_narrow && !coll && out.counts_out == nullptr;
-    const size_t smem = hot_kernel_smem_bytes(narrow, coll);
-    const int threads = narrow ? kNarrowThreads : kHotThreads;
-    const int grid = min(num_sms, (in.n_tiles + threads / 32 - 1) / (threads / 32));
     cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
-#define PB2_LAUNCH(CNT, THREADS, Q, C)                                                                                                       \
-    do {                                                                                                                                     \
-        e = cudaFuncSetAttribute(pileup_count_score_kernel<CNT, THREADS, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        if (e != cudaSuccess) return e;                                                                                                      \
-        pileup_count_score_kernel<CNT, THREADS, Q, C><<<grid, THREADS, smem, stream>>>(in, ex, out, cfg, tile_counter);                      \
+    if (out.counts_out == nullptr && max_depth + 2 * kChunk < (1 << 16)) {
+        // the hot path: vertical counters in registers; planes needed = bits of the largest row count (entries + PADs of a locus)
+        const int need = max_depth + 2 * kChunk;
+        const int grid = max(1, min(num_sms * 4, (in.n_tiles + 7) / 8));
+#define PB2_VLAUNCH(NP)                                                                                                        \
+    do {                                                                                                                       \
+        if (want_q && coll) pileup_vcount_score_kernel<NP, true, true><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);    \
+        else if (want_q) pileup_vcount_score_kernel<NP, true, false><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);      \
+        else if (coll) pileup_vcount_score_kernel<NP, false, true><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);        \
+        else pileup_vcount_score_kernel<NP, false, false><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);                 \
     } while (0)
-    if (narrow) {
-        if (want_q) PB2_LAUNCH(uint8_t, kNarrowThreads, true, false);
-        else PB2_LAUNCH(uint8_t, kNarrowThreads, false, false);
-    } else if (want_q && coll) PB2_LAUNCH(uint16_t, kHotThreads, true, true);
-    else if (want_q) PB2_LAUNCH(uint16_t, kHotThreads, true, false);
-    else if (coll) PB2_LAUNCH(uint16_t, kHotThreads, false, true);
-    else PB2_LAUNCH(uint16_t, kHotThreads, false, false);
+        if (need < (1 << 10)) PB2_VLAUNCH(10);
+        else if (need < (1 << 12)) PB2_VLAUNCH(12);
+        else PB2_VLAUNCH(16);
+#undef PB2_VLAUNCH
+    } else {
+        // general 198-bin variant (16-bit shared-memory histograms): pb2_get_counts, or loci deeper than 65 k entries are rejected by the caller
+        const size_t smem = hot_kernel_smem_bytes(false, coll);
+        const int grid = min(num_sms, (in.n_tiles + kHotThreads / 32 - 1) / (kHotThreads / 32));
+#define PB2_LAUNCH(Q, C)                                                                                                              \
+    do {                                                                                                                              \
+        e = cudaFuncSetAttribute(pileup_count_score_kernel<uint16_t, kHotThreads, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e != cudaSuccess) return e;                                                                                               \
+        pileup_count_score_kernel<uint16_t, kHotThreads, Q, C><<<grid, kHotThreads, smem, stream>>>(in, ex, out, cfg, tile_counter);  \
+    } while (0)
+        if (want_q && coll) PB2_LAUNCH(true, true);
+        else if (want_q) PB2_LAUNCH(true, false);
+        else if (coll) PB2_LAUNCH(false, true);
+        else PB2_LAUNCH(false, false);
 #undef PB2_LAUNCH
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     score_pending_kernel<<<num_sms * 4, 128, 0, stream>>>(in, ex, out, cfg);

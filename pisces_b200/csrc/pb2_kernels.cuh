@@ -31,6 +31,8 @@ struct DeviceConfig {
     int sb_model, filter_single_strand;
     float no_call_filter;
     int output_gvcf, expect_stitched, expect_collapsed, have_intervals, want_qsum;
+    double vq_error_rate;   // MathOperations.QtoP(noise_level) (VariantQualityCalculator.cs:31)
+    double sb_noise;        // Math.Pow(10, -1*noise_level/10f) (StrandBiasCalculator.cs:32)
 };
 
 // Device-resident, tile-interleaved pileup ("PTILE32").
@@ -85,7 +87,7 @@ struct HotInputsExtra {
 
 size_t hot_kernel_smem_bytes(bool narrow, bool collapsed);
 cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
-                              bool allow_narrow, cudaStream_t stream);
+                              int max_depth, cudaStream_t stream);
 
 // CSR -> PTILE32 staging
 cudaError_t launch_tile_layout(const int64_t* csr_offsets, int64_t n_loci, int32_t* depth, int64_t* tile_chunks /*[n_tiles]*/, int32_t* max_depth,

@@ -152,8 +152,9 @@ static __device__ __noinline__ double mathnet_gamma_lower_regularized(double a, 
 // MathOperations.QtoP(double q) = Math.Pow(10, -1 * q / 10f): q is double there, so the division is in double (MathOperations.cs:7-10)
 __device__ __forceinline__ double q_to_p(double q) { return pow(10.0, -1 * q / 10.0); }
 
-__device__ __forceinline__ double raw_poisson_qscore(int call_count, int coverage, int noise_level) {  // :27-52
-    const double error_rate = q_to_p((double)noise_level);
+// error_rate = MathOperations.QtoP(noise level): a per-run constant under the Flat noise model, computed once on the host (pb2_api.cu) with the
+// same expression; the Window noise model passes q_to_p(NL) per allele.
+__device__ __forceinline__ double raw_poisson_qscore(int call_count, int coverage, double error_rate) {  // :27-52
     const double k_minus_one = call_count - 1;
     const double k = call_count;
     const double lambda = error_rate * coverage;
@@ -165,9 +166,9 @@ __device__ __forceinline__ double raw_poisson_qscore(int call_count, int coverag
     const double correction = (k - lambda) / k;
     return -10.0 * (A - log(2.0 * correction)) / log(10.0);
 }
-__device__ __forceinline__ int poisson_qscore(int call_count, int coverage, int noise_level, int max_q) {  // :54-65
+__device__ __forceinline__ int poisson_qscore(int call_count, int coverage, double error_rate, int max_q) {  // :54-65
     if ((call_count <= 0) || (coverage <= 0)) return 0;
-    double q = fmin((double)max_q, raw_poisson_qscore(call_count, coverage, noise_level));
+    double q = fmin((double)max_q, raw_poisson_qscore(call_count, coverage, error_rate));
     q = fmax(q, 0.0);
     return (int)rint(q);  // Math.Round: half to even
 }
@@ -193,8 +194,8 @@ __device__ __forceinline__ SbStats sb_create_stats(double support, double covera
 
 struct SbResult { double bias, gatk; bool acceptable, var_both, cov_both; };
 
-__device__ __forceinline__ SbResult strand_bias(const int cov[3], const int sup[3], int q_noise, double acceptance, int model) {  // :21-72,89-105
-    const double noise = pow(10.0, (double)((float)(-1 * q_noise) / 10.0f));  // float exponent (:32)
+// noise = Math.Pow(10, -1*qNoise/10f) (float exponent, :32): a per-run constant, computed once on the host
+__device__ __forceinline__ SbResult strand_bias(const int cov[3], const int sup[3], double noise, double acceptance, int model) {  // :21-72,89-105
     const SbStats o = sb_create_stats(sup[0] + sup[1] + sup[2], cov[0] + cov[1] + cov[2], noise, model);
     const SbStats f = sb_create_stats(sup[0] + sup[2] / 2, cov[0] + cov[2] / 2, noise, model);
     const SbStats r = sb_create_stats(sup[1] + sup[2] / 2, cov[1] + cov[2] / 2, noise, model);

@@ -102,6 +102,7 @@ def make_pileup(n_loci, mean_depth, seed=1, device="cpu", depth_dist="poisson", 
                 snv_loci=int(is_snv.sum()), del_loci=int(is_del.sum()))
 
 
-def algorithmic_bytes(n_loci, n_entries, n_records):
-    """B(D,E) summed over loci: 3 B per entry + 8 B per locus + 96 B per emitted record."""
-    return 3 * n_entries + 8 * n_loci + 96 * n_records
+def algorithmic_bytes(n_loci, n_entries, n_records, third_byte=True):
+    """B(D,E) summed over loci: 3 B per entry + 8 B per locus + 96 B per emitted record; 2 B per entry when the
+    anchor/collapsed byte is not needed by the configuration (the hot kernel then never reads that plane)."""
+    return (3 if third_byte else 2) * n_entries + 8 * n_loci + 96 * n_records
