@@ -61,6 +61,7 @@ struct Segment {   // one staged pileup (pb2_push_pileup*)
     int64_t plane_bytes = 0;
     int64_t n_entries = 0;
     int32_t max_depth = 0;
+    size_t alloc_plane = 0, alloc_ref = 0, alloc_var = 0, alloc_pending = 0;
     // device
     int32_t* depth = nullptr;
     int32_t* pad = nullptr;
@@ -202,8 +203,18 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
     return PB2_OK;
 }
 
+// Staging buffers. (A per-handle cache of freed blocks was tried to avoid cudaMalloc/cudaFree of GB-sized buffers every push; on the B200 box it
+// produced 300 ms stalls in the driver on some steps, while plain cudaMalloc/cudaFree cost a stable ~3 ms per step — so: plain calls.)
+static cudaError_t pool_alloc(pb2_handle*, void** p, size_t bytes) { return cudaMalloc(p, std::max<size_t>(bytes, 256)); }
+static void pool_free(pb2_handle*, void* p, size_t) { if (p) cudaFree(p); }
+static void pool_release(pb2_handle*) {}
+
 static void free_segment(pb2_handle* h, Segment& s) {
-    void* ptrs[] = {s.depth, s.pad, s.tile_base, s.code, s.qual, s.anch, s.ref_base, s.positions, s.ref_records, s.ref_valid, s.var_records, s.exc_entries, s.counters, s.pending};
+    // the big staging buffers go back to the handle's cache, the small ones to the driver
+    pool_free(h, s.code, s.alloc_plane); pool_free(h, s.qual, s.alloc_plane); pool_free(h, s.anch, s.alloc_plane);
+    pool_free(h, s.ref_records, s.alloc_ref); pool_free(h, s.var_records, s.alloc_var); pool_free(h, s.pending, s.alloc_pending);
+    s.code = s.qual = s.anch = nullptr; s.ref_records = nullptr; s.var_records = nullptr; s.pending = nullptr;
+    void* ptrs[] = {s.depth, s.pad, s.tile_base, s.ref_base, s.positions, s.ref_valid, s.exc_entries, s.counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     s = Segment();
 }
@@ -222,6 +233,7 @@ extern "C" int pb2_reset(pb2_handle* h) {
 extern "C" void pb2_destroy(pb2_handle* h) {
     if (!h) return;
     pb2_reset(h);
+    pool_release(h);
     if (h->d_chr) cudaFree(h->d_chr);
     if (h->d_tile_counter) cudaFree(h->d_tile_counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -285,9 +297,9 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
         n_entries = p->offsets[p->n_loci];
         if (n_entries < 0) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: negative entry count");
         CU(h, cudaMalloc(&tmp_off, sizeof(int64_t) * (size_t)(p->n_loci + 1)));
-        CU(h, cudaMalloc(&tmp_code, (size_t)std::max<int64_t>(n_entries, 1)));
-        CU(h, cudaMalloc(&tmp_qual, (size_t)std::max<int64_t>(n_entries, 1)));
-        CU(h, cudaMalloc(&tmp_anch, (size_t)std::max<int64_t>(n_entries, 1)));
+        CU(h, pool_alloc(h, (void**)&tmp_code, (size_t)std::max<int64_t>(n_entries, 1)));
+        CU(h, pool_alloc(h, (void**)&tmp_qual, (size_t)std::max<int64_t>(n_entries, 1)));
+        CU(h, pool_alloc(h, (void**)&tmp_anch, (size_t)std::max<int64_t>(n_entries, 1)));
         CU(h, cudaMemcpyAsync(tmp_off, p->offsets, sizeof(int64_t) * (size_t)(p->n_loci + 1), cudaMemcpyHostToDevice, st));
         CU(h, cudaMemcpyAsync(tmp_code, p->code, (size_t)n_entries, cudaMemcpyHostToDevice, st));
         CU(h, cudaMemcpyAsync(tmp_qual, p->qual, (size_t)n_entries, cudaMemcpyHostToDevice, st));
@@ -335,29 +347,37 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     CU(h, cudaStreamSynchronize(st));
     if (s.max_depth >= 65000) return fail(h, PB2_ERR_UNSUPPORTED, "pb2_push_pileup: a locus with 65000 or more entries (16-bit counters)");
     const size_t pb = (size_t)std::max<int64_t>(s.plane_bytes, 16);
-    CU(h, cudaMalloc(&s.code, pb));
-    CU(h, cudaMalloc(&s.qual, pb));
-    CU(h, cudaMalloc(&s.anch, pb));
+    s.alloc_plane = pb;
+    CU(h, pool_alloc(h, (void**)&s.code, pb));
+    CU(h, pool_alloc(h, (void**)&s.qual, pb));
+    CU(h, pool_alloc(h, (void**)&s.anch, pb));
     CU(h, launch_tile_scatter(d_off, d_code, d_qual, d_anch, p->n_loci, s.tile_base, s.ref_base, h->dcfg.min_bq, s.code, s.qual, s.anch, s.pad, st));
     h->total_launches += 4;
 
     // outputs
     if (h->cfg.output_gvcf) {
-        CU(h, cudaMalloc(&s.ref_records, sizeof(pb2_call_record) * (size_t)p->n_loci));
+        s.alloc_ref = sizeof(pb2_call_record) * (size_t)p->n_loci;
+        CU(h, pool_alloc(h, (void**)&s.ref_records, s.alloc_ref));
         CU(h, cudaMalloc(&s.ref_valid, (size_t)p->n_loci));
     }
     s.var_capacity = std::max<int64_t>(1024, p->n_loci);
-    CU(h, cudaMalloc(&s.var_records, sizeof(pb2_call_record) * (size_t)s.var_capacity));
+    s.alloc_var = sizeof(pb2_call_record) * (size_t)s.var_capacity;
+    CU(h, pool_alloc(h, (void**)&s.var_records, s.alloc_var));
     s.exc_capacity = 1 << 20;
     CU(h, cudaMalloc(&s.exc_entries, sizeof(uint32_t) * 2 * (size_t)s.exc_capacity));
     CU(h, cudaMalloc(&s.counters, sizeof(unsigned long long) * 4));
     s.pending_capacity = std::max<int64_t>(1024, p->n_loci);
-    CU(h, cudaMalloc(&s.pending, sizeof(PendingLocus) * (size_t)s.pending_capacity));
+    s.alloc_pending = sizeof(PendingLocus) * (size_t)s.pending_capacity;
+    CU(h, pool_alloc(h, (void**)&s.pending, s.alloc_pending));
 
     CU(h, cudaStreamSynchronize(st));
     cudaFree(tile_bytes);
     cudaFree(temp);
-    if (tmp_off) { cudaFree(tmp_off); cudaFree(tmp_code); cudaFree(tmp_qual); cudaFree(tmp_anch); }
+    if (tmp_off) {
+        cudaFree(tmp_off);
+        const size_t nb = (size_t)std::max<int64_t>(n_entries, 1);
+        pool_free(h, tmp_code, nb); pool_free(h, tmp_qual, nb); pool_free(h, tmp_anch, nb);
+    }
     h->segs.push_back(std::move(s));
     return PB2_OK;
 }
@@ -597,10 +617,29 @@ static inline bool record_less(const pb2_call_record& a, const pb2_call_record& 
 static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std::vector<uint32_t>& exc, std::vector<pb2_call_record>& vars) {
     struct Key { uint32_t locus; int allele; bool operator<(const Key& o) const { return locus != o.locus ? locus < o.locus : allele < o.allele; } };
     struct Acc { int nocand = 0; int open_l = 0, open_r = 0, open_lr = 0; };
+    static const char base_of[4] = {'A', 'G', 'C', 'T'};
+    // emitted SNV records by (position, alt) for lookup; flagged entries of alleles that were not called cannot change anything
+    // (a split of a non-callable candidate is non-callable too: less support means a lower frequency and a lower q-score)
+    std::vector<std::pair<uint64_t, const pb2_call_record*>> index;
+    index.reserve(vars.size());
+    for (auto& v : vars)
+        if (v.type == CAT_SNV) index.push_back({((uint64_t)(uint32_t)v.position << 8) | ((v.allele_bytes >> 8) & 0xff), &v});
+    std::sort(index.begin(), index.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    auto key_of = [&](uint32_t locus, int allele) {
+        const int32_t pos = s.has_positions ? s.h_positions[locus] : s.first_position + (int32_t)locus;
+        return ((uint64_t)(uint32_t)pos << 8) | (uint8_t)base_of[allele & 3];
+    };
     std::vector<std::pair<Key, Acc>> groups;
     {
         std::vector<std::pair<Key, uint32_t>> items;
-        for (size_t i = 0; i + 1 < exc.size(); i += 2) items.push_back({Key{exc[i], (int)(exc[i + 1] & 7)}, exc[i + 1] & 0xffu});
+        for (size_t i = 0; i + 1 < exc.size(); i += 2) {
+            const int allele = (int)(exc[i + 1] & 7);
+            if (allele > 3) continue;
+            const uint64_t key = key_of(exc[i], allele);
+            auto it = std::lower_bound(index.begin(), index.end(), key, [](const auto& a, uint64_t k) { return a.first < k; });
+            if (it == index.end() || it->first != key) continue;
+            items.push_back({Key{exc[i], allele}, exc[i + 1] & 0xffu});
+        }
         std::sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
         for (auto& it : items) {
             if (groups.empty() || groups.back().first < it.first) groups.push_back({it.first, Acc()});
@@ -612,11 +651,11 @@ static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std:
             else if (r) a.open_r++;
         }
     }
-    static const char base_of[4] = {'A', 'G', 'C', 'T'};
     for (auto& g : groups) {
-        const int32_t pos = s.has_positions ? s.h_positions[g.first.locus] : s.first_position + (int32_t)g.first.locus;
-        for (auto& v : vars) {
-            if (v.position != pos || v.type != CAT_SNV || (char)((v.allele_bytes >> 8) & 0xff) != base_of[g.first.allele]) continue;
+        const uint64_t key = key_of(g.first.locus, g.first.allele);
+        auto it = std::lower_bound(index.begin(), index.end(), key, [](const auto& a, uint64_t k) { return a.first < k; });
+        for (; it != index.end() && it->first == key; ++it) {
+            const pb2_call_record& v = *it->second;
             const Acc& a = g.second;
             if (a.nocand > 0) return fail(h, PB2_ERR_UNSUPPORTED, "called SNV has support from '='/'X' operations: explicit-candidate path not built yet");
             if (!h->cfg.collapse) continue;   // open ends are not tracked without the collapser
