@@ -346,7 +346,7 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     CU(h, cudaMemcpyAsync(&s.plane_bytes, s.tile_base + s.n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     if (s.max_depth >= 65000) return fail(h, PB2_ERR_UNSUPPORTED, "pb2_push_pileup: a locus with 65000 or more entries (16-bit counters)");
-    const size_t pb = (size_t)std::max<int64_t>(s.plane_bytes, 16);
+    const size_t pb = (size_t)std::max<int64_t>(s.plane_bytes, 16) + 2048;   // slack: the hot kernel prefetches up to two steps past a tile
     s.alloc_plane = pb;
     CU(h, pool_alloc(h, (void**)&s.code, pb));
     CU(h, pool_alloc(h, (void**)&s.qual, pb));

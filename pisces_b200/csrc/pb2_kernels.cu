@@ -578,6 +578,20 @@ __device__ __forceinline__ void score_queued_locus(const PendingLocus* item /* n
     }
 }
 
+__device__ __noinline__ void note_flagged_words(const uint4 wc, const uint4 wq, uint32_t locus, uint32_t* __restrict__ exc_entries,
+                                                unsigned long long* __restrict__ exc_count, int64_t exc_capacity) {
+    const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w};
+    for (int k = 0; k < kChunk; k++) {
+        const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+        if ((code & 0xe0u) == 0) continue;
+        const unsigned long long slot = atomicAdd(exc_count, 1ull);
+        if ((int64_t)slot < exc_capacity) {
+            exc_entries[2 * slot] = locus;
+            exc_entries[2 * slot + 1] = code | (((qw[k >> 2] >> ((k & 3) * 8)) & 0xffu) << 8);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the hot kernel: vertical counters
 // Point alleles (Reference, SNV) only ever read anchor-summed counts (CoverageCalculator.CalculateSinglePoint, RegionState.GetAllCandidates), so
 // this kernel counts 18 rows (allele x direction) [+ 8 collapsed-read types] instead of 198 bins and keeps them in REGISTERS as bit-sliced
@@ -663,36 +677,8 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
 #pragma unroll
         for (int i = 0; i < NP; i++) P[i] = 0;
 
-        // software pipeline: chunk c+1 is in flight (registers) and chunk c+2 is being prefetched into L2 while chunk c is counted
-        const uint4 pad_c = make_uint4(kPadCode4, kPadCode4, kPadCode4, kPadCode4), pad_q = make_uint4(~0u, ~0u, ~0u, ~0u), pad_a = make_uint4(0, 0, 0, 0);
-        uint4 nc = pad_c, nq = pad_q, na = pad_a;
-        {
-            const bool active = 0 < nchunks;
-            const unsigned m = __ballot_sync(0xffffffffu, active);
-            if (active) {
-                const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
-                nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o);
-                if (kCollapsed) na = ldg_stream(in.anch + o);
-            }
-            base += (int64_t)__popc(m) * kChunk;
-        }
-        for (int c = 0; c < max_chunks; c++) {
-            const uint4 wc = nc, wq = nq, wa = na;
-            if (c >= nchunks) extra_pad += kChunk;
-            nc = pad_c; nq = pad_q; na = pad_a;
-            {
-                const bool active = (c + 1) < nchunks;
-                const unsigned m = __ballot_sync(0xffffffffu, active);
-                if (active) {
-                    const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
-                    nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o);
-                    if (kCollapsed) na = ldg_stream(in.anch + o);
-                }
-                base += (int64_t)__popc(m) * kChunk;
-                const int64_t pf = min(base + lane * kChunk, in.plane_bytes - kChunk);
-                prefetch_l2(in.code + pf); prefetch_l2(in.qual + pf);
-                if (kCollapsed) prefetch_l2(in.anch + pf);
-            }
+        // One 16-entry chunk into the planes below weight 16; returns the weight-16 carry (rippled by the caller, every second chunk in phase 1).
+        auto add_chunk = [&](const uint4& wc, const uint4& wq, const uint4& wa) -> uint32_t {
             const uint32_t r0 = rows_of_word(wc.x, wq.x, minbq4), r1 = rows_of_word(wc.y, wq.y, minbq4), r2 = rows_of_word(wc.z, wq.z, minbq4),
                            r3 = rows_of_word(wc.w, wq.w, minbq4);
             // weight 1: P[0] + 16 one-hot words -> P[0] and eight weight-2 carries
@@ -715,12 +701,9 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
             uint32_t w0, n0, n1;
             csa(w0, n0, m0, m1, m2);
             csa(P[2], n1, w0, m3, P[2]);
-            // weight 8: P[3] + 2 carries -> P[3] and one weight-16 carry, which ripples through the high planes
+            // weight 8: P[3] + 2 carries -> P[3] and one weight-16 carry
             uint32_t carry;
             csa(P[3], carry, n0, n1, P[3]);
-#pragma unroll
-            for (int i = 4; i < NP; i++) { const uint32_t t = P[i] & carry; P[i] ^= carry; carry = t; }
-
             if (kWantQsum) {   // Σ 10^(-q/10f) over entries counted as A/C/G/T (Deletion entries carry no base quality, :191)
                 const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
@@ -730,17 +713,74 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
                 }
             }
             // flagged entries (rare after staging normalisation): SNV-candidate bookkeeping the counts cannot express -> side list
-            if (((wc.x | wc.y | wc.z | wc.w) & 0xe0e0e0e0u) != 0) {
-                const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w};
-                for (int k = 0; k < kChunk; k++) {
-                    const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-                    if ((code & 0xe0u) == 0) continue;
-                    const unsigned long long slot = atomicAdd(out.exc_count, 1ull);
-                    if ((int64_t)slot < out.exc_capacity) {
-                        out.exc_entries[2 * slot] = (uint32_t)locus;
-                        out.exc_entries[2 * slot + 1] = code | (((qw[k >> 2] >> ((k & 3) * 8)) & 0xffu) << 8);
-                    }
+            if (((wc.x | wc.y | wc.z | wc.w) & 0xe0e0e0e0u) != 0) note_flagged_words(wc, wq, (uint32_t)locus, out.exc_entries, out.exc_count, out.exc_capacity);
+            return carry;
+        };
+        auto ripple = [&](uint32_t carry, int from) {
+#pragma unroll
+            for (int i = 4; i < NP; i++) if (i >= from) { const uint32_t t = P[i] & carry; P[i] ^= carry; carry = t; }
+        };
+
+        // ---- phase 1: the steps every lane of the tile takes part in (uniform: slot == lane, 512 contiguous bytes per plane per step, no ballots,
+        // immediate address offsets). Chunk c+1 is in flight in registers and chunk c+2 is prefetched into L2 while chunk c is counted. Two chunks
+        // per iteration so that their weight-16 carries meet in one more compressor and the ripple through the high planes runs half as often.
+        const int min_chunks = __reduce_min_sync(0xffffffffu, nchunks);
+        {
+            constexpr int kStep = kTileLoci * kChunk;
+            const uint8_t* pc = in.code + base + lane * kChunk;
+            const uint8_t* pq = in.qual + base + lane * kChunk;
+            const uint8_t* pa = in.anch + base + lane * kChunk;
+            uint4 nc = make_uint4(0, 0, 0, 0), nq = nc, na = nc;
+            if (min_chunks > 0) { nc = ldg_stream(pc); nq = ldg_stream(pq); if (kCollapsed) na = ldg_stream(pa); }
+            auto step = [&](bool more) -> uint32_t {
+                const uint4 wc = nc, wq = nq, wa = na;
+                pc += kStep; pq += kStep; if (kCollapsed) pa += kStep;
+                if (more) { nc = ldg_stream(pc); nq = ldg_stream(pq); if (kCollapsed) na = ldg_stream(pa); }
+                prefetch_l2(pc + kStep); prefetch_l2(pq + kStep); if (kCollapsed) prefetch_l2(pa + kStep);   // the planes carry 2 KB of slack
+                return add_chunk(wc, wq, wa);
+            };
+            int c = 0;
+            for (; c + 2 <= min_chunks; c += 2) {
+                const uint32_t ca = step(true);
+                const uint32_t cb = step(c + 2 < min_chunks);
+                uint32_t c32;
+                csa(P[4], c32, ca, cb, P[4]);
+                ripple(c32, 5);
+            }
+            if (c < min_chunks) ripple(step(false), 4);
+            base += (int64_t)min_chunks * kStep;
+        }
+
+        // ---- phase 2: the ragged end of the tile. Lanes that ran out of entries count PAD chunks (subtracted at read-out).
+        if (min_chunks < max_chunks) {
+            const uint4 pad_c = make_uint4(kPadCode4, kPadCode4, kPadCode4, kPadCode4), pad_q = make_uint4(~0u, ~0u, ~0u, ~0u), pad_a = make_uint4(0, 0, 0, 0);
+            uint4 nc = pad_c, nq = pad_q, na = pad_a;
+            {
+                const bool active = min_chunks < nchunks;
+                const unsigned m = __ballot_sync(0xffffffffu, active);
+                if (active) {
+                    const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
+                    nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o);
+                    if (kCollapsed) na = ldg_stream(in.anch + o);
                 }
+                base += (int64_t)__popc(m) * kChunk;
+            }
+#pragma unroll 1
+            for (int c = min_chunks; c < max_chunks; c++) {
+                const uint4 wc = nc, wq = nq, wa = na;
+                if (c >= nchunks) extra_pad += kChunk;
+                nc = pad_c; nq = pad_q; na = pad_a;
+                {
+                    const bool active = (c + 1) < nchunks;
+                    const unsigned m = __ballot_sync(0xffffffffu, active);
+                    if (active) {
+                        const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
+                        nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o);
+                        if (kCollapsed) na = ldg_stream(in.anch + o);
+                    }
+                    base += (int64_t)__popc(m) * kChunk;
+                }
+                ripple(add_chunk(wc, wq, wa), 4);
             }
         }
 
