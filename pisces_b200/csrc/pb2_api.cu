@@ -96,6 +96,8 @@ struct pb2_handle {
     std::string error;
     std::string chr_name;
     uint8_t* d_chr = nullptr;
+    double* d_q_to_p = nullptr;     // QtoP(q) for q = 0..max_variant_qscore (capped at 1024 entries)
+    int q_table_max = -1;
     int64_t chr_len = 0;
     std::vector<uint8_t> h_chr;
     std::vector<int32_t> iv_start, iv_end;
@@ -199,6 +201,13 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&h->d_tile_counter, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    {
+        h->q_table_max = std::min(std::max(cfg->max_variant_qscore, 0), 1023);
+        std::vector<double> t((size_t)h->q_table_max + 1);
+        for (int q = 0; q <= h->q_table_max; q++) t[(size_t)q] = std::pow(10.0, -1 * (double)q / 10.0);   // MathOperations.QtoP
+        if ((e = cudaMalloc(&h->d_q_to_p, t.size() * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMemcpy(h->d_q_to_p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+    }
     *out = h;
     return PB2_OK;
 }
@@ -236,6 +245,7 @@ extern "C" void pb2_destroy(pb2_handle* h) {
     pool_release(h);
     if (h->d_chr) cudaFree(h->d_chr);
     if (h->d_tile_counter) cudaFree(h->d_tile_counter);
+    if (h->d_q_to_p) cudaFree(h->d_q_to_p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -391,7 +401,7 @@ static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* 
     in.code = s.code; in.qual = s.qual; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
     in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles; in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);
     HotInputsExtra ex;
-    ex.gapped_ref = nullptr; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len;
+    ex.gapped_ref = nullptr; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len; ex.q_to_p_table = h->d_q_to_p; ex.q_table_max = h->q_table_max;
     HotOutputs out;
     out.ref_records = s.ref_records; out.ref_valid = s.ref_valid; out.var_records = s.var_records; out.var_count = s.counters;
     out.var_capacity = s.var_capacity; out.exc_entries = s.exc_entries; out.exc_count = s.counters + 1; out.exc_capacity = s.exc_capacity;

@@ -188,7 +188,9 @@ struct LocusCounts {
 // Fill one record for a point allele (Reference or Snv) exactly as ProcessVariant + SetGenotypes would. Returns false when a non-reference
 // allele is not callable (AlleleCaller.IsCallable) so nothing is emitted.
 __device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int position, int ref_allele, int alt_allele /* == ref_allele for Reference */, int gapped,
-                                   const DeviceConfig& cfg, const uint8_t* __restrict__ chr_seq, int64_t chr_len, pb2_call_record& r) {
+                                   const DeviceConfig& cfg, const HotInputsExtra& ex, pb2_call_record& r) {
+    const uint8_t* __restrict__ chr_seq = ex.chr_seq;
+    const int64_t chr_len = ex.chr_len;
     const bool is_ref = alt_allele == ref_allele;
     int cov[3], sup[3];
     int total = 0, nocalls = 0, ref_support = 0;
@@ -241,7 +243,7 @@ __device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int posit
     // SomaticGenotyper + GQ (per allele)
     const float ref_freq = allele_frequency(ref_support, total);
     const int gt = somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
-    const int gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq);
+    const int gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, ex.q_to_p_table, ex.q_table_max);
     if (cfg.low_gq_filter >= 0 && (float)gq < (float)cfg.low_gq_filter) filters |= 1u << FLT_LOW_GQ;
 
     r.position = position;
@@ -332,7 +334,7 @@ __device__ __forceinline__ void finish_locus(const LocusCounts& lc, int any, int
         if (emit) {
             const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
             pb2_call_record r;
-            score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex.chr_seq, ex.chr_len, r);
+            score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex, r);
             store_record(out.ref_records + locus, r);
         }
         out.ref_valid[locus] = emit ? 1 : 0;
@@ -558,7 +560,7 @@ __device__ __forceinline__ void score_queued_locus(const PendingLocus* item /* n
         const int alt = order[j];
         if ((cand_mask >> alt) & 1) {
             pb2_call_record r;
-            if (score_point_allele(lc, position, ref_allele, alt, gapped, cfg, ex.chr_seq, ex.chr_len, r)) {
+            if (score_point_allele(lc, position, ref_allele, alt, gapped, cfg, ex, r)) {
                 called = true;
                 const unsigned long long slot = atomicAdd(out.var_count, 1ull);
                 if ((int64_t)slot < out.var_capacity) store_record(out.var_records + slot, r);
@@ -571,7 +573,7 @@ __device__ __forceinline__ void score_queued_locus(const PendingLocus* item /* n
         const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (cand_mask & 0x200));
         if (emit) {
             pb2_call_record r;
-            score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex.chr_seq, ex.chr_len, r);
+            score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex, r);
             store_record(out.ref_records + locus, r);
         }
         out.ref_valid[locus] = emit ? 1 : 0;
@@ -841,7 +843,7 @@ __global__ void __launch_bounds__(128) score_pending_kernel(TilePileup in, HotIn
             const int alt = order[oi];
             if (!((pl.cand_mask >> alt) & 1)) continue;
             pb2_call_record r;
-            if (score_point_allele(lc, position, ref_allele, alt, pl.gapped, cfg, ex.chr_seq, ex.chr_len, r)) {
+            if (score_point_allele(lc, position, ref_allele, alt, pl.gapped, cfg, ex, r)) {
                 variant_called = true;
                 const unsigned long long slot = atomicAdd(out.var_count, 1ull);
                 if ((int64_t)slot < out.var_capacity) store_record(out.var_records + slot, r);
@@ -851,7 +853,7 @@ __global__ void __launch_bounds__(128) score_pending_kernel(TilePileup in, HotIn
             const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (pl.cand_mask & 0x200));
             if (emit) {
                 pb2_call_record r;
-                score_point_allele(lc, position, ref_allele, ref_allele, pl.gapped, cfg, ex.chr_seq, ex.chr_len, r);
+                score_point_allele(lc, position, ref_allele, ref_allele, pl.gapped, cfg, ex, r);
                 store_record(out.ref_records + locus, r);
             }
             out.ref_valid[locus] = emit ? 1 : 0;

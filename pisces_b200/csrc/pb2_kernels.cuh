@@ -83,6 +83,8 @@ struct HotInputsExtra {
     const uint8_t* locus_has_variant;  // [n_loci] or nullptr: a non-point variant was called at this position (ref pruning, AlleleCaller.cs:146-147)
     const uint8_t* chr_seq;         // upper-case chromosome (RMxN), or nullptr
     int64_t chr_len;
+    const double* q_to_p_table;     // QtoP(q), q = 0..q_table_max (MathOperations.cs:7-10), or nullptr
+    int q_table_max;
 };
 
 size_t hot_kernel_smem_bytes(bool narrow, bool collapsed);

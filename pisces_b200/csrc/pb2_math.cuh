@@ -166,8 +166,31 @@ __device__ __forceinline__ double raw_poisson_qscore(int call_count, int coverag
     const double correction = (k - lambda) / k;
     return -10.0 * (A - log(2.0 * correction)) / log(10.0);
 }
+// Rigorous short-circuit of the q-score cap: returns true when min(maxQ, raw) is provably maxQ, without evaluating the incomplete gamma.
+//  * p = P(X >= k) <= exp(-lambda + k - k ln(k/lambda)) (Chernoff, k > lambda). The reference's p-value is 1 - (1 - P_lower): p rounded to a
+//    multiple of 2^-53; if the bound is below 10^(-maxQ/10) / 4 (and that threshold is far above 2^-53, i.e. maxQ <= 150) the p > 0 branch gives
+//    raw >= maxQ;
+//  * if the p-value rounds to 0 the reference uses -10 (A - ln(2(k-lambda)/k)) / ln 10 with A = ln PMF(k-1); ln Gamma(k) >= (k-1/2) ln k - k +
+//    ln sqrt(2 pi) bounds A from above, hence that branch from below.
+// Both branches >= maxQ  =>  (int)Round(Max(0, Min(maxQ, raw))) == maxQ exactly as VariantQualityCalculator.cs:54-65 computes it.
+__device__ __forceinline__ bool qscore_is_capped(int k, int n, double error_rate, int max_q) {
+    if (max_q > 150 || max_q < 0) return false;
+    const double lambda = error_rate * n;
+    const double kd = k;
+    if (!(kd > lambda) || !(lambda > 0)) return false;
+    // single-precision logs are enough for a bound: their error (<= 2e-7 relative) times k <= 65535 is below 0.2; 1.0 of slack is charged
+    const double lnk = (double)logf((float)kd), lnl = (double)logf((float)lambda);
+    const double need = -(double)max_q * 0.23025850929940458 - 1.0;          // ln(10^(-maxQ/10)) minus the slack
+    const double ln_chernoff = -lambda + kd - kd * (lnk - lnl);
+    if (!(ln_chernoff <= need - 1.3862943611198906)) return false;           // bound <= T/4
+    const double a_ub = -lambda + (kd - 1.0) * lnl - ((kd - 0.5) * lnk - kd + 0.9189385332046727);
+    const double corr = (double)logf((float)(2.0 * ((kd - lambda) / kd)));
+    return (a_ub - corr) <= need;
+}
+
 __device__ __forceinline__ int poisson_qscore(int call_count, int coverage, double error_rate, int max_q) {  // :54-65
     if ((call_count <= 0) || (coverage <= 0)) return 0;
+    if (qscore_is_capped(call_count, coverage, error_rate, max_q)) return max_q;
     double q = fmin((double)max_q, raw_poisson_qscore(call_count, coverage, error_rate));
     q = fmax(q, 0.0);
     return (int)rint(q);  // Math.Round: half to even
@@ -185,7 +208,17 @@ __device__ __forceinline__ SbStats sb_create_stats(double support, double covera
         if (model == SBM_POISSON) { s.fp = 1; s.vg = 0; s.fn = 0; }
         else { s.vg = pow(1 - min_detectable, coverage); s.fp = 1 - s.vg; s.fn = s.vg; }
     } else {
-        s.vg = fmax(0.0, pisces_poisson_cdf(support - 1, coverage * noise));
+        // Rigorous short-circuit: Cdf(support-1, x) = 1 - gs with gs = sum * exp(a ln x - x - lnGamma~(a)), a = support. For x <= a/2 the series
+        // converges (ratio <= 1/2), sum <= 2, and lnGamma~(a) >= (a-1/2) ln a - a + ln sqrt(2 pi) - 1e-6 for both of the reference's
+        // approximations (Poisson.cs:106-128); when that bounds gs below 2^-54 the double subtraction yields exactly 1.0.
+        const double x = coverage * noise;
+        bool saturated = false;
+        if (x > 0 && x <= 0.5 * support) {
+            // single-precision logs + 1.0 of slack (see qscore_is_capped)
+            const double e_ub = support * (double)logf((float)x) - x - ((support - 0.5) * (double)logf((float)support) - support + 0.9189385332046727);
+            saturated = e_ub < -41.0;
+        }
+        s.vg = saturated ? 1.0 : fmax(0.0, pisces_poisson_cdf(support - 1, x));
         s.fp = fmax(0.0, 1 - s.vg);
         s.fn = 0.0;  // ChanceFalseNeg feeds nothing downstream of the record (StrandBiasStats only); computed on demand by the stats API
     }
@@ -205,7 +238,7 @@ __device__ __forceinline__ SbResult strand_bias(const int cov[3], const int sup[
     SbResult res;
     double p = (isnan(fb) || isnan(rb)) ? nan("") : fmax(fb, rb);  // Math.Max propagates NaN
     res.bias = p;
-    res.gatk = 10 * log10(p);
+    res.gatk = (p == 0) ? -INFINITY : 10 * log10(p);   // 10*log10(0) is -inf either way
     res.cov_both = (f.coverage > 0) && (r.coverage > 0);
     res.var_both = (f.support > 0) && (r.support > 0);
     if (!res.cov_both) { res.bias = 0; res.gatk = -INFINITY; }
@@ -234,12 +267,14 @@ __device__ __forceinline__ int somatic_genotype(bool is_ref, int total_cov, floa
     return GT_HOM_REF;
 }
 // SomaticGenotypeQualityCalculator.cs:10-48
-__device__ __forceinline__ int somatic_gq(int genotype, int vq, int total_cov, float freq, float target_lod, int min_gq, int max_gq) {
+// q_to_p_table: optional device table of QtoP(q) for q = 0..table_max (filled on the host with the same expression), nullptr -> pow on the device
+__device__ __forceinline__ int somatic_gq(int genotype, int vq, int total_cov, float freq, float target_lod, int min_gq, int max_gq,
+                                          const double* __restrict__ q_to_p_table = nullptr, int table_max = -1) {
     double raw = vq;
     const bool nocall = genotype == GT_ALT12_NOCALL || genotype == GT_ALT_NOCALL || genotype == GT_REF_NOCALL;
     if (total_cov == 0 || nocall) return min_gq;
     if (genotype == GT_HOM_REF || genotype == GT_HOM_ALT) {
-        const double p1 = q_to_p((double)vq);
+        const double p1 = (q_to_p_table != nullptr && vq >= 0 && vq <= table_max) ? q_to_p_table[vq] : q_to_p((double)vq);
         const float non_allele_obs = (1.0f - freq) * (float)total_cov;
         const float expected = target_lod * (float)total_cov;
         if (non_allele_obs >= expected) return min_gq;
