@@ -6,6 +6,8 @@
  *
  *   IStateManager.AddAlleleCounts(Read)            src/lib/Pisces.Processing/Interfaces/IStateManager.cs:8-15     -> pb2_push_reads
  *   IStateManager.AddCandidates(candidates)        src/lib/Pisces.Domain/Interfaces/IAlleleSource.cs:10            -> pb2_push_candidates
+ *   ICandidateVariantFinder.FindCandidates(Read..) src/lib/Pisces.Domain/Interfaces/ICandidateAlleleFinder.cs:7-10    -> pb2_push_reads (found on the device)
+ *   IVariantCollapser.Collapse / MnvReallocator    src/exe/Pisces/Logic/VariantCalling/VariantCollapser.cs:31-113, MnvReallocator.cs:12-98 -> inside pb2_flush
  *   IStateManager.GetCandidatesToProcess/DoneProcessing + IAlleleCaller.Call(batch, source)
  *                                                  src/exe/Pisces/Interfaces/IAlleleCaller.cs:8-13                 -> pb2_flush
  *   IAlleleSource.GetAlleleCount(pos, allele, dir, ...)   IAlleleSource.cs:12                                      -> pb2_get_counts
@@ -71,7 +73,13 @@ typedef struct pb2_config {
     int32_t expect_collapsed;            /* CollapsedRegionStateManager in use */
     int32_t want_sum_base_quality;       /* fill pb2_call_record.sum_base_quality (always on when noise_model == Window) */
     int32_t collapse;                    /* PiscesApplicationOptions.Collapse (1): candidates are tracked per open-end state (trackOpenEnded) */
-    int32_t call_mnvs;                   /* CallMNVs (0); 1 -> PB2_ERR_UNSUPPORTED until the MNV path lands */
+    int32_t call_mnvs;                   /* CallMNVs (0): SNV/MNV candidates then come from the candidate finder, not from the counts */
+    int32_t indel_repeat_filter;         /* IndelRepeatFilter (null = -1) */
+    int32_t max_size_mnv;                /* MaxSizeMNV (3) */
+    int32_t max_gap_mnv;                 /* MaxGapBetweenMNV (1) */
+    float   collapse_freq_threshold;     /* CollapseFreqThreshold (0) */
+    float   collapse_freq_ratio_threshold; /* CollapseFreqRatioThreshold (0.5) */
+    int32_t exclude_mnvs_from_collapsing;  /* ExcludeMNVsFromCollapsing (0) */
     int32_t reserved[2];
 } pb2_config;
 
@@ -114,6 +122,22 @@ typedef struct pb2_pileup_csr {
     const uint8_t* ref_bases;    /* optional [n_loci] ASCII; NULL -> taken from pb2_set_reference */
 } pb2_pileup_csr;
 
+/* One candidate allele: the POD image of CandidateAllele (src/lib/Pisces.Domain/Models/Alleles/CandidateAllele.cs:8-125) for
+ * IAlleleSource.AddCandidates. Insertions, deletions and MNVs (and, with CallMNVs, SNVs) are explicit candidates: their support is the number
+ * of reads in which CandidateVariantFinder raised them, which the pileup counts cannot express. 72 bytes. */
+typedef struct pb2_candidate {
+    int32_t  position;                 /* ReferencePosition (1-based; the base before an insertion / deletion) */
+    uint8_t  type;                     /* AlleleCategory: 0 Snv, 1 Insertion, 2 Deletion, 3 Mnv */
+    uint8_t  open_flags;               /* bit0 OpenOnLeft, bit1 OpenOnRight */
+    uint16_t ref_len;
+    uint16_t alt_len;
+    uint16_t reserved;
+    uint32_t allele_offset;            /* ReferenceAllele then AlternateAllele (ASCII) at this offset of the arena */
+    int32_t  support[3];               /* SupportByDirection */
+    int32_t  well_anchored[3];         /* WellAnchoredSupportByDirection */
+    int32_t  collapsed_mut[8];         /* ReadCollapsedCountsMut */
+} pb2_candidate;
+
 /* One called allele: the POD image of CalledAllele (src/lib/Pisces.Domain/Models/Alleles/CalledAllele.cs:7-140). 96 bytes. */
 typedef struct pb2_call_record {
     int32_t  position;                 /* ReferencePosition, 1-based */
@@ -132,7 +156,7 @@ typedef struct pb2_call_record {
     int32_t  reference_support;
     int32_t  num_no_calls;
     float    fraction_no_calls;
-    uint32_t allele_bytes;             /* ref_len + alt_len <= 4: the ASCII bases inline (ref then alt, little-endian); else offset into the flush arena */
+    uint32_t allele_bytes;             /* ref_len + alt_len <= 4: the ASCII bases inline (ref then alt, little-endian); else offset into pb2_allele_arena */
     uint16_t ref_len, alt_len;
     double   sum_base_quality;
     double   bias_score;               /* StrandBiasResults.BiasScore */
@@ -157,6 +181,13 @@ int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p);
  * positions they cover; the pileup is built on the device (read expansion, bucketing to loci, tile interleave). */
 int pb2_push_reads(pb2_handle* h, const pb2_read_batch* batch);
 
+/* IAlleleSource.AddCandidates: explicit candidates for the staged positions (the locus-major path has no reads to find them in; a host
+ * that keeps its own ICandidateVariantFinder uses this too). Candidates equal in (position, type, ref, alt[, open ends when Collapse is on])
+ * are merged by summing their counts (RegionState.AddCandidate, RegionState.cs:94-174). */
+int pb2_push_candidates(pb2_handle* h, const pb2_candidate* cands, int32_t n, const uint8_t* allele_arena, int64_t arena_len);
+/* The byte arena that pb2_call_record.allele_bytes of the last pb2_flush / pb2_call_resident points into for alleles longer than 4 bases. */
+int pb2_allele_arena(pb2_handle* h, const uint8_t** arena, int64_t* len);
+
 /* Count + score everything staged; records stay on the device (bench / multi-GPU gather use this). */
 int pb2_call_resident(pb2_handle* h, int64_t* n_records);
 /* Device pointers to the results of the last pb2_call_resident: the dense per-locus reference stream (gVCF), its validity bytes,
@@ -170,6 +201,9 @@ int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out
 int pb2_get_counts(pb2_handle* h, int32_t position0, int32_t n, int32_t* out);
 /* Drop staged pileups and results (IStateManager.DoneProcessing). */
 int pb2_reset(pb2_handle* h);
+
+/* IAlleleCaller.TotalNumCollapsed (src/exe/Pisces/Interfaces/IAlleleCaller.cs:11): candidates merged by the collapser since pb2_create. */
+int pb2_totals(pb2_handle* h, int64_t* total_collapsed);
 
 /* Timing/diagnostics for bench.py: kernel launches and device milliseconds of the hot kernel since the last call, measured with
  * CUDA events on the handle's stream. */

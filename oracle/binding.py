@@ -72,6 +72,8 @@ def lib():
         for f in ("po_caller_add_read", "po_caller_add_read_counts_only", "po_caller_add_read_candidates_only"):
             getattr(L, f).argtypes = [C.c_void_p, C.POINTER(ReadStruct)]
         L.po_caller_add_pileup.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.po_caller_add_candidate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                              C.POINTER(C.c_int32)]
         L.po_caller_finish.argtypes = [C.c_void_p]
         L.po_caller_num_records.argtypes = [C.c_void_p]
         L.po_caller_get_record.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Record)]
@@ -200,6 +202,11 @@ class Caller:
         code, qual, anchor = (np.ascontiguousarray(x, dtype=np.uint8) for x in (code, qual, anchor))
         self._chk(self.L.po_caller_add_pileup(self.h, len(offsets) - 1, first_position, offsets.ctypes.data, code.ctypes.data, qual.ctypes.data,
                                               anchor.ctypes.data, call_every))
+
+    def add_candidate(self, type_, pos, ref, alt, support=(0, 0, 0), well_anchored=(0, 0, 0), open_left=False, open_right=False, collapsed_mut=None):
+        cm = (C.c_int32 * 8)(*(collapsed_mut or [0] * 8))
+        self._chk(self.L.po_caller_add_candidate(self.h, type_, pos, ref.encode(), alt.encode(), (C.c_int32 * 3)(*support), (C.c_int32 * 3)(*well_anchored),
+                                                 int(open_left), int(open_right), cm))
 
     def records_array(self):
         """All records as a numpy structured array (fast path for large outputs)."""

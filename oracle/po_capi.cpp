@@ -123,6 +123,18 @@ int po_caller_add_pileup(void* h, int64_t n_loci, int32_t first_pos, const int64
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+int po_caller_add_candidate(void* h, int32_t type, int32_t pos, const char* ref, const char* alt, const int32_t support[3], const int32_t wa[3], int32_t open_left,
+                            int32_t open_right, const int32_t collapsed_mut[8]) {
+    try {
+        auto* s = (SmallVariantCaller*)h;
+        auto c = std::make_shared<CandidateAllele>(s->chrName, pos, ref, alt, (AlleleCategory)type);
+        for (int k = 0; k < 3; k++) { c->SupportByDirection[k] = support[k]; c->WellAnchoredSupportByDirection[k] = wa[k]; }
+        if (collapsed_mut) for (int k = 0; k < 8; k++) c->ReadCollapsedCountsMut[k] = collapsed_mut[k];
+        c->OpenOnLeft = open_left != 0; c->OpenOnRight = open_right != 0;
+        s->state->AddCandidates({c});
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 int po_caller_finish(void* h) { GUARD(((SmallVariantCaller*)h)->Finish()) }
 int32_t po_caller_num_records(void* h) { return (int32_t)((SmallVariantCaller*)h)->output.size(); }
 

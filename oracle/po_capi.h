@@ -64,6 +64,9 @@ int po_caller_add_read(void* h, const po_read* r);           /* find candidates 
 int po_caller_add_read_counts_only(void* h, const po_read* r); /* RegionStateManager.AddAlleleCounts only */
 int po_caller_add_read_candidates_only(void* h, const po_read* r); /* FindCandidates + AddCandidates only */
 int po_caller_add_pileup(void* h, int64_t n_loci, int32_t first_pos, const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int32_t call_every);
+/* IAlleleSource.AddCandidates with one hand-built candidate (explicit candidates of the locus-major path) */
+int po_caller_add_candidate(void* h, int32_t type, int32_t pos, const char* ref, const char* alt, const int32_t support[3], const int32_t well_anchored[3],
+                            int32_t open_left, int32_t open_right, const int32_t collapsed_mut[8]);
 int po_caller_finish(void* h);
 int32_t po_caller_num_records(void* h);
 int po_caller_get_record(void* h, int32_t i, po_record* out);

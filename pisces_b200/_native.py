@@ -17,7 +17,9 @@ class Config(C.Structure):
         ("forced_noise_level", C.c_int32), ("noise_model", C.c_int32), ("strand_bias_acceptance", C.c_float),
         ("strand_bias_model", C.c_int32), ("filter_single_strand", C.c_int32), ("no_call_filter", C.c_float), ("ploidy", C.c_int32),
         ("tracked_anchor_size", C.c_int32), ("output_gvcf", C.c_int32), ("expect_stitched", C.c_int32), ("expect_collapsed", C.c_int32),
-        ("want_sum_base_quality", C.c_int32), ("collapse", C.c_int32), ("call_mnvs", C.c_int32), ("reserved", C.c_int32 * 2)]
+        ("want_sum_base_quality", C.c_int32), ("collapse", C.c_int32), ("call_mnvs", C.c_int32), ("indel_repeat_filter", C.c_int32),
+        ("max_size_mnv", C.c_int32), ("max_gap_mnv", C.c_int32), ("collapse_freq_threshold", C.c_float),
+        ("collapse_freq_ratio_threshold", C.c_float), ("exclude_mnvs_from_collapsing", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class PileupCsr(C.Structure):
@@ -28,6 +30,17 @@ class PileupCsr(C.Structure):
 class ReadBatch(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("pos0", C.c_void_p), ("flag", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p),
                 ("seq_off", C.c_void_p), ("bases", C.c_void_p), ("quals", C.c_void_p), ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p)]
+
+
+class Candidate(C.Structure):
+    _fields_ = [("position", C.c_int32), ("type", C.c_uint8), ("open_flags", C.c_uint8), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16),
+                ("reserved", C.c_uint16), ("allele_offset", C.c_uint32), ("support", C.c_int32 * 3), ("well_anchored", C.c_int32 * 3),
+                ("collapsed_mut", C.c_int32 * 8)]
+
+
+assert C.sizeof(Candidate) == 72
+CANDIDATE_DTYPE = [("position", "<i4"), ("type", "u1"), ("open_flags", "u1"), ("ref_len", "<u2"), ("alt_len", "<u2"), ("reserved", "<u2"),
+                   ("allele_offset", "<u4"), ("support", "<i4", (3,)), ("well_anchored", "<i4", (3,)), ("collapsed_mut", "<i4", (8,))]
 
 
 class CallRecord(C.Structure):
@@ -49,8 +62,8 @@ RECORD_DTYPE = [("position", "<i4"), ("type", "u1"), ("genotype", "u1"), ("sb_fl
                 ("ref_len", "<u2"), ("alt_len", "<u2"), ("sum_base_quality", "<f8"), ("bias_score", "<f8"), ("gatk_bias_score", "<f8")]
 
 EXPORTS = ["pb2_default_config", "pb2_create", "pb2_destroy", "pb2_last_error", "pb2_device_count", "pb2_set_reference", "pb2_set_intervals",
-           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_call_resident", "pb2_resident_results", "pb2_flush",
-           "pb2_get_counts", "pb2_reset", "pb2_stats", "pb2_stream"]
+           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_candidates", "pb2_allele_arena", "pb2_call_resident", "pb2_resident_results", "pb2_flush",
+           "pb2_get_counts", "pb2_reset", "pb2_stats", "pb2_stream", "pb2_totals"]
 
 _lib = None
 
@@ -76,12 +89,15 @@ def load():
     L.pb2_push_pileup.argtypes = [H, C.POINTER(PileupCsr)]
     L.pb2_push_pileup_device.argtypes = [H, C.POINTER(PileupCsr)]
     L.pb2_push_reads.argtypes = [H, C.POINTER(ReadBatch)]
+    L.pb2_push_candidates.argtypes = [H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+    L.pb2_allele_arena.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.pb2_call_resident.argtypes = [H, C.POINTER(C.c_int64)]
     L.pb2_resident_results.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.pb2_flush.argtypes = [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.pb2_get_counts.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
     L.pb2_reset.argtypes = [H]
     L.pb2_stats.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.pb2_totals.argtypes = [H, C.POINTER(C.c_int64)]
     L.pb2_stream.argtypes = [H]
     L.pb2_stream.restype = C.c_void_p
     _lib = L

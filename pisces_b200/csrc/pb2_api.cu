@@ -6,110 +6,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
-#include "pb2_kernels.cuh"
-#include "pb2_math.cuh"
+#include "pb2_internal.hpp"
 
 using namespace pb2;
-
-namespace pb2 {
-struct ReadsView {
-    int32_t n_reads;
-    const int32_t* pos0;
-    const uint16_t* flag;
-    const int64_t* cigar_off;
-    const uint32_t* cigar;
-    const int64_t* seq_off;
-    const uint8_t* bases;
-    const uint8_t* quals;
-    const uint8_t* base_dirs;
-    const uint8_t* collapsed;
-};
-struct RegionView {
-    int32_t lo, hi;
-    const int32_t* index_of_pos;
-    const uint8_t* chr;
-    int64_t chr_len;
-    int min_bq;
-    int expect_collapsed;
-};
-cudaError_t launch_reads_count(const ReadsView& rv, const RegionView& rg, unsigned int* depth, cudaStream_t st);
-cudaError_t launch_reads_emit(const ReadsView& rv, const RegionView& rg, const int64_t* offsets, unsigned int* cursor, uint8_t* code, uint8_t* qual, uint8_t* anch,
-                              cudaStream_t st);
-cudaError_t launch_depth_to_i64(const unsigned int* depth, int64_t* out, int64_t n, cudaStream_t st);
-}  // namespace pb2
-
-namespace {
-
-struct HostReads {   // reads staged by pb2_push_reads, kept until a flush clears the positions they cover
-    std::vector<int32_t> pos0, end_pos;
-    std::vector<uint16_t> flag;
-    std::vector<int64_t> cigar_off{0}, seq_off{0};
-    std::vector<uint32_t> cigar;
-    std::vector<uint8_t> bases, quals, base_dirs, collapsed;
-    bool has_dirs = false, has_collapsed = false;
-    size_t size() const { return pos0.size(); }
-    void clear() { *this = HostReads(); }
-};
-
-thread_local std::string g_create_error;
-
-struct Segment {   // one staged pileup (pb2_push_pileup*)
-    int64_t n_loci = 0;
-    int32_t n_tiles = 0;
-    int32_t first_position = 0;
-    bool has_positions = false;
-    int64_t plane_bytes = 0;
-    int64_t n_entries = 0;
-    int32_t max_depth = 0;
-    size_t alloc_plane = 0, alloc_ref = 0, alloc_var = 0, alloc_pending = 0;
-    // device
-    int32_t* depth = nullptr;
-    int32_t* pad = nullptr;
-    int64_t* tile_base = nullptr;
-    uint8_t *code = nullptr, *qual = nullptr, *anch = nullptr, *ref_base = nullptr;
-    int32_t* positions = nullptr;
-    pb2_call_record* ref_records = nullptr;
-    uint8_t* ref_valid = nullptr;
-    pb2_call_record* var_records = nullptr;
-    int64_t var_capacity = 0;
-    uint32_t* exc_entries = nullptr;
-    int64_t exc_capacity = 0;
-    PendingLocus* pending = nullptr;
-    int64_t pending_capacity = 0;
-    unsigned long long* counters = nullptr;   // [0] var_count, [1] exc_count, [2] pending_count
-    // host copies needed for ordering / lookups
-    std::vector<int32_t> h_positions;
-    bool called = false;
-    bool temporary = false;   // built inside pb2_flush from staged reads; freed when the flush returns
-    unsigned long long h_var_count = 0, h_exc_count = 0;
-};
-
-}  // namespace
-
-struct pb2_handle {
-    pb2_config cfg;
-    DeviceConfig dcfg;
-    int device = 0;
-    int num_sms = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::string error;
-    std::string chr_name;
-    uint8_t* d_chr = nullptr;
-    double* d_q_to_p = nullptr;     // QtoP(q) for q = 0..max_variant_qscore (capped at 1024 entries)
-    int q_table_max = -1;
-    int64_t chr_len = 0;
-    std::vector<uint8_t> h_chr;
-    std::vector<int32_t> iv_start, iv_end;
-    bool have_intervals = false;
-    std::vector<Segment> segs;
-    HostReads reads;
-    int32_t cleared_through = 0;   // positions <= this were called by an earlier pb2_flush(up_to >= 0)
-    int* d_tile_counter = nullptr;
-    std::vector<pb2_call_record> h_out;
-    int64_t hot_launches = 0, total_launches = 0;
-    double hot_ms = 0;
-};
 
 #define CU(h, expr)                                                                                      \
     do {                                                                                                 \
@@ -120,10 +19,12 @@ struct pb2_handle {
         }                                                                                                \
     } while (0)
 
-static int fail(pb2_handle* h, int code, const std::string& msg) {
+static thread_local std::string g_create_error;
+int pb2_fail(pb2_handle* h, int code, const std::string& msg) {
     if (h) h->error = msg; else g_create_error = msg;
     return code;
 }
+static int fail(pb2_handle* h, int code, const std::string& msg) { return pb2_fail(h, code, msg); }
 
 extern "C" void pb2_default_config(pb2_config* c) {
     memset(c, 0, sizeof(*c));
@@ -140,6 +41,9 @@ extern "C" void pb2_default_config(pb2_config* c) {
     c->strand_bias_acceptance = 0.5f; c->strand_bias_model = 1; c->filter_single_strand = 0;
     c->no_call_filter = 0.6f; c->ploidy = 0; c->tracked_anchor_size = 5; c->output_gvcf = 1;
     c->expect_stitched = 0; c->expect_collapsed = 0; c->want_sum_base_quality = 0; c->collapse = 1; c->call_mnvs = 0;
+    c->indel_repeat_filter = -1;        // VariantCallingParameters.cs:74 (null)
+    c->max_size_mnv = 3; c->max_gap_mnv = 1;   // PiscesApplicationOptions.cs:43-66
+    c->collapse_freq_threshold = 0.0f; c->collapse_freq_ratio_threshold = 0.5f; c->exclude_mnvs_from_collapsing = 0;
 }
 
 extern "C" int pb2_device_count(void) {
@@ -170,6 +74,7 @@ static void derive_config(pb2_handle* h) {
     d.output_gvcf = c.output_gvcf; d.expect_stitched = c.expect_stitched; d.expect_collapsed = c.expect_collapsed;
     d.have_intervals = h->have_intervals ? 1 : 0;
     d.want_qsum = c.want_sum_base_quality;
+    d.snv_from_counts = c.call_mnvs ? 0 : 1;   // CallMNVs: SNV candidates come from the finder's state machine (explicit), not from the counts
     d.vq_error_rate = std::pow(10.0, -1 * (double)d.noise_level / 10.0);                      // QtoP: double division (MathOperations.cs:7-10)
     d.sb_noise = std::pow(10.0, (double)((float)(-1 * d.noise_level) / 10.0f));               // float exponent (StrandBiasCalculator.cs:32)
 }
@@ -236,6 +141,9 @@ extern "C" int pb2_reset(pb2_handle* h) {
     h->segs.clear();
     h->h_out.clear();
     h->reads.clear();
+    h->cands.clear(); h->block_max_endpoint.clear(); h->gapped_ref.clear(); h->triggers.clear(); h->arena.clear();
+    h->last_trigger_key = 0; h->push_last_key = 0; h->cleared_through = 0;
+    explicit_release_resident(h);
     return PB2_OK;
 }
 
@@ -395,13 +303,13 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
 extern "C" int pb2_push_pileup(pb2_handle* h, const pb2_pileup_csr* p) { return push_common(h, p, false); }
 extern "C" int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p) { return push_common(h, p, true); }
 
-static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out) {
+static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out, const int32_t* d_gapped = nullptr) {
     cudaStream_t st = h->stream;
     TilePileup in;
     in.code = s.code; in.qual = s.qual; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
     in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles; in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);
     HotInputsExtra ex;
-    ex.gapped_ref = nullptr; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len; ex.q_to_p_table = h->d_q_to_p; ex.q_table_max = h->q_table_max;
+    ex.gapped_ref = d_gapped; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len; ex.q_to_p_table = h->d_q_to_p; ex.q_table_max = h->q_table_max;
     HotOutputs out;
     out.ref_records = s.ref_records; out.ref_valid = s.ref_valid; out.var_records = s.var_records; out.var_count = s.counters;
     out.var_capacity = s.var_capacity; out.exc_entries = s.exc_entries; out.exc_count = s.counters + 1; out.exc_capacity = s.exc_capacity;
@@ -431,8 +339,8 @@ extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
     if (!h || !b || b->n_reads < 0) return fail(h, PB2_ERR_ARG, "pb2_push_reads: bad argument");
     if (b->n_reads == 0) return PB2_OK;
     if (!b->pos0 || !b->flag || !b->cigar_off || !b->cigar || !b->seq_off || !b->bases || !b->quals) return fail(h, PB2_ERR_ARG, "pb2_push_reads: null array");
-    if (h->cfg.call_mnvs) return fail(h, PB2_ERR_UNSUPPORTED, "pb2_push_reads: CallMNVs=true is not built yet");
     HostReads& R = h->reads;
+    const size_t first_new = R.size();
     if (R.size() == 0) { R.has_dirs = b->base_dirs != nullptr; R.has_collapsed = b->collapsed != nullptr; }
     else if (R.has_dirs != (b->base_dirs != nullptr) || R.has_collapsed != (b->collapsed != nullptr))
         return fail(h, PB2_ERR_ARG, "pb2_push_reads: base_dirs / collapsed must be given for all batches or none");
@@ -459,7 +367,17 @@ extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
         if (R.has_dirs) R.base_dirs.insert(R.base_dirs.end(), b->base_dirs + s0, b->base_dirs + s1);
         R.seq_off.push_back((int64_t)R.bases.size());
         if (R.has_collapsed) R.collapsed.push_back(b->collapsed[i]);
+        // SmallVariantCaller.Execute calls Call(read.Position - 1) after every read (:99-104); a batch forms when that enters a new block key
+        const int32_t up_to = b->pos0[i];
+        const int32_t key = up_to <= 0 ? 0 : (up_to + 999) / 1000;
+        if (key != h->push_last_key) { h->triggers.push_back(up_to); h->push_last_key = key; }
     }
+    return explicit_find_candidates(h, R, first_new);
+}
+
+extern "C" int pb2_totals(pb2_handle* h, int64_t* total_collapsed) {
+    if (!h) return PB2_ERR_ARG;
+    if (total_collapsed) *total_collapsed = h->total_collapsed;
     return PB2_OK;
 }
 
@@ -580,6 +498,12 @@ extern "C" int pb2_call_resident(pb2_handle* h, int64_t* n_records) {
         if (rc != PB2_OK) return rc;
         total += (int64_t)s.h_var_count;
     }
+    if (!h->cands.empty()) {   // explicit candidates: gathered, scored and appended to the (last) segment's variant stream on the device
+        if (h->segs.size() != 1) return fail(h, PB2_ERR_UNSUPPORTED, "pb2_call_resident with explicit candidates needs exactly one staged segment; use pb2_flush");
+        const int rc = explicit_call_resident(h, h->segs[0]);
+        if (rc != PB2_OK) return rc;
+        total = (int64_t)h->segs[0].h_var_count;
+    }
     if (n_records) *n_records = total;
     return PB2_OK;
 }
@@ -595,26 +519,6 @@ extern "C" int pb2_resident_results(pb2_handle* h, const pb2_call_record** ref_r
     if (variant_records) *variant_records = s.var_records;
     if (n_variants) *n_variants = (int64_t)s.h_var_count;
     return PB2_OK;
-}
-
-static inline bool record_less(const pb2_call_record& a, const pb2_call_record& b) {
-    if (a.position != b.position) return a.position < b.position;
-    // (ReferenceAllele, AlternateAllele) string order (AlleleCaller.cs:172-176); inline alleles only so far
-    const uint32_t ra = a.allele_bytes & ((1u << (8 * a.ref_len)) - 1), rb = b.allele_bytes & ((1u << (8 * b.ref_len)) - 1);
-    auto bytes_less = [](uint32_t x, int nx, uint32_t y, int ny, bool& eq) {
-        for (int i = 0; i < std::min(nx, ny); i++) {
-            const uint8_t cx = (x >> (8 * i)) & 0xff, cy = (y >> (8 * i)) & 0xff;
-            if (cx != cy) { eq = false; return cx < cy; }
-        }
-        eq = nx == ny;
-        return nx < ny;
-    };
-    bool eq;
-    bool l = bytes_less(ra, a.ref_len, rb, b.ref_len, eq);
-    if (!eq) return l;
-    const uint32_t aa = a.allele_bytes >> (8 * a.ref_len), ab = b.allele_bytes >> (8 * b.ref_len);
-    l = bytes_less(aa, a.alt_len, ab, b.alt_len, eq);
-    return eq ? false : l;
 }
 
 // Flagged mismatching entries (side list of the hot kernel) against the SNV records it emitted.
@@ -679,19 +583,156 @@ static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std:
     return PB2_OK;
 }
 
+// Allele strings of a record (inline when ref_len + alt_len <= 4, else in the flush arena)
+static inline void record_alleles(const pb2_call_record& r, const std::vector<uint8_t>& arena, const uint8_t*& ref, const uint8_t*& alt, uint8_t* inline_buf) {
+    if (r.ref_len + r.alt_len <= 4) {
+        for (int i = 0; i < 4; i++) inline_buf[i] = (uint8_t)((r.allele_bytes >> (8 * i)) & 0xff);
+        ref = inline_buf;
+    } else ref = arena.data() + r.allele_bytes;
+    alt = ref + r.ref_len;
+}
+// (position, ReferenceAllele, AlternateAllele) ordinal order: SortedList by position + ComputeGenotypeAndFilterAllele's OrderBy (AlleleCaller.cs:96-140,172-176)
+static bool record_less_arena(const pb2_call_record& a, const pb2_call_record& b, const std::vector<uint8_t>& arena) {
+    if (a.position != b.position) return a.position < b.position;
+    uint8_t ba[4], bb[4];
+    const uint8_t *ra, *aa, *rb, *ab;
+    record_alleles(a, arena, ra, aa, ba);
+    record_alleles(b, arena, rb, ab, bb);
+    auto cmp = [](const uint8_t* x, int nx, const uint8_t* y, int ny) {
+        const int c = memcmp(x, y, (size_t)std::min(nx, ny));
+        return c != 0 ? c : nx - ny;
+    };
+    const int c1 = cmp(ra, a.ref_len, rb, b.ref_len);
+    if (c1 != 0) return c1 < 0;
+    return cmp(aa, a.alt_len, ab, b.alt_len) < 0;
+}
+
+// Per-locus gapped-MNV reference counts of a segment (RegionState._gappedMnvReferenceCounts), or nullptr when there are none.
+static int upload_gapped(pb2_handle* h, const Segment& s, int32_t** d_out) {
+    *d_out = nullptr;
+    if (h->gapped_ref.empty()) return PB2_OK;
+    std::vector<int32_t> g((size_t)s.n_loci, 0);
+    bool any = false;
+    for (auto& kv : h->gapped_ref) {
+        int64_t l = -1;
+        if (s.has_positions) {
+            auto it = std::lower_bound(s.h_positions.begin(), s.h_positions.end(), kv.first);
+            if (it != s.h_positions.end() && *it == kv.first) l = it - s.h_positions.begin();
+        } else {
+            const int64_t k = (int64_t)kv.first - s.first_position;
+            if (k >= 0 && k < s.n_loci) l = k;
+        }
+        if (l >= 0) { g[(size_t)l] = kv.second; any = true; }
+    }
+    if (!any) return PB2_OK;
+    CU(h, cudaMalloc(d_out, sizeof(int32_t) * g.size()));
+    CU(h, cudaMemcpyAsync(*d_out, g.data(), sizeof(int32_t) * g.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PB2_OK;
+}
+
+// The explicit-candidate batches of this flush, replaying the batches SmallVariantCaller.Execute would have formed (SmallVariantCaller.cs:88-104,
+// RegionStateManager.GetCandidatesToProcess :283-334): a batch happens whenever upTo = (read position - 1) enters a new 1000-bp block key; it takes
+// the existing blocks that end at or before upTo, in order, up to the first block holding an allele that extends past upTo, plus — when an included
+// allele reaches past the last included block — the finished open-left SNV/MNV candidates of later blocks (AddCollapsableFromOtherBlocks :441-457).
+// Returns the last position cleared (0 = none; INT32_MAX = everything).
+static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, std::vector<pb2_call_record>& called, int32_t* cleared_out) {
+    *cleared_out = h->cleared_through;
+    auto all_alive_sorted = [&]() {
+        std::vector<size_t> idx;
+        for (size_t i = 0; i < h->cands.size(); i++) if (h->cands[i].alive) idx.push_back(i);
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return h->cands[a].position < h->cands[b].position; });
+        return idx;
+    };
+    if (!reads_path) {   // locus-major pushes are complete by construction: one batch, nothing left uncleared
+        const int rc = explicit_call_batch(h, all_alive_sorted(), -1, called);
+        *cleared_out = INT32_MAX;
+        return rc;
+    }
+    // blocks that exist: touched by a kept read, or holding a candidate
+    std::vector<int32_t> keys;
+    {
+        const HostReads& R = h->reads;
+        for (size_t i = 0; i < R.size(); i++) {
+            const int a = std::max(R.pos0[i] + 1, h->cleared_through + 1), e = R.end_pos[i];
+            for (int k = (a + 999) / 1000; a <= e && k <= (e + 999) / 1000; k++) keys.push_back(k);
+        }
+        for (auto& c : h->cands) if (c.alive) keys.push_back((c.position + 999) / 1000);
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    }
+    std::vector<int32_t> fire;   // upTo values in call order; -1 = the final Call(null)
+    {
+        size_t used = 0;
+        for (int32_t t : h->triggers) { if (up_to >= 0 && t > up_to) break; fire.push_back(t); used++; }
+        h->triggers.erase(h->triggers.begin(), h->triggers.begin() + (long)used);
+        fire.push_back(up_to >= 0 ? up_to : -1);
+    }
+    for (int32_t t : fire) {
+        const int key = t < 0 ? -1 : (t <= 0 ? 0 : (t + 999) / 1000);
+        if (t >= 0 && key == h->last_trigger_key) continue;     // GetCandidatesToProcess returns null (:288-291)
+        h->last_trigger_key = key;
+        int32_t max_end = 0, max_endpoint = 0;
+        for (int32_t k : keys) {
+            if ((int64_t)k * 1000 <= *cleared_out) continue;                    // already processed and recycled
+            if (t >= 0 && !((int64_t)k * 1000 <= t)) continue;
+            auto it = h->block_max_endpoint.find(k);
+            const int32_t mep = it == h->block_max_endpoint.end() ? 0 : it->second;
+            if (t >= 0 && mep > t) break;                                        // :305-306
+            max_end = k * 1000;
+            max_endpoint = std::max(max_endpoint, mep);
+        }
+        if (max_end == 0) continue;
+        std::vector<size_t> batch;
+        for (size_t i : all_alive_sorted()) if (h->cands[i].position > *cleared_out && h->cands[i].position <= max_end) batch.push_back(i);
+        if (t >= 0 && max_endpoint > max_end && h->cfg.collapse) {
+            for (size_t i : all_alive_sorted()) {   // ExtractCollapsable(upTo) of the blocks that start after max_end and at or before upTo (RegionState.cs:470-490)
+                const HostCand& c = h->cands[i];
+                const int32_t block_start = ((c.position + 999) / 1000 - 1) * 1000 + 1;
+                if (c.position > max_end && block_start <= t && c.position + (int)c.alt.size() - 1 <= t && !c.open_right && (c.type == CAT_MNV || c.type == CAT_SNV))
+                    batch.push_back(i);
+            }
+        }
+        const int rc = explicit_call_batch(h, batch, t >= 0 ? max_end : -1, called);
+        if (rc != PB2_OK) return rc;
+        *cleared_out = t >= 0 ? max_end : INT32_MAX;
+    }
+    return PB2_OK;
+}
+
 extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n) {
     if (!h || !out || !n) return fail(h, PB2_ERR_ARG, "pb2_flush: null argument");
     CU(h, cudaSetDevice(h->device));
     h->h_out.clear();
+    h->arena.clear();
+    const bool reads_path = h->reads.size() != 0 || !h->triggers.empty();
+    if (h->resident_explicit) for (auto& s : h->segs) s.called = false;   // a pb2_call_resident pass appended explicit alleles to the variant stream: redo
     // reads staged through pb2_push_reads: positions in complete 1000-bp blocks <= up_to_position are callable (RegionStateManager.cs:283-314);
     // locus-major pushes are complete by construction
     const int32_t cleared_end = up_to_position < 0 ? INT32_MAX : (up_to_position / 1000) * 1000;
     {
-        const int rc = stage_reads_segment(h, cleared_end, h->cleared_through + 1);
+        // counts are final for every position <= up_to (reads arrive in position order): stage them all, so that alleles reaching past the last
+        // complete block find their end-point coverage; only positions inside cleared blocks are emitted below
+        const int rc = stage_reads_segment(h, up_to_position < 0 ? INT32_MAX : up_to_position, h->cleared_through + 1);
         if (rc != PB2_OK) return rc;
     }
+    // explicit candidates first: their gapped-MNV reference counts feed the point alleles of the hot kernel
+    std::vector<pb2_call_record> explicit_called;
+    int32_t cleared_to = cleared_end;
+    {
+        const int rc = run_explicit_batches(h, up_to_position, reads_path, explicit_called, &cleared_to);
+        if (rc != PB2_OK) return rc;
+        if (!reads_path) cleared_to = INT32_MAX;
+    }
+    std::vector<uint8_t> explicit_used(explicit_called.size(), 0);
     for (auto& s : h->segs) {
-        if (!s.called) { int rc = run_segment(h, s, nullptr, nullptr); if (rc != PB2_OK) return rc; }
+        if (!s.called) {
+            int32_t* d_gapped = nullptr;
+            int rc = upload_gapped(h, s, &d_gapped);
+            if (rc == PB2_OK) rc = run_segment(h, s, nullptr, nullptr, d_gapped);
+            if (d_gapped) cudaFree(d_gapped);
+            if (rc != PB2_OK) return rc;
+        }
         std::vector<pb2_call_record> vars((size_t)s.h_var_count);
         std::vector<uint32_t> exc((size_t)s.h_exc_count * 2);
         if (!exc.empty()) CU(h, cudaMemcpyAsync(exc.data(), s.exc_entries, sizeof(uint32_t) * exc.size(), cudaMemcpyDeviceToHost, h->stream));
@@ -705,29 +746,54 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
             CU(h, cudaMemcpyAsync(valid.data(), s.ref_valid, valid.size(), cudaMemcpyDeviceToHost, h->stream));
         }
         CU(h, cudaStreamSynchronize(h->stream));
-        if (!exc.empty()) { const int rc = reconcile_flagged_entries(h, s, exc, vars); if (rc != PB2_OK) return rc; }
-        std::sort(vars.begin(), vars.end(), record_less);
-        // merge the dense reference stream (already in position order) with the sorted variant stream
+        if (!exc.empty() && !h->cfg.call_mnvs) { const int rc = reconcile_flagged_entries(h, s, exc, vars); if (rc != PB2_OK) return rc; }
+        // the explicit alleles called inside this segment's positions join its variant stream
+        const int32_t seg_lo = s.has_positions ? (s.h_positions.empty() ? 1 : s.h_positions.front()) : s.first_position;
+        const int32_t seg_hi = s.has_positions ? (s.h_positions.empty() ? 0 : s.h_positions.back()) : (int32_t)(s.first_position + s.n_loci - 1);
+        std::map<int32_t, pb2_call_record> ref_override;   // reference alleles that gained support from a reallocated MNV (MnvReallocator.cs:255-265)
+        for (size_t k = 0; k < explicit_called.size(); k++)
+            if (!explicit_used[k] && explicit_called[k].position >= seg_lo && explicit_called[k].position <= seg_hi) {
+                if (explicit_called[k].type == CAT_REF) ref_override[explicit_called[k].position] = explicit_called[k];
+                else vars.push_back(explicit_called[k]);
+                explicit_used[k] = 1;
+            }
+        std::sort(vars.begin(), vars.end(), [&](const pb2_call_record& a, const pb2_call_record& b) { return record_less_arena(a, b, h->arena); });
+        // merge the dense reference stream (already in position order) with the sorted variant stream; a reference allele is pruned wherever a
+        // variant was called (AlleleCaller.cs:146-147)
         size_t vi = 0;
         for (int64_t i = 0; i < s.n_loci; i++) {
             const int32_t pos = s.has_positions ? s.h_positions[(size_t)i] : s.first_position + (int32_t)i;
+            if (pos > cleared_to) break;
             while (vi < vars.size() && vars[vi].position < pos) h->h_out.push_back(vars[vi++]);
-            while (vi < vars.size() && vars[vi].position == pos) h->h_out.push_back(vars[vi++]);
-            if (!refs.empty() && valid[(size_t)i]) h->h_out.push_back(refs[(size_t)i]);
+            bool variant_here = false;
+            while (vi < vars.size() && vars[vi].position == pos) { h->h_out.push_back(vars[vi++]); variant_here = true; }
+            if (!refs.empty() && valid[(size_t)i] && !variant_here) {
+                auto ov = ref_override.find(pos);
+                h->h_out.push_back(ov == ref_override.end() ? refs[(size_t)i] : ov->second);
+            }
         }
-        while (vi < vars.size()) h->h_out.push_back(vars[vi++]);
+        while (vi < vars.size() && vars[vi].position <= cleared_to) h->h_out.push_back(vars[vi++]);
     }
-    // drop what this flush consumed: temporary segments, and reads that end inside the cleared positions
+    {   // explicit alleles at positions no segment stages (e.g. an insertion before the first covered base)
+        std::vector<pb2_call_record> rest;
+        for (size_t k = 0; k < explicit_called.size(); k++) if (!explicit_used[k]) rest.push_back(explicit_called[k]);
+        if (!rest.empty()) {
+            h->h_out.insert(h->h_out.end(), rest.begin(), rest.end());
+            std::stable_sort(h->h_out.begin(), h->h_out.end(), [&](const pb2_call_record& a, const pb2_call_record& b) { return a.position < b.position; });
+        }
+    }
+    // drop what this flush consumed: temporary segments, reads that end inside the cleared positions, dead candidates, used gapped counts
     for (size_t i = 0; i < h->segs.size();) {
         if (h->segs[i].temporary) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); } else i++;
     }
-    if (up_to_position < 0) { h->reads.clear(); h->cleared_through = 0; }
-    else if (h->reads.size() != 0 && cleared_end > h->cleared_through) {
+    h->cands.erase(std::remove_if(h->cands.begin(), h->cands.end(), [](const HostCand& c) { return !c.alive; }), h->cands.end());
+    if (up_to_position < 0) { h->reads.clear(); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; }
+    else if (reads_path && cleared_to > h->cleared_through) {
         HostReads keep;
         HostReads& R = h->reads;
         keep.has_dirs = R.has_dirs; keep.has_collapsed = R.has_collapsed;
         for (size_t i = 0; i < R.size(); i++) {
-            if (R.end_pos[i] <= cleared_end) continue;
+            if (R.end_pos[i] <= cleared_to) continue;
             keep.pos0.push_back(R.pos0[i]); keep.end_pos.push_back(R.end_pos[i]); keep.flag.push_back(R.flag[i]);
             keep.cigar.insert(keep.cigar.end(), R.cigar.begin() + R.cigar_off[i], R.cigar.begin() + R.cigar_off[i + 1]);
             keep.cigar_off.push_back((int64_t)keep.cigar.size());
@@ -738,10 +804,42 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
             if (R.has_collapsed) keep.collapsed.push_back(R.collapsed[i]);
         }
         h->reads = std::move(keep);
-        h->cleared_through = cleared_end;
+        h->cleared_through = cleared_to;
+        for (auto it = h->gapped_ref.begin(); it != h->gapped_ref.end();) { if (it->first <= cleared_to) it = h->gapped_ref.erase(it); else ++it; }
     }
     *out = h->h_out.data();
     *n = (int64_t)h->h_out.size();
+    return PB2_OK;
+}
+
+extern "C" int pb2_push_candidates(pb2_handle* h, const pb2_candidate* cands, int32_t n, const uint8_t* arena, int64_t arena_len) {
+    if (!h || n < 0 || (n > 0 && (!cands || !arena))) return fail(h, PB2_ERR_ARG, "pb2_push_candidates: bad argument");
+    for (int32_t i = 0; i < n; i++) {
+        const pb2_candidate& c = cands[i];
+        if (c.position <= 0) return fail(h, PB2_ERR_ARG, "Coordinate is invalid.");                        // CandidateAllele.cs:96-110
+        if (c.ref_len == 0) return fail(h, PB2_ERR_ARG, "Reference is empty.");
+        if (c.alt_len == 0) return fail(h, PB2_ERR_ARG, "Alternate is empty.");
+        if (c.type > CAT_MNV) return fail(h, PB2_ERR_ARG, "reference candidates are not tracked");           // RegionState.cs:96-97
+        if ((int64_t)c.allele_offset + c.ref_len + c.alt_len > arena_len) return fail(h, PB2_ERR_ARG, "pb2_push_candidates: allele outside the arena");
+        if (c.type == CAT_SNV && !h->cfg.call_mnvs)
+            return fail(h, PB2_ERR_ARG, "pb2_push_candidates: with CallMNVs off, SNV support is taken from the pileup counts; push SNV candidates only with call_mnvs=1");
+        HostCand hc;
+        hc.position = c.position; hc.type = c.type;
+        hc.open_left = (c.open_flags & 1) != 0; hc.open_right = (c.open_flags & 2) != 0;
+        hc.ref.assign(reinterpret_cast<const char*>(arena) + c.allele_offset, c.ref_len);
+        hc.alt.assign(reinterpret_cast<const char*>(arena) + c.allele_offset + c.ref_len, c.alt_len);
+        for (int k = 0; k < 3; k++) { hc.support[k] = c.support[k]; hc.well_anchored[k] = c.well_anchored[k]; }
+        for (int k = 0; k < 8; k++) hc.collapsed_mut[k] = c.collapsed_mut[k];
+        explicit_add_candidate(h, hc);
+    }
+    explicit_release_resident(h);
+    return PB2_OK;
+}
+
+extern "C" int pb2_allele_arena(pb2_handle* h, const uint8_t** arena, int64_t* len) {
+    if (!h || !arena || !len) return fail(h, PB2_ERR_ARG, "pb2_allele_arena: null argument");
+    *arena = h->arena.data();
+    *len = (int64_t)h->arena.size();
     return PB2_OK;
 }
 

@@ -1,0 +1,161 @@
+// Internal to libpisces_b200.so: the handle, a staged segment, the read buffer and the explicit-candidate table (host side).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+#include "pb2_candidates.cuh"
+#include "pb2_kernels.cuh"
+#include "pb2_math.cuh"
+
+namespace pb2 {
+struct ReadsView {
+    int32_t n_reads;
+    const int32_t* pos0;
+    const uint16_t* flag;
+    const int64_t* cigar_off;
+    const uint32_t* cigar;
+    const int64_t* seq_off;
+    const uint8_t* bases;
+    const uint8_t* quals;
+    const uint8_t* base_dirs;
+    const uint8_t* collapsed;
+};
+struct RegionView {
+    int32_t lo, hi;
+    const int32_t* index_of_pos;
+    const uint8_t* chr;
+    int64_t chr_len;
+    int min_bq;
+    int expect_collapsed;
+};
+cudaError_t launch_reads_count(const ReadsView& rv, const RegionView& rg, unsigned int* depth, cudaStream_t st);
+cudaError_t launch_reads_emit(const ReadsView& rv, const RegionView& rg, const int64_t* offsets, unsigned int* cursor, uint8_t* code, uint8_t* qual, uint8_t* anch,
+                              cudaStream_t st);
+cudaError_t launch_depth_to_i64(const unsigned int* depth, int64_t* out, int64_t n, cudaStream_t st);
+
+// One candidate found in one read by reads_candidates_kernel. 24 bytes.
+struct RawCand {
+    int32_t read;            // index of the read in the pushed buffer
+    int32_t order;           // (CIGAR operation index << 16) | offset in the operation: FindCandidates' emission order inside the read
+    int32_t position;        // ReferencePosition
+    int32_t start_in_read;   // first inserted / variant base in the read (insertions: the alt allele is the reference base + bases[start, start+len))
+    uint16_t ref_len, alt_len;
+    uint8_t type, dir;       // AlleleCategory, DirectionType of the support
+    uint8_t flags;           // bit0 OpenOnLeft, bit1 OpenOnRight, bit2 well anchored
+    uint8_t collapsed;       // ReadCollapsedType + 1, or 0
+};
+static_assert(sizeof(RawCand) == 24, "RawCand layout");
+cudaError_t launch_reads_candidates(const ReadsView& rv, int32_t first_read, const uint8_t* chr, int64_t chr_len, int min_bq, int call_mnvs, int max_mnv, int max_gap,
+                                    int expect_collapsed, RawCand* out, unsigned long long* count, int64_t capacity, cudaStream_t st);
+}  // namespace pb2
+
+struct HostReads {   // reads staged by pb2_push_reads, kept until a flush clears the positions they cover
+    std::vector<int32_t> pos0, end_pos;
+    std::vector<uint16_t> flag;
+    std::vector<int64_t> cigar_off{0}, seq_off{0};
+    std::vector<uint32_t> cigar;
+    std::vector<uint8_t> bases, quals, base_dirs, collapsed;
+    bool has_dirs = false, has_collapsed = false;
+    size_t size() const { return pos0.size(); }
+    void clear() { *this = HostReads(); }
+};
+
+// CandidateAllele (src/lib/Pisces.Domain/Models/Alleles/CandidateAllele.cs:8-125) on the host: one row of the explicit-candidate table.
+struct HostCand {
+    int32_t position = 0;
+    uint8_t type = 0;              // AlleleCategory
+    bool open_left = false, open_right = false;
+    std::string ref, alt;
+    int32_t support[3] = {0, 0, 0}, well_anchored[3] = {0, 0, 0}, collapsed_mut[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float frequency = 0;           // CandidateAllele.Frequency, set by the collapser
+    bool alive = true;
+    int Support() const { return support[0] + support[1] + support[2]; }
+    int WellAnchored() const { return well_anchored[0] + well_anchored[1] + well_anchored[2]; }
+    bool FullyAnchored() const { return !open_left && !open_right; }
+    int Length() const {           // BaseAllele.Length (BaseAllele.cs:24-43)
+        switch (type) { case 1: return (int)alt.size() - 1; case 2: return (int)ref.size() - 1; case 4: return (int)ref.size(); default: return (int)alt.size(); }
+    }
+    bool Equals(const HostCand& o) const { return o.position == position && o.type == type && o.alt == alt && o.ref == ref; }   // CandidateAllele.Equals (:56-66)
+};
+
+struct Segment {   // one staged pileup (pb2_push_pileup*)
+    int64_t n_loci = 0;
+    int32_t n_tiles = 0;
+    int32_t first_position = 0;
+    bool has_positions = false;
+    int64_t plane_bytes = 0;
+    int64_t n_entries = 0;
+    int32_t max_depth = 0;
+    size_t alloc_plane = 0, alloc_ref = 0, alloc_var = 0, alloc_pending = 0;
+    // device
+    int32_t* depth = nullptr;
+    int32_t* pad = nullptr;
+    int64_t* tile_base = nullptr;
+    uint8_t *code = nullptr, *qual = nullptr, *anch = nullptr, *ref_base = nullptr;
+    int32_t* positions = nullptr;
+    pb2_call_record* ref_records = nullptr;
+    uint8_t* ref_valid = nullptr;
+    pb2_call_record* var_records = nullptr;
+    int64_t var_capacity = 0;
+    uint32_t* exc_entries = nullptr;
+    int64_t exc_capacity = 0;
+    pb2::PendingLocus* pending = nullptr;
+    int64_t pending_capacity = 0;
+    unsigned long long* counters = nullptr;   // [0] var_count, [1] exc_count, [2] pending_count
+    // host copies needed for ordering / lookups
+    std::vector<int32_t> h_positions;
+    bool called = false;
+    bool temporary = false;   // built inside pb2_flush from staged reads; freed when the flush returns
+    unsigned long long h_var_count = 0, h_exc_count = 0;
+};
+
+struct pb2_handle {
+    pb2_config cfg;
+    pb2::DeviceConfig dcfg;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string error;
+    std::string chr_name;
+    uint8_t* d_chr = nullptr;
+    double* d_q_to_p = nullptr;     // QtoP(q) for q = 0..max_variant_qscore (capped at 1024 entries)
+    int q_table_max = -1;
+    int64_t chr_len = 0;
+    std::vector<uint8_t> h_chr;
+    std::vector<int32_t> iv_start, iv_end;
+    bool have_intervals = false;
+    std::vector<Segment> segs;
+    HostReads reads;
+    int32_t cleared_through = 0;   // positions <= this were called by an earlier pb2_flush(up_to >= 0)
+    int* d_tile_counter = nullptr;
+    std::vector<pb2_call_record> h_out;
+    int64_t hot_launches = 0, total_launches = 0;
+    double hot_ms = 0;
+    // ---- explicit candidates (pb2_explicit.cu)
+    std::vector<HostCand> cands;                      // uncleared candidates in RegionState.AddCandidate order
+    std::map<int32_t, int32_t> block_max_endpoint;    // RegionState.MaxAlleleEndpoint per 1000-bp block key
+    std::map<int32_t, int32_t> gapped_ref;            // RegionState._gappedMnvReferenceCounts of uncleared positions
+    std::vector<int32_t> triggers;                    // upTo values at which SmallVariantCaller.Execute would have called a batch
+    int32_t last_trigger_key = 0;                     // RegionStateManager._lastUpToBlockKey
+    int32_t push_last_key = 0;                        // the same, as seen while reads are pushed (which read positions open a batch)
+    void* resident_explicit = nullptr;                // cached device plan of pb2_call_resident's explicit-candidate pass
+    std::vector<uint8_t> arena;                       // allele bytes the last flush's records point into
+    int64_t total_collapsed = 0;
+};
+
+// pb2_explicit.cu
+int pb2_fail(pb2_handle* h, int code, const std::string& msg);
+// RegionState.AddCandidate (:94-174): merge into the table (summing counts) or append; tracks MaxAlleleEndpoint of the block.
+void explicit_add_candidate(pb2_handle* h, const HostCand& c);
+// The explicit-candidate part of AlleleCaller.Call for one batch of candidates (indices into h->cands, in batch order): VariantCollapser, MNV scoring
+// + MnvReallocator, gapped-MNV reference counts, final ProcessVariant of every callable allele on the device. Called alleles (IsCallable &&
+// ShouldReport) are appended to `called`; candidates that go back to the state (not cleared / MNV leftovers) are re-added to h->cands.
+// max_cleared < 0 = null (everything is cleared).
+int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, std::vector<pb2_call_record>& called);
+// Finds the candidates of the reads in R[first_read, end) on the device (CandidateVariantFinder.FindCandidates) and adds them to the table.
+int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_read);
+// pb2_call_resident: gather + score + append on the device, no host round trip; only for candidates that need neither the collapser nor the MNV logic.
+int explicit_call_resident(pb2_handle* h, Segment& seg);
+void explicit_release_resident(pb2_handle* h);
+

@@ -287,7 +287,7 @@ __device__ __forceinline__ void finish_locus(const LocusCounts& lc, int any, int
                                              const HotOutputs& out, const DeviceConfig& cfg, PendingLocus* cta_queue = nullptr, int* cta_count = nullptr) {
     const int gapped = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
     unsigned cand_mask = 0;
-    if (ref_allele != AT_N) {
+    if (ref_allele != AT_N && cfg.snv_from_counts) {
         int total = 0;
 #pragma unroll
         for (int d = 0; d < 3; d++) total += lc.c[AT_A][d] + lc.c[AT_C][d] + lc.c[AT_G][d] + lc.c[AT_T][d] + lc.c[AT_DEL][d];

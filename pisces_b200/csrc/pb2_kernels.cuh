@@ -31,6 +31,7 @@ struct DeviceConfig {
     int sb_model, filter_single_strand;
     float no_call_filter;
     int output_gvcf, expect_stitched, expect_collapsed, have_intervals, want_qsum;
+    int snv_from_counts;    // 1: SNV candidates = the counts (CallMNVs off); 0: SNVs are explicit candidates from the finder's state machine
     double vq_error_rate;   // MathOperations.QtoP(noise_level) (VariantQualityCalculator.cs:31)
     double sb_noise;        // Math.Pow(10, -1*noise_level/10f) (StrandBiasCalculator.cs:32)
 };

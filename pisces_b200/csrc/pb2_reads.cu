@@ -2,32 +2,9 @@
 // One thread walks one read's CIGAR exactly as RegionStateManager.AddAlleleCounts does
 // (src/lib/Pisces.Processing/RegionState/RegionStateManager.cs:118-220) and produces one entry per AddAlleleCount call; the SNV
 // candidate flags follow CandidateVariantFinder (src/lib/Pisces.Domain/Logic/CandidateVariantFinder.cs:90-203,496-553) for CallMNVs=false.
-#include "pb2_kernels.cuh"
-#include "pb2_math.cuh"
+#include "pb2_internal.hpp"
 
 namespace pb2 {
-
-struct ReadsView {
-    int32_t n_reads;
-    const int32_t* pos0;
-    const uint16_t* flag;
-    const int64_t* cigar_off;
-    const uint32_t* cigar;
-    const int64_t* seq_off;
-    const uint8_t* bases;
-    const uint8_t* quals;
-    const uint8_t* base_dirs;
-    const uint8_t* collapsed;
-};
-
-struct RegionView {
-    int32_t lo, hi;                 // staged reference positions [lo, hi] (1-based, inclusive)
-    const int32_t* index_of_pos;    // [hi-lo+1] locus index or -1 (nullptr: index = pos - lo)
-    const uint8_t* chr;             // chromosome, may be nullptr
-    int64_t chr_len;
-    int min_bq;
-    int expect_collapsed;
-};
 
 __device__ __forceinline__ bool op_ref_span(int op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }   // M D N = X  (BamCommon.cs:560-573)
 __device__ __forceinline__ bool op_read_span(int op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }  // M I S = X  (:575-588)
@@ -184,6 +161,144 @@ __global__ void reads_emit_kernel(ReadsView rv, RegionView rg, const int64_t* __
 __global__ void depth_to_i64_kernel(const unsigned int* __restrict__ depth, int64_t* __restrict__ out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = depth[i]; else if (i == n) out[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ candidate finder
+// CandidateVariantFinder.FindCandidates (CandidateVariantFinder.cs:31-83) for one read per thread: insertions (:234-260), deletions (:262-292) and —
+// with CallMNVs — the SNV/MNV state machine over 'M' operations (:90-203); Create (:334-387: support direction, well-anchored support, collapsed-read
+// type) and the open-end annotation (:496-553). Each candidate found becomes one RawCand; the host sums them per key (RegionState.AddCandidate).
+// Without CallMNVs the SNV candidates are the pileup counts themselves (flag bits of the entries), so 'M' operations emit nothing here.
+__device__ __forceinline__ void emit_raw(RawCand* out, unsigned long long* count, int64_t capacity, const RawCand& rc) {
+    const unsigned long long slot = atomicAdd(count, 1ull);
+    if ((int64_t)slot < capacity) out[slot] = rc;
+}
+
+__global__ void reads_candidates_kernel(ReadsView rv, int32_t first_read, const uint8_t* __restrict__ chr, int64_t chr_len, int min_bq, int call_mnvs, int max_mnv,
+                                        int max_gap, int expect_collapsed, RawCand* __restrict__ out, unsigned long long* __restrict__ count, int64_t capacity) {
+    const int r = first_read + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rv.n_reads) return;
+    const int64_t c0 = rv.cigar_off[r], c1 = rv.cigar_off[r + 1];
+    const int64_t s0 = rv.seq_off[r];
+    const int read_len = (int)(rv.seq_off[r + 1] - s0);
+    const int n_ops = (int)(c1 - c0);
+    if (n_ops == 0 || read_len == 0 || chr == nullptr) return;
+    const int start_pos = rv.pos0[r] + 1;
+    int ref_span = 0, max_mapped = -1;
+    {
+        int rp = start_pos;
+        for (int i = 0; i < n_ops; i++) {
+            const uint32_t c = rv.cigar[c0 + i];
+            const int op = c & 15, len = (int)(c >> 4);
+            if (op_ref_span(op)) { ref_span += len; if (op_read_span(op) && len > 0) max_mapped = rp + len - 1; rp += len; }
+        }
+    }
+    const int end_pos = rv.pos0[r] + ref_span;                         // Read.EndPosition
+    if (max_mapped == -1) max_mapped = start_pos - 1;                  // (:506-507)
+    const bool reverse = (rv.flag[r] & 0x10) != 0;
+    const int cbyte = (expect_collapsed && rv.collapsed) ? rv.collapsed[r] : 0;
+    const uint8_t* bases = rv.bases + s0;
+    const uint8_t* quals = rv.quals + s0;
+    const uint8_t* dirs = rv.base_dirs ? rv.base_dirs + s0 : nullptr;
+    auto dir_at = [&](int i) -> int { return dirs ? dirs[i] : (reverse ? DIR_R : DIR_F); };
+    int first_op = (int)(rv.cigar[c0] & 15), last_op = (int)(rv.cigar[c1 - 1] & 15);
+    if (first_op == 4 && n_ops >= 2) first_op = (int)(rv.cigar[c0 + 1] & 15);
+    if (last_op == 4 && n_ops >= 2) last_op = (int)(rv.cigar[c1 - 2] & 15);
+
+    // GetSupportDirection (:396-445); deletions in stitched reads use the per-base directions on both sides of the gap
+    auto support_dir = [&](int type, int start_idx, int length) -> int {
+        if (type == CAT_SNV) return dir_at(start_idx);
+        const int left = start_idx - 1;
+        const int right = type == CAT_DEL ? start_idx : start_idx + length;
+        const int last = read_len - 1;
+        if (right == 0) return dir_at(0);
+        if (left == last) return dir_at(last);
+        if (left == right - 1) { const int s = dir_at(left), e = dir_at(right); return s == DIR_S ? e : s; }
+        int d = DIR_F;
+        for (int i = left + 1; i < right && i < read_len; i++) { d = dir_at(i); if (d == DIR_S) return DIR_S; }
+        return d;
+    };
+    auto create = [&](int type, int position, int ref_len, int alt_len, int start_idx, int order, bool open_l, bool open_r) {
+        const int length = type == CAT_INS ? alt_len - 1 : (type == CAT_DEL ? ref_len - 1 : alt_len);
+        const int d = support_dir(type, start_idx, length);
+        const int anchor = min(position - start_pos, end_pos - position);
+        // Annotate (:496-553)
+        if (first_op == 0 && position == start_pos && (type == CAT_MNV || type == CAT_SNV)) open_l = true;
+        if (first_op == 1 && position == start_pos - 1 && type == CAT_INS) open_l = true;
+        if (first_op == 2 && position == start_pos - 1 && type == CAT_DEL) open_l = true;
+        if (last_op == 0 && position + alt_len - 1 == max_mapped && (type == CAT_MNV || type == CAT_SNV)) open_r = true;
+        if (last_op == 1 && position == max_mapped && type == CAT_INS) open_r = true;
+        if (last_op == 2 && position == max_mapped && type == CAT_DEL) open_r = true;
+        RawCand rc;
+        rc.read = r; rc.order = order; rc.position = position; rc.start_in_read = start_idx;
+        rc.ref_len = (uint16_t)ref_len; rc.alt_len = (uint16_t)alt_len;
+        rc.type = (uint8_t)type; rc.dir = (uint8_t)d;
+        rc.flags = (uint8_t)((open_l ? 1 : 0) | (open_r ? 2 : 0) | (anchor > min(kAnchorK - 1, alt_len - 1) ? 4 : 0));
+        rc.collapsed = (uint8_t)collapsed_code(cbyte, d);
+        emit_raw(out, count, capacity, rc);
+    };
+    auto is_n = [](uint8_t b) { return !(b == 'A' || b == 'C' || b == 'G' || b == 'T'); };
+
+    int read_idx = 0, ref_idx = start_pos - 1;   // startIndexInRead / startIndexInReference (0-based)
+    for (int oi = 0; oi < n_ops; oi++) {
+        const uint32_t c = rv.cigar[c0 + oi];
+        const int op = c & 15, len = (int)(c >> 4);
+        if (op == 1) {                                                  // insertion (:234-260)
+            if (!(ref_idx - 1 >= chr_len || ref_idx == 0) && (int)quals[read_idx] >= min_bq) create(CAT_INS, ref_idx, 1, 1 + len, read_idx, oi << 16, false, false);
+        } else if (op == 2) {                                           // deletion (:262-292)
+            if (!((int64_t)ref_idx + len >= chr_len) && ref_idx >= 1) {
+                const int after = read_idx < read_len ? quals[read_idx] : quals[read_idx - 1];
+                const int before = read_idx > 0 ? quals[read_idx - 1] : after;
+                if (before >= min_bq && after >= min_bq) create(CAT_DEL, ref_idx, len + 1, 1, read_idx, oi << 16, false, false);
+            }
+        } else if (op == 0 && call_mnvs) {                              // ExtractSnvsFromOperation (:90-168)
+            int vlen = 0, gap = 0;
+            bool open_left = false;
+            auto flush = [&](int i_end, bool open_right) {             // FlushVariant (:183-203); the variant ends just before operation offset i_end
+                int v = vlen;
+                if (gap >= 1) { v -= gap; open_right = false; }
+                if (v >= 1) {
+                    const int st = i_end - vlen;                        // offset of the variant's first base in the operation
+                    create(v > 1 ? CAT_MNV : CAT_SNV, ref_idx + st + 1, v, v, read_idx + st, (oi << 16) | min(st, 0xffff), open_left, open_right);
+                }
+            };
+            auto should_build = [&](bool ref_next) {                   // ShouldBuildUpMNV (:170-181)
+                if (ref_next && vlen == 0) return false;
+                if (vlen + 1 > max_mnv) return false;
+                if (gap + (ref_next ? 1 : 0) > max_gap) return false;
+                return true;
+            };
+            int i = 0;
+            for (; i < len; i++) {
+                if ((int64_t)ref_idx + i >= chr_len) break;
+                const bool good = (int)quals[read_idx + i] >= min_bq;
+                const uint8_t rb = bases[read_idx + i], fb = chr[ref_idx + i];
+                const bool at_end = i == len - 1;
+                const bool starting_at_end = at_end && vlen == 0;
+                if (is_n(rb) || is_n(fb) || !good) {
+                    flush(i, true);
+                    vlen = 0; gap = 0; open_left = true;
+                } else if (fb == rb) {
+                    if (should_build(true) && !starting_at_end) { vlen++; gap++; }
+                    else { flush(i, false); vlen = 0; gap = 0; open_left = false; }
+                } else {
+                    if (should_build(false) && !starting_at_end) { vlen++; gap = 0; }
+                    else { flush(i, false); vlen = 1; gap = 0; open_left = false; }
+                }
+            }
+            // the final flush of the operation uses operationLength even when the loop stopped at the chromosome end (:166-167)
+            flush(len, false);
+        }
+        if (op_read_span(op)) read_idx += len;
+        if (op_ref_span(op)) ref_idx += len;
+    }
+}
+
+cudaError_t launch_reads_candidates(const ReadsView& rv, int32_t first_read, const uint8_t* chr, int64_t chr_len, int min_bq, int call_mnvs, int max_mnv, int max_gap,
+                                    int expect_collapsed, RawCand* out, unsigned long long* count, int64_t capacity, cudaStream_t st) {
+    const int n = rv.n_reads - first_read;
+    if (n <= 0) return cudaSuccess;
+    reads_candidates_kernel<<<(n + 127) / 128, 128, 0, st>>>(rv, first_read, chr, chr_len, min_bq, call_mnvs, max_mnv, max_gap, expect_collapsed, out, count, capacity);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_reads_count(const ReadsView& rv, const RegionView& rg, unsigned int* depth, cudaStream_t st) {

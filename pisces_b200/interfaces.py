@@ -116,7 +116,7 @@ class Read:
 class CalledAllele:
     """View of one pb2_call_record with the reference's property names."""
 
-    def __init__(self, rec):
+    def __init__(self, rec, arena=b""):
         self._r = rec
         self.ReferencePosition = int(rec["position"])
         self.Type = AlleleCategory(int(rec["type"]))
@@ -138,9 +138,9 @@ class CalledAllele:
         f = int(rec["sb_flags"])
         self.BiasAcceptable, self.VarPresentOnBothStrands, self.CovPresentOnBothStrands = bool(f & 1), bool(f & 2), bool(f & 4)
         rl, al, ab = int(rec["ref_len"]), int(rec["alt_len"]), int(rec["allele_bytes"])
-        raw = ab.to_bytes(4, "little")
-        self.ReferenceAllele = raw[:rl].decode() if rl + al <= 4 else None
-        self.AlternateAllele = raw[rl:rl + al].decode() if rl + al <= 4 else None
+        raw = ab.to_bytes(4, "little") if rl + al <= 4 else bytes(arena[ab:ab + rl + al])
+        self.ReferenceAllele = raw[:rl].decode()
+        self.AlternateAllele = raw[rl:rl + al].decode()
 
     @property
     def Frequency(self):  # CalledAllele.cs:49-52 (float32 arithmetic)
@@ -188,6 +188,12 @@ class GpuStateManager:
             self.close()
         except Exception:
             pass
+
+    @property
+    def TotalNumCollapsed(self):
+        n = C.c_int64()
+        self._chk(self._L.pb2_totals(self._h, C.byref(n)))
+        return n.value
 
     @property
     def ExpectStitchedReads(self):
@@ -242,6 +248,33 @@ class GpuStateManager:
         p = N.PileupCsr(n_loci, int(first_position), ptr(positions), ptr(offsets), ptr(code), ptr(qual), ptr(anchor), ptr(ref_bases))
         self._keep = [offsets, code, qual, anchor, positions, ref_bases]
         self._chk((self._L.pb2_push_pileup_device if device else self._L.pb2_push_pileup)(self._h, C.byref(p)))
+
+    def AddCandidates(self, candidates, arena=None):
+        """IAlleleSource.AddCandidates (pb2_push_candidates). Either a list of dicts (type, pos, ref, alt, support[3], well_anchored[3], open_left,
+        open_right, collapsed_mut[8]) or a numpy array of pb2_candidate rows plus the allele arena they point into."""
+        if arena is None:
+            arr = np.zeros(len(candidates), dtype=N.CANDIDATE_DTYPE)
+            buf = bytearray()
+            for i, c in enumerate(candidates):
+                r = arr[i]
+                r["position"], r["type"] = c["pos"], int(c["type"])
+                r["open_flags"] = (1 if c.get("open_left") else 0) | (2 if c.get("open_right") else 0)
+                r["ref_len"], r["alt_len"], r["allele_offset"] = len(c["ref"]), len(c["alt"]), len(buf)
+                buf += c["ref"].encode() + c["alt"].encode()
+                r["support"] = tuple(c.get("support", (0, 0, 0)))
+                r["well_anchored"] = tuple(c.get("well_anchored", (0, 0, 0)))
+                r["collapsed_mut"] = tuple(c.get("collapsed_mut", (0,) * 8))
+            candidates, arena = arr, bytes(buf)
+        candidates = np.ascontiguousarray(candidates)
+        assert candidates.dtype.itemsize == 72
+        ab = np.frombuffer(arena, dtype=np.uint8) if len(arena) else np.zeros(1, dtype=np.uint8)
+        self._chk(self._L.pb2_push_candidates(self._h, candidates.ctypes.data, len(candidates), ab.ctypes.data, len(arena)))
+
+    def AlleleArena(self):
+        """Bytes that pb2_call_record.allele_bytes of the last Call points into for alleles longer than 4 bases."""
+        p, n = C.c_void_p(), C.c_int64()
+        self._chk(self._L.pb2_allele_arena(self._h, C.byref(p), C.byref(n)))
+        return C.string_at(p.value, n.value) if n.value else b""
 
     def GetAlleleCounts(self, position0, n):
         """RegionState._alleleCounts over [position0, position0+n): int32 [n][6][3][11]."""
@@ -308,6 +341,7 @@ class GpuAlleleCaller:
         if raw:
             return recs
         out = {}
+        arena = source.AlleleArena()
         for r in recs:
-            out.setdefault(int(r["position"]), []).append(CalledAllele(r))
+            out.setdefault(int(r["position"]), []).append(CalledAllele(r, arena))
         return out

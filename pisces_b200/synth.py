@@ -25,8 +25,12 @@ def _quality_table():
 
 
 def make_pileup(n_loci, mean_depth, seed=1, device="cpu", depth_dist="poisson", snv_rate=0.01, vaf=(0.01, 0.5), del_rate=0.001, stitched_frac=0.0,
-                collapsed_frac=0.0, strand_skew_frac=0.0, chunk_entries=1 << 25, flags=True):
-    """Returns dict(offsets int64[n+1], code/qual/anchor uint8[total], ref_bases uint8[n] ASCII, snv_loci, del_loci)."""
+                collapsed_frac=0.0, strand_skew_frac=0.0, chunk_entries=1 << 25, flags=True, indel_rate=0.0, min_bq=20):
+    """Returns dict(offsets int64[n+1], code/qual/anchor uint8[total], ref_bases uint8[n] ASCII, snv_loci, del_loci) and, when indel_rate > 0,
+    candidates (numpy structured array, pb2_candidate layout) + arena (bytes): 1-3 bp insertions and deletions at indel_rate of the loci
+    (0.1 %). A deletion candidate at position p puts Deletion entries on loci p+1..p+len at its VAF and takes its support from
+    the usable Deletion entries of locus p+1 (one per read carrying it, as CandidateVariantFinder would count them); an insertion has no
+    pileup entries (inserted bases are not mapped), its support is Binomial(depth, VAF) split by direction."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(int(seed))
@@ -44,6 +48,23 @@ def make_pileup(n_loci, mean_depth, seed=1, device="cpu", depth_dist="poisson", 
     locus_vaf = torch.where(is_snv, locus_vaf, torch.zeros_like(locus_vaf))
     is_del = (torch.rand(n_loci, device=dev, generator=g) < del_rate) & ~is_snv
     del_vaf = torch.where(is_del, 0.05 + 0.3 * torch.rand(n_loci, device=dev, generator=g), torch.zeros(n_loci, device=dev))
+    indel_pos = indel_len = indel_is_ins = indel_vaf = None
+    if indel_rate > 0:
+        # candidate position p = the base before the event; keep events apart (>= 8 loci) and inside the staged range
+        cand = torch.nonzero(torch.rand(n_loci, device=dev, generator=g) < indel_rate).flatten()
+        cand = cand[(cand >= 1) & (cand < n_loci - 8)]
+        if cand.numel() > 1:
+            keep = torch.ones_like(cand, dtype=torch.bool)
+            keep[1:] = (cand[1:] - cand[:-1]) >= 8
+            cand = cand[keep]
+        k = cand.numel()
+        indel_pos = cand
+        indel_len = torch.randint(1, 4, (k,), device=dev, generator=g)
+        indel_is_ins = torch.rand(k, device=dev, generator=g) < 0.5
+        indel_vaf = 0.03 + 0.4 * torch.rand(k, device=dev, generator=g)
+        for j in range(1, 4):   # Deletion entries on the deleted positions p+1..p+len
+            m = (~indel_is_ins) & (indel_len >= j)
+            del_vaf[cand[m] + j] = indel_vaf[m]
     skew = torch.rand(n_loci, device=dev, generator=g) < strand_skew_frac   # variant support 90/10 across strands (SB filter fires)
 
     code = torch.empty(total, dtype=torch.uint8, device=dev)
@@ -98,8 +119,49 @@ def make_pileup(n_loci, mean_depth, seed=1, device="cpu", depth_dist="poisson", 
         qual[e0:e1] = q.to(torch.uint8)
         anchor[e0:e1] = ab.to(torch.uint8)
     ref_bases = _ASCII_ACGT.to(dev)[ref_idx]
-    return dict(offsets=offsets, code=code, qual=qual, anchor=anchor, ref_bases=ref_bases, n_entries=total,
-                snv_loci=int(is_snv.sum()), del_loci=int(is_del.sum()))
+    out = dict(offsets=offsets, code=code, qual=qual, anchor=anchor, ref_bases=ref_bases, n_entries=total,
+               snv_loci=int(is_snv.sum()), del_loci=int(is_del.sum()))
+    if indel_pos is not None:
+        import numpy as np
+        from . import _native as N
+        k = int(indel_pos.numel())
+        cands = np.zeros(k, dtype=N.CANDIDATE_DTYPE)
+        arena = bytearray()
+        refb = ref_bases.cpu().numpy()
+        pos_h, len_h, ins_h, vaf_h = (t.cpu().numpy() for t in (indel_pos, indel_len, indel_is_ins, indel_vaf))
+        depth_h = depth[indel_pos].cpu().numpy()
+        off_h = offsets.cpu()
+        rng = np.random.default_rng(int(seed) + 7919)
+        for i in range(k):
+            p, L = int(pos_h[i]), int(len_h[i])          # locus index p  <->  reference position p + 1
+            c = cands[i]
+            c["position"] = p + 1
+            c["allele_offset"] = len(arena)
+            if ins_h[i]:
+                ins = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L).tolist())
+                ref_s, alt_s = bytes([refb[p]]), bytes([refb[p]]) + ins
+                c["type"] = 1
+                n_sup = int(rng.binomial(int(depth_h[i]), float(vaf_h[i])))
+                f = int(rng.binomial(n_sup, 0.5))
+                c["support"] = (f, n_sup - f, 0)
+                wf = int(rng.binomial(f, 0.9))
+                wr = int(rng.binomial(n_sup - f, 0.9))
+                c["well_anchored"] = (wf, wr, 0)
+            else:
+                ref_s, alt_s = bytes(refb[p:p + L + 1].tolist()), bytes([refb[p]])
+                c["type"] = 2
+                e0, e1 = int(off_h[p + 1]), int(off_h[p + 2])
+                cc, qq, aa = code[e0:e1], qual[e0:e1], anchor[e0:e1]
+                usable = ((cc & 7) == 5) & (qq >= min_bq)
+                d = (cc >> 3) & 3
+                sup = [int((usable & (d == j)).sum()) for j in range(3)]
+                wa = [int((usable & (d == j) & ((aa & 15) == 5)).sum()) for j in range(3)]
+                c["support"], c["well_anchored"] = tuple(sup), tuple(wa)
+            c["ref_len"], c["alt_len"] = len(ref_s), len(alt_s)
+            arena += ref_s + alt_s
+        out["candidates"], out["arena"] = cands, bytes(arena)
+        out["indel_loci"] = k
+    return out
 
 
 def algorithmic_bytes(n_loci, n_entries, n_records, third_byte=True):

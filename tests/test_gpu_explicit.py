@@ -1,0 +1,219 @@
+"""Parity of the explicit-candidate path (insertions, deletions, MNVs: pb2_push_candidates / the device candidate finder, spanning coverage,
+collapser, MNV reallocator) against the CPU oracle and the reference's own CoverageCalculator vectors. Needs a B200: -m gpu."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from tests import util_reads as U
+from tests.util_counts import COVERAGE_VECTORS, pileup_from_counts
+
+pytestmark = pytest.mark.gpu
+
+
+def _pb():
+    import pisces_b200 as pb
+    return pb
+
+
+def compare_records(orecs, precs, arena, check_qsum=False):
+    assert len(orecs) == len(precs), (len(orecs), len(precs), [(o.pos, o.ref, o.alt) for o in orecs][:20],
+                                      [(int(p["position"]), int(p["type"])) for p in precs][:20])
+    for o, p in zip(orecs, precs):
+        ctx = f"pos {o.pos} {o.ref}>{o.alt}"
+        assert o.pos == int(p["position"]) and o.type == int(p["type"]), ctx
+        rl, al, ab = int(p["ref_len"]), int(p["alt_len"]), int(p["allele_bytes"])
+        raw = ab.to_bytes(4, "little") if rl + al <= 4 else bytes(arena[ab:ab + rl + al])
+        assert raw[:rl].decode() == o.ref and raw[rl:rl + al].decode() == o.alt, ctx
+        assert o.total_coverage == int(p["total_coverage"]), ctx
+        assert list(o.cov) == list(p["coverage_by_direction"]), ctx
+        assert list(o.support) == list(p["support_by_direction"]), ctx
+        assert o.allele_support == int(p["allele_support"]) and o.ref_support == int(p["reference_support"]), ctx
+        assert o.num_no_calls == int(p["num_no_calls"]), ctx
+        assert o.vq == int(p["variant_qscore"]) and o.gq == int(p["genotype_qscore"]), ctx
+        assert o.genotype == int(p["genotype"]), ctx
+        assert o.filter_mask == int(p["filters"]), (ctx, o.filter_mask, int(p["filters"]))
+        assert o.noise_level == int(p["noise_level"]), ctx
+        assert o.fraction_no_calls == float(p["fraction_no_calls"]), ctx
+        assert (bool(o.bias_acceptable), bool(o.var_both_strands), bool(o.cov_both_strands)) == \
+            (bool(p["sb_flags"] & 1), bool(p["sb_flags"] & 2), bool(p["sb_flags"] & 4)), ctx
+        for a, b in ((o.bias_score, float(p["bias_score"])), (o.gatk_bias_score, float(p["gatk_bias_score"]))):
+            if math.isinf(a) or math.isnan(a):
+                assert (math.isinf(b) and (a > 0) == (b > 0)) or (math.isnan(a) and math.isnan(b)), ctx
+            else:
+                assert b == pytest.approx(a, rel=1e-6, abs=1e-9), ctx
+        if check_qsum:
+            assert float(p["sum_base_quality"]) == pytest.approx(o.sum_base_quality, rel=1e-9), ctx
+
+
+@pytest.mark.parametrize("name", sorted(COVERAGE_VECTORS))
+def test_reference_coverage_vectors_through_kernels(name):
+    """CoverageCalculatorTests.cs (ComputeCoverage_Insertions / _Spanning_HappyPath): the staged counts become pileup entries, the allele an
+    explicit candidate; the record's coverage must be the reference's expected values."""
+    pb = _pb()
+    v = COVERAGE_VECTORS[name]
+    off, code, qual, anch = pileup_from_counts(v["counts"], v["n_loci"])
+    sm = pb.GpuStateManager(pb.make_config(min_variant_qscore=0, min_frequency=1e-6, min_coverage=0, collapse=0, output_gvcf=0, expect_stitched=v.get("stitched", 0)),
+                            "chr1", "A" * 64)
+    sm.AddPileup(off, code, qual, anch, first_position=1)
+    sm.AddCandidates([dict(type=v["type"], pos=1, ref=v["ref"], alt=v["alt"], support=v["support"], well_anchored=v["well_anchored"])])
+    calls = pb.GpuAlleleCaller().Call(sm)
+    sm.close()
+    a = [c for c in calls[1] if int(c.Type) == v["type"]][0]
+    assert a.EstimatedCoverageByDirection == list(v["expected_cov"]) and a.TotalCoverage == sum(v["expected_cov"])
+    assert a.ReferenceSupport == max(0, a.TotalCoverage - a.AlleleSupport)
+    assert (a.ReferenceAllele, a.AlternateAllele) == (v["ref"], v["alt"])
+
+
+def _pileup_indels_both(d, gvcf, **kw):
+    pb = _pb()
+    ref = bytes(d["ref_bases"].numpy()).decode()
+    off, code, qual, anch = (d[k].numpy() for k in ("offsets", "code", "qual", "anchor"))
+    arena = d["arena"]
+    oc = ob.Caller(ob.default_config(output_gvcf=gvcf, **kw), "chr1", ref)
+    for c in d["candidates"]:
+        o = int(c["allele_offset"])
+        r, a = arena[o:o + int(c["ref_len"])].decode(), arena[o + int(c["ref_len"]):o + int(c["ref_len"]) + int(c["alt_len"])].decode()
+        oc.add_candidate(int(c["type"]), int(c["position"]), r, a, [int(x) for x in c["support"]], [int(x) for x in c["well_anchored"]],
+                         bool(c["open_flags"] & 1), bool(c["open_flags"] & 2))
+    oc.add_pileup(off, code, qual, anch, 1)
+    oc.finish()
+    pkw = dict(kw)
+    if pkw.get("noise_model") == 1:
+        pkw["want_sum_base_quality"] = 1
+    sm = pb.GpuStateManager(pb.make_config(output_gvcf=gvcf, **pkw), "chr1", ref)
+    sm.AddPileup(off, code, qual, anch, first_position=1)
+    sm.AddCandidates(d["candidates"], arena)
+    # the resident (bench) path must produce the same number of variant records, on the first (plan-building) and on a replayed call
+    n_res = sm.call_resident()
+    assert sm.call_resident() == n_res
+    precs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    parena = sm.AlleleArena()
+    sm.close()
+    return oc.records(), precs, parena, n_res
+
+
+@pytest.mark.parametrize("gvcf", [0, 1])
+@pytest.mark.parametrize("depth,n_loci", [(60, 4000), (500, 3000)])
+def test_locus_major_indels_match_oracle(depth, n_loci, gvcf):
+    """BASELINE configs[1] shape (SNV + indel) at test size: synthetic insertions / deletions as explicit candidates next to the SNV / reference
+    stream, against the oracle fed the same entries and candidates."""
+    from pisces_b200 import synth
+    d = synth.make_pileup(n_loci, depth, seed=depth + gvcf, snv_rate=0.03, indel_rate=0.02)
+    orecs, precs, arena, n_res = _pileup_indels_both(d, gvcf)
+    n_indel = sum(1 for o in orecs if o.type in (ob.INSERTION, ob.DELETION))
+    assert n_indel > 20
+    compare_records(orecs, precs, arena)
+    assert n_res == sum(1 for o in orecs if o.type != ob.REFERENCE)
+
+
+def test_locus_major_indels_window_noise_and_long_alleles():
+    from pisces_b200 import synth
+    d = synth.make_pileup(2000, 200, seed=9, snv_rate=0.02, indel_rate=0.03)
+    orecs, precs, arena, _ = _pileup_indels_both(d, 1, noise_model=1)
+    assert any(o.ref_len + o.alt_len > 4 for o in orecs)
+    compare_records(orecs, precs, arena, check_qsum=True)
+
+
+def test_indel_repeat_and_rmxn_filters():
+    """A 1-base deletion inside a homopolymer run: IndelRepeatLength (AlleleProcessor.cs:80-213) and RMxN (RMxNCalculator.cs) fire on both sides."""
+    pb = _pb()
+    ref = "ACGTACGTTG" + "A" * 12 + "CGTACGTACGTTGCATGCAA"
+    n = len(ref)
+    counts = np.zeros((n, 6, 3, 11), dtype=np.int32)
+    for i, b in enumerate(ref):
+        a = {"A": 0, "G": 1, "C": 2, "T": 3}[b]
+        counts[i, a, 0, 5] = 150
+        counts[i, a, 1, 5] = 150
+    counts[10, 0, 0, 5] -= 20
+    counts[10, 5, 0, 5] += 20      # deletion of the first A of the run: position 10 (the G) is the anchor base
+    off, code, qual, anch = pileup_from_counts(counts, n)
+    cand = dict(type=2, pos=10, ref="GA", alt="G", support=(20, 0, 0), well_anchored=(20, 0, 0))
+    kw = dict(indel_repeat_filter=8, output_gvcf=0, collapse=0)
+    oc = ob.Caller(ob.default_config(**kw), "chr1", ref)
+    oc.add_candidate(cand["type"], cand["pos"], cand["ref"], cand["alt"], cand["support"], cand["well_anchored"])
+    oc.add_pileup(off, code, qual, anch, 1)
+    oc.finish()
+    sm = pb.GpuStateManager(pb.make_config(**kw), "chr1", ref)
+    sm.AddPileup(off, code, qual, anch, first_position=1)
+    sm.AddCandidates([cand])
+    precs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    arena = sm.AlleleArena()
+    sm.close()
+    orecs = oc.records()
+    assert len(orecs) == 1 and orecs[0].filter_mask & (1 << 7) and orecs[0].filter_mask & (1 << 9)
+    compare_records(orecs, precs, arena)
+
+
+def _reads_both(reads, ref, o_kw, p_kw, intervals=None, flush_every=None):
+    pb = _pb()
+    oc = ob.Caller(ob.default_config(**o_kw), "chr1", ref, intervals=intervals)
+    for rd in reads:
+        oc.add_read(U.to_oracle(rd))
+    oc.finish()
+    sm = pb.GpuStateManager(pb.make_config(**p_kw), "chr1", ref, intervals=intervals)
+    caller = pb.GpuAlleleCaller()
+    precs, arenas = [], []
+    if flush_every:
+        for i in range(0, len(reads), flush_every):
+            chunk = reads[i:i + flush_every]
+            sm.AddAlleleCounts([U.to_product(rd) for rd in chunk])
+            r = caller.Call(sm, upToPosition=chunk[-1]["pos"] - 1, raw=True)
+            precs.append((r, sm.AlleleArena()))
+    else:
+        sm.AddAlleleCounts([U.to_product(rd) for rd in reads])
+    r = caller.Call(sm, raw=True)
+    precs.append((r, sm.AlleleArena()))
+    total_collapsed = sm.TotalNumCollapsed
+    sm.close()
+    return oc, precs, total_collapsed
+
+
+def _compare_chunks(orecs, chunks):
+    i = 0
+    for recs, arena in chunks:
+        compare_records(orecs[i:i + len(recs)], recs, arena)
+        i += len(recs)
+    assert i == len(orecs)
+
+
+@pytest.mark.parametrize("collapse", [0, 1])
+@pytest.mark.parametrize("seed", [41, 42])
+def test_reads_with_indels_match_oracle(seed, collapse):
+    """Reads with insertions, deletions and soft clips: candidates are found on the device (CandidateVariantFinder), merged per position,
+    collapsed (open-ended indels at read ends) and scored with spanning coverage."""
+    rng = np.random.default_rng(seed)
+    ref = U.random_reference(rng, 2600)
+    hot = {int(p): ("ACGT"[int(rng.integers(0, 4))], float(rng.uniform(0.05, 0.5))) for p in rng.integers(60, 2400, 30)}
+    reads = U.make_reads(rng, ref, 6000, read_len=60, hotspots=hot, del_rate=0.08, ins_rate=0.08, clip_rate=0.1, indel_sites=40)
+    kw = dict(output_gvcf=1, collapse=collapse)
+    oc, chunks, ncoll = _reads_both(reads, ref, dict(kw, min_vq=10), dict(kw, min_variant_qscore=10))
+    orecs = oc.records()
+    assert sum(1 for o in orecs if o.type in (ob.INSERTION, ob.DELETION)) > 10
+    _compare_chunks(orecs, chunks)
+    # TotalNumCollapsed of the oracle also counts open-ended SNV merges, which the count-based SNV path resolves without materialising candidates
+    assert (ncoll > 0) == bool(collapse) and ncoll <= oc.L.po_caller_total_collapsed(oc.h)
+
+
+@pytest.mark.parametrize("seed", [51, 52])
+def test_reads_with_mnvs_match_oracle(seed):
+    """CallMNVs: the SNV/MNV state machine of the finder, collapsing, failed-MNV reallocation (incl. spill into the next block) and gapped-MNV
+    reference take-away, streamed block by block like SmallVariantCaller.Execute."""
+    rng = np.random.default_rng(seed)
+    ref = U.random_reference(rng, 3300)
+    hot = {}
+    for p in rng.integers(60, 3100, 40):
+        p = int(p)
+        f = float(rng.uniform(0.03, 0.5))
+        for k in range(int(rng.integers(1, 4))):
+            hot[p + k * int(rng.integers(1, 3))] = ("ACGT"[int(rng.integers(0, 4))], f)
+    for p in (998, 999, 1000, 1001, 1999, 2001):     # MNVs across the 1000-bp block boundaries
+        hot[p] = ("ACGT"[int(rng.integers(0, 4))], 0.3)
+    reads = U.make_reads(rng, ref, 9000, read_len=60, hotspots=hot, del_rate=0.03, ins_rate=0.03, clip_rate=0.1, linked_hotspots=True)
+    kw = dict(output_gvcf=1, collapse=1, call_mnvs=1, max_size_mnv=3, max_gap_mnv=1)
+    oc, chunks, ncoll = _reads_both(reads, ref, dict(kw, min_vq=10), dict(kw, min_variant_qscore=10), flush_every=700)
+    orecs = oc.records()
+    assert sum(1 for o in orecs if o.type == ob.MNV) > 5
+    _compare_chunks(orecs, chunks)
+    assert ncoll == oc.L.po_caller_total_collapsed(oc.h)

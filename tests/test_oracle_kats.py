@@ -226,3 +226,20 @@ def test_collapsed_counts():
     s.add_read(SimpleRead(11, "ACGT", "4M", 30, xv=3, xw=0, xr="FR"), "counts")
     s.add_read(SimpleRead(11, "ACGT", "4M", 30, xv=3, xr="RR"), "counts")
     assert [s.collapsed_count(12, t) for t in range(8)] == [1, 0, 0, 1, 0, 1, 0, 0]
+
+
+@pytest.mark.parametrize("name", sorted(__import__("tests.util_counts", fromlist=["x"]).COVERAGE_VECTORS))
+def test_coverage_calculator_insertion_vectors(name):
+    # CoverageCalculatorTests.cs:268-398 (ComputeCoverage_Insertions), CoverageCalculator(considerAnchorInformation: true)
+    from tests.util_counts import COVERAGE_VECTORS
+    v = COVERAGE_VECTORS[name]
+    c = ob.Caller(ob.default_config(), "chr1", "A" * 64)
+    cnt = v["counts"]
+    for i in range(cnt.shape[0]):
+        for a in range(6):
+            for d in range(3):
+                for an in range(11):
+                    if cnt[i, a, d, an]:
+                        c.set_count(i + 1, a, d, an, int(cnt[i, a, d, an]))
+    r = c.process_allele(v["type"], 1, v["ref"], v["alt"], v["support"], v["well_anchored"], coverage_only=True)
+    assert tuple(r.cov) == v["expected_cov"] and r.total_coverage == sum(v["expected_cov"])

@@ -14,23 +14,58 @@ def random_reference(rng, n, n_rate=0.0):
 
 
 def make_reads(rng, ref, n_reads, read_len=60, start=1, span=None, snv_rate=0.01, lowq_rate=0.08, n_base_rate=0.005, del_rate=0.05, ins_rate=0.05,
-               clip_rate=0.15, hotspots=None, stitched=False, collapsed=False, sorted_by_pos=True):
+               clip_rate=0.15, hotspots=None, stitched=False, collapsed=False, sorted_by_pos=True, indel_sites=0, linked_hotspots=False):
     """Returns a list of dicts: pos (1-based), seq, cigar (string), quals, flag, dirs (or None), coll (or None), xd/xr/xv/xw for the oracle.
 
     hotspots: {position: (alt_base, fraction)} real variants so that some calls pass the frequency / q-score bars."""
     span = span or (len(ref) - read_len - 12)
     reads = []
+    # recurrent indels: site position (base before the event) -> (op, length, inserted bases, fraction of covering reads)
+    sites = {}
+    for p in rng.integers(start + 10, start + span, indel_sites) if indel_sites else []:
+        ln = int(rng.integers(1, 5))
+        sites[int(p)] = ("I" if rng.random() < 0.5 else "D", ln, "".join(BASES[int(x)] for x in rng.integers(0, 4, ln)), float(rng.uniform(0.05, 0.5)))
     for _ in range(n_reads):
         pos = int(rng.integers(start, start + span))
         ops = []
+        ins_bases = None
         r = rng.random()
+        u_link = rng.random()
         body = read_len
         lead_clip = int(rng.integers(1, 6)) if rng.random() < clip_rate else 0
         tail_clip = int(rng.integers(1, 6)) if rng.random() < clip_rate else 0
         body -= lead_clip + tail_clip
         if lead_clip:
             ops.append(("S", lead_clip))
-        if r < del_rate and body > 12:
+        site = None
+        for sp in range(pos, pos + body - 5):      # first recurrent site this read covers (may sit right at the read ends: open-ended candidates)
+            if sp in sites and rng.random() < sites[sp][3]:
+                site = sp
+                break
+        edge = rng.random() if site is not None else 1.0
+        if site is not None and sites[site][0] == "I" and edge < 0.2 and not lead_clip and not tail_clip:
+            # the read starts or ends inside the insertion: an open-ended insertion candidate carrying a suffix / prefix of the inserted bases
+            kind, ln, ib, _ = sites[site]
+            k = int(rng.integers(1, ln + 1))
+            if edge < 0.1:
+                pos = site + 1
+                ops += [("I", k), ("M", body - k)]
+                ins_bases = ib[ln - k:]
+            else:
+                pos = max(1, site - (body - k) + 1)
+                ops += [("M", site - pos + 1), ("I", k)]
+                ins_bases = ib[:k]
+                body = site - pos + 1 + k
+        elif site is not None:
+            kind, ln, ib, _ = sites[site]
+            a = site - pos + 1
+            if kind == "D":
+                ops += [("M", a), ("D", ln), ("M", body - a)]
+            else:
+                ln = min(ln, body - a)
+                ops += [("M", a), ("I", ln)] + ([("M", body - a - ln)] if body - a - ln > 0 else [])
+                ins_bases = ib[:ln]
+        elif r < del_rate and body > 12:
             a = int(rng.integers(3, body - 6))
             ops += [("M", a), ("D", int(rng.integers(1, 4))), ("M", body - a)]
         elif r < del_rate + ins_rate and body > 12:
@@ -47,7 +82,7 @@ def make_reads(rng, ref, n_reads, read_len=60, start=1, span=None, snv_rate=0.01
                 for k in range(ln):
                     b = ref[rp + k] if rp + k < len(ref) else "A"
                     p1 = rp + k + 1
-                    if hotspots and p1 in hotspots and rng.random() < hotspots[p1][1]:
+                    if hotspots and p1 in hotspots and (u_link if linked_hotspots else rng.random()) < hotspots[p1][1]:
                         b = hotspots[p1][0]
                     elif rng.random() < snv_rate:
                         b = BASES[int(rng.integers(0, 4))]
@@ -57,9 +92,11 @@ def make_reads(rng, ref, n_reads, read_len=60, start=1, span=None, snv_rate=0.01
                 rp += ln
             elif op == "D":
                 rp += ln
+            elif op == "I" and ins_bases is not None:
+                seq += list(ins_bases)
             else:  # I, S
                 seq += [BASES[int(rng.integers(0, 4))] for _ in range(ln)]
-        quals = np.where(rng.random(read_len) < lowq_rate, rng.integers(2, 20, read_len), rng.integers(20, 41, read_len)).astype(int).tolist()
+        quals = np.where(rng.random(len(seq)) < lowq_rate, rng.integers(2, 20, len(seq)), rng.integers(20, 41, len(seq))).astype(int).tolist()
         reverse = bool(rng.random() < 0.5)
         flag = (0x10 if reverse else 0) | 0x1 | 0x2 | (0x40 if rng.random() < 0.5 else 0x80)
         rd = dict(pos=pos, seq="".join(seq), cigar="".join(f"{ln}{op}" for op, ln in ops), quals=quals, flag=flag, dirs=None, coll=None,
