@@ -217,3 +217,58 @@ def test_reads_with_mnvs_match_oracle(seed):
     assert sum(1 for o in orecs if o.type == ob.MNV) > 5
     _compare_chunks(orecs, chunks)
     assert ncoll == oc.L.po_caller_total_collapsed(oc.h)
+
+
+class _RecordView:
+    """A pb2_call_record shaped like the oracle's record, for the VCF text restatement (oracle/vcf_text.py, test infrastructure)."""
+    _FILTER_ORDER = [4, 3, 12, 0, 2, 7, 9, 5, 6, 10]   # the order AlleleProcessor.ApplyFilters / the genotyper add them (AlleleProcessor.cs:25-71)
+
+    def __init__(self, p, arena):
+        rl, al, ab = int(p["ref_len"]), int(p["alt_len"]), int(p["allele_bytes"])
+        raw = ab.to_bytes(4, "little") if rl + al <= 4 else bytes(arena[ab:ab + rl + al])
+        self.ref, self.alt = raw[:rl].decode(), raw[rl:rl + al].decode()
+        self.pos, self.type, self.genotype = int(p["position"]), int(p["type"]), int(p["genotype"])
+        self.gq, self.vq = int(p["genotype_qscore"]), int(p["variant_qscore"])
+        self.filters = [f for f in self._FILTER_ORDER if int(p["filters"]) >> f & 1]
+        self.n_filters = len(self.filters)
+        self.total_coverage, self.allele_support, self.ref_support = int(p["total_coverage"]), int(p["allele_support"]), int(p["reference_support"])
+        self.frequency = np.float32(0) if self.total_coverage == 0 else min(np.float32(self.allele_support) / np.float32(self.total_coverage), np.float32(1))
+        self.noise_level, self.gatk_bias_score, self.forced = int(p["noise_level"]), float(p["gatk_bias_score"]), 0
+
+
+def test_phix_full_text_golden_through_cuda_path():
+    """The reference's own full-text golden (PhiX_S3.bam -> PhiX_S3.noisy.vcf, ForcedGTFxnlTest.cs:11-112) reproduced line by line from the records
+    the CUDA path emits: MNVs up to 10 with gaps of 5, collapsing, MNV reallocation, gapped-MNV reference take-away, q-scores, strand bias."""
+    import gzip
+    import json
+    import os
+    from oracle.vcf_text import VcfText
+    pb = _pb()
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    d = json.load(gzip.open(os.path.join(G, "phix_s3_reads.json.gz"), "rt"))
+    genome = open(os.path.join(G, "phix_genome.txt")).read().strip()
+    okw = dict(min_coverage=2, min_base_call_quality=10, min_vq=1, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1, max_size_mnv=10,
+               max_gap_mnv=5, no_call_filter=1.0)
+    pkw = dict(min_coverage=2, min_base_call_quality=10, min_variant_qscore=1, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1, max_size_mnv=10,
+               max_gap_mnv=5, no_call_filter=1.0)
+    # AlignmentSource.ShouldSkipRead (AlignmentsSource.cs:84-92): mapped, primary, not duplicate, mapq >= 1, has a CIGAR — host-side filter
+    reads = [r for r in d["reads"] if not (r["flag"] & 0x4) and not (r["flag"] & 0x100) and not (r["flag"] & 0x400) and r["mapq"] >= 1 and r["cigar"]]
+    sm = pb.GpuStateManager(pb.make_config(**pkw), "phix", genome)
+    caller = pb.GpuAlleleCaller()
+    views = []
+    for i in range(0, len(reads), 50):      # streamed like SmallVariantCaller.Execute: push a few reads, call up to the last read's position - 1
+        chunk = reads[i:i + 50]
+        sm.AddAlleleCounts([pb.Read(r["pos0"] + 1, r["seq"], r["cigar"], r["qual"], flag=r["flag"]) for r in chunk])
+        recs = caller.Call(sm, upToPosition=chunk[-1]["pos0"], raw=True)
+        arena = sm.AlleleArena()
+        views += [_RecordView(p, arena) for p in recs]
+    recs = caller.Call(sm, raw=True)
+    arena = sm.AlleleArena()
+    views += [_RecordView(p, arena) for p in recs]
+    sm.close()
+    vt = VcfText(ob.default_config(**okw), ob.FILTERS, ob.GENOTYPES)
+    got = [vt.line("phix", v) for v in views]
+    exp = [l.rstrip("\n") for l in open(os.path.join(G, "phix_s3_noisy.records.vcf"))]
+    assert len(got) == len(exp)
+    for a, b in zip(got, exp):
+        assert a == b
