@@ -4,8 +4,8 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--loci L] [--depth D] [--gvcf 0|1]
 
 A step = one pass of the hot path (pileup count + score + record compaction) over one batch of `loci` synthetic pileup columns per GPU.
-Default workload = BASELINE.json configs[1]: 1 M loci x depth ~Poisson(500), SNV (1 % of loci) + deletion entries, flat Poisson noise model
-NL 20, gVCF off, one B200. N>1 (torchrun): loci are sharded by interval across ranks (weak scaling: `loci` per GPU), no data-path
+Default workload = BASELINE.json configs[1]: 1 M loci x depth ~Poisson(500), SNV (1 % of loci) + 1-3 bp insertions / deletions (0.1 % of loci,
+explicit candidates with spanning coverage), flat Poisson noise model NL 20, gVCF off, one B200. N>1 (torchrun): loci are sharded by interval across ranks (weak scaling: `loci` per GPU), no data-path
 collective; each step ends with the single all-gather of the per-rank call records (NCCL).
 """
 import argparse
@@ -34,6 +34,9 @@ def parse():
     ap.add_argument("--depth-dist", default="poisson", choices=["poisson", "fixed"])
     ap.add_argument("--gvcf", type=int, default=0)
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--indel-rate", type=float, default=0.001)
+    ap.add_argument("--tune-ctas", type=int, default=0, help="hot-kernel CTAs per SM (tuning experiments)")
+    ap.add_argument("--tune-prefetch", type=int, default=0, help="hot-kernel L2 prefetch distance (tuning experiments)")
     ap.add_argument("--cpu-sample-loci", type=int, default=200_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -73,7 +76,7 @@ class ClockSampler(threading.Thread):
 
 
 def workload_name(a):
-    return (f"synthetic {a.loci} loci x depth {'~Poisson' if a.depth_dist == 'poisson' else '='}({a.depth}) per GPU, SNV 1% + deletion entries, "
+    return (f"synthetic {a.loci} loci x depth {'~Poisson' if a.depth_dist == 'poisson' else '='}({a.depth}) per GPU, SNV 1% + indel {100 * a.indel_rate:g}%, "
             f"Poisson noise model NL20, gvcf={a.gvcf} (BASELINE.json configs[1] shape)")
 
 
@@ -92,11 +95,22 @@ def run_oracle_slices(a, d, n_threads, loci_per_thread):
         l0, l1 = t * loci_per_thread, (t + 1) * loci_per_thread
         e0, e1 = int(off[l0]), int(off[l1])
         ref = bytes(d["ref_bases"][l0:l1].cpu().numpy()).decode()
+        cands = []
+        if d.get("candidates") is not None:
+            arena = d["arena"]
+            for c in d["candidates"]:
+                p = int(c["position"])
+                if l0 + 1 <= p and p + int(c["ref_len"]) + 1 <= l1:
+                    o, rl, al = int(c["allele_offset"]), int(c["ref_len"]), int(c["alt_len"])
+                    cands.append((int(c["type"]), p - l0, arena[o:o + rl].decode(), arena[o + rl:o + rl + al].decode(), [int(x) for x in c["support"]],
+                                  [int(x) for x in c["well_anchored"]]))
         slices.append((ob.Caller(oracle_config(a), "chr1", ref), (off[l0:l1 + 1] - e0).astype(np.int64), d["code"][e0:e1].cpu().numpy(),
-                       d["qual"][e0:e1].cpu().numpy(), d["anchor"][e0:e1].cpu().numpy()))
+                       d["qual"][e0:e1].cpu().numpy(), d["anchor"][e0:e1].cpu().numpy(), cands))
 
     def work(s):
-        c, o, co, q, an = s
+        c, o, co, q, an, cands = s
+        for t, p, r, al, sup, wa in cands:
+            c.add_candidate(t, p, r, al, sup, wa)
         c.add_pileup(o, co, q, an, 1, call_every=1)
         c.finish()
     ths = [threading.Thread(target=work, args=(s,)) for s in slices]
@@ -119,7 +133,7 @@ def main_reference(a):
     cores = os.cpu_count() or 1
     per_thread = max(1000, min(20_000, a.loci // cores))
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    d = synth.make_pileup(cores * per_thread, a.depth, seed=a.seed, device=dev, depth_dist=a.depth_dist)
+    d = synth.make_pileup(cores * per_thread, a.depth, seed=a.seed, device=dev, depth_dist=a.depth_dist, indel_rate=a.indel_rate)
     d = {k: (v.cpu() if hasattr(v, "cpu") else v) for k, v in d.items()}
     times = []
     for i in range(a.warmup + a.steps):
@@ -154,12 +168,16 @@ def main_ours(a):
     dev = f"cuda:{local}"
 
     # ---- synthetic shard for this rank, resident in HBM (interval shard `rank` of `world`)
-    d = synth.make_pileup(a.loci, a.depth, seed=a.seed + 1000 * rank, device=dev, depth_dist=a.depth_dist)
+    d = synth.make_pileup(a.loci, a.depth, seed=a.seed + 1000 * rank, device=dev, depth_dist=a.depth_dist, indel_rate=a.indel_rate)
     n_entries = d["n_entries"]
     ref = bytes(d["ref_bases"].cpu().numpy())
     cfg = pb.make_config(device=local, output_gvcf=a.gvcf)
+    cfg.reserved[0] = a.tune_ctas
+    cfg.reserved[1] = a.tune_prefetch
     sm = pb.GpuStateManager(cfg, "chr1", ref)
     sm.AddPileup(d["offsets"], d["code"], d["qual"], d["anchor"], first_position=1, ref_bases=d["ref_bases"], device=True)
+    if d.get("candidates") is not None:
+        sm.AddCandidates(d["candidates"], d["arena"])
     torch.cuda.synchronize()
 
     import ctypes as C
@@ -249,6 +267,8 @@ def main_ours(a):
 
         def e2e_step():
             sm2.AddPileup(h["offsets"].numpy(), h["code"].numpy(), h["qual"].numpy(), h["anchor"].numpy(), first_position=1, ref_bases=h["ref_bases"].numpy())
+            if d.get("candidates") is not None:
+                sm2.AddCandidates(d["candidates"], d["arena"])
             recs = caller.Call(sm2, raw=True)
             sm2.DoneProcessing()
             return len(recs)

@@ -74,6 +74,9 @@ static void derive_config(pb2_handle* h) {
     d.output_gvcf = c.output_gvcf; d.expect_stitched = c.expect_stitched; d.expect_collapsed = c.expect_collapsed;
     d.have_intervals = h->have_intervals ? 1 : 0;
     d.want_qsum = c.want_sum_base_quality;
+    d.one = 1;
+    d.tune_prefetch = c.reserved[1];
+    d.tune_ctas_per_sm = c.reserved[0] == 3 ? 3 : 4;   // tuning knob (bench.py --tune-ctas)
     d.snv_from_counts = c.call_mnvs ? 0 : 1;   // CallMNVs: SNV candidates come from the finder's state machine (explicit), not from the counts
     d.vq_error_rate = std::pow(10.0, -1 * (double)d.noise_level / 10.0);                      // QtoP: double division (MathOperations.cs:7-10)
     d.sb_noise = std::pow(10.0, (double)((float)(-1 * d.noise_level) / 10.0f));               // float exponent (StrandBiasCalculator.cs:32)
@@ -105,6 +108,22 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (int i = 0; i < 2; i++) {
+        if ((e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&h->ev_scattered[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = h->device;
+        if ((e = cudaMemPoolCreate(&h->pool, &props)) != cudaSuccess) return bail("cudaMemPoolCreate", e);
+        uint64_t keep = UINT64_MAX;
+        if ((e = cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return bail("cudaMemPoolSetAttribute", e);
+    }
     if ((e = cudaMalloc(&h->d_tile_counter, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     {
         h->q_table_max = std::min(std::max(cfg->max_variant_qscore, 0), 1023);
@@ -117,19 +136,16 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
     return PB2_OK;
 }
 
-// Staging buffers. (A per-handle cache of freed blocks was tried to avoid cudaMalloc/cudaFree of GB-sized buffers every push; on the B200 box it
-// produced 300 ms stalls in the driver on some steps, while plain cudaMalloc/cudaFree cost a stable ~3 ms per step — so: plain calls.)
-static cudaError_t pool_alloc(pb2_handle*, void** p, size_t bytes) { return cudaMalloc(p, std::max<size_t>(bytes, 256)); }
-static void pool_free(pb2_handle*, void* p, size_t) { if (p) cudaFree(p); }
-static void pool_release(pb2_handle*) {}
+// Device memory of a handle comes from its own stream-ordered pool (cudaMallocFromPoolAsync on the handle's stream) that never returns memory to
+// the driver while the handle lives: after the first push every staging buffer is a pool hit, so a push costs no cudaMalloc / cudaFree.
+static cudaError_t pool_alloc(pb2_handle* h, void** p, size_t bytes) { return cudaMallocFromPoolAsync(p, std::max<size_t>(bytes, 256), h->pool, h->stream); }
+static void pool_free(pb2_handle* h, void* p, size_t = 0) { if (p) cudaFreeAsync(p, h->stream); }
+template <class T>
+static cudaError_t pool_alloc_t(pb2_handle* h, T** p, size_t count) { return pool_alloc(h, reinterpret_cast<void**>(p), count * sizeof(T)); }
 
 static void free_segment(pb2_handle* h, Segment& s) {
-    // the big staging buffers go back to the handle's cache, the small ones to the driver
-    pool_free(h, s.code, s.alloc_plane); pool_free(h, s.qual, s.alloc_plane); pool_free(h, s.anch, s.alloc_plane);
-    pool_free(h, s.ref_records, s.alloc_ref); pool_free(h, s.var_records, s.alloc_var); pool_free(h, s.pending, s.alloc_pending);
-    s.code = s.qual = s.anch = nullptr; s.ref_records = nullptr; s.var_records = nullptr; s.pending = nullptr;
-    void* ptrs[] = {s.depth, s.pad, s.tile_base, s.ref_base, s.positions, s.ref_valid, s.exc_entries, s.counters};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    void* ptrs[] = {s.code, s.anch, s.ref_records, s.var_records, s.pending, s.depth, s.pad, s.tile_base, s.ref_base, s.positions, s.ref_valid, s.exc_entries, s.counters};
+    for (void* p : ptrs) pool_free(h, p);
     s = Segment();
 }
 
@@ -150,13 +166,16 @@ extern "C" int pb2_reset(pb2_handle* h) {
 extern "C" void pb2_destroy(pb2_handle* h) {
     if (!h) return;
     pb2_reset(h);
-    pool_release(h);
     if (h->d_chr) cudaFree(h->d_chr);
     if (h->d_tile_counter) cudaFree(h->d_tile_counter);
     if (h->d_q_to_p) cudaFree(h->d_q_to_p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_scattered[i]) cudaEventDestroy(h->ev_scattered[i]); }
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->pool) cudaMemPoolDestroy(h->pool);
     delete h;
 }
 
@@ -201,39 +220,31 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     s.first_position = p->first_position;
     s.has_positions = p->positions != nullptr;
 
-    // CSR on the device
+    // CSR offsets on the device (the entry planes follow in chunks below)
     const int64_t* d_off = nullptr;
-    const uint8_t *d_code = nullptr, *d_qual = nullptr, *d_anch = nullptr;
     int64_t* tmp_off = nullptr;
-    uint8_t *tmp_code = nullptr, *tmp_qual = nullptr, *tmp_anch = nullptr;
     int64_t n_entries = 0;
     if (device_ptrs) {
-        d_off = p->offsets; d_code = p->code; d_qual = p->qual; d_anch = p->anchor;
+        d_off = p->offsets;
         CU(h, cudaMemcpyAsync(&n_entries, p->offsets + p->n_loci, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
     } else {
         n_entries = p->offsets[p->n_loci];
         if (n_entries < 0) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: negative entry count");
-        CU(h, cudaMalloc(&tmp_off, sizeof(int64_t) * (size_t)(p->n_loci + 1)));
-        CU(h, pool_alloc(h, (void**)&tmp_code, (size_t)std::max<int64_t>(n_entries, 1)));
-        CU(h, pool_alloc(h, (void**)&tmp_qual, (size_t)std::max<int64_t>(n_entries, 1)));
-        CU(h, pool_alloc(h, (void**)&tmp_anch, (size_t)std::max<int64_t>(n_entries, 1)));
+        CU(h, pool_alloc_t(h, &tmp_off, (size_t)(p->n_loci + 1)));
         CU(h, cudaMemcpyAsync(tmp_off, p->offsets, sizeof(int64_t) * (size_t)(p->n_loci + 1), cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(tmp_code, p->code, (size_t)n_entries, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(tmp_qual, p->qual, (size_t)n_entries, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(tmp_anch, p->anchor, (size_t)n_entries, cudaMemcpyHostToDevice, st));
-        d_off = tmp_off; d_code = tmp_code; d_qual = tmp_qual; d_anch = tmp_anch;
+        d_off = tmp_off;
     }
     s.n_entries = n_entries;
 
     // per-locus side arrays
-    CU(h, cudaMalloc(&s.depth, sizeof(int32_t) * (size_t)p->n_loci));
-    CU(h, cudaMalloc(&s.pad, sizeof(int32_t) * (size_t)p->n_loci));
-    CU(h, cudaMalloc(&s.tile_base, sizeof(int64_t) * (size_t)(s.n_tiles + 1)));
-    CU(h, cudaMalloc(&s.ref_base, (size_t)p->n_loci));
+    CU(h, pool_alloc_t(h, &s.depth, (size_t)p->n_loci));
+    CU(h, pool_alloc_t(h, &s.pad, (size_t)p->n_loci));
+    CU(h, pool_alloc_t(h, &s.tile_base, (size_t)(s.n_tiles + 1)));
+    CU(h, pool_alloc_t(h, &s.ref_base, (size_t)p->n_loci));
     const cudaMemcpyKind kind = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (p->positions) {
-        CU(h, cudaMalloc(&s.positions, sizeof(int32_t) * (size_t)p->n_loci));
+        CU(h, pool_alloc_t(h, &s.positions, (size_t)p->n_loci));
         CU(h, cudaMemcpyAsync(s.positions, p->positions, sizeof(int32_t) * (size_t)p->n_loci, kind, st));
         s.h_positions.resize((size_t)p->n_loci);
         CU(h, cudaMemcpyAsync(s.h_positions.data(), p->positions, sizeof(int32_t) * (size_t)p->n_loci, device_ptrs ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost, st));
@@ -248,9 +259,9 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
         CU(h, cudaMemcpyAsync(s.ref_base, h->d_chr + a, (size_t)p->n_loci, cudaMemcpyDeviceToDevice, st));
     }
 
-    // layout: depths, per-tile sizes, exclusive scan -> tile_base, then the interleaving scatter
+    // layout: depths, per-tile sizes, exclusive scan -> tile_base
     int64_t* tile_bytes = nullptr;
-    CU(h, cudaMalloc(&tile_bytes, sizeof(int64_t) * (size_t)(s.n_tiles + 1)));
+    CU(h, pool_alloc_t(h, &tile_bytes, (size_t)(s.n_tiles + 1)));
     CU(h, cudaMemsetAsync(tile_bytes, 0, sizeof(int64_t) * (size_t)(s.n_tiles + 1), st));
     int32_t* d_max_depth = reinterpret_cast<int32_t*>(h->d_tile_counter);   // scratch int of the handle (the hot kernel resets it before use)
     CU(h, cudaMemsetAsync(d_max_depth, 0, sizeof(int32_t), st));
@@ -259,43 +270,86 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     size_t temp_bytes = 0;
     CU(h, exclusive_scan_i64(tile_bytes, s.tile_base, s.n_tiles + 1, nullptr, 0, &temp_bytes, st));
     void* temp = nullptr;
-    CU(h, cudaMalloc(&temp, std::max<size_t>(temp_bytes, 16)));
+    CU(h, pool_alloc(h, &temp, std::max<size_t>(temp_bytes, 16)));
     CU(h, exclusive_scan_i64(tile_bytes, s.tile_base, s.n_tiles + 1, temp, temp_bytes, nullptr, st));
     CU(h, cudaMemcpyAsync(&s.plane_bytes, s.tile_base + s.n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     if (s.max_depth >= 65000) return fail(h, PB2_ERR_UNSUPPORTED, "pb2_push_pileup: a locus with 65000 or more entries (16-bit counters)");
-    const size_t pb = (size_t)std::max<int64_t>(s.plane_bytes, 16) + 2048;   // slack: the hot kernel prefetches up to two steps past a tile
+    const size_t pb = (size_t)std::max<int64_t>(s.plane_bytes, 16) + 4096;   // slack: the hot kernel prefetches up to two steps past a tile
     s.alloc_plane = pb;
-    CU(h, pool_alloc(h, (void**)&s.code, pb));
-    CU(h, pool_alloc(h, (void**)&s.qual, pb));
+    CU(h, pool_alloc(h, (void**)&s.code, 2 * pb));   // code + quality plane
     CU(h, pool_alloc(h, (void**)&s.anch, pb));
-    CU(h, launch_tile_scatter(d_off, d_code, d_qual, d_anch, p->n_loci, s.tile_base, s.ref_base, h->dcfg.min_bq, s.code, s.qual, s.anch, s.pad, st));
-    h->total_launches += 4;
+    // the side list of flagged entries is filled by the scatter below (counters[3]; counters[0..2] are reset by every run)
+    s.exc_capacity = 1 << 20;
+    CU(h, pool_alloc_t(h, &s.exc_entries, 2 * (size_t)s.exc_capacity));
+    CU(h, pool_alloc_t(h, &s.counters, 4));
+    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
+    h->total_launches += 3;
+
+    // the interleaving scatter
+    if (device_ptrs) {
+        CU(h, launch_tile_scatter(d_off, p->code, p->qual, p->anchor, p->n_loci, 0, s.n_tiles, 0, s.tile_base, s.ref_base, h->dcfg.min_bq, s.code, s.anch, s.pad, s.exc_entries,
+                                  s.counters + 3, s.exc_capacity, st));
+        h->total_launches += 1;
+    } else {
+        // Host planes: chunks of whole tiles through two staging buffers; the H2D copy of chunk i+1 (copy stream) overlaps the scatter of chunk i
+        // (handle stream), so a push costs the PCIe time of the three planes and little else.
+        const int64_t chunk_target = (int64_t)48 << 20;   // entries (= bytes per plane) per chunk
+        int64_t max_chunk = 0;
+        std::vector<std::pair<int32_t, int32_t>> chunks;   // [tile0, tile1)
+        for (int32_t t0 = 0; t0 < s.n_tiles;) {
+            const int64_t e0 = p->offsets[(int64_t)t0 * kTileLoci];
+            int32_t lo = t0 + 1, hi = s.n_tiles;           // first tile end whose entry count reaches the target (offsets are monotone)
+            while (lo < hi) {
+                const int32_t mid = lo + (hi - lo) / 2;
+                if (p->offsets[std::min<int64_t>((int64_t)mid * kTileLoci, p->n_loci)] - e0 >= chunk_target) hi = mid; else lo = mid + 1;
+            }
+            const int32_t t1 = lo;
+            max_chunk = std::max(max_chunk, p->offsets[std::min<int64_t>((int64_t)t1 * kTileLoci, p->n_loci)] - e0);
+            chunks.push_back({t0, t1});
+            t0 = t1;
+        }
+        uint8_t* stage[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+        const int n_buf = chunks.size() > 1 ? 2 : 1;
+        for (int b = 0; b < n_buf; b++) for (int k = 0; k < 3; k++) CU(h, pool_alloc(h, (void**)&stage[b][k], (size_t)std::max<int64_t>(max_chunk, 16)));
+        CU(h, cudaEventRecord(h->ev_scattered[0], st));   // the copy stream must not run ahead of the allocations made on the handle stream
+        CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_scattered[0], 0));
+        for (size_t i = 0; i < chunks.size(); i++) {
+            const int b = (int)(i % 2);
+            const int32_t t0 = chunks[i].first, t1 = chunks[i].second;
+            const int64_t e0 = p->offsets[(int64_t)t0 * kTileLoci], e1 = p->offsets[std::min<int64_t>((int64_t)t1 * kTileLoci, p->n_loci)];
+            if (i >= 2) CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_scattered[b], 0));
+            if (e1 > e0) {
+                CU(h, cudaMemcpyAsync(stage[b][0], p->code + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, h->copy_stream));
+                CU(h, cudaMemcpyAsync(stage[b][1], p->qual + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, h->copy_stream));
+                CU(h, cudaMemcpyAsync(stage[b][2], p->anchor + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, h->copy_stream));
+            }
+            CU(h, cudaEventRecord(h->ev_copied[b], h->copy_stream));
+            CU(h, cudaStreamWaitEvent(st, h->ev_copied[b], 0));
+            CU(h, launch_tile_scatter(d_off, stage[b][0], stage[b][1], stage[b][2], p->n_loci, t0, t1 - t0, e0, s.tile_base, s.ref_base, h->dcfg.min_bq, s.code, s.anch, s.pad,
+                                      s.exc_entries, s.counters + 3, s.exc_capacity, st));
+            CU(h, cudaEventRecord(h->ev_scattered[b], st));
+            h->total_launches += 1;
+        }
+        for (int b = 0; b < n_buf; b++) for (int k = 0; k < 3; k++) pool_free(h, stage[b][k]);
+    }
 
     // outputs
     if (h->cfg.output_gvcf) {
         s.alloc_ref = sizeof(pb2_call_record) * (size_t)p->n_loci;
         CU(h, pool_alloc(h, (void**)&s.ref_records, s.alloc_ref));
-        CU(h, cudaMalloc(&s.ref_valid, (size_t)p->n_loci));
+        CU(h, pool_alloc_t(h, &s.ref_valid, (size_t)p->n_loci));
     }
     s.var_capacity = std::max<int64_t>(1024, p->n_loci);
     s.alloc_var = sizeof(pb2_call_record) * (size_t)s.var_capacity;
     CU(h, pool_alloc(h, (void**)&s.var_records, s.alloc_var));
-    s.exc_capacity = 1 << 20;
-    CU(h, cudaMalloc(&s.exc_entries, sizeof(uint32_t) * 2 * (size_t)s.exc_capacity));
-    CU(h, cudaMalloc(&s.counters, sizeof(unsigned long long) * 4));
     s.pending_capacity = std::max<int64_t>(1024, p->n_loci);
     s.alloc_pending = sizeof(PendingLocus) * (size_t)s.pending_capacity;
     CU(h, pool_alloc(h, (void**)&s.pending, s.alloc_pending));
-
-    CU(h, cudaStreamSynchronize(st));
-    cudaFree(tile_bytes);
-    cudaFree(temp);
-    if (tmp_off) {
-        cudaFree(tmp_off);
-        const size_t nb = (size_t)std::max<int64_t>(n_entries, 1);
-        pool_free(h, tmp_code, nb); pool_free(h, tmp_qual, nb); pool_free(h, tmp_anch, nb);
-    }
+    pool_free(h, tile_bytes);
+    pool_free(h, temp);
+    pool_free(h, tmp_off);
+    CU(h, cudaStreamSynchronize(st));   // the caller's buffers are consumed when this returns
     h->segs.push_back(std::move(s));
     return PB2_OK;
 }
@@ -303,36 +357,46 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
 extern "C" int pb2_push_pileup(pb2_handle* h, const pb2_pileup_csr* p) { return push_common(h, p, false); }
 extern "C" int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p) { return push_common(h, p, true); }
 
-static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out, const int32_t* d_gapped = nullptr) {
+// enqueue: counters reset, hot kernel (+ overflow scorer) between the timing events. finish: counters back, one synchronize, bookkeeping.
+static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out, const int32_t* d_gapped, bool reset_counters = true) {
     cudaStream_t st = h->stream;
     TilePileup in;
-    in.code = s.code; in.qual = s.qual; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
+    in.cq = s.code; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
     in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles; in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);
     HotInputsExtra ex;
     ex.gapped_ref = d_gapped; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len; ex.q_to_p_table = h->d_q_to_p; ex.q_table_max = h->q_table_max;
     HotOutputs out;
     out.ref_records = s.ref_records; out.ref_valid = s.ref_valid; out.var_records = s.var_records; out.var_count = s.counters;
-    out.var_capacity = s.var_capacity; out.exc_entries = s.exc_entries; out.exc_count = s.counters + 1; out.exc_capacity = s.exc_capacity;
+    out.var_capacity = s.var_capacity; out.exc_entries = s.exc_entries; out.exc_count = s.counters + 3; out.exc_capacity = s.exc_capacity;
     out.counts_out = counts_out; out.collapsed_out = collapsed_out;
     out.pending = s.pending; out.pending_count = s.counters + 2; out.pending_capacity = s.pending_capacity;
-    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
+    if (reset_counters) CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 3, st));
     CU(h, cudaEventRecord(h->ev0, st));
     CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, s.max_depth, st));
     CU(h, cudaEventRecord(h->ev1, st));
-    unsigned long long cnt[2];
-    CU(h, cudaMemcpyAsync(cnt, s.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    return PB2_OK;
+}
+static int finish_segment(pb2_handle* h, Segment& s) {
+    cudaStream_t st = h->stream;
+    unsigned long long cnt4[4];
+    CU(h, cudaMemcpyAsync(cnt4, s.counters, sizeof(cnt4), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     float ms = 0;
     CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->hot_ms += ms;
     h->hot_launches += 1;
     h->total_launches += 2;
+    const unsigned long long cnt[2] = {cnt4[0], cnt4[3]};
     s.h_var_count = cnt[0];
     s.h_exc_count = cnt[1];
     s.called = true;
     if ((int64_t)cnt[0] > s.var_capacity) return fail(h, PB2_ERR_NOMEM, "variant record buffer overflow");
     if ((int64_t)cnt[1] > s.exc_capacity) return fail(h, PB2_ERR_NOMEM, "open-ended candidate side list overflow");
     return PB2_OK;
+}
+static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out, const int32_t* d_gapped = nullptr) {
+    const int rc = enqueue_segment(h, s, counts_out, collapsed_out, d_gapped);
+    return rc != PB2_OK ? rc : finish_segment(h, s);
 }
 
 extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
@@ -493,16 +557,38 @@ extern "C" int pb2_call_resident(pb2_handle* h, int64_t* n_records) {
     if (!h) return PB2_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
     int64_t total = 0;
-    for (auto& s : h->segs) {
-        int rc = run_segment(h, s, nullptr, nullptr);
-        if (rc != PB2_OK) return rc;
-        total += (int64_t)s.h_var_count;
-    }
-    if (!h->cands.empty()) {   // explicit candidates: gathered, scored and appended to the (last) segment's variant stream on the device
+    if (!h->cands.empty()) {
+        // explicit candidates: gathered, scored and appended to the segment's variant stream on the device, behind the hot kernel on the same
+        // stream; one synchronize for the whole step
         if (h->segs.size() != 1) return fail(h, PB2_ERR_UNSUPPORTED, "pb2_call_resident with explicit candidates needs exactly one staged segment; use pb2_flush");
-        const int rc = explicit_call_resident(h, h->segs[0]);
+        Segment& s = h->segs[0];
+        int rc;
+        if (!explicit_resident_ready(h)) {   // first call: plan building, everything in order on the handle stream
+            rc = enqueue_segment(h, s, nullptr, nullptr, nullptr);
+            if (rc == PB2_OK) rc = explicit_call_resident(h, s, h->stream);
+        } else {
+            // the explicit pass (two small latency-bound kernels) goes to the side stream ahead of the hot kernel and runs next to it
+            cudaStream_t st = h->stream;
+            CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 3, st));
+            CU(h, cudaEventRecord(h->ev_scattered[0], st));
+            CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_scattered[0], 0));
+            rc = explicit_call_resident(h, s, h->copy_stream);
+            if (rc != PB2_OK) return rc;
+            CU(h, cudaEventRecord(h->ev_copied[0], h->copy_stream));
+            rc = enqueue_segment(h, s, nullptr, nullptr, nullptr, false);
+            if (rc != PB2_OK) return rc;
+            CU(h, cudaStreamWaitEvent(st, h->ev_copied[0], 0));
+            rc = explicit_prune_resident(h, s);
+        }
+        if (rc == PB2_OK) rc = finish_segment(h, s);
         if (rc != PB2_OK) return rc;
-        total = (int64_t)h->segs[0].h_var_count;
+        total = (int64_t)s.h_var_count;
+    } else {
+        for (auto& s : h->segs) {
+            int rc = run_segment(h, s, nullptr, nullptr);
+            if (rc != PB2_OK) return rc;
+            total += (int64_t)s.h_var_count;
+        }
     }
     if (n_records) *n_records = total;
     return PB2_OK;

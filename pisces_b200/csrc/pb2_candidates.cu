@@ -46,20 +46,21 @@ gather_locus_counts_kernel(TilePileup in, const int32_t* __restrict__ req_locus,
         const int n_target = __shfl_sync(0xffffffffu, nch, tl);
         const unsigned below = (1u << tl) - 1u;
         int64_t base = in.tile_base[tile];
-        int64_t my_off = -1;
+        int64_t my_off = -1, my_cq = 0;
+        int my_run = 0;
         for (int s = 0; s < n_target; s++) {
             const unsigned m = __ballot_sync(0xffffffffu, nch > s);
-            if ((s & 31) == lane) my_off = base + (int64_t)__popc(m & below) * kChunk;
+            if ((s & 31) == lane) { my_off = base + (int64_t)__popc(m & below) * kChunk; my_cq = base + my_off; my_run = __popc(m) * kChunk; }
             base += (int64_t)__popc(m) * kChunk;
             if ((s & 31) == 31 || s == n_target - 1) {
                 if (my_off >= 0) {
-                    const uint4 wc = *reinterpret_cast<const uint4*>(in.code + my_off);
-                    const uint4 wq = *reinterpret_cast<const uint4*>(in.qual + my_off);
+                    const uint4 wc = *reinterpret_cast<const uint4*>(in.cq + my_cq);             // code chunks of the step, then its quality chunks
+                    const uint4 wq = *reinterpret_cast<const uint4*>(in.cq + my_cq + my_run);
                     const uint4 wa = *reinterpret_cast<const uint4*>(in.anch + my_off);
                     const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w}, aw[4] = {wa.x, wa.y, wa.z, wa.w};
 #pragma unroll
                     for (int k = 0; k < kChunk; k++) {
-                        const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu, q = (qw[k >> 2] >> ((k & 3) * 8)) & 0xffu, an = (aw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                        const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu, q = (qw[k >> 2] >> ((k & 3) * 8)) & 0x7fu, an = (aw[k >> 2] >> ((k & 3) * 8)) & 0xffu;   // staged q carries bit 7
                         int allele = (int)(code & 7u);
                         if (allele == 7 || (int)q < min_bq) allele = AT_N;    // staged N is 7; RegionStateManager.cs:180-181: low quality -> N
                         const int dir = (int)((code >> 3) & 3u);
@@ -121,49 +122,58 @@ __device__ __forceinline__ bool bytes_equal(const uint8_t* a, const uint8_t* b, 
     for (int k = 0; k < n; k++) if (a[k] != b[k]) return false;
     return true;
 }
-// RMxNCalculator.ComputeRMxNLengthForIndel (:49-95); counts are capped at `cap` (callers compare min/max of them against cap only)
-__device__ int cand_rmxn_length(int variant_position, const uint8_t* vb, int length, const uint8_t* __restrict__ ref, int64_t ref_len, int max_unit, int cap) {
-    int best = 0;
-    const int first = length - min(max_unit, length);
-    for (int pass = 0; pass < 2; pass++) {          // prefixes, then suffixes (bookends)
-        for (int i = first; i < length; i++) {
-            const int blen = length - i;
-            const uint8_t* book = pass == 0 ? vb : vb + i;
-            int64_t back = variant_position;
-            for (int steps = 0; steps < cap; steps++) {
-                const int64_t nb = back - blen;
-                if (nb < 0 || nb + blen > ref_len) break;
-                if (!bytes_equal(ref + nb, book, blen)) break;
-                back = nb;
-            }
-            int reps = 0;
-            int64_t cur = back;
-            while (reps < cap) {
-                if (cur < 0 || cur + blen > ref_len) break;
-                if (!bytes_equal(ref + cur, book, blen)) break;
-                reps++;
-                cur += blen;
-            }
-            best = max(best, reps);
-        }
+// One bookend of RMxNCalculator.ComputeRMxNLengthForIndel (:49-95): the prefix (pass 0) or suffix (pass 1) of the variant bases starting at offset i,
+// walked back over the reference while it repeats, then counted forward. Counts are capped at `cap` (callers compare min/max of them against cap only;
+// going back further than cap units cannot change a count that is capped at cap).
+__device__ int cand_rmxn_bookend(int variant_position, const uint8_t* vb, int length, int i, int pass, const uint8_t* __restrict__ ref, int64_t ref_len, int cap) {
+    const int blen = length - i;
+    const uint8_t* book = pass == 0 ? vb : vb + i;
+    int64_t back = variant_position;
+    for (int steps = 0; steps < cap; steps++) {
+        const int64_t nb = back - blen;
+        if (nb < 0 || nb + blen > ref_len) break;
+        if (!bytes_equal(ref + nb, book, blen)) break;
+        back = nb;
     }
-    return best;
+    int reps = 0;
+    int64_t cur = back;
+    while (reps < cap) {
+        if (cur < 0 || cur + blen > ref_len) break;
+        if (!bytes_equal(ref + cur, book, blen)) break;
+        reps++;
+        cur += blen;
+    }
+    return reps;
 }
-// RMxNCalculator.ShouldFilter (:19-38,104-133) for any allele type
-__device__ bool cand_rmxn_should_filter(const DevCand& c, const uint8_t* ref_allele, const uint8_t* alt_allele, float freq, const DeviceConfig& cfg,
-                                        const uint8_t* __restrict__ chr, int64_t chr_len) {
-    if (freq >= cfg.rmxn_freq_limit) return false;
-    if (cfg.rmxn_max_len < 0 || cfg.rmxn_min_reps < 0 || chr == nullptr) return false;
+// RMxNCalculator.ShouldFilter (:19-38,104-133) for any allele type, by a full warp: the (up to 3 calls x 2 x max unit length) bookend scans are
+// independent chains of dependent reference reads, so each lane takes one and the per-call maxima are warp-reduced.
+__device__ bool cand_rmxn_should_filter_warp(const DevCand& c, const uint8_t* ref_allele, const uint8_t* alt_allele, const DeviceConfig& cfg,
+                                             const uint8_t* __restrict__ chr, int64_t chr_len) {
+    const int lane = threadIdx.x & 31;
     const int cap = max(cfg.rmxn_min_reps, 1);
-    int c1, c2 = INT32_MAX;
-    if (c.type == CAT_INS) c1 = cand_rmxn_length(c.position, alt_allele + 1, c.alt_len - 1, chr, chr_len, cfg.rmxn_max_len, cap);
-    else if (c.type == CAT_DEL) c1 = cand_rmxn_length(c.position, ref_allele + 1, c.ref_len - 1, chr, chr_len, cfg.rmxn_max_len, cap);
+    const int U = max(cfg.rmxn_max_len, 1);
+    int n_calls;
+    int vpos[3], vlen[3];
+    const uint8_t* vb[3];
+    if (c.type == CAT_INS) { n_calls = 1; vpos[0] = c.position; vb[0] = alt_allele + 1; vlen[0] = c.alt_len - 1; }
+    else if (c.type == CAT_DEL) { n_calls = 1; vpos[0] = c.position; vb[0] = ref_allele + 1; vlen[0] = c.ref_len - 1; }
     else {
-        c1 = cand_rmxn_length(c.position - 1, ref_allele, c.ref_len, chr, chr_len, cfg.rmxn_max_len, cap);
-        const int i1 = cand_rmxn_length(c.position + c.ref_len - 1, alt_allele, c.alt_len, chr, chr_len, cfg.rmxn_max_len, cap);
-        const int i2 = cand_rmxn_length(c.position - 1, alt_allele, c.alt_len, chr, chr_len, cfg.rmxn_max_len, cap);
-        c2 = max(i1, i2);
+        n_calls = 3;
+        vpos[0] = c.position - 1; vb[0] = ref_allele; vlen[0] = c.ref_len;
+        vpos[1] = c.position + c.ref_len - 1; vb[1] = alt_allele; vlen[1] = c.alt_len;
+        vpos[2] = c.position - 1; vb[2] = alt_allele; vlen[2] = c.alt_len;
     }
+    int best[3] = {0, 0, 0};
+    for (int t = lane; t < n_calls * 2 * U; t += 32) {
+        const int call = t / (2 * U), pass = (t / U) & 1, ui = t % U;
+        const int units = min(cfg.rmxn_max_len, vlen[call]);
+        if (ui >= units) continue;
+        const int i = vlen[call] - units + ui;
+        best[call] = max(best[call], cand_rmxn_bookend(vpos[call], vb[call], vlen[call], i, pass, chr, chr_len, cap));
+    }
+    for (int k = 0; k < 3; k++) best[k] = __reduce_max_sync(0xffffffffu, best[k]);
+    const int c1 = best[0];
+    const int c2 = n_calls == 3 ? max(best[1], best[2]) : INT32_MAX;
     return min(c1, c2) >= cfg.rmxn_min_reps;
 }
 
@@ -219,8 +229,15 @@ __device__ int cand_indel_repeat_length(const DevCand& c, const uint8_t* ref_all
 }
 
 // ------------------------------------------------------------------------------------------------ the candidate scorer
-__global__ void __launch_bounds__(64) score_candidates_kernel(CandScoreArgs a, DeviceConfig cfg) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per candidate: the lanes stage the two 198-bin count rows in shared memory (coalesced) and share the RMxN reference scans; lane 0 does
+// the coverage arithmetic, the q-score / strand-bias / genotype chain and writes the record.
+constexpr int kScoreWarps = 4;
+
+__global__ void __launch_bounds__(32 * kScoreWarps) score_candidates_kernel(CandScoreArgs a, DeviceConfig cfg) {
+    __shared__ int32_t s_cnt[kScoreWarps][2][kNumBins];
+    __shared__ double s_qs[kScoreWarps][2][kNumBins];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * kScoreWarps + warp;
     if (i >= a.n) return;
     const DevCand c = a.cands[i];
     const uint8_t* ref_allele = a.arena + c.allele_off;
@@ -228,6 +245,21 @@ __global__ void __launch_bounds__(64) score_candidates_kernel(CandScoreArgs a, D
     int allele_support = c.support[0] + c.support[1] + c.support[2];
     if (c.type == CAT_REF) allele_support = max(0, allele_support - c.gapped_ref);   // CoverageCalculator.cs:94-97
     const bool want_q = a.qsum != nullptr;
+    for (int b = lane; b < kNumBins; b += 32) {
+        s_cnt[warp][0][b] = c.req_start >= 0 ? a.counts[(int64_t)c.req_start * kNumBins + b] : 0;
+        s_cnt[warp][1][b] = c.req_end >= 0 ? a.counts[(int64_t)c.req_end * kNumBins + b] : 0;
+        if (want_q) {
+            s_qs[warp][0][b] = c.req_start >= 0 ? a.qsum[(int64_t)c.req_start * kNumBins + b] : 0.0;
+            s_qs[warp][1][b] = c.req_end >= 0 ? a.qsum[(int64_t)c.req_end * kNumBins + b] : 0.0;
+        }
+    }
+    __syncwarp();
+    const bool is_ref = c.type == CAT_REF;
+    // the reference scans need no coverage: all lanes, before lane 0 goes on alone (skipped by ShouldFilter when the frequency is above the limit; the
+    // limit test is applied to the result below)
+    bool rmxn_hit = false;
+    if (!is_ref && cfg.rmxn_max_len >= 0 && cfg.rmxn_min_reps >= 0 && a.chr_seq != nullptr) rmxn_hit = cand_rmxn_should_filter_warp(c, ref_allele, alt_allele, cfg, a.chr_seq, a.chr_len);
+    if (lane != 0) return;
 
     int cov[3] = {0, 0, 0};
     int total = 0, ref_support = 0, nocalls = 0;
@@ -236,8 +268,8 @@ __global__ void __launch_bounds__(64) score_candidates_kernel(CandScoreArgs a, D
 
     if (c.type == CAT_SNV || c.type == CAT_REF) {
         // CalculateSinglePoint (:49-98)
-        const int32_t* cs = c.req_start >= 0 ? a.counts + (int64_t)c.req_start * kNumBins : nullptr;
-        const double* qs = (want_q && c.req_start >= 0) ? a.qsum + (int64_t)c.req_start * kNumBins : nullptr;
+        const int32_t* cs = s_cnt[warp][0];
+        const double* qs = want_q ? s_qs[warp][0] : nullptr;
         const int ref_type = c.ref_len == 1 ? cand_allele_of_base(ref_allele[0]) : AT_N;
         for (int d = 0; d < 3; d++) {
             for (int k = 0; k < 5; k++) {
@@ -255,10 +287,10 @@ __global__ void __launch_bounds__(64) score_candidates_kernel(CandScoreArgs a, D
         // CalculateSpanning (:162-321)
         const int length = c.type == CAT_DEL ? c.ref_len - 1 : c.type == CAT_INS ? c.alt_len - 1 : c.alt_len;   // BaseAllele.Length (:24-43)
         const bool presume_anchored = c.type == CAT_INS ? (cfg.expect_stitched != 0) : true;
-        const int32_t* cs = c.req_start >= 0 ? a.counts + (int64_t)c.req_start * kNumBins : nullptr;
-        const int32_t* ce = c.req_end >= 0 ? a.counts + (int64_t)c.req_end * kNumBins : nullptr;
-        const double* qs = (want_q && c.req_start >= 0) ? a.qsum + (int64_t)c.req_start * kNumBins : nullptr;
-        const double* qe = (want_q && c.req_end >= 0) ? a.qsum + (int64_t)c.req_end * kNumBins : nullptr;
+        const int32_t* cs = s_cnt[warp][0];
+        const int32_t* ce = s_cnt[warp][1];
+        const double* qs = want_q ? s_qs[warp][0] : nullptr;
+        const double* qe = want_q ? s_qs[warp][1] : nullptr;
         const bool picky = c.type == CAT_INS;   // considerAnchorInformation: TrackedAnchorSize > 0 (Factory.cs:193-199)
         int first_base = AT_N, last_base = AT_N;
         if (picky) { first_base = cand_allele_of_base(alt_allele[1]); last_base = cand_allele_of_base(alt_allele[c.alt_len - 1]); }
@@ -301,7 +333,6 @@ __global__ void __launch_bounds__(64) score_candidates_kernel(CandScoreArgs a, D
     }
 
     // ---- AlleleCaller.ProcessVariant (:208-234)
-    const bool is_ref = c.type == CAT_REF;
     const float freq = allele_frequency(allele_support, total);
     int vq = 0, nl_applied = 0;
     SbResult sb;
@@ -326,7 +357,7 @@ __global__ void __launch_bounds__(64) score_candidates_kernel(CandScoreArgs a, D
         if (cfg.no_call_filter >= 0 && frac_nc > cfg.no_call_filter) filters |= 1u << FLT_NO_CALL;
         if (!sb.acceptable || (cfg.filter_single_strand && !sb.var_both)) filters |= 1u << FLT_STRAND_BIAS;
         if (a.indel_repeat_filter > 0 && a.indel_repeat_filter <= cand_indel_repeat_length(c, ref_allele, alt_allele, a.chr_seq, a.chr_len)) filters |= 1u << FLT_INDEL_REPEAT;
-        if (cand_rmxn_should_filter(c, ref_allele, alt_allele, freq, cfg, a.chr_seq, a.chr_len)) filters |= 1u << FLT_RMXN;
+        if (rmxn_hit && !(freq >= cfg.rmxn_freq_limit)) filters |= 1u << FLT_RMXN;
         if (freq < cfg.variant_freq_filter) filters |= 1u << FLT_LOW_VF;
         if (cfg.expect_stitched && (c.flags & kCandAltHasN)) filters |= 1u << FLT_STRAND_BIAS;
     }
@@ -380,9 +411,21 @@ __global__ void __launch_bounds__(64) score_candidates_kernel(CandScoreArgs a, D
     }
 }
 
+// After a scorer pass that ran next to the hot kernel: prune the reference records of the positions where an explicit allele was called
+// (AlleleCaller.cs:146-147); the hot kernel has written ref_valid by now.
+__global__ void prune_ref_valid_kernel(const DevCand* __restrict__ cands, const uint8_t* __restrict__ flags, int32_t n, uint8_t* __restrict__ ref_valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (flags[i] & 2) && cands[i].locus >= 0 && cands[i].type != CAT_REF) ref_valid[cands[i].locus] = 0;
+}
+cudaError_t launch_prune_ref_valid(const DevCand* cands, const uint8_t* flags, int32_t n, uint8_t* ref_valid, cudaStream_t stream) {
+    if (n <= 0 || ref_valid == nullptr) return cudaSuccess;
+    prune_ref_valid_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cands, flags, n, ref_valid);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_score_candidates(const CandScoreArgs& args, const DeviceConfig& cfg, cudaStream_t stream) {
     if (args.n <= 0) return cudaSuccess;
-    score_candidates_kernel<<<(args.n + 63) / 64, 64, 0, stream>>>(args, cfg);
+    score_candidates_kernel<<<(args.n + kScoreWarps - 1) / kScoreWarps, 32 * kScoreWarps, 0, stream>>>(args, cfg);
     return cudaGetLastError();
 }
 

@@ -97,6 +97,7 @@ struct CandScoreArgs {
 
 cudaError_t launch_gather_locus_counts(const TilePileup& in, const int32_t* req_locus, int32_t n_req, int32_t* out_counts, int32_t* out_collapsed,
                                        double* out_qsum, int min_bq, cudaStream_t stream);
+cudaError_t launch_prune_ref_valid(const DevCand* cands, const uint8_t* flags, int32_t n, uint8_t* ref_valid, cudaStream_t stream);
 cudaError_t launch_score_candidates(const CandScoreArgs& args, const DeviceConfig& cfg, cudaStream_t stream);
 
 }  // namespace pb2

@@ -110,7 +110,7 @@ struct BatchCtx {
     }
     static TilePileup view(const Segment& s) {
         TilePileup in;
-        in.code = s.code; in.qual = s.qual; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
+        in.cq = s.code; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
         in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles;
         in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);
         return in;
@@ -563,7 +563,11 @@ void explicit_release_resident(pb2_handle* h) {
     if (h->resident_explicit) { delete static_cast<ResidentPlan*>(h->resident_explicit); h->resident_explicit = nullptr; }
 }
 
-int explicit_call_resident(pb2_handle* h, Segment& seg) {
+bool explicit_resident_ready(pb2_handle* h) { return h->resident_explicit != nullptr; }
+
+// First call: builds the plan (tables, gathers, scorer in append mode behind the hot kernel on the handle stream). Later calls (`side` given): replays the
+// recorded launches on the side stream so that they run next to the hot kernel; the caller joins the streams and then prunes the reference records.
+int explicit_call_resident(pb2_handle* h, Segment& seg, cudaStream_t side) {
     cudaStream_t st = h->stream;
     ResidentPlan* plan = static_cast<ResidentPlan*>(h->resident_explicit);
     if (plan == nullptr) {
@@ -581,7 +585,6 @@ int explicit_call_resident(pb2_handle* h, Segment& seg) {
         std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return h->cands[a].position < h->cands[b].position; });
         for (size_t i : idx) { store.push_back(piece_of(h->cands[i])); ps.push_back(&store.back()); }
         h->arena.clear();
-        // first call: builds the tables, gathers and scores (append mode); the launches are recorded for the replays below
         const int rc = score_pieces(plan->ctx, ps, h->arena, nullptr, nullptr, nullptr, &seg);
         if (rc != PB2_OK) { explicit_release_resident(h); return rc; }
         memset(&plan->args, 0, sizeof(plan->args));
@@ -589,23 +592,29 @@ int explicit_call_resident(pb2_handle* h, Segment& seg) {
         a.cands = plan->ctx.d_cands.p; a.n = (int32_t)ps.size(); a.counts = plan->ctx.counts.p; a.collapsed = plan->ctx.collapsed.p;
         a.qsum = plan->ctx.want_q ? plan->ctx.qsum.p : nullptr; a.arena = plan->ctx.d_arena.p; a.chr_seq = h->d_chr; a.chr_len = h->chr_len;
         a.q_to_p_table = h->d_q_to_p; a.q_table_max = h->q_table_max; a.indel_repeat_filter = h->cfg.indel_repeat_filter;
-        a.var_records = seg.var_records; a.var_count = seg.counters; a.var_capacity = seg.var_capacity; a.ref_valid = seg.ref_valid;
-    } else {
-        BatchCtx& ctx = plan->ctx;
-        for (auto& g : ctx.gathers) {
-            CUX(h, launch_gather_locus_counts(BatchCtx::view(h->segs[g.seg]), ctx.req.p + g.req_off, g.n, ctx.counts.p + (size_t)g.row0 * kNumBins,
-                                              ctx.collapsed.p + (size_t)g.row0 * kNumCollapsed, ctx.want_q ? ctx.qsum.p + (size_t)g.row0 * kNumBins : nullptr,
-                                              h->dcfg.min_bq, st));
-            h->total_launches += 1;
-        }
-        CUX(h, launch_score_candidates(plan->args, h->dcfg, st));
+        a.var_records = seg.var_records; a.var_count = seg.counters; a.var_capacity = seg.var_capacity;
+        // replays run concurrently with the hot kernel: the scorer only flags what it called, explicit_prune_resident clears ref_valid afterwards
+        a.ref_valid = nullptr;
+        CUX(h, plan->ctx.d_flags.reserve(ps.size(), st));
+        a.out_callable = plan->ctx.d_flags.p;
+        return PB2_OK;
+    }
+    BatchCtx& ctx = plan->ctx;
+    for (auto& g : ctx.gathers) {
+        CUX(h, launch_gather_locus_counts(BatchCtx::view(h->segs[g.seg]), ctx.req.p + g.req_off, g.n, ctx.counts.p + (size_t)g.row0 * kNumBins,
+                                          ctx.collapsed.p + (size_t)g.row0 * kNumCollapsed, ctx.want_q ? ctx.qsum.p + (size_t)g.row0 * kNumBins : nullptr,
+                                          h->dcfg.min_bq, side));
         h->total_launches += 1;
     }
-    unsigned long long cnt = 0;
-    CUX(h, cudaMemcpyAsync(&cnt, seg.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-    CUX(h, cudaStreamSynchronize(st));
-    seg.h_var_count = cnt;
-    if ((int64_t)cnt > seg.var_capacity) return pb2_fail(h, PB2_ERR_NOMEM, "variant record buffer overflow");
+    CUX(h, launch_score_candidates(plan->args, h->dcfg, side));
+    h->total_launches += 1;
+    return PB2_OK;
+}
+int explicit_prune_resident(pb2_handle* h, Segment& seg) {
+    ResidentPlan* plan = static_cast<ResidentPlan*>(h->resident_explicit);
+    if (plan == nullptr || seg.ref_valid == nullptr) return PB2_OK;
+    CUX(h, launch_prune_ref_valid(plan->args.cands, plan->args.out_callable, plan->args.n, seg.ref_valid, h->stream));
+    h->total_launches += 1;
     return PB2_OK;
 }
 

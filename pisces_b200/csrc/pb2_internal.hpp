@@ -114,7 +114,9 @@ struct pb2_handle {
     pb2::DeviceConfig dcfg;
     int device = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_scattered[2] = {nullptr, nullptr};
+    cudaMemPool_t pool = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string error;
     std::string chr_name;
@@ -156,6 +158,8 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
 // Finds the candidates of the reads in R[first_read, end) on the device (CandidateVariantFinder.FindCandidates) and adds them to the table.
 int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_read);
 // pb2_call_resident: gather + score + append on the device, no host round trip; only for candidates that need neither the collapser nor the MNV logic.
-int explicit_call_resident(pb2_handle* h, Segment& seg);
+int explicit_call_resident(pb2_handle* h, Segment& seg, cudaStream_t side);
+bool explicit_resident_ready(pb2_handle* h);
+int explicit_prune_resident(pb2_handle* h, Segment& seg);
 void explicit_release_resident(pb2_handle* h);
 

@@ -14,6 +14,7 @@ namespace pb2 {
 
 constexpr uint32_t kStagedN = 7;                 // staged allele code of N (the external pb2_pileup_csr code is AlleleType.N = 4)
 constexpr uint32_t kPadCode4 = 0x07070707u;      // four PAD code bytes: N | Forward
+constexpr uint32_t kQualMask = 0x7fu;            // staged quality bytes carry bit 7 (see tile_scatter_kernel)
 
 // ------------------------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {  // 16-byte streaming load: read once, do not pollute L1
@@ -47,19 +48,25 @@ __global__ void tile_layout_kernel(const int64_t* __restrict__ off, int64_t n_lo
 //   * the tail of a locus' last 16-entry chunk is filled with PAD entries;
 //   * PAD = (code N|Forward, qual 255, anchor 0): it lands in bin [N][Forward][0] and pad[i] of them are subtracted at read-out;
 //   * N is staged as allele code 7 (kStagedN) so that the quality rule `q < minBQ -> N` is a byte-parallel OR with 7 in the hot loop;
+//   * the quality byte is staged with bit 7 set (q | 0x80, q clamped to 127: Phred qualities end at 93) so that the hot loop's byte-parallel
+//     `q - minBQ` cannot borrow across bytes and its sign test is one byte-permute; readers of the plane mask with 0x7f (kQualMask);
 //   * candidate flags are kept only where they can matter: the base is a usable (q >= minBQ, A/C/G/T) mismatch against an A/C/G/T
 //     reference base. Every flagged entry the hot kernel meets is then a real SNV-candidate exception.
 __global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8_t* __restrict__ code, const uint8_t* __restrict__ qual,
-                                    const uint8_t* __restrict__ anch, int64_t n_loci, const int64_t* __restrict__ tile_base, const uint8_t* __restrict__ ref_base,
-                                    int min_bq, uint8_t* __restrict__ tcode, uint8_t* __restrict__ tqual, uint8_t* __restrict__ tanch, int32_t* __restrict__ pad) {
+                                    const uint8_t* __restrict__ anch, int64_t n_loci, int32_t tile0, int32_t n_tiles, int64_t entry_base,
+                                    const int64_t* __restrict__ tile_base, const uint8_t* __restrict__ ref_base, int min_bq, uint8_t* __restrict__ tcq,
+                                    uint8_t* __restrict__ tanch, int32_t* __restrict__ pad, uint32_t* __restrict__ exc_entries, unsigned long long* __restrict__ exc_count,
+                                    int64_t exc_capacity) {
     const int lane = threadIdx.x & 31;
-    const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t wi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wi >= n_tiles) return;
+    const int64_t tile = tile0 + wi;
     const int64_t locus = tile * kTileLoci + lane;
     if (tile * kTileLoci >= n_loci) return;
     int64_t src = 0;
     int d = 0;
     int ref_allele = AT_N;
-    if (locus < n_loci) { src = off[locus]; d = (int)(off[locus + 1] - src); ref_allele = allele_of_base(ref_base[locus]); }
+    if (locus < n_loci) { src = off[locus]; d = (int)(off[locus + 1] - src); src -= entry_base; ref_allele = allele_of_base(ref_base[locus]); }
     const int nchunks = (d + kChunk - 1) / kChunk;
     const int max_chunks = __reduce_max_sync(0xffffffffu, nchunks);
     int64_t base = tile_base[tile];
@@ -84,14 +91,24 @@ __global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8
                 } else if (lowq || allele >= AT_N || ref_allele == AT_N || allele == ref_allele) {
                     cb &= 0x1f;                                     // flags cannot matter here
                 }
+                if (cb & 0xe0u) {
+                    // a flagged usable mismatch: SNV-candidate bookkeeping the counts cannot express (open ends, '='/'X' support). It is a property of
+                    // the entry, not of the counting, so it goes to the segment's side list here and the hot loop never looks at flag bits.
+                    const unsigned long long slot = atomicAdd(exc_count, 1ull);
+                    if ((int64_t)slot < exc_capacity) { exc_entries[2 * slot] = (uint32_t)locus; exc_entries[2 * slot + 1] = cb | (qb << 8) | (ab << 16); }
+                    cb &= 0x1f;
+                }
                 if ((cb & 7) == AT_N) cb |= kStagedN;
+                qb = min(qb, 127u) | 0x80u;
                 const int sh = (k & 3) * 8;
                 wc[k >> 2] = (wc[k >> 2] & ~(0xffu << sh)) | (cb << sh);
                 wq[k >> 2] = (wq[k >> 2] & ~(0xffu << sh)) | (qb << sh);
                 wa[k >> 2] = (wa[k >> 2] & ~(0xffu << sh)) | (ab << sh);
             }
-            *reinterpret_cast<uint4*>(tcode + dst) = make_uint4(wc[0], wc[1], wc[2], wc[3]);
-            *reinterpret_cast<uint4*>(tqual + dst) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+            // code and quality share one plane: per step the code chunks of the active lanes, then their quality chunks
+            const int64_t dcq = 2 * base + (int64_t)slot * kChunk;
+            *reinterpret_cast<uint4*>(tcq + dcq) = make_uint4(wc[0], wc[1], wc[2], wc[3]);
+            *reinterpret_cast<uint4*>(tcq + dcq + (int64_t)__popc(m) * kChunk) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
             *reinterpret_cast<uint4*>(tanch + dst) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
         }
         base += (int64_t)__popc(m) * kChunk;
@@ -106,12 +123,13 @@ cudaError_t launch_tile_layout(const int64_t* off, int64_t n_loci, int32_t* dept
     if (blocks) tile_layout_kernel<<<blocks, threads, 0, stream>>>(off, n_loci, depth, tile_chunks, max_depth);
     return cudaGetLastError();
 }
-cudaError_t launch_tile_scatter(const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci, const int64_t* tile_base,
-                                const uint8_t* ref_base, int min_bq, uint8_t* tcode, uint8_t* tqual, uint8_t* tanch, int32_t* pad, cudaStream_t stream) {
+cudaError_t launch_tile_scatter(const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci, int32_t tile0, int32_t n_tiles,
+                                int64_t entry_base, const int64_t* tile_base, const uint8_t* ref_base, int min_bq, uint8_t* tcq, uint8_t* tanch, int32_t* pad,
+                                uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, cudaStream_t stream) {
     const int threads = 256;
-    const int64_t n_tiles = (n_loci + kTileLoci - 1) / kTileLoci;
-    const unsigned blocks = (unsigned)((n_tiles * 32 + threads - 1) / threads);
-    if (blocks) tile_scatter_kernel<<<blocks, threads, 0, stream>>>(off, code, qual, anch, n_loci, tile_base, ref_base, min_bq, tcode, tqual, tanch, pad);
+    const unsigned blocks = (unsigned)(((int64_t)n_tiles * 32 + threads - 1) / threads);
+    if (blocks) tile_scatter_kernel<<<blocks, threads, 0, stream>>>(off, code, qual, anch, n_loci, tile0, n_tiles, entry_base, tile_base, ref_base, min_bq, tcq, tanch, pad, exc_entries, exc_count,
+                                                                 exc_capacity);
     return cudaGetLastError();
 }
 
@@ -283,17 +301,20 @@ __device__ __forceinline__ void store_record(pb2_call_record* dst, const pb2_cal
 // score and emit its reference allele in place.
 constexpr int kCtaPending = 64;   // per-CTA queue of the vertical-counter kernel: 64 loci x 4 alleles = one 256-thread scoring pass
 
-__device__ __forceinline__ void finish_locus(const LocusCounts& lc, int any, int64_t locus, int ref_allele, const TilePileup& in, const HotInputsExtra& ex,
-                                             const HotOutputs& out, const DeviceConfig& cfg, PendingLocus* cta_queue = nullptr, int* cta_count = nullptr) {
+// The counts arrive as a plain array indexed with compile-time constants only, so they stay in registers: LocusCounts (whose address the out-of-line
+// scorer takes) is built inside the branches that need it, not for every locus (that cost 129 MB of local-memory stores per million loci).
+__device__ __forceinline__ void finish_locus(const int (&cnt)[kNumAlleles][kNumDirs], double qsum, int any, int64_t locus, int ref_allele, const TilePileup& in,
+                                             const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, PendingLocus* cta_queue = nullptr,
+                                             int* cta_count = nullptr) {
     const int gapped = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
     unsigned cand_mask = 0;
     if (ref_allele != AT_N && cfg.snv_from_counts) {
         int total = 0;
 #pragma unroll
-        for (int d = 0; d < 3; d++) total += lc.c[AT_A][d] + lc.c[AT_C][d] + lc.c[AT_G][d] + lc.c[AT_T][d] + lc.c[AT_DEL][d];
+        for (int d = 0; d < 3; d++) total += cnt[AT_A][d] + cnt[AT_C][d] + cnt[AT_G][d] + cnt[AT_T][d] + cnt[AT_DEL][d];
 #pragma unroll
         for (int alt = 0; alt < 4; alt++) {
-            const int sup = lc.c[alt][0] + lc.c[alt][1] + lc.c[alt][2];
+            const int sup = cnt[alt][0] + cnt[alt][1] + cnt[alt][2];
             if (alt == ref_allele || sup == 0) continue;
             if (total < cfg.min_coverage && !cfg.output_gvcf) continue;
             if (total != 0 && allele_frequency(sup, total) < cfg.min_frequency) continue;
@@ -318,10 +339,10 @@ __device__ __forceinline__ void finish_locus(const LocusCounts& lc, int any, int
 #pragma unroll
             for (int a = 0; a < kNumAlleles; a++)
 #pragma unroll
-                for (int d = 0; d < kNumDirs; d++) pl.c[a * kNumDirs + d] = lc.c[a][d];
+                for (int d = 0; d < kNumDirs; d++) pl.c[a * kNumDirs + d] = cnt[a][d];
             pl.gapped = gapped;
             pl.pad_ = 0;
-            pl.qsum = lc.qsum;
+            pl.qsum = qsum;
             const uint4* sp = reinterpret_cast<const uint4*>(&pl);
             uint4* dp = reinterpret_cast<uint4*>(dst);
 #pragma unroll
@@ -333,6 +354,12 @@ __device__ __forceinline__ void finish_locus(const LocusCounts& lc, int any, int
         const bool emit = cfg.output_gvcf && !has_ext_variant && (cfg.have_intervals || any > 0);
         if (emit) {
             const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+            LocusCounts lc;
+#pragma unroll
+            for (int a = 0; a < kNumAlleles; a++)
+#pragma unroll
+                for (int d = 0; d < kNumDirs; d++) lc.c[a][d] = cnt[a][d];
+            lc.qsum = qsum;
             pb2_call_record r;
             score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex, r);
             store_record(out.ref_records + locus, r);
@@ -352,7 +379,7 @@ __device__ __forceinline__ uint32_t bins_of_word(uint32_t c4, uint32_t q4, uint3
     const uint32_t dr6 = ((c4 >> 3) & 0x03030303u) * 6u;            // per byte <= 12
     const uint32_t row4 = al4 + dr6;                                  // <= 17
     const uint32_t rowN4 = dr6 + 0x04040404u;                         // the N row of the same direction
-    const uint32_t g7 = ((q4 | 0x80808080u) - minbq4) & 0x80808080u;  // bit 7 of a byte set <=> q >= minBQ (no borrow crosses bytes: q | 0x80 >= 128 > minBQ)
+    const uint32_t g7 = (q4 - minbq4) & 0x80808080u;                  // bit 7 of a byte set <=> q >= minBQ (staged q carries bit 7: no borrow crosses bytes)
     const uint32_t m = (g7 - (g7 >> 7)) | g7;                         // 0xFF where q >= minBQ
     const uint32_t rs4 = (row4 & m) | (rowN4 & ~m);                   // RegionStateManager.cs:180-181: low quality -> N
     return rs4 * 11u + (a4 & 0x0f0f0f0fu);                            // per byte <= 197
@@ -372,7 +399,7 @@ __device__ __forceinline__ void count_word(uint32_t c4, uint32_t q4, uint32_t a4
     if (kWantQsum || kCollapsed) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const uint32_t code = (c4 >> (8 * k)) & 0xffu, q = (q4 >> (8 * k)) & 0xffu, an = (a4 >> (8 * k)) & 0xffu;
+            const uint32_t code = (c4 >> (8 * k)) & 0xffu, q = (q4 >> (8 * k)) & kQualMask, an = (a4 >> (8 * k)) & 0xffu;
             const int allele = code & 7;   // staged: A,G,C,T = 0..3, Del = 5, N = 7
             const bool usable = allele == AT_DEL || (allele < AT_N && (int)q >= min_bq);   // counted as something other than N (PADs are N)
             if (kWantQsum) { if (usable && allele != AT_DEL) qsum += q_lut[q]; }   // Σ over A,C,G,T (Deletion entries carry no base quality, :191)
@@ -410,7 +437,8 @@ __device__ __noinline__ void note_wraps(const uint4 wc, const uint4 wq, const ui
 // Cnt = uint8_t, 1024 threads: twice the resident warps for the same shared memory; wraps are caught per chunk and kept per row.
 template <typename Cnt, int kThreads, bool kWantQsum, bool kCollapsed>
 __global__ void __launch_bounds__(kThreads, 1)
-pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, DeviceConfig cfg, int* __restrict__ tile_counter) {
+pileup_count_score_kernel(const __grid_constant__ TilePileup in, const __grid_constant__ HotInputsExtra ex, const __grid_constant__ HotOutputs out,
+                          const __grid_constant__ DeviceConfig cfg, int* __restrict__ tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool kNarrow = sizeof(Cnt) == 1;
     constexpr int kHotThreads = kThreads;
@@ -457,7 +485,7 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
             const unsigned m = __ballot_sync(0xffffffffu, active);
             if (active) {
                 const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
-                nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o); na = ldg_stream(in.anch + o);
+                nc = ldg_stream(in.cq + base + o); nq = ldg_stream(in.cq + base + o + (int64_t)__popc(m) * kChunk); na = ldg_stream(in.anch + o);
             }
             base += (int64_t)__popc(m) * kChunk;
         }
@@ -471,11 +499,11 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
                 const unsigned m = __ballot_sync(0xffffffffu, active);
                 if (active) {
                     const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
-                    nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o); na = ldg_stream(in.anch + o);
+                    nc = ldg_stream(in.cq + base + o); nq = ldg_stream(in.cq + base + o + (int64_t)__popc(m) * kChunk); na = ldg_stream(in.anch + o);
                 }
                 base += (int64_t)__popc(m) * kChunk;
                 const int64_t pf = min(base + lane * kChunk, in.plane_bytes - kChunk);
-                prefetch_l2(in.code + pf); prefetch_l2(in.qual + pf); prefetch_l2(in.anch + pf);
+                prefetch_l2(in.cq + 2 * pf); prefetch_l2(in.cq + 2 * pf + 512); prefetch_l2(in.anch + pf);
                 asm volatile("" ::: "memory");   // keep the histogram traffic below the loads
             }
             uint32_t wrap_acc = 0;
@@ -484,24 +512,10 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
             count_word<Cnt, kThreads, kWantQsum, kCollapsed>(wc.z, wq.z, wa.z, minbq4, my, q_lut, cfg.min_bq, qsum, wrap_acc);
             count_word<Cnt, kThreads, kWantQsum, kCollapsed>(wc.w, wq.w, wa.w, minbq4, my, q_lut, cfg.min_bq, qsum, wrap_acc);
             if (kNarrow) { if (wrap_acc & 0x100u) note_wraps<kThreads>(wc, wq, wa, minbq4, reinterpret_cast<const uint8_t*>(my), my_wraps); }
-            // flagged entries (rare after staging normalisation): SNV-candidate bookkeeping the counts cannot express -> side list
-            if (((wc.x | wc.y | wc.z | wc.w) & 0xe0e0e0e0u) != 0) {
-                const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w}, aw[4] = {wa.x, wa.y, wa.z, wa.w};
-                for (int k = 0; k < kChunk; k++) {
-                    const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-                    if ((code & 0xe0u) == 0) continue;
-                    const unsigned long long slot = atomicAdd(out.exc_count, 1ull);
-                    if ((int64_t)slot < out.exc_capacity) {
-                        out.exc_entries[2 * slot] = (uint32_t)locus;
-                        out.exc_entries[2 * slot + 1] = code | (((qw[k >> 2] >> ((k & 3) * 8)) & 0xffu) << 8) | (((aw[k >> 2] >> ((k & 3) * 8)) & 0xffu) << 16);
-                    }
-                }
-            }
         }
 
         // ---- read the histogram out (and clear it for the next tile)
-        LocusCounts lc;
-        lc.qsum = qsum;
+        int cnt[kNumAlleles][kNumDirs];
         int any = 0;
         const int npad = (have_locus ? in.pad[locus] : 0) + extra_pad;
 #pragma unroll
@@ -519,7 +533,7 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
                     s += v;
                 }
                 if (kNarrow) { s += 256 * (int)my_wraps[(a + 6 * d) * kThreads]; my_wraps[(a + 6 * d) * kThreads] = 0; }
-                lc.c[a][d] = s;
+                cnt[a][d] = s;
                 any += s;
             }
         if (kCollapsed) {
@@ -532,7 +546,7 @@ pileup_count_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Devi
         }
         if (!have_locus) continue;
 
-        finish_locus(lc, any, locus, ref_allele, in, ex, out, cfg);
+        finish_locus(cnt, qsum, any, locus, ref_allele, in, ex, out, cfg);
     }
 }
 
@@ -580,20 +594,6 @@ __device__ __forceinline__ void score_queued_locus(const PendingLocus* item /* n
     }
 }
 
-__device__ __noinline__ void note_flagged_words(const uint4 wc, const uint4 wq, uint32_t locus, uint32_t* __restrict__ exc_entries,
-                                                unsigned long long* __restrict__ exc_count, int64_t exc_capacity) {
-    const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w};
-    for (int k = 0; k < kChunk; k++) {
-        const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-        if ((code & 0xe0u) == 0) continue;
-        const unsigned long long slot = atomicAdd(exc_count, 1ull);
-        if ((int64_t)slot < exc_capacity) {
-            exc_entries[2 * slot] = locus;
-            exc_entries[2 * slot + 1] = code | (((qw[k >> 2] >> ((k & 3) * 8)) & 0xffu) << 8);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ the hot kernel: vertical counters
 // Point alleles (Reference, SNV) only ever read anchor-summed counts (CoverageCalculator.CalculateSinglePoint, RegionState.GetAllCandidates), so
 // this kernel counts 18 rows (allele x direction) [+ 8 collapsed-read types] instead of 198 bins and keeps them in REGISTERS as bit-sliced
@@ -610,10 +610,14 @@ __device__ __forceinline__ void csa(uint32_t& sum, uint32_t& carry, uint32_t a, 
 // Rows of four entries after the quality rule, byte-parallel. Staged code bytes carry allele' | direction << 3 in their low 5 bits with N staged
 // as 7, so row = direction * 8 + allele' is the low 5 bits as they are and `q < minBQ -> N` (RegionStateManager.cs:180-181) is an OR with 7.
 // The ALU pipe (LOP3/SHF) is this kernel's bottleneck: the subtract and the x7 are written as multiplies to run on the FMA pipe.
-__device__ __forceinline__ uint32_t rows_of_word(uint32_t c4, uint32_t q4, uint32_t minbq4) {
-    const uint32_t d = (q4 | 0x80808080u) + (0u - minbq4);          // bit 7 of a byte set <=> q >= minBQ (no borrow crosses bytes)
-    const uint32_t low = ~(d >> 7) & 0x01010101u;                   // 1 where q < minBQ
-    return (c4 & 0x1f1f1f1fu) | (low * 7u);
+__device__ __forceinline__ uint32_t rows_of_word(uint32_t c4, uint32_t q4, uint32_t neg_minbq4, uint32_t one) {
+    // staged q carries bit 7: after the subtract bit 7 of a byte is set <=> q >= minBQ. Written as q * one + (-minBQ) with a run-time `one` so that it
+    // issues on the FMA pipe (IMAD) instead of the saturated ALU pipe (IADD3).
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(q4), "r"(one), "r"(neg_minbq4));
+    uint32_t ok;                                                    // PRMT with sign replication (selector nibbles 8..b; __byte_perm masks them off):
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(ok) : "r"(d), "r"(0u), "r"(0xba98u));   // 0xFF where q >= minBQ, 0x00 where the base becomes N
+    return c4 | (~ok & 0x07070707u);                                // the flag bits 5-7 stay in the bytes: every consumer looks at the low 5 (or 3) bits only
 }
 template <bool kCollapsed>
 __device__ __forceinline__ uint32_t onehot(uint32_t rows4, uint32_t a4, int k) {
@@ -644,9 +648,10 @@ __device__ __forceinline__ int vcount_row(const uint32_t (&P)[NP], int r) {
     return (int)v;
 }
 
-template <int NP, bool kWantQsum, bool kCollapsed>
-__global__ void __launch_bounds__(256, 4)
-pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, DeviceConfig cfg, int* __restrict__ tile_counter) {
+template <int NP, bool kWantQsum, bool kCollapsed, int kCtasPerSm, int kPf = 0>
+__global__ void __launch_bounds__(256, kCtasPerSm)
+pileup_vcount_score_kernel(const __grid_constant__ TilePileup in, const __grid_constant__ HotInputsExtra ex, const __grid_constant__ HotOutputs out,
+                           const __grid_constant__ DeviceConfig cfg, int* __restrict__ tile_counter) {
     __shared__ int s_tile[8];
     __shared__ double q_lut[kWantQsum ? 256 : 1];
     __shared__ __align__(16) PendingLocus s_pend[kCtaPending];
@@ -658,7 +663,8 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
         for (int q = threadIdx.x; q < 256; q += blockDim.x) q_lut[q] = pow(10.0, (double)((float)(-q) / 10.0f));  // RegionStateManager.cs:191 (float exponent)
     }
     __syncthreads();
-    const uint32_t minbq4 = (uint32_t)cfg.min_bq * 0x01010101u;
+    const uint32_t neg_minbq4 = 0u - (uint32_t)cfg.min_bq * 0x01010101u;
+    const uint32_t one = cfg.one;   // 1, read from the constant bank: opaque to the compiler, costs no register
 
     while (true) {
         if (lane == 0) s_tile[warp] = atomicAdd(tile_counter, 1);
@@ -681,8 +687,8 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
 
         // One 16-entry chunk into the planes below weight 16; returns the weight-16 carry (rippled by the caller, every second chunk in phase 1).
         auto add_chunk = [&](const uint4& wc, const uint4& wq, const uint4& wa) -> uint32_t {
-            const uint32_t r0 = rows_of_word(wc.x, wq.x, minbq4), r1 = rows_of_word(wc.y, wq.y, minbq4), r2 = rows_of_word(wc.z, wq.z, minbq4),
-                           r3 = rows_of_word(wc.w, wq.w, minbq4);
+            const uint32_t r0 = rows_of_word(wc.x, wq.x, neg_minbq4, one), r1 = rows_of_word(wc.y, wq.y, neg_minbq4, one),
+                           r2 = rows_of_word(wc.z, wq.z, neg_minbq4, one), r3 = rows_of_word(wc.w, wq.w, neg_minbq4, one);
             // weight 1: P[0] + 16 one-hot words -> P[0] and eight weight-2 carries
             uint32_t s0, s1, s2, s3, s4, t0, t1, k0, k1, k2, k3, k4, k5, k6, k7;
             csa(s0, k0, onehot<kCollapsed>(r0, wa.x, 0), onehot<kCollapsed>(r0, wa.x, 1), onehot<kCollapsed>(r0, wa.x, 2));
@@ -710,12 +716,10 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
                 const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
                 for (int k = 0; k < kChunk; k++) {
-                    const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu, q = (qw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                    const uint32_t code = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu, q = (qw[k >> 2] >> ((k & 3) * 8)) & kQualMask;
                     if ((code & 7) < AT_N && (int)q >= cfg.min_bq) qsum += q_lut[q];
                 }
             }
-            // flagged entries (rare after staging normalisation): SNV-candidate bookkeeping the counts cannot express -> side list
-            if (((wc.x | wc.y | wc.z | wc.w) & 0xe0e0e0e0u) != 0) note_flagged_words(wc, wq, (uint32_t)locus, out.exc_entries, out.exc_count, out.exc_capacity);
             return carry;
         };
         auto ripple = [&](uint32_t carry, int from) {
@@ -728,28 +732,44 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
         // per iteration so that their weight-16 carries meet in one more compressor and the ripple through the high planes runs half as often.
         const int min_chunks = __reduce_min_sync(0xffffffffu, nchunks);
         {
-            constexpr int kStep = kTileLoci * kChunk;
-            const uint8_t* pc = in.code + base + lane * kChunk;
-            const uint8_t* pq = in.qual + base + lane * kChunk;
+            constexpr int kStep = kTileLoci * kChunk;   // bytes of one full step in one plane; code and quality share a plane: 2 * kStep per step there
+            const uint8_t* pc = in.cq + 2 * base + lane * kChunk;
             const uint8_t* pa = in.anch + base + lane * kChunk;
             uint4 nc = make_uint4(0, 0, 0, 0), nq = nc, na = nc;
-            if (min_chunks > 0) { nc = ldg_stream(pc); nq = ldg_stream(pq); if (kCollapsed) na = ldg_stream(pa); }
-            auto step = [&](bool more) -> uint32_t {
+            if (min_chunks > 0) { nc = ldg_stream(pc); nq = ldg_stream(pc + kStep); if (kCollapsed) na = ldg_stream(pa); }
+            // chunk j of the current iteration: the next chunk goes into the registers, the one after it into L2, then this one is counted
+            auto step = [&](int j, bool more) -> uint32_t {
                 const uint4 wc = nc, wq = nq, wa = na;
-                pc += kStep; pq += kStep; if (kCollapsed) pa += kStep;
-                if (more) { nc = ldg_stream(pc); nq = ldg_stream(pq); if (kCollapsed) na = ldg_stream(pa); }
-                prefetch_l2(pc + kStep); prefetch_l2(pq + kStep); if (kCollapsed) prefetch_l2(pa + kStep);   // the planes carry 2 KB of slack
+                if (more) { nc = ldg_stream(pc + (j + 1) * 2 * kStep); nq = ldg_stream(pc + (j + 1) * 2 * kStep + kStep); if (kCollapsed) na = ldg_stream(pa + (j + 1) * kStep); }
+                // kPf steps ahead into L2 (the planes carry slack for the prefetches past the last tile)
+                if (kPf > 0) { prefetch_l2(pc + (j + kPf) * 2 * kStep); prefetch_l2(pc + (j + kPf) * 2 * kStep + kStep); if (kCollapsed) prefetch_l2(pa + (j + kPf) * kStep); }
                 return add_chunk(wc, wq, wa);
             };
+            auto advance = [&](int n) { pc += n * 2 * kStep; if (kCollapsed) pa += n * kStep; };
             int c = 0;
+            // four chunks per iteration: the weight-16 carries pair up into weight 32, those into weight 64, and only that one ripples through the high
+            // planes (a quarter of the ripples); the plane pointers advance once, the loads use immediate offsets
+            for (; c + 4 <= min_chunks; c += 4) {
+                uint32_t ca = step(0, true);
+                uint32_t cb = step(1, true);
+                uint32_t c32a, c32b, c64;
+                csa(P[4], c32a, ca, cb, P[4]);
+                ca = step(2, true);
+                cb = step(3, c + 4 < min_chunks);
+                csa(P[4], c32b, ca, cb, P[4]);
+                csa(P[5], c64, c32a, c32b, P[5]);
+                ripple(c64, 6);
+                advance(4);
+            }
             for (; c + 2 <= min_chunks; c += 2) {
-                const uint32_t ca = step(true);
-                const uint32_t cb = step(c + 2 < min_chunks);
+                const uint32_t ca = step(0, true);
+                const uint32_t cb = step(1, c + 2 < min_chunks);
                 uint32_t c32;
                 csa(P[4], c32, ca, cb, P[4]);
                 ripple(c32, 5);
+                advance(2);
             }
-            if (c < min_chunks) ripple(step(false), 4);
+            if (c < min_chunks) ripple(step(0, false), 4);
             base += (int64_t)min_chunks * kStep;
         }
 
@@ -762,7 +782,7 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
                 const unsigned m = __ballot_sync(0xffffffffu, active);
                 if (active) {
                     const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
-                    nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o);
+                    nc = ldg_stream(in.cq + base + o); nq = ldg_stream(in.cq + base + o + (int64_t)__popc(m) * kChunk);
                     if (kCollapsed) na = ldg_stream(in.anch + o);
                 }
                 base += (int64_t)__popc(m) * kChunk;
@@ -777,7 +797,7 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
                     const unsigned m = __ballot_sync(0xffffffffu, active);
                     if (active) {
                         const int64_t o = base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
-                        nc = ldg_stream(in.code + o); nq = ldg_stream(in.qual + o);
+                        nc = ldg_stream(in.cq + base + o); nq = ldg_stream(in.cq + base + o + (int64_t)__popc(m) * kChunk);
                         if (kCollapsed) na = ldg_stream(in.anch + o);
                     }
                     base += (int64_t)__popc(m) * kChunk;
@@ -787,18 +807,17 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
         }
 
         // ---- read the vertical counters out
-        LocusCounts lc;
-        lc.qsum = qsum;
+        int cnt[kNumAlleles][kNumDirs];
         int any = 0;
         const int npad = (have_locus ? in.pad[locus] : 0) + extra_pad;
 #pragma unroll
         for (int a = 0; a < kNumAlleles; a++)
 #pragma unroll
             for (int d = 0; d < kNumDirs; d++) {
-                int cnt = vcount_row<NP>(P, d * 8 + (a == AT_N ? (int)kStagedN : a));
-                if (a == AT_N && d == DIR_F) cnt -= npad;
-                lc.c[a][d] = cnt;
-                any += cnt;
+                int v = vcount_row<NP>(P, d * 8 + (a == AT_N ? (int)kStagedN : a));
+                if (a == AT_N && d == DIR_F) v -= npad;
+                cnt[a][d] = v;
+                any += v;
             }
         if (kCollapsed) {
             if (out.collapsed_out != nullptr && have_locus) {
@@ -808,7 +827,7 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
         }
         if (!have_locus) continue;
         const int ref_allele = allele_of_base(in.ref_base[locus]);
-        finish_locus(lc, any, locus, ref_allele, in, ex, out, cfg, s_pend, &s_pend_n);
+        finish_locus(cnt, qsum, any, locus, ref_allele, in, ex, out, cfg, s_pend, &s_pend_n);
     }
 
     // ---- the CTA's queued loci: 4 lanes per locus, all 256 threads at once. Other CTAs of this SM are still counting, so this FP64 latency
@@ -823,7 +842,8 @@ pileup_vcount_score_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, Dev
 
 // One thread per queued locus: the full ProcessVariant + genotype chain for its SNV candidates in (ref, alt) order (AlleleCaller.cs:172-176),
 // then the reference allele if nothing was called there (:146-147).
-__global__ void __launch_bounds__(128) score_pending_kernel(TilePileup in, HotInputsExtra ex, HotOutputs out, DeviceConfig cfg) {
+__global__ void __launch_bounds__(128) score_pending_kernel(const __grid_constant__ TilePileup in, const __grid_constant__ HotInputsExtra ex,
+                                                            const __grid_constant__ HotOutputs out, const __grid_constant__ DeviceConfig cfg) {
     const unsigned long long n = min(*out.pending_count, (unsigned long long)out.pending_capacity);
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
         const PendingLocus pl = out.pending[i];
@@ -877,18 +897,28 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
     if (out.counts_out == nullptr && max_depth + 2 * kChunk < (1 << 16)) {
         // the hot path: vertical counters in registers; planes needed = bits of the largest row count (entries + PADs of a locus)
         const int need = max_depth + 2 * kChunk;
-        const int grid = max(1, min(num_sms * 4, (in.n_tiles + 7) / 8));
-#define PB2_VLAUNCH(NP)                                                                                                        \
-    do {                                                                                                                       \
-        if (want_q && coll) pileup_vcount_score_kernel<NP, true, true><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);    \
-        else if (want_q) pileup_vcount_score_kernel<NP, true, false><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);      \
-        else if (coll) pileup_vcount_score_kernel<NP, false, true><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);        \
-        else pileup_vcount_score_kernel<NP, false, false><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);                 \
+        const int ctas = cfg.tune_ctas_per_sm == 3 ? 3 : 4;
+        const int grid = max(1, min(num_sms * ctas, (in.n_tiles + 7) / 8));
+#define PB2_VLAUNCH2(NP, Q, C)                                                                                                     \
+    do {                                                                                                                           \
+        if (NP == 10 && !Q && !C && cfg.tune_prefetch == 2) pileup_vcount_score_kernel<10, false, false, 4, 2><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter); \
+        else if (NP == 10 && !Q && !C && cfg.tune_prefetch == 3) pileup_vcount_score_kernel<10, false, false, 4, 3><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter); \
+        else if (NP == 10 && !Q && !C && cfg.tune_prefetch == 4) pileup_vcount_score_kernel<10, false, false, 4, 4><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter); \
+        else if (ctas == 3) pileup_vcount_score_kernel<NP, Q, C, 3><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);     \
+        else pileup_vcount_score_kernel<NP, Q, C, 4><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);                    \
+    } while (0)
+#define PB2_VLAUNCH(NP)                                   \
+    do {                                                  \
+        if (want_q && coll) PB2_VLAUNCH2(NP, true, true); \
+        else if (want_q) PB2_VLAUNCH2(NP, true, false);   \
+        else if (coll) PB2_VLAUNCH2(NP, false, true);     \
+        else PB2_VLAUNCH2(NP, false, false);              \
     } while (0)
         if (need < (1 << 10)) PB2_VLAUNCH(10);
         else if (need < (1 << 12)) PB2_VLAUNCH(12);
         else PB2_VLAUNCH(16);
 #undef PB2_VLAUNCH
+#undef PB2_VLAUNCH2
     } else {
         // general 198-bin variant (16-bit shared-memory histograms): pb2_get_counts, or loci deeper than 65 k entries are rejected by the caller
         const size_t smem = hot_kernel_smem_bytes(false, coll);

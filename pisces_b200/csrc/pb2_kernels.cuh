@@ -31,6 +31,9 @@ struct DeviceConfig {
     int sb_model, filter_single_strand;
     float no_call_filter;
     int output_gvcf, expect_stitched, expect_collapsed, have_intervals, want_qsum;
+    uint32_t one;           // always 1 (see rows_of_word)
+    int tune_prefetch;      // tuning experiments: 0 default (2 steps ahead), 1 none, 3, 4
+    int tune_ctas_per_sm;   // resident CTAs per SM of the hot kernel (launch bound -> register budget): 4 (64 registers) or 3 (85)
     int snv_from_counts;    // 1: SNV candidates = the counts (CallMNVs off); 0: SNVs are explicit candidates from the finder's state machine
     double vq_error_rate;   // MathOperations.QtoP(noise_level) (VariantQualityCalculator.cs:31)
     double sb_noise;        // Math.Pow(10, -1*noise_level/10f) (StrandBiasCalculator.cs:32)
@@ -38,9 +41,8 @@ struct DeviceConfig {
 
 // Device-resident, tile-interleaved pileup ("PTILE32").
 struct TilePileup {
-    const uint8_t* code;
-    const uint8_t* qual;
-    const uint8_t* anch;
+    const uint8_t* cq;          // code + quality plane: per tile step the 16-byte code chunks of the active lanes, then their quality chunks
+    const uint8_t* anch;        // anchor / collapsed-type plane (same chunk order, one chunk run per step)
     const int64_t* tile_base;   // [n_tiles] first byte of the tile in each plane (multiple of 16)
     const int32_t* depth;       // [n_loci] entries in the source pileup
     const int32_t* pad;         // [n_loci] PAD entries the staged locus carries (chunk tail + dropped low-quality deletions)
@@ -49,7 +51,7 @@ struct TilePileup {
     int32_t first_position;
     int64_t n_loci;
     int32_t n_tiles;
-    int64_t plane_bytes;        // size of each plane (multiple of 16, >= 16)
+    int64_t plane_bytes;        // size of the anchor plane (multiple of 16, >= 16); the code + quality plane is twice that
 };
 
 // A locus whose SNV candidates passed the cheap callability bars: scored by score_pending_kernel. 96 bytes.
@@ -95,8 +97,10 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
 // CSR -> PTILE32 staging
 cudaError_t launch_tile_layout(const int64_t* csr_offsets, int64_t n_loci, int32_t* depth, int64_t* tile_chunks /*[n_tiles]*/, int32_t* max_depth,
                                cudaStream_t stream);
-cudaError_t launch_tile_scatter(const int64_t* csr_offsets, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci,
-                                const int64_t* tile_base, const uint8_t* ref_base, int min_bq, uint8_t* tcode, uint8_t* tqual, uint8_t* tanch, int32_t* pad,
+// tiles [tile0, tile0 + n_tiles); code/qual/anch point at entry `entry_base` of the CSR planes (chunked staging)
+cudaError_t launch_tile_scatter(const int64_t* csr_offsets, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int64_t n_loci, int32_t tile0,
+                                int32_t n_tiles, int64_t entry_base, const int64_t* tile_base, const uint8_t* ref_base, int min_bq, uint8_t* tcq, uint8_t* tanch, int32_t* pad,
+                                uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity,
                                 cudaStream_t stream);
 cudaError_t exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* temp, size_t temp_bytes, size_t* temp_needed, cudaStream_t stream);
 

@@ -66,6 +66,28 @@ def test_reference_coverage_vectors_through_kernels(name):
     assert (a.ReferenceAllele, a.AlternateAllele) == (v["ref"], v["alt"])
 
 
+def _resident_records(sm):
+    """Device-resident results of pb2_call_resident (dense reference stream + compacted variant stream), copied back with torch."""
+    import ctypes as C
+    import torch
+    from pisces_b200 import _native as N
+
+    class DevBuf:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    rr, rv, vr = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nl, nv = C.c_int64(), C.c_int64()
+    sm._chk(sm._L.pb2_resident_results(sm._h, C.byref(rr), C.byref(rv), C.byref(nl), C.byref(vr), C.byref(nv)))
+    out = []
+    if nv.value:
+        out.append(np.frombuffer(torch.as_tensor(DevBuf(vr.value, nv.value * 96), device="cuda").cpu().numpy().tobytes(), dtype=N.RECORD_DTYPE))
+    if rr.value:
+        refs = np.frombuffer(torch.as_tensor(DevBuf(rr.value, nl.value * 96), device="cuda").cpu().numpy().tobytes(), dtype=N.RECORD_DTYPE)
+        valid = torch.as_tensor(DevBuf(rv.value, nl.value), device="cuda").cpu().numpy().astype(bool)
+        out.append(refs[valid])
+    return np.concatenate(out) if out else np.zeros(0, dtype=N.RECORD_DTYPE)
+
+
 def _pileup_indels_both(d, gvcf, **kw):
     pb = _pb()
     ref = bytes(d["ref_bases"].numpy()).decode()
@@ -85,12 +107,17 @@ def _pileup_indels_both(d, gvcf, **kw):
     sm = pb.GpuStateManager(pb.make_config(output_gvcf=gvcf, **pkw), "chr1", ref)
     sm.AddPileup(off, code, qual, anch, first_position=1)
     sm.AddCandidates(d["candidates"], arena)
-    # the resident (bench) path must produce the same number of variant records, on the first (plan-building) and on a replayed call
+    # the resident (bench) path must produce the same records, on the first (plan-building) call and on a replayed one (explicit pass on the side stream)
     n_res = sm.call_resident()
     assert sm.call_resident() == n_res
+    res = _resident_records(sm)
     precs = pb.GpuAlleleCaller().Call(sm, raw=True)
     parena = sm.AlleleArena()
     sm.close()
+    key = lambda r: (int(r["position"]), int(r["type"]), int(r["ref_len"]), int(r["alt_len"]), int(r["allele_bytes"]) if int(r["ref_len"]) + int(r["alt_len"]) <= 4 else -1)
+    assert sorted(bytes(r.tobytes()) for r in res if int(r["ref_len"]) + int(r["alt_len"]) <= 4) == \
+        sorted(bytes(r.tobytes()) for r in precs if int(r["ref_len"]) + int(r["alt_len"]) <= 4)
+    assert sorted(key(r) for r in res) == sorted(key(r) for r in precs)
     return oc.records(), precs, parena, n_res
 
 
