@@ -187,19 +187,25 @@ def main_ours(a):
         def __init__(self, ptr, nbytes):
             self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
-    cap_records = 1 << 16
-    gather_in = torch.zeros(cap_records * 96 + 8, dtype=torch.uint8, device=dev)
-    gather_out = torch.zeros(world * (cap_records * 96 + 8), dtype=torch.uint8, device=dev) if world > 1 else None
+    # ---- the single all-gather of per-interval call records (NCCL): [int64 count | records] per rank, fixed capacity. The variant stream of the
+    # staged segment lives at a fixed device address, so its torch view is created once; a step adds two small device copies and one collective.
+    gather_in = gather_out = var_view = count_pinned = None
+    if world > 1:
+        n0 = sm.call_resident()
+        cap_records = 1 << max(12, (2 * n0 - 1).bit_length())
+        vr, nv = C.c_void_p(), C.c_int64()
+        sm._chk(sm._L.pb2_resident_results(sm._h, None, None, None, C.byref(vr), C.byref(nv)))
+        var_view = torch.as_tensor(DevBuf(vr.value, cap_records * 96), device=dev)
+        gather_in = torch.zeros(8 + cap_records * 96, dtype=torch.uint8, device=dev)
+        gather_out = torch.zeros(world * (8 + cap_records * 96), dtype=torch.uint8, device=dev)
+        count_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
 
     def step():
         n = sm.call_resident()
-        if world > 1:   # the single all-gather of per-interval call records (variant stream; the dense gVCF stream stays sharded)
-            vr, nv = C.c_void_p(), C.c_int64()
-            sm._chk(sm._L.pb2_resident_results(sm._h, None, None, None, C.byref(vr), C.byref(nv)))
-            k = min(nv.value, cap_records)
-            if k:
-                gather_in[8:8 + k * 96].copy_(torch.as_tensor(DevBuf(vr.value, k * 96), device=dev))
-            gather_in[:8].copy_(torch.tensor([k], dtype=torch.int64, device=dev).view(torch.uint8))
+        if world > 1:
+            count_pinned[0] = min(n, cap_records)
+            gather_in[:8].copy_(count_pinned.view(torch.uint8), non_blocking=True)
+            gather_in[8:].copy_(var_view, non_blocking=True)
             dist.all_gather_into_tensor(gather_out, gather_in)
         return n
 

@@ -5,10 +5,33 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "pb2_internal.hpp"
 
 using namespace pb2;
+
+// PB2_TRACE=1: wall-clock breakdown of pushes and flushes on stderr (diagnostics only)
+#include <chrono>
+static bool trace_on() { static const bool on = getenv("PB2_TRACE") != nullptr; return on; }
+struct Trace {
+    const char* what;
+    std::chrono::steady_clock::time_point t0, last;
+    std::string line;
+    explicit Trace(const char* w) : what(w), t0(std::chrono::steady_clock::now()), last(t0) {}
+    void mark(const char* label) {
+        if (!trace_on()) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof buf, " %s=%.2fms", label, std::chrono::duration<double, std::milli>(now - last).count());
+        line += buf;
+        last = now;
+    }
+    ~Trace() {
+        if (!trace_on()) return;
+        fprintf(stderr, "[pb2] %s total=%.2fms%s\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), line.c_str());
+    }
+};
 
 #define CU(h, expr)                                                                                      \
     do {                                                                                                 \
@@ -213,6 +236,7 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     if (p->n_loci > (int64_t)1 << 31) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: more than 2^31 loci in one push");
     if (!p->ref_bases && !p->positions && (h->chr_len == 0)) return fail(h, PB2_ERR_STATE, "pb2_push_pileup: no ref_bases given and no reference set");
     CU(h, cudaSetDevice(h->device));
+    Trace tr("push_pileup");
     cudaStream_t st = h->stream;
     Segment s;
     s.n_loci = p->n_loci;
@@ -274,6 +298,7 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     CU(h, exclusive_scan_i64(tile_bytes, s.tile_base, s.n_tiles + 1, temp, temp_bytes, nullptr, st));
     CU(h, cudaMemcpyAsync(&s.plane_bytes, s.tile_base + s.n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
+    tr.mark("layout");
     if (s.max_depth >= 65000) return fail(h, PB2_ERR_UNSUPPORTED, "pb2_push_pileup: a locus with 65000 or more entries (16-bit counters)");
     const size_t pb = (size_t)std::max<int64_t>(s.plane_bytes, 16) + 4096;   // slack: the hot kernel prefetches up to two steps past a tile
     s.alloc_plane = pb;
@@ -334,6 +359,7 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
         for (int b = 0; b < n_buf; b++) for (int k = 0; k < 3; k++) pool_free(h, stage[b][k]);
     }
 
+    tr.mark("enqueue_chunks");
     // outputs
     if (h->cfg.output_gvcf) {
         s.alloc_ref = sizeof(pb2_call_record) * (size_t)p->n_loci;
@@ -350,6 +376,7 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     pool_free(h, temp);
     pool_free(h, tmp_off);
     CU(h, cudaStreamSynchronize(st));   // the caller's buffers are consumed when this returns
+    tr.mark("copy+scatter");
     h->segs.push_back(std::move(s));
     return PB2_OK;
 }
@@ -620,11 +647,10 @@ static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std:
     static const char base_of[4] = {'A', 'G', 'C', 'T'};
     // emitted SNV records by (position, alt) for lookup; flagged entries of alleles that were not called cannot change anything
     // (a split of a non-callable candidate is non-callable too: less support means a lower frequency and a lower q-score)
-    std::vector<std::pair<uint64_t, const pb2_call_record*>> index;
-    index.reserve(vars.size());
+    std::unordered_map<uint64_t, const pb2_call_record*> index;   // (position, alt) is unique among SNV records
+    index.reserve(vars.size() * 2);
     for (auto& v : vars)
-        if (v.type == CAT_SNV) index.push_back({((uint64_t)(uint32_t)v.position << 8) | ((v.allele_bytes >> 8) & 0xff), &v});
-    std::sort(index.begin(), index.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        if (v.type == CAT_SNV) index.emplace(((uint64_t)(uint32_t)v.position << 8) | ((v.allele_bytes >> 8) & 0xff), &v);
     auto key_of = [&](uint32_t locus, int allele) {
         const int32_t pos = s.has_positions ? s.h_positions[locus] : s.first_position + (int32_t)locus;
         return ((uint64_t)(uint32_t)pos << 8) | (uint8_t)base_of[allele & 3];
@@ -635,9 +661,7 @@ static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std:
         for (size_t i = 0; i + 1 < exc.size(); i += 2) {
             const int allele = (int)(exc[i + 1] & 7);
             if (allele > 3) continue;
-            const uint64_t key = key_of(exc[i], allele);
-            auto it = std::lower_bound(index.begin(), index.end(), key, [](const auto& a, uint64_t k) { return a.first < k; });
-            if (it == index.end() || it->first != key) continue;
+            if (index.find(key_of(exc[i], allele)) == index.end()) continue;
             items.push_back({Key{exc[i], allele}, exc[i + 1] & 0xffu});
         }
         std::sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
@@ -652,9 +676,8 @@ static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std:
         }
     }
     for (auto& g : groups) {
-        const uint64_t key = key_of(g.first.locus, g.first.allele);
-        auto it = std::lower_bound(index.begin(), index.end(), key, [](const auto& a, uint64_t k) { return a.first < k; });
-        for (; it != index.end() && it->first == key; ++it) {
+        auto it = index.find(key_of(g.first.locus, g.first.allele));
+        if (it != index.end()) {
             const pb2_call_record& v = *it->second;
             const Acc& a = g.second;
             if (a.nocand > 0) return fail(h, PB2_ERR_UNSUPPORTED, "called SNV has support from '='/'X' operations: explicit-candidate path not built yet");
@@ -789,6 +812,7 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
 extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n) {
     if (!h || !out || !n) return fail(h, PB2_ERR_ARG, "pb2_flush: null argument");
     CU(h, cudaSetDevice(h->device));
+    Trace tr("flush");
     h->h_out.clear();
     h->arena.clear();
     const bool reads_path = h->reads.size() != 0 || !h->triggers.empty();
@@ -802,6 +826,7 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
         const int rc = stage_reads_segment(h, up_to_position < 0 ? INT32_MAX : up_to_position, h->cleared_through + 1);
         if (rc != PB2_OK) return rc;
     }
+    tr.mark("stage_reads");
     // explicit candidates first: their gapped-MNV reference counts feed the point alleles of the hot kernel
     std::vector<pb2_call_record> explicit_called;
     int32_t cleared_to = cleared_end;
@@ -810,6 +835,7 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
         if (rc != PB2_OK) return rc;
         if (!reads_path) cleared_to = INT32_MAX;
     }
+    tr.mark("explicit");
     std::vector<uint8_t> explicit_used(explicit_called.size(), 0);
     for (auto& s : h->segs) {
         if (!s.called) {
@@ -832,6 +858,7 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
             CU(h, cudaMemcpyAsync(valid.data(), s.ref_valid, valid.size(), cudaMemcpyDeviceToHost, h->stream));
         }
         CU(h, cudaStreamSynchronize(h->stream));
+        tr.mark("hot+d2h");
         if (!exc.empty() && !h->cfg.call_mnvs) { const int rc = reconcile_flagged_entries(h, s, exc, vars); if (rc != PB2_OK) return rc; }
         // the explicit alleles called inside this segment's positions join its variant stream
         const int32_t seg_lo = s.has_positions ? (s.h_positions.empty() ? 1 : s.h_positions.front()) : s.first_position;
@@ -847,6 +874,10 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
         // merge the dense reference stream (already in position order) with the sorted variant stream; a reference allele is pruned wherever a
         // variant was called (AlleleCaller.cs:146-147)
         size_t vi = 0;
+        if (refs.empty() && ref_override.empty()) {   // no reference stream: the sorted variant stream is the output
+            while (vi < vars.size() && vars[vi].position <= cleared_to) h->h_out.push_back(vars[vi++]);
+            continue;
+        }
         for (int64_t i = 0; i < s.n_loci; i++) {
             const int32_t pos = s.has_positions ? s.h_positions[(size_t)i] : s.first_position + (int32_t)i;
             if (pos > cleared_to) break;
@@ -868,6 +899,7 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
             std::stable_sort(h->h_out.begin(), h->h_out.end(), [&](const pb2_call_record& a, const pb2_call_record& b) { return a.position < b.position; });
         }
     }
+    tr.mark("merge");
     // drop what this flush consumed: temporary segments, reads that end inside the cleared positions, dead candidates, used gapped counts
     for (size_t i = 0; i < h->segs.size();) {
         if (h->segs[i].temporary) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); } else i++;

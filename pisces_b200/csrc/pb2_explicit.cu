@@ -53,21 +53,22 @@ void explicit_add_candidate(pb2_handle* h, const HostCand& nc) {
 // ------------------------------------------------------------------------------------------------ device context of one batch
 namespace {
 
+// Device scratch of the explicit pass, from the handle's pool (stream-ordered: no cudaMalloc / cudaFree on the steady-state path).
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t reserve(size_t n, cudaStream_t st, bool keep = false) {
+    pb2_handle* owner = nullptr;
+    ~DevBuf() { if (p) { if (owner) cudaFreeAsync(p, owner->stream); else cudaFree(p); } }
+    cudaError_t reserve(size_t n, cudaStream_t st, bool keep = false, pb2_handle* h = nullptr) {
         if (n <= cap) return cudaSuccess;
         const size_t ncap = std::max<size_t>(n, cap * 2 + 64);
         T* np = nullptr;
-        cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+        cudaError_t e = h ? cudaMallocFromPoolAsync(reinterpret_cast<void**>(&np), ncap * sizeof(T), h->pool, st) : cudaMalloc(&np, ncap * sizeof(T));
         if (e != cudaSuccess) return e;
         if (keep && p && cap) e = cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (p) cudaFree(p);
-        p = np; cap = ncap;
+        if (p) { if (owner) cudaFreeAsync(p, st); else { cudaStreamSynchronize(st); cudaFree(p); } }
+        p = np; cap = ncap; owner = h;
         return e;
     }
 };
@@ -130,13 +131,13 @@ struct BatchCtx {
         }
         if (next == n_rows) return PB2_OK;
         cudaStream_t st = h->stream;
-        CUX(h, counts.reserve((size_t)next * kNumBins, st, true));
-        CUX(h, collapsed.reserve((size_t)next * kNumCollapsed, st, true));
-        if (want_q) CUX(h, qsum.reserve((size_t)next * kNumBins, st, true));
+        CUX(h, counts.reserve((size_t)next * kNumBins, st, true, h));
+        CUX(h, collapsed.reserve((size_t)next * kNumCollapsed, st, true, h));
+        if (want_q) CUX(h, qsum.reserve((size_t)next * kNumBins, st, true, h));
         // rows were numbered segment by segment in position order within this call; launch one gather per segment over its contiguous run
         std::vector<int32_t> loci((size_t)(next - n_rows), -1);
         for (auto& v : per_seg) for (auto& rl : v) loci[(size_t)(rl.first - n_rows)] = rl.second;
-        CUX(h, req.reserve(loci.size(), st));
+        CUX(h, req.reserve(loci.size(), st, false, h));
         CUX(h, cudaMemcpyAsync(req.p, loci.data(), loci.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         for (size_t si = 0; si < h->segs.size(); si++) {
             if (per_seg[si].empty()) continue;
@@ -218,8 +219,8 @@ int score_pieces(BatchCtx& ctx, const std::vector<Piece*>& pieces, std::vector<u
         d.locus = append_seg ? (int32_t)BatchCtx::locus_of(*append_seg, p.position) : -1;
     }
     cudaStream_t st = h->stream;
-    CUX(h, ctx.d_cands.reserve(n, st));
-    CUX(h, ctx.d_arena.reserve(arena.size() + 16, st));
+    CUX(h, ctx.d_cands.reserve(n, st, false, h));
+    CUX(h, ctx.d_arena.reserve(arena.size() + 16, st, false, h));
     CUX(h, cudaMemcpyAsync(ctx.d_cands.p, dc.data(), n * sizeof(DevCand), cudaMemcpyHostToDevice, st));
     CUX(h, cudaMemcpyAsync(ctx.d_arena.p, arena.data(), arena.size(), cudaMemcpyHostToDevice, st));
     CandScoreArgs a;
@@ -230,9 +231,9 @@ int score_pieces(BatchCtx& ctx, const std::vector<Piece*>& pieces, std::vector<u
     if (append_seg) {
         a.var_records = append_seg->var_records; a.var_count = append_seg->counters; a.var_capacity = append_seg->var_capacity; a.ref_valid = append_seg->ref_valid;
     } else {
-        CUX(h, ctx.d_out.reserve(n, st));
-        CUX(h, ctx.d_flags.reserve(n, st));
-        CUX(h, ctx.d_ingr.reserve(n, st));
+        CUX(h, ctx.d_out.reserve(n, st, false, h));
+        CUX(h, ctx.d_flags.reserve(n, st, false, h));
+        CUX(h, ctx.d_ingr.reserve(n, st, false, h));
         a.out_dense = ctx.d_out.p; a.out_callable = ctx.d_flags.p; a.out_ingredients = out_ingr ? ctx.d_ingr.p : nullptr;
     }
     CUX(h, launch_score_candidates(a, h->dcfg, st));
@@ -595,7 +596,7 @@ int explicit_call_resident(pb2_handle* h, Segment& seg, cudaStream_t side) {
         a.var_records = seg.var_records; a.var_count = seg.counters; a.var_capacity = seg.var_capacity;
         // replays run concurrently with the hot kernel: the scorer only flags what it called, explicit_prune_resident clears ref_valid afterwards
         a.ref_valid = nullptr;
-        CUX(h, plan->ctx.d_flags.reserve(ps.size(), st));
+        CUX(h, plan->ctx.d_flags.reserve(ps.size(), st, false, h));
         a.out_callable = plan->ctx.d_flags.p;
         return PB2_OK;
     }
