@@ -148,6 +148,7 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
         if ((e = cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return bail("cudaMemPoolSetAttribute", e);
     }
     if ((e = cudaMalloc(&h->d_tile_counter, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaHostAlloc(&h->h_counters, sizeof(unsigned long long) * 4, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
     {
         h->q_table_max = std::min(std::max(cfg->max_variant_qscore, 0), 1023);
         std::vector<double> t((size_t)h->q_table_max + 1);
@@ -166,6 +167,11 @@ static void pool_free(pb2_handle* h, void* p, size_t = 0) { if (p) cudaFreeAsync
 template <class T>
 static cudaError_t pool_alloc_t(pb2_handle* h, T** p, size_t count) { return pool_alloc(h, reinterpret_cast<void**>(p), count * sizeof(T)); }
 
+static void release_resident_graph(pb2_handle* h) {
+    if (h->resident_graph) { cudaGraphExecDestroy(h->resident_graph); h->resident_graph = nullptr; }
+    h->resident_graph_failed = false;
+}
+
 static void free_segment(pb2_handle* h, Segment& s) {
     void* ptrs[] = {s.code, s.anch, s.ref_records, s.var_records, s.pending, s.depth, s.pad, s.tile_base, s.ref_base, s.positions, s.ref_valid, s.exc_entries, s.counters};
     for (void* p : ptrs) pool_free(h, p);
@@ -183,6 +189,7 @@ extern "C" int pb2_reset(pb2_handle* h) {
     h->cands.clear(); h->block_max_endpoint.clear(); h->gapped_ref.clear(); h->triggers.clear(); h->arena.clear();
     h->last_trigger_key = 0; h->push_last_key = 0; h->cleared_through = 0;
     explicit_release_resident(h);
+    release_resident_graph(h);
     return PB2_OK;
 }
 
@@ -191,6 +198,7 @@ extern "C" void pb2_destroy(pb2_handle* h) {
     pb2_reset(h);
     if (h->d_chr) cudaFree(h->d_chr);
     if (h->d_tile_counter) cudaFree(h->d_tile_counter);
+    if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->d_q_to_p) cudaFree(h->d_q_to_p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -236,6 +244,7 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     if (p->n_loci > (int64_t)1 << 31) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: more than 2^31 loci in one push");
     if (!p->ref_bases && !p->positions && (h->chr_len == 0)) return fail(h, PB2_ERR_STATE, "pb2_push_pileup: no ref_bases given and no reference set");
     CU(h, cudaSetDevice(h->device));
+    release_resident_graph(h);
     Trace tr("push_pileup");
     cudaStream_t st = h->stream;
     Segment s;
@@ -385,7 +394,8 @@ extern "C" int pb2_push_pileup(pb2_handle* h, const pb2_pileup_csr* p) { return 
 extern "C" int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p) { return push_common(h, p, true); }
 
 // enqueue: counters reset, hot kernel (+ overflow scorer) between the timing events. finish: counters back, one synchronize, bookkeeping.
-static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out, const int32_t* d_gapped, bool reset_counters = true) {
+static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out, const int32_t* d_gapped, bool reset_counters = true,
+                           bool capturing = false) {
     cudaStream_t st = h->stream;
     TilePileup in;
     in.cq = s.code; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
@@ -398,15 +408,16 @@ static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32
     out.counts_out = counts_out; out.collapsed_out = collapsed_out;
     out.pending = s.pending; out.pending_count = s.counters + 2; out.pending_capacity = s.pending_capacity;
     if (reset_counters) CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 3, st));
-    CU(h, cudaEventRecord(h->ev0, st));
+    // inside a stream capture the timing events must be external event-record nodes to be readable with cudaEventElapsedTime
+    CU(h, cudaEventRecordWithFlags(h->ev0, st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, s.max_depth, st));
-    CU(h, cudaEventRecord(h->ev1, st));
+    CU(h, cudaEventRecordWithFlags(h->ev1, st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     return PB2_OK;
 }
-static int finish_segment(pb2_handle* h, Segment& s) {
+static int finish_segment(pb2_handle* h, Segment& s, bool counters_already_copied = false) {
     cudaStream_t st = h->stream;
-    unsigned long long cnt4[4];
-    CU(h, cudaMemcpyAsync(cnt4, s.counters, sizeof(cnt4), cudaMemcpyDeviceToHost, st));
+    unsigned long long* cnt4 = h->h_counters;
+    if (!counters_already_copied) CU(h, cudaMemcpyAsync(cnt4, s.counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     float ms = 0;
     CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -580,6 +591,55 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     return PB2_OK;
 }
 
+// One resident step over one segment: counters reset; the explicit pass (two small latency-bound kernels) on the side stream ahead of the hot kernel so
+// that it runs next to it; join; prune; counters to pinned memory. The sequence is captured once into a CUDA graph and replayed (one launch call per
+// step instead of a dozen API calls); if capture is not possible the same sequence is issued directly.
+static int resident_step_enqueue(pb2_handle* h, Segment& s, bool with_explicit, bool capturing) {
+    cudaStream_t st = h->stream;
+    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 3, st));
+    if (with_explicit) {
+        CU(h, cudaEventRecord(h->ev_scattered[0], st));
+        CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_scattered[0], 0));
+        const int rc = explicit_call_resident(h, s, h->copy_stream);
+        if (rc != PB2_OK) return rc;
+        CU(h, cudaEventRecord(h->ev_copied[0], h->copy_stream));
+    }
+    const int rc = enqueue_segment(h, s, nullptr, nullptr, nullptr, false, capturing);
+    if (rc != PB2_OK) return rc;
+    if (with_explicit) {
+        CU(h, cudaStreamWaitEvent(st, h->ev_copied[0], 0));
+        const int rc2 = explicit_prune_resident(h, s);
+        if (rc2 != PB2_OK) return rc2;
+    }
+    CU(h, cudaMemcpyAsync(h->h_counters, s.counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    return PB2_OK;
+}
+static int resident_step(pb2_handle* h, Segment& s, bool with_explicit) {
+    cudaStream_t st = h->stream;
+    if (h->resident_graph == nullptr && !h->resident_graph_failed) {
+        const int64_t launches_before = h->total_launches;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            ok = resident_step_enqueue(h, s, with_explicit, true) == PB2_OK;
+            ok = (cudaStreamEndCapture(st, &graph) == cudaSuccess) && ok && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&h->resident_graph, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        h->resident_graph_launches = h->total_launches - launches_before + 2;   // + hot kernel and overflow scorer (counted by finish_segment otherwise)
+        h->total_launches = launches_before;
+        if (!ok) { cudaGetLastError(); h->resident_graph = nullptr; h->resident_graph_failed = true; }
+    }
+    if (h->resident_graph != nullptr) {
+        CU(h, cudaGraphLaunch(h->resident_graph, st));
+        h->total_launches += h->resident_graph_launches - 2;
+    } else {
+        const int rc = resident_step_enqueue(h, s, with_explicit, false);
+        if (rc != PB2_OK) return rc;
+    }
+    return finish_segment(h, s, true);
+}
+
 extern "C" int pb2_call_resident(pb2_handle* h, int64_t* n_records) {
     if (!h) return PB2_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
@@ -594,22 +654,19 @@ extern "C" int pb2_call_resident(pb2_handle* h, int64_t* n_records) {
             rc = enqueue_segment(h, s, nullptr, nullptr, nullptr);
             if (rc == PB2_OK) rc = explicit_call_resident(h, s, h->stream);
         } else {
-            // the explicit pass (two small latency-bound kernels) goes to the side stream ahead of the hot kernel and runs next to it
-            cudaStream_t st = h->stream;
-            CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 3, st));
-            CU(h, cudaEventRecord(h->ev_scattered[0], st));
-            CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_scattered[0], 0));
-            rc = explicit_call_resident(h, s, h->copy_stream);
+            rc = resident_step(h, s, true);
             if (rc != PB2_OK) return rc;
-            CU(h, cudaEventRecord(h->ev_copied[0], h->copy_stream));
-            rc = enqueue_segment(h, s, nullptr, nullptr, nullptr, false);
-            if (rc != PB2_OK) return rc;
-            CU(h, cudaStreamWaitEvent(st, h->ev_copied[0], 0));
-            rc = explicit_prune_resident(h, s);
+            total = (int64_t)s.h_var_count;
+            if (n_records) *n_records = total;
+            return PB2_OK;
         }
         if (rc == PB2_OK) rc = finish_segment(h, s);
         if (rc != PB2_OK) return rc;
         total = (int64_t)s.h_var_count;
+    } else if (h->segs.size() == 1) {
+        const int rc = resident_step(h, h->segs[0], false);
+        if (rc != PB2_OK) return rc;
+        total = (int64_t)h->segs[0].h_var_count;
     } else {
         for (auto& s : h->segs) {
             int rc = run_segment(h, s, nullptr, nullptr);
@@ -951,6 +1008,7 @@ extern "C" int pb2_push_candidates(pb2_handle* h, const pb2_candidate* cands, in
         explicit_add_candidate(h, hc);
     }
     explicit_release_resident(h);
+    release_resident_graph(h);
     return PB2_OK;
 }
 

@@ -142,6 +142,10 @@ struct pb2_handle {
     int32_t last_trigger_key = 0;                     // RegionStateManager._lastUpToBlockKey
     int32_t push_last_key = 0;                        // the same, as seen while reads are pushed (which read positions open a batch)
     void* resident_explicit = nullptr;                // cached device plan of pb2_call_resident's explicit-candidate pass
+    cudaGraphExec_t resident_graph = nullptr;         // the whole resident step (both streams) as one CUDA graph, replayed by pb2_call_resident
+    bool resident_graph_failed = false;
+    int64_t resident_graph_launches = 0;              // kernels inside the graph
+    unsigned long long* h_counters = nullptr;         // pinned: the segment's counters after a step
     std::vector<uint8_t> arena;                       // allele bytes the last flush's records point into
     int64_t total_collapsed = 0;
 };
