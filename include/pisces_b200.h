@@ -80,7 +80,10 @@ typedef struct pb2_config {
     float   collapse_freq_threshold;     /* CollapseFreqThreshold (0) */
     float   collapse_freq_ratio_threshold; /* CollapseFreqRatioThreshold (0.5) */
     int32_t exclude_mnvs_from_collapsing;  /* ExcludeMNVsFromCollapsing (0) */
-    int32_t reserved[2];
+    int32_t skip_validation;             /* 1: take the option values as given, without the adjustments of VariantCallingParameters.Validate (:137-155) that
+                                            Program.Main applies (filters raised to their minimum values); the reference's own functional tests build
+                                            options by hand this way (SomaticVariantCallerFunctionalTests.cs:683-758) */
+    int32_t reserved[2];                 /* tuning knobs of bench.py; 0 in production */
 } pb2_config;
 
 /* Reads for IStateManager.AddAlleleCounts(Read) / ICandidateVariantFinder.FindCandidates(Read, ...), as a struct of arrays. Only
@@ -163,6 +166,16 @@ typedef struct pb2_call_record {
     double   gatk_bias_score;          /* StrandBiasResults.GATKBiasScore */
 } pb2_call_record;
 
+/* The rest of CalledAllele that does not fit the 96-byte record (CalledAllele.cs:7-140): one per record of the last pb2_flush, same order. 80 bytes.
+ * collapsed_mut is the candidate's ReadCollapsedCountsMut (explicit candidates; zero for count-based SNVs and reference alleles), collapsed_total is
+ * ReadCollapsedCountTotal (CollapsedCoverageCalculator.cs:18-37: the counts at the allele's position / start point; zero unless expect_collapsed). */
+typedef struct pb2_call_record_ext {
+    int32_t collapsed_mut[8];
+    int32_t collapsed_total[8];
+    int32_t well_anchored_support[3];  /* WellAnchoredSupportByDirection */
+    int32_t reserved;
+} pb2_call_record_ext;
+
 void pb2_default_config(pb2_config* cfg);
 int pb2_create(const pb2_config* cfg, pb2_handle** out);
 void pb2_destroy(pb2_handle* h);
@@ -197,6 +210,8 @@ int pb2_resident_results(pb2_handle* h, const pb2_call_record** ref_records, con
 /* IAlleleCaller.Call for everything staged up to up_to_position (-1 = all): runs pb2_call_resident if needed, copies the
  * records to the host ordered by (position, ref, alt) as AlleleCaller.cs:96-140,172-176 orders them. */
 int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n);
+/* The pb2_call_record_ext rows of the records the last pb2_flush returned (valid until the next flush). */
+int pb2_flush_ext(pb2_handle* h, const pb2_call_record_ext** out, int64_t* n);
 /* Parity hook = IAlleleSource.GetAlleleCount over a position range: out[n][6][3][11] int32 (RegionState._alleleCounts). */
 int pb2_get_counts(pb2_handle* h, int32_t position0, int32_t n, int32_t* out);
 /* Drop staged pileups and results (IStateManager.DoneProcessing). */

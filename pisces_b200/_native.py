@@ -19,7 +19,8 @@ class Config(C.Structure):
         ("tracked_anchor_size", C.c_int32), ("output_gvcf", C.c_int32), ("expect_stitched", C.c_int32), ("expect_collapsed", C.c_int32),
         ("want_sum_base_quality", C.c_int32), ("collapse", C.c_int32), ("call_mnvs", C.c_int32), ("indel_repeat_filter", C.c_int32),
         ("max_size_mnv", C.c_int32), ("max_gap_mnv", C.c_int32), ("collapse_freq_threshold", C.c_float),
-        ("collapse_freq_ratio_threshold", C.c_float), ("exclude_mnvs_from_collapsing", C.c_int32), ("reserved", C.c_int32 * 2)]
+        ("collapse_freq_ratio_threshold", C.c_float), ("exclude_mnvs_from_collapsing", C.c_int32), ("skip_validation", C.c_int32),
+        ("reserved", C.c_int32 * 2)]
 
 
 class PileupCsr(C.Structure):
@@ -61,8 +62,10 @@ RECORD_DTYPE = [("position", "<i4"), ("type", "u1"), ("genotype", "u1"), ("sb_fl
                 ("reference_support", "<i4"), ("num_no_calls", "<i4"), ("fraction_no_calls", "<f4"), ("allele_bytes", "<u4"),
                 ("ref_len", "<u2"), ("alt_len", "<u2"), ("sum_base_quality", "<f8"), ("bias_score", "<f8"), ("gatk_bias_score", "<f8")]
 
+RECORD_EXT_DTYPE = [("collapsed_mut", "<i4", (8,)), ("collapsed_total", "<i4", (8,)), ("well_anchored_support", "<i4", (3,)), ("reserved", "<i4")]
+
 EXPORTS = ["pb2_default_config", "pb2_create", "pb2_destroy", "pb2_last_error", "pb2_device_count", "pb2_set_reference", "pb2_set_intervals",
-           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_candidates", "pb2_allele_arena", "pb2_call_resident", "pb2_resident_results", "pb2_flush",
+           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_candidates", "pb2_allele_arena", "pb2_call_resident", "pb2_resident_results", "pb2_flush", "pb2_flush_ext",
            "pb2_get_counts", "pb2_reset", "pb2_stats", "pb2_stream", "pb2_totals"]
 
 _lib = None
@@ -94,6 +97,7 @@ def load():
     L.pb2_call_resident.argtypes = [H, C.POINTER(C.c_int64)]
     L.pb2_resident_results.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.pb2_flush.argtypes = [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.pb2_flush_ext.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.pb2_get_counts.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
     L.pb2_reset.argtypes = [H]
     L.pb2_stats.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]

@@ -86,11 +86,13 @@ static void derive_config(pb2_handle* h) {
     d.min_frequency = c.min_frequency;
     d.min_frequency_filter = c.min_frequency_filter < c.min_frequency ? c.min_frequency : c.min_frequency_filter;  // Validate :144-147
     d.target_lod = c.target_lod_frequency < d.min_frequency_filter ? d.min_frequency_filter : c.target_lod_frequency;  // :152-155
+    if (c.skip_validation) { d.min_frequency_filter = c.min_frequency_filter; d.target_lod = c.target_lod_frequency; }
     d.variant_freq_filter = d.min_frequency_filter > c.min_frequency ? d.min_frequency_filter : c.min_frequency;  // SomaticGenotyper.SetMinFreqFilter
     d.max_vq = c.max_variant_qscore; d.min_vq = c.min_variant_qscore; d.vq_filter = c.variant_qscore_filter;
     d.max_gq = c.max_genotype_qscore; d.min_gq = c.min_genotype_qscore; d.low_gq_filter = c.low_genotype_quality_filter;
     d.min_coverage = c.min_coverage;
     d.low_depth_filter = c.low_depth_filter < c.min_coverage ? c.min_coverage : c.low_depth_filter;  // :137-141
+    if (c.skip_validation) d.low_depth_filter = c.low_depth_filter;   // -1 = null: no LowDepth filter
     d.rmxn_max_len = c.rmxn_max_repeat_len; d.rmxn_min_reps = c.rmxn_min_repetitions; d.rmxn_freq_limit = c.rmxn_frequency_limit;
     d.sb_acceptance = c.strand_bias_acceptance; d.sb_model = c.strand_bias_model; d.filter_single_strand = c.filter_single_strand;
     d.no_call_filter = c.no_call_filter;
@@ -185,6 +187,7 @@ extern "C" int pb2_reset(pb2_handle* h) {
     for (auto& s : h->segs) free_segment(h, s);
     h->segs.clear();
     h->h_out.clear();
+    h->h_out_ext.clear();
     h->reads.clear();
     h->cands.clear(); h->block_max_endpoint.clear(); h->gapped_ref.clear(); h->triggers.clear(); h->arena.clear();
     h->last_trigger_key = 0; h->push_last_key = 0; h->cleared_through = 0;
@@ -802,7 +805,8 @@ static int upload_gapped(pb2_handle* h, const Segment& s, int32_t** d_out) {
 // the existing blocks that end at or before upTo, in order, up to the first block holding an allele that extends past upTo, plus — when an included
 // allele reaches past the last included block — the finished open-left SNV/MNV candidates of later blocks (AddCollapsableFromOtherBlocks :441-457).
 // Returns the last position cleared (0 = none; INT32_MAX = everything).
-static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, std::vector<pb2_call_record>& called, int32_t* cleared_out) {
+static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, std::vector<pb2_call_record>& called, std::vector<pb2_call_record_ext>& called_ext,
+                                int32_t* cleared_out) {
     *cleared_out = h->cleared_through;
     auto all_alive_sorted = [&]() {
         std::vector<size_t> idx;
@@ -811,7 +815,7 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
         return idx;
     };
     if (!reads_path) {   // locus-major pushes are complete by construction: one batch, nothing left uncleared
-        const int rc = explicit_call_batch(h, all_alive_sorted(), -1, called);
+        const int rc = explicit_call_batch(h, all_alive_sorted(), -1, called, called_ext);
         *cleared_out = INT32_MAX;
         return rc;
     }
@@ -859,7 +863,7 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
                     batch.push_back(i);
             }
         }
-        const int rc = explicit_call_batch(h, batch, t >= 0 ? max_end : -1, called);
+        const int rc = explicit_call_batch(h, batch, t >= 0 ? max_end : -1, called, called_ext);
         if (rc != PB2_OK) return rc;
         *cleared_out = t >= 0 ? max_end : INT32_MAX;
     }
@@ -886,26 +890,39 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
     tr.mark("stage_reads");
     // explicit candidates first: their gapped-MNV reference counts feed the point alleles of the hot kernel
     std::vector<pb2_call_record> explicit_called;
+    std::vector<pb2_call_record_ext> explicit_ext;
     int32_t cleared_to = cleared_end;
     {
-        const int rc = run_explicit_batches(h, up_to_position, reads_path, explicit_called, &cleared_to);
+        const int rc = run_explicit_batches(h, up_to_position, reads_path, explicit_called, explicit_ext, &cleared_to);
         if (rc != PB2_OK) return rc;
         if (!reads_path) cleared_to = INT32_MAX;
     }
     tr.mark("explicit");
+    struct OutRec { pb2_call_record r; pb2_call_record_ext e; };
+    pb2_call_record_ext zero_ext;
+    memset(&zero_ext, 0, sizeof(zero_ext));
+    h->h_out_ext.clear();
+    auto emit = [&](const OutRec& o) { h->h_out.push_back(o.r); h->h_out_ext.push_back(o.e); };
     std::vector<uint8_t> explicit_used(explicit_called.size(), 0);
+    const bool want_collapsed = h->cfg.expect_collapsed != 0;
     for (auto& s : h->segs) {
+        int32_t* d_collapsed = nullptr;   // ReadCollapsedCountTotal source: CollapsedRegionState._collapsedCount per locus
+        std::vector<int32_t> collapsed;
+        if (want_collapsed) {
+            CU(h, pool_alloc_t(h, &d_collapsed, (size_t)s.n_loci * kNumCollapsed));
+            s.called = false;
+        }
         if (!s.called) {
             int32_t* d_gapped = nullptr;
             int rc = upload_gapped(h, s, &d_gapped);
-            if (rc == PB2_OK) rc = run_segment(h, s, nullptr, nullptr, d_gapped);
+            if (rc == PB2_OK) rc = run_segment(h, s, nullptr, d_collapsed, d_gapped);
             if (d_gapped) cudaFree(d_gapped);
             if (rc != PB2_OK) return rc;
         }
-        std::vector<pb2_call_record> vars((size_t)s.h_var_count);
+        std::vector<pb2_call_record> hot_vars((size_t)s.h_var_count);
         std::vector<uint32_t> exc((size_t)s.h_exc_count * 2);
         if (!exc.empty()) CU(h, cudaMemcpyAsync(exc.data(), s.exc_entries, sizeof(uint32_t) * exc.size(), cudaMemcpyDeviceToHost, h->stream));
-        if (!vars.empty()) CU(h, cudaMemcpyAsync(vars.data(), s.var_records, sizeof(pb2_call_record) * vars.size(), cudaMemcpyDeviceToHost, h->stream));
+        if (!hot_vars.empty()) CU(h, cudaMemcpyAsync(hot_vars.data(), s.var_records, sizeof(pb2_call_record) * hot_vars.size(), cudaMemcpyDeviceToHost, h->stream));
         std::vector<pb2_call_record> refs;
         std::vector<uint8_t> valid;
         if (s.ref_records) {
@@ -914,46 +931,74 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
             CU(h, cudaMemcpyAsync(refs.data(), s.ref_records, sizeof(pb2_call_record) * refs.size(), cudaMemcpyDeviceToHost, h->stream));
             CU(h, cudaMemcpyAsync(valid.data(), s.ref_valid, valid.size(), cudaMemcpyDeviceToHost, h->stream));
         }
+        if (d_collapsed) {
+            collapsed.resize((size_t)s.n_loci * kNumCollapsed);
+            CU(h, cudaMemcpyAsync(collapsed.data(), d_collapsed, sizeof(int32_t) * collapsed.size(), cudaMemcpyDeviceToHost, h->stream));
+        }
         CU(h, cudaStreamSynchronize(h->stream));
+        pool_free(h, d_collapsed);
         tr.mark("hot+d2h");
-        if (!exc.empty() && !h->cfg.call_mnvs) { const int rc = reconcile_flagged_entries(h, s, exc, vars); if (rc != PB2_OK) return rc; }
+        if (!exc.empty() && !h->cfg.call_mnvs) { const int rc = reconcile_flagged_entries(h, s, exc, hot_vars); if (rc != PB2_OK) return rc; }
+        auto locus_of = [&](int32_t pos) -> int64_t {
+            if (s.has_positions) {
+                auto it = std::lower_bound(s.h_positions.begin(), s.h_positions.end(), pos);
+                return (it != s.h_positions.end() && *it == pos) ? (int64_t)(it - s.h_positions.begin()) : -1;
+            }
+            const int64_t k = (int64_t)pos - s.first_position;
+            return (k >= 0 && k < s.n_loci) ? k : -1;
+        };
+        auto with_totals = [&](OutRec o) {   // CollapsedCoverageCalculator (:18-37): the counts at the allele's position / spanning start point
+            if (!collapsed.empty()) {
+                const int64_t l = locus_of(o.r.type == CAT_DEL ? o.r.position + 1 : o.r.position);
+                if (l >= 0) for (int t = 0; t < kNumCollapsed; t++) o.e.collapsed_total[t] = collapsed[(size_t)l * kNumCollapsed + t];
+            }
+            return o;
+        };
+        std::vector<OutRec> vars;
+        vars.reserve(hot_vars.size());
+        for (auto& r : hot_vars) vars.push_back(with_totals(OutRec{r, zero_ext}));
         // the explicit alleles called inside this segment's positions join its variant stream
         const int32_t seg_lo = s.has_positions ? (s.h_positions.empty() ? 1 : s.h_positions.front()) : s.first_position;
         const int32_t seg_hi = s.has_positions ? (s.h_positions.empty() ? 0 : s.h_positions.back()) : (int32_t)(s.first_position + s.n_loci - 1);
-        std::map<int32_t, pb2_call_record> ref_override;   // reference alleles that gained support from a reallocated MNV (MnvReallocator.cs:255-265)
+        std::map<int32_t, OutRec> ref_override;   // reference alleles that gained support from a reallocated MNV (MnvReallocator.cs:255-265)
         for (size_t k = 0; k < explicit_called.size(); k++)
             if (!explicit_used[k] && explicit_called[k].position >= seg_lo && explicit_called[k].position <= seg_hi) {
-                if (explicit_called[k].type == CAT_REF) ref_override[explicit_called[k].position] = explicit_called[k];
-                else vars.push_back(explicit_called[k]);
+                const OutRec o = with_totals(OutRec{explicit_called[k], explicit_ext[k]});
+                if (o.r.type == CAT_REF) ref_override[o.r.position] = o;
+                else vars.push_back(o);
                 explicit_used[k] = 1;
             }
-        std::sort(vars.begin(), vars.end(), [&](const pb2_call_record& a, const pb2_call_record& b) { return record_less_arena(a, b, h->arena); });
+        std::sort(vars.begin(), vars.end(), [&](const OutRec& a, const OutRec& b) { return record_less_arena(a.r, b.r, h->arena); });
         // merge the dense reference stream (already in position order) with the sorted variant stream; a reference allele is pruned wherever a
         // variant was called (AlleleCaller.cs:146-147)
         size_t vi = 0;
         if (refs.empty() && ref_override.empty()) {   // no reference stream: the sorted variant stream is the output
-            while (vi < vars.size() && vars[vi].position <= cleared_to) h->h_out.push_back(vars[vi++]);
+            while (vi < vars.size() && vars[vi].r.position <= cleared_to) emit(vars[vi++]);
             continue;
         }
         for (int64_t i = 0; i < s.n_loci; i++) {
             const int32_t pos = s.has_positions ? s.h_positions[(size_t)i] : s.first_position + (int32_t)i;
             if (pos > cleared_to) break;
-            while (vi < vars.size() && vars[vi].position < pos) h->h_out.push_back(vars[vi++]);
+            while (vi < vars.size() && vars[vi].r.position < pos) emit(vars[vi++]);
             bool variant_here = false;
-            while (vi < vars.size() && vars[vi].position == pos) { h->h_out.push_back(vars[vi++]); variant_here = true; }
+            while (vi < vars.size() && vars[vi].r.position == pos) { emit(vars[vi++]); variant_here = true; }
             if (!refs.empty() && valid[(size_t)i] && !variant_here) {
                 auto ov = ref_override.find(pos);
-                h->h_out.push_back(ov == ref_override.end() ? refs[(size_t)i] : ov->second);
+                emit(ov == ref_override.end() ? with_totals(OutRec{refs[(size_t)i], zero_ext}) : ov->second);
             }
         }
-        while (vi < vars.size() && vars[vi].position <= cleared_to) h->h_out.push_back(vars[vi++]);
+        while (vi < vars.size() && vars[vi].r.position <= cleared_to) emit(vars[vi++]);
     }
     {   // explicit alleles at positions no segment stages (e.g. an insertion before the first covered base)
-        std::vector<pb2_call_record> rest;
-        for (size_t k = 0; k < explicit_called.size(); k++) if (!explicit_used[k]) rest.push_back(explicit_called[k]);
-        if (!rest.empty()) {
-            h->h_out.insert(h->h_out.end(), rest.begin(), rest.end());
-            std::stable_sort(h->h_out.begin(), h->h_out.end(), [&](const pb2_call_record& a, const pb2_call_record& b) { return a.position < b.position; });
+        std::vector<OutRec> all;
+        bool any_rest = false;
+        for (size_t k = 0; k < explicit_called.size(); k++) any_rest |= !explicit_used[k];
+        if (any_rest) {
+            for (size_t k = 0; k < h->h_out.size(); k++) all.push_back(OutRec{h->h_out[k], h->h_out_ext[k]});
+            for (size_t k = 0; k < explicit_called.size(); k++) if (!explicit_used[k]) all.push_back(OutRec{explicit_called[k], explicit_ext[k]});
+            std::stable_sort(all.begin(), all.end(), [&](const OutRec& a, const OutRec& b) { return a.r.position < b.r.position; });
+            h->h_out.clear(); h->h_out_ext.clear();
+            for (auto& o : all) emit(o);
         }
     }
     tr.mark("merge");
@@ -984,6 +1029,13 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
     }
     *out = h->h_out.data();
     *n = (int64_t)h->h_out.size();
+    return PB2_OK;
+}
+
+extern "C" int pb2_flush_ext(pb2_handle* h, const pb2_call_record_ext** out, int64_t* n) {
+    if (!h || !out || !n) return fail(h, PB2_ERR_ARG, "pb2_flush_ext: null argument");
+    *out = h->h_out_ext.data();
+    *n = (int64_t)h->h_out_ext.size();
     return PB2_OK;
 }
 

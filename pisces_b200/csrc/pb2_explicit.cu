@@ -81,6 +81,8 @@ struct Piece {
     int32_t allele_support = 0;
     int32_t support[3] = {0, 0, 0};
     int32_t well_anchored = 0;
+    int32_t wa[3] = {0, 0, 0};                      // WellAnchoredSupportByDirection
+    int32_t collapsed_mut[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ReadCollapsedCountsMut (candidates only; alleles the reallocator creates start from zero)
     bool from_candidate = false;
     int32_t original_support = 0;   // reference alleles drawn into the MNV reallocation: re-scored only when their support changed
 };
@@ -253,6 +255,8 @@ Piece piece_of(const HostCand& c) {   // AlleleHelper.Map (Utility/AlleleHelper.
     p.allele_support = c.Support();
     for (int k = 0; k < 3; k++) p.support[k] = c.support[k];
     p.well_anchored = c.WellAnchored();
+    for (int k = 0; k < 3; k++) p.wa[k] = c.well_anchored[k];
+    for (int k = 0; k < 8; k++) p.collapsed_mut[k] = c.collapsed_mut[k];
     p.from_candidate = true;
     return p;
 }
@@ -299,7 +303,8 @@ float candidate_frequency(const pb2_handle* h, const HostCand& c, const SpanIngr
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ AlleleCaller.Call, explicit part
-int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, std::vector<pb2_call_record>& called) {
+int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, std::vector<pb2_call_record>& called,
+                        std::vector<pb2_call_record_ext>& called_ext) {
     if (batch.empty()) return PB2_OK;
     std::vector<HostCand> cs;
     cs.reserve(batch.size());
@@ -526,7 +531,8 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
         for (Piece* l : outside) {   // leftovers become candidates of later blocks (AlleleCaller.cs:91-92, AlleleHelper.Map :62-85)
             HostCand c;
             c.position = l->position; c.type = l->type; c.ref = l->ref; c.alt = l->alt;
-            for (int k = 0; k < 3; k++) c.support[k] = l->support[k];
+            for (int k = 0; k < 3; k++) { c.support[k] = l->support[k]; c.well_anchored[k] = l->wa[k]; }
+            for (int k = 0; k < 8; k++) c.collapsed_mut[k] = l->collapsed_mut[k];
             explicit_add_candidate(h, c);
         }
     }
@@ -545,7 +551,15 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
         std::vector<uint8_t> flags;
         rc = score_pieces(ctx, callable, arena, &recs, &flags, nullptr, nullptr);
         if (rc != PB2_OK) return rc;
-        for (size_t i = 0; i < recs.size(); i++) if (flags[i] & 2) called.push_back(recs[i]);
+        for (size_t i = 0; i < recs.size(); i++) {
+            if (!(flags[i] & 2)) continue;
+            called.push_back(recs[i]);
+            pb2_call_record_ext e;
+            memset(&e, 0, sizeof(e));
+            for (int k = 0; k < 8; k++) e.collapsed_mut[k] = callable[i]->collapsed_mut[k];
+            for (int k = 0; k < 3; k++) e.well_anchored_support[k] = callable[i]->wa[k];
+            called_ext.push_back(e);
+        }
     }
     return PB2_OK;
 }

@@ -132,6 +132,7 @@ struct pb2_handle {
     int32_t cleared_through = 0;   // positions <= this were called by an earlier pb2_flush(up_to >= 0)
     int* d_tile_counter = nullptr;
     std::vector<pb2_call_record> h_out;
+    std::vector<pb2_call_record_ext> h_out_ext;   // parallel to h_out
     int64_t hot_launches = 0, total_launches = 0;
     double hot_ms = 0;
     // ---- explicit candidates (pb2_explicit.cu)
@@ -158,7 +159,8 @@ void explicit_add_candidate(pb2_handle* h, const HostCand& c);
 // + MnvReallocator, gapped-MNV reference counts, final ProcessVariant of every callable allele on the device. Called alleles (IsCallable &&
 // ShouldReport) are appended to `called`; candidates that go back to the state (not cleared / MNV leftovers) are re-added to h->cands.
 // max_cleared < 0 = null (everything is cleared).
-int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, std::vector<pb2_call_record>& called);
+int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, std::vector<pb2_call_record>& called,
+                        std::vector<pb2_call_record_ext>& called_ext);
 // Finds the candidates of the reads in R[first_read, end) on the device (CandidateVariantFinder.FindCandidates) and adds them to the table.
 int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_read);
 // pb2_call_resident: gather + score + append on the device, no host round trip; only for candidates that need neither the collapser nor the MNV logic.

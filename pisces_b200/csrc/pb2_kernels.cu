@@ -351,9 +351,10 @@ __device__ __forceinline__ void finish_locus(const int (&cnt)[kNumAlleles][kNumD
         if (out.ref_records != nullptr) out.ref_valid[locus] = 0;   // decided when the queued locus is scored
     } else if (out.ref_records != nullptr) {
         // RegionState.GetAllCandidates: a Reference candidate per position when gVCF; zero-coverage positions only with intervals (:446)
-        const bool emit = cfg.output_gvcf && !has_ext_variant && (cfg.have_intervals || any > 0);
+        // ... and never past the chromosome end (:411-412)
+        const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+        const bool emit = cfg.output_gvcf && !has_ext_variant && (cfg.have_intervals || any > 0) && (ex.chr_len == 0 || position <= ex.chr_len);
         if (emit) {
-            const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
             LocusCounts lc;
 #pragma unroll
             for (int a = 0; a < kNumAlleles; a++)
@@ -584,7 +585,7 @@ __device__ __forceinline__ void score_queued_locus(const PendingLocus* item /* n
     const unsigned b = __ballot_sync(0xffffffffu, called);
     if (item != nullptr && j == 0 && out.ref_records != nullptr) {
         const bool variant_called = ((cand_mask & 0x100) != 0) || (((b >> (lane & ~3)) & 0xfu) != 0);
-        const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (cand_mask & 0x200));
+        const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (cand_mask & 0x200)) && (ex.chr_len == 0 || position <= ex.chr_len);
         if (emit) {
             pb2_call_record r;
             score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex, r);
@@ -870,7 +871,7 @@ __global__ void __launch_bounds__(128) score_pending_kernel(const __grid_constan
             }
         }
         if (out.ref_records != nullptr) {
-            const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (pl.cand_mask & 0x200));
+            const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (pl.cand_mask & 0x200)) && (ex.chr_len == 0 || position <= ex.chr_len);
             if (emit) {
                 pb2_call_record r;
                 score_point_allele(lc, position, ref_allele, ref_allele, pl.gapped, cfg, ex, r);

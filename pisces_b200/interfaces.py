@@ -276,6 +276,14 @@ class GpuStateManager:
         self._chk(self._L.pb2_allele_arena(self._h, C.byref(p), C.byref(n)))
         return C.string_at(p.value, n.value) if n.value else b""
 
+    def AlleleExt(self):
+        """pb2_call_record_ext rows (ReadCollapsedCountsMut / ...Total, WellAnchoredSupportByDirection) of the records of the last Call, same order."""
+        p, n = C.c_void_p(), C.c_int64()
+        self._chk(self._L.pb2_flush_ext(self._h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=N.RECORD_EXT_DTYPE)
+        return np.frombuffer((C.c_char * (80 * n.value)).from_address(p.value), dtype=N.RECORD_EXT_DTYPE).copy()
+
     def GetAlleleCounts(self, position0, n):
         """RegionState._alleleCounts over [position0, position0+n): int32 [n][6][3][11]."""
         out = np.zeros((n, 6, 3, 11), dtype=np.int32)

@@ -250,7 +250,9 @@ class _RecordView:
     """A pb2_call_record shaped like the oracle's record, for the VCF text restatement (oracle/vcf_text.py, test infrastructure)."""
     _FILTER_ORDER = [4, 3, 12, 0, 2, 7, 9, 5, 6, 10]   # the order AlleleProcessor.ApplyFilters / the genotyper add them (AlleleProcessor.cs:25-71)
 
-    def __init__(self, p, arena):
+    def __init__(self, p, arena, ext=None):
+        self.collapsed_mut = [int(x) for x in ext["collapsed_mut"]] if ext is not None else [0] * 8
+        self.collapsed_total = [int(x) for x in ext["collapsed_total"]] if ext is not None else [0] * 8
         rl, al, ab = int(p["ref_len"]), int(p["alt_len"]), int(p["allele_bytes"])
         raw = ab.to_bytes(4, "little") if rl + al <= 4 else bytes(arena[ab:ab + rl + al])
         self.ref, self.alt = raw[:rl].decode(), raw[rl:rl + al].decode()
@@ -296,6 +298,58 @@ def test_phix_full_text_golden_through_cuda_path():
     vt = VcfText(ob.default_config(**okw), ob.FILTERS, ob.GENOTYPES)
     got = [vt.line("phix", v) for v in views]
     exp = [l.rstrip("\n") for l in open(os.path.join(G, "phix_s3_noisy.records.vcf"))]
+    assert len(got) == len(exp)
+    for a, b in zip(got, exp):
+        assert a == b
+
+
+def test_collapsed_stitched_full_text_golden_through_cuda_path():
+    """src/test/Pisces.Tests/FunctionalTests/SomaticVariantCallerFunctionalTests.cs:683-758: collapsed.test.stitched.bam against the mock chr1 ->
+    test_truth.stitched.genome.vcf (171 records), line by line from the CUDA path's records: stitched directions (XD), collapsed-read categories
+    (XV/XW/XR), MNVs up to 100 with gaps of 10, and the 12-field US tag from pb2_call_record_ext. The reference test builds its options by hand
+    (no Validate()), hence skip_validation."""
+    import json
+    import os
+    from oracle.vcf_text import VcfText
+    pb = _pb()
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    reads = json.load(open(os.path.join(G, "collapsed_stitched_reads.json")))
+    seq = "N" * (9770498 - 1) + ("GAAGTAACAACGCAGGATGCCCCCTGGGGTGGACTGCCCCATGGAATTCTGGACCAAGGAGGAGAATCAGAGCGTTGTGGTTGACTTCCTGCTGCCCACAGGGGTCTACCTGAACTTCCCTGTGTCCCGCAATGCCAACCTC"
+                                 "AGCACCATCAAGCAGGTATGGCCTCCATC")
+    okw = dict(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, source_is_stitched=1, source_is_collapsed=1, apply_validation=0)
+    pkw = dict(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, expect_stitched=1, expect_collapsed=1, skip_validation=1)
+
+    def base_dirs(r):   # Read.SequencedBaseDirectionMap: the XD runs projected onto the read bases (Read.cs:390-421,664-682)
+        exp, num = [], ""
+        for ch in r["xd"]:
+            if ch.isdigit():
+                num += ch
+            else:
+                exp += [{"F": 0, "R": 1, "S": 2}[ch]] * int(num)
+                num = ""
+        dirs, ci = [], 0
+        for c in r["cigar"]:
+            op, ln = c & 15, c >> 4
+            for _ in range(ln):
+                if op in (0, 1, 4, 7, 8):
+                    dirs.append(exp[ci])
+                ci += 1
+        return dirs
+
+    def collapsed_byte(r):   # pb2_read_batch.collapsed: IsCollapsedRead, IsDuplex, ReadPairDirection (Read.cs:17-71,311-349)
+        has = r["xv"] is not None or r["xw"] is not None
+        duplex = bool(r["xv"]) and bool(r["xw"])
+        return (1 if has else 0) | (2 if duplex else 0) | ({"FR": 1, "RF": 2}.get(r["xr"], 0) << 2)
+
+    sm = pb.GpuStateManager(pb.make_config(**pkw), "chr1", seq)
+    sm.AddAlleleCounts([pb.Read(r["pos0"] + 1, r["seq"], r["cigar"], r["qual"], flag=r["flag"], base_directions=base_dirs(r), collapsed=collapsed_byte(r)) for r in reads])
+    recs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    arena, ext = sm.AlleleArena(), sm.AlleleExt()
+    sm.close()
+    assert len(ext) == len(recs)
+    vt = VcfText(ob.default_config(**okw), ob.FILTERS, ob.GENOTYPES, debug=True, output_bias_files=True, report_rc_counts=True, report_ts_counts=True)
+    got = [vt.line("chr1", _RecordView(p, arena, e)) for p, e in zip(recs, ext)]
+    exp = [l.rstrip("\n") for l in open(os.path.join(G, "collapsed_stitched.records.vcf"))]
     assert len(got) == len(exp)
     for a, b in zip(got, exp):
         assert a == b
