@@ -198,6 +198,14 @@ int pb2_push_reads(pb2_handle* h, const pb2_read_batch* batch);
  * that keeps its own ICandidateVariantFinder uses this too). Candidates equal in (position, type, ref, alt[, open ends when Collapse is on])
  * are merged by summing their counts (RegionState.AddCandidate, RegionState.cs:94-174). */
 int pb2_push_candidates(pb2_handle* h, const pb2_candidate* cands, int32_t n, const uint8_t* allele_arena, int64_t arena_len);
+/* Forced-genotyping alleles of this chromosome (the forcedGtAlleles argument of Factory.CreateSomaticVariantCaller -> SmallVariantCaller's
+ * constructor, src/exe/Pisces/Logic/SmallVariantCaller.cs:48-77, and AlleleCaller.AddForcedGtAlleles, AlleleCaller.cs:63-66). Only position,
+ * ref_len, alt_len and allele_offset of each pb2_candidate are read. Alleles outside the interval set are dropped; the rest become zero-support
+ * candidates once calling passes their position (AddForcedAlleleAsCandidate :118-155), put a reference candidate at their position
+ * (RegionState.GetAllCandidates :383-453) and are reported by pb2_flush even when not callable: sb_flags bit3 (IsForcedToReport) and the
+ * ForcedReport filter set, genotype / GQ left at a new CalledAllele's values (AlleleCaller.cs:98-118,143-150). They stay set across pb2_reset;
+ * n = 0 clears them. pb2_call_resident refuses to run while any are set (their records only come through pb2_flush). */
+int pb2_set_forced_alleles(pb2_handle* h, const pb2_candidate* alleles, int32_t n, const uint8_t* allele_arena, int64_t arena_len);
 /* The byte arena that pb2_call_record.allele_bytes of the last pb2_flush / pb2_call_resident points into for alleles longer than 4 bases. */
 int pb2_allele_arena(pb2_handle* h, const uint8_t** arena, int64_t* len);
 

@@ -9,6 +9,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 #include "pisces_b200.h"
 
@@ -43,6 +44,23 @@ public:
 
     bool ExpectStitchedReads() const { return cfg_.expect_stitched != 0; }
     void SetIntervals(const std::vector<int32_t>& start, const std::vector<int32_t>& end) { check(pb2_set_intervals(h_, start.data(), end.data(), (int32_t)start.size())); }
+
+    // forcedGtAlleles of Factory.CreateSomaticVariantCaller (Factory.cs:253) for this chromosome: (position, ref, alt)
+    void SetForcedAlleles(const std::vector<std::tuple<int32_t, std::string, std::string>>& alleles) {
+        std::vector<pb2_candidate> cs(alleles.size());
+        std::vector<uint8_t> arena;
+        for (size_t i = 0; i < alleles.size(); i++) {
+            pb2_candidate c{};
+            c.position = std::get<0>(alleles[i]);
+            const std::string &ref = std::get<1>(alleles[i]), &alt = std::get<2>(alleles[i]);
+            c.ref_len = (uint16_t)ref.size(); c.alt_len = (uint16_t)alt.size(); c.allele_offset = (uint32_t)arena.size();
+            arena.insert(arena.end(), ref.begin(), ref.end());
+            arena.insert(arena.end(), alt.begin(), alt.end());
+            cs[i] = c;
+        }
+        arena.push_back(0);
+        check(pb2_set_forced_alleles(h_, cs.data(), (int32_t)cs.size(), arena.data(), (int64_t)arena.size()));
+    }
 
     // IStateManager.AddAlleleCounts(Read) (+ the SNV part of ICandidateVariantFinder.FindCandidates): buffered, expanded on the device at the next Call
     void AddAlleleCounts(const Read& r) { buffer_.push_back(r); if (buffer_.size() >= 65536) PushBuffered(); }

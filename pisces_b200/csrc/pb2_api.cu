@@ -48,6 +48,8 @@ int pb2_fail(pb2_handle* h, int code, const std::string& msg) {
     return code;
 }
 static int fail(pb2_handle* h, int code, const std::string& msg) { return pb2_fail(h, code, msg); }
+// SmallVariantCaller's constructor (SmallVariantCaller.cs:48-77): the forced alleles of this chromosome, by position, minus those outside the intervals
+static void rearm_forced(pb2_handle* h);
 
 extern "C" void pb2_default_config(pb2_config* c) {
     memset(c, 0, sizeof(*c));
@@ -191,6 +193,7 @@ extern "C" int pb2_reset(pb2_handle* h) {
     h->reads.clear();
     h->cands.clear(); h->block_max_endpoint.clear(); h->gapped_ref.clear(); h->triggers.clear(); h->arena.clear();
     h->last_trigger_key = 0; h->push_last_key = 0; h->cleared_through = 0;
+    rearm_forced(h);
     explicit_release_resident(h);
     release_resident_graph(h);
     return PB2_OK;
@@ -236,6 +239,7 @@ extern "C" int pb2_set_intervals(pb2_handle* h, const int32_t* start, const int3
     h->iv_start.assign(start, start + n);
     h->iv_end.assign(end, end + n);
     h->have_intervals = true;   // an empty set still means "intervals applied" (Factory.cs:229-245)
+    rearm_forced(h);
     derive_config(h);
     return PB2_OK;
 }
@@ -815,7 +819,8 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
         return idx;
     };
     if (!reads_path) {   // locus-major pushes are complete by construction: one batch, nothing left uncleared
-        const int rc = explicit_call_batch(h, all_alive_sorted(), -1, called, called_ext);
+        explicit_add_forced_candidates(h, -1);
+        const int rc = explicit_call_batch(h, all_alive_sorted(), -1, 0, INT32_MAX, called, called_ext);
         *cleared_out = INT32_MAX;
         return rc;
     }
@@ -839,6 +844,12 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
         fire.push_back(up_to >= 0 ? up_to : -1);
     }
     for (int32_t t : fire) {
+        if (!h->forced_pending.empty()) {   // AddForcedAlleleAsCandidate(upTo) runs before Call(upTo) (SmallVariantCaller.cs:99-104); AddCandidates creates the block
+            for (auto& kv : h->forced_pending) { if (t >= 0 && kv.first > t) break; keys.push_back((kv.first + 999) / 1000); }
+            std::sort(keys.begin(), keys.end());
+            keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+            explicit_add_forced_candidates(h, t);
+        }
         const int key = t < 0 ? -1 : (t <= 0 ? 0 : (t + 999) / 1000);
         if (t >= 0 && key == h->last_trigger_key) continue;     // GetCandidatesToProcess returns null (:288-291)
         h->last_trigger_key = key;
@@ -863,7 +874,8 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
                     batch.push_back(i);
             }
         }
-        const int rc = explicit_call_batch(h, batch, t >= 0 ? max_end : -1, called, called_ext);
+        const int rc = explicit_call_batch(h, batch, t >= 0 ? max_end : -1, *cleared_out == INT32_MAX ? INT32_MAX : *cleared_out, t >= 0 ? max_end : INT32_MAX, called,
+                                           called_ext);
         if (rc != PB2_OK) return rc;
         *cleared_out = t >= 0 ? max_end : INT32_MAX;
     }
@@ -960,14 +972,36 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
         // the explicit alleles called inside this segment's positions join its variant stream
         const int32_t seg_lo = s.has_positions ? (s.h_positions.empty() ? 1 : s.h_positions.front()) : s.first_position;
         const int32_t seg_hi = s.has_positions ? (s.h_positions.empty() ? 0 : s.h_positions.back()) : (int32_t)(s.first_position + s.n_loci - 1);
-        std::map<int32_t, OutRec> ref_override;   // reference alleles that gained support from a reallocated MNV (MnvReallocator.cs:255-265)
+        std::multimap<int32_t, OutRec> ref_override;   // reference alleles that gained support from a reallocated MNV (MnvReallocator.cs:255-265)
         for (size_t k = 0; k < explicit_called.size(); k++)
             if (!explicit_used[k] && explicit_called[k].position >= seg_lo && explicit_called[k].position <= seg_hi) {
                 const OutRec o = with_totals(OutRec{explicit_called[k], explicit_ext[k]});
-                if (o.r.type == CAT_REF) ref_override[o.r.position] = o;
-                else vars.push_back(o);
                 explicit_used[k] = 1;
+                // CallMNVs off: a forced SNV that is callable on its own merits is already in the hot kernel's variant stream
+                if (!h->cfg.call_mnvs && o.r.type == CAT_SNV && !(o.r.sb_flags & 8)) continue;
+                if (o.r.type == CAT_REF) ref_override.insert({o.r.position, o});
+                else vars.push_back(o);
             }
+        if (!h->forced.empty()) {
+            // AlleleCaller.ComputeGenotypeAndFilterAllele (:143-150): an allele that is only reported because it is forced (IsForcedToReport) does not prune
+            // the reference allele of its position; the reference allele then takes its place among them in (ref, alt) order
+            std::set<int32_t> real_pos, forced_pos;
+            for (auto& v : vars) ((v.r.sb_flags & 8) ? forced_pos : real_pos).insert(v.r.position);
+            for (int32_t pos : forced_pos) {
+                const int64_t l = locus_of(pos);
+                if (!real_pos.count(pos)) {
+                    auto ov = ref_override.equal_range(pos);
+                    if (ov.first != ov.second) for (auto it = ov.first; it != ov.second; ++it) vars.push_back(it->second);
+                    else if (!refs.empty() && l >= 0 && valid[(size_t)l]) vars.push_back(with_totals(OutRec{refs[(size_t)l], zero_ext}));
+                }
+                ref_override.erase(pos);
+                if (!valid.empty() && l >= 0) valid[(size_t)l] = 0;
+            }
+            if (!h->cfg.output_gvcf) {   // reference candidates of forced positions (RegionState.GetAllCandidates :393-449) where no forced allele was left to report
+                for (auto& kv : ref_override) if (!real_pos.count(kv.first)) vars.push_back(kv.second);
+                ref_override.clear();
+            }
+        }
         std::sort(vars.begin(), vars.end(), [&](const OutRec& a, const OutRec& b) { return record_less_arena(a.r, b.r, h->arena); });
         // merge the dense reference stream (already in position order) with the sorted variant stream; a reference allele is pruned wherever a
         // variant was called (AlleleCaller.cs:146-147)
@@ -996,7 +1030,9 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
         if (any_rest) {
             for (size_t k = 0; k < h->h_out.size(); k++) all.push_back(OutRec{h->h_out[k], h->h_out_ext[k]});
             for (size_t k = 0; k < explicit_called.size(); k++) if (!explicit_used[k]) all.push_back(OutRec{explicit_called[k], explicit_ext[k]});
-            std::stable_sort(all.begin(), all.end(), [&](const OutRec& a, const OutRec& b) { return a.r.position < b.r.position; });
+            std::stable_sort(all.begin(), all.end(), [&](const OutRec& a, const OutRec& b) {
+                return a.r.position != b.r.position ? a.r.position < b.r.position : (h->forced.empty() ? false : record_less_arena(a.r, b.r, h->arena));
+            });
             h->h_out.clear(); h->h_out_ext.clear();
             for (auto& o : all) emit(o);
         }
@@ -1007,7 +1043,7 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
         if (h->segs[i].temporary) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); } else i++;
     }
     h->cands.erase(std::remove_if(h->cands.begin(), h->cands.end(), [](const HostCand& c) { return !c.alive; }), h->cands.end());
-    if (up_to_position < 0) { h->reads.clear(); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; }
+    if (up_to_position < 0) { h->reads.clear(); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; rearm_forced(h); }
     else if (reads_path && cleared_to > h->cleared_through) {
         HostReads keep;
         HostReads& R = h->reads;
@@ -1037,6 +1073,43 @@ extern "C" int pb2_flush_ext(pb2_handle* h, const pb2_call_record_ext** out, int
     *out = h->h_out_ext.data();
     *n = (int64_t)h->h_out_ext.size();
     return PB2_OK;
+}
+
+extern "C" int pb2_set_forced_alleles(pb2_handle* h, const pb2_candidate* alleles, int32_t n, const uint8_t* arena, int64_t arena_len) {
+    if (!h || n < 0 || (n > 0 && (!alleles || !arena))) return fail(h, PB2_ERR_ARG, "pb2_set_forced_alleles: bad argument");
+    std::set<std::tuple<int32_t, std::string, std::string>> forced;
+    std::vector<std::tuple<int32_t, std::string, std::string>> order;
+    for (int32_t i = 0; i < n; i++) {
+        const pb2_candidate& c = alleles[i];
+        if (c.position < 1 || c.ref_len == 0 || c.alt_len == 0 || (int64_t)c.allele_offset + c.ref_len + c.alt_len > arena_len)
+            return fail(h, PB2_ERR_ARG, "pb2_set_forced_alleles: allele " + std::to_string(i) + " is malformed");
+        const char* b = reinterpret_cast<const char*>(arena) + c.allele_offset;
+        std::string ref(b, c.ref_len), alt(b + c.ref_len, c.alt_len);
+        if (ref.size() == alt.size() && ref.size() > 1 && !h->cfg.call_mnvs)
+            return fail(h, PB2_ERR_UNSUPPORTED, "pb2_set_forced_alleles: a forced MNV needs call_mnvs=1 (its reallocation targets are count-based SNVs otherwise)");
+        if (forced.insert(std::make_tuple(c.position, ref, alt)).second) order.push_back(std::make_tuple(c.position, ref, alt));
+    }
+    h->forced_order = std::move(order);
+    rearm_forced(h);
+    explicit_release_resident(h);
+    release_resident_graph(h);
+    return PB2_OK;
+}
+static void rearm_forced(pb2_handle* h) {
+    h->forced_pending.clear();
+    h->forced_positions.clear();
+    h->forced.clear();   // Factory.SelectForcedAllele (Factory.cs:270-285): only the alleles inside the intervals are forced at all
+    for (auto& f : h->forced_order) {
+        const int32_t pos = std::get<0>(f);
+        if (h->have_intervals) {   // _intervalSet.ContainsPosition (SmallVariantCaller.cs:58-61)
+            bool in = false;
+            for (size_t i = 0; i < h->iv_start.size() && !in; i++) in = pos >= h->iv_start[i] && pos <= h->iv_end[i];
+            if (!in) continue;
+        }
+        h->forced.insert(f);
+        h->forced_pending[pos].push_back({std::get<1>(f), std::get<2>(f)});
+        h->forced_positions.push_back(pos);
+    }
 }
 
 extern "C" int pb2_push_candidates(pb2_handle* h, const pb2_candidate* cands, int32_t n, const uint8_t* arena, int64_t arena_len) {

@@ -242,8 +242,6 @@ __global__ void __launch_bounds__(32 * kScoreWarps) score_candidates_kernel(Cand
     const DevCand c = a.cands[i];
     const uint8_t* ref_allele = a.arena + c.allele_off;
     const uint8_t* alt_allele = ref_allele + c.ref_len;
-    int allele_support = c.support[0] + c.support[1] + c.support[2];
-    if (c.type == CAT_REF) allele_support = max(0, allele_support - c.gapped_ref);   // CoverageCalculator.cs:94-97
     const bool want_q = a.qsum != nullptr;
     for (int b = lane; b < kNumBins; b += 32) {
         s_cnt[warp][0][b] = c.req_start >= 0 ? a.counts[(int64_t)c.req_start * kNumBins + b] : 0;
@@ -254,6 +252,8 @@ __global__ void __launch_bounds__(32 * kScoreWarps) score_candidates_kernel(Cand
         }
     }
     __syncwarp();
+    int allele_support = c.support[0] + c.support[1] + c.support[2];
+    if (c.type == CAT_REF) allele_support = max(0, allele_support - c.gapped_ref);   // CoverageCalculator.cs:94-97
     const bool is_ref = c.type == CAT_REF;
     // the reference scans need no coverage: all lanes, before lane 0 goes on alone (skipped by ShouldFilter when the frequency is above the limit; the
     // limit test is applied to the result below)
@@ -362,10 +362,6 @@ __global__ void __launch_bounds__(32 * kScoreWarps) score_candidates_kernel(Cand
         if (cfg.expect_stitched && (c.flags & kCandAltHasN)) filters |= 1u << FLT_STRAND_BIAS;
     }
     const float ref_freq = allele_frequency(ref_support, total);
-    const int gt = somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
-    const int gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, a.q_to_p_table, a.q_table_max);
-    if (cfg.low_gq_filter >= 0 && (float)gq < (float)cfg.low_gq_filter) filters |= 1u << FLT_LOW_GQ;
-
     // AlleleCaller.IsCallable (:236-258) && ShouldReport (:260-263)
     bool callable = true;
     if (!is_ref) {
@@ -374,12 +370,18 @@ __global__ void __launch_bounds__(32 * kScoreWarps) score_candidates_kernel(Cand
         if (vq < cfg.min_vq) callable = false;
     }
     const bool report = callable && (c.flags & kCandReportable);
+    // a forced allele that would not be reported is reported anyway, flagged, and keeps the genotype a new CalledAllele starts with (:108-118,150)
+    const bool forced_report = (c.flags & kCandForced) && !report;
+    if (forced_report) filters |= 1u << FLT_FORCED_REPORT;
+    const int gt = forced_report ? (is_ref ? GT_HOM_REF : GT_HET_ALT_REF) : somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
+    const int gq = forced_report ? 0 : somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, a.q_to_p_table, a.q_table_max);
+    if (cfg.low_gq_filter >= 0 && (float)gq < (float)cfg.low_gq_filter) filters |= 1u << FLT_LOW_GQ;
 
     pb2_call_record r;
     r.position = c.position;
     r.type = c.type;
     r.genotype = (uint8_t)gt;
-    r.sb_flags = (sb.acceptable ? 1 : 0) | (sb.var_both ? 2 : 0) | (sb.cov_both ? 4 : 0);
+    r.sb_flags = (sb.acceptable ? 1 : 0) | (sb.var_both ? 2 : 0) | (sb.cov_both ? 4 : 0) | (forced_report ? 8 : 0);
     r.open_flags = 0;
     r.filters = (uint16_t)filters;
     r.noise_level = (uint16_t)nl_applied;
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(32 * kScoreWarps) score_candidates_kernel(Cand
     r.gatk_bias_score = sb.gatk;
 
     if (a.out_dense != nullptr) a.out_dense[i] = r;
-    if (a.out_callable != nullptr) a.out_callable[i] = (callable ? 1 : 0) | (report ? 2 : 0);
+    if (a.out_callable != nullptr) a.out_callable[i] = (callable ? 1 : 0) | (report ? 2 : 0) | (forced_report ? 4 : 0);
     if (a.var_records != nullptr && report) {
         const unsigned long long slot = atomicAdd(a.var_count, 1ull);
         if ((int64_t)slot < a.var_capacity) a.var_records[slot] = r;

@@ -23,6 +23,7 @@ struct DevCand {
 static_assert(sizeof(DevCand) == 64, "DevCand layout");
 constexpr uint8_t kCandAltHasN = 1;       // AlternateAllele contains 'N' (stitched-source strand-bias filter, AlleleProcessor.cs:66-69)
 constexpr uint8_t kCandReportable = 2;    // AlleleCaller.ShouldReport: position inside the interval set (or no intervals)
+constexpr uint8_t kCandForced = 4;        // AlleleCaller.IsForcedAllele: reported even when not callable, with the ForcedReport filter (:108-118)
 
 // What CoverageCalculator.CalculateSpanning (CoverageCalculator.cs:162-321) reads from the counts; independent of the candidate's support, so the
 // host collapser can re-derive a candidate's coverage (-> CandidateAllele.Frequency) after every merge without another launch.
@@ -86,7 +87,7 @@ struct CandScoreArgs {
     const double* q_to_p_table;
     int q_table_max;
     pb2_call_record* out_dense;   // [n]: every candidate's record (host-orchestrated passes), or nullptr
-    uint8_t* out_callable;        // [n] bit0 AlleleCaller.IsCallable, bit1 && ShouldReport; or nullptr
+    uint8_t* out_callable;        // [n] bit0 AlleleCaller.IsCallable, bit1 && ShouldReport, bit2 forced to report; or nullptr
     SpanIngredients* out_ingredients;  // [n] (spanning alleles) or nullptr
     pb2_call_record* var_records; // append mode: callable alleles go to the variant stream ...
     unsigned long long* var_count;

@@ -8,10 +8,12 @@
 //   MnvReallocator.ReallocateFailedMnvs                      src/exe/Pisces/Logic/VariantCalling/MnvReallocator.cs:12-265
 //   AlleleCaller.Call / GetRefSupportFromGappedMnvs          src/exe/Pisces/Logic/VariantCalling/AlleleCaller.cs:50-141,186-206
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <deque>
 #include <memory>
+#include <set>
 #include <unordered_map>
 #include "pb2_internal.hpp"
 
@@ -85,6 +87,7 @@ struct Piece {
     int32_t collapsed_mut[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ReadCollapsedCountsMut (candidates only; alleles the reallocator creates start from zero)
     bool from_candidate = false;
     int32_t original_support = 0;   // reference alleles drawn into the MNV reallocation: re-scored only when their support changed
+    bool keep_ref = false;          // the Reference candidate of a forced position (reference calls off): always scored and reported
 };
 
 struct BatchCtx {
@@ -203,7 +206,8 @@ int score_pieces(BatchCtx& ctx, const std::vector<Piece*>& pieces, std::vector<u
         memset(&d, 0, sizeof(d));
         d.position = p.position;
         d.type = p.type;
-        d.flags = (p.alt.find('N') != std::string::npos ? kCandAltHasN : 0) | (in_intervals(h, p.position) ? kCandReportable : 0);
+        d.flags = (p.alt.find('N') != std::string::npos ? kCandAltHasN : 0) | (in_intervals(h, p.position) ? kCandReportable : 0) |
+                  (!h->forced.empty() && h->forced.count(std::make_tuple(p.position, p.ref, p.alt)) ? kCandForced : 0);
         d.ref_len = (int32_t)p.ref.size();
         d.alt_len = (int32_t)p.alt.size();
         d.allele_off = (uint32_t)arena.size();
@@ -302,8 +306,25 @@ float candidate_frequency(const pb2_handle* h, const HostCand& c, const SpanIngr
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ forced-genotyping alleles
+int explicit_add_forced_candidates(pb2_handle* h, int32_t up_to) {   // SmallVariantCaller.AddForcedAlleleAsCandidate (:118-155)
+    while (!h->forced_pending.empty()) {
+        auto it = h->forced_pending.begin();
+        if (up_to >= 0 && it->first > up_to) break;
+        for (auto& ra : it->second) {
+            HostCand c;
+            c.position = it->first; c.ref = ra.first; c.alt = ra.second;
+            // CandidateAllele type of a forced allele (:131-147)
+            c.type = (c.ref.size() == 1 && c.alt.size() == 1) ? CAT_SNV : c.ref.size() == c.alt.size() ? CAT_MNV : c.ref.size() > c.alt.size() ? CAT_DEL : CAT_INS;
+            explicit_add_candidate(h, c);
+        }
+        h->forced_pending.erase(it);
+    }
+    return PB2_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ AlleleCaller.Call, explicit part
-int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, std::vector<pb2_call_record>& called,
+int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, int32_t ref_lo, int32_t ref_hi, std::vector<pb2_call_record>& called,
                         std::vector<pb2_call_record_ext>& called_ext) {
     if (batch.empty()) return PB2_OK;
     std::vector<HostCand> cs;
@@ -312,6 +333,38 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
     BatchCtx ctx(h);
     std::vector<uint8_t>& arena = h->arena;
     int rc;
+    // anchor-summed counts [allele][direction] of a few positions on the host (what RegionState.GetAllCandidates :417-440 sums for a reference candidate)
+    auto host_point_counts = [&](std::vector<int32_t> positions, std::unordered_map<int32_t, std::array<int32_t, kNumAlleles * kNumDirs>>& out) -> int {
+        std::sort(positions.begin(), positions.end());
+        positions.erase(std::unique(positions.begin(), positions.end()), positions.end());
+        const int r0 = ctx.ensure_rows(positions);
+        if (r0 != PB2_OK) return r0;
+        std::vector<int32_t> table((size_t)ctx.n_rows * kNumBins);
+        if (!table.empty()) CUX(h, cudaMemcpy(table.data(), ctx.counts.p, table.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int32_t pos : positions) {
+            std::array<int32_t, kNumAlleles * kNumDirs> sums{};
+            const int32_t r = ctx.row_of_pos[pos];
+            if (r >= 0)
+                for (int ad = 0; ad < kNumAlleles * kNumDirs; ad++)
+                    for (int an = 0; an < kNumAnchors; an++) sums[(size_t)ad] += table[(size_t)r * kNumBins + (size_t)(ad * kNumAnchors + an)];
+            out[pos] = sums;
+        }
+        return PB2_OK;
+    };
+    auto allele_index = [](char base) { return base == 'A' ? AT_A : base == 'C' ? AT_C : base == 'G' ? AT_G : base == 'T' ? AT_T : AT_N; };
+    if (!h->cfg.call_mnvs) {
+        // CallMNVs off: SNV candidates are the counts themselves and never enter this table — except forced SNV alleles, which arrive with zero
+        // support and merge with what the finder raised from the reads (RegionState.AddCandidate :94-174): that support is the count of their base
+        std::vector<int32_t> snv_pos;
+        for (auto& c : cs) if (c.type == CAT_SNV) snv_pos.push_back(c.position);
+        if (!snv_pos.empty()) {
+            std::unordered_map<int32_t, std::array<int32_t, kNumAlleles * kNumDirs>> pc;
+            rc = host_point_counts(snv_pos, pc);
+            if (rc != PB2_OK) return rc;
+            for (auto& c : cs)
+                if (c.type == CAT_SNV) for (int d = 0; d < 3; d++) c.support[d] = pc[c.position][(size_t)(allele_index(c.alt[0]) * kNumDirs + d)];
+        }
+    }
 
     // ---- VariantCollapser.Collapse (:31-113)
     const bool any_open = std::any_of(cs.begin(), cs.end(), [](const HostCand& c) { return c.open_left || c.open_right; });
@@ -395,37 +448,58 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
             else callable.push_back(p);
         }
     }
-    if (!failed.empty() && h->cfg.output_gvcf) {
-        // With reference calls on, the batch also holds one Reference candidate per position (RegionState.GetAllCandidates :393-449) and the
-        // reallocator treats them like any callable allele (IsPotentialOverlap :262): a failed gapped MNV hands its support to the reference allele
-        // at a position where its alternate base equals the reference base. Only those positions can match (OverlapMatches), so only they are built.
-        std::vector<int32_t> gap_pos;
-        for (Piece* f : failed)
-            for (size_t i = 0; i < f->ref.size(); i++) {
-                const int32_t pos = f->position + (int32_t)i;
-                if (f->ref[i] == f->alt[i] && pos >= 1 && pos <= h->chr_len && (max_cleared < 0 || pos <= max_cleared)) gap_pos.push_back(pos);
+    {
+        // Reference candidates of the batch (RegionState.GetAllCandidates :393-449). With reference calls on there is one per position and the
+        // reallocator treats them like any callable allele (IsPotentialOverlap :262): a failed gapped MNV hands its support to the reference allele at a
+        // position where its alternate base equals the reference base; only those positions can match (OverlapMatches), so only they are built here —
+        // the rest stay with the hot kernel's per-locus reference stream. With reference calls off and forced alleles present there is one at every
+        // forced position of the batch's blocks, reported whatever its support.
+        std::vector<int32_t> gap_pos, forced_pos;
+        if (!failed.empty() && h->cfg.output_gvcf)
+            for (Piece* f : failed)
+                for (size_t i = 0; i < f->ref.size(); i++) {
+                    const int32_t pos = f->position + (int32_t)i;
+                    if (f->ref[i] == f->alt[i] && pos >= 1 && pos <= h->chr_len && (max_cleared < 0 || pos <= max_cleared)) gap_pos.push_back(pos);
+                }
+        if (!h->cfg.output_gvcf && !h->forced_positions.empty()) {
+            // block by block; inside a block ChrIntervalSet.GetClipped (IntervalSet.cs:76-105) walks the one-position intervals in the forced set's own
+            // order and stops at the first one beyond the block — with an unsorted set that skips the rest, as in the reference
+            std::set<int32_t> block_keys;
+            for (int32_t pos : h->forced_positions) if (pos > ref_lo && pos <= ref_hi) block_keys.insert(block_key(pos));
+            for (int32_t k : block_keys) {
+                const int32_t start = (k - 1) * 1000 + 1, end = k * 1000;
+                for (int32_t pos : h->forced_positions) {
+                    if (pos > end) break;
+                    if (pos < start) continue;
+                    if (pos >= 1 && pos <= h->chr_len) forced_pos.push_back(pos);
+                }
             }
+        }
         std::sort(gap_pos.begin(), gap_pos.end());
         gap_pos.erase(std::unique(gap_pos.begin(), gap_pos.end()), gap_pos.end());
-        rc = ctx.ensure_rows(gap_pos);
-        if (rc != PB2_OK) return rc;
-        for (int32_t pos : gap_pos) {
-            std::vector<int32_t> row(kNumBins, 0);
-            const int32_t r = ctx.row_of_pos[pos];
-            if (r >= 0) CUX(h, cudaMemcpy(row.data(), ctx.counts.p + (size_t)r * kNumBins, sizeof(int32_t) * kNumBins, cudaMemcpyDeviceToHost));
-            const char base = (char)h->h_chr[(size_t)pos - 1];
-            const int ref_idx = base == 'A' ? AT_A : base == 'C' ? AT_C : base == 'G' ? AT_G : base == 'T' ? AT_T : AT_N;
-            int total = 0, sup[3] = {0, 0, 0};
-            for (int a = 0; a < kNumAlleles; a++)
-                for (int d = 0; d < kNumDirs; d++)
-                    for (int an = 0; an < kNumAnchors; an++) { const int v = row[(size_t)((a * kNumDirs + d) * kNumAnchors + an)]; total += v; if (a == ref_idx) sup[d] += v; }
-            if (!(h->have_intervals ? in_intervals(h, pos) : total > 0)) continue;
-            store.emplace_back();
-            Piece* p = &store.back();
-            p->position = pos; p->type = CAT_REF; p->ref.assign(1, base); p->alt.assign(1, base);
-            for (int d = 0; d < 3; d++) p->support[d] = sup[d];
-            p->allele_support = p->original_support = sup[0] + sup[1] + sup[2];
-            callable.push_back(p);
+        std::vector<int32_t> all_pos = gap_pos;
+        all_pos.insert(all_pos.end(), forced_pos.begin(), forced_pos.end());
+        if (!all_pos.empty()) {
+            std::unordered_map<int32_t, std::array<int32_t, kNumAlleles * kNumDirs>> pc;
+            rc = host_point_counts(all_pos, pc);
+            if (rc != PB2_OK) return rc;
+            auto add_ref = [&](int32_t pos, bool forced_position) {
+                const auto& sums = pc[pos];
+                const char base = (char)h->h_chr[(size_t)pos - 1];
+                const int ref_idx = allele_index(base);
+                int total = 0;
+                for (int32_t v : sums) total += v;
+                if (!forced_position && !(h->have_intervals ? in_intervals(h, pos) : total > 0)) return;
+                store.emplace_back();
+                Piece* p = &store.back();
+                p->position = pos; p->type = CAT_REF; p->ref.assign(1, base); p->alt.assign(1, base);
+                for (int d = 0; d < 3; d++) p->support[d] = sums[(size_t)(ref_idx * kNumDirs + d)];
+                p->allele_support = p->original_support = p->support[0] + p->support[1] + p->support[2];
+                p->keep_ref = forced_position;
+                callable.push_back(p);
+            };
+            for (int32_t pos : gap_pos) add_ref(pos, false);
+            for (int32_t pos : forced_pos) add_ref(pos, true);
         }
     }
     if (!failed.empty()) {
@@ -542,8 +616,12 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
         for (size_t i = 0; i < a->ref.size(); i++)
             if (a->ref[i] == a->alt[i]) h->gapped_ref[a->position + (int)i] += a->allele_support;
     }
+    // a failed MNV that is a forced allele is reported all the same (:98-106)
+    if (!h->forced.empty())
+        for (Piece* f : failed) if (h->forced.count(std::make_tuple(f->position, f->ref, f->alt))) callable.push_back(f);
     // reference alleles the reallocation left untouched stay with the per-locus reference stream of the hot kernel
-    callable.erase(std::remove_if(callable.begin(), callable.end(), [](const Piece* p) { return p->type == CAT_REF && p->allele_support == p->original_support; }),
+    callable.erase(std::remove_if(callable.begin(), callable.end(),
+                                  [](const Piece* p) { return p->type == CAT_REF && !p->keep_ref && p->allele_support == p->original_support; }),
                    callable.end());
     // ---- every callable allele: ProcessVariant, IsCallable && ShouldReport (:96-118)
     if (!callable.empty()) {
@@ -552,7 +630,7 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
         rc = score_pieces(ctx, callable, arena, &recs, &flags, nullptr, nullptr);
         if (rc != PB2_OK) return rc;
         for (size_t i = 0; i < recs.size(); i++) {
-            if (!(flags[i] & 2)) continue;
+            if (!(flags[i] & (2 | 4))) continue;   // IsCallable && ShouldReport, or a forced allele (:108-118)
             called.push_back(recs[i]);
             pb2_call_record_ext e;
             memset(&e, 0, sizeof(e));
@@ -586,6 +664,7 @@ int explicit_call_resident(pb2_handle* h, Segment& seg, cudaStream_t side) {
     cudaStream_t st = h->stream;
     ResidentPlan* plan = static_cast<ResidentPlan*>(h->resident_explicit);
     if (plan == nullptr) {
+        if (!h->forced.empty()) return pb2_fail(h, PB2_ERR_UNSUPPORTED, "pb2_call_resident: forced alleles are reported through pb2_flush");
         for (auto& c : h->cands) {
             if (!c.alive) continue;
             if (c.type == CAT_MNV || c.type == CAT_SNV) return pb2_fail(h, PB2_ERR_UNSUPPORTED, "pb2_call_resident: MNV/SNV candidates need the MNV reallocator; use pb2_flush");

@@ -1,7 +1,9 @@
 // Internal to libpisces_b200.so: the handle, a staged segment, the read buffer and the explicit-candidate table (host side).
 #pragma once
 #include <map>
+#include <set>
 #include <string>
+#include <tuple>
 #include <vector>
 #include "pb2_candidates.cuh"
 #include "pb2_kernels.cuh"
@@ -148,6 +150,11 @@ struct pb2_handle {
     int64_t resident_graph_launches = 0;              // kernels inside the graph
     unsigned long long* h_counters = nullptr;         // pinned: the segment's counters after a step
     std::vector<uint8_t> arena;                       // allele bytes the last flush's records point into
+    // ---- forced-genotyping alleles (pb2_set_forced_alleles)
+    std::set<std::tuple<int32_t, std::string, std::string>> forced;                             // AlleleCaller.ForcedGtAlleles (position, ref, alt)
+    std::map<int32_t, std::vector<std::pair<std::string, std::string>>> forced_pending;         // SmallVariantCaller._unProcessedForcedAllelesByPos
+    std::vector<std::tuple<int32_t, std::string, std::string>> forced_order;                    // the HashSet's enumeration (= insertion) order
+    std::vector<int32_t> forced_positions;   // one per forced allele inside the intervals, in that order: RegionState.CreateIntervalsFromAllels (:455-468)
     int64_t total_collapsed = 0;
 };
 
@@ -158,9 +165,12 @@ void explicit_add_candidate(pb2_handle* h, const HostCand& c);
 // The explicit-candidate part of AlleleCaller.Call for one batch of candidates (indices into h->cands, in batch order): VariantCollapser, MNV scoring
 // + MnvReallocator, gapped-MNV reference counts, final ProcessVariant of every callable allele on the device. Called alleles (IsCallable &&
 // ShouldReport) are appended to `called`; candidates that go back to the state (not cleared / MNV leftovers) are re-added to h->cands.
-// max_cleared < 0 = null (everything is cleared).
-int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, std::vector<pb2_call_record>& called,
+// max_cleared < 0 = null (everything is cleared). (ref_lo, ref_hi] are the positions of the batch's blocks: with forced alleles and reference calls off,
+// RegionState.GetAllCandidates (:383-453) adds a Reference candidate at every forced position in them.
+int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, int32_t ref_lo, int32_t ref_hi, std::vector<pb2_call_record>& called,
                         std::vector<pb2_call_record_ext>& called_ext);
+// SmallVariantCaller.AddForcedAlleleAsCandidate (:118-155): forced alleles at positions <= up_to (< 0: all) become zero-support candidates.
+int explicit_add_forced_candidates(pb2_handle* h, int32_t up_to);
 // Finds the candidates of the reads in R[first_read, end) on the device (CandidateVariantFinder.FindCandidates) and adds them to the table.
 int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_read);
 // pb2_call_resident: gather + score + append on the device, no host round trip; only for candidates that need neither the collapser nor the MNV logic.

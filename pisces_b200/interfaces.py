@@ -270,6 +270,19 @@ class GpuStateManager:
         ab = np.frombuffer(arena, dtype=np.uint8) if len(arena) else np.zeros(1, dtype=np.uint8)
         self._chk(self._L.pb2_push_candidates(self._h, candidates.ctypes.data, len(candidates), ab.ctypes.data, len(arena)))
 
+    def SetForcedAlleles(self, alleles):
+        """The forcedGtAlleles of Factory.CreateSomaticVariantCaller / SmallVariantCaller's constructor (SmallVariantCaller.cs:48-77) for this chromosome:
+        an iterable of (position, ref, alt). pb2_set_forced_alleles."""
+        alleles = list(alleles)
+        arr = np.zeros(max(len(alleles), 1), dtype=N.CANDIDATE_DTYPE)
+        buf = bytearray()
+        for i, (pos, ref, alt) in enumerate(alleles):
+            r = arr[i]
+            r["position"], r["ref_len"], r["alt_len"], r["allele_offset"] = pos, len(ref), len(alt), len(buf)
+            buf += ref.encode() + alt.encode()
+        ab = np.frombuffer(bytes(buf), dtype=np.uint8) if len(buf) else np.zeros(1, dtype=np.uint8)
+        self._chk(self._L.pb2_set_forced_alleles(self._h, arr.ctypes.data, len(alleles), ab.ctypes.data, len(buf)))
+
     def AlleleArena(self):
         """Bytes that pb2_call_record.allele_bytes of the last Call points into for alleles longer than 4 bases."""
         p, n = C.c_void_p(), C.c_int64()

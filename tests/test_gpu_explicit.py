@@ -36,8 +36,8 @@ def compare_records(orecs, precs, arena, check_qsum=False):
         assert o.filter_mask == int(p["filters"]), (ctx, o.filter_mask, int(p["filters"]))
         assert o.noise_level == int(p["noise_level"]), ctx
         assert o.fraction_no_calls == float(p["fraction_no_calls"]), ctx
-        assert (bool(o.bias_acceptable), bool(o.var_both_strands), bool(o.cov_both_strands)) == \
-            (bool(p["sb_flags"] & 1), bool(p["sb_flags"] & 2), bool(p["sb_flags"] & 4)), ctx
+        assert (bool(o.bias_acceptable), bool(o.var_both_strands), bool(o.cov_both_strands), bool(o.forced)) == \
+            (bool(p["sb_flags"] & 1), bool(p["sb_flags"] & 2), bool(p["sb_flags"] & 4), bool(p["sb_flags"] & 8)), ctx
         for a, b in ((o.bias_score, float(p["bias_score"])), (o.gatk_bias_score, float(p["gatk_bias_score"]))):
             if math.isinf(a) or math.isnan(a):
                 assert (math.isinf(b) and (a > 0) == (b > 0)) or (math.isnan(a) and math.isnan(b)), ctx
@@ -173,13 +173,17 @@ def test_indel_repeat_and_rmxn_filters():
     compare_records(orecs, precs, arena)
 
 
-def _reads_both(reads, ref, o_kw, p_kw, intervals=None, flush_every=None):
+def _reads_both(reads, ref, o_kw, p_kw, intervals=None, flush_every=None, forced=()):
     pb = _pb()
     oc = ob.Caller(ob.default_config(**o_kw), "chr1", ref, intervals=intervals)
+    for f in forced:
+        oc.add_forced(*f)
     for rd in reads:
         oc.add_read(U.to_oracle(rd))
     oc.finish()
     sm = pb.GpuStateManager(pb.make_config(**p_kw), "chr1", ref, intervals=intervals)
+    if forced:
+        sm.SetForcedAlleles(forced)
     caller = pb.GpuAlleleCaller()
     precs, arenas = [], []
     if flush_every:
@@ -246,6 +250,45 @@ def test_reads_with_mnvs_match_oracle(seed):
     assert ncoll == oc.L.po_caller_total_collapsed(oc.h)
 
 
+@pytest.mark.parametrize("gvcf", [0, 1])
+@pytest.mark.parametrize("mnvs", [0, 1])
+def test_forced_alleles_match_oracle(mnvs, gvcf):
+    """Forced-genotyping alleles (SmallVariantCaller.cs:48-77,118-155; AlleleCaller.cs:98-118,143-150): alleles the reads support and alleles they do
+    not, SNVs / indels (/ MNVs with CallMNVs), inside and outside the intervals, streamed block by block. Reported whether callable or not, with the
+    reference allele of their position kept beside the ones that are only reported because they are forced."""
+    rng = np.random.default_rng(70 + 2 * mnvs + gvcf)
+    ref = U.random_reference(rng, 3300)
+    hot = {int(p): ("ACGT"[int(rng.integers(0, 4))], float(rng.uniform(0.02, 0.5))) for p in rng.integers(60, 3100, 40)}
+    reads = U.make_reads(rng, ref, 7000, read_len=60, hotspots=hot, del_rate=0.04, ins_rate=0.04, clip_rate=0.1, indel_sites=30, linked_hotspots=bool(mnvs))
+    forced = []
+    for p, (b, _) in list(hot.items())[:25]:        # alleles with support (some callable, some not)
+        if ref[p - 1] != b:
+            forced.append((p, ref[p - 1], b))
+    for p in rng.integers(60, 3100, 25):             # alleles without any support, a few at uncovered or boundary positions
+        p = int(p)
+        alt = "ACGT"[("ACGT".index(ref[p - 1]) + 1 + int(rng.integers(0, 3))) % 4]
+        forced.append((p, ref[p - 1], alt))
+    for p in (1000, 1001, 2000, 3290):
+        forced.append((p, ref[p - 1], "ACGT"[("ACGT".index(ref[p - 1]) + 1) % 4]))
+    for p in rng.integers(100, 3000, 8):
+        p = int(p)
+        forced.append((p, ref[p - 1:p + 2], ref[p - 1]))              # a 2-base deletion
+        forced.append((p + 7, ref[p + 6], ref[p + 6] + "GT"))        # a 2-base insertion
+    if mnvs:
+        for p in rng.integers(100, 3000, 8):
+            p = int(p)
+            forced.append((p, ref[p - 1:p + 1], "".join("ACGT"[("ACGT".index(c) + 2) % 4] for c in ref[p - 1:p + 1])))
+    forced = sorted(set(forced))
+    if gvcf == 0 and mnvs == 1:     # the forced set's own (file) order decides which reference candidates GetClipped reaches: keep it unsorted once
+        forced = [forced[int(i)] for i in rng.permutation(len(forced))]
+    intervals = [(50, 1500), (1700, 3300)]
+    kw = dict(output_gvcf=gvcf, collapse=mnvs, call_mnvs=mnvs, max_size_mnv=3, max_gap_mnv=1)
+    oc, chunks, _ = _reads_both(reads, ref, dict(kw, min_vq=20), dict(kw, min_variant_qscore=20), intervals=intervals, flush_every=900, forced=forced)
+    orecs = oc.records()
+    assert sum(1 for o in orecs if o.forced) > 20 and sum(1 for o in orecs if o.type == ob.REFERENCE) >= 1
+    _compare_chunks(orecs, chunks)
+
+
 class _RecordView:
     """A pb2_call_record shaped like the oracle's record, for the VCF text restatement (oracle/vcf_text.py, test infrastructure)."""
     _FILTER_ORDER = [4, 3, 12, 0, 2, 7, 9, 5, 6, 10]   # the order AlleleProcessor.ApplyFilters / the genotyper add them (AlleleProcessor.cs:25-71)
@@ -262,12 +305,15 @@ class _RecordView:
         self.n_filters = len(self.filters)
         self.total_coverage, self.allele_support, self.ref_support = int(p["total_coverage"]), int(p["allele_support"]), int(p["reference_support"])
         self.frequency = np.float32(0) if self.total_coverage == 0 else min(np.float32(self.allele_support) / np.float32(self.total_coverage), np.float32(1))
-        self.noise_level, self.gatk_bias_score, self.forced = int(p["noise_level"]), float(p["gatk_bias_score"]), 0
+        self.noise_level, self.gatk_bias_score, self.forced = int(p["noise_level"]), float(p["gatk_bias_score"]), int(p["sb_flags"]) >> 3 & 1
 
 
-def test_phix_full_text_golden_through_cuda_path():
-    """The reference's own full-text golden (PhiX_S3.bam -> PhiX_S3.noisy.vcf, ForcedGTFxnlTest.cs:11-112) reproduced line by line from the records
-    the CUDA path emits: MNVs up to 10 with gaps of 5, collapsing, MNV reallocation, gapped-MNV reference take-away, q-scores, strand bias."""
+@pytest.mark.parametrize("min_vq,forced,golden", [(1, False, "phix_s3_noisy.records.vcf"), (1, True, "phix_s3_forced1.records.vcf"),
+                                                  (20, True, "phix_s3_forced2.records.vcf")])
+def test_phix_full_text_golden_through_cuda_path(min_vq, forced, golden):
+    """The reference's own full-text goldens (PhiX_S3.bam -> PhiX_S3.noisy.vcf, .Forced1.vcf, .Forced2.vcf; ForcedGTFxnlTest.cs:11-112) reproduced
+    line by line from the records the CUDA path emits: MNVs up to 10 with gaps of 5, collapsing, MNV reallocation, gapped-MNV reference take-away,
+    q-scores, strand bias, and the forced alleles of PhiX_S3.forcedGTInput.vcf (pb2_set_forced_alleles)."""
     import gzip
     import json
     import os
@@ -276,13 +322,16 @@ def test_phix_full_text_golden_through_cuda_path():
     G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     d = json.load(gzip.open(os.path.join(G, "phix_s3_reads.json.gz"), "rt"))
     genome = open(os.path.join(G, "phix_genome.txt")).read().strip()
-    okw = dict(min_coverage=2, min_base_call_quality=10, min_vq=1, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1, max_size_mnv=10,
+    okw = dict(min_coverage=2, min_base_call_quality=10, min_vq=min_vq, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1, max_size_mnv=10,
                max_gap_mnv=5, no_call_filter=1.0)
-    pkw = dict(min_coverage=2, min_base_call_quality=10, min_variant_qscore=1, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1, max_size_mnv=10,
+    pkw = dict(min_coverage=2, min_base_call_quality=10, min_variant_qscore=min_vq, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1, max_size_mnv=10,
                max_gap_mnv=5, no_call_filter=1.0)
     # AlignmentSource.ShouldSkipRead (AlignmentsSource.cs:84-92): mapped, primary, not duplicate, mapq >= 1, has a CIGAR — host-side filter
     reads = [r for r in d["reads"] if not (r["flag"] & 0x4) and not (r["flag"] & 0x100) and not (r["flag"] & 0x400) and r["mapq"] >= 1 and r["cigar"]]
     sm = pb.GpuStateManager(pb.make_config(**pkw), "phix", genome)
+    if forced:   # Factory.cs:80-93: forced alleles with a non-ACGT alternate (".") are dropped by the host
+        fa = json.load(open(os.path.join(G, "phix_forced_alleles.json")))
+        sm.SetForcedAlleles([(p, r, a) for p, r, a in fa if all(ch in "ACGT" for ch in a)])
     caller = pb.GpuAlleleCaller()
     views = []
     for i in range(0, len(reads), 50):      # streamed like SmallVariantCaller.Execute: push a few reads, call up to the last read's position - 1
@@ -297,7 +346,7 @@ def test_phix_full_text_golden_through_cuda_path():
     sm.close()
     vt = VcfText(ob.default_config(**okw), ob.FILTERS, ob.GENOTYPES)
     got = [vt.line("phix", v) for v in views]
-    exp = [l.rstrip("\n") for l in open(os.path.join(G, "phix_s3_noisy.records.vcf"))]
+    exp = [l.rstrip("\n") for l in open(os.path.join(G, golden))]
     assert len(got) == len(exp)
     for a, b in zip(got, exp):
         assert a == b
