@@ -27,7 +27,8 @@ class Config(C.Structure):
         [("no_call_filter", C.c_float)] + \
         [(n, C.c_int32) for n in ("call_mnvs", "max_size_mnv", "max_gap_mnv", "collapse")] + \
         [(n, C.c_float) for n in ("collapse_freq_threshold", "collapse_freq_ratio_threshold")] + \
-        [(n, C.c_int32) for n in ("exclude_mnvs_from_collapsing", "tracked_anchor_size", "output_gvcf", "source_is_stitched", "source_is_collapsed", "apply_validation")]
+        [(n, C.c_int32) for n in ("exclude_mnvs_from_collapsing", "tracked_anchor_size", "output_gvcf", "source_is_stitched", "source_is_collapsed", "apply_validation")] + \
+        [(n, C.c_float) for n in ("diploid_minor_vf", "diploid_major_vf", "diploid_sum_vf_multiallelic")] + [("is_male", C.c_int32)]
 
 
 class ReadStruct(C.Structure):
@@ -110,8 +111,28 @@ def lib():
         L.po_somatic_gq.argtypes = [C.c_int32] * 5 + [C.c_float, C.c_int32, C.c_int32]
         L.po_somatic_genotype.argtypes = [C.c_int32] * 4 + [C.c_float, C.c_int32]
         L.po_anchor_adjusted_count.argtypes = [C.POINTER(C.c_int32)] + [C.c_int32] * 5
+        L.po_mathnet_binomial_cdf.argtypes = [C.c_double, C.c_int32, C.c_double]
+        L.po_mathnet_binomial_cdf.restype = C.c_double
+        L.po_mathnet_binomial_probability_ln.argtypes = [C.c_double, C.c_int32, C.c_int32]
+        L.po_mathnet_binomial_probability_ln.restype = C.c_double
+        L.po_diploid_gq.argtypes = [C.c_int32] * 5
+        L.po_haploid_gq.argtypes = [C.c_int32] * 5
+        L.po_genotype_locus.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_char_p), C.c_int32, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int32)]
+        L.po_ploidy_for_chr.argtypes = [C.c_int32, C.c_int32, C.c_char_p]
         _lib = L
     return _lib
+
+
+def genotype_locus(ploidy, alleles, min_depth=100, minor_vf=0.20, major_vf=0.70, sum_vf=0.80):
+    """alleles: list of (type, allele_support, total_coverage, ref_support[, "REF>ALT"]). Returns (genotype name, pruned flags, multiallelic flag, gqs)."""
+    n = len(alleles)
+    arr = lambda k: (C.c_int32 * max(n, 1))(*[a[k] for a in alleles])
+    names = (C.c_char_p * max(n, 1))(*[(a[4].encode() if len(a) > 4 else b"A>C") for a in alleles])
+    pruned, multi, gq = (C.c_int32 * max(n, 1))(), C.c_int32(), (C.c_int32 * max(n, 1))()
+    g = lib().po_genotype_locus(ploidy, n, arr(0), arr(1), arr(2), arr(3), names, min_depth, minor_vf, major_vf, sum_vf, pruned, C.byref(multi), gq)
+    return GENOTYPES[g], list(pruned)[:n], multi.value, list(gq)[:n]
 
 
 def default_config(**kw):

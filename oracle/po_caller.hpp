@@ -4,6 +4,7 @@
 #pragma once
 #include "po_calc.hpp"
 #include "po_finder.hpp"
+#include "po_genotype.hpp"
 
 namespace po {
 
@@ -66,7 +67,7 @@ inline int ComputeIndelRepeatLength(const CalledAllele& allele, const std::strin
 }
 
 // AlleleProcessor.Process / ApplyFilters :16-71
-inline void AlleleProcessorProcess(CalledAllele& a, const Config& cfg, const std::string& chrSeq, bool isStitchedSource) {
+inline void AlleleProcessorProcess(CalledAllele& a, const Config& cfg, const std::string& chrSeq, bool isStitchedSource, float variantFreqFilter) {
     a.SetFractionNoCalls();
     a.Filters.clear();
     if (cfg.LowDepthFilter >= 0 && a.TotalCoverage < cfg.LowDepthFilter) a.AddFilter(F_LowDepth);
@@ -79,9 +80,8 @@ inline void AlleleProcessorProcess(CalledAllele& a, const Config& cfg, const std
             if (cfg.IndelRepeatFilter <= ComputeIndelRepeatLength(a, chrSeq)) a.AddFilter(F_IndelRepeatLength);
         }
         if (RMxNShouldFilter(a, cfg, chrSeq)) a.AddFilter(F_RMxN);
-        // VariantFreqFilter = genotypeCalculator.MinVarFrequencyFilter (Factory.cs:166) = max(MinimumFrequencyFilter, MinimumFrequency) (SomaticGenotyper.SetMinFreqFilter)
-        float vff = cfg.MinimumFrequencyFilter > cfg.MinimumFrequency ? cfg.MinimumFrequencyFilter : cfg.MinimumFrequency;
-        if (a.Frequency() < vff) a.AddFilter(F_LowVariantFrequency);
+        // VariantFreqFilter = genotypeCalculator.MinVarFrequencyFilter (Factory.cs:166) = max(MinimumFrequencyFilter, MinVarFrequency) (SetMinFreqFilter)
+        if (a.Frequency() < variantFreqFilter) a.AddFilter(F_LowVariantFrequency);
         if (isStitchedSource && a.AlternateAllele.find('N') != std::string::npos) a.AddFilter(F_StrandBias);
     }
 }
@@ -354,11 +354,19 @@ struct AlleleCaller {
     std::unique_ptr<VariantCollapser> collapser;
     std::set<ForcedAllele> ForcedGtAlleles;
     int TotalNumCalled = 0;
+    // GenotypeCreator.CreateGenotypeCalculator (GenotypeCreator.cs:10-37) for this chromosome; VariantCallerConfig.MinFrequency = MinVarFrequency,
+    // .VariantFreqFilter = MinVarFrequencyFilter (Factory.cs:160,166); the locus processor follows the SAMPLE ploidy (Factory.cs:145-147)
+    int chrPloidy = PM_Somatic;
+    float minFrequency = 0, variantFreqFilter = 0;
 
     AlleleCaller(const Config& c, const std::string& chr, const std::string* seq, ChrIntervalSet* iv)
         : cfg(c), chrName(chr), chrSeq(seq), intervalSet(iv),
           coverage(c.TrackedAnchorSize > 0, c.SourceIsCollapsed && c.SourceIsStitched) {  // Factory.cs:193-199
         if (cfg.Collapse) collapser = std::make_unique<VariantCollapser>(&coverage, cfg.CollapseFreqThreshold, cfg.CollapseFreqRatioThreshold, cfg.ExcludeMNVsFromCollapsing);
+        chrPloidy = GetPloidyForThisChr(cfg.ploidy, cfg.IsMale, chrName);
+        if (chrPloidy == PM_DiploidByAdaptiveGT) throw std::runtime_error("DiploidByAdaptiveGT genotyper is out of scope (SURVEY 8f rank 4)");
+        minFrequency = chrPloidy == PM_Somatic ? cfg.MinimumFrequency : cfg.DiploidMinorVF;
+        variantFreqFilter = cfg.MinimumFrequencyFilter > minFrequency ? cfg.MinimumFrequencyFilter : minFrequency;
     }
     int TotalNumCollapsed() const { return collapser ? collapser->TotalNumCollapsed : 0; }
     bool IsForcedAllele(const CalledAllele& a) const { return ForcedGtAlleles.count(ForcedAllele{a.Chromosome, a.ReferencePosition, a.ReferenceAllele, a.AlternateAllele}) > 0; }
@@ -369,16 +377,16 @@ struct AlleleCaller {
             int NL = cfg.NoiseLevelUsedForQScoring();
             if (cfg.noiseModel == NM_Window) VariantQualityCompute(v, cfg.MaximumVariantQScore, (int)PtoQ(v.SumOfBaseQuality / v.TotalCoverage));
             else VariantQualityCompute(v, cfg.MaximumVariantQScore, NL);
-            // _config.MinFrequency = genotypeCalculator.MinVarFrequency = MinimumFrequency (Factory.cs:140,160)
-            v.StrandBiasResults = CalculateStrandBiasResults(v.EstimatedCoverageByDirection.data(), v.SupportByDirection.data(), NL, cfg.MinimumFrequency,
+            // _config.MinFrequency = genotypeCalculator.MinVarFrequency (Factory.cs:140,160)
+            v.StrandBiasResults = CalculateStrandBiasResults(v.EstimatedCoverageByDirection.data(), v.SupportByDirection.data(), NL, minFrequency,
                                                              cfg.StrandBiasAcceptanceCriteria, cfg.strandBiasModel);
         }
-        AlleleProcessorProcess(v, cfg, *chrSeq, source.ExpectStitchedReads());
+        AlleleProcessorProcess(v, cfg, *chrSeq, source.ExpectStitchedReads(), variantFreqFilter);
     }
     bool IsCallable(const CalledAllele& a) {  // :236-258
         if (a.Type == Reference) { TotalNumCalled++; return true; }
         if (a.TotalCoverage < cfg.MinimumCoverage && !cfg.OutputGvcfFile) return false;
-        if (a.TotalCoverage != 0 && a.Frequency() < cfg.MinimumFrequency) return false;
+        if (a.TotalCoverage != 0 && a.Frequency() < minFrequency) return false;
         if (a.VariantQscore < cfg.MinimumVariantQScore) return false;
         TotalNumCalled++;
         return true;
@@ -396,16 +404,31 @@ struct AlleleCaller {
         }
         return taken;
     }
-    void ComputeGenotypeAndFilterAllele(std::vector<CalledPtr>& at) {  // :143-177 (somatic genotyper: nothing pruned)
+    void ComputeGenotypeAndFilterAllele(std::vector<CalledPtr>& at) {  // :143-177
         bool anyVar = false;
         for (auto& v : at) if (v->Type != Reference && !v->IsForcedToReport) anyVar = true;
         if (anyVar) at.erase(std::remove_if(at.begin(), at.end(), [](const CalledPtr& v) { return v->Type == Reference; }), at.end());
-        // SomaticGenotyper.SetGenotypes :51-63 ; ctor args Factory.cs:131-141: minVariantFrequencyFilter = MinimumFrequencyFilter,
-        // MinDepthToGenotype = MinimumCoverage, targetLOD = TargetLODFrequency
-        for (auto& a : at) {
-            if (a->IsForcedToReport) continue;
-            a->genotype = CalculateSomaticGenotype(*a, cfg.MinimumFrequencyFilter, cfg.MinimumCoverage);
-            a->GenotypeQscore = SomaticGenotypeQuality(*a, cfg.TargetLODFrequency, cfg.MinimumGenotypeQScore, cfg.MaximumGenotypeQScore);
+        std::vector<CalledPtr> toGenotype;
+        for (auto& a : at) if (!a->IsForcedToReport) toGenotype.push_back(a);
+        std::vector<CalledPtr> toPrune;
+        if (chrPloidy == PM_Somatic) {
+            // SomaticGenotyper.SetGenotypes :51-63 ; ctor args Factory.cs:131-141: minVariantFrequencyFilter = MinimumFrequencyFilter,
+            // MinDepthToGenotype = MinimumCoverage, targetLOD = TargetLODFrequency; nothing is pruned
+            for (auto& a : toGenotype) {
+                a->genotype = CalculateSomaticGenotype(*a, cfg.MinimumFrequencyFilter, cfg.MinimumCoverage);
+                a->GenotypeQscore = SomaticGenotypeQuality(*a, cfg.TargetLODFrequency, cfg.MinimumGenotypeQScore, cfg.MaximumGenotypeQScore);
+            }
+        } else {
+            DiploidThresholdingParameters snv;
+            snv.MinorVF = cfg.DiploidMinorVF; snv.MajorVF = cfg.DiploidMajorVF; snv.SumVFforMultiAllelicSite = cfg.DiploidSumVFforMultiAllelicSite;
+            toPrune = chrPloidy == PM_Haploid
+                          ? HaploidSetGenotypes(toGenotype, cfg.MinimumCoverage, snv.MinorVF, snv.MajorVF, cfg.MinimumGenotypeQScore, cfg.MaximumGenotypeQScore)
+                          : DiploidSetGenotypes(toGenotype, cfg.MinimumCoverage, snv, snv, cfg.MinimumGenotypeQScore, cfg.MaximumGenotypeQScore);
+        }
+        for (auto& p : toPrune) {   // :153-162: pruned unless it is a forced allele; List.Remove = first element that Equals (reference equality for CalledAllele)
+            if (IsForcedAllele(*p)) continue;
+            auto it = std::find(at.begin(), at.end(), p);
+            if (it != at.end()) at.erase(it);
         }
         for (auto& a : at)
             if (cfg.LowGenotypeQualityFilter >= 0 && (float)a->GenotypeQscore < (float)cfg.LowGenotypeQualityFilter) a->AddFilter(F_LowGenotypeQuality);
@@ -440,7 +463,10 @@ struct AlleleCaller {
             if (IsForcedAllele(*a) && !(IsCallable(*a) && ShouldReport(*a))) { a->IsForcedToReport = true; a->AddFilter(F_ForcedReport); }
             if ((IsCallable(*a) && ShouldReport(*a)) || IsForcedAllele(*a)) byPos[a->ReferencePosition].push_back(a);
         }
-        for (auto& kv : byPos) ComputeGenotypeAndFilterAllele(kv.second);  // SomaticLocusProcessor.Process is a no-op
+        for (auto& kv : byPos) {
+            ComputeGenotypeAndFilterAllele(kv.second);
+            if (cfg.ploidy == PM_DiploidByThresholding) DiploidLocusProcess(kv.second);   // Factory.cs:145-147; SomaticLocusProcessor.Process is a no-op
+        }
         return byPos;
     }
 };

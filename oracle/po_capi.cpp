@@ -6,7 +6,7 @@
 using namespace po;
 
 namespace po {
-double MathNetBinomialCdf(double, int, double) { throw std::runtime_error("Diploid strand-bias model (MathNet Binomial CDF) not restated yet"); }
+double MathNetBinomialCdf(double p, int n, double x) { return mathnet::BinomialCdf(p, n, x); }   // Distributions.Binomial(p, n).CumulativeDistribution(x)
 }
 
 static thread_local std::string g_err;
@@ -25,6 +25,7 @@ void po_default_config(po_config* c) {
     c->collapse_freq_threshold = d.CollapseFreqThreshold; c->collapse_freq_ratio_threshold = d.CollapseFreqRatioThreshold;
     c->exclude_mnvs_from_collapsing = d.ExcludeMNVsFromCollapsing; c->tracked_anchor_size = d.TrackedAnchorSize; c->output_gvcf = d.OutputGvcfFile;
     c->source_is_stitched = d.SourceIsStitched; c->source_is_collapsed = d.SourceIsCollapsed; c->apply_validation = 1;
+    c->diploid_minor_vf = d.DiploidMinorVF; c->diploid_major_vf = d.DiploidMajorVF; c->diploid_sum_vf_multiallelic = d.DiploidSumVFforMultiAllelicSite; c->is_male = d.IsMale;
 }
 static Config FromC(const po_config* c) {
     Config d;
@@ -39,6 +40,7 @@ static Config FromC(const po_config* c) {
     d.CollapseFreqThreshold = c->collapse_freq_threshold; d.CollapseFreqRatioThreshold = c->collapse_freq_ratio_threshold;
     d.ExcludeMNVsFromCollapsing = c->exclude_mnvs_from_collapsing; d.TrackedAnchorSize = c->tracked_anchor_size; d.OutputGvcfFile = c->output_gvcf;
     d.SourceIsStitched = c->source_is_stitched; d.SourceIsCollapsed = c->source_is_collapsed; d.ApplyValidation = c->apply_validation != 0;
+    d.DiploidMinorVF = c->diploid_minor_vf; d.DiploidMajorVF = c->diploid_major_vf; d.DiploidSumVFforMultiAllelicSite = c->diploid_sum_vf_multiallelic; d.IsMale = c->is_male;
     return d;
 }
 static Read ToRead(const po_read* r) {
@@ -249,3 +251,37 @@ int32_t po_somatic_genotype(int32_t type, int32_t total_coverage, int32_t allele
 int32_t po_anchor_adjusted_count(const int32_t* bins, int32_t k, int32_t min_anchor, int32_t max_anchor, int32_t from_end, int32_t symmetric) {
     return AnchorAdjusted<int>(min_anchor, from_end != 0, k, 2 * k + 1, bins, max_anchor < 0 ? std::nullopt : std::optional<int>(max_anchor), symmetric != 0);
 }
+
+// ------------------------------------------------------------------ germline genotypers (po_genotype.hpp)
+double po_mathnet_binomial_cdf(double p, int32_t n, double x) { return mathnet::BinomialCdf(p, n, x); }
+double po_mathnet_binomial_probability_ln(double p, int32_t n, int32_t k) { return mathnet::BinomialProbabilityLn(p, n, k); }
+int32_t po_diploid_gq(int32_t genotype, int32_t total_coverage, int32_t allele_support, int32_t min_gq, int32_t max_gq) {
+    CalledAllele a; a.genotype = (Genotype)genotype; a.TotalCoverage = total_coverage; a.AlleleSupport = allele_support;
+    return DiploidGenotypeQuality(a, min_gq, max_gq);
+}
+int32_t po_haploid_gq(int32_t genotype, int32_t total_coverage, int32_t allele_support, int32_t min_gq, int32_t max_gq) {
+    CalledAllele a; a.genotype = (Genotype)genotype; a.TotalCoverage = total_coverage; a.AlleleSupport = allele_support;
+    return HaploidGenotypeQuality(a, min_gq, max_gq);
+}
+int32_t po_genotype_locus(int32_t ploidy, int32_t n, const int32_t* types, const int32_t* allele_support, const int32_t* total_coverage, const int32_t* ref_support,
+                          const char* const* ref_alt, int32_t min_depth, float minor_vf, float major_vf, float sum_vf, int32_t* pruned, int32_t* multiallelic,
+                          int32_t* gq_out) {
+    std::vector<CalledPtr> alleles;
+    for (int i = 0; i < n; i++) {
+        auto a = std::make_shared<CalledAllele>((AlleleCategory)types[i]);
+        a->Chromosome = "chr1"; a->ReferencePosition = 1;
+        a->AlleleSupport = allele_support[i]; a->TotalCoverage = total_coverage[i]; a->ReferenceSupport = ref_support[i];
+        if (ref_alt && ref_alt[i]) { std::string s(ref_alt[i]); auto k = s.find('>'); a->ReferenceAllele = s.substr(0, k); a->AlternateAllele = s.substr(k + 1); }
+        alleles.push_back(a);
+    }
+    DiploidThresholdingParameters snv; snv.MinorVF = minor_vf; snv.MajorVF = major_vf; snv.SumVFforMultiAllelicSite = sum_vf;
+    auto prune = ploidy == PM_Haploid ? HaploidSetGenotypes(alleles, min_depth, minor_vf, major_vf, 0, 100) : DiploidSetGenotypes(alleles, min_depth, snv, snv, 0, 100);
+    *multiallelic = 0;
+    for (int i = 0; i < n; i++) {
+        pruned[i] = std::find(prune.begin(), prune.end(), alleles[(size_t)i]) != prune.end();
+        for (auto f : alleles[(size_t)i]->Filters) if (f == F_MultiAllelicSite) *multiallelic = 1;
+        if (gq_out) gq_out[i] = alleles[(size_t)i]->GenotypeQscore;
+    }
+    return n ? (int32_t)alleles[0]->genotype : -1;
+}
+int32_t po_ploidy_for_chr(int32_t sample_ploidy, int32_t is_male, const char* chr_name) { return GetPloidyForThisChr(sample_ploidy, is_male, chr_name); }

@@ -21,6 +21,8 @@ typedef struct po_config {
     float collapse_freq_threshold, collapse_freq_ratio_threshold;
     int32_t exclude_mnvs_from_collapsing, tracked_anchor_size, output_gvcf, source_is_stitched, source_is_collapsed;
     int32_t apply_validation;   /* 1: VariantCallingParameters.Validate() derived values (what Program.Main does); 0: raw options as some reference tests build them */
+    float diploid_minor_vf, diploid_major_vf, diploid_sum_vf_multiallelic;   /* DiploidSNVThresholdingParameters (VariantCallingParameters.cs:84) */
+    int32_t is_male;            /* bool? IsMale: -1 = null (GenotypeCreator.GetPloidyForThisChr) */
 } po_config;
 
 typedef struct po_read {
@@ -103,6 +105,17 @@ void po_strand_bias(const int32_t cov[3], const int32_t sup[3], int32_t q_noise,
                     double* out /* [0]=bias [1]=gatk [2]=acceptable [3]=varBoth [4]=covBoth, then 4 stats x {FN,FP,VG,cov,freq,sup}: overall,fwd,rev,stitched */);
 int32_t po_somatic_gq(int32_t type, int32_t genotype, int32_t vq, int32_t total_coverage, int32_t allele_support, float target_lod, int32_t min_gq, int32_t max_gq);
 int32_t po_somatic_genotype(int32_t type, int32_t total_coverage, int32_t allele_support, int32_t ref_support, float min_freq_filter, int32_t min_depth);
+/* germline genotypers (po_genotype.hpp) */
+double po_mathnet_binomial_cdf(double p, int32_t n, double x);
+double po_mathnet_binomial_probability_ln(double p, int32_t n, int32_t k);
+int32_t po_diploid_gq(int32_t genotype, int32_t total_coverage, int32_t allele_support, int32_t min_gq, int32_t max_gq);
+int32_t po_haploid_gq(int32_t genotype, int32_t total_coverage, int32_t allele_support, int32_t min_gq, int32_t max_gq);
+/* ploidy: 1 = DiploidThresholdingGenotyper.SetGenotypes, 3 = HaploidGenotyper.SetGenotypes over n alleles of one locus (types[] AlleleCategory;
+ * ref_alt: n strings "REF>ALT" or NULL). Returns the locus genotype; pruned[i] = 1 for allelesToPrune; *multiallelic = MultiAllelicSite filter set. */
+int32_t po_genotype_locus(int32_t ploidy, int32_t n, const int32_t* types, const int32_t* allele_support, const int32_t* total_coverage, const int32_t* ref_support,
+                          const char* const* ref_alt, int32_t min_depth, float minor_vf, float major_vf, float sum_vf, int32_t* pruned, int32_t* multiallelic,
+                          int32_t* gq_out);
+int32_t po_ploidy_for_chr(int32_t sample_ploidy, int32_t is_male, const char* chr_name);
 int32_t po_anchor_adjusted_count(const int32_t* bins, int32_t k, int32_t min_anchor, int32_t max_anchor, int32_t from_end, int32_t symmetric);
 
 #ifdef __cplusplus

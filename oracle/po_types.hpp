@@ -210,6 +210,8 @@ struct Config {
     int RMxNFilterMaxLengthRepeat = 5, RMxNFilterMinRepetitions = 9;  // <0 = null
     float RMxNFilterFrequencyLimit = 0.35f;
     int ploidy = PM_Somatic;
+    float DiploidMinorVF = 0.20f, DiploidMajorVF = 0.70f, DiploidSumVFforMultiAllelicSite = 0.80f;   // DiploidSNVThresholdingParameters (:84)
+    int IsMale = -1;                    // bool? IsMale: -1 = null
     int ForcedNoiseLevel = -1;          // NL = ForcedNoiseLevel == -1 ? MinimumBaseCallQuality : ForcedNoiseLevel  (:109-118)
     int noiseModel = NM_Flat;
     float StrandBiasAcceptanceCriteria = 0.5f;
