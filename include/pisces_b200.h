@@ -63,10 +63,12 @@ typedef struct pb2_config {
     int32_t forced_noise_level;          /* -1 -> noise level = min_base_call_quality (VariantCallingParameters.cs:109-118) */
     int32_t noise_model;                 /* 0 Flat, 1 Window */
     float   strand_bias_acceptance;      /* 0.5 */
-    int32_t strand_bias_model;           /* 0 Poisson, 1 Extended (default); 2 Diploid -> PB2_ERR_UNSUPPORTED */
+    int32_t strand_bias_model;           /* 0 Poisson, 1 Extended (default), 2 Diploid (StrandBiasCalculator.PopulateDiploidStats :150-173) */
     int32_t filter_single_strand;        /* FilterOutVariantsPresentOnlyOneStrand */
     float   no_call_filter;              /* 0.6 */
-    int32_t ploidy;                      /* 0 Somatic; others -> PB2_ERR_UNSUPPORTED */
+    int32_t ploidy;                      /* PloidyModel of the sample: 0 Somatic, 1 DiploidByThresholding, 3 Haploid (2 DiploidByAdaptiveGT -> PB2_ERR_UNSUPPORTED).
+                                            The genotyper of a chromosome follows GenotypeCreator.GetPloidyForThisChr (chrM -> somatic, sex chromosomes
+                                            of a male sample -> haploid) from the name given to pb2_set_reference */
     int32_t tracked_anchor_size;         /* TrackedAnchorSize 5 -> 11 anchor bins; only 5 is built */
     int32_t output_gvcf;                 /* VcfWritingParameters.OutputGvcfFile (1) = IncludeReferenceCalls */
     int32_t expect_stitched;             /* IAlleleSource.ExpectStitchedReads */
@@ -83,6 +85,10 @@ typedef struct pb2_config {
     int32_t skip_validation;             /* 1: take the option values as given, without the adjustments of VariantCallingParameters.Validate (:137-155) that
                                             Program.Main applies (filters raised to their minimum values); the reference's own functional tests build
                                             options by hand this way (SomaticVariantCallerFunctionalTests.cs:683-758) */
+    float   diploid_minor_vf;            /* DiploidSNVThresholdingParameters.MinorVF (0.20): also MinVarFrequency of the germline genotypers */
+    float   diploid_major_vf;            /* .MajorVF (0.70) */
+    float   diploid_sum_vf_multiallelic; /* .SumVFforMultiAllelicSite (0.80) */
+    int32_t is_male;                     /* VariantCallingParameters.IsMale: -1 null, 0 false, 1 true */
     int32_t reserved[2];                 /* tuning knobs of bench.py; 0 in production */
 } pb2_config;
 

@@ -20,6 +20,7 @@ class Config(C.Structure):
         ("want_sum_base_quality", C.c_int32), ("collapse", C.c_int32), ("call_mnvs", C.c_int32), ("indel_repeat_filter", C.c_int32),
         ("max_size_mnv", C.c_int32), ("max_gap_mnv", C.c_int32), ("collapse_freq_threshold", C.c_float),
         ("collapse_freq_ratio_threshold", C.c_float), ("exclude_mnvs_from_collapsing", C.c_int32), ("skip_validation", C.c_int32),
+        ("diploid_minor_vf", C.c_float), ("diploid_major_vf", C.c_float), ("diploid_sum_vf_multiallelic", C.c_float), ("is_male", C.c_int32),
         ("reserved", C.c_int32 * 2)]
 
 

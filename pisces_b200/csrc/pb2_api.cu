@@ -69,6 +69,8 @@ extern "C" void pb2_default_config(pb2_config* c) {
     c->indel_repeat_filter = -1;        // VariantCallingParameters.cs:74 (null)
     c->max_size_mnv = 3; c->max_gap_mnv = 1;   // PiscesApplicationOptions.cs:43-66
     c->collapse_freq_threshold = 0.0f; c->collapse_freq_ratio_threshold = 0.5f; c->exclude_mnvs_from_collapsing = 0;
+    c->diploid_minor_vf = 0.20f; c->diploid_major_vf = 0.70f; c->diploid_sum_vf_multiallelic = 0.80f;   // VariantCallingParameters.cs:84
+    c->is_male = -1;
 }
 
 extern "C" int pb2_device_count(void) {
@@ -85,11 +87,25 @@ static void derive_config(pb2_handle* h) {
     d.min_bq = c.min_base_call_quality;
     d.noise_level = c.forced_noise_level == -1 ? c.min_base_call_quality : c.forced_noise_level;  // VariantCallingParameters.cs:109-118
     d.noise_model = c.noise_model;
-    d.min_frequency = c.min_frequency;
+    // GenotypeCreator.GetPloidyForThisChr (GenotypeCreator.cs:39-68)
+    {
+        const std::string& n = h->chr_name;
+        int p = c.ploidy;
+        if (p == PLOIDY_SOMATIC || n == "chrM" || n == "M") p = PLOIDY_SOMATIC;
+        else if (p == PLOIDY_HAPLOID) p = PLOIDY_HAPLOID;
+        else if (c.is_male < 0) {}
+        else if (c.is_male > 0 && (n == "chrY" || n == "chrX" || n == "Y" || n == "X")) p = PLOIDY_HAPLOID;
+        else if (c.is_male == 0 && (n == "chrY" || n == "Y")) p = PLOIDY_HAPLOID;
+        d.ploidy = p;
+    }
+    d.diploid_minor_vf = c.diploid_minor_vf; d.diploid_major_vf = c.diploid_major_vf; d.diploid_sum_vf = c.diploid_sum_vf_multiallelic;
+    // VariantCallerConfig.MinFrequency = genotypeCalculator.MinVarFrequency (Factory.cs:160): MinimumFrequency for the somatic genotyper, MinorVF otherwise
+    d.min_frequency = d.ploidy == PLOIDY_SOMATIC ? c.min_frequency : c.diploid_minor_vf;
+    d.sb_min_vf = (double)d.min_frequency;
     d.min_frequency_filter = c.min_frequency_filter < c.min_frequency ? c.min_frequency : c.min_frequency_filter;  // Validate :144-147
     d.target_lod = c.target_lod_frequency < d.min_frequency_filter ? d.min_frequency_filter : c.target_lod_frequency;  // :152-155
     if (c.skip_validation) { d.min_frequency_filter = c.min_frequency_filter; d.target_lod = c.target_lod_frequency; }
-    d.variant_freq_filter = d.min_frequency_filter > c.min_frequency ? d.min_frequency_filter : c.min_frequency;  // SomaticGenotyper.SetMinFreqFilter
+    d.variant_freq_filter = d.min_frequency_filter > d.min_frequency ? d.min_frequency_filter : d.min_frequency;  // IGenotypeCalculator.SetMinFreqFilter
     d.max_vq = c.max_variant_qscore; d.min_vq = c.min_variant_qscore; d.vq_filter = c.variant_qscore_filter;
     d.max_gq = c.max_genotype_qscore; d.min_gq = c.min_genotype_qscore; d.low_gq_filter = c.low_genotype_quality_filter;
     d.min_coverage = c.min_coverage;
@@ -112,8 +128,8 @@ static void derive_config(pb2_handle* h) {
 extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
     if (!cfg || !out) return fail(nullptr, PB2_ERR_ARG, "pb2_create: null argument");
     *out = nullptr;
-    if (cfg->ploidy != 0) return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: only the Somatic ploidy model is built (SURVEY 8f rank 3)");
-    if (cfg->strand_bias_model == 2) return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: Diploid strand-bias model not built (SURVEY 8f rank 3)");
+    if (cfg->ploidy != PLOIDY_SOMATIC && cfg->ploidy != PLOIDY_DIPLOID && cfg->ploidy != PLOIDY_HAPLOID)
+        return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: ploidy must be 0 Somatic, 1 DiploidByThresholding or 3 Haploid (DiploidByAdaptiveGT is not built, SURVEY 8f rank 4)");
     if (cfg->tracked_anchor_size != 5) return fail(nullptr, PB2_ERR_UNSUPPORTED, "pb2_create: tracked_anchor_size must be 5");
     if (cfg->min_base_call_quality < 0 || cfg->min_base_call_quality > 127) return fail(nullptr, PB2_ERR_ARG, "pb2_create: min_base_call_quality must be in [0,127]");
     int n = 0;
@@ -231,6 +247,9 @@ extern "C" int pb2_set_reference(pb2_handle* h, const char* chr_name, const uint
         CU(h, cudaMemcpyAsync(h->d_chr, h->h_chr.data(), (size_t)len, cudaMemcpyHostToDevice, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
     }
+    derive_config(h);   // the genotyper follows the chromosome (GenotypeCreator.GetPloidyForThisChr)
+    explicit_release_resident(h);
+    release_resident_graph(h);
     return PB2_OK;
 }
 
@@ -649,6 +668,8 @@ static int resident_step(pb2_handle* h, Segment& s, bool with_explicit) {
 
 extern "C" int pb2_call_resident(pb2_handle* h, int64_t* n_records) {
     if (!h) return PB2_ERR_ARG;
+    if (h->dcfg.ploidy != PLOIDY_SOMATIC || h->cfg.ploidy == PLOIDY_DIPLOID)
+        return fail(h, PB2_ERR_UNSUPPORTED, "pb2_call_resident: the germline genotypers assign one genotype per locus when pb2_flush merges the alleles; use pb2_flush");
     CU(h, cudaSetDevice(h->device));
     int64_t total = 0;
     if (!h->cands.empty()) {
@@ -882,6 +903,137 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
     return PB2_OK;
 }
 
+// The per-locus part of AlleleCaller.ComputeGenotypeAndFilterAllele (:143-177) for the germline genotypers, over the records of one flush (already
+// grouped by position, reference alleles pruned where a variant was called): DiploidThresholdingGenotyper.SetGenotypes / HaploidGenotyper.SetGenotypes
+// with GenotypeCalculatorUtilities (the alleles of a locus ordered by frequency, 0.20 / 0.70 / 0.80 thresholds, tri-allelic check, pruning) and then
+// DiploidLocusProcessor.Process (DiploidLocusProcessor.cs:13-51). A locus that only holds its reference allele was genotyped on the device.
+static void germline_locus_pass(pb2_handle* h) {
+    const DeviceConfig& d = h->dcfg;
+    const bool germline = d.ploidy != PLOIDY_SOMATIC;
+    const bool locus_processor = h->cfg.ploidy == PLOIDY_DIPLOID;   // follows the SAMPLE ploidy (Factory.cs:145-147)
+    if (!germline && !locus_processor) return;
+    std::vector<pb2_call_record>& R = h->h_out;
+    std::vector<pb2_call_record_ext>& E = h->h_out_ext;
+    auto freq_of = [](int support, int total) { return total == 0 ? 0.0f : std::min((float)support / (float)total, 1.0f); };
+    std::vector<uint8_t> drop(R.size(), 0);
+    bool any_drop = false;
+    for (size_t b = 0; b < R.size();) {
+        size_t e = b + 1;
+        while (e < R.size() && R[e].position == R[b].position) e++;
+        std::vector<size_t> ng;   // allelesAtPosition.Where(x => !x.IsForcedToReport)
+        bool any_variant = false;
+        for (size_t i = b; i < e; i++) if (!(R[i].sb_flags & 8)) { ng.push_back(i); any_variant |= R[i].type != CAT_REF; }
+        if (germline && any_variant) {
+            const bool hap = d.ploidy == PLOIDY_HAPLOID;
+            const float minor = d.diploid_minor_vf, major = d.diploid_major_vf, sum_vf = d.diploid_sum_vf;
+            // FilterAndOrderAllelesByFrequency (GenotypeCalculatorUtilities.cs:60-82): ng is in (ref, alt) order already, the sort is stable
+            std::vector<size_t> ordered, prune;
+            for (size_t i : ng) {
+                if (R[i].type == CAT_REF) continue;
+                if ((double)freq_of(R[i].allele_support, R[i].total_coverage) >= (double)minor) ordered.push_back(i); else prune.push_back(i);
+            }
+            std::stable_sort(ordered.begin(), ordered.end(), [&](size_t x, size_t y) {
+                return freq_of(R[x].allele_support, R[x].total_coverage) > freq_of(R[y].allele_support, R[y].total_coverage);
+            });
+            // GetReferenceFrequency (:85-130)
+            double reference_frequency = 0;
+            if (ng.size() == 1) reference_frequency = freq_of(R[ng[0]].reference_support, R[ng[0]].total_coverage);
+            else {
+                double by_snp = 0, indel = 0;
+                bool returned = false;
+                for (size_t i : ng) {
+                    if (R[i].type == CAT_REF) { reference_frequency = freq_of(R[i].allele_support, R[i].total_coverage); returned = true; break; }
+                    if (R[i].type == CAT_SNV) by_snp = freq_of(R[i].reference_support, R[i].total_coverage);
+                    else indel += freq_of(R[i].allele_support, R[i].total_coverage);
+                }
+                if (!returned) reference_frequency = std::max(by_snp - indel, 0.0);
+            }
+            const bool ref_exists = reference_frequency >= (double)minor;
+            bool depth_issue = false;
+            for (size_t i : ng) depth_issue |= R[i].total_coverage < d.min_coverage;
+            const float top = ordered.empty() ? 0.0f : freq_of(R[ordered[0]].allele_support, R[ordered[0]].total_coverage);
+            const bool ref_call = ordered.empty() || top < minor;
+            int gt;
+            bool multi_allelic = false;
+            if (hap) {   // HaploidGenotyper.CalculateHaploidGenotype (HaploidGenotyper.cs:54-82)
+                gt = GT_HEMI_NOCALL;
+                if (!depth_issue && ref_call && ref_exists && reference_frequency > (double)major) gt = GT_HEMI_REF;
+                if (!depth_issue && !ref_call && !ref_exists && top > major) gt = GT_HEMI_ALT;
+            } else {     // CalculateDiploidGenotype (DiploidThresholdingGenotyper.cs:77-125) + ConvertSimpleGenotypeToComplexGenotype (:160-233)
+                enum { P_HOM_REF, P_HET, P_HOM_ALT } prelim;
+                if (ref_call) prelim = P_HOM_REF;
+                else if (top >= minor && top <= major) prelim = P_HET;
+                else if (top > major) prelim = P_HOM_ALT;
+                else prelim = P_HOM_REF;
+                if (depth_issue) gt = ref_call ? GT_REF_NOCALL : GT_ALT_NOCALL;
+                else if (prelim == P_HOM_REF) {
+                    const pb2_call_record& first = R[ng[0]];
+                    if (!ref_exists) gt = GT_REF_NOCALL;
+                    else if (first.type == CAT_REF && (1 - freq_of(first.allele_support, first.total_coverage)) > minor) gt = GT_REF_AND_NOCALL;
+                    else gt = GT_HOM_REF;
+                } else if (prelim == P_HET) {
+                    if (ordered.size() == 1) gt = ref_exists ? GT_HET_ALT_REF : GT_ALT_AND_NOCALL;
+                    else {
+                        // CheckForTriAllelicIssue (:133-150)
+                        bool fail = false;
+                        if (R[ordered.back()].type == CAT_SNV) {
+                            const float f0 = top, f1 = freq_of(R[ordered[1]].allele_support, R[ordered[1]].total_coverage);
+                            if (ref_exists && (((double)f0 + reference_frequency) < (double)sum_vf)) fail = true;
+                            else fail = (f0 + f1) < sum_vf;
+                        }
+                        if (fail) { multi_allelic = true; gt = ref_exists ? GT_ALT_NOCALL : GT_ALT12_NOCALL; }
+                        else gt = ref_exists ? GT_HET_ALT_REF : GT_HET_ALT12;
+                    }
+                } else gt = GT_HOM_ALT;
+            }
+            // GetAllelesToPruneBasedOnGTCall (:11-46)
+            int allowed = 0;
+            if (gt == GT_ALT_AND_NOCALL || gt == GT_ALT_NOCALL || gt == GT_HOM_ALT || gt == GT_HET_ALT_REF || gt == GT_HEMI_ALT) allowed = 1;
+            else if (gt == GT_ALT12_NOCALL || gt == GT_HET_ALT12) allowed = 2;
+            for (size_t k = 0; k < ordered.size(); k++) if ((int)k >= allowed) prune.push_back(ordered[k]);
+            for (size_t i : ng) {
+                R[i].genotype = (uint8_t)gt;
+                R[i].genotype_qscore = germline_gq(hap, gt, R[i].total_coverage, R[i].allele_support, d.min_gq, d.max_gq);
+                if (multi_allelic) R[i].filters |= (uint16_t)(1u << FLT_MULTI_ALLELIC);
+                R[i].filters &= (uint16_t)~(1u << FLT_LOW_GQ);
+                if (d.low_gq_filter >= 0 && (float)R[i].genotype_qscore < (float)d.low_gq_filter) R[i].filters |= (uint16_t)(1u << FLT_LOW_GQ);
+            }
+            for (size_t i : prune) {   // pruned unless it is one of the forced alleles (AlleleCaller.cs:153-162)
+                uint8_t buf[4];
+                const uint8_t *ra, *aa;
+                record_alleles(R[i], h->arena, ra, aa, buf);
+                if (!h->forced.empty() && h->forced.count(std::make_tuple(R[i].position, std::string((const char*)ra, R[i].ref_len), std::string((const char*)aa, R[i].alt_len))))
+                    continue;
+                drop[i] = 1;
+                any_drop = true;
+            }
+        }
+        if (locus_processor) {   // DiploidLocusProcessor.Process
+            std::vector<size_t> forced, non_forced;
+            for (size_t i = b; i < e; i++) if (!drop[i]) ((R[i].filters >> FLT_FORCED_REPORT) & 1 ? forced : non_forced).push_back(i);
+            if (!forced.empty()) {
+                bool is_ref = false, any_nocall = false;
+                int min_gq = 0;
+                for (size_t k = 0; k < non_forced.size(); k++) {
+                    const pb2_call_record& r = R[non_forced[k]];
+                    is_ref |= r.type == CAT_REF;
+                    any_nocall |= r.genotype == GT_ALT12_NOCALL || r.genotype == GT_ALT_NOCALL || r.genotype == GT_HEMI_NOCALL || r.genotype == GT_REF_NOCALL;
+                    min_gq = k == 0 ? r.genotype_qscore : std::min(min_gq, r.genotype_qscore);
+                }
+                const int gt = (non_forced.empty() || any_nocall) ? GT_ALT_NOCALL : (is_ref ? GT_HOM_REF : GT_OTHERS);
+                for (size_t i : forced) R[i].genotype = (uint8_t)gt;
+                for (size_t i = b; i < e; i++) if (!drop[i]) R[i].genotype_qscore = min_gq;
+            }
+        }
+        b = e;
+    }
+    if (any_drop) {
+        size_t w = 0;
+        for (size_t i = 0; i < R.size(); i++) if (!drop[i]) { R[w] = R[i]; E[w] = E[i]; w++; }
+        R.resize(w); E.resize(w);
+    }
+}
+
 extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n) {
     if (!h || !out || !n) return fail(h, PB2_ERR_ARG, "pb2_flush: null argument");
     CU(h, cudaSetDevice(h->device));
@@ -1037,6 +1189,7 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
             for (auto& o : all) emit(o);
         }
     }
+    germline_locus_pass(h);
     tr.mark("merge");
     // drop what this flush consumed: temporary segments, reads that end inside the cleared positions, dead candidates, used gapped counts
     for (size_t i = 0; i < h->segs.size();) {

@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(32 * kScoreWarps) score_candidates_kernel(Cand
         }
         nl_applied = nl;
         vq = (total == 0) ? 0 : poisson_qscore(allele_support, total, error_rate, cfg.max_vq);
-        sb = strand_bias(cov, c.support, cfg.sb_noise, (double)cfg.sb_acceptance, cfg.sb_model);
+        sb = strand_bias(cov, c.support, cfg.sb_noise, (double)cfg.sb_acceptance, cfg.sb_model, cfg.sb_min_vf);
     }
     const float all_reads = (float)(total + nocalls);
     const float frac_nc = all_reads == 0 ? 0.0f : ((float)nocalls / all_reads);
@@ -373,8 +373,16 @@ __global__ void __launch_bounds__(32 * kScoreWarps) score_candidates_kernel(Cand
     // a forced allele that would not be reported is reported anyway, flagged, and keeps the genotype a new CalledAllele starts with (:108-118,150)
     const bool forced_report = (c.flags & kCandForced) && !report;
     if (forced_report) filters |= 1u << FLT_FORCED_REPORT;
-    const int gt = forced_report ? (is_ref ? GT_HOM_REF : GT_HET_ALT_REF) : somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
-    const int gq = forced_report ? 0 : somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, a.q_to_p_table, a.q_table_max);
+    int gt = is_ref ? GT_HOM_REF : GT_HET_ALT_REF, gq = 0;
+    if (forced_report) {
+    } else if (cfg.ploidy == PLOIDY_SOMATIC) {
+        gt = somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
+        gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, a.q_to_p_table, a.q_table_max);
+    } else if (is_ref) {   // germline: exact for a reference-only locus; loci with variants are genotyped together in pb2_flush
+        const bool hap = cfg.ploidy == PLOIDY_HAPLOID;
+        gt = germline_reference_only_genotype(hap, total, allele_support, ref_support, cfg.diploid_minor_vf, cfg.diploid_major_vf, cfg.min_coverage);
+        gq = germline_gq(hap, gt, total, allele_support, cfg.min_gq, cfg.max_gq);
+    }
     if (cfg.low_gq_filter >= 0 && (float)gq < (float)cfg.low_gq_filter) filters |= 1u << FLT_LOW_GQ;
 
     pb2_call_record r;

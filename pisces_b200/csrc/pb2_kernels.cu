@@ -244,7 +244,7 @@ __device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int posit
         vq = (total == 0) ? 0 : poisson_qscore(allele_support, total, error_rate, cfg.max_vq);
     }
     if (!is_ref && vq < cfg.min_vq) return false;
-    if (allele_support > 0) sb = strand_bias(cov, sup, cfg.sb_noise, (double)cfg.sb_acceptance, cfg.sb_model);
+    if (allele_support > 0) sb = strand_bias(cov, sup, cfg.sb_noise, (double)cfg.sb_acceptance, cfg.sb_model, cfg.sb_min_vf);
 
     // AlleleProcessor.Process / ApplyFilters
     const float all_reads = (float)(total + nocalls);
@@ -258,10 +258,18 @@ __device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int posit
         if (rmxn_should_filter_snv(position, base_of_allele(ref_allele), base_of_allele(alt_allele), freq, cfg, chr_seq, chr_len)) filters |= 1u << FLT_RMXN;
         if (freq < cfg.variant_freq_filter) filters |= 1u << FLT_LOW_VF;
     }
-    // SomaticGenotyper + GQ (per allele)
+    // SomaticGenotyper + GQ (per allele). Germline ploidy: exact for a locus whose only allele is this reference allele; the alleles of a locus
+    // with variants are genotyped together when pb2_flush merges them (germline_locus_pass)
     const float ref_freq = allele_frequency(ref_support, total);
-    const int gt = somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
-    const int gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, ex.q_to_p_table, ex.q_table_max);
+    int gt, gq;
+    if (cfg.ploidy == PLOIDY_SOMATIC) {
+        gt = somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
+        gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, ex.q_to_p_table, ex.q_table_max);
+    } else {
+        const bool hap = cfg.ploidy == PLOIDY_HAPLOID;
+        gt = is_ref ? germline_reference_only_genotype(hap, total, allele_support, ref_support, cfg.diploid_minor_vf, cfg.diploid_major_vf, cfg.min_coverage) : GT_HET_ALT_REF;
+        gq = is_ref ? germline_gq(hap, gt, total, allele_support, cfg.min_gq, cfg.max_gq) : 0;
+    }
     if (cfg.low_gq_filter >= 0 && (float)gq < (float)cfg.low_gq_filter) filters |= 1u << FLT_LOW_GQ;
 
     r.position = position;

@@ -35,6 +35,9 @@ struct DeviceConfig {
     int tune_prefetch;      // tuning experiments: 0 default (2 steps ahead), 1 none, 3, 4
     int tune_ctas_per_sm;   // resident CTAs per SM of the hot kernel (launch bound -> register budget): 4 (64 registers) or 3 (85)
     int snv_from_counts;    // 1: SNV candidates = the counts (CallMNVs off); 0: SNVs are explicit candidates from the finder's state machine
+    int ploidy;             // PloidyModel of THIS chromosome (GenotypeCreator.GetPloidyForThisChr): 0 Somatic, 1 DiploidByThresholding, 3 Haploid
+    float diploid_minor_vf, diploid_major_vf, diploid_sum_vf;   // DiploidSNVThresholdingParameters
+    double sb_min_vf;       // (double)_config.MinFrequency: minDetectableSNP of the Diploid strand-bias model (StrandBiasCalculator.cs:137-148)
     double vq_error_rate;   // MathOperations.QtoP(noise_level) (VariantQualityCalculator.cs:31)
     double sb_noise;        // Math.Pow(10, -1*noise_level/10f) (StrandBiasCalculator.cs:32)
 };

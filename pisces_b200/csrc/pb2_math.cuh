@@ -22,7 +22,7 @@ enum : int { CAT_SNV = 0, CAT_INS = 1, CAT_DEL = 2, CAT_MNV = 3, CAT_REF = 4 };
 enum : int { FLT_STRAND_BIAS = 0, FLT_POOL_BIAS, FLT_AMPLICON_BIAS, FLT_LOW_VQ, FLT_LOW_DEPTH, FLT_LOW_VF, FLT_LOW_GQ, FLT_INDEL_REPEAT,
              FLT_MULTI_ALLELIC, FLT_RMXN, FLT_FORCED_REPORT, FLT_OFF_TARGET, FLT_NO_CALL };
 enum : int { GT_HET_ALT12 = 0, GT_ALT12_NOCALL, GT_HET_ALT_REF, GT_HOM_ALT, GT_HOM_REF, GT_REF_NOCALL, GT_ALT_NOCALL, GT_REF_AND_NOCALL,
-             GT_ALT_AND_NOCALL };
+             GT_ALT_AND_NOCALL, GT_HEMI_REF, GT_HEMI_ALT, GT_HEMI_NOCALL, GT_OTHERS };
 enum : int { SBM_POISSON = 0, SBM_EXTENDED = 1, SBM_DIPLOID = 2 };
 
 // ---------------------------------------------------------------- Pisces' own regularised upper incomplete gamma (Poisson.cs)
@@ -86,7 +86,7 @@ static __device__ __noinline__ double pisces_poisson_cdf(double num_occurrences,
 }
 
 // ---------------------------------------------------------------- MathNet.Numerics 4.5.1 (IL of the shipped dll)
-__device__ __forceinline__ double mathnet_gamma_ln(double z) {  // SpecialFunctions::GammaLn, z >= 0.5 branch only (callers pass z >= 1)
+__host__ __device__ __forceinline__ double mathnet_gamma_ln(double z) {  // SpecialFunctions::GammaLn, z >= 0.5 branch only (callers pass z >= 1)
     const double dk[11] = {2.4857408913875355e-05, 1.0514237858172197,   -3.4568709722201625,  4.512277094668948,
                            -2.9828522532357664,    1.056397115771267,    -0.19542877319164587, 0.01709705434044412,
                            -0.0005719261174043057, 4.633994733599057e-06, -2.7199490848860772e-09};
@@ -96,7 +96,7 @@ __device__ __forceinline__ double mathnet_gamma_ln(double z) {  // SpecialFuncti
     return log(s) + 0.6207822376352452 + ((z - 0.5) * log((z - 0.5 + 10.900511) / 2.718281828459045));
 }
 
-__device__ __forceinline__ double mathnet_factorial_ln(int x) {  // SpecialFunctions::FactorialLn; cache f[i] = f[i-1]*i, 171 entries
+__host__ __device__ __forceinline__ double mathnet_factorial_ln(int x) {  // SpecialFunctions::FactorialLn; cache f[i] = f[i-1]*i, 171 entries
     if (x <= 1) return 0.0;
     if (x < 171) {
         double f = 1.0;
@@ -199,14 +199,63 @@ __device__ __forceinline__ int poisson_qscore(int call_count, int coverage, doub
 // ---------------------------------------------------------------- StrandBiasCalculator.cs
 struct SbStats { double fn, fp, vg, coverage, support; };
 
-__device__ __forceinline__ SbStats sb_create_stats(double support, double coverage, double noise, int model) {  // :137-148,175-231 (non-diploid)
+// MathNet SpecialFunctions::BetaRegularized (IL of the shipped dll): Lentz continued fraction, eps = 2^-53, fpmin = 4.94e-324 / eps
+static __device__ __noinline__ double mathnet_beta_regularized(double a, double b, double x) {
+    const double bt = (x == 0.0 || x == 1.0) ? 0.0 : exp(mathnet_gamma_ln(a + b) - mathnet_gamma_ln(a) - mathnet_gamma_ln(b) + a * log(x) + b * log(1.0 - x));
+    const bool symmetry = x >= (a + 1.0) / (a + b + 2.0);
+    const double eps = 1.1102230246251565e-16;
+    const double fpmin = 4.9406564584124654e-324 / eps;
+    if (symmetry) { x = 1.0 - x; const double t = a; a = b; b = t; }
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0;
+    double d = 1.0 - qab * x / qap;
+    if (fabs(d) < fpmin) d = fpmin;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1, m2 = 2; m <= 50000; m++, m2 += 2) {
+        double aa = (double)m * (b - (double)m) * x / ((qam + (double)m2) * (a + (double)m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < fpmin) d = fpmin;
+        c = 1.0 + aa / c;
+        if (fabs(c) < fpmin) c = fpmin;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + (double)m) * (qab + (double)m) * x / ((a + (double)m2) * (qap + (double)m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < fpmin) d = fpmin;
+        c = 1.0 + aa / c;
+        if (fabs(c) < fpmin) c = fpmin;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) <= eps) break;
+    }
+    return symmetry ? 1.0 - bt * h / a : bt * h / a;
+}
+// MathNet Distributions.Binomial(p, n).CumulativeDistribution(x)
+__device__ __forceinline__ double mathnet_binomial_cdf(double p, int n, double x) {
+    if (x < 0.0) return 0.0;
+    if (x > (double)n) return 1.0;
+    const double k = floor(x);
+    return mathnet_beta_regularized((double)n - k, k + 1.0, 1.0 - p);
+}
+
+// min_vf: _config.MinFrequency as a double (only the Diploid model reads it: CreateStats :137-148)
+__device__ __forceinline__ SbStats sb_create_stats(double support, double coverage, double noise, int model, double min_vf) {  // :137-148,150-231
     SbStats s;
     s.support = support;
     s.coverage = coverage;
-    const double min_detectable = noise;  // model != Diploid: minDetectableSNP = noiseFreq
+    const double min_detectable = model == SBM_DIPLOID ? min_vf : noise;  // model != Diploid: minDetectableSNP = noiseFreq
     if (support == 0) {
         if (model == SBM_POISSON) { s.fp = 1; s.vg = 0; s.fn = 0; }
         else { s.vg = pow(1 - min_detectable, coverage); s.fp = 1 - s.vg; s.fn = s.vg; }
+    } else if (model == SBM_DIPLOID) {   // PopulateDiploidStats :150-173
+        if (support / coverage >= min_detectable) { s.fn = 1; s.fp = 0; s.vg = 1; }
+        else {
+            s.fn = fmax(mathnet_binomial_cdf(min_detectable, (int)coverage, support), 0.0);
+            s.fp = fmax(0.0, 1 - pisces_poisson_cdf(support, coverage * 0.1));
+            s.vg = s.fn;
+        }
     } else {
         // Rigorous short-circuit: Cdf(support-1, x) = 1 - gs with gs = sum * exp(a ln x - x - lnGamma~(a)), a = support. For x <= a/2 the series
         // converges (ratio <= 1/2), sum <= 2, and lnGamma~(a) >= (a-1/2) ln a - a + ln sqrt(2 pi) - 1e-6 for both of the reference's
@@ -228,10 +277,10 @@ __device__ __forceinline__ SbStats sb_create_stats(double support, double covera
 struct SbResult { double bias, gatk; bool acceptable, var_both, cov_both; };
 
 // noise = Math.Pow(10, -1*qNoise/10f) (float exponent, :32): a per-run constant, computed once on the host
-__device__ __forceinline__ SbResult strand_bias(const int cov[3], const int sup[3], double noise, double acceptance, int model) {  // :21-72,89-105
-    const SbStats o = sb_create_stats(sup[0] + sup[1] + sup[2], cov[0] + cov[1] + cov[2], noise, model);
-    const SbStats f = sb_create_stats(sup[0] + sup[2] / 2, cov[0] + cov[2] / 2, noise, model);
-    const SbStats r = sb_create_stats(sup[1] + sup[2] / 2, cov[1] + cov[2] / 2, noise, model);
+__device__ __forceinline__ SbResult strand_bias(const int cov[3], const int sup[3], double noise, double acceptance, int model, double min_vf) {  // :21-72,89-105
+    const SbStats o = sb_create_stats(sup[0] + sup[1] + sup[2], cov[0] + cov[1] + cov[2], noise, model, min_vf);
+    const SbStats f = sb_create_stats(sup[0] + sup[2] / 2, cov[0] + cov[2] / 2, noise, model, min_vf);
+    const SbStats r = sb_create_stats(sup[1] + sup[2] / 2, cov[1] + cov[2] / 2, noise, model, min_vf);
     double fb = (f.vg * r.fp) / o.vg;
     double rb = (r.vg * f.fp) / o.vg;
     if (o.vg == 0) { fb = 1; rb = 1; }
@@ -284,6 +333,69 @@ __device__ __forceinline__ int somatic_gq(int genotype, int vq, int total_cov, f
     double q = fmin((double)max_gq, raw);
     q = fmax(q, (double)min_gq);
     return (int)rint(q);
+}
+
+// ---------------------------------------------------------------- germline genotypers; shared by the kernels (reference-only loci)
+// and the per-locus pass of pb2_flush (loci with variant alleles)
+enum : int { PLOIDY_SOMATIC = 0, PLOIDY_DIPLOID = 1, PLOIDY_ADAPTIVE = 2, PLOIDY_HAPLOID = 3 };
+
+// MathNet Distributions.Poisson(lambda).ProbabilityLn(k) and Binomial(p, n).ProbabilityLn(k) (PMFLn, IL of the shipped dll)
+__host__ __device__ __forceinline__ double mathnet_poisson_probability_ln(double lambda, int k) { return -lambda + (double)k * log(lambda) - mathnet_factorial_ln(k); }
+__host__ __device__ __forceinline__ double mathnet_binomial_probability_ln(double p, int n, int k) {
+    if (k < 0 || k > n) return -INFINITY;
+    if (p == 0.0) return k == 0 ? 0.0 : -INFINITY;
+    if (p == 1.0) return k == n ? 0.0 : -INFINITY;
+    const double binomial_ln = mathnet_factorial_ln(n) - mathnet_factorial_ln(k) - mathnet_factorial_ln(n - k);
+    return binomial_ln + (double)k * log(p) + (double)(n - k) * log(1.0 - p);
+}
+// (int) of a double in C# (unchecked, x64): NaN / out of range -> int.MinValue
+__host__ __device__ __forceinline__ int cs_int_cast(double v) {
+    if (!(v < 2147483648.0) || !(v > -2147483649.0)) return (int)0x80000000;
+    return (int)v;
+}
+// DiploidGenotypeQualityCalculator.Compute (Thresholding/DiploidGenotypeQualityCalculator.cs:17-103) and HaploidGenotypeQualityCalculator.Compute
+// (Haploid/HaploidGenotypeQualityCalculator.cs:12-59): float parameters, MathNet log-probabilities in double
+__host__ __device__ inline int germline_gq(bool haploid, int genotype, int total_cov, int allele_support, int min_q, int max_q) {
+    if (total_cov == 0) return min_q;
+    const float noise_hom_ref = 0.05f, noise_hom_alt = 0.075f, noise_het_alt = 0.10f, expected_het = 0.40f;
+    const float depth = (float)total_cov;
+    const double lam_hom_ref = (double)(noise_hom_ref * depth), lam_hom_alt = (double)(noise_hom_alt * depth);
+    const int non_allele = total_cov - allele_support > 0 ? total_cov - allele_support : 0;
+    double h0 = 0, h1 = 0;
+    if (genotype == (haploid ? GT_HEMI_REF : GT_HOM_REF)) {
+        h0 = mathnet_poisson_probability_ln(lam_hom_ref, non_allele);
+        h1 = mathnet_binomial_probability_ln((double)expected_het, total_cov, non_allele);
+    } else if (genotype == (haploid ? GT_HEMI_ALT : GT_HOM_ALT)) {
+        h0 = mathnet_poisson_probability_ln(lam_hom_alt, non_allele);
+        h1 = mathnet_binomial_probability_ln((double)expected_het, total_cov, allele_support);
+    } else if (!haploid && (genotype == GT_HET_ALT12 || genotype == GT_HET_ALT_REF)) {
+        const float freq = total_cov == 0 ? 0.0f : fminf((float)allele_support / (float)total_cov, 1.0f);
+        const int k = (int)(depth * freq);
+        h0 = mathnet_binomial_probability_ln((double)expected_het, total_cov, k);
+        h1 = ((double)freq >= 0.50) ? mathnet_binomial_probability_ln((double)(1 - noise_het_alt), total_cov, k) : mathnet_binomial_probability_ln((double)noise_het_alt, total_cov, k);
+    } else {
+        return min_q;
+    }
+    const int q = cs_int_cast(floor(10.0 * 0.4342944819032518 * (h0 - h1)));   // 10.0 * Math.Log10(Math.E) * (...)
+    if (!haploid) {
+        if ((h1 <= -2147483648.0) && (h0 > h1)) return max_q;
+        if ((h0 <= -2147483648.0) && (h0 < h1)) return min_q;
+    }
+    const int lo = q < max_q ? q : max_q;
+    return lo > min_q ? lo : min_q;
+}
+// The genotype of a locus whose only allele is its reference allele: DiploidThresholdingGenotyper.CalculateDiploidGenotype
+// (DiploidThresholdingGenotyper.cs:77-100, GenotypeCalculatorUtilities.ConvertSimpleGenotypeToComplexGenotype :160-190) /
+// HaploidGenotyper.CalculateHaploidGenotype (HaploidGenotyper.cs:54-82) with alleles = [reference]
+__host__ __device__ inline int germline_reference_only_genotype(bool haploid, int total_cov, int allele_support, int ref_support, float minor_vf, float major_vf, int min_depth) {
+    const float ref_frequency = total_cov == 0 ? 0.0f : fminf((float)ref_support / (float)total_cov, 1.0f);   // alleles.First().RefFrequency (:93-94)
+    const float frequency = total_cov == 0 ? 0.0f : fminf((float)allele_support / (float)total_cov, 1.0f);
+    const bool ref_exists = (double)ref_frequency >= (double)minor_vf;
+    const bool depth_issue = total_cov < min_depth;
+    if (haploid) return (!depth_issue && ref_exists && (double)ref_frequency > (double)major_vf) ? GT_HEMI_REF : GT_HEMI_NOCALL;
+    if (depth_issue || !ref_exists) return GT_REF_NOCALL;
+    if ((1 - frequency) > minor_vf) return GT_REF_AND_NOCALL;
+    return GT_HOM_REF;
 }
 
 }  // namespace pb2
