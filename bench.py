@@ -266,13 +266,18 @@ def main_ours(a):
 
     # ---- end to end through the C ABI with HOST buffers: pinned H2D of the step's pileup, tile staging, call, D2H of the records
     if not a.no_e2e:
-        h = {k: d[k].cpu().pin_memory() for k in ("offsets", "code", "qual", "anchor", "ref_bases")}
+        # host buffers in PB2_LAYOUT_PACKED2 (2 bytes per entry + the sparse candidate flags): what a host behind a PCIe link hands to pb2_push_pileup
+        pc, pq, fi, fb = pb.GpuStateManager.pack_pileup(d["code"].cpu().numpy(), d["qual"].cpu().numpy(), d["anchor"].cpu().numpy())
+        h = {"offsets": d["offsets"].cpu().pin_memory(), "ref_bases": d["ref_bases"].cpu().pin_memory(), "pcode": torch.from_numpy(pc).pin_memory(),
+             "pqual": torch.from_numpy(pq).pin_memory(), "flag_index": torch.from_numpy(fi).pin_memory(), "flag_bits": torch.from_numpy(fb).pin_memory()}
+        del pc, pq
         sm2 = pb.GpuStateManager(cfg, "chr1", ref)
         caller = pb.GpuAlleleCaller()
         e2e_steps = max(2, min(a.steps, 4))
 
         def e2e_step():
-            sm2.AddPileup(h["offsets"].numpy(), h["code"].numpy(), h["qual"].numpy(), h["anchor"].numpy(), first_position=1, ref_bases=h["ref_bases"].numpy())
+            sm2.AddPileupPacked(h["offsets"].numpy(), h["pcode"].numpy(), h["pqual"].numpy(), h["flag_index"].numpy(), h["flag_bits"].numpy(), first_position=1,
+                                ref_bases=h["ref_bases"].numpy())
             if d.get("candidates") is not None:
                 sm2.AddCandidates(d["candidates"], d["arena"])
             recs = caller.Call(sm2, raw=True)
@@ -287,7 +292,7 @@ def main_ours(a):
         edt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(edt, op=dist.ReduceOp.MAX)
-        line["e2e"] = {"value": world * a.loci * e2e_steps / float(edt.item()), "unit": UNIT, "h2d_bytes_per_step": 3 * n_entries + 8 * (a.loci + 1) + a.loci,
+        line["e2e"] = {"value": world * a.loci * e2e_steps / float(edt.item()), "unit": UNIT, "h2d_bytes_per_step": 2 * n_entries + 8 * (a.loci + 1) + a.loci + 9 * int(h["flag_index"].numel()),
                        "d2h_bytes_per_step": 96 * nrec, "steps": e2e_steps}
         sm2.close()
 

@@ -129,7 +129,18 @@ typedef struct pb2_pileup_csr {
     const uint8_t* qual;
     const uint8_t* anchor;
     const uint8_t* ref_bases;    /* optional [n_loci] ASCII; NULL -> taken from pb2_set_reference */
+    /* PB2_LAYOUT_PLANES (0): the three planes above. PB2_LAYOUT_PACKED2 (1): two bytes per entry for hosts behind a PCIe link — `anchor` is NULL, the
+     * anchor bin rides in the spare bits (code = AlleleType | DirectionType << 3 | (bin & 7) << 5, qual = quality | (bin >> 3) << 7), and the rare
+     * candidate flags come as a sparse list: flag_index[n_flags] (entry indices, increasing) with flag_bits[n_flags] (PB2_ENTRY_* bits). Not available
+     * with expect_collapsed (the collapsed-read type needs the third byte). */
+    int32_t layout;
+    int32_t reserved;
+    int64_t n_flags;
+    const int64_t* flag_index;
+    const uint8_t* flag_bits;
 } pb2_pileup_csr;
+#define PB2_LAYOUT_PLANES 0
+#define PB2_LAYOUT_PACKED2 1
 
 /* One candidate allele: the POD image of CandidateAllele (src/lib/Pisces.Domain/Models/Alleles/CandidateAllele.cs:8-125) for
  * IAlleleSource.AddCandidates. Insertions, deletions and MNVs (and, with CallMNVs, SNVs) are explicit candidates: their support is the number

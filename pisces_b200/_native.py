@@ -26,7 +26,8 @@ class Config(C.Structure):
 
 class PileupCsr(C.Structure):
     _fields_ = [("n_loci", C.c_int64), ("first_position", C.c_int32), ("positions", C.c_void_p), ("offsets", C.c_void_p),
-                ("code", C.c_void_p), ("qual", C.c_void_p), ("anchor", C.c_void_p), ("ref_bases", C.c_void_p)]
+                ("code", C.c_void_p), ("qual", C.c_void_p), ("anchor", C.c_void_p), ("ref_bases", C.c_void_p),
+                ("layout", C.c_int32), ("reserved", C.c_int32), ("n_flags", C.c_int64), ("flag_index", C.c_void_p), ("flag_bits", C.c_void_p)]
 
 
 class ReadBatch(C.Structure):

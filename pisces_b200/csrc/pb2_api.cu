@@ -264,8 +264,12 @@ extern "C" int pb2_set_intervals(pb2_handle* h, const int32_t* start, const int3
 }
 
 static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs) {
-    if (!h || !p || p->n_loci < 0 || (p->n_loci > 0 && (!p->offsets || !p->code || !p->qual || !p->anchor)))
+    const bool packed = p && p->layout == PB2_LAYOUT_PACKED2;
+    if (!h || !p || p->n_loci < 0 || (p->n_loci > 0 && (!p->offsets || !p->code || !p->qual || (!packed && !p->anchor))))
         return fail(h, PB2_ERR_ARG, "pb2_push_pileup: bad argument");
+    if (p->layout != PB2_LAYOUT_PLANES && !packed) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: unknown layout");
+    if (packed && (p->n_flags < 0 || (p->n_flags > 0 && (!p->flag_index || !p->flag_bits)))) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: bad flag list");
+    if (packed && h->cfg.expect_collapsed) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: PB2_LAYOUT_PACKED2 has no room for the collapsed-read type (expect_collapsed)");
     if (p->n_loci == 0) return PB2_OK;
     if (p->n_loci > (int64_t)1 << 31) return fail(h, PB2_ERR_ARG, "pb2_push_pileup: more than 2^31 loci in one push");
     if (!p->ref_bases && !p->positions && (h->chr_len == 0)) return fail(h, PB2_ERR_STATE, "pb2_push_pileup: no ref_bases given and no reference set");
@@ -347,10 +351,31 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     h->total_launches += 3;
 
     // the interleaving scatter
+    // sparse candidate flags of the packed layout, on the device
+    int64_t* d_flag_index = nullptr;
+    uint8_t* d_flag_bits = nullptr;
+    if (packed && p->n_flags > 0 && !device_ptrs) {
+        CU(h, pool_alloc_t(h, &d_flag_index, (size_t)p->n_flags));
+        CU(h, pool_alloc_t(h, &d_flag_bits, (size_t)p->n_flags));
+        CU(h, cudaMemcpyAsync(d_flag_index, p->flag_index, sizeof(int64_t) * (size_t)p->n_flags, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(d_flag_bits, p->flag_bits, (size_t)p->n_flags, cudaMemcpyHostToDevice, st));
+    }
     if (device_ptrs) {
-        CU(h, launch_tile_scatter(d_off, p->code, p->qual, p->anchor, p->n_loci, 0, s.n_tiles, 0, s.tile_base, s.ref_base, h->dcfg.min_bq, s.code, s.anch, s.pad, s.exc_entries,
+        const uint8_t *pc = p->code, *pq = p->qual, *pa = p->anchor;
+        uint8_t* tmp[3] = {nullptr, nullptr, nullptr};
+        if (packed) {   // unpack into scratch planes (the caller's buffers stay as they are)
+            for (int k = 0; k < 3; k++) CU(h, pool_alloc(h, (void**)&tmp[k], (size_t)std::max<int64_t>(n_entries, 16)));
+            CU(h, cudaMemcpyAsync(tmp[0], p->code, (size_t)n_entries, cudaMemcpyDeviceToDevice, st));
+            CU(h, cudaMemcpyAsync(tmp[1], p->qual, (size_t)n_entries, cudaMemcpyDeviceToDevice, st));
+            CU(h, launch_unpack_packed2(tmp[0], tmp[1], tmp[2], n_entries, st));
+            CU(h, launch_apply_entry_flags(tmp[0], p->flag_index, p->flag_bits, p->n_flags, 0, n_entries, st));
+            h->total_launches += 2;
+            pc = tmp[0]; pq = tmp[1]; pa = tmp[2];
+        }
+        CU(h, launch_tile_scatter(d_off, pc, pq, pa, p->n_loci, 0, s.n_tiles, 0, s.tile_base, s.ref_base, h->dcfg.min_bq, s.code, s.anch, s.pad, s.exc_entries,
                                   s.counters + 3, s.exc_capacity, st));
         h->total_launches += 1;
+        for (int k = 0; k < 3; k++) pool_free(h, tmp[k]);
     } else {
         // Host planes: chunks of whole tiles through two staging buffers; the H2D copy of chunk i+1 (copy stream) overlaps the scatter of chunk i
         // (handle stream), so a push costs the PCIe time of the three planes and little else.
@@ -382,10 +407,15 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
             if (e1 > e0) {
                 CU(h, cudaMemcpyAsync(stage[b][0], p->code + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, h->copy_stream));
                 CU(h, cudaMemcpyAsync(stage[b][1], p->qual + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, h->copy_stream));
-                CU(h, cudaMemcpyAsync(stage[b][2], p->anchor + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, h->copy_stream));
+                if (!packed) CU(h, cudaMemcpyAsync(stage[b][2], p->anchor + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, h->copy_stream));
             }
             CU(h, cudaEventRecord(h->ev_copied[b], h->copy_stream));
             CU(h, cudaStreamWaitEvent(st, h->ev_copied[b], 0));
+            if (packed && e1 > e0) {
+                CU(h, launch_unpack_packed2(stage[b][0], stage[b][1], stage[b][2], e1 - e0, st));
+                CU(h, launch_apply_entry_flags(stage[b][0], d_flag_index, d_flag_bits, p->n_flags, e0, e1, st));
+                h->total_launches += 2;
+            }
             CU(h, launch_tile_scatter(d_off, stage[b][0], stage[b][1], stage[b][2], p->n_loci, t0, t1 - t0, e0, s.tile_base, s.ref_base, h->dcfg.min_bq, s.code, s.anch, s.pad,
                                       s.exc_entries, s.counters + 3, s.exc_capacity, st));
             CU(h, cudaEventRecord(h->ev_scattered[b], st));
@@ -410,6 +440,8 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     pool_free(h, tile_bytes);
     pool_free(h, temp);
     pool_free(h, tmp_off);
+    pool_free(h, d_flag_index);
+    pool_free(h, d_flag_bits);
     CU(h, cudaStreamSynchronize(st));   // the caller's buffers are consumed when this returns
     tr.mark("copy+scatter");
     h->segs.push_back(std::move(s));

@@ -116,6 +116,52 @@ __global__ void tile_scatter_kernel(const int64_t* __restrict__ off, const uint8
     if (locus < n_loci) pad[locus] = npad;
 }
 
+// ------------------------------------------------------------------------------------------------ PB2_LAYOUT_PACKED2 (host pushes of 2 B / entry)
+__global__ void unpack_packed2_kernel(uint8_t* __restrict__ code, uint8_t* __restrict__ qual, uint8_t* __restrict__ anch, int64_t n) {
+    // 16 entries per thread, 16-byte accesses (the staging buffers are 256-byte aligned); the tail is handled byte by byte
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i >= n) return;
+    if (i + 16 <= n) {
+        uint4 c = *reinterpret_cast<const uint4*>(code + i), q = *reinterpret_cast<const uint4*>(qual + i), a;
+        const uint32_t* cw = &c.x; const uint32_t* qw = &q.x; uint32_t* aw = &a.x;
+        uint32_t co[4], qo[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            aw[k] = ((cw[k] >> 5) & 0x07070707u) | ((qw[k] >> 4) & 0x08080808u);
+            co[k] = cw[k] & 0x1f1f1f1fu;
+            qo[k] = qw[k] & 0x7f7f7f7fu;
+        }
+        *reinterpret_cast<uint4*>(code + i) = make_uint4(co[0], co[1], co[2], co[3]);
+        *reinterpret_cast<uint4*>(qual + i) = make_uint4(qo[0], qo[1], qo[2], qo[3]);
+        *reinterpret_cast<uint4*>(anch + i) = a;
+    } else {
+        for (int64_t k = i; k < n; k++) {
+            const uint8_t c = code[k], q = qual[k];
+            anch[k] = (uint8_t)((c >> 5) | ((q >> 7) << 3));
+            code[k] = c & 0x1f;
+            qual[k] = q & 0x7f;
+        }
+    }
+}
+__global__ void apply_entry_flags_kernel(uint8_t* __restrict__ code, const int64_t* __restrict__ flag_index, const uint8_t* __restrict__ flag_bits, int64_t n_flags,
+                                         int64_t e0, int64_t e1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_flags) return;
+    const int64_t e = flag_index[i];
+    if (e >= e0 && e < e1) code[e - e0] |= (uint8_t)(flag_bits[i] & 0xe0);
+}
+cudaError_t launch_unpack_packed2(uint8_t* code, uint8_t* qual, uint8_t* anch, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t threads = (n + 15) / 16;
+    unpack_packed2_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(code, qual, anch, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_apply_entry_flags(uint8_t* code, const int64_t* flag_index, const uint8_t* flag_bits, int64_t n_flags, int64_t e0, int64_t e1, cudaStream_t stream) {
+    if (n_flags <= 0 || e1 <= e0) return cudaSuccess;
+    apply_entry_flags_kernel<<<(unsigned)((n_flags + 255) / 256), 256, 0, stream>>>(code, flag_index, flag_bits, n_flags, e0, e1);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_tile_layout(const int64_t* off, int64_t n_loci, int32_t* depth, int64_t* tile_chunks, int32_t* max_depth, cudaStream_t stream) {
     const int threads = 256;
     const int64_t n_pad = (n_loci + kTileLoci - 1) / kTileLoci * kTileLoci;

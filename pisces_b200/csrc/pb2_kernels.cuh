@@ -98,6 +98,9 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
                               int max_depth, cudaStream_t stream);
 
 // CSR -> PTILE32 staging
+// PB2_LAYOUT_PACKED2 -> the three planes the scatter reads (in place for code / qual, anchor plane written), then the sparse candidate flags
+cudaError_t launch_unpack_packed2(uint8_t* code, uint8_t* qual, uint8_t* anch, int64_t n, cudaStream_t stream);
+cudaError_t launch_apply_entry_flags(uint8_t* code, const int64_t* flag_index, const uint8_t* flag_bits, int64_t n_flags, int64_t e0, int64_t e1, cudaStream_t stream);
 cudaError_t launch_tile_layout(const int64_t* csr_offsets, int64_t n_loci, int32_t* depth, int64_t* tile_chunks /*[n_tiles]*/, int32_t* max_depth,
                                cudaStream_t stream);
 // tiles [tile0, tile0 + n_tiles); code/qual/anch point at entry `entry_base` of the CSR planes (chunked staging)

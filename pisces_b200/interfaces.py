@@ -249,6 +249,34 @@ class GpuStateManager:
         self._keep = [offsets, code, qual, anchor, positions, ref_bases]
         self._chk((self._L.pb2_push_pileup_device if device else self._L.pb2_push_pileup)(self._h, C.byref(p)))
 
+    @staticmethod
+    def pack_pileup(code, qual, anchor):
+        """Host planes (code, qual, anchor) -> PB2_LAYOUT_PACKED2: two bytes per entry plus the sparse list of candidate flags."""
+        code, qual, anchor = (np.ascontiguousarray(x, dtype=np.uint8) for x in (code, qual, anchor))
+        if (anchor >> 4).any():
+            raise ValueError("PB2_LAYOUT_PACKED2 cannot carry the collapsed-read type (anchor bits 4-7)")
+        flag_index = np.flatnonzero(code & 0xe0).astype(np.int64)
+        flag_bits = (code[flag_index] & 0xe0).astype(np.uint8)
+        pcode = (code & 0x1f) | ((anchor & 7) << 5)
+        pqual = (qual & 0x7f) | ((anchor >> 3) << 7)
+        return pcode.astype(np.uint8), pqual.astype(np.uint8), flag_index, flag_bits
+
+    def AddPileupPacked(self, offsets, pcode, pqual, flag_index=None, flag_bits=None, first_position=1, positions=None, ref_bases=None):
+        """pb2_push_pileup with PB2_LAYOUT_PACKED2 host buffers (see pack_pileup): 2 bytes per entry cross the PCIe link instead of 3."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        pcode, pqual = (np.ascontiguousarray(x, dtype=np.uint8) for x in (pcode, pqual))
+        nf = 0 if flag_index is None else len(flag_index)
+        fi = np.ascontiguousarray(flag_index, dtype=np.int64) if nf else None
+        fb = np.ascontiguousarray(flag_bits, dtype=np.uint8) if nf else None
+        if positions is not None:
+            positions = np.ascontiguousarray(positions, dtype=np.int32)
+        if ref_bases is not None:
+            ref_bases = np.ascontiguousarray(ref_bases, dtype=np.uint8)
+        ptr = lambda a: None if a is None else a.ctypes.data
+        p = N.PileupCsr(len(offsets) - 1, int(first_position), ptr(positions), ptr(offsets), ptr(pcode), ptr(pqual), None, ptr(ref_bases), 1, 0, nf, ptr(fi), ptr(fb))
+        self._keep = [offsets, pcode, pqual, fi, fb, positions, ref_bases]
+        self._chk(self._L.pb2_push_pileup(self._h, C.byref(p)))
+
     def AddCandidates(self, candidates, arena=None):
         """IAlleleSource.AddCandidates (pb2_push_candidates). Either a list of dicts (type, pos, ref, alt, support[3], well_anchored[3], open_left,
         open_right, collapsed_mut[8]) or a numpy array of pb2_candidate rows plus the allele arena they point into."""

@@ -209,3 +209,34 @@ def test_window_noise_model_and_qsum():
     d = synth.make_pileup(1500, 300, seed=5, snv_rate=0.05)
     orecs, precs, _, _ = _pileup_both(d, 1, noise_model=1)
     _compare_records(orecs, precs, check_qsum=True)
+
+
+def test_packed2_layout_matches_three_planes():
+    """PB2_LAYOUT_PACKED2 (two bytes per entry + sparse candidate flags, the e2e / PCIe form of pb2_push_pileup) stages the same pileup as the three
+    planes: identical records, field for field, and identical 198-bin counts."""
+    import pisces_b200 as pb
+    from pisces_b200 import synth
+    d = synth.make_pileup(3000, 90, seed=31, snv_rate=0.05)
+    ref = bytes(d["ref_bases"].numpy()).decode()
+    off, code, qual, anch = (d[k].numpy().copy() for k in ("offsets", "code", "qual", "anchor"))
+    rng = np.random.default_rng(5)
+    pick = rng.choice(len(code), 400, replace=False)
+    code[pick] |= 0x20                                    # some open-left SNV candidates (PB2_ENTRY_OPEN_LEFT) for the sparse flag list
+    outs = []
+    for packed in (False, True):
+        sm = pb.GpuStateManager(pb.make_config(output_gvcf=1), "chr1", ref)
+        if packed:
+            pc, pq, fi, fb = pb.GpuStateManager.pack_pileup(code, qual, anch)
+            assert len(fi) >= 400 and pc.nbytes + pq.nbytes == 2 * len(code)
+            sm.AddPileupPacked(off, pc, pq, fi, fb, first_position=1)
+        else:
+            sm.AddPileup(off, code, qual, anch, first_position=1)
+        counts = sm.GetAlleleCounts(1, 3000)
+        recs = pb.GpuAlleleCaller().Call(sm, raw=True)
+        outs.append((np.asarray(counts).copy(), np.array(recs)))
+        sm.close()
+    assert (outs[0][0] == outs[1][0]).all()
+    a, b = outs[0][1], outs[1][1]
+    assert len(a) == len(b) and len(a) >= 3000
+    for f in a.dtype.names:
+        assert np.array_equal(a[f], b[f], equal_nan=a[f].dtype.kind == "f"), f
