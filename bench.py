@@ -267,7 +267,8 @@ def main_ours(a):
     # ---- end to end through the C ABI with HOST buffers: pinned H2D of the step's pileup, tile staging, call, D2H of the records
     if not a.no_e2e:
         # host buffers in PB2_LAYOUT_PACKED2 (2 bytes per entry + the sparse candidate flags): what a host behind a PCIe link hands to pb2_push_pileup
-        pc, pq, fi, fb = pb.GpuStateManager.pack_pileup(d["code"].cpu().numpy(), d["qual"].cpu().numpy(), d["anchor"].cpu().numpy())
+        pc, pq, fi, fb = pb.GpuStateManager.pack_pileup(d["code"].cpu().numpy(), d["qual"].cpu().numpy(), d["anchor"].cpu().numpy(), d["offsets"].cpu().numpy(),
+                                                        d["ref_bases"].cpu().numpy())
         h = {"offsets": d["offsets"].cpu().pin_memory(), "ref_bases": d["ref_bases"].cpu().pin_memory(), "pcode": torch.from_numpy(pc).pin_memory(),
              "pqual": torch.from_numpy(pq).pin_memory(), "flag_index": torch.from_numpy(fi).pin_memory(), "flag_bits": torch.from_numpy(fb).pin_memory()}
         del pc, pq

@@ -209,6 +209,7 @@ extern "C" int pb2_reset(pb2_handle* h) {
     h->reads.clear();
     h->cands.clear(); h->block_max_endpoint.clear(); h->gapped_ref.clear(); h->triggers.clear(); h->arena.clear();
     h->last_trigger_key = 0; h->push_last_key = 0; h->cleared_through = 0;
+    h->snv_explicit_ranges.clear();
     rearm_forced(h);
     explicit_release_resident(h);
     release_resident_graph(h);
@@ -639,6 +640,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     CUC(upload(&d_ref, refb, st));
     CUC(cudaStreamSynchronize(st));
     pb2_pileup_csr csr;
+    memset(&csr, 0, sizeof(csr));
     csr.n_loci = n_loci; csr.first_position = lo; csr.positions = h->have_intervals ? d_positions : nullptr; csr.offsets = d_off;
     csr.code = d_code; csr.qual = d_qual; csr.anchor = d_anch; csr.ref_bases = d_ref;
     const int rc = push_common(h, &csr, true);
@@ -772,13 +774,26 @@ static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std:
         const int32_t pos = s.has_positions ? s.h_positions[locus] : s.first_position + (int32_t)locus;
         return ((uint64_t)(uint32_t)pos << 8) | (uint8_t)base_of[allele & 3];
     };
+    // one byte per locus: which alleles were called there (the flagged entries are many, the called alleles few: no hashing per entry)
+    std::vector<uint8_t> called_mask((size_t)s.n_loci, 0);
+    for (auto& v : vars) {
+        if (v.type != CAT_SNV) continue;
+        int64_t l = -1;
+        if (s.has_positions) {
+            auto it = std::lower_bound(s.h_positions.begin(), s.h_positions.end(), v.position);
+            if (it != s.h_positions.end() && *it == v.position) l = it - s.h_positions.begin();
+        } else l = (int64_t)v.position - s.first_position;
+        if (l < 0 || l >= s.n_loci) continue;
+        const char alt = (char)((v.allele_bytes >> 8) & 0xff);
+        for (int a = 0; a < 4; a++) if (base_of[a] == alt) called_mask[(size_t)l] |= (uint8_t)(1u << a);
+    }
     std::vector<std::pair<Key, Acc>> groups;
     {
         std::vector<std::pair<Key, uint32_t>> items;
         for (size_t i = 0; i + 1 < exc.size(); i += 2) {
             const int allele = (int)(exc[i + 1] & 7);
             if (allele > 3) continue;
-            if (index.find(key_of(exc[i], allele)) == index.end()) continue;
+            if (exc[i] >= (uint32_t)s.n_loci || !((called_mask[exc[i]] >> allele) & 1)) continue;
             items.push_back({Key{exc[i], allele}, exc[i + 1] & 0xffu});
         }
         std::sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
@@ -836,20 +851,27 @@ static bool record_less_arena(const pb2_call_record& a, const pb2_call_record& b
 // Per-locus gapped-MNV reference counts of a segment (RegionState._gappedMnvReferenceCounts), or nullptr when there are none.
 static int upload_gapped(pb2_handle* h, const Segment& s, int32_t** d_out) {
     *d_out = nullptr;
-    if (h->gapped_ref.empty()) return PB2_OK;
+    if (h->gapped_ref.empty() && h->snv_explicit_ranges.empty()) return PB2_OK;
     std::vector<int32_t> g((size_t)s.n_loci, 0);
     bool any = false;
-    for (auto& kv : h->gapped_ref) {
-        int64_t l = -1;
+    auto locus_of = [&](int32_t pos) -> int64_t {
         if (s.has_positions) {
-            auto it = std::lower_bound(s.h_positions.begin(), s.h_positions.end(), kv.first);
-            if (it != s.h_positions.end() && *it == kv.first) l = it - s.h_positions.begin();
-        } else {
-            const int64_t k = (int64_t)kv.first - s.first_position;
-            if (k >= 0 && k < s.n_loci) l = k;
+            auto it = std::lower_bound(s.h_positions.begin(), s.h_positions.end(), pos);
+            return (it != s.h_positions.end() && *it == pos) ? (int64_t)(it - s.h_positions.begin()) : -1;
         }
-        if (l >= 0) { g[(size_t)l] = kv.second; any = true; }
+        const int64_t k = (int64_t)pos - s.first_position;
+        return (k >= 0 && k < s.n_loci) ? k : -1;
+    };
+    for (auto& kv : h->gapped_ref) {
+        const int64_t l = locus_of(kv.first);
+        if (l >= 0) { g[(size_t)l] = kv.second & (kSuppressCountSnvs - 1); any = true; }
     }
+    // positions whose SNV candidates are explicit (explicit_materialize_snvs): the hot kernel must not derive SNVs from the counts there
+    for (auto& r : h->snv_explicit_ranges)
+        for (int64_t i = 0; i < s.n_loci; i++) {
+            const int32_t pos = s.has_positions ? s.h_positions[(size_t)i] : s.first_position + (int32_t)i;
+            if (pos > r.first && pos <= r.second) { g[(size_t)i] |= kSuppressCountSnvs; any = true; }
+        }
     if (!any) return PB2_OK;
     CU(h, cudaMalloc(d_out, sizeof(int32_t) * g.size()));
     CU(h, cudaMemcpyAsync(*d_out, g.data(), sizeof(int32_t) * g.size(), cudaMemcpyHostToDevice, h->stream));
@@ -917,18 +939,43 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
             max_endpoint = std::max(max_endpoint, mep);
         }
         if (max_end == 0) continue;
-        std::vector<size_t> batch;
-        for (size_t i : all_alive_sorted()) if (h->cands[i].position > *cleared_out && h->cands[i].position <= max_end) batch.push_back(i);
-        if (t >= 0 && max_endpoint > max_end && h->cfg.collapse) {
-            for (size_t i : all_alive_sorted()) {   // ExtractCollapsable(upTo) of the blocks that start after max_end and at or before upTo (RegionState.cs:470-490)
-                const HostCand& c = h->cands[i];
-                const int32_t block_start = ((c.position + 999) / 1000 - 1) * 1000 + 1;
-                if (c.position > max_end && block_start <= t && c.position + (int)c.alt.size() - 1 <= t && !c.open_right && (c.type == CAT_MNV || c.type == CAT_SNV))
-                    batch.push_back(i);
+        const bool pull_collapsable = t >= 0 && max_endpoint > max_end && h->cfg.collapse;   // AddCollapsableFromOtherBlocks (:441-457)
+        if (pull_collapsable && !h->cfg.call_mnvs) {
+            // the count-based SNVs of the later blocks' positions <= upTo become explicit candidates first (see explicit_materialize_snvs)
+            int32_t lo = max_end;
+            for (auto& r : h->snv_explicit_ranges) lo = std::max(lo, r.second);
+            const int rc = explicit_materialize_snvs(h, lo, t);
+            if (rc != PB2_OK) return rc;
+        }
+        std::vector<size_t> batch, kill;
+        for (size_t i : all_alive_sorted()) if (h->cands[i].position > *cleared_out && h->cands[i].position <= max_end) { batch.push_back(i); kill.push_back(i); }
+        if (pull_collapsable) {
+            // ExtractCollapsable(upTo) of the blocks that start after max_end and at or before upTo (RegionState.cs:470-490), position by position; each
+            // collapsable goes to the batch, and List.Remove takes the FIRST candidate of the position's list that Equals it out of the state
+            const std::vector<size_t> order = all_alive_sorted();
+            for (size_t a = 0; a < order.size();) {
+                size_t b = a;
+                while (b < order.size() && h->cands[order[b]].position == h->cands[order[a]].position) b++;
+                const HostCand& first = h->cands[order[a]];
+                const int32_t block_start = ((first.position + 999) / 1000 - 1) * 1000 + 1;
+                if (first.position > max_end && block_start <= t) {
+                    std::vector<size_t> list(order.begin() + (long)a, order.begin() + (long)b);
+                    std::vector<size_t> collapsables;
+                    for (size_t i : list) {
+                        const HostCand& c = h->cands[i];
+                        if (c.position + (int)c.alt.size() - 1 <= t && !c.open_right && (c.type == CAT_MNV || c.type == CAT_SNV)) collapsables.push_back(i);
+                    }
+                    for (size_t c : collapsables) {
+                        batch.push_back(c);
+                        for (size_t k = 0; k < list.size(); k++)
+                            if (h->cands[list[k]].Equals(h->cands[c])) { kill.push_back(list[k]); list.erase(list.begin() + (long)k); break; }
+                    }
+                }
+                a = b;
             }
         }
         const int rc = explicit_call_batch(h, batch, t >= 0 ? max_end : -1, *cleared_out == INT32_MAX ? INT32_MAX : *cleared_out, t >= 0 ? max_end : INT32_MAX, called,
-                                           called_ext);
+                                           called_ext, &kill);
         if (rc != PB2_OK) return rc;
         *cleared_out = t >= 0 ? max_end : INT32_MAX;
     }
@@ -1162,7 +1209,11 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
                 const OutRec o = with_totals(OutRec{explicit_called[k], explicit_ext[k]});
                 explicit_used[k] = 1;
                 // CallMNVs off: a forced SNV that is callable on its own merits is already in the hot kernel's variant stream
-                if (!h->cfg.call_mnvs && o.r.type == CAT_SNV && !(o.r.sb_flags & 8)) continue;
+                if (!h->cfg.call_mnvs && o.r.type == CAT_SNV && !(o.r.sb_flags & 8)) {
+                    bool explicit_here = false;   // ... unless the SNV candidates of this position are explicit (the hot kernel derives none there)
+                    for (auto& r : h->snv_explicit_ranges) explicit_here |= o.r.position > r.first && o.r.position <= r.second;
+                    if (!explicit_here) continue;
+                }
                 if (o.r.type == CAT_REF) ref_override.insert({o.r.position, o});
                 else vars.push_back(o);
             }
@@ -1186,7 +1237,24 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
                 ref_override.clear();
             }
         }
-        std::sort(vars.begin(), vars.end(), [&](const OutRec& a, const OutRec& b) { return record_less_arena(a.r, b.r, h->arena); });
+        {   // (position, ref, alt) order: sort 8-byte keys by position, then settle the few positions that hold several alleles
+            std::vector<uint64_t> keys(vars.size());
+            for (size_t k = 0; k < vars.size(); k++) keys[k] = ((uint64_t)(uint32_t)vars[k].r.position << 32) | (uint32_t)k;
+            std::sort(keys.begin(), keys.end());
+            for (size_t a = 0; a < keys.size();) {
+                size_t b = a + 1;
+                while (b < keys.size() && (keys[b] >> 32) == (keys[a] >> 32)) b++;
+                if (b - a > 1)
+                    std::stable_sort(keys.begin() + (long)a, keys.begin() + (long)b, [&](uint64_t x, uint64_t y) {
+                        return record_less_arena(vars[(uint32_t)x].r, vars[(uint32_t)y].r, h->arena);
+                    });
+                a = b;
+            }
+            std::vector<OutRec> sorted;
+            sorted.reserve(vars.size());
+            for (uint64_t k : keys) sorted.push_back(vars[(uint32_t)k]);
+            vars.swap(sorted);
+        }
         // merge the dense reference stream (already in position order) with the sorted variant stream; a reference allele is pruned wherever a
         // variant was called (AlleleCaller.cs:146-147)
         size_t vi = 0;
@@ -1228,7 +1296,7 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
         if (h->segs[i].temporary) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); } else i++;
     }
     h->cands.erase(std::remove_if(h->cands.begin(), h->cands.end(), [](const HostCand& c) { return !c.alive; }), h->cands.end());
-    if (up_to_position < 0) { h->reads.clear(); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; rearm_forced(h); }
+    if (up_to_position < 0) { h->reads.clear(); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; h->snv_explicit_ranges.clear(); rearm_forced(h); }
     else if (reads_path && cleared_to > h->cleared_through) {
         HostReads keep;
         HostReads& R = h->reads;
@@ -1247,6 +1315,8 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
         h->reads = std::move(keep);
         h->cleared_through = cleared_to;
         for (auto it = h->gapped_ref.begin(); it != h->gapped_ref.end();) { if (it->first <= cleared_to) it = h->gapped_ref.erase(it); else ++it; }
+        h->snv_explicit_ranges.erase(std::remove_if(h->snv_explicit_ranges.begin(), h->snv_explicit_ranges.end(),
+                                                    [&](const std::pair<int32_t, int32_t>& r) { return r.second <= cleared_to; }), h->snv_explicit_ranges.end());
     }
     *out = h->h_out.data();
     *n = (int64_t)h->h_out.size();

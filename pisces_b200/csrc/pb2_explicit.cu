@@ -325,11 +325,12 @@ int explicit_add_forced_candidates(pb2_handle* h, int32_t up_to) {   // SmallVar
 
 // ------------------------------------------------------------------------------------------------ AlleleCaller.Call, explicit part
 int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, int32_t ref_lo, int32_t ref_hi, std::vector<pb2_call_record>& called,
-                        std::vector<pb2_call_record_ext>& called_ext) {
+                        std::vector<pb2_call_record_ext>& called_ext, const std::vector<size_t>* kill) {
     if (batch.empty()) return PB2_OK;
     std::vector<HostCand> cs;
     cs.reserve(batch.size());
-    for (size_t idx : batch) { cs.push_back(h->cands[idx]); h->cands[idx].alive = false; }   // the batch leaves the state (DoneProcessing / ExtractCollapsable)
+    for (size_t idx : batch) { cs.push_back(h->cands[idx]); cs.back().alive = true; }
+    for (size_t idx : (kill ? *kill : batch)) h->cands[idx].alive = false;   // the batch leaves the state (DoneProcessing / ExtractCollapsable)
     BatchCtx ctx(h);
     std::vector<uint8_t>& arena = h->arena;
     int rc;
@@ -355,14 +356,20 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
     if (!h->cfg.call_mnvs) {
         // CallMNVs off: SNV candidates are the counts themselves and never enter this table — except forced SNV alleles, which arrive with zero
         // support and merge with what the finder raised from the reads (RegionState.AddCandidate :94-174): that support is the count of their base
+        // (positions whose SNV candidates were made explicit carry the finder's own support: explicit_materialize_snvs)
+        auto count_based = [&](const HostCand& c) {
+            if (c.type != CAT_SNV) return false;
+            for (auto& r : h->snv_explicit_ranges) if (c.position > r.first && c.position <= r.second) return false;
+            return true;
+        };
         std::vector<int32_t> snv_pos;
-        for (auto& c : cs) if (c.type == CAT_SNV) snv_pos.push_back(c.position);
+        for (auto& c : cs) if (count_based(c)) snv_pos.push_back(c.position);
         if (!snv_pos.empty()) {
             std::unordered_map<int32_t, std::array<int32_t, kNumAlleles * kNumDirs>> pc;
             rc = host_point_counts(snv_pos, pc);
             if (rc != PB2_OK) return rc;
             for (auto& c : cs)
-                if (c.type == CAT_SNV) for (int d = 0; d < 3; d++) c.support[d] = pc[c.position][(size_t)(allele_index(c.alt[0]) * kNumDirs + d)];
+                if (count_based(c)) for (int d = 0; d < 3; d++) c.support[d] = pc[c.position][(size_t)(allele_index(c.alt[0]) * kNumDirs + d)];
         }
     }
 
@@ -713,11 +720,34 @@ int explicit_prune_resident(pb2_handle* h, Segment& seg) {
 }
 
 // ------------------------------------------------------------------------------------------------ candidates of pushed reads
-int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_read) {
+static int find_candidates_impl(pb2_handle* h, const HostReads& R, size_t first_read, int32_t snv_lo, int32_t snv_hi);
+int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_read) { return find_candidates_impl(h, R, first_read, 0, 0); }
+// CallMNVs off: SNV candidates are the counts — until RegionStateManager.AddCollapsableFromOtherBlocks (:441-457) pulls the finished SNV candidates of a
+// later block into an earlier batch. What happens to them there depends on their open-end twins and the order they were raised in
+// (RegionState.ExtractCollapsable :470-490 removes with List.Remove, i.e. the first candidate that Equals), so from then on the SNV candidates at the
+// positions (lo, hi] are explicit: found in the kept reads exactly as the reference's finder raised them, and the hot kernel stops deriving SNVs from
+// the counts there (Segment gapped/suppress array). No read that arrives later can touch these positions (reads come in position order).
+int explicit_materialize_snvs(pb2_handle* h, int32_t lo, int32_t hi) {
+    if (hi <= lo) return PB2_OK;
+    // SNV candidates already in the table here can only be forced alleles; the reference adds a forced allele once calling has passed its position
+    // (SmallVariantCaller.cs:99-104), i.e. after every read that covers it: keep that order in the position's candidate list
+    std::vector<HostCand> forced_here;
+    for (auto& c : h->cands)
+        if (c.alive && c.type == CAT_SNV && c.position > lo && c.position <= hi) { forced_here.push_back(c); c.alive = false; }
+    const int rc = find_candidates_impl(h, h->reads, 0, lo, hi);
+    if (rc != PB2_OK) return rc;
+    for (auto& c : forced_here) { c.alive = true; explicit_add_candidate(h, c); }
+    h->snv_explicit_ranges.push_back({lo, hi});
+    return PB2_OK;
+}
+// snv_lo < snv_hi: only the SNV candidates at positions in (snv_lo, snv_hi], found with the CallMNVs-off state machine (ShouldBuildUpMNV :170-181 returns
+// false: every mismatch is its own SNV); used when count-based SNVs have to become explicit candidates (explicit_materialize_snvs)
+static int find_candidates_impl(pb2_handle* h, const HostReads& R, size_t first_read, int32_t snv_lo, int32_t snv_hi) {
+    const bool snv_only = snv_lo < snv_hi;
     const size_t n = R.size() - first_read;
     if (n == 0) return PB2_OK;
     if (h->chr_len == 0) return PB2_OK;   // no reference: the finder has nothing to compare against (the reference would throw on refChromosome[...])
-    bool any = h->cfg.call_mnvs != 0;
+    bool any = h->cfg.call_mnvs != 0 || snv_only;
     if (!any)
         for (int64_t k = R.cigar_off[first_read]; k < R.cigar_off[R.size()] && !any; k++) { const uint32_t op = R.cigar[(size_t)k] & 15; any = op == 1 || op == 2; }
     if (!any) return PB2_OK;
@@ -745,13 +775,13 @@ int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_rea
     if (R.has_dirs) CUX(h, up(d_dirs, R.base_dirs.data() + s_base, n_seq));
     if (R.has_collapsed) CUX(h, up(d_coll, R.collapsed.data() + first_read, n));
     // every insertion / deletion operation raises at most one candidate, every aligned base at most one SNV/MNV
-    const int64_t capacity = (int64_t)n_cig + (h->cfg.call_mnvs ? (int64_t)n_seq : 0) + 16;
+    const int64_t capacity = (int64_t)n_cig + ((h->cfg.call_mnvs || snv_only) ? (int64_t)n_seq : 0) + 16;
     CUX(h, d_raw.reserve((size_t)capacity, st));
     CUX(h, d_count.reserve(1, st));
     CUX(h, cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), st));
     ReadsView rv{(int32_t)n, d_pos0.p, d_flag.p, d_coff.p, d_cigar.p, d_soff.p, d_bases.p, d_quals.p, R.has_dirs ? d_dirs.p : nullptr, R.has_collapsed ? d_coll.p : nullptr};
-    CUX(h, launch_reads_candidates(rv, 0, h->d_chr, h->chr_len, h->dcfg.min_bq, h->cfg.call_mnvs, h->cfg.max_size_mnv, h->cfg.max_gap_mnv, h->cfg.expect_collapsed, d_raw.p,
-                                   d_count.p, capacity, st));
+    CUX(h, launch_reads_candidates(rv, 0, h->d_chr, h->chr_len, h->dcfg.min_bq, snv_only ? 1 : h->cfg.call_mnvs, snv_only ? 0 : h->cfg.max_size_mnv,
+                                   snv_only ? 0 : h->cfg.max_gap_mnv, h->cfg.expect_collapsed, d_raw.p, d_count.p, capacity, st));
     h->total_launches += 1;
     unsigned long long cnt = 0;
     CUX(h, cudaMemcpyAsync(&cnt, d_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
@@ -763,6 +793,7 @@ int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_rea
     std::sort(raw.begin(), raw.end(), [](const RawCand& a, const RawCand& b) { return a.read != b.read ? a.read < b.read : a.order < b.order; });
     for (const RawCand& rc : raw) {
         if (rc.position <= h->cleared_through || rc.position < 1) continue;
+        if (snv_only && (rc.type != CAT_SNV || rc.position <= snv_lo || rc.position > snv_hi)) continue;
         HostCand c;
         c.position = rc.position; c.type = rc.type;
         c.open_left = (rc.flags & 1) != 0; c.open_right = (rc.flags & 2) != 0;

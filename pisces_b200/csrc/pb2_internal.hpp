@@ -150,6 +150,7 @@ struct pb2_handle {
     int64_t resident_graph_launches = 0;              // kernels inside the graph
     unsigned long long* h_counters = nullptr;         // pinned: the segment's counters after a step
     std::vector<uint8_t> arena;                       // allele bytes the last flush's records point into
+    std::vector<std::pair<int32_t, int32_t>> snv_explicit_ranges;   // (lo, hi] positions whose SNV candidates were made explicit (explicit_materialize_snvs)
     // ---- forced-genotyping alleles (pb2_set_forced_alleles)
     std::set<std::tuple<int32_t, std::string, std::string>> forced;                             // AlleleCaller.ForcedGtAlleles (position, ref, alt)
     std::map<int32_t, std::vector<std::pair<std::string, std::string>>> forced_pending;         // SmallVariantCaller._unProcessedForcedAllelesByPos
@@ -167,8 +168,11 @@ void explicit_add_candidate(pb2_handle* h, const HostCand& c);
 // ShouldReport) are appended to `called`; candidates that go back to the state (not cleared / MNV leftovers) are re-added to h->cands.
 // max_cleared < 0 = null (everything is cleared). (ref_lo, ref_hi] are the positions of the batch's blocks: with forced alleles and reference calls off,
 // RegionState.GetAllCandidates (:383-453) adds a Reference candidate at every forced position in them.
+// `kill`: the candidates that leave the state when the batch is formed (default: the batch itself). RegionState.ExtractCollapsable (:470-490) removes
+// with List.Remove — the first candidate that Equals (open ends ignored) — so the two can differ.
 int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, int32_t ref_lo, int32_t ref_hi, std::vector<pb2_call_record>& called,
-                        std::vector<pb2_call_record_ext>& called_ext);
+                        std::vector<pb2_call_record_ext>& called_ext, const std::vector<size_t>* kill = nullptr);
+int explicit_materialize_snvs(pb2_handle* h, int32_t lo, int32_t hi);
 // SmallVariantCaller.AddForcedAlleleAsCandidate (:118-155): forced alleles at positions <= up_to (< 0: all) become zero-support candidates.
 int explicit_add_forced_candidates(pb2_handle* h, int32_t up_to);
 // Finds the candidates of the reads in R[first_read, end) on the device (CandidateVariantFinder.FindCandidates) and adds them to the table.

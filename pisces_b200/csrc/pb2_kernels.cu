@@ -360,9 +360,10 @@ constexpr int kCtaPending = 64;   // per-CTA queue of the vertical-counter kerne
 __device__ __forceinline__ void finish_locus(const int (&cnt)[kNumAlleles][kNumDirs], double qsum, int any, int64_t locus, int ref_allele, const TilePileup& in,
                                              const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, PendingLocus* cta_queue = nullptr,
                                              int* cta_count = nullptr) {
-    const int gapped = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
+    const int gapped_word = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
+    const int gapped = gapped_word & (kSuppressCountSnvs - 1);
     unsigned cand_mask = 0;
-    if (ref_allele != AT_N && cfg.snv_from_counts) {
+    if (ref_allele != AT_N && cfg.snv_from_counts && !(gapped_word & kSuppressCountSnvs)) {
         int total = 0;
 #pragma unroll
         for (int d = 0; d < 3; d++) total += cnt[AT_A][d] + cnt[AT_C][d] + cnt[AT_G][d] + cnt[AT_T][d] + cnt[AT_DEL][d];

@@ -19,6 +19,10 @@ constexpr int kNarrowThreads = 1024;        // 8-bit histograms: twice the warps
 constexpr int kNarrowMaxDepth = 60000;      // 8-bit row-wrap counters hold 255 wraps of 256
 
 // Scalars the kernels need from pb2_config (validated / derived on the host, Config semantics of VariantCallingParameters.Validate).
+// HotInputsExtra.gapped_ref[locus]: RegionState._gappedMnvReferenceCounts in the low bits; this bit = do not derive SNV candidates from the counts at
+// this locus (its SNV candidates are explicit, pb2_explicit.cu:explicit_materialize_snvs)
+constexpr int32_t kSuppressCountSnvs = 1 << 30;
+
 struct DeviceConfig {
     int min_bq;
     int noise_level;

@@ -250,12 +250,20 @@ class GpuStateManager:
         self._chk((self._L.pb2_push_pileup_device if device else self._L.pb2_push_pileup)(self._h, C.byref(p)))
 
     @staticmethod
-    def pack_pileup(code, qual, anchor):
-        """Host planes (code, qual, anchor) -> PB2_LAYOUT_PACKED2: two bytes per entry plus the sparse list of candidate flags."""
+    def pack_pileup(code, qual, anchor, offsets=None, ref_bases=None):
+        """Host planes (code, qual, anchor) -> PB2_LAYOUT_PACKED2: two bytes per entry plus the sparse list of candidate flags. With offsets and
+        ref_bases given, flags on entries whose base is the reference base of their locus are left out: such a base raises no SNV candidate
+        (CandidateVariantFinder.cs:112-141), so its open-end flags say nothing (staging clears them as well)."""
         code, qual, anchor = (np.ascontiguousarray(x, dtype=np.uint8) for x in (code, qual, anchor))
         if (anchor >> 4).any():
             raise ValueError("PB2_LAYOUT_PACKED2 cannot carry the collapsed-read type (anchor bits 4-7)")
         flag_index = np.flatnonzero(code & 0xe0).astype(np.int64)
+        if offsets is not None and ref_bases is not None and len(flag_index):
+            locus = np.searchsorted(np.asarray(offsets, dtype=np.int64), flag_index, side="right") - 1
+            ref_allele = np.full(256, 4, dtype=np.uint8)
+            ref_allele[[ord("A"), ord("G"), ord("C"), ord("T")]] = [0, 1, 2, 3]
+            keep = (code[flag_index] & 7) != ref_allele[np.asarray(ref_bases, dtype=np.uint8)[locus]]
+            flag_index = flag_index[keep]
         flag_bits = (code[flag_index] & 0xe0).astype(np.uint8)
         pcode = (code & 0x1f) | ((anchor & 7) << 5)
         pqual = (qual & 0x7f) | ((anchor >> 3) << 7)

@@ -226,8 +226,8 @@ def test_packed2_layout_matches_three_planes():
     for packed in (False, True):
         sm = pb.GpuStateManager(pb.make_config(output_gvcf=1), "chr1", ref)
         if packed:
-            pc, pq, fi, fb = pb.GpuStateManager.pack_pileup(code, qual, anch)
-            assert len(fi) >= 400 and pc.nbytes + pq.nbytes == 2 * len(code)
+            pc, pq, fi, fb = pb.GpuStateManager.pack_pileup(code, qual, anch, off, d["ref_bases"].numpy())
+            assert 0 < len(fi) < len(pb.GpuStateManager.pack_pileup(code, qual, anch)[2]) and pc.nbytes + pq.nbytes == 2 * len(code)
             sm.AddPileupPacked(off, pc, pq, fi, fb, first_position=1)
         else:
             sm.AddPileup(off, code, qual, anch, first_position=1)
