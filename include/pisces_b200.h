@@ -242,6 +242,38 @@ int pb2_get_counts(pb2_handle* h, int32_t position0, int32_t n, int32_t* out);
 /* Drop staged pileups and results (IStateManager.DoneProcessing). */
 int pb2_reset(pb2_handle* h);
 
+/* VCF record lines for called alleles, as the reference's writer prints them when every allele gets its own line (AllowMultipleVcfLinesPerLoci, the
+ * somatic default): VcfFileWriter.WriteListOfColocatedAlleles (src/lib/Pisces.IO/VcfFileWriter.cs:206-260) with VcfFormatter
+ * (src/lib/Pisces.IO/VcfFormatter.cs:52-71,143-251,283-420). CHROM is the name given to pb2_set_reference; alleles longer than 4 bases are read from
+ * the arena of the last pb2_flush. `ext` (pb2_flush_ext) feeds the US tag and may be NULL. The text (one '\n'-terminated line per record; no header)
+ * is owned by the handle until the next call. The crushed one-line-per-locus form of the germline writer is not built. */
+typedef struct pb2_vcf_options {
+    int32_t debug_mode;          /* PiscesApplicationOptions.DebugMode */
+    int32_t output_bias_files;   /* OutputBiasFiles */
+    int32_t report_rc_counts;    /* VcfWritingParameters.ReportRcCounts: the US tag */
+    int32_t report_ts_counts;    /* ReportTsCounts */
+} pb2_vcf_options;
+int pb2_vcf_format(pb2_handle* h, const pb2_call_record* records, const pb2_call_record_ext* ext, int64_t n, const pb2_vcf_options* options, const char** text,
+                   int64_t* len);
+
+/* BAM -> pb2_read_batch stager (host code; rows a1-a4 of the path): BGZF inflate + record decode (src/lib/Alignment.IO/BamReader.cs:137-224), the read
+ * filter AlignmentSource.ShouldSkipRead (src/exe/Pisces/Logic/Alignment/AlignmentsSource.cs:84-92), Read.SequencedBaseDirectionMap from the XD tag
+ * (Read.cs:390-421,664-682) and the collapsed-read summary from XV / XW / XR or the pair flags (Read.cs:66-71,311-349). pb2_bam_next_batch hands out up
+ * to max_reads kept reads of ONE reference sequence in file order (*ref_id; n_reads == 0 at the end of the file) as a pb2_read_batch whose arrays the
+ * reader owns until the next call: push it with pb2_push_reads. is_stitched / is_collapsed are read off the @PG header lines
+ * (BamFileAlignmentExtractor.cs:111-153) and belong in pb2_config.expect_stitched / expect_collapsed. */
+typedef struct pb2_bam_reader pb2_bam_reader;
+typedef struct pb2_bam_filter {
+    int32_t min_map_quality;     /* BamFilterParameters.MinimumMapQuality (1) */
+    int32_t remove_duplicates;   /* RemoveDuplicates (1) */
+    int32_t only_proper_pairs;   /* OnlyUseProperPairs (0) */
+} pb2_bam_filter;
+int pb2_bam_open(const char* path, pb2_bam_reader** out);
+void pb2_bam_close(pb2_bam_reader* r);
+const char* pb2_bam_last_error(pb2_bam_reader* r);
+int pb2_bam_header(pb2_bam_reader* r, int32_t* n_refs, const char* const** names, const int32_t** lengths, int32_t* is_stitched, int32_t* is_collapsed);
+int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* filter, int32_t max_reads, pb2_read_batch* batch, int32_t* ref_id, int64_t* n_skipped);
+
 /* IAlleleCaller.TotalNumCollapsed (src/exe/Pisces/Interfaces/IAlleleCaller.cs:11): candidates merged by the collapser since pb2_create. */
 int pb2_totals(pb2_handle* h, int64_t* total_collapsed);
 

@@ -157,6 +157,7 @@ struct pb2_handle {
     std::vector<std::tuple<int32_t, std::string, std::string>> forced_order;                    // the HashSet's enumeration (= insertion) order
     std::vector<int32_t> forced_positions;   // one per forced allele inside the intervals, in that order: RegionState.CreateIntervalsFromAllels (:455-468)
     int64_t total_collapsed = 0;
+    std::string vcf_text;                             // pb2_vcf_format's output
 };
 
 // pb2_explicit.cu

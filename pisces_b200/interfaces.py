@@ -319,6 +319,15 @@ class GpuStateManager:
         ab = np.frombuffer(bytes(buf), dtype=np.uint8) if len(buf) else np.zeros(1, dtype=np.uint8)
         self._chk(self._L.pb2_set_forced_alleles(self._h, arr.ctypes.data, len(alleles), ab.ctypes.data, len(buf)))
 
+    def FormatVcf(self, records, ext=None, debug_mode=False, output_bias_files=False, report_rc_counts=False, report_ts_counts=False):
+        """pb2_vcf_format: the VCF record lines of raw records (Call(..., raw=True)) of the last flush, as a list of strings."""
+        records = np.ascontiguousarray(records)
+        opt = (C.c_int32 * 4)(int(debug_mode), int(output_bias_files), int(report_rc_counts), int(report_ts_counts))
+        text, n = C.c_char_p(), C.c_int64()
+        e = None if ext is None else np.ascontiguousarray(ext)
+        self._chk(self._L.pb2_vcf_format(self._h, records.ctypes.data, None if e is None else e.ctypes.data, len(records), opt, C.byref(text), C.byref(n)))
+        return C.string_at(text, n.value).decode().split("\n")[:-1]
+
     def AlleleArena(self):
         """Bytes that pb2_call_record.allele_bytes of the last Call points into for alleles longer than 4 bases."""
         p, n = C.c_void_p(), C.c_int64()

@@ -320,41 +320,19 @@ def test_streamed_reads_collapsable_snvs_from_later_blocks(seed, gvcf):
     _compare_chunks(orecs, chunks)
 
 
-class _RecordView:
-    """A pb2_call_record shaped like the oracle's record, for the VCF text restatement (oracle/vcf_text.py, test infrastructure)."""
-    _FILTER_ORDER = [4, 3, 12, 0, 2, 7, 9, 5, 6, 10]   # the order AlleleProcessor.ApplyFilters / the genotyper add them (AlleleProcessor.cs:25-71)
-
-    def __init__(self, p, arena, ext=None):
-        self.collapsed_mut = [int(x) for x in ext["collapsed_mut"]] if ext is not None else [0] * 8
-        self.collapsed_total = [int(x) for x in ext["collapsed_total"]] if ext is not None else [0] * 8
-        rl, al, ab = int(p["ref_len"]), int(p["alt_len"]), int(p["allele_bytes"])
-        raw = ab.to_bytes(4, "little") if rl + al <= 4 else bytes(arena[ab:ab + rl + al])
-        self.ref, self.alt = raw[:rl].decode(), raw[rl:rl + al].decode()
-        self.pos, self.type, self.genotype = int(p["position"]), int(p["type"]), int(p["genotype"])
-        self.gq, self.vq = int(p["genotype_qscore"]), int(p["variant_qscore"])
-        self.filters = [f for f in self._FILTER_ORDER if int(p["filters"]) >> f & 1]
-        self.n_filters = len(self.filters)
-        self.total_coverage, self.allele_support, self.ref_support = int(p["total_coverage"]), int(p["allele_support"]), int(p["reference_support"])
-        self.frequency = np.float32(0) if self.total_coverage == 0 else min(np.float32(self.allele_support) / np.float32(self.total_coverage), np.float32(1))
-        self.noise_level, self.gatk_bias_score, self.forced = int(p["noise_level"]), float(p["gatk_bias_score"]), int(p["sb_flags"]) >> 3 & 1
-
-
 @pytest.mark.parametrize("min_vq,forced,golden", [(1, False, "phix_s3_noisy.records.vcf"), (1, True, "phix_s3_forced1.records.vcf"),
                                                   (20, True, "phix_s3_forced2.records.vcf")])
 def test_phix_full_text_golden_through_cuda_path(min_vq, forced, golden):
     """The reference's own full-text goldens (PhiX_S3.bam -> PhiX_S3.noisy.vcf, .Forced1.vcf, .Forced2.vcf; ForcedGTFxnlTest.cs:11-112) reproduced
     line by line from the records the CUDA path emits: MNVs up to 10 with gaps of 5, collapsing, MNV reallocation, gapped-MNV reference take-away,
-    q-scores, strand bias, and the forced alleles of PhiX_S3.forcedGTInput.vcf (pb2_set_forced_alleles)."""
+    q-scores, strand bias, the forced alleles of PhiX_S3.forcedGTInput.vcf (pb2_set_forced_alleles), and the VCF text of the library's writer (pb2_vcf_format)."""
     import gzip
     import json
     import os
-    from oracle.vcf_text import VcfText
     pb = _pb()
     G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     d = json.load(gzip.open(os.path.join(G, "phix_s3_reads.json.gz"), "rt"))
     genome = open(os.path.join(G, "phix_genome.txt")).read().strip()
-    okw = dict(min_coverage=2, min_base_call_quality=10, min_vq=min_vq, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1, max_size_mnv=10,
-               max_gap_mnv=5, no_call_filter=1.0)
     pkw = dict(min_coverage=2, min_base_call_quality=10, min_variant_qscore=min_vq, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1, max_size_mnv=10,
                max_gap_mnv=5, no_call_filter=1.0)
     # AlignmentSource.ShouldSkipRead (AlignmentsSource.cs:84-92): mapped, primary, not duplicate, mapq >= 1, has a CIGAR — host-side filter
@@ -364,19 +342,13 @@ def test_phix_full_text_golden_through_cuda_path(min_vq, forced, golden):
         fa = json.load(open(os.path.join(G, "phix_forced_alleles.json")))
         sm.SetForcedAlleles([(p, r, a) for p, r, a in fa if all(ch in "ACGT" for ch in a)])
     caller = pb.GpuAlleleCaller()
-    views = []
+    got = []      # the VCF text comes from the library's own writer (pb2_vcf_format), formatted flush by flush
     for i in range(0, len(reads), 50):      # streamed like SmallVariantCaller.Execute: push a few reads, call up to the last read's position - 1
         chunk = reads[i:i + 50]
         sm.AddAlleleCounts([pb.Read(r["pos0"] + 1, r["seq"], r["cigar"], r["qual"], flag=r["flag"]) for r in chunk])
-        recs = caller.Call(sm, upToPosition=chunk[-1]["pos0"], raw=True)
-        arena = sm.AlleleArena()
-        views += [_RecordView(p, arena) for p in recs]
-    recs = caller.Call(sm, raw=True)
-    arena = sm.AlleleArena()
-    views += [_RecordView(p, arena) for p in recs]
+        got += sm.FormatVcf(caller.Call(sm, upToPosition=chunk[-1]["pos0"], raw=True))
+    got += sm.FormatVcf(caller.Call(sm, raw=True))
     sm.close()
-    vt = VcfText(ob.default_config(**okw), ob.FILTERS, ob.GENOTYPES)
-    got = [vt.line("phix", v) for v in views]
     exp = [l.rstrip("\n") for l in open(os.path.join(G, golden))]
     assert len(got) == len(exp)
     for a, b in zip(got, exp):
@@ -390,13 +362,11 @@ def test_collapsed_stitched_full_text_golden_through_cuda_path():
     (no Validate()), hence skip_validation."""
     import json
     import os
-    from oracle.vcf_text import VcfText
     pb = _pb()
     G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     reads = json.load(open(os.path.join(G, "collapsed_stitched_reads.json")))
     seq = "N" * (9770498 - 1) + ("GAAGTAACAACGCAGGATGCCCCCTGGGGTGGACTGCCCCATGGAATTCTGGACCAAGGAGGAGAATCAGAGCGTTGTGGTTGACTTCCTGCTGCCCACAGGGGTCTACCTGAACTTCCCTGTGTCCCGCAATGCCAACCTC"
                                  "AGCACCATCAAGCAGGTATGGCCTCCATC")
-    okw = dict(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, source_is_stitched=1, source_is_collapsed=1, apply_validation=0)
     pkw = dict(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, expect_stitched=1, expect_collapsed=1, skip_validation=1)
 
     def base_dirs(r):   # Read.SequencedBaseDirectionMap: the XD runs projected onto the read bases (Read.cs:390-421,664-682)
@@ -424,11 +394,10 @@ def test_collapsed_stitched_full_text_golden_through_cuda_path():
     sm = pb.GpuStateManager(pb.make_config(**pkw), "chr1", seq)
     sm.AddAlleleCounts([pb.Read(r["pos0"] + 1, r["seq"], r["cigar"], r["qual"], flag=r["flag"], base_directions=base_dirs(r), collapsed=collapsed_byte(r)) for r in reads])
     recs = pb.GpuAlleleCaller().Call(sm, raw=True)
-    arena, ext = sm.AlleleArena(), sm.AlleleExt()
-    sm.close()
+    ext = sm.AlleleExt()
     assert len(ext) == len(recs)
-    vt = VcfText(ob.default_config(**okw), ob.FILTERS, ob.GENOTYPES, debug=True, output_bias_files=True, report_rc_counts=True, report_ts_counts=True)
-    got = [vt.line("chr1", _RecordView(p, arena, e)) for p, e in zip(recs, ext)]
+    got = sm.FormatVcf(recs, ext, debug_mode=True, output_bias_files=True, report_rc_counts=True, report_ts_counts=True)
+    sm.close()
     exp = [l.rstrip("\n") for l in open(os.path.join(G, "collapsed_stitched.records.vcf"))]
     assert len(got) == len(exp)
     for a, b in zip(got, exp):
