@@ -5,8 +5,8 @@ host-side mirror of the reference's interfaces for that path (IStateManager / IA
 tests, bench.py and Python hosts. Importing it never falls back to a CPU implementation.
 """
 from . import _native  # noqa: F401
-from .interfaces import (AlleleCategory, AlleleType, CalledAllele, DirectionType, FilterType, Genotype, GpuAlleleCaller, GpuStateManager,
+from .interfaces import (AlleleCategory, AlleleType, BamReadStager, CalledAllele, DirectionType, FilterType, Genotype, GpuAlleleCaller, GpuStateManager,
                          PiscesB200Error, Read, VariantCallerConfig, make_config)
 
-__all__ = ["AlleleCategory", "AlleleType", "CalledAllele", "DirectionType", "FilterType", "Genotype", "GpuAlleleCaller", "GpuStateManager",
+__all__ = ["AlleleCategory", "AlleleType", "BamReadStager", "CalledAllele", "DirectionType", "FilterType", "Genotype", "GpuAlleleCaller", "GpuStateManager",
            "PiscesB200Error", "Read", "VariantCallerConfig", "make_config"]

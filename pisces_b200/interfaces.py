@@ -10,6 +10,7 @@ Method names and argument meaning follow the reference so that tests read like t
 libpisces_b200.so on the GPU; this module only marshals.
 """
 import ctypes as C
+import os
 import enum
 
 import numpy as np
@@ -285,6 +286,10 @@ class GpuStateManager:
         self._keep = [offsets, pcode, pqual, fi, fb, positions, ref_bases]
         self._chk(self._L.pb2_push_pileup(self._h, C.byref(p)))
 
+    def AddReadBatch(self, batch):
+        """pb2_push_reads with a ready pb2_read_batch (e.g. from BamReadStager): IStateManager.AddAlleleCounts + FindCandidates for each read."""
+        self._chk(self._L.pb2_push_reads(self._h, C.byref(batch)))
+
     def AddCandidates(self, candidates, arena=None):
         """IAlleleSource.AddCandidates (pb2_push_candidates). Either a list of dicts (type, pos, ref, alt, support[3], well_anchored[3], open_left,
         open_right, collapsed_mut[8]) or a numpy array of pb2_candidate rows plus the allele arena they point into."""
@@ -392,6 +397,43 @@ class GpuStateManager:
 
 
 N_ERR_ARG = -1
+
+
+class BamReadStager:
+    """pb2_bam_*: BAM file -> pb2_read_batch batches (BGZF inflate, record decode, AlignmentSource.ShouldSkipRead, XD / XV / XW / XR), all in the library.
+    Iterating yields (ref_id, ReadBatch struct, n_skipped); a batch is only valid until the next one is fetched."""
+
+    def __init__(self, path, min_map_quality=1, remove_duplicates=True, only_proper_pairs=False, max_reads=65536):
+        self._L = N.load()
+        self._r = C.c_void_p()
+        if self._L.pb2_bam_open(os.fsencode(path), C.byref(self._r)) != 0:
+            raise PiscesB200Error(N_ERR_ARG, f"pb2_bam_open({path}) failed")
+        self._flt = (C.c_int32 * 3)(int(min_map_quality), int(remove_duplicates), int(only_proper_pairs))
+        self.max_reads = max_reads
+        n, names, lens, st, co = C.c_int32(), C.POINTER(C.c_char_p)(), C.POINTER(C.c_int32)(), C.c_int32(), C.c_int32()
+        self._L.pb2_bam_header(self._r, C.byref(n), C.byref(names), C.byref(lens), C.byref(st), C.byref(co))
+        self.references = [(names[i].decode(), int(lens[i])) for i in range(n.value)]
+        self.is_stitched, self.is_collapsed = bool(st.value), bool(co.value)
+
+    def __iter__(self):
+        while True:
+            b, ref_id, skipped = N.ReadBatch(), C.c_int32(), C.c_int64()
+            if self._L.pb2_bam_next_batch(self._r, self._flt, self.max_reads, C.byref(b), C.byref(ref_id), C.byref(skipped)) != 0:
+                raise PiscesB200Error(N_ERR_ARG, self._L.pb2_bam_last_error(self._r).decode())
+            if b.n_reads == 0:
+                return
+            yield ref_id.value, b, skipped.value
+
+    def close(self):
+        if self._r:
+            self._L.pb2_bam_close(self._r)
+            self._r = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class GpuAlleleCaller:

@@ -5,7 +5,7 @@
   inputs : /root/reference/src/test/SharedData/Bams/PhiX_S3.bam, .../Genomes/PhiX/WholeGenomeFasta/genome.fa,
            /root/reference/src/test/Pisces.Tests/TestData/PhiX_S3.{noisy,Forced1,Forced2}.vcf, PhiX_S3.forcedGTInput.vcf
            (the full-text goldens of src/test/Pisces.Tests/FunctionalTests/ForcedGTFxnlTest.cs:11-112)
-  outputs: phix_s3_reads.json.gz (decoded alignments), phix_genome.txt, phix_s3_{noisy,forced1,forced2}.records.vcf (record lines only),
+  outputs: PhiX_S3.bam, collapsed.test.stitched.bam (copies), phix_s3_reads.json.gz (decoded alignments), phix_genome.txt, phix_s3_{noisy,forced1,forced2}.records.vcf (record lines only),
            phix_forced_alleles.json
 """
 import gzip
@@ -21,6 +21,12 @@ REF = "/root/reference/src/test"
 
 
 def main():
+    # the two BAM files themselves (15.7 KB and 1.3 KB of test data, not source): inputs of the library's own BAM stager (pb2_bam_*)
+    import shutil
+    shutil.copyfile(f"{REF}/SharedData/Bams/PhiX_S3.bam", os.path.join(HERE, "PhiX_S3.bam"))
+    shutil.copyfile(f"{REF}/Pisces.Tests/TestData/collapsed.test.stitched.bam", os.path.join(HERE, "collapsed.test.stitched.bam"))
+    os.chmod(os.path.join(HERE, "PhiX_S3.bam"), 0o644)
+    os.chmod(os.path.join(HERE, "collapsed.test.stitched.bam"), 0o644)
     _, refs, recs = bamio.read_bam(f"{REF}/SharedData/Bams/PhiX_S3.bam")
     fa = bamio.read_fasta(f"{REF}/SharedData/Genomes/PhiX/WholeGenomeFasta/genome.fa")
     out = [dict(pos0=r["pos0"], flag=r["flag"], mapq=r["mapq"], cigar=r["cigar"], seq=r["seq"], qual=r["qual"], ref_id=r["ref_id"],

@@ -1,0 +1,83 @@
+"""The library's BAM stager (pb2_bam_*: BGZF inflate, record decode, AlignmentSource.ShouldSkipRead, XD / XV / XW / XR) against the independent
+Python decoder of the test suite (tests/bamio.py) on the reference's own BAM test files (copies under tests/golden/). Host code: runs without a GPU."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from tests import bamio
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _batches(path, **kw):
+    import pisces_b200 as pb
+    st = pb.BamReadStager(path, **kw)
+    out = []
+    for ref_id, b, skipped in st:
+        n = b.n_reads
+        pos0 = np.ctypeslib.as_array(C.cast(b.pos0, C.POINTER(C.c_int32)), (n,)).copy()
+        flag = np.ctypeslib.as_array(C.cast(b.flag, C.POINTER(C.c_uint16)), (n,)).copy()
+        coff = np.ctypeslib.as_array(C.cast(b.cigar_off, C.POINTER(C.c_int64)), (n + 1,)).copy()
+        soff = np.ctypeslib.as_array(C.cast(b.seq_off, C.POINTER(C.c_int64)), (n + 1,)).copy()
+        cigar = np.ctypeslib.as_array(C.cast(b.cigar, C.POINTER(C.c_uint32)), (int(coff[-1]),)).copy()
+        bases = bytes(np.ctypeslib.as_array(C.cast(b.bases, C.POINTER(C.c_uint8)), (int(soff[-1]),)))
+        quals = np.ctypeslib.as_array(C.cast(b.quals, C.POINTER(C.c_uint8)), (int(soff[-1]),)).copy()
+        dirs = np.ctypeslib.as_array(C.cast(b.base_dirs, C.POINTER(C.c_uint8)), (int(soff[-1]),)).copy() if b.base_dirs else None
+        coll = np.ctypeslib.as_array(C.cast(b.collapsed, C.POINTER(C.c_uint8)), (n,)).copy() if b.collapsed else None
+        out.append(dict(ref_id=ref_id, skipped=skipped, pos0=pos0, flag=flag, coff=coff, soff=soff, cigar=cigar, bases=bases, quals=quals, dirs=dirs, coll=coll))
+    refs, flags = st.references, (st.is_stitched, st.is_collapsed)
+    st.close()
+    return out, refs, flags
+
+
+def _kept(recs):   # AlignmentSource.ShouldSkipRead (AlignmentsSource.cs:84-92) with the default BamFilterParameters
+    return [r for r in recs if not (r["flag"] & 0x4) and not (r["flag"] & 0x100) and not (r["flag"] & 0x400) and r["mapq"] >= 1 and r["cigar"] and r["ref_id"] >= 0]
+
+
+def test_phix_bam_matches_python_decoder():
+    text, refs, recs = bamio.read_bam(os.path.join(G, "PhiX_S3.bam"))
+    for max_reads in (65536, 37):     # one batch, and many small ones
+        batches, brefs, _ = _batches(os.path.join(G, "PhiX_S3.bam"), max_reads=max_reads)
+        assert brefs == [(n, l) for n, l in refs]
+        kept = _kept(recs)
+        assert sum(b["skipped"] for b in batches) == len(recs) - len(kept) and sum(len(b["pos0"]) for b in batches) == len(kept)
+        i = 0
+        for b in batches:
+            assert b["dirs"] is None and b["coll"] is None
+            for k in range(len(b["pos0"])):
+                r = kept[i]
+                assert (int(b["pos0"][k]), int(b["flag"][k])) == (r["pos0"], r["flag"])
+                assert list(b["cigar"][b["coff"][k]:b["coff"][k + 1]]) == r["cigar"]
+                assert b["bases"][b["soff"][k]:b["soff"][k + 1]].decode() == r["seq"]
+                assert list(b["quals"][b["soff"][k]:b["soff"][k + 1]]) == r["qual"]
+                i += 1
+
+
+def test_collapsed_stitched_bam_tags():
+    _, _, recs = bamio.read_bam(os.path.join(G, "collapsed.test.stitched.bam"))
+    batches, _, _ = _batches(os.path.join(G, "collapsed.test.stitched.bam"))
+    kept = _kept(recs)
+    assert len(batches) == 1 and len(batches[0]["pos0"]) == len(kept)
+    b = batches[0]
+    assert b["dirs"] is not None and b["coll"] is not None
+    for k, r in enumerate(kept):
+        t = r["tags"]
+        # Read.SequencedBaseDirectionMap (Read.cs:390-421,664-682): XD runs along the expanded CIGAR, kept where the operation spans the read
+        exp, num = [], ""
+        for ch in t["XD"]:
+            if ch.isdigit():
+                num += ch
+            else:
+                exp += [{"F": 0, "R": 1, "S": 2}[ch]] * int(num)
+                num = ""
+        dirs, ci = [], 0
+        for c in r["cigar"]:
+            for _ in range(c >> 4):
+                if (c & 15) in (0, 1, 4, 7, 8):
+                    dirs.append(exp[ci])
+                ci += 1
+        assert list(b["dirs"][b["soff"][k]:b["soff"][k + 1]]) == dirs
+        has = "XV" in t or "XW" in t
+        duplex = bool(t.get("XV")) and bool(t.get("XW"))
+        assert int(b["coll"][k]) == (1 if has else 0) | (2 if duplex else 0) | ({"FR": 1, "RF": 2}.get(t.get("XR"), 0) << 2)

@@ -402,3 +402,39 @@ def test_collapsed_stitched_full_text_golden_through_cuda_path():
     assert len(got) == len(exp)
     for a, b in zip(got, exp):
         assert a == b
+
+
+def test_bam_file_to_vcf_text_through_the_library():
+    """The whole path from the library's own entry points: PhiX_S3.bam -> pb2_bam_* (decode, read filter) -> pb2_push_reads -> pb2_flush, streamed
+    block by block -> pb2_vcf_format == PhiX_S3.noisy.vcf, line by line; and collapsed.test.stitched.bam (XD / XV / XW / XR from the tags)
+    -> test_truth.stitched.genome.vcf."""
+    import ctypes as C
+    import os
+    pb = _pb()
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    genome = open(os.path.join(G, "phix_genome.txt")).read().strip()
+    st = pb.BamReadStager(os.path.join(G, "PhiX_S3.bam"), max_reads=50)
+    sm = pb.GpuStateManager(pb.make_config(min_coverage=2, min_base_call_quality=10, min_variant_qscore=1, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1,
+                                           max_size_mnv=10, max_gap_mnv=5, no_call_filter=1.0, expect_stitched=int(st.is_stitched)), st.references[0][0], genome)
+    caller = pb.GpuAlleleCaller()
+    got = []
+    for _, batch, _ in st:
+        last_pos0 = C.cast(batch.pos0, C.POINTER(C.c_int32))[batch.n_reads - 1]
+        sm.AddReadBatch(batch)
+        got += sm.FormatVcf(caller.Call(sm, upToPosition=int(last_pos0), raw=True))
+    got += sm.FormatVcf(caller.Call(sm, raw=True))
+    sm.close()
+    st.close()
+    assert got == [l.rstrip("\n") for l in open(os.path.join(G, "phix_s3_noisy.records.vcf"))]
+
+    seq = "N" * (9770498 - 1) + ("GAAGTAACAACGCAGGATGCCCCCTGGGGTGGACTGCCCCATGGAATTCTGGACCAAGGAGGAGAATCAGAGCGTTGTGGTTGACTTCCTGCTGCCCACAGGGGTCTACCTGAACTTCCCTGTGTCCCGCAATGCCAACCTC"
+                                 "AGCACCATCAAGCAGGTATGGCCTCCATC")
+    st = pb.BamReadStager(os.path.join(G, "collapsed.test.stitched.bam"))
+    sm = pb.GpuStateManager(pb.make_config(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, expect_stitched=1, expect_collapsed=1, skip_validation=1), "chr1", seq)
+    for _, batch, _ in st:
+        sm.AddReadBatch(batch)
+    recs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    got = sm.FormatVcf(recs, sm.AlleleExt(), debug_mode=True, output_bias_files=True, report_rc_counts=True, report_ts_counts=True)
+    sm.close()
+    st.close()
+    assert got == [l.rstrip("\n") for l in open(os.path.join(G, "collapsed_stitched.records.vcf"))]
