@@ -193,7 +193,8 @@ static void release_resident_graph(pb2_handle* h) {
 }
 
 static void free_segment(pb2_handle* h, Segment& s) {
-    void* ptrs[] = {s.code, s.anch, s.ref_records, s.var_records, s.pending, s.depth, s.pad, s.tile_base, s.ref_base, s.positions, s.ref_valid, s.exc_entries, s.counters};
+    void* ptrs[] = {s.code, s.anch, s.ref_records, s.var_records, s.pending, s.depth, s.pad, s.tile_base, s.ref_base, s.positions, s.ref_valid, s.exc_entries, s.counters,
+                    s.nib, s.nib_tile_base, s.nib_store, s.nib_depth};
     for (void* p : ptrs) pool_free(h, p);
     s = Segment();
 }
@@ -426,6 +427,49 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     }
 
     tr.mark("enqueue_chunks");
+    // ---- PNIB16: the direction-split, nibble-packed form the hot kernel reads (1.5 B / entry), derived from the staged planes on the device. Not for
+    // collapsed-read tracking or quality sums (they need the third byte / per-entry work) and not when a Stitched-direction entry or a very deep locus
+    // shows up: those segments stay with the PTILE32 kernel.
+    if (!h->cfg.expect_collapsed && !h->cfg.want_sum_base_quality && h->cfg.noise_model != 1 && h->cfg.reserved[1] != 9) {
+        s.n_nib_tiles = (int32_t)((p->n_loci + kNibLoci - 1) / kNibLoci);
+        int64_t* nib_tile_bytes = nullptr;
+        int32_t* d_flags = nullptr;
+        CU(h, pool_alloc_t(h, &s.nib_store, 2 * (size_t)p->n_loci));
+        CU(h, pool_alloc_t(h, &s.nib_depth, 2 * (size_t)p->n_loci));
+        CU(h, pool_alloc_t(h, &s.nib_tile_base, (size_t)s.n_nib_tiles + 1));
+        CU(h, pool_alloc_t(h, &nib_tile_bytes, (size_t)s.n_nib_tiles + 1));
+        CU(h, pool_alloc_t(h, &d_flags, 2));
+        CU(h, cudaMemsetAsync(nib_tile_bytes, 0, sizeof(int64_t) * ((size_t)s.n_nib_tiles + 1), st));
+        CU(h, cudaMemsetAsync(d_flags, 0, sizeof(int32_t) * 2, st));
+        TilePileup view;
+        memset(&view, 0, sizeof(view));
+        view.cq = s.code; view.anch = s.anch; view.tile_base = s.tile_base; view.depth = s.depth; view.pad = s.pad; view.ref_base = s.ref_base;
+        view.n_loci = s.n_loci; view.n_tiles = s.n_tiles; view.n_nib_tiles = s.n_nib_tiles;
+        CU(h, launch_nib_count(view, s.nib_store, s.nib_depth, nib_tile_bytes, d_flags, st));
+        size_t nib_temp_bytes = 0;
+        CU(h, exclusive_scan_i64(nib_tile_bytes, s.nib_tile_base, s.n_nib_tiles + 1, nullptr, 0, &nib_temp_bytes, st));
+        void* nib_temp = nullptr;
+        CU(h, pool_alloc(h, &nib_temp, std::max<size_t>(nib_temp_bytes, 16)));
+        CU(h, exclusive_scan_i64(nib_tile_bytes, s.nib_tile_base, s.n_nib_tiles + 1, nib_temp, nib_temp_bytes, nullptr, st));
+        int32_t flags[2] = {0, 0};
+        CU(h, cudaMemcpyAsync(&s.nib_bytes, s.nib_tile_base + s.n_nib_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        h->total_launches += 3;
+        if (flags[0] == 0 && flags[1] <= kChunk * kNibMaxChunks) {
+            s.nib_max_store = flags[1];
+            CU(h, pool_alloc(h, (void**)&s.nib, (size_t)s.nib_bytes + 4096));
+            CU(h, launch_nib_scatter(view, s.nib_store, s.nib_tile_base, s.nib, st));
+            h->total_launches += 1;
+        } else {
+            pool_free(h, s.nib_store); pool_free(h, s.nib_depth); pool_free(h, s.nib_tile_base);
+            s.nib_store = s.nib_depth = nullptr; s.nib_tile_base = nullptr; s.n_nib_tiles = 0;
+        }
+        pool_free(h, nib_tile_bytes);
+        pool_free(h, d_flags);
+        pool_free(h, nib_temp);
+    }
+    tr.mark("pnib16");
     // outputs
     if (h->cfg.output_gvcf) {
         s.alloc_ref = sizeof(pb2_call_record) * (size_t)p->n_loci;
@@ -457,8 +501,10 @@ static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32
                            bool capturing = false) {
     cudaStream_t st = h->stream;
     TilePileup in;
+    memset(&in, 0, sizeof(in));
     in.cq = s.code; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
     in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles; in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);
+    in.nib = s.nib; in.nib_tile_base = s.nib_tile_base; in.nib_store = s.nib_store; in.nib_depth = s.nib_depth; in.n_nib_tiles = s.n_nib_tiles; in.nib_max_store = s.nib_max_store;
     HotInputsExtra ex;
     ex.gapped_ref = d_gapped; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len; ex.q_to_p_table = h->d_q_to_p; ex.q_table_max = h->q_table_max;
     HotOutputs out;

@@ -116,6 +116,7 @@ struct BatchCtx {
     }
     static TilePileup view(const Segment& s) {
         TilePileup in;
+        memset(&in, 0, sizeof(in));
         in.cq = s.code; in.anch = s.anch; in.tile_base = s.tile_base; in.depth = s.depth; in.pad = s.pad; in.ref_base = s.ref_base;
         in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles;
         in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);

@@ -95,6 +95,12 @@ struct Segment {   // one staged pileup (pb2_push_pileup*)
     int64_t* tile_base = nullptr;
     uint8_t *code = nullptr, *qual = nullptr, *anch = nullptr, *ref_base = nullptr;
     int32_t* positions = nullptr;
+    // PNIB16 form of the same pileup (pileup_nib_score_kernel); nib == nullptr: not staged (stitched directions, collapsed reads, very deep loci)
+    uint8_t* nib = nullptr;
+    int64_t* nib_tile_base = nullptr;
+    int32_t *nib_store = nullptr, *nib_depth = nullptr;
+    int32_t n_nib_tiles = 0, nib_max_store = 0;
+    int64_t nib_bytes = 0;
     pb2_call_record* ref_records = nullptr;
     uint8_t* ref_valid = nullptr;
     pb2_call_record* var_records = nullptr;

@@ -943,6 +943,310 @@ size_t hot_kernel_smem_bytes(bool narrow, bool collapsed) {
     return (size_t)rows * kHotThreads * sizeof(uint16_t) + 256 * sizeof(double);
 }
 
+// ================================================================================================ PNIB16: direction-split, nibble-packed pileup
+// The vertical-counter kernel above spends its time on the integer pipe: a shift per entry to make the one-hot row word and 15 compressors per
+// 16 entries, because allele AND direction select the row. Here the direction is a property of the lane (sub-locus = (locus, direction)) and the
+// allele a 4-bit code, so ONE byte-permute turns four entries into four one-hot bytes (PRMT as a table lookup: selector nibble = allele code,
+// table = {1, 2, 4, 8, 0, 16, 0, 0}), the quality rule is an AND with the byte mask of `q >= minBQ`, and four words per chunk go through the
+// compressors instead of sixteen. Counters are vertical over (byte lane, allele): 4 x 8 = 32 of them per plane. 1.5 bytes per entry instead of 2.
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {   // bit i -> bit 2i
+    x &= 0xffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+__device__ __forceinline__ int nib_step_bytes(int active) { return (24 * active + 15) & ~15; }
+constexpr uint32_t kNibPadCode = 6;   // table entry 0: contributes nothing
+
+// one warp per PTILE32 tile, lane = locus: calls f(code chunk, quality chunk) for the lane's own chunks, in order (the addressing of tile_scatter_kernel)
+template <class F>
+__device__ __forceinline__ void walk_ptile(const TilePileup& in, int64_t tile, int lane, F&& f) {
+    const int64_t locus = tile * kTileLoci + lane;
+    const int depth = locus < in.n_loci ? in.depth[locus] : 0;
+    const int nchunks = (depth + kChunk - 1) / kChunk;
+    const int max_chunks = __reduce_max_sync(0xffffffffu, nchunks);
+    int64_t base = in.tile_base[tile];
+    for (int c = 0; c < max_chunks; c++) {
+        const bool active = c < nchunks;
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const int64_t o = 2 * base + (int64_t)__popc(m & ((1u << lane) - 1)) * kChunk;
+            const uint4 wc = *reinterpret_cast<const uint4*>(in.cq + o);
+            const uint4 wq = *reinterpret_cast<const uint4*>(in.cq + o + (int64_t)__popc(m) * kChunk);
+            f(wc, wq);
+        }
+        base += (int64_t)__popc(m) * kChunk;
+    }
+}
+
+__global__ void nib_count_kernel(const __grid_constant__ TilePileup in, int32_t* __restrict__ nib_store, int32_t* __restrict__ nib_depth,
+                                 int64_t* __restrict__ nib_tile_bytes, int32_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (tile >= in.n_tiles) return;
+    int st[2] = {0, 0}, dp[2] = {0, 0};
+    bool stitched = false;
+    walk_ptile(in, tile, lane, [&](const uint4& wc, const uint4& wq) {
+        const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {   // four entries at a time; every mask below lives in bit 3 of its byte
+            const uint32_t c4 = cw[k], y = ~qw[k];
+            const uint32_t n7 = ((c4 & 0x07070707u) + 0x01010101u) & 0x08080808u;                                  // staged allele code 7 (N or PAD)
+            const uint32_t qff = (~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u) >> 4;                   // quality byte 0xff
+            const uint32_t pad = n7 & qff;
+            const uint32_t dir_r = c4 & 0x08080808u, dir_s = (c4 & 0x10101010u) >> 1;
+            const uint32_t valid = 0x08080808u & ~pad & ~dir_s;
+            stitched |= (dir_s & ~pad) != 0;
+            dp[1] += __popc(valid & dir_r); dp[0] += __popc(valid & ~dir_r);
+            const uint32_t stored = valid & ~n7;
+            st[1] += __popc(stored & dir_r); st[0] += __popc(stored & ~dir_r);
+        }
+    });
+    const int64_t locus = tile * kTileLoci + lane;
+    if (locus < in.n_loci) {
+        nib_store[2 * locus] = st[0]; nib_store[2 * locus + 1] = st[1];
+        nib_depth[2 * locus] = dp[0]; nib_depth[2 * locus + 1] = dp[1];
+    }
+    const int nc0 = (st[0] + kChunk - 1) / kChunk, nc1 = (st[1] + kChunk - 1) / kChunk;
+    const int maxc = __reduce_max_sync(0xffffffffu, max(nc0, nc1));
+    int64_t bytes_lo = 0, bytes_hi = 0;
+    for (int c = 0; c < maxc; c++) {
+        const unsigned b0 = __ballot_sync(0xffffffffu, nc0 > c), b1 = __ballot_sync(0xffffffffu, nc1 > c);
+        bytes_lo += nib_step_bytes(__popc(b0 & 0xffffu) + __popc(b1 & 0xffffu));
+        bytes_hi += nib_step_bytes(__popc(b0 >> 16) + __popc(b1 >> 16));
+    }
+    if (lane == 0) {
+        nib_tile_bytes[2 * tile] = bytes_lo;
+        if (2 * tile + 1 < in.n_nib_tiles) nib_tile_bytes[2 * tile + 1] = bytes_hi;
+    }
+    const int mx = __reduce_max_sync(0xffffffffu, max(st[0], st[1]));
+    if (lane == 0) atomicMax(flags + 1, mx);
+    if (__any_sync(0xffffffffu, stitched) && lane == 0) atomicOr(flags, 1);
+}
+
+constexpr int kNibScatterWarps = 4;
+__global__ void __launch_bounds__(32 * kNibScatterWarps) nib_scatter_kernel(const __grid_constant__ TilePileup in, const int32_t* __restrict__ nib_store,
+                                                                           const int64_t* __restrict__ nib_tile_base, uint8_t* __restrict__ nib) {
+    __shared__ int32_t s_off[kNibScatterWarps][2][kNibMaxChunks];
+    __shared__ uint32_t s_mask[kNibScatterWarps][2][kNibMaxChunks];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = (int64_t)blockIdx.x * kNibScatterWarps + warp;
+    if (tile >= in.n_tiles) return;
+    const int64_t locus = tile * kTileLoci + lane;
+    int nst[2] = {0, 0};
+    if (locus < in.n_loci) { nst[0] = nib_store[2 * locus]; nst[1] = nib_store[2 * locus + 1]; }
+    const int nc0 = (nst[0] + kChunk - 1) / kChunk, nc1 = (nst[1] + kChunk - 1) / kChunk;
+    const int maxc = min(__reduce_max_sync(0xffffffffu, max(nc0, nc1)), kNibMaxChunks);
+    {   // per step: which of the sub-tile's 32 sub-loci are active (bit 2 * (lane & 15) + direction) and where the step starts
+        int off_lo = 0, off_hi = 0;
+        for (int c = 0; c < maxc; c++) {
+            const unsigned b0 = __ballot_sync(0xffffffffu, nc0 > c), b1 = __ballot_sync(0xffffffffu, nc1 > c);
+            const uint32_t m_lo = spread16(b0) | (spread16(b1) << 1), m_hi = spread16(b0 >> 16) | (spread16(b1 >> 16) << 1);
+            if (lane == 0) { s_off[warp][0][c] = off_lo; s_off[warp][1][c] = off_hi; s_mask[warp][0][c] = m_lo; s_mask[warp][1][c] = m_hi; }
+            off_lo += nib_step_bytes(__popc(m_lo));
+            off_hi += nib_step_bytes(__popc(m_hi));
+        }
+    }
+    __syncwarp();
+    const int sub = lane >> 4;
+    const int64_t tb = (2 * tile + sub < in.n_nib_tiles) ? nib_tile_base[2 * tile + sub] : 0;
+    // per (lane, direction) a 32-entry ring of pending entries in shared memory, one byte per allele code and one per quality, laid out
+    // [direction][word of 4 entries][lane] so that every access is bank-conflict free. Appending is two byte stores at a computed address (entries that
+    // are not stored go to a per-lane dump word: no branches in the per-entry code); 16 entries leave as one chunk.
+    __shared__ uint32_t s_al[kNibScatterWarps][2][8][32], s_q[kNibScatterWarps][2][8][32], s_dump[kNibScatterWarps][32];
+    uint8_t* const al_bytes = reinterpret_cast<uint8_t*>(&s_al[warp][0][0][0]);
+    uint8_t* const q_bytes = reinterpret_cast<uint8_t*>(&s_q[warp][0][0][0]);
+    uint8_t* const dump = reinterpret_cast<uint8_t*>(&s_dump[warp][lane]);
+    int fill[2] = {0, 0}, head[2] = {0, 0}, cidx[2] = {0, 0};
+    auto flush = [&](int d, int n) {   // the oldest min(n, 16) pending entries of direction d become chunk cidx[d] of the sub-locus
+        const int c = cidx[d];
+        uint32_t a4[4], q4[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) { a4[w] = s_al[warp][d][(head[d] >> 2) + w][lane]; q4[w] = s_q[warp][d][(head[d] >> 2) + w][lane]; }
+        if (n < kChunk) {   // the last, partial chunk: PAD the tail
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const int keep = min(max(n - 4 * w, 0), 4);
+                const uint32_t km = keep >= 4 ? 0xffffffffu : ((1u << (8 * keep)) - 1u);
+                a4[w] = (a4[w] & km) | (0x06060606u & ~km);
+                q4[w] = q4[w] | ~km;
+            }
+        }
+        uint32_t nib16[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) nib16[w] = __byte_perm(a4[w] | (a4[w] >> 4), 0, 0x4420) & 0xffffu;   // bytes b0|b1<<4, b2|b3<<4
+        if (c < kNibMaxChunks) {
+            const uint32_t m = s_mask[warp][sub][c];
+            const int j = 2 * (lane & 15) + d;
+            const int active = __popc(m), rank = __popc(m & ((1u << j) - 1));
+            uint8_t* dst = nib + tb + s_off[warp][sub][c];
+            *reinterpret_cast<uint4*>(dst + 16 * rank) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+            *reinterpret_cast<uint2*>(dst + 16 * active + 8 * rank) = make_uint2(nib16[0] | (nib16[1] << 16), nib16[2] | (nib16[3] << 16));
+        }
+        head[d] = (head[d] + kChunk) & 31;
+        fill[d] -= min(n, kChunk);
+        cidx[d] = c + 1;
+    };
+    walk_ptile(in, tile, lane, [&](const uint4& wc, const uint4& wq) {
+        const uint32_t cw[4] = {wc.x, wc.y, wc.z, wc.w}, qw[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+        for (int k = 0; k < kChunk; k++) {
+            const uint32_t c = (cw[k >> 2] >> ((k & 3) * 8)) & 0xffu, q = (qw[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+            const uint32_t al = c & 7u, dir = (c >> 3) & 1u;
+            const bool take = (al != kStagedN) & (((c >> 4) & 1u) == 0);   // PADs and N bases are not stored (N = counted - stored alleles)
+            const int f = (dir ? head[1] + fill[1] : head[0] + fill[0]) & 31;
+            const int off = (((int)dir * 8 + (f >> 2)) * 32 + lane) * 4 + (f & 3);
+            *(take ? al_bytes + off : dump) = (uint8_t)al;
+            *(take ? q_bytes + off : dump + 1) = (uint8_t)q;
+            fill[0] += (take & (dir == 0)) ? 1 : 0;
+            fill[1] += (take & (dir == 1)) ? 1 : 0;
+        }
+        if (fill[0] >= kChunk) flush(0, kChunk);
+        if (fill[1] >= kChunk) flush(1, kChunk);
+    });
+    if (fill[0] > 0) flush(0, fill[0]);
+    if (fill[1] > 0) flush(1, fill[1]);
+}
+
+// counter of (byte lane b, allele bit a) summed over the four byte lanes
+template <int NP>
+__device__ __forceinline__ int nib_count_allele(const uint32_t (&P)[NP], int a) {
+    return vcount_row<NP>(P, a) + vcount_row<NP>(P, 8 + a) + vcount_row<NP>(P, 16 + a) + vcount_row<NP>(P, 24 + a);
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256, 4)
+pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_constant__ HotInputsExtra ex, const __grid_constant__ HotOutputs out,
+                        const __grid_constant__ DeviceConfig cfg, int* __restrict__ tile_counter) {
+    __shared__ int s_tile[8];
+    __shared__ __align__(16) PendingLocus s_pend[kCtaPending];
+    __shared__ int s_pend_n;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_pend_n = 0;
+    __syncthreads();
+    const uint32_t neg_minbq4 = 0u - (uint32_t)cfg.min_bq * 0x01010101u;
+    const uint32_t one = cfg.one;
+    const uint32_t t_lo = 0x08040201u, t_hi = 0x00001000u;   // allele code -> one-hot byte: A 1, G 2, C 4, T 8, (4) 0, Deletion 16, PAD 0, (7) 0
+    const unsigned lt = (1u << lane) - 1;
+
+    while (true) {
+        if (lane == 0) s_tile[warp] = atomicAdd(tile_counter, 1);
+        __syncwarp();
+        const int tile = s_tile[warp];
+        __syncwarp();
+        if (tile >= in.n_nib_tiles) break;
+        const int64_t locus = (int64_t)tile * kNibLoci + (lane >> 1);
+        const bool have_locus = locus < in.n_loci;
+        const int64_t sub = 2 * locus + (lane & 1);
+        const int store = have_locus ? in.nib_store[sub] : 0;
+        const int nchunks = (store + kChunk - 1) / kChunk;
+        const int max_chunks = __reduce_max_sync(0xffffffffu, nchunks);
+        const uint8_t* p = in.nib + in.nib_tile_base[tile];
+        uint32_t P[NP];
+#pragma unroll
+        for (int i = 0; i < NP; i++) P[i] = 0;
+
+        // four one-hot byte words of a chunk (quality rule applied) into the planes below weight 4; returns the weight-4 carry
+        auto add_chunk = [&](const uint2& wc, const uint4& wq) -> uint32_t {
+            const uint32_t sel[4] = {wc.x, wc.x >> 16, wc.y, wc.y >> 16};
+            const uint32_t qv[4] = {wq.x, wq.y, wq.z, wq.w};
+            uint32_t x[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t oh, d, ok;
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(oh) : "r"(t_lo), "r"(t_hi), "r"(sel[k]));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(qv[k]), "r"(one), "r"(neg_minbq4));
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(ok) : "r"(d), "r"(0u), "r"(0xba98u));   // 0xFF where q >= minBQ (RegionStateManager.cs:180-181)
+                x[k] = oh & ok;
+            }
+            uint32_t s0, k0, k1, m0;
+            csa(s0, k0, x[0], x[1], x[2]);
+            csa(P[0], k1, P[0], s0, x[3]);
+            csa(P[1], m0, k0, k1, P[1]);
+            return m0;
+        };
+        auto ripple = [&](uint32_t carry, int from) {
+#pragma unroll
+            for (int i = 2; i < NP; i++) if (i >= from) { const uint32_t t = P[i] & carry; P[i] ^= carry; carry = t; }
+        };
+
+        // two chunks are counted per iteration while the next two are already on their way into registers (the kernel is bound by the bytes it keeps in
+        // flight, not by the integer pipe: 4 chunks x 24 B per lane outstanding)
+        auto fetch = [&](int c, uint2& dc, uint4& dq) {
+            const bool active = c < nchunks;
+            const unsigned m = __ballot_sync(0xffffffffu, active);
+            const int n_act = __popc(m);
+            dc = make_uint2(kNibPadCode * 0x11111111u, kNibPadCode * 0x11111111u);
+            dq = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (active) {
+                const int rank = __popc(m & lt);
+                dq = ldg_stream(p + 16 * rank);
+                const uint8_t* pcode = p + 16 * n_act + 8 * rank;
+                asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v2.u32 {%0,%1}, [%2];" : "=r"(dc.x), "=r"(dc.y) : "l"(pcode));
+            }
+            p += nib_step_bytes(n_act);
+        };
+        uint2 c0, c1, c2, c3;
+        uint4 q0, q1, q2, q3;
+        fetch(0, c0, q0);   // chunks past the last one come back as PAD chunks without touching memory (max_chunks is uniform across the warp)
+        fetch(1, c1, q1);
+        for (int c = 0; c < max_chunks; c += 2) {
+            fetch(c + 2, c2, q2);
+            fetch(c + 3, c3, q3);
+            const uint32_t ca = add_chunk(c0, q0);
+            const uint32_t cb = add_chunk(c1, q1);
+            uint32_t c8;
+            csa(P[2], c8, ca, cb, P[2]);
+            ripple(c8, 3);
+            c0 = c2; q0 = q2; c1 = c3; q1 = q3;
+        }
+
+        // ---- counts of this (locus, direction); the partner lane holds the other direction
+        int mine[kNumAlleles];
+        mine[AT_A] = nib_count_allele<NP>(P, 0);
+        mine[AT_G] = nib_count_allele<NP>(P, 1);
+        mine[AT_C] = nib_count_allele<NP>(P, 2);
+        mine[AT_T] = nib_count_allele<NP>(P, 3);
+        mine[AT_DEL] = nib_count_allele<NP>(P, 4);
+        const int counted = have_locus ? in.nib_depth[sub] : 0;
+        mine[AT_N] = counted - (mine[AT_A] + mine[AT_G] + mine[AT_C] + mine[AT_T] + mine[AT_DEL]);   // N bases and bases below the quality bar
+        int cnt[kNumAlleles][kNumDirs];
+        int any = 0;
+#pragma unroll
+        for (int a = 0; a < kNumAlleles; a++) {
+            const int other = __shfl_xor_sync(0xffffffffu, mine[a], 1);
+            cnt[a][DIR_F] = mine[a]; cnt[a][DIR_R] = other; cnt[a][DIR_S] = 0;
+            any += mine[a] + other;
+        }
+        if (!have_locus || (lane & 1)) continue;
+        const int ref_allele = allele_of_base(in.ref_base[locus]);
+        finish_locus(cnt, 0.0, any, locus, ref_allele, in, ex, out, cfg, s_pend, &s_pend_n);
+    }
+
+    __syncthreads();
+    {
+        const int n = min(s_pend_n, kCtaPending);
+        const int item = threadIdx.x >> 2;
+        score_queued_locus(item < n ? &s_pend[item] : nullptr, threadIdx.x & 3, in, ex, out, cfg);
+    }
+}
+
+cudaError_t launch_nib_count(const TilePileup& in, int32_t* nib_store, int32_t* nib_depth, int64_t* nib_tile_bytes, int32_t* flags, cudaStream_t stream) {
+    if (in.n_tiles == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)(((int64_t)in.n_tiles * 32 + 255) / 256);
+    nib_count_kernel<<<blocks, 256, 0, stream>>>(in, nib_store, nib_depth, nib_tile_bytes, flags);
+    return cudaGetLastError();
+}
+cudaError_t launch_nib_scatter(const TilePileup& in, const int32_t* nib_store, const int64_t* nib_tile_base, uint8_t* nib, cudaStream_t stream) {
+    if (in.n_tiles == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((in.n_tiles + kNibScatterWarps - 1) / kNibScatterWarps);
+    nib_scatter_kernel<<<blocks, 32 * kNibScatterWarps, 0, stream>>>(in, nib_store, nib_tile_base, nib);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
                               int max_depth, cudaStream_t stream) {
     if (in.n_tiles == 0) return cudaSuccess;
@@ -950,8 +1254,14 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
     const bool coll = cfg.expect_collapsed != 0;
     cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
-    if (out.counts_out == nullptr && max_depth + 2 * kChunk < (1 << 16)) {
-        // the hot path: vertical counters in registers; planes needed = bits of the largest row count (entries + PADs of a locus)
+    if (out.counts_out == nullptr && in.nib != nullptr && !want_q && !coll && cfg.tune_prefetch != 9) {
+        // the hot path: PNIB16 (direction-split, nibble-packed); planes needed = bits of the largest (byte lane, allele) count = stored / 4
+        const int need = in.nib_max_store / 4 + 2;
+        const int grid = max(1, min(num_sms * 4, (in.n_nib_tiles + 7) / 8));
+        if (need < (1 << 8)) pileup_nib_score_kernel<8><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);
+        else pileup_nib_score_kernel<12><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);
+    } else if (out.counts_out == nullptr && max_depth + 2 * kChunk < (1 << 16)) {
+        // vertical counters over the PTILE32 planes; planes needed = bits of the largest row count (entries + PADs of a locus)
         const int need = max_depth + 2 * kChunk;
         const int ctas = cfg.tune_ctas_per_sm == 3 ? 3 : 4;
         const int grid = max(1, min(num_sms * ctas, (in.n_tiles + 7) / 8));

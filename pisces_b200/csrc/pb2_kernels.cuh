@@ -59,7 +59,18 @@ struct TilePileup {
     int64_t n_loci;
     int32_t n_tiles;
     int64_t plane_bytes;        // size of the anchor plane (multiple of 16, >= 16); the code + quality plane is twice that
+    // "PNIB16" (DESIGN.md 3): the same pileup split by direction and nibble-packed, read by pileup_nib_score_kernel when present (nib != nullptr).
+    // Sub-locus (locus, direction in {F, R}) = one lane; sub-tile = 16 loci = 32 sub-loci; per step the 16-byte quality chunks of the active sub-loci,
+    // then their 8-byte code chunks (16 allele nibbles), the step padded to 16 bytes.
+    const uint8_t* nib;
+    const int64_t* nib_tile_base;   // [n_nib_tiles] byte offset of a sub-tile
+    const int32_t* nib_store;       // [2 * n_loci] entries stored for (locus, direction): A/C/G/T of any quality and countable deletions
+    const int32_t* nib_depth;       // [2 * n_loci] entries counted for (locus, direction): the stored ones + N bases
+    int32_t n_nib_tiles;
+    int32_t nib_max_store;
 };
+constexpr int kNibLoci = 16;        // loci per PNIB16 sub-tile
+constexpr int kNibMaxChunks = 256;  // chunks per sub-locus the PNIB16 staging handles (deeper loci stay with the PTILE32 kernel)
 
 // A locus whose SNV candidates passed the cheap callability bars: scored by score_pending_kernel. 96 bytes.
 struct PendingLocus {
@@ -112,6 +123,9 @@ cudaError_t launch_tile_scatter(const int64_t* csr_offsets, const uint8_t* code,
                                 int32_t n_tiles, int64_t entry_base, const int64_t* tile_base, const uint8_t* ref_base, int min_bq, uint8_t* tcq, uint8_t* tanch, int32_t* pad,
                                 uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity,
                                 cudaStream_t stream);
+// PTILE32 -> PNIB16 staging: count (per sub-locus sizes, per sub-tile bytes; flags[0] = a Stitched-direction entry exists, flags[1] = max stored), then scatter
+cudaError_t launch_nib_count(const TilePileup& in, int32_t* nib_store, int32_t* nib_depth, int64_t* nib_tile_bytes, int32_t* flags, cudaStream_t stream);
+cudaError_t launch_nib_scatter(const TilePileup& in, const int32_t* nib_store, const int64_t* nib_tile_base, uint8_t* nib, cudaStream_t stream);
 cudaError_t exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* temp, size_t temp_bytes, size_t* temp_needed, cudaStream_t stream);
 
 }  // namespace pb2
