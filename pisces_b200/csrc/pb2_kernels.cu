@@ -1113,7 +1113,10 @@ __global__ void __launch_bounds__(32 * kNibScatterWarps) nib_scatter_kernel(cons
 // counter of (byte lane b, allele bit a) summed over the four byte lanes
 template <int NP>
 __device__ __forceinline__ int nib_count_allele(const uint32_t (&P)[NP], int a) {
-    return vcount_row<NP>(P, a) + vcount_row<NP>(P, 8 + a) + vcount_row<NP>(P, 16 + a) + vcount_row<NP>(P, 24 + a);
+    int v = 0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) v += __popc(P[i] & (0x01010101u << a)) << i;   // plane i: how many of the four byte lanes have bit i of their counter set
+    return v;
 }
 
 template <int NP>
@@ -1191,17 +1194,51 @@ pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_cons
         };
         uint2 c0, c1, c2, c3;
         uint4 q0, q1, q2, q3;
-        fetch(0, c0, q0);   // chunks past the last one come back as PAD chunks without touching memory (max_chunks is uniform across the warp)
-        fetch(1, c1, q1);
-        for (int c = 0; c < max_chunks; c += 2) {
-            fetch(c + 2, c2, q2);
-            fetch(c + 3, c3, q3);
-            const uint32_t ca = add_chunk(c0, q0);
-            const uint32_t cb = add_chunk(c1, q1);
-            uint32_t c8;
-            csa(P[2], c8, ca, cb, P[2]);
-            ripple(c8, 3);
-            c0 = c2; q0 = q2; c1 = c3; q1 = q3;
+        int c = 0;
+        // ---- phase 1: the steps every sub-locus of the sub-tile takes part in: slot == lane, 768 contiguous bytes per step (512 of quality chunks, 256
+        // of code chunks), no ballots, immediate offsets; four chunks per iteration, the next pair always in flight (ping-pong, no register moves)
+        const int uniform = __reduce_min_sync(0xffffffffu, nchunks) & ~3;
+        if (uniform > 0) {
+            constexpr int kFull = 768;
+            const uint8_t* pq = p + 16 * lane;
+            const uint8_t* pk = p + 512 + 8 * lane;
+            auto ld = [&](int j, uint2& dc, uint4& dq) {
+                dq = ldg_stream(pq + j * kFull);
+                asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v2.u32 {%0,%1}, [%2];" : "=r"(dc.x), "=r"(dc.y) : "l"(pk + j * kFull));
+            };
+            ld(0, c0, q0);
+            ld(1, c1, q1);
+            for (; c < uniform; c += 4) {
+                ld(2, c2, q2);
+                ld(3, c3, q3);
+                uint32_t ca = add_chunk(c0, q0);
+                uint32_t cb = add_chunk(c1, q1);
+                uint32_t c8a, c8b, c16;
+                csa(P[2], c8a, ca, cb, P[2]);
+                if (c + 4 < uniform) { ld(4, c0, q0); ld(5, c1, q1); }
+                ca = add_chunk(c2, q2);
+                cb = add_chunk(c3, q3);
+                csa(P[2], c8b, ca, cb, P[2]);
+                csa(P[3], c16, c8a, c8b, P[3]);
+                ripple(c16, 4);
+                pq += 4 * kFull; pk += 4 * kFull;
+            }
+            p += (int64_t)uniform * kFull;
+        }
+        // ---- phase 2: the ragged end (sub-loci that ran out come back as PAD chunks without touching memory; max_chunks is uniform across the warp)
+        if (c < max_chunks) {
+            fetch(c, c0, q0);
+            fetch(c + 1, c1, q1);
+            for (; c < max_chunks; c += 2) {
+                fetch(c + 2, c2, q2);
+                fetch(c + 3, c3, q3);
+                const uint32_t ca = add_chunk(c0, q0);
+                const uint32_t cb = add_chunk(c1, q1);
+                uint32_t c8;
+                csa(P[2], c8, ca, cb, P[2]);
+                ripple(c8, 3);
+                c0 = c2; q0 = q2; c1 = c3; q1 = q3;
+            }
         }
 
         // ---- counts of this (locus, direction); the partner lane holds the other direction
