@@ -248,19 +248,26 @@ def main_ours(a):
         peak_src = "measured"
     except Exception:
         pass
+    # which hot kernel ran: the PNIB16 one (direction-split, nibble-packed pileup: 1.5 staged bytes per entry) unless collapsed-read tracking / quality
+    # sums are on or it is switched off for comparison (--tune-prefetch 9 -> the PTILE32 vertical-counter kernel, 2 staged bytes per entry)
+    nib = not cfg.expect_collapsed and not cfg.want_sum_base_quality and cfg.noise_model != 1 and a.tune_prefetch != 9
+    kernel_name = "pileup_nib_score_kernel" if nib else "pileup_vcount_score_kernel"
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
+    try:   # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture of this command (default workload only)
+        if not a.gvcf and a.loci == 1_000_000 and a.depth == 500:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[kernel_name]["dram_bytes_per_launch"]
     except Exception:
         pass
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": 1e3 * dt / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "loci_per_gpu": a.loci, "entries_per_gpu": n_entries, "records_per_step": n_records + n_ref_records,
-                       "l2": "inputs (%.2f GB per GPU) larger than L2, no flush needed" % (3 * n_entries / 1e9), "parallelism": f"interval-sharded x{world}"},
+                       "l2": "staged input of the hot kernel (%.2f GB per GPU) larger than L2, no flush needed" % ((1.5 if nib else 2) * n_entries / 1e9), "parallelism": f"interval-sharded x{world}"},
             "gpu_launches": st["total_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "pileup_vcount_score_kernel", "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_entry": 3 if third_byte else 2,
+                         "kernel": kernel_name, "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_entry": 3 if third_byte else 2,
+                         "staged_bytes_per_entry": 1.5 if nib else (3 if third_byte else 2),
+                         "dram_frac": (traffic / (hot_ms * 1e-3) / 1e9 / peak) if traffic else None,
                          "kernel_ms": hot_ms},
             "clocks": sampler.summary()}
 

@@ -1119,7 +1119,7 @@ __device__ __forceinline__ int nib_count_allele(const uint32_t (&P)[NP], int a) 
     return v;
 }
 
-template <int NP>
+template <int NP, bool kPair>
 __global__ void __launch_bounds__(256, 4)
 pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_constant__ HotInputsExtra ex, const __grid_constant__ HotOutputs out,
                         const __grid_constant__ DeviceConfig cfg, int* __restrict__ tile_counter) {
@@ -1136,10 +1136,19 @@ pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_cons
     const unsigned lt = (1u << lane) - 1;
 
     while (true) {
+        // a warp takes two sub-tiles (32 loci) at a time: each is counted with one (locus, direction) per lane, then the 2 x 16 loci are scored with one
+        // locus per lane, so that the per-locus work (candidate screening; in gVCF mode the reference allele's q-score / genotype chain) runs on full warps
         if (lane == 0) s_tile[warp] = atomicAdd(tile_counter, 1);
         __syncwarp();
-        const int tile = s_tile[warp];
+        const int tile_pair = s_tile[warp];
         __syncwarp();
+        if ((kPair ? 2 : 1) * tile_pair >= in.n_nib_tiles) break;
+        uint32_t keep[kNumAlleles];   // this lane's locus: counts packed as forward | reverse << 16
+#pragma unroll
+        for (int a = 0; a < kNumAlleles; a++) keep[a] = 0;
+#pragma unroll 1
+        for (int half = 0; half < (kPair ? 2 : 1); half++) {
+        const int tile = (kPair ? 2 : 1) * tile_pair + half;
         if (tile >= in.n_nib_tiles) break;
         const int64_t locus = (int64_t)tile * kNibLoci + (lane >> 1);
         const bool have_locus = locus < in.n_loci;
@@ -1250,15 +1259,27 @@ pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_cons
         mine[AT_DEL] = nib_count_allele<NP>(P, 4);
         const int counted = have_locus ? in.nib_depth[sub] : 0;
         mine[AT_N] = counted - (mine[AT_A] + mine[AT_G] + mine[AT_C] + mine[AT_T] + mine[AT_DEL]);   // N bases and bases below the quality bar
+#pragma unroll
+        for (int a = 0; a < kNumAlleles; a++) {
+            const uint32_t other = (uint32_t)__shfl_xor_sync(0xffffffffu, mine[a], 1);
+            const uint32_t packed = (uint32_t)mine[a] | (other << 16);                       // valid in the even (forward) lanes
+            if (kPair) {
+                const uint32_t got = __shfl_sync(0xffffffffu, packed, 2 * (lane & 15));      // locus (lane & 15) of this sub-tile
+                if ((lane >> 4) == half) keep[a] = got;
+            } else keep[a] = packed;
+        }
+        }   // half
+
+        // kPair (gVCF: every locus scores its reference allele): one locus per lane over both sub-tiles; otherwise the even lanes finish their own locus
+        const int64_t locus = kPair ? ((int64_t)2 * tile_pair + (lane >> 4)) * kNibLoci + (lane & 15) : (int64_t)tile_pair * kNibLoci + (lane >> 1);
+        if (kPair ? (2 * tile_pair + (lane >> 4) >= in.n_nib_tiles || locus >= in.n_loci) : ((lane & 1) || locus >= in.n_loci)) continue;
         int cnt[kNumAlleles][kNumDirs];
         int any = 0;
 #pragma unroll
         for (int a = 0; a < kNumAlleles; a++) {
-            const int other = __shfl_xor_sync(0xffffffffu, mine[a], 1);
-            cnt[a][DIR_F] = mine[a]; cnt[a][DIR_R] = other; cnt[a][DIR_S] = 0;
-            any += mine[a] + other;
+            cnt[a][DIR_F] = (int)(keep[a] & 0xffffu); cnt[a][DIR_R] = (int)(keep[a] >> 16); cnt[a][DIR_S] = 0;
+            any += cnt[a][DIR_F] + cnt[a][DIR_R];
         }
-        if (!have_locus || (lane & 1)) continue;
         const int ref_allele = allele_of_base(in.ref_base[locus]);
         finish_locus(cnt, 0.0, any, locus, ref_allele, in, ex, out, cfg, s_pend, &s_pend_n);
     }
@@ -1294,9 +1315,15 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
     if (out.counts_out == nullptr && in.nib != nullptr && !want_q && !coll && cfg.tune_prefetch != 9) {
         // the hot path: PNIB16 (direction-split, nibble-packed); planes needed = bits of the largest (byte lane, allele) count = stored / 4
         const int need = in.nib_max_store / 4 + 2;
-        const int grid = max(1, min(num_sms * 4, (in.n_nib_tiles + 7) / 8));
-        if (need < (1 << 8)) pileup_nib_score_kernel<8><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);
-        else pileup_nib_score_kernel<12><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);
+        const bool pair = cfg.output_gvcf != 0;
+        const int grid = max(1, min(num_sms * 4, (in.n_nib_tiles + (pair ? 15 : 7)) / (pair ? 16 : 8)));
+        if (need < (1 << 8)) {
+            if (pair) pileup_nib_score_kernel<8, true><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);
+            else pileup_nib_score_kernel<8, false><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);
+        } else {
+            if (pair) pileup_nib_score_kernel<12, true><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);
+            else pileup_nib_score_kernel<12, false><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);
+        }
     } else if (out.counts_out == nullptr && max_depth + 2 * kChunk < (1 << 16)) {
         // vertical counters over the PTILE32 planes; planes needed = bits of the largest row count (entries + PADs of a locus)
         const int need = max_depth + 2 * kChunk;
