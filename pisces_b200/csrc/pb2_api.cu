@@ -176,6 +176,11 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
         if ((e = cudaMalloc(&h->d_q_to_p, t.size() * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
         if ((e = cudaMemcpy(h->d_q_to_p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
     }
+    if (h->dcfg.ploidy == PLOIDY_SOMATIC) {
+        if ((e = cudaMalloc(&h->d_gq_tail, sizeof(double) * kGqTailMaxCov * kGqTailMaxA)) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = launch_gq_tail_fill(h->d_gq_tail, h->dcfg.target_lod, h->stream)) != cudaSuccess) return bail("gq_tail_fill", e);
+        if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("gq_tail_fill", e);
+    }
     *out = h;
     return PB2_OK;
 }
@@ -224,6 +229,7 @@ extern "C" void pb2_destroy(pb2_handle* h) {
     if (h->d_tile_counter) cudaFree(h->d_tile_counter);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->d_q_to_p) cudaFree(h->d_q_to_p);
+    if (h->d_gq_tail) cudaFree(h->d_gq_tail);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_scattered[i]) cudaEventDestroy(h->ev_scattered[i]); }
@@ -506,7 +512,7 @@ static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32
     in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles; in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);
     in.nib = s.nib; in.nib_tile_base = s.nib_tile_base; in.nib_store = s.nib_store; in.nib_depth = s.nib_depth; in.n_nib_tiles = s.n_nib_tiles; in.nib_max_store = s.nib_max_store;
     HotInputsExtra ex;
-    ex.gapped_ref = d_gapped; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len; ex.q_to_p_table = h->d_q_to_p; ex.q_table_max = h->q_table_max;
+    ex.gapped_ref = d_gapped; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len; ex.q_to_p_table = h->d_q_to_p; ex.q_table_max = h->q_table_max; ex.gq_tail_table = h->d_gq_tail;
     HotOutputs out;
     out.ref_records = s.ref_records; out.ref_valid = s.ref_valid; out.var_records = s.var_records; out.var_count = s.counters;
     out.var_capacity = s.var_capacity; out.exc_entries = s.exc_entries; out.exc_count = s.counters + 3; out.exc_capacity = s.exc_capacity;

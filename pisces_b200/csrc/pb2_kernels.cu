@@ -251,20 +251,33 @@ struct LocusCounts {
 
 // Fill one record for a point allele (Reference or Snv) exactly as ProcessVariant + SetGenotypes would. Returns false when a non-reference
 // allele is not callable (AlleleCaller.IsCallable) so nothing is emitted.
-__device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int position, int ref_allele, int alt_allele /* == ref_allele for Reference */, int gapped,
-                                   const DeviceConfig& cfg, const HotInputsExtra& ex, pb2_call_record& r) {
+// counts of a run-time allele out of an array that must stay in registers (no dynamic indexing: a select chain over the six rows)
+__device__ __forceinline__ int count_of(const int (&c)[kNumAlleles][kNumDirs], int allele, int d) {
+    int v = 0;
+#pragma unroll
+    for (int a = 0; a < kNumAlleles; a++) v = (a == allele) ? c[a][d] : v;
+    return v;
+}
+
+// One point allele (SNV or Reference) of a locus: coverage, q-score, strand bias, filters, genotype, record. kRefOnly: the allele is known at compile
+// time to be the locus' reference allele (the per-locus Reference candidate of gVCF mode) - that instance is inlined into the hot kernel, its counts
+// and its record living in registers; the general one sits behind the out-of-line score_point_allele below.
+template <bool kRefOnly>
+__device__ __forceinline__ bool score_point_allele_impl(const int (&c)[kNumAlleles][kNumDirs], double qsum, int position, int ref_allele,
+                                                        int alt_allele /* == ref_allele for Reference */, int gapped, const DeviceConfig& cfg,
+                                                        const HotInputsExtra& ex, pb2_call_record& r) {
     const uint8_t* __restrict__ chr_seq = ex.chr_seq;
     const int64_t chr_len = ex.chr_len;
-    const bool is_ref = alt_allele == ref_allele;
+    const bool is_ref = kRefOnly || alt_allele == ref_allele;
     int cov[3], sup[3];
     int total = 0, nocalls = 0, ref_support = 0;
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-        cov[d] = lc.c[AT_A][d] + lc.c[AT_C][d] + lc.c[AT_G][d] + lc.c[AT_T][d] + lc.c[AT_DEL][d];
+        cov[d] = c[AT_A][d] + c[AT_C][d] + c[AT_G][d] + c[AT_T][d] + c[AT_DEL][d];
         total += cov[d];
-        nocalls += lc.c[AT_N][d];
-        sup[d] = lc.c[alt_allele][d];
-        if (ref_allele != AT_N) ref_support += lc.c[ref_allele][d];
+        nocalls += c[AT_N][d];
+        sup[d] = count_of(c, alt_allele, d);
+        if (ref_allele != AT_N) ref_support += kRefOnly ? sup[d] : count_of(c, ref_allele, d);
     }
     int allele_support = sup[0] + sup[1] + sup[2];
     if (is_ref) allele_support = max(0, allele_support - gapped);  // CoverageCalculator.cs:94-97
@@ -283,7 +296,7 @@ __device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int posit
         int nl = cfg.noise_level;
         double error_rate = cfg.vq_error_rate;
         if (cfg.noise_model == 1) {   // NoiseModel.Window (AlleleCaller.cs:215-218)
-            nl = (int)(-10 * log10(lc.qsum / total));
+            nl = (int)(-10 * log10(qsum / total));
             error_rate = q_to_p((double)nl);
         }
         nl_applied = nl;
@@ -310,7 +323,7 @@ __device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int posit
     int gt, gq;
     if (cfg.ploidy == PLOIDY_SOMATIC) {
         gt = somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
-        gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, ex.q_to_p_table, ex.q_table_max);
+        gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, ex.q_to_p_table, ex.q_table_max, ex.gq_tail_table);
     } else {
         const bool hap = cfg.ploidy == PLOIDY_HAPLOID;
         gt = is_ref ? germline_reference_only_genotype(hap, total, allele_support, ref_support, cfg.diploid_minor_vf, cfg.diploid_major_vf, cfg.min_coverage) : GT_HET_ALT_REF;
@@ -337,10 +350,15 @@ __device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int posit
     r.allele_bytes = (uint32_t)(uint8_t)base_of_allele(ref_allele) | ((uint32_t)(uint8_t)base_of_allele(alt_allele) << 8);
     r.ref_len = 1;
     r.alt_len = 1;
-    r.sum_base_quality = lc.qsum;
+    r.sum_base_quality = qsum;
     r.bias_score = sb.bias;
     r.gatk_bias_score = sb.gatk;
     return true;
+}
+
+__device__ __noinline__ bool score_point_allele(const LocusCounts& lc, int position, int ref_allele, int alt_allele /* == ref_allele for Reference */, int gapped,
+                                   const DeviceConfig& cfg, const HotInputsExtra& ex, pb2_call_record& r) {
+    return score_point_allele_impl<false>(lc.c, lc.qsum, position, ref_allele, alt_allele, gapped, cfg, ex, r);
 }
 
 __device__ __forceinline__ void store_record(pb2_call_record* dst, const pb2_call_record& r) {
@@ -410,14 +428,8 @@ __device__ __forceinline__ void finish_locus(const int (&cnt)[kNumAlleles][kNumD
         const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
         const bool emit = cfg.output_gvcf && !has_ext_variant && (cfg.have_intervals || any > 0) && (ex.chr_len == 0 || position <= ex.chr_len);
         if (emit) {
-            LocusCounts lc;
-#pragma unroll
-            for (int a = 0; a < kNumAlleles; a++)
-#pragma unroll
-                for (int d = 0; d < kNumDirs; d++) lc.c[a][d] = cnt[a][d];
-            lc.qsum = qsum;
-            pb2_call_record r;
-            score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex, r);
+            pb2_call_record r;   // registers: the inlined scorer writes fields, store_record reads them back as six 16-byte words
+            score_point_allele_impl<true>(cnt, qsum, position, ref_allele, ref_allele, gapped, cfg, ex, r);
             store_record(out.ref_records + locus, r);
         }
         out.ref_valid[locus] = emit ? 1 : 0;
@@ -1290,6 +1302,19 @@ pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_cons
         const int item = threadIdx.x >> 2;
         score_queued_locus(item < n ? &s_pend[item] : nullptr, threadIdx.x & 3, in, ex, out, cfg);
     }
+}
+
+// table[cov][a] = Poisson.Cdf(a - 1, targetLOD * cov) with the float product of SomaticGenotypeQualityCalculator.cs:33 (see somatic_gq)
+__global__ void gq_tail_fill_kernel(double* __restrict__ table, float target_lod) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kGqTailMaxCov * kGqTailMaxA) return;
+    const int cov = i / kGqTailMaxA, a = i % kGqTailMaxA;
+    const float expected = target_lod * (float)cov;
+    table[i] = a >= 1 ? pisces_poisson_cdf((double)(a - 1), (double)expected) : 0.0;
+}
+cudaError_t launch_gq_tail_fill(double* table, float target_lod, cudaStream_t stream) {
+    gq_tail_fill_kernel<<<(kGqTailMaxCov * kGqTailMaxA + 255) / 256, 256, 0, stream>>>(table, target_lod);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_nib_count(const TilePileup& in, int32_t* nib_store, int32_t* nib_depth, int64_t* nib_tile_bytes, int32_t* flags, cudaStream_t stream) {

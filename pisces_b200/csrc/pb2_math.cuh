@@ -317,8 +317,13 @@ __device__ __forceinline__ int somatic_genotype(bool is_ref, int total_cov, floa
 }
 // SomaticGenotypeQualityCalculator.cs:10-48
 // q_to_p_table: optional device table of QtoP(q) for q = 0..table_max (filled on the host with the same expression), nullptr -> pow on the device
+// gq_tail_table: optional device table of the Poisson tail below, Cdf((int)(nonAlleleObservations + 1) - 1, targetLOD * coverage), indexed
+// [coverage][(int)(nonAlleleObservations + 1)] for coverage < kGqTailMaxCov and a < kGqTailMaxA: the value depends on nothing else (Poisson.Cdf
+// truncates its first argument, Poisson.cs:26-44), and gq_tail_fill_kernel fills it with this very function, so a lookup returns the same double.
+constexpr int kGqTailMaxCov = 8192, kGqTailMaxA = 32;
 __device__ __forceinline__ int somatic_gq(int genotype, int vq, int total_cov, float freq, float target_lod, int min_gq, int max_gq,
-                                          const double* __restrict__ q_to_p_table = nullptr, int table_max = -1) {
+                                          const double* __restrict__ q_to_p_table = nullptr, int table_max = -1,
+                                          const double* __restrict__ gq_tail_table = nullptr) {
     double raw = vq;
     const bool nocall = genotype == GT_ALT12_NOCALL || genotype == GT_ALT_NOCALL || genotype == GT_REF_NOCALL;
     if (total_cov == 0 || nocall) return min_gq;
@@ -327,7 +332,10 @@ __device__ __forceinline__ int somatic_gq(int genotype, int vq, int total_cov, f
         const float non_allele_obs = (1.0f - freq) * (float)total_cov;
         const float expected = target_lod * (float)total_cov;
         if (non_allele_obs >= expected) return min_gq;
-        const double p2 = pisces_poisson_cdf((double)non_allele_obs, (double)expected);
+        const int a_key = (int)((double)non_allele_obs + 1.0);
+        const double p2 = (gq_tail_table != nullptr && total_cov < kGqTailMaxCov && a_key >= 1 && a_key < kGqTailMaxA)
+                              ? gq_tail_table[total_cov * kGqTailMaxA + a_key]
+                              : pisces_poisson_cdf((double)non_allele_obs, (double)expected);
         raw = -10 * log10(p1 + p2);
     }
     double q = fmin((double)max_gq, raw);
