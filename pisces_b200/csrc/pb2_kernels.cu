@@ -1135,11 +1135,9 @@ template <int NP, bool kPair>
 __global__ void __launch_bounds__(256, 4)
 pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_constant__ HotInputsExtra ex, const __grid_constant__ HotOutputs out,
                         const __grid_constant__ DeviceConfig cfg, int* __restrict__ tile_counter) {
-    __shared__ int s_tile[8];
     __shared__ __align__(16) PendingLocus s_pend[kCtaPending];
     __shared__ int s_pend_n;
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_pend_n = 0;
     __syncthreads();
     const uint32_t neg_minbq4 = 0u - (uint32_t)cfg.min_bq * 0x01010101u;
@@ -1147,13 +1145,16 @@ pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_cons
     const uint32_t t_lo = 0x08040201u, t_hi = 0x00001000u;   // allele code -> one-hot byte: A 1, G 2, C 4, T 8, (4) 0, Deletion 16, PAD 0, (7) 0
     const unsigned lt = (1u << lane) - 1;
 
+    auto grab = [&]() -> int {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    int next_pair = grab();
     while (true) {
         // a warp takes two sub-tiles (32 loci) at a time: each is counted with one (locus, direction) per lane, then the 2 x 16 loci are scored with one
         // locus per lane, so that the per-locus work (candidate screening; in gVCF mode the reference allele's q-score / genotype chain) runs on full warps
-        if (lane == 0) s_tile[warp] = atomicAdd(tile_counter, 1);
-        __syncwarp();
-        const int tile_pair = s_tile[warp];
-        __syncwarp();
+        const int tile_pair = next_pair;
         if ((kPair ? 2 : 1) * tile_pair >= in.n_nib_tiles) break;
         uint32_t keep[kNumAlleles];   // this lane's locus: counts packed as forward | reverse << 16
 #pragma unroll
@@ -1282,6 +1283,20 @@ pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_cons
         }
         }   // half
 
+        // the next piece of work is taken before this one is finished; in gVCF mode, where finishing means a q-score / strand-bias / genotype chain per
+        // locus during which the warp has no loads in flight, the head of the next pair (2 x 8 KB) is pulled into L2 meanwhile
+        next_pair = grab();
+        if (kPair && cfg.tune_prefetch != 8) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int t = 2 * next_pair + h;
+                if (t < in.n_nib_tiles) {
+                    const int64_t b0 = in.nib_tile_base[t], b1 = in.nib_tile_base[t + 1];   // [n_nib_tiles + 1] entries
+                    if (b0 + 128 * lane < b1) prefetch_l2(in.nib + b0 + 128 * lane);
+                    if (b0 + 128 * (32 + lane) < b1) prefetch_l2(in.nib + b0 + 128 * (32 + lane));
+                }
+            }
+        }
         // kPair (gVCF: every locus scores its reference allele): one locus per lane over both sub-tiles; otherwise the even lanes finish their own locus
         const int64_t locus = kPair ? ((int64_t)2 * tile_pair + (lane >> 4)) * kNibLoci + (lane & 15) : (int64_t)tile_pair * kNibLoci + (lane >> 1);
         if (kPair ? (2 * tile_pair + (lane >> 4) >= in.n_nib_tiles || locus >= in.n_loci) : ((lane & 1) || locus >= in.n_loci)) continue;

@@ -63,7 +63,7 @@ struct TilePileup {
     // Sub-locus (locus, direction in {F, R}) = one lane; sub-tile = 16 loci = 32 sub-loci; per step the 16-byte quality chunks of the active sub-loci,
     // then their 8-byte code chunks (16 allele nibbles), the step padded to 16 bytes.
     const uint8_t* nib;
-    const int64_t* nib_tile_base;   // [n_nib_tiles] byte offset of a sub-tile
+    const int64_t* nib_tile_base;   // [n_nib_tiles + 1] byte offset of a sub-tile (last entry: total bytes)
     const int32_t* nib_store;       // [2 * n_loci] entries stored for (locus, direction): A/C/G/T of any quality and countable deletions
     const int32_t* nib_depth;       // [2 * n_loci] entries counted for (locus, direction): the stored ones + N bases
     int32_t n_nib_tiles;
