@@ -190,7 +190,8 @@ typedef struct pb2_call_record_ext {
     int32_t collapsed_mut[8];
     int32_t collapsed_total[8];
     int32_t well_anchored_support[3];  /* WellAnchoredSupportByDirection */
-    int32_t reserved;
+    int32_t phase_set_index;           /* CalledAllele.PhaseSetIndex as the diploid genotyper sets it (DiploidThresholdingGenotyper.cs:57-72): 0 for the
+                                        * reference allele, 1, 2, ... for the variant alleles of a locus in their order; 0 where no genotyper set it */
 } pb2_call_record_ext;
 
 void pb2_default_config(pb2_config* cfg);
@@ -242,16 +243,25 @@ int pb2_get_counts(pb2_handle* h, int32_t position0, int32_t n, int32_t* out);
 /* Drop staged pileups and results (IStateManager.DoneProcessing). */
 int pb2_reset(pb2_handle* h);
 
-/* VCF record lines for called alleles, as the reference's writer prints them when every allele gets its own line (AllowMultipleVcfLinesPerLoci, the
- * somatic default): VcfFileWriter.WriteListOfColocatedAlleles (src/lib/Pisces.IO/VcfFileWriter.cs:206-260) with VcfFormatter
+/* VCF record lines for called alleles, as the reference's writer prints them: every allele on its own line (AllowMultipleVcfLinesPerLoci, the
+ * somatic default) or, with options->crushed, the alleles of a position merged into one line (REF / ALT of MergeCrushedReferenceAndAlt, the smallest
+ * QUAL and GQ, merged filters, AD / VF of the 1/2 genotypes; the germline default), optionally with RegionMapper's padding of uncovered interval
+ * positions: VcfFileWriter.WriteListOfColocatedAlleles (src/lib/Pisces.IO/VcfFileWriter.cs:206-260) with VcfFormatter
  * (src/lib/Pisces.IO/VcfFormatter.cs:52-71,143-251,283-420). CHROM is the name given to pb2_set_reference; alleles longer than 4 bases are read from
  * the arena of the last pb2_flush. `ext` (pb2_flush_ext) feeds the US tag and may be NULL. The text (one '\n'-terminated line per record; no header)
- * is owned by the handle until the next call. The crushed one-line-per-locus form of the germline writer is not built. */
+ * is owned by the handle until the next call. */
 typedef struct pb2_vcf_options {
     int32_t debug_mode;          /* PiscesApplicationOptions.DebugMode */
     int32_t output_bias_files;   /* OutputBiasFiles */
     int32_t report_rc_counts;    /* VcfWritingParameters.ReportRcCounts: the US tag */
     int32_t report_ts_counts;    /* ReportTsCounts */
+    int32_t crushed;             /* !VcfWritingParameters.AllowMultipleVcfLinesPerLoci: one line per position (GroupsAllelesThenWrite, VcfFileWriter.cs:177-204;
+                                  * the default of the diploid / haploid ploidy models, VcfWritingParameters.cs:18-40) */
+    int32_t report_no_calls;     /* VcfWritingParameters.ReportNoCalls: the NC tag */
+    int32_t pad_intervals;       /* RegionMapper padding (RegionMapper.cs:31-84) with the handle's intervals and reference: 1 = the uncovered interval positions
+                                  * before each written position (PadIfNeeded), 2 = also those after the last one (WriteRemaining). One call is one writer
+                                  * pass over a chromosome: the padding state starts fresh on every call */
+    int32_t reserved_[1];
 } pb2_vcf_options;
 int pb2_vcf_format(pb2_handle* h, const pb2_call_record* records, const pb2_call_record_ext* ext, int64_t n, const pb2_vcf_options* options, const char** text,
                    int64_t* len);

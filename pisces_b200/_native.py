@@ -64,7 +64,7 @@ RECORD_DTYPE = [("position", "<i4"), ("type", "u1"), ("genotype", "u1"), ("sb_fl
                 ("reference_support", "<i4"), ("num_no_calls", "<i4"), ("fraction_no_calls", "<f4"), ("allele_bytes", "<u4"),
                 ("ref_len", "<u2"), ("alt_len", "<u2"), ("sum_base_quality", "<f8"), ("bias_score", "<f8"), ("gatk_bias_score", "<f8")]
 
-RECORD_EXT_DTYPE = [("collapsed_mut", "<i4", (8,)), ("collapsed_total", "<i4", (8,)), ("well_anchored_support", "<i4", (3,)), ("reserved", "<i4")]
+RECORD_EXT_DTYPE = [("collapsed_mut", "<i4", (8,)), ("collapsed_total", "<i4", (8,)), ("well_anchored_support", "<i4", (3,)), ("phase_set_index", "<i4")]
 
 EXPORTS = ["pb2_default_config", "pb2_create", "pb2_destroy", "pb2_last_error", "pb2_device_count", "pb2_set_reference", "pb2_set_intervals",
            "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_candidates", "pb2_set_forced_alleles", "pb2_allele_arena", "pb2_call_resident", "pb2_resident_results", "pb2_flush", "pb2_flush_ext",

@@ -1122,7 +1122,9 @@ static void germline_locus_pass(pb2_handle* h) {
             if (gt == GT_ALT_AND_NOCALL || gt == GT_ALT_NOCALL || gt == GT_HOM_ALT || gt == GT_HET_ALT_REF || gt == GT_HEMI_ALT) allowed = 1;
             else if (gt == GT_ALT12_NOCALL || gt == GT_HET_ALT12) allowed = 2;
             for (size_t k = 0; k < ordered.size(); k++) if ((int)k >= allowed) prune.push_back(ordered[k]);
+            int phase_set_index = 1;   // DiploidThresholdingGenotyper.SetGenotypes (:57-72); the haploid genotyper leaves it unset
             for (size_t i : ng) {
+                if (!hap) E[i].phase_set_index = R[i].type == CAT_REF ? 0 : phase_set_index++;
                 R[i].genotype = (uint8_t)gt;
                 R[i].genotype_qscore = germline_gq(hap, gt, R[i].total_coverage, R[i].allele_support, d.min_gq, d.max_gq);
                 if (multi_allelic) R[i].filters |= (uint16_t)(1u << FLT_MULTI_ALLELIC);

@@ -324,10 +324,14 @@ class GpuStateManager:
         ab = np.frombuffer(bytes(buf), dtype=np.uint8) if len(buf) else np.zeros(1, dtype=np.uint8)
         self._chk(self._L.pb2_set_forced_alleles(self._h, arr.ctypes.data, len(alleles), ab.ctypes.data, len(buf)))
 
-    def FormatVcf(self, records, ext=None, debug_mode=False, output_bias_files=False, report_rc_counts=False, report_ts_counts=False):
-        """pb2_vcf_format: the VCF record lines of raw records (Call(..., raw=True)) of the last flush, as a list of strings."""
+    def FormatVcf(self, records, ext=None, debug_mode=False, output_bias_files=False, report_rc_counts=False, report_ts_counts=False, crushed=False,
+                  report_no_calls=False, pad_intervals=0):
+        """pb2_vcf_format: the VCF record lines of raw records (Call(..., raw=True)) of the last flush, as a list of strings. crushed: one line per
+        position (the germline writer, VcfFileWriter.GroupsAllelesThenWrite); pad_intervals: RegionMapper's empty reference calls (1 = before each
+        written position, 2 = also after the last one)."""
         records = np.ascontiguousarray(records)
-        opt = (C.c_int32 * 4)(int(debug_mode), int(output_bias_files), int(report_rc_counts), int(report_ts_counts))
+        opt = (C.c_int32 * 8)(int(debug_mode), int(output_bias_files), int(report_rc_counts), int(report_ts_counts), int(crushed), int(report_no_calls),
+                              int(pad_intervals), 0)
         text, n = C.c_char_p(), C.c_int64()
         e = None if ext is None else np.ascontiguousarray(ext)
         self._chk(self._L.pb2_vcf_format(self._h, records.ctypes.data, None if e is None else e.ctypes.data, len(records), opt, C.byref(text), C.byref(n)))

@@ -6,7 +6,7 @@
            /root/reference/src/test/Pisces.Tests/TestData/PhiX_S3.{noisy,Forced1,Forced2}.vcf, PhiX_S3.forcedGTInput.vcf
            (the full-text goldens of src/test/Pisces.Tests/FunctionalTests/ForcedGTFxnlTest.cs:11-112)
   outputs: PhiX_S3.bam, collapsed.test.stitched.bam (copies), phix_s3_reads.json.gz (decoded alignments), phix_genome.txt, phix_s3_{noisy,forced1,forced2}.records.vcf (record lines only),
-           phix_forced_alleles.json
+           phix_forced_alleles.json, vcfwriter_crushed_padded.records.vcf (record lines of Pisces.IO.Tests/TestData/VcfFileWriterTests_Crushed_Padded_expected.vcf)
 """
 import gzip
 import json
@@ -20,7 +20,15 @@ from tests import bamio  # noqa: E402
 REF = "/root/reference/src/test"
 
 
+def writer_fixture():
+    """Record lines of the crushed / padded writer golden (src/test/Pisces.IO.Tests/UnitTests/VcfFileWriterTests.cs:162-275)."""
+    src = f"{REF}/Pisces.IO.Tests/TestData/VcfFileWriterTests_Crushed_Padded_expected.vcf"
+    lines = [l for l in open(src) if not l.startswith("#")]
+    open(os.path.join(HERE, "vcfwriter_crushed_padded.records.vcf"), "w").writelines(lines)
+
+
 def main():
+    writer_fixture()
     # the two BAM files themselves (15.7 KB and 1.3 KB of test data, not source): inputs of the library's own BAM stager (pb2_bam_*)
     import shutil
     shutil.copyfile(f"{REF}/SharedData/Bams/PhiX_S3.bam", os.path.join(HERE, "PhiX_S3.bam"))
