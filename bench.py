@@ -26,8 +26,8 @@ UNIT = "loci/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--loci", type=int, default=1_000_000, help="loci per GPU")
     ap.add_argument("--depth", type=int, default=500)
@@ -51,8 +51,32 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_flag = gpu_index, [], threading.Event()
+        # NVML in-process, initialised here (before the timed region): spawning nvidia-smi from a process with torch loaded, or nvmlInit itself,
+        # costs the main thread milliseconds - the size of the whole timed region at small K. nvidia-smi only if NVML cannot be loaded.
+        self.nv = self.hd = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.hd = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(self.hd, nv.NVML_CLOCK_SM)
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nv = nv
+        except Exception:
+            self.nv = None
 
     def run(self):
+        if self.nv is not None:
+            nv = self.nv
+            try:
+                while True:
+                    m = int(self.get_reasons(self.hd))
+                    act = lambda bit: "Active" if m & bit else "Not Active"   # noqa: E731
+                    self.rows.append([str(self.gpu), str(nv.nvmlDeviceGetClockInfo(self.hd, nv.NVML_CLOCK_SM)), str(self.mx), "0", act(0x8), act(0x40), act(0x20),
+                                      act(0x4)])
+                    if self.stop_flag.wait(0.005):
+                        return
+            except Exception:
+                pass
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
@@ -187,44 +211,58 @@ def main_ours(a):
         def __init__(self, ptr, nbytes):
             self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
-    # ---- the single all-gather of per-interval call records (NCCL): [int64 count | records] per rank, fixed capacity. The variant stream of the
-    # staged segment lives at a fixed device address, so its torch view is created once; a step adds two small device copies and one collective.
-    gather_in = gather_out = var_view = count_pinned = None
+    # ---- the single all-gather of per-interval call records (NCCL) at the end of the job: a step appends its variant records to the
+    # rank's job buffer (one device copy out of the library's variant stream, which lives at a fixed device address, so its torch view is created
+    # once); when the K steps are done the ranks exchange [K int64 counts | K x fixed-capacity record blocks] in ONE all_gather, inside the timed region.
+    job_buf = gather_out = var_view = counts_pinned = None
+    n_slots = max(1, a.steps)
     if world > 1:
         n0 = sm.call_resident()
-        cap_records = 1 << max(12, (2 * n0 - 1).bit_length())
+        cap_records = (n0 + n0 // 8 + 127) // 64 * 64   # fixed capacity of a step's block: its record count plus 12 % head-room
         vr, nv = C.c_void_p(), C.c_int64()
         sm._chk(sm._L.pb2_resident_results(sm._h, None, None, None, C.byref(vr), C.byref(nv)))
         var_view = torch.as_tensor(DevBuf(vr.value, cap_records * 96), device=dev)
-        gather_in = torch.zeros(8 + cap_records * 96, dtype=torch.uint8, device=dev)
-        gather_out = torch.zeros(world * (8 + cap_records * 96), dtype=torch.uint8, device=dev)
-        count_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
+        job_buf = torch.zeros(8 * n_slots + n_slots * cap_records * 96, dtype=torch.uint8, device=dev)
+        gather_out = torch.zeros(world * job_buf.numel(), dtype=torch.uint8, device=dev)
+        counts_pinned = torch.zeros(n_slots, dtype=torch.int64).pin_memory()
 
-    def step():
-        n = sm.call_resident()
+    def step(k=0):
+        n = sm.call_resident()   # returns after the step's counters are on the host: the library's stream is idle, the variant stream complete
         if world > 1:
-            count_pinned[0] = min(n, cap_records)
-            gather_in[:8].copy_(count_pinned.view(torch.uint8), non_blocking=True)
-            gather_in[8:].copy_(var_view, non_blocking=True)
-            dist.all_gather_into_tensor(gather_out, gather_in)
+            slot = k % n_slots
+            counts_pinned[slot] = min(n, cap_records)
+            o = 8 * n_slots + slot * cap_records * 96
+            job_buf[o:o + cap_records * 96].copy_(var_view, non_blocking=True)
         return n
+
+    def gather_job():
+        if world > 1:
+            job_buf[:8 * n_slots].copy_(counts_pinned.view(torch.uint8), non_blocking=True)
+            dist.all_gather_into_tensor(gather_out, job_buf)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, a.warmup)):
-        n_records = step()
+    for k in range(max(3, a.warmup)):
+        n_records = step(k)
+    gather_job()   # untimed: NCCL sets its channels up on the first collective
     sm.stats()
     sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
+    ev0.record()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        n_records = step()
+    for k in range(a.steps):
+        n_records = step(k)
+    gather_job()
     barrier()
-    dt = time.perf_counter() - t0
+    ev1.record()
+    ev1.synchronize()
+    dt_wall = time.perf_counter() - t0
+    dt = ev0.elapsed_time(ev1) * 1e-3   # device clock between the two synchronised brackets (the wall clock beside it: wall_ms_per_step)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     st = sm.stats()
@@ -259,7 +297,7 @@ def main_ours(a):
     except Exception:
         pass
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": 1e3 * dt / a.steps,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": 1e3 * dt / a.steps, "wall_ms_per_step": 1e3 * dt_wall / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "loci_per_gpu": a.loci, "entries_per_gpu": n_entries, "records_per_step": n_records + n_ref_records,
                        "l2": "staged input of the hot kernel (%.2f GB per GPU) larger than L2, no flush needed" % ((1.5 if nib else 2) * n_entries / 1e9), "parallelism": f"interval-sharded x{world}"},
