@@ -177,8 +177,11 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
         if ((e = cudaMemcpy(h->d_q_to_p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
     }
     if (h->dcfg.ploidy == PLOIDY_SOMATIC) {
-        if ((e = cudaMalloc(&h->d_gq_tail, sizeof(double) * kGqTailMaxCov * kGqTailMaxA)) != cudaSuccess) return bail("cudaMalloc", e);
-        if ((e = launch_gq_tail_fill(h->d_gq_tail, h->dcfg.target_lod, h->stream)) != cudaSuccess) return bail("gq_tail_fill", e);
+        if ((e = cudaMalloc(&h->d_gq_tail, (sizeof(double) + sizeof(int)) * kGqTailMaxCov * kGqTailMaxA)) != cudaSuccess) return bail("cudaMalloc", e);
+        // the finished-GQ half of the table is for a variant q-score at its cap; p1 is the very double the kernels would read from d_q_to_p
+        h->gq_capped_vq = (h->dcfg.max_vq >= 0 && h->dcfg.max_vq <= h->q_table_max) ? h->dcfg.max_vq : -1;
+        const double p1 = h->gq_capped_vq >= 0 ? std::pow(10.0, -1 * (double)h->gq_capped_vq / 10.0) : 0.0;
+        if ((e = launch_gq_tail_fill(h->d_gq_tail, h->dcfg.target_lod, p1, h->dcfg.min_gq, h->dcfg.max_gq, h->stream)) != cudaSuccess) return bail("gq_tail_fill", e);
         if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("gq_tail_fill", e);
     }
     *out = h;
@@ -512,7 +515,7 @@ static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32
     in.positions = s.positions; in.first_position = s.first_position; in.n_loci = s.n_loci; in.n_tiles = s.n_tiles; in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);
     in.nib = s.nib; in.nib_tile_base = s.nib_tile_base; in.nib_store = s.nib_store; in.nib_depth = s.nib_depth; in.n_nib_tiles = s.n_nib_tiles; in.nib_max_store = s.nib_max_store;
     HotInputsExtra ex;
-    ex.gapped_ref = d_gapped; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len; ex.q_to_p_table = h->d_q_to_p; ex.q_table_max = h->q_table_max; ex.gq_tail_table = h->d_gq_tail;
+    ex.gapped_ref = d_gapped; ex.locus_has_variant = nullptr; ex.chr_seq = h->d_chr; ex.chr_len = h->chr_len; ex.q_to_p_table = h->d_q_to_p; ex.q_table_max = h->q_table_max; ex.gq_tail_table = h->d_gq_tail; ex.gq_capped_vq = h->gq_capped_vq;
     HotOutputs out;
     out.ref_records = s.ref_records; out.ref_valid = s.ref_valid; out.var_records = s.var_records; out.var_count = s.counters;
     out.var_capacity = s.var_capacity; out.exc_entries = s.exc_entries; out.exc_count = s.counters + 3; out.exc_capacity = s.exc_capacity;

@@ -129,6 +129,7 @@ struct pb2_handle {
     std::string error;
     std::string chr_name;
     uint8_t* d_chr = nullptr;
+    int gq_capped_vq = -1;          // the variant q-score the finished-GQ half of d_gq_tail was filled for
     double* d_gq_tail = nullptr;    // somatic-GQ Poisson tails [kGqTailMaxCov][kGqTailMaxA] (pb2_math.cuh:somatic_gq)
     double* d_q_to_p = nullptr;     // QtoP(q) for q = 0..max_variant_qscore (capped at 1024 entries)
     int q_table_max = -1;

@@ -23,10 +23,20 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t* p) {  // 16-byte stre
     return r;
 }
 __device__ __forceinline__ void prefetch_l2(const uint8_t* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// branch-free both ways (a switch here compiles to divergent branches in the per-locus tail of the hot kernel)
 __device__ __forceinline__ int allele_of_base(uint8_t c) {  // AlleleHelper.GetAlleleType (Utility/AlleleHelper.cs:13-32)
-    switch (c) { case 'A': return AT_A; case 'C': return AT_C; case 'G': return AT_G; case 'T': return AT_T; default: return AT_N; }
+    int a = AT_N;
+    a = c == 'A' ? AT_A : a;
+    a = c == 'C' ? AT_C : a;
+    a = c == 'G' ? AT_G : a;
+    a = c == 'T' ? AT_T : a;
+    return a;
 }
-__device__ __forceinline__ char base_of_allele(int a) { return a == AT_A ? 'A' : a == AT_C ? 'C' : a == AT_G ? 'G' : a == AT_T ? 'T' : 'N'; }
+__device__ __forceinline__ char base_of_allele(int a) {   // AT_A 0, AT_G 1, AT_C 2, AT_T 3, everything else 'N'
+    static_assert(AT_A == 0 && AT_G == 1 && AT_C == 2 && AT_T == 3, "allele codes");
+    const unsigned lut = 'A' | ('G' << 8) | ('C' << 16) | ((unsigned)'T' << 24);
+    return (unsigned)a < 4u ? (char)((lut >> (8 * a)) & 0xffu) : 'N';
+}
 
 // ------------------------------------------------------------------------------------------------ CSR -> PTILE32
 // depth[i] = off[i+1]-off[i];  tile_chunks[t] = bytes per plane of tile t = 16 * sum over the tile's loci of ceil(depth/16)
@@ -323,7 +333,7 @@ __device__ __forceinline__ bool score_point_allele_impl(const int (&c)[kNumAllel
     int gt, gq;
     if (cfg.ploidy == PLOIDY_SOMATIC) {
         gt = somatic_genotype(is_ref, total, freq, ref_freq, cfg.min_frequency_filter, cfg.min_coverage);
-        gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, ex.q_to_p_table, ex.q_table_max, ex.gq_tail_table);
+        gq = somatic_gq(gt, vq, total, freq, cfg.target_lod, cfg.min_gq, cfg.max_gq, ex.q_to_p_table, ex.q_table_max, ex.gq_tail_table, ex.gq_capped_vq);
     } else {
         const bool hap = cfg.ploidy == PLOIDY_HAPLOID;
         gt = is_ref ? germline_reference_only_genotype(hap, total, allele_support, ref_support, cfg.diploid_minor_vf, cfg.diploid_major_vf, cfg.min_coverage) : GT_HET_ALT_REF;
@@ -1319,16 +1329,22 @@ pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_cons
     }
 }
 
-// table[cov][a] = Poisson.Cdf(a - 1, targetLOD * cov) with the float product of SomaticGenotypeQualityCalculator.cs:33 (see somatic_gq)
-__global__ void gq_tail_fill_kernel(double* __restrict__ table, float target_lod) {
+// table[cov][a] = Poisson.Cdf(a - 1, targetLOD * cov) with the float product of SomaticGenotypeQualityCalculator.cs:33 (see somatic_gq); behind it
+// int32 gq[cov][a] = the GQ of a homozygous genotype whose variant q-score is capped_vq (the same statements as somatic_gq's tail)
+__global__ void gq_tail_fill_kernel(double* __restrict__ table, float target_lod, double p1_capped, int min_gq, int max_gq) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kGqTailMaxCov * kGqTailMaxA) return;
     const int cov = i / kGqTailMaxA, a = i % kGqTailMaxA;
     const float expected = target_lod * (float)cov;
-    table[i] = a >= 1 ? pisces_poisson_cdf((double)(a - 1), (double)expected) : 0.0;
+    const double p2 = a >= 1 ? pisces_poisson_cdf((double)(a - 1), (double)expected) : 0.0;
+    table[i] = p2;
+    const double raw = -10 * log10(p1_capped + p2);
+    double q = fmin((double)max_gq, raw);
+    q = fmax(q, (double)min_gq);
+    reinterpret_cast<int*>(table + kGqTailMaxCov * kGqTailMaxA)[i] = (int)rint(q);
 }
-cudaError_t launch_gq_tail_fill(double* table, float target_lod, cudaStream_t stream) {
-    gq_tail_fill_kernel<<<(kGqTailMaxCov * kGqTailMaxA + 255) / 256, 256, 0, stream>>>(table, target_lod);
+cudaError_t launch_gq_tail_fill(double* table, float target_lod, double p1_capped, int min_gq, int max_gq, cudaStream_t stream) {
+    gq_tail_fill_kernel<<<(kGqTailMaxCov * kGqTailMaxA + 255) / 256, 256, 0, stream>>>(table, target_lod, p1_capped, min_gq, max_gq);
     return cudaGetLastError();
 }
 

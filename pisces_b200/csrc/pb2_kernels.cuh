@@ -106,11 +106,13 @@ struct HotInputsExtra {
     int64_t chr_len;
     const double* q_to_p_table;     // QtoP(q), q = 0..q_table_max (MathOperations.cs:7-10), or nullptr
     int q_table_max;
-    const double* gq_tail_table;    // [kGqTailMaxCov][kGqTailMaxA] Poisson tails of the somatic GQ (pb2_math.cuh:somatic_gq), or nullptr
+    const double* gq_tail_table;    // [kGqTailMaxCov][kGqTailMaxA] Poisson tails of the somatic GQ (pb2_math.cuh:somatic_gq), or nullptr; followed by
+                                    // int32 [kGqTailMaxCov][kGqTailMaxA]: the finished GQ when the variant q-score is gq_capped_vq
+    int gq_capped_vq;
 };
 
 // fills the somatic-GQ tail table for this target LOD (once per handle)
-cudaError_t launch_gq_tail_fill(double* table, float target_lod, cudaStream_t stream);
+cudaError_t launch_gq_tail_fill(double* table, float target_lod, double p1_capped, int min_gq, int max_gq, cudaStream_t stream);
 size_t hot_kernel_smem_bytes(bool narrow, bool collapsed);
 cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
                               int max_depth, cudaStream_t stream);

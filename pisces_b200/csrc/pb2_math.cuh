@@ -178,6 +178,10 @@ __device__ __forceinline__ bool qscore_is_capped(int k, int n, double error_rate
     const double lambda = error_rate * n;
     const double kd = k;
     if (!(kd > lambda) || !(lambda > 0)) return false;
+    const double need0 = -(double)max_q * 0.23025850929940458 - 1.0;   // = `need` below
+    // log-free pre-test (the common case of a well-supported allele): with k >= 8 lambda, ln(k/lambda) >= ln 8 bounds both expressions below from
+    // above: ln_chernoff <= k (1 - ln 8), and a_ub - corr <= k (1 - ln 8) + ln 8 - 0.9189 - ln(2 * 7/8) <= k (1 - ln 8) + 0.61
+    if (kd >= 8.0 * lambda && kd * -1.0794415416798357 + 0.61 <= need0 - 1.3862943611198906) return true;
     // single-precision logs are enough for a bound: their error (<= 2e-7 relative) times k <= 65535 is below 0.2; 1.0 of slack is charged
     const double lnk = (double)logf((float)kd), lnl = (double)logf((float)lambda);
     const double need = -(double)max_q * 0.23025850929940458 - 1.0;          // ln(10^(-maxQ/10)) minus the slack
@@ -262,7 +266,10 @@ __device__ __forceinline__ SbStats sb_create_stats(double support, double covera
         // approximations (Poisson.cs:106-128); when that bounds gs below 2^-54 the double subtraction yields exactly 1.0.
         const double x = coverage * noise;
         bool saturated = false;
-        if (x > 0 && x <= 0.5 * support) {
+        if (x > 0 && x <= 0.125 * support && support >= 45.0) {
+            // log-free: ln(support / x) >= ln 8 gives e_ub <= support (1 - ln 8) + ln(support) / 2 - 0.9189, which decreases in support and is -47.6 at 45
+            saturated = true;
+        } else if (x > 0 && x <= 0.5 * support) {
             // single-precision logs + 1.0 of slack (see qscore_is_capped)
             const double e_ub = support * (double)logf((float)x) - x - ((support - 0.5) * (double)logf((float)support) - support + 0.9189385332046727);
             saturated = e_ub < -41.0;
@@ -320,10 +327,12 @@ __device__ __forceinline__ int somatic_genotype(bool is_ref, int total_cov, floa
 // gq_tail_table: optional device table of the Poisson tail below, Cdf((int)(nonAlleleObservations + 1) - 1, targetLOD * coverage), indexed
 // [coverage][(int)(nonAlleleObservations + 1)] for coverage < kGqTailMaxCov and a < kGqTailMaxA: the value depends on nothing else (Poisson.Cdf
 // truncates its first argument, Poisson.cs:26-44), and gq_tail_fill_kernel fills it with this very function, so a lookup returns the same double.
+// Behind the doubles sits a second table of the same shape: the finished GQ (an int32) of a variant q-score equal to the cap, max_variant_qscore -
+// what nearly every confidently homozygous locus has - computed by the fill kernel with the statements below.
 constexpr int kGqTailMaxCov = 8192, kGqTailMaxA = 32;
 __device__ __forceinline__ int somatic_gq(int genotype, int vq, int total_cov, float freq, float target_lod, int min_gq, int max_gq,
                                           const double* __restrict__ q_to_p_table = nullptr, int table_max = -1,
-                                          const double* __restrict__ gq_tail_table = nullptr) {
+                                          const double* __restrict__ gq_tail_table = nullptr, int capped_vq = -1) {
     double raw = vq;
     const bool nocall = genotype == GT_ALT12_NOCALL || genotype == GT_ALT_NOCALL || genotype == GT_REF_NOCALL;
     if (total_cov == 0 || nocall) return min_gq;
@@ -333,6 +342,8 @@ __device__ __forceinline__ int somatic_gq(int genotype, int vq, int total_cov, f
         const float expected = target_lod * (float)total_cov;
         if (non_allele_obs >= expected) return min_gq;
         const int a_key = (int)((double)non_allele_obs + 1.0);
+        if (gq_tail_table != nullptr && vq == capped_vq && total_cov < kGqTailMaxCov && a_key >= 1 && a_key < kGqTailMaxA)
+            return reinterpret_cast<const int*>(gq_tail_table + kGqTailMaxCov * kGqTailMaxA)[total_cov * kGqTailMaxA + a_key];
         const double p2 = (gq_tail_table != nullptr && total_cov < kGqTailMaxCov && a_key >= 1 && a_key < kGqTailMaxA)
                               ? gq_tail_table[total_cov * kGqTailMaxA + a_key]
                               : pisces_poisson_cdf((double)non_allele_obs, (double)expected);
