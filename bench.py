@@ -255,8 +255,11 @@ def main_ours(a):
     sampler.start()
     ev0.record()
     t0 = time.perf_counter()
+    blocks = []   # hot-kernel time of every 10 timed steps (the library's own CUDA events): shows a machine-state change inside the timed region
     for k in range(a.steps):
         n_records = step(k)
+        if (k + 1) % 10 == 0 or k + 1 == a.steps:
+            blocks.append(sm.stats())
     gather_job()
     barrier()
     ev1.record()
@@ -265,7 +268,8 @@ def main_ours(a):
     dt = ev0.elapsed_time(ev1) * 1e-3   # device clock between the two synchronised brackets (the wall clock beside it: wall_ms_per_step)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
-    st = sm.stats()
+    st = {k: sum(b[k] for b in blocks) for k in ("hot_launches", "hot_ms", "total_launches")}
+    per_block = sorted(b["hot_ms"] / max(1, b["hot_launches"]) for b in blocks)
     tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -306,7 +310,10 @@ def main_ours(a):
                          "kernel": kernel_name, "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_entry": 3 if third_byte else 2,
                          "staged_bytes_per_entry": 1.5 if nib else (3 if third_byte else 2),
                          "dram_frac": (traffic / (hot_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                         "kernel_ms": hot_ms},
+                         "kernel_ms": hot_ms,
+                         # the same kernel over blocks of 10 timed steps: on this pool the kernel runs at one of two plateaus (x1.0 / x1.5) that
+                         # switch on a seconds scale with no clock change or throttle reason reported (profiles/r1_summary.md, "machine state")
+                         "kernel_ms_blocks": {"min": per_block[0], "median": per_block[len(per_block) // 2], "max": per_block[-1]}},
             "clocks": sampler.summary()}
 
     # ---- end to end through the C ABI with HOST buffers: pinned H2D of the step's pileup, tile staging, call, D2H of the records
