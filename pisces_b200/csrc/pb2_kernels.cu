@@ -1371,7 +1371,10 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
     if (out.counts_out == nullptr && in.nib != nullptr && !want_q && !coll && cfg.tune_prefetch != 9) {
         // the hot path: PNIB16 (direction-split, nibble-packed); planes needed = bits of the largest (byte lane, allele) count = stored / 4
         const int need = in.nib_max_store / 4 + 2;
-        const bool pair = cfg.output_gvcf != 0;
+        // two sub-tiles per draw in both modes: the single-tile instance (--tune-prefetch 5, VCF mode only) is 10 % faster when the memory system is in its
+        // fast state (0.170 against 0.187 ms) but waits on the tile-counter atomic twice as often and falls to 0.256 ms in the slow state this pool's
+        // boxes are often in (profiles/r1_summary.md, "machine state"); the paired instance measures 0.187 ms in that state
+        const bool pair = cfg.output_gvcf != 0 || cfg.tune_prefetch != 5;
         const int grid = max(1, min(num_sms * 4, (in.n_nib_tiles + (pair ? 15 : 7)) / (pair ? 16 : 8)));
         if (need < (1 << 8)) {
             if (pair) pileup_nib_score_kernel<8, true><<<grid, 256, 0, stream>>>(in, ex, out, cfg, tile_counter);
