@@ -1296,7 +1296,7 @@ pileup_nib_score_kernel(const __grid_constant__ TilePileup in, const __grid_cons
         // the next piece of work is taken before this one is finished; in gVCF mode, where finishing means a q-score / strand-bias / genotype chain per
         // locus during which the warp has no loads in flight, the head of the next pair (2 x 8 KB) is pulled into L2 meanwhile
         next_pair = grab();
-        if (kPair && cfg.tune_prefetch != 8) {
+        if (kPair && cfg.output_gvcf && cfg.tune_prefetch != 8) {   // VCF mode: the prefetch costs 0.186 against 0.177 ms (measured)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int t = 2 * next_pair + h;
