@@ -72,6 +72,14 @@ public:
         return out;
     }
     void DoneProcessing() { check(pb2_reset(h_)); }
+    // VcfFileWriter's record lines for called alleles (src/lib/Pisces.IO/VcfFileWriter.cs:177-260): options.crushed = !AllowMultipleVcfLinesPerLoci,
+    // options.pad_intervals replays RegionMapper. `ext` (pb2_flush_ext) may be null.
+    std::string FormatVcf(const pb2_call_record* records, const pb2_call_record_ext* ext, int64_t n, const pb2_vcf_options& options) {
+        const char* text = nullptr;
+        int64_t len = 0;
+        check(pb2_vcf_format(h_, records, ext, n, &options, &text, &len));
+        return std::string(text, (size_t)len);
+    }
     pb2_handle* handle() { return h_; }
 
     void PushBuffered() {
