@@ -101,6 +101,9 @@ def lib():
         L.po_vq.argtypes = [C.c_int32] * 4
         L.po_pvalue.argtypes = [C.c_int32] * 3
         L.po_pvalue.restype = C.c_double
+        L.po_amplicon_bias.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.c_void_p]
+        L.po_amplicon_bias.restype = C.c_int32
         L.po_poisson_cdf.argtypes = [C.c_double, C.c_double]
         L.po_poisson_cdf.restype = C.c_double
         L.po_mathnet_gamma_lower_regularized.argtypes = [C.c_double, C.c_double]
@@ -312,3 +315,22 @@ def strand_bias(cov, sup, q_noise, min_vf=0.01, acceptance=0.5, model=1):
         o = out[5 + 6 * i: 11 + 6 * i]
         res[n] = dict(fn=o[0], fp=o[1], vg=o[2], coverage=o[3], frequency=o[4], support=o[5])
     return res
+
+
+def amplicon_bias(support, coverage, acceptance=0.01, max_qscore=100):
+    """AmpliconBiasCalculator.CalculateAmpliconBias on (names, counts) pairs; names are ints (-1 = null), support names None = null array.
+    Returns None for a null result, else dict(bias_detected, artifact, per_amplicon=[dict(...)])."""
+    import numpy as np
+    sn, sc = support
+    cn, cc = coverage
+    ns = -1 if sn is None else len(sn)
+    a = lambda v: np.ascontiguousarray(v if v is not None and len(v) else [0], dtype=np.int32)   # noqa: E731
+    sn_, sc_, cn_, cc_ = a(sn), a(sc), a(cn), a(cc)
+    per = np.zeros((max(len(cn), 1), 8), dtype=np.float64)
+    bd, art = C.c_int32(0), C.c_int32(-1)
+    n = lib().po_amplicon_bias(sn_.ctypes.data, sc_.ctypes.data, ns, cn_.ctypes.data, cc_.ctypes.data, len(cn), acceptance, max_qscore, C.byref(bd),
+                               C.byref(art), per.ctypes.data)
+    if n < 0:
+        return None
+    keys = ("name", "frequency", "coverage", "observed_support", "expected_support", "chance_its_real", "qscore", "bias_detected")
+    return dict(bias_detected=bool(bd.value), artifact=art.value, per_amplicon=[dict(zip(keys, per[i])) for i in range(n)])

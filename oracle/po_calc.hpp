@@ -271,4 +271,61 @@ inline bool RMxNShouldFilter(const CalledAllele& a, const Config& cfg, const std
 // ------------------------------------------------------------------ AlleleProcessor.cs
 int ComputeIndelRepeatLength(const CalledAllele& allele, const std::string& referenceBases);  // :80-213, po_caller.hpp
 
+// ---------------------------------------------------------------- AmpliconBiasCalculator.cs (src/lib/Pisces.Calculators/AmpliconBiasCalculator.cs)
+// Amplicon names are small integers here (a host-side dictionary of the XN tag strings, Read.cs:479-495); -1 stands for a null name.
+struct AmpliconBiasEntry {   // AmpliconBiasResult (Models/AmpliconCounts.cs:13-23)
+    int name = -1;
+    double frequency = 0, coverage = 0, observedSupport = 0, expectedSupport = 0, chanceItsReal = 0;
+    int confidenceQScore = 0;
+    bool biasDetected = false;
+};
+struct AmpliconBiasResults {  // BiasResultsAcrossAmplicons (:6-11); isNull: CalculateAmpliconBias returned null
+    bool isNull = true, biasDetected = false;
+    int ampliconWithCandidateArtifact = -1;
+    std::vector<AmpliconBiasEntry> results;   // Dictionary enumeration order = insertion order
+};
+inline int CsDoubleToInt(double v) { return (v > -2147483649.0 && v < 2147483648.0) ? (int)v : (int)0x80000000; }   // (int)double of the CLR on x64
+// CalculateAmpliconBias (:45-133). Arrays may be shorter than Constants.MaxNumOverlappingAmplicons (RegionState.GetCountsByAmpliconForPosition trims
+// them, RegionState.cs:325-352); nSupport < 0 stands for a null AmpliconNames array.
+inline AmpliconBiasResults CalculateAmpliconBias(const int* supportNames, const int* supportCounts, int nSupport, const int* coverageNames, const int* coverageCounts,
+                                                 int nCoverage, float acceptanceCriteria, int maxQScore) {
+    const int MinNumObservations = 5;             // Constants (:15-19)
+    const double FreePassObservationFreq = 0.1;
+    AmpliconBiasResults out;
+    if (nSupport <= 0 || supportNames[0] < 0) return out;   // :50-54
+    if (nCoverage < 2) return out;                           // :57-59
+    out.isNull = false;
+    double maxFreq = 0.0;
+    for (int i = 0; i < nCoverage; i++) {                    // :64-82
+        const int name = coverageNames[i];
+        if (name < 0) break;
+        double support = 0;                                  // AmpliconCounts.GetCountsForAmplicon (AmpliconCounts.cs:74-81): first equal name, else 0
+        for (int k = 0; k < nSupport; k++) if (supportNames[k] == name) { support = supportCounts[k]; break; }
+        const double coverage = coverageCounts[i];
+        const double freq = (coverage > 0) ? support / coverage : 0;
+        if (freq >= maxFreq) { out.ampliconWithCandidateArtifact = name; maxFreq = freq; }
+        AmpliconBiasEntry e;
+        e.name = name; e.frequency = freq; e.observedSupport = support; e.coverage = coverage;
+        out.results.push_back(e);
+    }
+    bool shouldFailVariant = false;
+    for (auto& e : out.results) {                            // :84-129
+        int qScore = 0;
+        bool biasDetected = false;
+        const float allowableProb = acceptanceCriteria;
+        const double expectedNumObservationsOfVariant = maxFreq * e.coverage;
+        double pChanceItsReal = 1.0;
+        if (expectedNumObservationsOfVariant < MinNumObservations) qScore = maxQScore;
+        else if ((expectedNumObservationsOfVariant <= e.observedSupport) || (e.frequency > FreePassObservationFreq)) qScore = maxQScore;
+        else {
+            pChanceItsReal = std::max(0.0, pisces_poisson::Cdf(e.observedSupport, expectedNumObservationsOfVariant));
+            qScore = CsDoubleToInt(PtoQ(1.0 - pChanceItsReal));
+        }
+        if (pChanceItsReal < (double)allowableProb) { biasDetected = true; shouldFailVariant = true; }
+        e.chanceItsReal = pChanceItsReal; e.confidenceQScore = qScore; e.biasDetected = biasDetected; e.expectedSupport = expectedNumObservationsOfVariant;
+        out.biasDetected = shouldFailVariant;
+    }
+    return out;
+}
+
 }  // namespace po

@@ -227,6 +227,20 @@ double po_raw_vq(int32_t k, int32_t n, int32_t nl) { return AssignRawPoissonQSco
 int32_t po_vq(int32_t k, int32_t n, int32_t nl, int32_t max_q) { return AssignPoissonQScore(k, n, nl, max_q); }
 double po_pvalue(int32_t k, int32_t n, int32_t nl) { return AssignPValue(k, n, nl); }
 double po_poisson_cdf(double k, double lambda) { return pisces_poisson::Cdf(k, lambda); }
+int32_t po_amplicon_bias(const int32_t* sn, const int32_t* sc, int32_t ns, const int32_t* cn, const int32_t* cc, int32_t nc, float acceptance, int32_t max_q,
+                         int32_t* bias_detected, int32_t* artifact, double* per_amp) {
+    const AmpliconBiasResults r = CalculateAmpliconBias(sn, sc, ns, cn, cc, nc, acceptance, max_q);
+    if (r.isNull) return -1;
+    if (bias_detected) *bias_detected = r.biasDetected ? 1 : 0;
+    if (artifact) *artifact = r.ampliconWithCandidateArtifact;
+    for (size_t i = 0; per_amp && i < r.results.size(); i++) {
+        const AmpliconBiasEntry& e = r.results[i];
+        double* o = per_amp + 8 * i;
+        o[0] = e.name; o[1] = e.frequency; o[2] = e.coverage; o[3] = e.observedSupport; o[4] = e.expectedSupport; o[5] = e.chanceItsReal;
+        o[6] = e.confidenceQScore; o[7] = e.biasDetected ? 1 : 0;
+    }
+    return (int32_t)r.results.size();
+}
 double po_mathnet_gamma_lower_regularized(double a, double x) { return mathnet::GammaLowerRegularized(a, x); }
 double po_mathnet_gamma_ln(double z) { return mathnet::GammaLn(z); }
 void po_strand_bias(const int32_t cov[3], const int32_t sup[3], int32_t q, double min_vf, double acc, int32_t model, double* out) {

@@ -107,6 +107,11 @@ int32_t po_somatic_gq(int32_t type, int32_t genotype, int32_t vq, int32_t total_
 int32_t po_somatic_genotype(int32_t type, int32_t total_coverage, int32_t allele_support, int32_t ref_support, float min_freq_filter, int32_t min_depth);
 /* germline genotypers (po_genotype.hpp) */
 double po_mathnet_binomial_cdf(double p, int32_t n, double x);
+/* AmpliconBiasCalculator.CalculateAmpliconBias (AmpliconBiasCalculator.cs:45-133); names are ints, -1 = null, n_support < 0 = null array. Returns -1 for a
+ * null result, else the number of amplicons; per_amp[i] = {name, frequency, coverage, observedSupport, expectedSupport, chanceItsReal, qScore, biasDetected} */
+int32_t po_amplicon_bias(const int32_t* support_names, const int32_t* support_counts, int32_t n_support, const int32_t* coverage_names,
+                         const int32_t* coverage_counts, int32_t n_coverage, float acceptance, int32_t max_qscore, int32_t* bias_detected,
+                         int32_t* artifact_amplicon, double* per_amp /* [n_coverage][8] */);
 double po_mathnet_binomial_probability_ln(double p, int32_t n, int32_t k);
 int32_t po_diploid_gq(int32_t genotype, int32_t total_coverage, int32_t allele_support, int32_t min_gq, int32_t max_gq);
 int32_t po_haploid_gq(int32_t genotype, int32_t total_coverage, int32_t allele_support, int32_t min_gq, int32_t max_gq);
