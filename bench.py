@@ -296,8 +296,8 @@ def main_ours(a):
     kernel_name = "pileup_nib_score_kernel" if nib else "pileup_vcount_score_kernel"
     traffic = None
     try:   # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture of this command (default workload only)
-        if not a.gvcf and a.loci == 1_000_000 and a.depth == 500:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[kernel_name]["dram_bytes_per_launch"]
+        if a.loci == 1_000_000 and a.depth == 500 and a.indel_rate == 0.001 and (nib or not a.gvcf):
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[kernel_name + ("_gvcf" if a.gvcf else "")]["dram_bytes_per_launch"]
     except Exception:
         pass
 
