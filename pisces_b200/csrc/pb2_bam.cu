@@ -30,6 +30,9 @@ struct pb2_bam_reader {
     std::vector<int64_t> cigar_off, seq_off;
     std::vector<uint32_t> cigar;
     std::vector<uint8_t> bases, quals, base_dirs, collapsed;
+    std::vector<int32_t> amplicon_id;                    // per read of the batch: index into amplicon_names, -1 without an XN tag
+    std::vector<std::string> amplicon_names;             // the file's amplicon names in first-seen order (kept reads only)
+    std::vector<const char*> amplicon_name_ptrs;
     // a record read ahead that belongs to the next chromosome
     std::vector<uint8_t> pending;
     bool have_pending = false;
@@ -84,7 +87,8 @@ int32_t rd_i32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
 uint32_t rd_u32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 std::string lower(std::string s) { for (auto& c : s) c = (char)tolower((unsigned char)c); return s; }
 
-struct Tags { bool has_xv = false, has_xw = false; int64_t xv = 0, xw = 0; bool has_xr = false, has_xd = false; std::string xr, xd; bool any = false; };
+struct Tags { bool has_xv = false, has_xw = false; int64_t xv = 0, xw = 0; bool has_xr = false, has_xd = false; std::string xr, xd; bool any = false;
+              bool has_xn = false, bad_xn = false; std::string xn; };
 Tags parse_tags(const uint8_t* p, size_t n) {
     Tags t;
     size_t i = 0;
@@ -96,6 +100,12 @@ Tags parse_tags(const uint8_t* p, size_t n) {
         bool is_int = false;
         std::string sv;
         bool is_str = false;
+        if (a == 'X' && b == 'N') {   // Read.GetAmpliconNameIfExists -> TagUtils.GetStringTag (BamCommon.cs:1182-1216): Z / H strings, A / C (upper-cased type)
+            t.has_xn = true;          // one character, anything else throws
+            const char up = (char)toupper((unsigned char)ty);
+            if (up == 'A' || up == 'C') t.xn.assign(1, (char)p[i]);
+            else if (up != 'Z' && up != 'H') t.bad_xn = true;
+        }
         switch (ty) {
             case 'c': iv = (int8_t)p[i]; i += 1; is_int = true; break;
             case 'C': iv = p[i]; i += 1; is_int = true; break;
@@ -119,6 +129,7 @@ Tags parse_tags(const uint8_t* p, size_t n) {
         else if (a == 'X' && b == 'W' && is_int) { t.has_xw = true; t.xw = iv; }
         else if (a == 'X' && b == 'R' && is_str) { t.has_xr = true; t.xr = sv; }
         else if (a == 'X' && b == 'D' && is_str) { t.has_xd = true; t.xd = sv; }
+        else if (a == 'X' && b == 'N' && is_str) t.xn = sv;
     }
     return t;
 }
@@ -179,7 +190,7 @@ extern "C" int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* flt, 
     pb2_bam_filter f;
     f.min_map_quality = 1; f.remove_duplicates = 1; f.only_proper_pairs = 0;   // BamFilterParameters.cs:7-11
     if (flt) f = *flt;
-    r->pos0.clear(); r->flag.clear(); r->cigar.clear(); r->bases.clear(); r->quals.clear(); r->base_dirs.clear(); r->collapsed.clear();
+    r->pos0.clear(); r->flag.clear(); r->cigar.clear(); r->bases.clear(); r->quals.clear(); r->base_dirs.clear(); r->collapsed.clear(); r->amplicon_id.clear();
     r->cigar_off.assign(1, 0); r->seq_off.assign(1, 0);
     bool any_dirs = false, any_coll = false;
     int64_t skipped = 0;
@@ -211,6 +222,13 @@ extern "C" int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* flt, 
         if (batch_ref == -2) batch_ref = ref_id;
         else if (ref_id != batch_ref) { r->pending.swap(rec); r->have_pending = true; break; }   // the next chromosome starts: its reads go to the next batch
         const Tags t = parse_tags(p + o_tags, rec.size() - o_tags);
+        if (t.bad_xn) return bfail(r, "Found an unexpected string BAM tag data type while looking for a tag (XN)");
+        int32_t amp = -1;
+        if (t.has_xn) {
+            for (size_t k = 0; k < r->amplicon_names.size() && amp < 0; k++) if (r->amplicon_names[k] == t.xn) amp = (int32_t)k;
+            if (amp < 0) { amp = (int32_t)r->amplicon_names.size(); r->amplicon_names.push_back(t.xn); }
+        }
+        r->amplicon_id.push_back(amp);
         r->pos0.push_back(pos);
         r->flag.push_back((uint16_t)flag);
         for (uint32_t k = 0; k < n_cig; k++) r->cigar.push_back(rd_u32(p + o_cig + 4 * k));
@@ -262,5 +280,22 @@ extern "C" int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* flt, 
     batch->collapsed = any_coll ? r->collapsed.data() : nullptr;
     if (ref_id_out) *ref_id_out = batch_ref == -2 ? -1 : batch_ref;
     if (n_skipped) *n_skipped = skipped;
+    return PB2_OK;
+}
+
+// Amplicon names of the reads (the XN tag, Read.GetAmpliconNameIfExists, src/lib/Pisces.Domain/Models/Read.cs:479-486): ids of the reads of the batch
+// handed out last, and the file's dictionary so far (first-seen order over the kept reads). Input of the amplicon-bias row.
+extern "C" int pb2_bam_batch_amplicons(pb2_bam_reader* r, const int32_t** amplicon_id, int32_t* n_reads) {
+    if (!r || !amplicon_id || !n_reads) return PB2_ERR_ARG;
+    *amplicon_id = r->amplicon_id.data();
+    *n_reads = (int32_t)r->amplicon_id.size();
+    return PB2_OK;
+}
+extern "C" int pb2_bam_amplicon_names(pb2_bam_reader* r, int32_t* n, const char* const** names) {
+    if (!r || !n || !names) return PB2_ERR_ARG;
+    r->amplicon_name_ptrs.clear();
+    for (auto& s : r->amplicon_names) r->amplicon_name_ptrs.push_back(s.c_str());
+    *n = (int32_t)r->amplicon_names.size();
+    *names = r->amplicon_name_ptrs.data();
     return PB2_OK;
 }

@@ -428,6 +428,20 @@ class BamReadStager:
                 return
             yield ref_id.value, b, skipped.value
 
+    def batch_amplicons(self):
+        """Read.GetAmpliconNameIfExists of the reads of the batch fetched last: ids into amplicon_names() (-1 = no XN tag). pb2_bam_batch_amplicons."""
+        p, n = C.POINTER(C.c_int32)(), C.c_int32()
+        if self._L.pb2_bam_batch_amplicons(self._r, C.byref(p), C.byref(n)) != 0:
+            raise PiscesB200Error(N_ERR_ARG, "pb2_bam_batch_amplicons failed")
+        return [int(p[i]) for i in range(n.value)]
+
+    def amplicon_names(self):
+        """The file's amplicon names so far, in first-seen order over the kept reads. pb2_bam_amplicon_names."""
+        n, names = C.c_int32(), C.POINTER(C.c_char_p)()
+        if self._L.pb2_bam_amplicon_names(self._r, C.byref(n), C.byref(names)) != 0:
+            raise PiscesB200Error(N_ERR_ARG, "pb2_bam_amplicon_names failed")
+        return [names[i].decode() for i in range(n.value)]
+
     def close(self):
         if self._r:
             self._L.pb2_bam_close(self._r)

@@ -81,3 +81,33 @@ def test_collapsed_stitched_bam_tags():
         has = "XV" in t or "XW" in t
         duplex = bool(t.get("XV")) and bool(t.get("XW"))
         assert int(b["coll"][k]) == (1 if has else 0) | (2 if duplex else 0) | ({"FR": 1, "RF": 2}.get(t.get("XR"), 0) << 2)
+
+
+def test_amplicon_names_from_the_xn_tag():
+    """Read.GetAmpliconNameIfExists (Read.cs:479-486) through pb2_bam_batch_amplicons / pb2_bam_amplicon_names on the mapped reads of the reference's
+    testdata/example_S1.bam (tests/golden/example_S1.mapped.bam, written by tests/golden/make_amplicon_fixture.py): per-read names equal the XN tags the
+    Python decoder reads, the dictionary is in first-seen order over the kept reads, across batch boundaries."""
+    import pisces_b200 as pb
+    path = os.path.join(G, "example_S1.mapped.bam")
+    _, _, recs = bamio.read_bam(path)
+    kept = _kept(recs)
+    assert len(kept) > 300 and all("XN" in r["tags"] for r in kept)
+    for max_reads in (65536, 50):
+        st = pb.BamReadStager(path, max_reads=max_reads)
+        got = []
+        for _ref_id, b, _skipped in st:
+            ids = st.batch_amplicons()
+            assert len(ids) == b.n_reads
+            names = st.amplicon_names()
+            got += [names[i] if i >= 0 else None for i in ids]
+        names = st.amplicon_names()
+        st.close()
+        assert got == [r["tags"]["XN"] for r in kept]
+        first_seen = list(dict.fromkeys(got))
+        assert names == first_seen and len(names) == 8
+    # a file without the tag: every id is -1, the dictionary stays empty
+    st = pb.BamReadStager(os.path.join(G, "PhiX_S3.bam"))
+    for _ref_id, b, _skipped in st:
+        assert set(st.batch_amplicons()) == {-1}
+    assert st.amplicon_names() == []
+    st.close()
