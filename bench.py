@@ -218,7 +218,10 @@ def main_ours(a):
     n_slots = max(1, a.steps)
     if world > 1:
         n0 = sm.call_resident()
-        cap_records = (n0 + n0 // 8 + 127) // 64 * 64   # fixed capacity of a step's block: its record count plus 12 % head-room
+        n0_all = torch.tensor([n0], dtype=torch.int64, device=dev)
+        dist.all_reduce(n0_all, op=dist.ReduceOp.MAX)    # the ranks' shards differ: the block capacity (hence the gathered size) must be the same on all
+        n0 = int(n0_all.item())
+        cap_records = (n0 + n0 // 8 + 127) // 64 * 64   # fixed capacity of a step's block: the largest shard's record count plus 12 % head-room
         vr, nv = C.c_void_p(), C.c_int64()
         sm._chk(sm._L.pb2_resident_results(sm._h, None, None, None, C.byref(vr), C.byref(nv)))
         var_view = torch.as_tensor(DevBuf(vr.value, cap_records * 96), device=dev)
