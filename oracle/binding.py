@@ -101,6 +101,8 @@ def lib():
         L.po_vq.argtypes = [C.c_int32] * 4
         L.po_pvalue.argtypes = [C.c_int32] * 3
         L.po_pvalue.restype = C.c_double
+        L.po_exact_spanning_read_direction.argtypes = [C.c_int32] * 5 + [C.c_char_p, C.c_char_p]
+        L.po_exact_spanning_read_direction.restype = C.c_int32
         L.po_amplicon_bias.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.c_void_p]
         L.po_amplicon_bias.restype = C.c_int32
@@ -334,3 +336,11 @@ def amplicon_bias(support, coverage, acceptance=0.01, max_qscore=100):
         return None
     keys = ("name", "frequency", "coverage", "observed_support", "expected_support", "chance_its_real", "qscore", "bias_detected")
     return dict(bias_detected=bool(bd.value), artifact=art.value, per_amplicon=[dict(zip(keys, per[i])) for i in range(n)])
+
+
+def exact_spanning_read_direction(allele_type, start, end, cigar, directions, position=10, allele_length=4):
+    """ExactCoverageCalculator on one ReadCoverageSummary: 0 Forward / 1 Reverse / 2 Stitched, or None when the read does not contribute."""
+    r = lib().po_exact_spanning_read_direction(allele_type, position, allele_length, start, end, cigar.encode(), directions.encode())
+    if r < -1:
+        raise ValueError(f"po_exact_spanning_read_direction: {r}")
+    return None if r == -1 else r

@@ -2,6 +2,7 @@
 #include "po_capi.h"
 #include <cstring>
 #include "po_caller.hpp"
+#include "po_exact_coverage.hpp"
 
 using namespace po;
 
@@ -227,6 +228,21 @@ double po_raw_vq(int32_t k, int32_t n, int32_t nl) { return AssignRawPoissonQSco
 int32_t po_vq(int32_t k, int32_t n, int32_t nl, int32_t max_q) { return AssignPoissonQScore(k, n, nl, max_q); }
 double po_pvalue(int32_t k, int32_t n, int32_t nl) { return AssignPValue(k, n, nl); }
 double po_poisson_cdf(double k, double lambda) { return pisces_poisson::Cdf(k, lambda); }
+int32_t po_exact_spanning_read_direction(int32_t type, int32_t pos, int32_t len, int32_t start, int32_t end, const char* cigar, const char* dirs) {
+    std::vector<CigarOp> ops;
+    std::vector<std::pair<int, DirectionType>> d;
+    int num = 0;
+    for (const char* c = cigar; *c; c++) {
+        if (*c >= '0' && *c <= '9') num = num * 10 + (*c - '0');
+        else { ops.push_back(CigarOp{*c, (uint32_t)num}); num = 0; }
+    }
+    num = 0;
+    for (const char* c = dirs; *c; c++) {
+        if (*c >= '0' && *c <= '9') num = num * 10 + (*c - '0');
+        else if (*c != ':') { d.push_back({num, *c == 'F' ? Forward : *c == 'R' ? Reverse : Stitched}); num = 0; }
+    }
+    return ExactSpanningReadDirection((AlleleCategory)type, pos, len, start, end, ops, d);
+}
 int32_t po_amplicon_bias(const int32_t* sn, const int32_t* sc, int32_t ns, const int32_t* cn, const int32_t* cc, int32_t nc, float acceptance, int32_t max_q,
                          int32_t* bias_detected, int32_t* artifact, double* per_amp) {
     const AmpliconBiasResults r = CalculateAmpliconBias(sn, sc, ns, cn, cc, nc, acceptance, max_q);

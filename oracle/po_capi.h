@@ -107,6 +107,10 @@ int32_t po_somatic_gq(int32_t type, int32_t genotype, int32_t vq, int32_t total_
 int32_t po_somatic_genotype(int32_t type, int32_t total_coverage, int32_t allele_support, int32_t ref_support, float min_freq_filter, int32_t min_depth);
 /* germline genotypers (po_genotype.hpp) */
 double po_mathnet_binomial_cdf(double p, int32_t n, double x);
+/* ExactCoverageCalculator (ExactCoverageCalculator.cs:18-109), one spanning read summary: cigar as "5M4I4M", directions as "2F:9S:2R" (DirectionInfo.cs:15-33).
+ * Returns the DirectionType the read's coverage goes to, -1 if it does not contribute, -2 for single-point allele types, -3 where the reference throws. */
+int32_t po_exact_spanning_read_direction(int32_t allele_type, int32_t reference_position, int32_t allele_length, int32_t clip_adjusted_start,
+                                         int32_t clip_adjusted_end, const char* cigar, const char* direction_string);
 /* AmpliconBiasCalculator.CalculateAmpliconBias (AmpliconBiasCalculator.cs:45-133); names are ints, -1 = null, n_support < 0 = null array. Returns -1 for a
  * null result, else the number of amplicons; per_amp[i] = {name, frequency, coverage, observedSupport, expectedSupport, chanceItsReal, qScore, biasDetected} */
 int32_t po_amplicon_bias(const int32_t* support_names, const int32_t* support_counts, int32_t n_support, const int32_t* coverage_names,
