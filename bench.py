@@ -57,7 +57,18 @@ class ClockSampler(threading.Thread):
         try:
             import pynvml as nv
             nv.nvmlInit()
-            self.hd = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.hd = None
+            try:   # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES re-maps the devices: go through the UUID
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.gpu).uuid)
+                try:
+                    self.hd = nv.nvmlDeviceGetHandleByUUID(uuid)
+                except TypeError:
+                    self.hd = nv.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.hd = None
+            if self.hd is None:
+                self.hd = nv.nvmlDeviceGetHandleByIndex(self.gpu)
             self.mx = nv.nvmlDeviceGetMaxClockInfo(self.hd, nv.NVML_CLOCK_SM)
             self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
             self.nv = nv
