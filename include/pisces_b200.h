@@ -94,7 +94,10 @@ typedef struct pb2_config {
 
 /* Reads for IStateManager.AddAlleleCounts(Read) / ICandidateVariantFinder.FindCandidates(Read, ...), as a struct of arrays. Only
  * reads that passed AlignmentSource.ShouldSkipRead (src/exe/Pisces/Logic/Alignment/AlignmentsSource.cs:84-92) are pushed; they must
- * arrive in position order like the BAM. Bases are upper-case ASCII (BamReader.cs:185-201). */
+ * arrive in position order like the BAM. Bases are upper-case ASCII (BamReader.cs:185-201). cigar_off / seq_off need not start at 0 (a batch may be
+ * a window of larger arrays). base_dirs / collapsed may be given for some batches and not for others: reads pushed without them get the values
+ * their flag implies. The arrays are copied to the device with cudaMemcpyAsync before the call returns: page-locked (pinned) arrays are copied at the
+ * full rate of the link. */
 typedef struct pb2_read_batch {
     int32_t n_reads;
     const int32_t*  pos0;        /* [n] BamAlignment.Position (0-based) */
@@ -211,6 +214,11 @@ int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p);
 /* IStateManager.AddAlleleCounts + FindCandidates for a batch of reads: the reads are kept by the handle until a pb2_flush clears the
  * positions they cover; the pileup is built on the device (read expansion, bucketing to loci, tile interleave). */
 int pb2_push_reads(pb2_handle* h, const pb2_read_batch* batch);
+
+/* Stages everything pushed through pb2_push_reads so far as one device-resident segment (the pileup is built on the device from the reads the handle
+ * keeps there), so that pb2_call_resident / pb2_resident_results run on it: the whole-chromosome form of IStateManager for hosts that push all reads
+ * first (bench.py, multi-GPU shards). The reads stay staged; a later pb2_flush re-stages what it needs and supersedes this segment. */
+int pb2_stage_reads(pb2_handle* h);
 
 /* IAlleleSource.AddCandidates: explicit candidates for the staged positions (the locus-major path has no reads to find them in; a host
  * that keeps its own ICandidateVariantFinder uses this too). Candidates equal in (position, type, ref, alt[, open ends when Collapse is on])

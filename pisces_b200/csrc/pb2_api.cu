@@ -33,6 +33,12 @@ struct Trace {
     }
 };
 
+#include <nvtx3/nvToolsExt.h>
+struct nvtx_range {   // NVTX ranges around push / stage / resident step / flush (tracing hook)
+    explicit nvtx_range(const char* name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+};
+
 #define CU(h, expr)                                                                                      \
     do {                                                                                                 \
         cudaError_t _e = (expr);                                                                         \
@@ -202,11 +208,12 @@ static void release_resident_graph(pb2_handle* h) {
 
 static void free_segment(pb2_handle* h, Segment& s) {
     void* ptrs[] = {s.code, s.anch, s.ref_records, s.var_records, s.pending, s.depth, s.pad, s.tile_base, s.ref_base, s.positions, s.ref_valid, s.exc_entries, s.counters,
-                    s.nib, s.nib_tile_base, s.nib_store, s.nib_depth};
+                    s.nib, s.nib_tile_base, s.nib_store, s.nib_depth, s.pv_data, s.pv_row_meta, s.pv_tile_row0, s.pv_cls_end};
     for (void* p : ptrs) pool_free(h, p);
     s = Segment();
 }
 
+static void free_reads(pb2_handle* h);
 extern "C" int pb2_reset(pb2_handle* h) {
     if (!h) return PB2_ERR_ARG;
     cudaSetDevice(h->device);
@@ -215,8 +222,8 @@ extern "C" int pb2_reset(pb2_handle* h) {
     h->segs.clear();
     h->h_out.clear();
     h->h_out_ext.clear();
-    h->reads.clear();
-    h->cands.clear(); h->block_max_endpoint.clear(); h->gapped_ref.clear(); h->triggers.clear(); h->arena.clear();
+    free_reads(h);
+    h->cands.clear(); h->cand_by_pos.clear(); h->block_max_endpoint.clear(); h->gapped_ref.clear(); h->triggers.clear(); h->arena.clear();
     h->last_trigger_key = 0; h->push_last_key = 0; h->cleared_through = 0;
     h->snv_explicit_ranges.clear();
     rearm_forced(h);
@@ -524,7 +531,8 @@ static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32
     if (reset_counters) CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 3, st));
     // inside a stream capture the timing events must be external event-record nodes to be readable with cudaEventElapsedTime
     CU(h, cudaEventRecordWithFlags(h->ev0, st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-    CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, s.max_depth, st));
+    if (s.pv_data != nullptr) CU(h, launch_pvert_hot_kernel(pvert_view(s), ex, out, h->dcfg, h->num_sms, h->d_tile_counter, st));
+    else CU(h, launch_hot_kernel(in, ex, out, h->dcfg, h->num_sms, h->d_tile_counter, s.max_depth, st));
     CU(h, cudaEventRecordWithFlags(h->ev1, st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     return PB2_OK;
 }
@@ -551,44 +559,132 @@ static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* 
     return rc != PB2_OK ? rc : finish_segment(h, s);
 }
 
+// ------------------------------------------------------------------------------------------------ the device read store
+template <class T>
+static cudaError_t grow(pb2_handle* h, GrowBuf<T>& b, size_t need, size_t keep) {
+    if (need <= b.cap) return cudaSuccess;
+    const size_t ncap = std::max(need, b.cap + b.cap / 2 + 64);
+    T* np = nullptr;
+    cudaError_t e = pool_alloc_t(h, &np, ncap);
+    if (e != cudaSuccess) return e;
+    if (b.p && keep) e = cudaMemcpyAsync(np, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, h->stream);
+    pool_free(h, b.p);
+    b.p = np; b.cap = ncap;
+    return e;
+}
+static void free_reads(pb2_handle* h) {
+    DeviceReads& R = h->reads;
+    void* ptrs[] = {R.pos0.p, R.end_pos.p, R.flag.p, R.cigar_off.p, R.seq_off.p, R.cigar.p, R.bases.p, R.quals.p, R.base_dirs.p, R.collapsed.p};
+    for (void* p : ptrs) pool_free(h, p);
+    h->reads = DeviceReads();
+}
+// per-base directions of reads pushed without base_dirs: the read's own direction (Read.cs:390-421 without an XD tag)
+__global__ static void dirs_from_flags_kernel(const uint16_t* __restrict__ flag, const int64_t* __restrict__ seq_off, int64_t r0, int64_t r1, uint8_t* __restrict__ dirs) {
+    const int64_t r = r0 + blockIdx.x;
+    if (r >= r1) return;
+    const uint8_t d = (flag[r] & 0x10) ? DIR_R : DIR_F;
+    for (int64_t k = seq_off[r] + threadIdx.x; k < seq_off[r + 1]; k += blockDim.x) dirs[k] = d;
+}
+
 extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
     if (!h || !b || b->n_reads < 0) return fail(h, PB2_ERR_ARG, "pb2_push_reads: bad argument");
     if (b->n_reads == 0) return PB2_OK;
     if (!b->pos0 || !b->flag || !b->cigar_off || !b->cigar || !b->seq_off || !b->bases || !b->quals) return fail(h, PB2_ERR_ARG, "pb2_push_reads: null array");
-    HostReads& R = h->reads;
-    const size_t first_new = R.size();
-    if (R.size() == 0) { R.has_dirs = b->base_dirs != nullptr; R.has_collapsed = b->collapsed != nullptr; }
-    else if (R.has_dirs != (b->base_dirs != nullptr) || R.has_collapsed != (b->collapsed != nullptr))
-        return fail(h, PB2_ERR_ARG, "pb2_push_reads: base_dirs / collapsed must be given for all batches or none");
-    static const bool ref_span[16] = {1, 0, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0}, read_span[16] = {1, 1, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < b->n_reads; i++) {
-        const int64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1], s0 = b->seq_off[i], s1 = b->seq_off[i + 1];
-        if (c1 < c0 || s1 < s0) return fail(h, PB2_ERR_ARG, "pb2_push_reads: offsets not monotone");
-        if (b->pos0[i] < 0) return fail(h, PB2_ERR_ARG, "Position must be greater than 0.");   // RegionStateManager.cs:363-364
-        int64_t rs = 0, fs = 0;
-        for (int64_t k = c0; k < c1; k++) {
-            const uint32_t c = b->cigar[k];
-            if ((c & 15) > 8) return fail(h, PB2_ERR_ARG, "pb2_push_reads: bad CIGAR operation");
-            if (read_span[c & 15]) rs += c >> 4;
-            if (ref_span[c & 15]) fs += c >> 4;
-        }
-        if (c1 > c0 && rs != s1 - s0) return fail(h, PB2_ERR_ARG, "Invalid cigar: does not match length of read");   // Read.cs:603-605
-        R.pos0.push_back(b->pos0[i]);
-        R.end_pos.push_back(b->pos0[i] + (int32_t)fs);
-        R.flag.push_back(b->flag[i]);
-        R.cigar.insert(R.cigar.end(), b->cigar + c0, b->cigar + c1);
-        R.cigar_off.push_back((int64_t)R.cigar.size());
-        R.bases.insert(R.bases.end(), b->bases + s0, b->bases + s1);
-        R.quals.insert(R.quals.end(), b->quals + s0, b->quals + s1);
-        if (R.has_dirs) R.base_dirs.insert(R.base_dirs.end(), b->base_dirs + s0, b->base_dirs + s1);
-        R.seq_off.push_back((int64_t)R.bases.size());
-        if (R.has_collapsed) R.collapsed.push_back(b->collapsed[i]);
-        // SmallVariantCaller.Execute calls Call(read.Position - 1) after every read (:99-104); a batch forms when that enters a new block key
-        const int32_t up_to = b->pos0[i];
-        const int32_t key = up_to <= 0 ? 0 : (up_to + 999) / 1000;
-        if (key != h->push_last_key) { h->triggers.push_back(up_to); h->push_last_key = key; }
+    CU(h, cudaSetDevice(h->device));
+    nvtx_range nv("pb2_push_reads");
+    Trace tr("push_reads");
+    DeviceReads& R = h->reads;
+    cudaStream_t st = h->stream;
+    const int64_t nb = b->n_reads;
+    const int64_t c_lo = b->cigar_off[0], c_hi = b->cigar_off[nb], s_lo = b->seq_off[0], s_hi = b->seq_off[nb];
+    if (c_hi < c_lo || s_hi < s_lo) return fail(h, PB2_ERR_ARG, "pb2_push_reads: offsets not monotone");
+    if (R.n + nb > INT32_MAX) return fail(h, PB2_ERR_ARG, "pb2_push_reads: more than 2^31 reads staged");
+    const int64_t first = R.n, ncig = c_hi - c_lo, nseq = s_hi - s_lo;
+    // per-base directions / collapsed summaries: optional per batch. Once any batch carried them the store holds them for every read (a stitched or
+    // collapsed BAM streamed in small batches mixes tagged and untagged reads): reads pushed without get the flag-derived defaults.
+    const bool want_dirs = R.has_dirs || b->base_dirs != nullptr, want_coll = R.has_collapsed || b->collapsed != nullptr;
+    CU(h, grow(h, R.pos0, (size_t)(first + nb), (size_t)first));
+    CU(h, grow(h, R.end_pos, (size_t)(first + nb), (size_t)first));
+    CU(h, grow(h, R.flag, (size_t)(first + nb), (size_t)first));
+    CU(h, grow(h, R.cigar_off, (size_t)(first + nb + 1), (size_t)(first ? first + 1 : 0)));
+    CU(h, grow(h, R.seq_off, (size_t)(first + nb + 1), (size_t)(first ? first + 1 : 0)));
+    CU(h, grow(h, R.cigar, (size_t)(R.n_cigar + ncig), (size_t)R.n_cigar));
+    CU(h, grow(h, R.bases, (size_t)(R.n_seq + nseq), (size_t)R.n_seq));
+    CU(h, grow(h, R.quals, (size_t)(R.n_seq + nseq), (size_t)R.n_seq));
+    if (want_dirs) {
+        CU(h, grow(h, R.base_dirs, (size_t)(R.n_seq + nseq), R.has_dirs ? (size_t)R.n_seq : 0));
+        if (!R.has_dirs && first > 0) dirs_from_flags_kernel<<<(unsigned)first, 64, 0, st>>>(R.flag.p, R.seq_off.p, 0, first, R.base_dirs.p);
     }
-    return explicit_find_candidates(h, R, first_new);
+    if (want_coll) {
+        CU(h, grow(h, R.collapsed, (size_t)(first + nb), R.has_collapsed ? (size_t)first : 0));
+        if (!R.has_collapsed && first > 0) CU(h, cudaMemsetAsync(R.collapsed.p, 0, (size_t)first, st));
+    }
+    if (first == 0) { CU(h, cudaMemsetAsync(R.cigar_off.p, 0, sizeof(int64_t), st)); CU(h, cudaMemsetAsync(R.seq_off.p, 0, sizeof(int64_t), st)); }
+    const cudaMemcpyKind k = cudaMemcpyHostToDevice;
+    CU(h, cudaMemcpyAsync(R.pos0.p + first, b->pos0, sizeof(int32_t) * (size_t)nb, k, st));
+    CU(h, cudaMemcpyAsync(R.flag.p + first, b->flag, sizeof(uint16_t) * (size_t)nb, k, st));
+    CU(h, cudaMemcpyAsync(R.cigar_off.p + first + 1, b->cigar_off + 1, sizeof(int64_t) * (size_t)nb, k, st));
+    CU(h, cudaMemcpyAsync(R.seq_off.p + first + 1, b->seq_off + 1, sizeof(int64_t) * (size_t)nb, k, st));
+    if (ncig) CU(h, cudaMemcpyAsync(R.cigar.p + R.n_cigar, b->cigar + c_lo, sizeof(uint32_t) * (size_t)ncig, k, st));
+    if (nseq) {
+        CU(h, cudaMemcpyAsync(R.bases.p + R.n_seq, b->bases + s_lo, (size_t)nseq, k, st));
+        CU(h, cudaMemcpyAsync(R.quals.p + R.n_seq, b->quals + s_lo, (size_t)nseq, k, st));
+        if (b->base_dirs) CU(h, cudaMemcpyAsync(R.base_dirs.p + R.n_seq, b->base_dirs + s_lo, (size_t)nseq, k, st));
+    }
+    if (want_coll) {
+        if (b->collapsed) CU(h, cudaMemcpyAsync(R.collapsed.p + first, b->collapsed, (size_t)nb, k, st));
+        else CU(h, cudaMemsetAsync(R.collapsed.p + first, 0, (size_t)nb, st));
+    }
+    // ingest: offsets rebased, Read.EndPosition, validation, the batch triggers of SmallVariantCaller.Execute
+    IngestStatus* d_status = nullptr;
+    int2* d_trig = nullptr;
+    const int32_t trig_cap = (int32_t)std::min<int64_t>(nb, 1 << 22);
+    CU(h, pool_alloc_t(h, &d_status, 1));
+    CU(h, pool_alloc_t(h, &d_trig, (size_t)trig_cap));
+    IngestStatus init;
+    memset(&init, 0, sizeof(init));
+    init.min_start = INT32_MAX;
+    CU(h, cudaMemcpyAsync(d_status, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    R.n = first + nb;
+    R.has_dirs = want_dirs; R.has_collapsed = want_coll;
+    ReadsView rv = R.view();
+    CU(h, launch_reads_ingest(rv, (int32_t)first, R.n_cigar - c_lo, R.n_seq - s_lo, R.cigar_off.p, R.seq_off.p, R.end_pos.p, h->push_last_key, d_trig, trig_cap, d_status, st));
+    if (want_dirs && !b->base_dirs) dirs_from_flags_kernel<<<(unsigned)nb, 64, 0, st>>>(R.flag.p, R.seq_off.p, first, first + nb, R.base_dirs.p);
+    h->total_launches += 2;
+    IngestStatus status;
+    CU(h, cudaMemcpyAsync(&status, d_status, sizeof(status), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));   // the caller's buffers are consumed
+    tr.mark("h2d+ingest");
+    auto rollback = [&]() { R.n = first; pool_free(h, d_status); pool_free(h, d_trig); };
+    if (status.error) {
+        rollback();
+        switch (status.error) {
+            case 1: return fail(h, PB2_ERR_ARG, "pb2_push_reads: bad CIGAR operation");
+            case 2: return fail(h, PB2_ERR_ARG, "Invalid cigar: does not match length of read");   // Read.cs:603-605
+            case 3: return fail(h, PB2_ERR_ARG, "Position must be greater than 0.");               // RegionStateManager.cs:363-364
+            default: return fail(h, PB2_ERR_ARG, "pb2_push_reads: offsets not monotone");
+        }
+    }
+    if (status.n_triggers > trig_cap) { rollback(); return fail(h, PB2_ERR_UNSUPPORTED, "pb2_push_reads: reads are not in position order (more than 4 M block changes in one batch)"); }
+    if (status.n_triggers > 0) {
+        std::vector<int2> trig((size_t)status.n_triggers);
+        CU(h, cudaMemcpy(trig.data(), d_trig, sizeof(int2) * trig.size(), cudaMemcpyDeviceToHost));
+        std::sort(trig.begin(), trig.end(), [](const int2& a, const int2& b2) { return a.x < b2.x; });
+        for (auto& t : trig) h->triggers.push_back(t.y);
+    }
+    pool_free(h, d_status); pool_free(h, d_trig);
+    {
+        const int32_t last = b->pos0[nb - 1];
+        h->push_last_key = last <= 0 ? 0 : (last + 999) / 1000;
+        R.last_pos0 = last;
+    }
+    R.n_cigar += ncig; R.n_seq += nseq;
+    R.min_start = std::min(R.min_start, status.min_start);
+    R.max_end = std::max(R.max_end, status.max_end);
+    BatchHostView hv{b->bases + s_lo, b->seq_off, s_lo};
+    const int rc = explicit_find_candidates(h, (size_t)first, &hv);
+    tr.mark("candidates");
+    return rc;
 }
 
 extern "C" int pb2_totals(pb2_handle* h, int64_t* total_collapsed) {
@@ -605,12 +701,42 @@ static cudaError_t upload(T** d, const std::vector<T>& v, cudaStream_t st) {
     return e;
 }
 
-// Build a (temporary) segment from the staged reads for reference positions <= cleared_end (INT32_MAX = everything).
-static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t cleared_from) {
-    HostReads& R = h->reads;
+// the outputs every segment needs: record streams, queues, counters (the flagged-entry side list is allocated by the staging itself)
+static int alloc_segment_outputs(pb2_handle* h, Segment& s) {
+    if (h->cfg.output_gvcf) {
+        s.alloc_ref = sizeof(pb2_call_record) * (size_t)s.n_loci;
+        CU(h, pool_alloc(h, (void**)&s.ref_records, s.alloc_ref));
+        CU(h, pool_alloc_t(h, &s.ref_valid, (size_t)s.n_loci));
+    }
+    s.var_capacity = std::max<int64_t>(1024, s.n_loci);
+    s.alloc_var = sizeof(pb2_call_record) * (size_t)s.var_capacity;
+    CU(h, pool_alloc(h, (void**)&s.var_records, s.alloc_var));
+    s.pending_capacity = std::max<int64_t>(1024, s.n_loci);
+    s.alloc_pending = sizeof(PendingLocus) * (size_t)s.pending_capacity;
+    CU(h, pool_alloc(h, (void**)&s.pending, s.alloc_pending));
+    return PB2_OK;
+}
+
+// can the reads of this handle be staged in the PVERT form (pb2_pvert.cuh)?
+static bool pvert_eligible(const pb2_handle* h) {
+    return h->cfg.min_base_call_quality >= 2 && h->cfg.min_base_call_quality <= 63 && !h->cfg.want_sum_base_quality && h->cfg.noise_model != 1 && h->cfg.reserved[1] != 9;
+}
+
+PvertPileup pvert_view(const Segment& s) {
+    PvertPileup pv;
+    memset(&pv, 0, sizeof(pv));
+    pv.data = s.pv_data; pv.row_meta = s.pv_row_meta; pv.tile_row0 = s.pv_tile_row0; pv.cls_end = s.pv_cls_end; pv.n_classes = s.pv_classes;
+    pv.ref_base = s.ref_base; pv.positions = s.positions; pv.first_position = s.first_position; pv.n_loci = s.n_loci; pv.n_tiles = s.n_tiles;
+    return pv;
+}
+
+// Build a segment from the staged reads for reference positions cleared_from .. cleared_end (INT32_MAX = everything). temporary: built inside
+// pb2_flush / pb2_get_counts and freed when they return; otherwise it stays staged (pb2_stage_reads -> pb2_call_resident).
+static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t cleared_from, bool temporary = true) {
+    DeviceReads& R = h->reads;
     if (R.size() == 0) return PB2_OK;
-    int32_t lo = INT32_MAX, hi = 0;
-    for (size_t i = 0; i < R.size(); i++) { lo = std::min(lo, R.pos0[i] + 1); hi = std::max(hi, R.end_pos[i]); }
+    nvtx_range nv("stage_reads");
+    int32_t lo = R.min_start, hi = R.max_end;
     if (h->have_intervals) {   // interval positions are reported for every position of a block some read touched, covered or not
         lo = ((lo - 1) / 1000) * 1000 + 1;
         hi = (int32_t)std::min<int64_t>(((int64_t)(hi - 1) / 1000 + 1) * 1000, INT32_MAX);
@@ -618,91 +744,152 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     lo = std::max(lo, cleared_from);
     hi = std::min(hi, cleared_end);
     if (hi < lo) return PB2_OK;
+    cudaStream_t st = h->stream;
     const int64_t span = (int64_t)hi - lo + 1;
     // loci: the whole span, or — with intervals — the interval positions inside 1000-bp blocks some read touched
     // (reference candidates are only generated for existing blocks: RegionStateManager.cs:295-314, RegionState.cs:393-399)
     std::vector<int32_t> positions, index_of_pos;
     if (h->have_intervals) {
-        std::vector<uint8_t> block_touched((size_t)((hi - 1) / 1000 - (lo - 1) / 1000 + 1), 0);
-        const int b0 = (lo - 1) / 1000;
-        for (size_t i = 0; i < R.size(); i++) {
-            const int a = std::max(R.pos0[i] + 1, lo), e = std::min(R.end_pos[i], hi);
-            for (int b = (a - 1) / 1000; a <= e && b <= (e - 1) / 1000; b++) block_touched[(size_t)(b - b0)] = 1;
-        }
+        const int b0 = (lo - 1) / 1000, nbk = (hi - 1) / 1000 - b0 + 1;
+        std::vector<uint32_t> bits((size_t)(nbk + 31) / 32, 0);
+        uint32_t* d_bits = nullptr;
+        CU(h, pool_alloc_t(h, &d_bits, bits.size()));
+        CU(h, cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * bits.size(), st));
+        // block key of position p is (p + 999) / 1000 = (p - 1) / 1000 + 1
+        CU(h, launch_reads_block_bitmap(R.pos0.p, R.end_pos.p, R.n, lo - 1, b0 + 1, nbk, d_bits, st));
+        CU(h, cudaMemcpyAsync(bits.data(), d_bits, sizeof(uint32_t) * bits.size(), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        pool_free(h, d_bits);
+        auto touched = [&](int64_t p) { const int k = (int)((p - 1) / 1000) - b0; return k >= 0 && k < nbk && ((bits[(size_t)k >> 5] >> (k & 31)) & 1u); };
         index_of_pos.assign((size_t)span, -1);
         std::vector<std::pair<int32_t, int32_t>> iv;
         for (size_t i = 0; i < h->iv_start.size(); i++) iv.push_back({h->iv_start[i], h->iv_end[i]});
         std::sort(iv.begin(), iv.end());
         for (auto& v : iv)
             for (int64_t p = std::max<int64_t>(v.first, lo); p <= std::min<int64_t>(v.second, hi); p++)
-                if (index_of_pos[(size_t)(p - lo)] < 0 && block_touched[(size_t)((p - 1) / 1000 - b0)]) index_of_pos[(size_t)(p - lo)] = 0;
+                if (index_of_pos[(size_t)(p - lo)] < 0 && touched(p)) index_of_pos[(size_t)(p - lo)] = 0;
         for (int64_t k = 0; k < span; k++)
             if (index_of_pos[(size_t)k] == 0) { index_of_pos[(size_t)k] = (int32_t)positions.size(); positions.push_back((int32_t)(lo + k)); }
         if (positions.empty()) return PB2_OK;
     }
     const int64_t n_loci = h->have_intervals ? (int64_t)positions.size() : span;
-    if (!h->have_intervals && (h->chr_len < hi)) hi = hi;  // loci beyond the chromosome end keep ref base 'N' below
-
-    cudaStream_t st = h->stream;
-    int32_t *d_pos0 = nullptr, *d_index = nullptr, *d_positions = nullptr;
-    uint16_t* d_flag = nullptr;
-    int64_t *d_coff = nullptr, *d_soff = nullptr, *d_off = nullptr;
-    uint32_t* d_cigar = nullptr;
-    uint8_t *d_bases = nullptr, *d_quals = nullptr, *d_dirs = nullptr, *d_coll = nullptr, *d_code = nullptr, *d_qual = nullptr, *d_anch = nullptr, *d_ref = nullptr;
-    unsigned int *d_depth = nullptr, *d_cursor = nullptr;
-    void* temp = nullptr;
-    auto cleanup = [&]() {
-        void* ptrs[] = {d_pos0, d_index, d_positions, d_flag, d_coff, d_soff, d_off, d_cigar, d_bases, d_quals, d_dirs, d_coll, d_code, d_qual, d_anch, d_ref, d_depth, d_cursor, temp};
-        for (void* p : ptrs) if (p) cudaFree(p);
-    };
-#define CUC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->error = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return PB2_ERR_CUDA; } } while (0)
-    CUC(upload(&d_pos0, R.pos0, st)); CUC(upload(&d_flag, R.flag, st)); CUC(upload(&d_coff, R.cigar_off, st)); CUC(upload(&d_soff, R.seq_off, st));
-    CUC(upload(&d_cigar, R.cigar, st)); CUC(upload(&d_bases, R.bases, st)); CUC(upload(&d_quals, R.quals, st));
-    if (R.has_dirs) CUC(upload(&d_dirs, R.base_dirs, st));
-    if (R.has_collapsed) CUC(upload(&d_coll, R.collapsed, st));
-    if (h->have_intervals) { CUC(upload(&d_index, index_of_pos, st)); CUC(upload(&d_positions, positions, st)); }
-    ReadsView rv{(int32_t)R.size(), d_pos0, d_flag, d_coff, d_cigar, d_soff, d_bases, d_quals, d_dirs, d_coll};
-    RegionView rg{lo, hi, d_index, h->d_chr, h->chr_len, h->dcfg.min_bq, h->cfg.expect_collapsed};
-    CUC(cudaMalloc(&d_depth, sizeof(unsigned int) * (size_t)n_loci));
-    CUC(cudaMalloc(&d_cursor, sizeof(unsigned int) * (size_t)n_loci));
-    CUC(cudaMemsetAsync(d_depth, 0, sizeof(unsigned int) * (size_t)n_loci, st));
-    CUC(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int) * (size_t)n_loci, st));
-    CUC(launch_reads_count(rv, rg, d_depth, st));
-    int64_t* d_depth64 = nullptr;
-    CUC(cudaMalloc(&d_off, sizeof(int64_t) * (size_t)(n_loci + 1)));
-    CUC(cudaMalloc(&d_depth64, sizeof(int64_t) * (size_t)(n_loci + 1)));
-    cudaError_t e2 = launch_depth_to_i64(d_depth, d_depth64, n_loci, st);
-    size_t tb = 0;
-    if (e2 == cudaSuccess) e2 = exclusive_scan_i64(d_depth64, d_off, n_loci + 1, nullptr, 0, &tb, st);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(&temp, std::max<size_t>(tb, 16));
-    if (e2 == cudaSuccess) e2 = exclusive_scan_i64(d_depth64, d_off, n_loci + 1, temp, tb, nullptr, st);
-    int64_t n_entries = 0;
-    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(&n_entries, d_off + n_loci, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
-    cudaFree(d_depth64);
-    CUC(e2);
-    CUC(cudaMalloc(&d_code, (size_t)std::max<int64_t>(n_entries, 1)));
-    CUC(cudaMalloc(&d_qual, (size_t)std::max<int64_t>(n_entries, 1)));
-    CUC(cudaMalloc(&d_anch, (size_t)std::max<int64_t>(n_entries, 1)));
-    CUC(launch_reads_emit(rv, rg, d_off, d_cursor, d_code, d_qual, d_anch, st));
-    h->total_launches += 5;
-    // reference bases of the staged loci ('N' beyond the chromosome end or when no reference was set)
-    std::vector<uint8_t> refb((size_t)n_loci, (uint8_t)'N');
-    for (int64_t i = 0; i < n_loci; i++) {
-        const int64_t p = h->have_intervals ? positions[(size_t)i] : lo + i;
-        if (p >= 1 && p <= h->chr_len) refb[(size_t)i] = h->h_chr[(size_t)(p - 1)];
+    int32_t* d_index = nullptr;
+    Segment s;
+    s.n_loci = n_loci;
+    s.n_tiles = (int32_t)((n_loci + kTileLoci - 1) / kTileLoci);
+    s.first_position = lo;
+    s.has_positions = h->have_intervals;
+    s.temporary = temporary;
+    if (h->have_intervals) {
+        CU(h, pool_alloc_t(h, &d_index, index_of_pos.size()));
+        CU(h, cudaMemcpyAsync(d_index, index_of_pos.data(), sizeof(int32_t) * index_of_pos.size(), cudaMemcpyHostToDevice, st));
+        CU(h, pool_alloc_t(h, &s.positions, positions.size()));
+        CU(h, cudaMemcpyAsync(s.positions, positions.data(), sizeof(int32_t) * positions.size(), cudaMemcpyHostToDevice, st));
+        s.h_positions = positions;
     }
-    CUC(upload(&d_ref, refb, st));
-    CUC(cudaStreamSynchronize(st));
-    pb2_pileup_csr csr;
-    memset(&csr, 0, sizeof(csr));
-    csr.n_loci = n_loci; csr.first_position = lo; csr.positions = h->have_intervals ? d_positions : nullptr; csr.offsets = d_off;
-    csr.code = d_code; csr.qual = d_qual; csr.anchor = d_anch; csr.ref_bases = d_ref;
-    const int rc = push_common(h, &csr, true);
-    cleanup();
+    ReadsView rv = R.view();
+    RegionView rg{lo, hi, d_index, h->d_chr, h->chr_len, h->dcfg.min_bq, h->cfg.expect_collapsed};
+    if (!pvert_eligible(h)) {
+        // quality sums / unusual quality bars: the PTILE32 form, through the locus-major entry list (reads_count / reads_emit -> push_common)
+        unsigned int *d_depth = nullptr, *d_cursor = nullptr;
+        int64_t *d_off = nullptr, *d_depth64 = nullptr;
+        uint8_t *d_code = nullptr, *d_qual = nullptr, *d_anch = nullptr, *d_ref = nullptr;
+        void* temp = nullptr;
+        auto cleanup = [&]() {
+            void* ptrs[] = {d_depth, d_cursor, d_off, d_depth64, d_code, d_qual, d_anch, d_ref, temp, d_index, s.positions};
+            for (void* p : ptrs) pool_free(h, p);
+        };
+#define CUC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->error = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return PB2_ERR_CUDA; } } while (0)
+        CUC(pool_alloc_t(h, &d_depth, (size_t)n_loci));
+        CUC(pool_alloc_t(h, &d_cursor, (size_t)n_loci));
+        CUC(cudaMemsetAsync(d_depth, 0, sizeof(unsigned int) * (size_t)n_loci, st));
+        CUC(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int) * (size_t)n_loci, st));
+        CUC(launch_reads_count(rv, rg, d_depth, st));
+        CUC(pool_alloc_t(h, &d_off, (size_t)(n_loci + 1)));
+        CUC(pool_alloc_t(h, &d_depth64, (size_t)(n_loci + 1)));
+        CUC(launch_depth_to_i64(d_depth, d_depth64, n_loci, st));
+        size_t tb = 0;
+        CUC(exclusive_scan_i64(d_depth64, d_off, n_loci + 1, nullptr, 0, &tb, st));
+        CUC(pool_alloc(h, &temp, std::max<size_t>(tb, 16)));
+        CUC(exclusive_scan_i64(d_depth64, d_off, n_loci + 1, temp, tb, nullptr, st));
+        int64_t n_entries = 0;
+        CUC(cudaMemcpyAsync(&n_entries, d_off + n_loci, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CUC(cudaStreamSynchronize(st));
+        CUC(pool_alloc(h, (void**)&d_code, (size_t)std::max<int64_t>(n_entries, 1)));
+        CUC(pool_alloc(h, (void**)&d_qual, (size_t)std::max<int64_t>(n_entries, 1)));
+        CUC(pool_alloc(h, (void**)&d_anch, (size_t)std::max<int64_t>(n_entries, 1)));
+        CUC(launch_reads_emit(rv, rg, d_off, d_cursor, d_code, d_qual, d_anch, st));
+        CUC(pool_alloc(h, (void**)&d_ref, (size_t)n_loci));
+        CUC(launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, d_ref, st));
+        h->total_launches += 6;
+        pb2_pileup_csr csr;
+        memset(&csr, 0, sizeof(csr));
+        csr.n_loci = n_loci; csr.first_position = lo; csr.positions = s.positions; csr.offsets = d_off;
+        csr.code = d_code; csr.qual = d_qual; csr.anchor = d_anch; csr.ref_bases = d_ref;
+        const int rc = push_common(h, &csr, true);
+        cleanup();
 #undef CUC
+        if (rc != PB2_OK) return rc;
+        h->segs.back().temporary = temporary;
+        return PB2_OK;
+    }
+    // ---- PVERT: rows per (tile, class), layout, fill, bit transposition
+    const int nc = h->cfg.expect_collapsed ? kPvClassesCollapsed : kPvClassesPlain;
+    s.pv_classes = nc;
+    int32_t* d_cursor = nullptr;
+    int64_t* tile_rows = nullptr;
+    void* temp = nullptr;
+    const size_t n_cls = (size_t)s.n_tiles * (size_t)nc;
+    CU(h, pool_alloc_t(h, &s.pv_cls_end, n_cls));
+    CU(h, pool_alloc_t(h, &d_cursor, n_cls));
+    CU(h, pool_alloc_t(h, &tile_rows, (size_t)s.n_tiles + 1));
+    CU(h, pool_alloc_t(h, &s.pv_tile_row0, (size_t)s.n_tiles + 1));
+    CU(h, cudaMemsetAsync(s.pv_cls_end, 0, sizeof(int32_t) * n_cls, st));
+    CU(h, cudaMemsetAsync(d_cursor, 0, sizeof(int32_t) * n_cls, st));
+    CU(h, launch_pvert_count(rv, rg, nc, s.pv_cls_end, st));
+    CU(h, launch_pvert_layout(s.pv_cls_end, s.n_tiles, nc, tile_rows, st));
+    size_t tb = 0;
+    CU(h, exclusive_scan_i64(tile_rows, s.pv_tile_row0, s.n_tiles + 1, nullptr, 0, &tb, st));
+    CU(h, pool_alloc(h, &temp, std::max<size_t>(tb, 16)));
+    CU(h, exclusive_scan_i64(tile_rows, s.pv_tile_row0, s.n_tiles + 1, temp, tb, nullptr, st));
+    CU(h, cudaMemcpyAsync(&s.pv_rows, s.pv_tile_row0 + s.n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    const size_t data_bytes = (size_t)std::max<int64_t>(s.pv_rows, 32) * 32;
+    CU(h, pool_alloc(h, (void**)&s.pv_data, data_bytes + 4096));
+    CU(h, pool_alloc_t(h, &s.pv_row_meta, (size_t)std::max<int64_t>(s.pv_rows, 32)));
+    CU(h, cudaMemsetAsync(s.pv_data, 0, data_bytes + 4096, st));
+    s.exc_capacity = std::max<int64_t>(1 << 20, R.n_seq / 128);
+    CU(h, pool_alloc_t(h, &s.exc_entries, 2 * (size_t)s.exc_capacity));
+    CU(h, pool_alloc_t(h, &s.counters, 4));
+    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
+    CU(h, launch_pvert_fill(rv, rg, nc, s.pv_tile_row0, s.pv_cls_end, d_cursor, s.pv_data, s.pv_row_meta, s.exc_entries, s.counters + 3, s.exc_capacity, st));
+    CU(h, launch_pvert_transpose(s.pv_data, s.pv_rows / 32, st));
+    CU(h, pool_alloc_t(h, &s.ref_base, (size_t)n_loci));
+    CU(h, launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, s.ref_base, st));
+    h->total_launches += 6;
+    s.n_entries = R.n_seq;
+    const int rc = alloc_segment_outputs(h, s);
+    pool_free(h, d_cursor); pool_free(h, tile_rows); pool_free(h, temp); pool_free(h, d_index);
     if (rc != PB2_OK) return rc;
-    h->segs.back().temporary = true;
+    h->segs.push_back(std::move(s));
+    return PB2_OK;
+}
+
+// IStateManager view for hosts that keep the whole chromosome's reads on the device: stages everything pushed so far as one resident segment, so
+// that pb2_call_resident / pb2_resident_results can run on it (the reads stay staged; pb2_flush still works and re-stages what it needs).
+extern "C" int pb2_stage_reads(pb2_handle* h) {
+    if (!h) return PB2_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    release_resident_graph(h);
+    explicit_release_resident(h);
+    for (size_t i = 0; i < h->segs.size();) {
+        if (h->segs[i].from_reads) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); } else i++;
+    }
+    const size_t before = h->segs.size();
+    const int rc = stage_reads_segment(h, INT32_MAX, h->cleared_through + 1, false);
+    if (rc != PB2_OK) return rc;
+    for (size_t i = before; i < h->segs.size(); i++) h->segs[i].from_reads = true;
+    CU(h, cudaStreamSynchronize(h->stream));
     return PB2_OK;
 }
 
@@ -957,10 +1144,21 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
     // blocks that exist: touched by a kept read, or holding a candidate
     std::vector<int32_t> keys;
     {
-        const HostReads& R = h->reads;
-        for (size_t i = 0; i < R.size(); i++) {
-            const int a = std::max(R.pos0[i] + 1, h->cleared_through + 1), e = R.end_pos[i];
-            for (int k = (a + 999) / 1000; a <= e && k <= (e + 999) / 1000; k++) keys.push_back(k);
+        const DeviceReads& R = h->reads;
+        if (R.n > 0) {
+            const int32_t a = std::max(R.min_start, h->cleared_through + 1), e = R.max_end;
+            if (a <= e) {
+                const int32_t k0 = (a + 999) / 1000, nk = (e + 999) / 1000 - k0 + 1;
+                std::vector<uint32_t> bits((size_t)(nk + 31) / 32, 0);
+                uint32_t* d_bits = nullptr;
+                CU(h, pool_alloc_t(h, &d_bits, bits.size()));
+                CU(h, cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * bits.size(), h->stream));
+                CU(h, launch_reads_block_bitmap(R.pos0.p, R.end_pos.p, R.n, h->cleared_through, k0, nk, d_bits, h->stream));
+                CU(h, cudaMemcpyAsync(bits.data(), d_bits, sizeof(uint32_t) * bits.size(), cudaMemcpyDeviceToHost, h->stream));
+                CU(h, cudaStreamSynchronize(h->stream));
+                pool_free(h, d_bits);
+                for (int32_t k = 0; k < nk; k++) if ((bits[(size_t)k >> 5] >> (k & 31)) & 1u) keys.push_back(k0 + k);
+            }
         }
         for (auto& c : h->cands) if (c.alive) keys.push_back((c.position + 999) / 1000);
         std::sort(keys.begin(), keys.end());
@@ -1170,6 +1368,59 @@ static void germline_locus_pass(pb2_handle* h) {
     }
 }
 
+// After a flush that cleared positions <= cleared_to: the reads that end inside the cleared positions leave the store (device compaction).
+static int compact_reads(pb2_handle* h, int32_t cleared_to) {
+    DeviceReads& R = h->reads;
+    if (R.n == 0) return PB2_OK;
+    cudaStream_t st = h->stream;
+    const size_t n1 = (size_t)R.n + 1;
+    int64_t *flags = nullptr, *lc = nullptr, *ls = nullptr, *ni = nullptr, *nc = nullptr, *ns = nullptr;
+    void* temp = nullptr;
+    CU(h, pool_alloc_t(h, &flags, n1)); CU(h, pool_alloc_t(h, &lc, n1)); CU(h, pool_alloc_t(h, &ls, n1));
+    CU(h, pool_alloc_t(h, &ni, n1)); CU(h, pool_alloc_t(h, &nc, n1)); CU(h, pool_alloc_t(h, &ns, n1));
+    CU(h, launch_reads_keep_flags(R.end_pos.p, R.n, cleared_to, R.cigar_off.p, R.seq_off.p, flags, lc, ls, st));
+    size_t tb = 0;
+    CU(h, exclusive_scan_i64(flags, ni, (int64_t)n1, nullptr, 0, &tb, st));
+    CU(h, pool_alloc(h, &temp, std::max<size_t>(tb, 16)));
+    CU(h, exclusive_scan_i64(flags, ni, (int64_t)n1, temp, tb, nullptr, st));
+    CU(h, exclusive_scan_i64(lc, nc, (int64_t)n1, temp, tb, nullptr, st));
+    CU(h, exclusive_scan_i64(ls, ns, (int64_t)n1, temp, tb, nullptr, st));
+    int64_t totals[3] = {0, 0, 0};
+    CU(h, cudaMemcpyAsync(&totals[0], ni + R.n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(&totals[1], nc + R.n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(&totals[2], ns + R.n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    if (totals[0] == 0) {
+        const int32_t last = R.last_pos0;
+        free_reads(h);
+        h->reads.last_pos0 = last;
+    } else if (totals[0] < R.n) {
+        DeviceReads K;
+        K.has_dirs = R.has_dirs; K.has_collapsed = R.has_collapsed;
+        const size_t kn = (size_t)totals[0], kc = (size_t)totals[1], ks = (size_t)totals[2];
+        CU(h, grow(h, K.pos0, kn, 0)); CU(h, grow(h, K.end_pos, kn, 0)); CU(h, grow(h, K.flag, kn, 0));
+        CU(h, grow(h, K.cigar_off, kn + 1, 0)); CU(h, grow(h, K.seq_off, kn + 1, 0));
+        CU(h, grow(h, K.cigar, std::max<size_t>(kc, 1), 0)); CU(h, grow(h, K.bases, std::max<size_t>(ks, 1), 0)); CU(h, grow(h, K.quals, std::max<size_t>(ks, 1), 0));
+        if (R.has_dirs) CU(h, grow(h, K.base_dirs, std::max<size_t>(ks, 1), 0));
+        if (R.has_collapsed) CU(h, grow(h, K.collapsed, kn, 0));
+        ReadsCompactArgs a;
+        a.n = R.n; a.new_index = ni; a.new_cigar = nc; a.new_seq = ns;
+        a.pos0 = R.pos0.p; a.end_pos = R.end_pos.p; a.flag = R.flag.p; a.cigar_off = R.cigar_off.p; a.cigar = R.cigar.p; a.seq_off = R.seq_off.p;
+        a.bases = R.bases.p; a.quals = R.quals.p; a.base_dirs = R.has_dirs ? R.base_dirs.p : nullptr; a.collapsed = R.has_collapsed ? R.collapsed.p : nullptr;
+        a.o_pos0 = K.pos0.p; a.o_end_pos = K.end_pos.p; a.o_flag = K.flag.p; a.o_cigar_off = K.cigar_off.p; a.o_cigar = K.cigar.p; a.o_seq_off = K.seq_off.p;
+        a.o_bases = K.bases.p; a.o_quals = K.quals.p; a.o_base_dirs = K.base_dirs.p; a.o_collapsed = K.collapsed.p;
+        CU(h, launch_reads_compact(a, st));
+        K.n = totals[0]; K.n_cigar = totals[1]; K.n_seq = totals[2];
+        K.min_start = R.min_start; K.max_end = R.max_end; K.last_pos0 = R.last_pos0;
+        CU(h, cudaStreamSynchronize(st));
+        free_reads(h);
+        h->reads = K;
+    }
+    void* ptrs[] = {flags, lc, ls, ni, nc, ns, temp};
+    for (void* p : ptrs) pool_free(h, p);
+    return PB2_OK;
+}
+
 extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n) {
     if (!h || !out || !n) return fail(h, PB2_ERR_ARG, "pb2_flush: null argument");
     CU(h, cudaSetDevice(h->device));
@@ -1177,6 +1428,9 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
     h->h_out.clear();
     h->arena.clear();
     const bool reads_path = h->reads.size() != 0 || !h->triggers.empty();
+    for (size_t i = 0; i < h->segs.size();) {   // a resident staging of the reads (pb2_stage_reads) is superseded: the flush stages what it needs itself
+        if (h->segs[i].from_reads) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); explicit_release_resident(h); release_resident_graph(h); } else i++;
+    }
     if (h->resident_explicit) for (auto& s : h->segs) s.called = false;   // a pb2_call_resident pass appended explicit alleles to the variant stream: redo
     // reads staged through pb2_push_reads: positions in complete 1000-bp blocks <= up_to_position are callable (RegionStateManager.cs:283-314);
     // locus-major pushes are complete by construction
@@ -1353,23 +1607,11 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
         if (h->segs[i].temporary) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); } else i++;
     }
     h->cands.erase(std::remove_if(h->cands.begin(), h->cands.end(), [](const HostCand& c) { return !c.alive; }), h->cands.end());
-    if (up_to_position < 0) { h->reads.clear(); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; h->snv_explicit_ranges.clear(); rearm_forced(h); }
+    explicit_reindex(h);
+    if (up_to_position < 0) { free_reads(h); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; h->snv_explicit_ranges.clear(); rearm_forced(h); }
     else if (reads_path && cleared_to > h->cleared_through) {
-        HostReads keep;
-        HostReads& R = h->reads;
-        keep.has_dirs = R.has_dirs; keep.has_collapsed = R.has_collapsed;
-        for (size_t i = 0; i < R.size(); i++) {
-            if (R.end_pos[i] <= cleared_to) continue;
-            keep.pos0.push_back(R.pos0[i]); keep.end_pos.push_back(R.end_pos[i]); keep.flag.push_back(R.flag[i]);
-            keep.cigar.insert(keep.cigar.end(), R.cigar.begin() + R.cigar_off[i], R.cigar.begin() + R.cigar_off[i + 1]);
-            keep.cigar_off.push_back((int64_t)keep.cigar.size());
-            keep.bases.insert(keep.bases.end(), R.bases.begin() + R.seq_off[i], R.bases.begin() + R.seq_off[i + 1]);
-            keep.quals.insert(keep.quals.end(), R.quals.begin() + R.seq_off[i], R.quals.begin() + R.seq_off[i + 1]);
-            if (R.has_dirs) keep.base_dirs.insert(keep.base_dirs.end(), R.base_dirs.begin() + R.seq_off[i], R.base_dirs.begin() + R.seq_off[i + 1]);
-            keep.seq_off.push_back((int64_t)keep.bases.size());
-            if (R.has_collapsed) keep.collapsed.push_back(R.collapsed[i]);
-        }
-        h->reads = std::move(keep);
+        const int rc = compact_reads(h, cleared_to);
+        if (rc != PB2_OK) return rc;
         h->cleared_through = cleared_to;
         for (auto it = h->gapped_ref.begin(); it != h->gapped_ref.end();) { if (it->first <= cleared_to) it = h->gapped_ref.erase(it); else ++it; }
         h->snv_explicit_ranges.erase(std::remove_if(h->snv_explicit_ranges.begin(), h->snv_explicit_ranges.end(),
@@ -1469,13 +1711,26 @@ extern "C" int pb2_get_counts(pb2_handle* h, int32_t position0, int32_t n, int32
         if (rc != PB2_OK) return rc;
     }
     for (auto& s : h->segs) {
+        if (s.from_reads) continue;   // the same reads were just staged over the requested window
         int32_t* d_counts = nullptr;
         CU(h, cudaMalloc(&d_counts, sizeof(int32_t) * (size_t)s.n_loci * kNumBins));
-        const bool was_called = s.called;
-        const unsigned long long vc = s.h_var_count, ec = s.h_exc_count;
-        int rc = run_segment(h, s, d_counts, nullptr);
-        s.called = was_called; s.h_var_count = vc; s.h_exc_count = ec;
-        if (rc != PB2_OK) { cudaFree(d_counts); return rc; }
+        if (s.pv_data != nullptr) {   // PVERT: the 198-bin gather over every locus of the window
+            int32_t* d_req = nullptr;
+            std::vector<int32_t> req((size_t)s.n_loci);
+            for (int64_t i = 0; i < s.n_loci; i++) req[(size_t)i] = (int32_t)i;
+            CU(h, cudaMalloc(&d_req, sizeof(int32_t) * req.size()));
+            CU(h, cudaMemcpyAsync(d_req, req.data(), sizeof(int32_t) * req.size(), cudaMemcpyHostToDevice, h->stream));
+            cudaError_t e = launch_pvert_gather(pvert_view(s), d_req, (int32_t)s.n_loci, d_counts, nullptr, h->dcfg.min_bq, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            cudaFree(d_req);
+            if (e != cudaSuccess) { cudaFree(d_counts); h->error = std::string("pvert_gather: ") + cudaGetErrorString(e); return PB2_ERR_CUDA; }
+        } else {
+            const bool was_called = s.called;
+            const unsigned long long vc = s.h_var_count, ec = s.h_exc_count;
+            int rc = run_segment(h, s, d_counts, nullptr);
+            s.called = was_called; s.h_var_count = vc; s.h_exc_count = ec;
+            if (rc != PB2_OK) { cudaFree(d_counts); return rc; }
+        }
         std::vector<int32_t> hc((size_t)s.n_loci * kNumBins);
         CU(h, cudaMemcpy(hc.data(), d_counts, sizeof(int32_t) * hc.size(), cudaMemcpyDeviceToHost));
         cudaFree(d_counts);

@@ -40,16 +40,23 @@ void explicit_add_candidate(pb2_handle* h, const HostCand& nc) {
     int32_t& mx = h->block_max_endpoint[block_key(nc.position)];
     if (other_end > mx) mx = other_end;
     const bool track_open = h->cfg.collapse != 0;   // trackOpenEnded (Factory.cs:209-227)
-    for (auto& c : h->cands) {
-        if (!c.alive || c.position != nc.position) continue;
+    std::vector<uint32_t>& at = h->cand_by_pos[nc.position];   // the position's candidate list (RegionState._candidateVariantsLookup), in insertion order
+    for (uint32_t idx : at) {
+        HostCand& c = h->cands[idx];
+        if (!c.alive) continue;
         if (c.Equals(nc) && (!track_open || (c.open_left == nc.open_left && c.open_right == nc.open_right))) {
             for (int i = 0; i < 3; i++) { c.support[i] += nc.support[i]; c.well_anchored[i] += nc.well_anchored[i]; }
             for (int i = 0; i < 8; i++) c.collapsed_mut[i] += nc.collapsed_mut[i];
             return;
         }
     }
+    at.push_back((uint32_t)h->cands.size());
     h->cands.push_back(nc);
     h->cands.back().alive = true;
+}
+void explicit_reindex(pb2_handle* h) {   // after h->cands was compacted
+    h->cand_by_pos.clear();
+    for (size_t i = 0; i < h->cands.size(); i++) h->cand_by_pos[h->cands[i].position].push_back((uint32_t)i);
 }
 
 // ------------------------------------------------------------------------------------------------ device context of one batch
@@ -101,6 +108,7 @@ struct BatchCtx {
     DevBuf<pb2_call_record> d_out;
     DevBuf<SpanIngredients> d_ingr;
     bool want_q;
+    bool use_resident_reads = false;   // pb2_call_resident: the segment pb2_stage_reads built is the one to gather from
     struct GatherRec { size_t seg; int32_t req_off, n, row0; };
     std::vector<GatherRec> gathers;   // the gather launches made so far (replayed by pb2_call_resident)
     explicit BatchCtx(pb2_handle* hh) : h(hh) { want_q = hh->cfg.want_sum_base_quality || hh->cfg.noise_model == 1; }
@@ -122,6 +130,11 @@ struct BatchCtx {
         in.plane_bytes = std::max<int64_t>(s.plane_bytes, 16);
         return in;
     }
+    // 198-bin counts of the requested loci of a segment, whichever form it is staged in
+    static cudaError_t gather_rows(const Segment& s, const int32_t* req, int32_t n, int32_t* counts, int32_t* collapsed, double* qsum, int min_bq, cudaStream_t st) {
+        if (s.pv_data != nullptr) return launch_pvert_gather(pvert_view(s), req, n, counts, collapsed, min_bq, st);   // (no quality sums in this form: pvert_eligible)
+        return launch_gather_locus_counts(view(s), req, n, counts, collapsed, qsum, min_bq, st);
+    }
     // make sure the count tables hold a row for each of these positions (gathered from whichever segment stages it)
     int ensure_rows(const std::vector<int32_t>& positions) {
         std::vector<std::vector<std::pair<int32_t, int32_t>>> per_seg(h->segs.size());   // (row, locus)
@@ -130,6 +143,7 @@ struct BatchCtx {
             if (row_of_pos.count(pos)) continue;
             int32_t row = -1;
             for (size_t si = 0; si < h->segs.size(); si++) {
+                if (h->segs[si].from_reads && !use_resident_reads) continue;
                 const int64_t l = locus_of(h->segs[si], pos);
                 if (l >= 0) { row = next++; per_seg[si].push_back({row, (int32_t)l}); break; }
             }
@@ -154,8 +168,8 @@ struct BatchCtx {
                 size_t b = a + 1;
                 while (b < v.size() && v[b].first == v[b - 1].first + 1) b++;
                 const int32_t r0 = v[a].first, n = (int32_t)(b - a);
-                CUX(h, launch_gather_locus_counts(view(h->segs[si]), req.p + (r0 - n_rows), n, counts.p + (size_t)r0 * kNumBins,
-                                                  collapsed.p + (size_t)r0 * kNumCollapsed, want_q ? qsum.p + (size_t)r0 * kNumBins : nullptr, h->dcfg.min_bq, st));
+                CUX(h, gather_rows(h->segs[si], req.p + (r0 - n_rows), n, counts.p + (size_t)r0 * kNumBins, collapsed.p + (size_t)r0 * kNumCollapsed,
+                                   want_q ? qsum.p + (size_t)r0 * kNumBins : nullptr, h->dcfg.min_bq, st));
                 h->total_launches += 1;
                 gathers.push_back({si, r0 - n_rows, n, r0});
                 a = b;
@@ -679,6 +693,7 @@ int explicit_call_resident(pb2_handle* h, Segment& seg, cudaStream_t side) {
             if (h->cfg.collapse && (c.open_left || c.open_right)) return pb2_fail(h, PB2_ERR_UNSUPPORTED, "pb2_call_resident: open-ended candidates need the collapser; use pb2_flush");
         }
         plan = new ResidentPlan(h);
+        plan->ctx.use_resident_reads = true;
         h->resident_explicit = plan;
         std::deque<Piece> store;
         std::vector<Piece*> ps;
@@ -703,9 +718,8 @@ int explicit_call_resident(pb2_handle* h, Segment& seg, cudaStream_t side) {
     }
     BatchCtx& ctx = plan->ctx;
     for (auto& g : ctx.gathers) {
-        CUX(h, launch_gather_locus_counts(BatchCtx::view(h->segs[g.seg]), ctx.req.p + g.req_off, g.n, ctx.counts.p + (size_t)g.row0 * kNumBins,
-                                          ctx.collapsed.p + (size_t)g.row0 * kNumCollapsed, ctx.want_q ? ctx.qsum.p + (size_t)g.row0 * kNumBins : nullptr,
-                                          h->dcfg.min_bq, side));
+        CUX(h, BatchCtx::gather_rows(h->segs[g.seg], ctx.req.p + g.req_off, g.n, ctx.counts.p + (size_t)g.row0 * kNumBins,
+                                     ctx.collapsed.p + (size_t)g.row0 * kNumCollapsed, ctx.want_q ? ctx.qsum.p + (size_t)g.row0 * kNumBins : nullptr, h->dcfg.min_bq, side));
         h->total_launches += 1;
     }
     CUX(h, launch_score_candidates(plan->args, h->dcfg, side));
@@ -721,8 +735,8 @@ int explicit_prune_resident(pb2_handle* h, Segment& seg) {
 }
 
 // ------------------------------------------------------------------------------------------------ candidates of pushed reads
-static int find_candidates_impl(pb2_handle* h, const HostReads& R, size_t first_read, int32_t snv_lo, int32_t snv_hi);
-int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_read) { return find_candidates_impl(h, R, first_read, 0, 0); }
+static int find_candidates_impl(pb2_handle* h, size_t first_read, const BatchHostView* host, int32_t snv_lo, int32_t snv_hi);
+int explicit_find_candidates(pb2_handle* h, size_t first_read, const BatchHostView* host) { return find_candidates_impl(h, first_read, host, 0, 0); }
 // CallMNVs off: SNV candidates are the counts — until RegionStateManager.AddCollapsableFromOtherBlocks (:441-457) pulls the finished SNV candidates of a
 // later block into an earlier batch. What happens to them there depends on their open-end twins and the order they were raised in
 // (RegionState.ExtractCollapsable :470-490 removes with List.Remove, i.e. the first candidate that Equals), so from then on the SNV candidates at the
@@ -735,7 +749,7 @@ int explicit_materialize_snvs(pb2_handle* h, int32_t lo, int32_t hi) {
     std::vector<HostCand> forced_here;
     for (auto& c : h->cands)
         if (c.alive && c.type == CAT_SNV && c.position > lo && c.position <= hi) { forced_here.push_back(c); c.alive = false; }
-    const int rc = find_candidates_impl(h, h->reads, 0, lo, hi);
+    const int rc = find_candidates_impl(h, 0, nullptr, lo, hi);
     if (rc != PB2_OK) return rc;
     for (auto& c : forced_here) { c.alive = true; explicit_add_candidate(h, c); }
     h->snv_explicit_ranges.push_back({lo, hi});
@@ -743,68 +757,70 @@ int explicit_materialize_snvs(pb2_handle* h, int32_t lo, int32_t hi) {
 }
 // snv_lo < snv_hi: only the SNV candidates at positions in (snv_lo, snv_hi], found with the CallMNVs-off state machine (ShouldBuildUpMNV :170-181 returns
 // false: every mismatch is its own SNV); used when count-based SNVs have to become explicit candidates (explicit_materialize_snvs)
-static int find_candidates_impl(pb2_handle* h, const HostReads& R, size_t first_read, int32_t snv_lo, int32_t snv_hi) {
+static int find_candidates_impl(pb2_handle* h, size_t first_read, const BatchHostView* host, int32_t snv_lo, int32_t snv_hi) {
     const bool snv_only = snv_lo < snv_hi;
+    const DeviceReads& R = h->reads;
     const size_t n = R.size() - first_read;
     if (n == 0) return PB2_OK;
     if (h->chr_len == 0) return PB2_OK;   // no reference: the finder has nothing to compare against (the reference would throw on refChromosome[...])
-    bool any = h->cfg.call_mnvs != 0 || snv_only;
-    if (!any)
-        for (int64_t k = R.cigar_off[first_read]; k < R.cigar_off[R.size()] && !any; k++) { const uint32_t op = R.cigar[(size_t)k] & 15; any = op == 1 || op == 2; }
-    if (!any) return PB2_OK;
     cudaStream_t st = h->stream;
     CUX(h, cudaSetDevice(h->device));
-    // the new reads only, offsets rebased
-    std::vector<int64_t> coff(n + 1), soff(n + 1);
-    const int64_t c_base = R.cigar_off[first_read], s_base = R.seq_off[first_read];
-    for (size_t i = 0; i <= n; i++) { coff[i] = R.cigar_off[first_read + i] - c_base; soff[i] = R.seq_off[first_read + i] - s_base; }
-    DevBuf<int32_t> d_pos0; DevBuf<uint16_t> d_flag; DevBuf<int64_t> d_coff, d_soff; DevBuf<uint32_t> d_cigar; DevBuf<uint8_t> d_bases, d_quals, d_dirs, d_coll;
     DevBuf<RawCand> d_raw; DevBuf<unsigned long long> d_count;
-    const size_t n_cig = (size_t)coff[n], n_seq = (size_t)soff[n];
-    auto up = [&](auto& buf, const auto* src, size_t cnt) -> cudaError_t {
-        cudaError_t e = buf.reserve(std::max<size_t>(cnt, 1), st);
-        if (e == cudaSuccess && cnt) e = cudaMemcpyAsync(buf.p, src, cnt * sizeof(*src), cudaMemcpyHostToDevice, st);
-        return e;
-    };
-    CUX(h, up(d_pos0, R.pos0.data() + first_read, n));
-    CUX(h, up(d_flag, R.flag.data() + first_read, n));
-    CUX(h, up(d_coff, coff.data(), n + 1));
-    CUX(h, up(d_soff, soff.data(), n + 1));
-    CUX(h, up(d_cigar, R.cigar.data() + c_base, n_cig));
-    CUX(h, up(d_bases, R.bases.data() + s_base, n_seq));
-    CUX(h, up(d_quals, R.quals.data() + s_base, n_seq));
-    if (R.has_dirs) CUX(h, up(d_dirs, R.base_dirs.data() + s_base, n_seq));
-    if (R.has_collapsed) CUX(h, up(d_coll, R.collapsed.data() + first_read, n));
-    // every insertion / deletion operation raises at most one candidate, every aligned base at most one SNV/MNV
-    const int64_t capacity = (int64_t)n_cig + ((h->cfg.call_mnvs || snv_only) ? (int64_t)n_seq : 0) + 16;
-    CUX(h, d_raw.reserve((size_t)capacity, st));
-    CUX(h, d_count.reserve(1, st));
-    CUX(h, cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), st));
-    ReadsView rv{(int32_t)n, d_pos0.p, d_flag.p, d_coff.p, d_cigar.p, d_soff.p, d_bases.p, d_quals.p, R.has_dirs ? d_dirs.p : nullptr, R.has_collapsed ? d_coll.p : nullptr};
-    CUX(h, launch_reads_candidates(rv, 0, h->d_chr, h->chr_len, h->dcfg.min_bq, snv_only ? 1 : h->cfg.call_mnvs, snv_only ? 0 : h->cfg.max_size_mnv,
-                                   snv_only ? 0 : h->cfg.max_gap_mnv, h->cfg.expect_collapsed, d_raw.p, d_count.p, capacity, st));
-    h->total_launches += 1;
+    // every insertion / deletion operation raises at most one candidate, every aligned base at most one SNV/MNV; the SNV/MNV bound is far from tight on
+    // real data, so the buffer starts smaller and the kernel is run again with the exact size if it did not fit
+    const bool per_base = h->cfg.call_mnvs || snv_only;
+    const int64_t n_cig = R.n_cigar, n_seq = R.n_seq;
+    int64_t capacity = n_cig + (per_base ? std::min<int64_t>(n_seq, std::max<int64_t>(1 << 20, n_seq / 16)) : 0) + 16;
+    CUX(h, d_count.reserve(1, st, false, h));
+    const ReadsView rv = R.view();
     unsigned long long cnt = 0;
-    CUX(h, cudaMemcpyAsync(&cnt, d_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-    CUX(h, cudaStreamSynchronize(st));
-    if ((int64_t)cnt > capacity) return pb2_fail(h, PB2_ERR_NOMEM, "candidate buffer overflow");
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CUX(h, d_raw.reserve((size_t)capacity, st, false, h));
+        CUX(h, cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), st));
+        CUX(h, launch_reads_candidates(rv, (int32_t)first_read, h->d_chr, h->chr_len, h->dcfg.min_bq, snv_only ? 1 : h->cfg.call_mnvs, snv_only ? 0 : h->cfg.max_size_mnv,
+                                       snv_only ? 0 : h->cfg.max_gap_mnv, h->cfg.expect_collapsed, d_raw.p, d_count.p, capacity, st));
+        h->total_launches += 1;
+        CUX(h, cudaMemcpyAsync(&cnt, d_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CUX(h, cudaStreamSynchronize(st));
+        if ((int64_t)cnt <= capacity) break;
+        if (attempt == 1) return pb2_fail(h, PB2_ERR_NOMEM, "candidate buffer overflow");
+        capacity = (int64_t)cnt + 16;
+    }
+    if (cnt == 0) return PB2_OK;
     std::vector<RawCand> raw((size_t)cnt);
-    if (cnt) CUX(h, cudaMemcpy(raw.data(), d_raw.p, sizeof(RawCand) * (size_t)cnt, cudaMemcpyDeviceToHost));
+    CUX(h, cudaMemcpy(raw.data(), d_raw.p, sizeof(RawCand) * (size_t)cnt, cudaMemcpyDeviceToHost));
     // FindCandidates' own order: read by read, operation by operation
     std::sort(raw.begin(), raw.end(), [](const RawCand& a, const RawCand& b) { return a.read != b.read ? a.read < b.read : a.order < b.order; });
+    // alleles longer than RawCand::read_bases whose read is not in the caller's batch: fetched from the device store
+    std::vector<uint8_t> fetched;
+    auto read_bases_of = [&](const RawCand& rc, int n_from_read, std::string& out) -> int {
+        if (n_from_read <= 8) { out.append(reinterpret_cast<const char*>(rc.read_bases), (size_t)n_from_read); return PB2_OK; }
+        if (host != nullptr && (size_t)rc.read >= first_read) {
+            const int64_t j = (int64_t)rc.read - (int64_t)first_read;
+            out.append(reinterpret_cast<const char*>(host->bases) + (host->seq_off[j] - host->seq_lo) + rc.start_in_read, (size_t)n_from_read);
+            return PB2_OK;
+        }
+        int64_t off = 0;
+        CUX(h, cudaMemcpy(&off, R.seq_off.p + rc.read, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        fetched.resize((size_t)n_from_read);
+        CUX(h, cudaMemcpy(fetched.data(), R.bases.p + off + rc.start_in_read, (size_t)n_from_read, cudaMemcpyDeviceToHost));
+        out.append(reinterpret_cast<const char*>(fetched.data()), (size_t)n_from_read);
+        return PB2_OK;
+    };
+    const char* chr = reinterpret_cast<const char*>(h->h_chr.data());
     for (const RawCand& rc : raw) {
         if (rc.position <= h->cleared_through || rc.position < 1) continue;
         if (snv_only && (rc.type != CAT_SNV || rc.position <= snv_lo || rc.position > snv_hi)) continue;
+        if ((int64_t)rc.position - 1 + rc.ref_len > h->chr_len) continue;   // Substring past the chromosome end throws in the reference
         HostCand c;
         c.position = rc.position; c.type = rc.type;
         c.open_left = (rc.flags & 1) != 0; c.open_right = (rc.flags & 2) != 0;
-        const char* chr = reinterpret_cast<const char*>(h->h_chr.data());
-        const char* rb = reinterpret_cast<const char*>(R.bases.data()) + R.seq_off[first_read + (size_t)rc.read] + rc.start_in_read;
-        if ((int64_t)rc.position - 1 + rc.ref_len > h->chr_len) continue;   // Substring past the chromosome end throws in the reference
         c.ref.assign(chr + rc.position - 1, rc.ref_len);
-        if (rc.type == CAT_INS) { c.alt.assign(1, chr[rc.position - 1]); c.alt.append(rb, (size_t)rc.alt_len - 1); }
+        int rcode = PB2_OK;
+        if (rc.type == CAT_INS) { c.alt.assign(1, chr[rc.position - 1]); rcode = read_bases_of(rc, (int)rc.alt_len - 1, c.alt); }
         else if (rc.type == CAT_DEL) c.alt.assign(1, chr[rc.position - 1]);
-        else c.alt.assign(rb, rc.alt_len);
+        else rcode = read_bases_of(rc, (int)rc.alt_len, c.alt);
+        if (rcode != PB2_OK) return rcode;
         c.support[rc.dir] = 1;
         if (rc.flags & 4) c.well_anchored[rc.dir] = 1;
         if (rc.collapsed) {   // CandidateVariantFinder.Create (:352-384)

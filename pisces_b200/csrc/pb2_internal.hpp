@@ -4,6 +4,7 @@
 #include <set>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 #include "pb2_candidates.cuh"
 #include "pb2_kernels.cuh"
@@ -35,7 +36,7 @@ cudaError_t launch_reads_emit(const ReadsView& rv, const RegionView& rg, const i
                               cudaStream_t st);
 cudaError_t launch_depth_to_i64(const unsigned int* depth, int64_t* out, int64_t n, cudaStream_t st);
 
-// One candidate found in one read by reads_candidates_kernel. 24 bytes.
+// One candidate found in one read by reads_candidates_kernel. 32 bytes.
 struct RawCand {
     int32_t read;            // index of the read in the pushed buffer
     int32_t order;           // (CIGAR operation index << 16) | offset in the operation: FindCandidates' emission order inside the read
@@ -45,21 +46,64 @@ struct RawCand {
     uint8_t type, dir;       // AlleleCategory, DirectionType of the support
     uint8_t flags;           // bit0 OpenOnLeft, bit1 OpenOnRight, bit2 well anchored
     uint8_t collapsed;       // ReadCollapsedType + 1, or 0
+    uint8_t read_bases[8];   // the first (up to 8) read bases of the allele, bases[start_in_read ...]: the reads themselves stay on the device
 };
-static_assert(sizeof(RawCand) == 24, "RawCand layout");
+static_assert(sizeof(RawCand) == 32, "RawCand layout");
 cudaError_t launch_reads_candidates(const ReadsView& rv, int32_t first_read, const uint8_t* chr, int64_t chr_len, int min_bq, int call_mnvs, int max_mnv, int max_gap,
                                     int expect_collapsed, RawCand* out, unsigned long long* count, int64_t capacity, cudaStream_t st);
-}  // namespace pb2
 
-struct HostReads {   // reads staged by pb2_push_reads, kept until a flush clears the positions they cover
-    std::vector<int32_t> pos0, end_pos;
-    std::vector<uint16_t> flag;
-    std::vector<int64_t> cigar_off{0}, seq_off{0};
-    std::vector<uint32_t> cigar;
-    std::vector<uint8_t> bases, quals, base_dirs, collapsed;
+// pb2_push_reads on the device: the new reads [first, n) of the store are validated (Read.cs:603-605, RegionStateManager.cs:363-364), their offsets
+// rebased, Read.EndPosition computed, and the positions where SmallVariantCaller.Execute would have called a batch collected
+// (SmallVariantCaller.cs:99-104: Call(read.Position - 1) whenever that enters a new 1000-bp block key).
+struct IngestStatus {
+    int32_t error;            // 0 ok, 1 bad CIGAR operation, 2 CIGAR does not match the read length, 3 negative position, 4 offsets not monotone
+    int32_t error_read;
+    int32_t n_triggers;
+    int32_t min_start, max_end;   // 1-based first / last reference position covered by the new reads
+    int32_t pad_[3];
+};
+cudaError_t launch_reads_ingest(const ReadsView& rv, int32_t first_read, int64_t cigar_base, int64_t seq_base, int64_t* cigar_off, int64_t* seq_off, int32_t* end_pos,
+                                int32_t prev_pos0, int2* triggers, int32_t trigger_capacity, IngestStatus* status, cudaStream_t st);
+// keep[i] = read i ends after `cleared_to`; compaction of the store after a partial flush (exclusive scans of the flags / lengths by the caller)
+cudaError_t launch_reads_keep_flags(const int32_t* end_pos, int64_t n, int32_t cleared_to, const int64_t* cigar_off, const int64_t* seq_off, int64_t* keep_reads,
+                                    int64_t* keep_cigar, int64_t* keep_seq, cudaStream_t st);
+struct ReadsCompactArgs {
+    int64_t n;
+    const int64_t *new_index, *new_cigar, *new_seq;   // exclusive scans, [n + 1]
+    const int32_t* pos0; const int32_t* end_pos; const uint16_t* flag; const int64_t* cigar_off; const uint32_t* cigar; const int64_t* seq_off;
+    const uint8_t *bases, *quals, *base_dirs, *collapsed;
+    int32_t* o_pos0; int32_t* o_end_pos; uint16_t* o_flag; int64_t* o_cigar_off; uint32_t* o_cigar; int64_t* o_seq_off;
+    uint8_t *o_bases, *o_quals, *o_base_dirs, *o_collapsed;
+};
+cudaError_t launch_reads_compact(const ReadsCompactArgs& a, cudaStream_t st);
+// 1000-bp blocks touched by the reads at positions > cleared_through: bit (key - key0) of the bitmap
+cudaError_t launch_reads_block_bitmap(const int32_t* pos0, const int32_t* end_pos, int64_t n, int32_t cleared_through, int32_t key0, int32_t n_keys, uint32_t* bitmap,
+                                      cudaStream_t st);
+}  // namespace pb2
+#include "pb2_pvert.cuh"
+
+// Reads staged by pb2_push_reads: a struct of arrays in device memory (the handle's pool), kept until a flush clears the positions they cover. The host
+// keeps no per-read state: what the host-side replay of SmallVariantCaller.Execute needs (batch triggers, touched blocks, extent) is computed by kernels.
+template <class T>
+struct GrowBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+};
+struct DeviceReads {
+    int64_t n = 0, n_cigar = 0, n_seq = 0;
+    GrowBuf<int32_t> pos0, end_pos;
+    GrowBuf<uint16_t> flag;
+    GrowBuf<int64_t> cigar_off, seq_off;   // [n + 1]
+    GrowBuf<uint32_t> cigar;
+    GrowBuf<uint8_t> bases, quals, base_dirs, collapsed;
     bool has_dirs = false, has_collapsed = false;
-    size_t size() const { return pos0.size(); }
-    void clear() { *this = HostReads(); }
+    int32_t min_start = INT32_MAX, max_end = 0;   // extent of the stored reads (1-based positions)
+    int32_t last_pos0 = -1;                       // Position of the read pushed last (-1: none yet)
+    size_t size() const { return (size_t)n; }
+    pb2::ReadsView view() const {
+        return pb2::ReadsView{(int32_t)n, pos0.p, flag.p, cigar_off.p, cigar.p, seq_off.p, bases.p, quals.p, has_dirs ? base_dirs.p : nullptr,
+                              has_collapsed ? collapsed.p : nullptr};
+    }
 };
 
 // CandidateAllele (src/lib/Pisces.Domain/Models/Alleles/CandidateAllele.cs:8-125) on the host: one row of the explicit-candidate table.
@@ -95,6 +139,13 @@ struct Segment {   // one staged pileup (pb2_push_pileup*)
     int64_t* tile_base = nullptr;
     uint8_t *code = nullptr, *qual = nullptr, *anch = nullptr, *ref_base = nullptr;
     int32_t* positions = nullptr;
+    // PVERT form (pb2_pvert.cuh; segments built from pushed reads): pv_data != nullptr, and none of the PTILE32 / PNIB16 planes exist
+    uint8_t* pv_data = nullptr;
+    int2* pv_row_meta = nullptr;
+    int64_t* pv_tile_row0 = nullptr;
+    int32_t* pv_cls_end = nullptr;
+    int32_t pv_classes = 0;
+    int64_t pv_rows = 0;
     // PNIB16 form of the same pileup (pileup_nib_score_kernel); nib == nullptr: not staged (stitched directions, collapsed reads, very deep loci)
     uint8_t* nib = nullptr;
     int64_t* nib_tile_base = nullptr;
@@ -114,6 +165,7 @@ struct Segment {   // one staged pileup (pb2_push_pileup*)
     std::vector<int32_t> h_positions;
     bool called = false;
     bool temporary = false;   // built inside pb2_flush from staged reads; freed when the flush returns
+    bool from_reads = false;  // built by pb2_stage_reads: replaced by the next pb2_stage_reads, ignored by pb2_flush (which stages the reads itself)
     unsigned long long h_var_count = 0, h_exc_count = 0;
 };
 
@@ -138,7 +190,7 @@ struct pb2_handle {
     std::vector<int32_t> iv_start, iv_end;
     bool have_intervals = false;
     std::vector<Segment> segs;
-    HostReads reads;
+    DeviceReads reads;
     int32_t cleared_through = 0;   // positions <= this were called by an earlier pb2_flush(up_to >= 0)
     int* d_tile_counter = nullptr;
     std::vector<pb2_call_record> h_out;
@@ -147,6 +199,7 @@ struct pb2_handle {
     double hot_ms = 0;
     // ---- explicit candidates (pb2_explicit.cu)
     std::vector<HostCand> cands;                      // uncleared candidates in RegionState.AddCandidate order
+    std::unordered_map<int32_t, std::vector<uint32_t>> cand_by_pos;   // position -> indices into cands, in insertion order (explicit_reindex after a compaction)
     std::map<int32_t, int32_t> block_max_endpoint;    // RegionState.MaxAlleleEndpoint per 1000-bp block key
     std::map<int32_t, int32_t> gapped_ref;            // RegionState._gappedMnvReferenceCounts of uncleared positions
     std::vector<int32_t> triggers;                    // upTo values at which SmallVariantCaller.Execute would have called a batch
@@ -172,6 +225,7 @@ struct pb2_handle {
 int pb2_fail(pb2_handle* h, int code, const std::string& msg);
 // RegionState.AddCandidate (:94-174): merge into the table (summing counts) or append; tracks MaxAlleleEndpoint of the block.
 void explicit_add_candidate(pb2_handle* h, const HostCand& c);
+void explicit_reindex(pb2_handle* h);
 // The explicit-candidate part of AlleleCaller.Call for one batch of candidates (indices into h->cands, in batch order): VariantCollapser, MNV scoring
 // + MnvReallocator, gapped-MNV reference counts, final ProcessVariant of every callable allele on the device. Called alleles (IsCallable &&
 // ShouldReport) are appended to `called`; candidates that go back to the state (not cleared / MNV leftovers) are re-added to h->cands.
@@ -184,8 +238,12 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
 int explicit_materialize_snvs(pb2_handle* h, int32_t lo, int32_t hi);
 // SmallVariantCaller.AddForcedAlleleAsCandidate (:118-155): forced alleles at positions <= up_to (< 0: all) become zero-support candidates.
 int explicit_add_forced_candidates(pb2_handle* h, int32_t up_to);
-// Finds the candidates of the reads in R[first_read, end) on the device (CandidateVariantFinder.FindCandidates) and adds them to the table.
-int explicit_find_candidates(pb2_handle* h, const HostReads& R, size_t first_read);
+// Finds the candidates of the stored reads [first_read, end) on the device (CandidateVariantFinder.FindCandidates) and adds them to the table. host_bases:
+// the caller's bases array of the batch being pushed (read first_read starts at offset 0 of it), or nullptr (alleles longer than RawCand::read_bases
+// are then fetched from the device store).
+struct BatchHostView { const uint8_t* bases; const int64_t* seq_off; int64_t seq_lo; };   // bases points at the first base of the batch's first read
+int explicit_find_candidates(pb2_handle* h, size_t first_read, const BatchHostView* host);
+pb2::PvertPileup pvert_view(const Segment& s);
 // pb2_call_resident: gather + score + append on the device, no host round trip; only for candidates that need neither the collapser nor the MNV logic.
 int explicit_call_resident(pb2_handle* h, Segment& seg, cudaStream_t side);
 bool explicit_resident_ready(pb2_handle* h);

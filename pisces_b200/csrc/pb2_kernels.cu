@@ -9,6 +9,7 @@
 #include <cub/device/device_scan.cuh>
 #include "pb2_kernels.cuh"
 #include "pb2_math.cuh"
+#include "pb2_pvert.cuh"
 
 namespace pb2 {
 
@@ -1426,6 +1427,138 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    score_pending_kernel<<<num_sms * 4, 128, 0, stream>>>(in, ex, out, cfg);
+    return cudaGetLastError();
+}
+
+// ================================================================================================ PVERT: read-major, bit-sliced pileup (pb2_pvert.cuh)
+// The hot kernel of the reads path. Lane = locus, warp = tile of 32 loci. A block holds 32 rows (read stretches) of the tile bit-sliced per locus: two
+// coalesced 16-byte loads give a lane the planes B0 B1 Q5..Q0 of its 32 slots. The quality rule `q < minBQ -> N` (RegionStateManager.cs:180-181) is a
+// bit-serial comparison of the six quality planes against the bits of minBQ (one LOP3 per plane), the four allele indicators are one LOP3 each, and a
+// count is a POPC: about 30 instructions per 32 entries, no counters to read out. Direction, collapsed-read category and entry kind are properties of
+// the block's class, so stitched and collapsed-read data run through the same loop at the same byte per entry.
+template <bool kCollapsed>
+__global__ void __launch_bounds__(256, 4)
+pileup_pvert_score_kernel(const __grid_constant__ PvertPileup pv, const __grid_constant__ HotInputsExtra ex, const __grid_constant__ HotOutputs out,
+                          const __grid_constant__ DeviceConfig cfg, int* __restrict__ tile_counter) {
+    __shared__ __align__(16) PendingLocus s_pend[kCtaPending];
+    __shared__ int s_pend_n;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_pend_n = 0;
+    __syncthreads();
+    TilePileup in;   // what finish_locus / score_queued_locus read of the staged pileup
+    in.ref_base = pv.ref_base; in.positions = pv.positions; in.first_position = pv.first_position; in.n_loci = pv.n_loci; in.n_tiles = pv.n_tiles;
+    // bit i of minBQ as a lane-wide mask
+    uint32_t M[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) M[i] = ((cfg.min_bq >> i) & 1) ? 0xffffffffu : 0u;
+    const int nc = pv.n_classes;
+
+    auto grab = [&]() -> int {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    int next_tile = grab();
+    while (true) {
+        const int tile = next_tile;
+        if (tile >= pv.n_tiles) break;
+        const uint8_t* p = pv.data + pv.tile_row0[tile] * 32 + lane * 16;
+        const int32_t* ce = pv.cls_end + (int64_t)tile * nc;
+        const int total = ce[nc - 1];   // rows of the tile (multiple of 32)
+        int cnt[kNumAlleles][kNumDirs];
+#pragma unroll
+        for (int a = 0; a < kNumAlleles; a++)
+#pragma unroll
+            for (int d = 0; d < kNumDirs; d++) cnt[a][d] = 0;
+        int coll[kNumCollapsed];
+#pragma unroll
+        for (int t = 0; t < kNumCollapsed; t++) coll[t] = 0;
+
+        // blocks of all classes sit back to back: the loads run one block ahead of the counting, across class boundaries
+        uint4 nx = make_uint4(0, 0, 0, 0), ny = nx, nx2 = nx, ny2 = nx;
+        if (total > 0) { nx = ldg_stream(p); ny = ldg_stream(p + 512); }
+        if (total > 32) { nx2 = ldg_stream(p + 1024); ny2 = ldg_stream(p + 1536); }
+        int row = 0;
+#pragma unroll 1
+        for (int c = 0; c < nc; c++) {
+            const int end = ce[c];
+            if (end == row) continue;
+            int a0 = 0, a1 = 0, a2 = 0, a3 = 0, pres = 0;
+#pragma unroll 1
+            for (; row < end; row += 32) {
+                const uint4 x = nx, y = ny;
+                nx = nx2; ny = ny2;
+                if (row + 64 < total) { nx2 = ldg_stream(p + 2048); ny2 = ldg_stream(p + 2560); }
+                p += 1024;
+                // q >= minBQ, least significant plane first: ge_i = m_i ? (Q_i & ge) : (Q_i | ge)
+                uint32_t ge = y.w | ~M[0];
+                ge = (y.z & ge) | (~M[1] & (y.z | ge));
+                ge = (y.y & ge) | (~M[2] & (y.y | ge));
+                ge = (y.x & ge) | (~M[3] & (y.x | ge));
+                ge = (x.w & ge) | (~M[4] & (x.w | ge));
+                ge = (x.z & ge) | (~M[5] & (x.z | ge));
+                a0 += __popc(ge & ~x.y & ~x.x);
+                a1 += __popc(ge & ~x.y & x.x);
+                a2 += __popc(ge & x.y & ~x.x);
+                a3 += __popc(ge & x.y & x.x);
+                pres += __popc(x.x | x.y | x.z | x.w | y.x | y.y | y.z | y.w);
+            }
+            const int kind = pv_class_kind(c), dir = pv_class_dir(c);
+            const int counted = a0 + a1 + a2 + a3;
+#pragma unroll
+            for (int d = 0; d < kNumDirs; d++) {
+                if (d != dir) continue;
+                if (kind == 0) { cnt[AT_A][d] += a0; cnt[AT_G][d] += a1; cnt[AT_C][d] += a2; cnt[AT_T][d] += a3; cnt[AT_N][d] += pres - counted; }
+                else cnt[AT_DEL][d] += counted;
+            }
+            if (kCollapsed) {   // CollapsedRegionState.AddCollapsedReadCount (:28-44): every entry not counted as N, typed reads only
+                const int ct = pv_collapsed_code(pv_class_cg(c), dir);
+#pragma unroll
+                for (int t = 0; t < kNumCollapsed; t++) {
+                    if (ct == t + 1) coll[t] += counted;
+                    if (t == 2 && (ct - 1 == 4 || ct - 1 == 6)) coll[t] += counted;
+                    if (t == 3 && (ct - 1 == 5 || ct - 1 == 7)) coll[t] += counted;
+                }
+            }
+        }
+        next_tile = grab();
+        const int64_t locus = (int64_t)tile * kTileLoci + lane;
+        if (locus >= pv.n_loci) continue;
+        if (kCollapsed && out.collapsed_out != nullptr) {
+#pragma unroll
+            for (int t = 0; t < kNumCollapsed; t++) out.collapsed_out[locus * kNumCollapsed + t] = coll[t];
+        }
+        int any = 0;
+#pragma unroll
+        for (int a = 0; a < kNumAlleles; a++)
+#pragma unroll
+            for (int d = 0; d < kNumDirs; d++) any += cnt[a][d];
+        const int ref_allele = allele_of_base(pv.ref_base[locus]);
+        finish_locus(cnt, 0.0, any, locus, ref_allele, in, ex, out, cfg, s_pend, &s_pend_n);
+    }
+
+    __syncthreads();
+    {
+        const int n = min(s_pend_n, kCtaPending);
+        const int item = threadIdx.x >> 2;
+        score_queued_locus(item < n ? &s_pend[item] : nullptr, threadIdx.x & 3, in, ex, out, cfg);
+    }
+}
+
+cudaError_t launch_pvert_hot_kernel(const PvertPileup& pv, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
+                                    cudaStream_t stream) {
+    if (pv.n_tiles == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    const int grid = max(1, min(num_sms * 4, (pv.n_tiles + 7) / 8));
+    if (cfg.expect_collapsed) pileup_pvert_score_kernel<true><<<grid, 256, 0, stream>>>(pv, ex, out, cfg, tile_counter);
+    else pileup_pvert_score_kernel<false><<<grid, 256, 0, stream>>>(pv, ex, out, cfg, tile_counter);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    TilePileup in;
+    memset(&in, 0, sizeof(in));
+    in.ref_base = pv.ref_base; in.positions = pv.positions; in.first_position = pv.first_position; in.n_loci = pv.n_loci; in.n_tiles = pv.n_tiles;
     score_pending_kernel<<<num_sms * 4, 128, 0, stream>>>(in, ex, out, cfg);
     return cudaGetLastError();
 }

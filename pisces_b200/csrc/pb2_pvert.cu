@@ -1,0 +1,360 @@
+// Reads -> PVERT on the device (pb2_pvert.cuh): the staging side of pb2_push_reads / pb2_flush, and the 198-bin gather the explicit-candidate path
+// and pb2_get_counts read from it.
+//
+// Follows (reference @ /root/reference):
+//   RegionStateManager.AddAlleleCounts / GetAnchorType      src/lib/Pisces.Processing/RegionState/RegionStateManager.cs:83-220
+//   Read.PositionMap / SequencedBaseDirectionMap             src/lib/Pisces.Domain/Models/Read.cs:390-421,535-562
+//   CandidateVariantFinder.CheckDeletionQuality + the SNV open-end bookkeeping   src/lib/Pisces.Domain/Logic/CandidateVariantFinder.cs:90-203,294-320,496-553
+//   CollapsedRegionState.AddCollapsedReadCount               src/lib/Pisces.Processing/RegionState/CollapsedRegionState.cs:28-44
+#include <cub/device/device_scan.cuh>
+#include "pb2_internal.hpp"
+
+namespace pb2 {
+
+namespace {
+__device__ __forceinline__ bool pv_ref_span(int op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }   // M D N = X  (BamCommon.cs:560-573)
+__device__ __forceinline__ bool pv_read_span(int op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }  // M I S = X  (:575-588)
+__device__ __forceinline__ int pv_anchor_type(int end_pos, int base_pos, int start_pos) {   // RegionStateManager.GetAnchorType (:83-116), K = 5
+    const int left = base_pos - start_pos, right = end_pos - base_pos;
+    if (left >= right) return right >= kAnchorK ? kAnchorK : kNumAnchors - right - 1;
+    return left >= kAnchorK ? kAnchorK : left;
+}
+__device__ __forceinline__ int64_t pv_locus_index(const RegionView& rg, int position) {
+    if (position < rg.lo || position > rg.hi) return -1;
+    return rg.index_of_pos ? (int64_t)rg.index_of_pos[position - rg.lo] : (int64_t)(position - rg.lo);
+}
+__device__ __forceinline__ int pv_allele2(uint8_t b) { return b == 'A' ? 0 : b == 'G' ? 1 : b == 'C' ? 2 : b == 'T' ? 3 : -1; }   // AlleleType order A G C T
+
+// One row being written by a thread: the slots of the current (tile, class) stretch of its read, a 32-bit word (4 loci) at a time.
+struct RowState {
+    int64_t key;    // tile * n_classes + class, -1 = none
+    int64_t row;
+    int widx;       // word of the row being assembled, -1 = none
+    int tag;        // deletion rows: the anchor bin all entries of the row share (row_meta holds one per row)
+    uint32_t acc;
+};
+
+struct FillTargets {
+    const int64_t* tile_row0;
+    const int32_t* cls_end;
+    int32_t* cursor;
+    uint8_t* data;
+    int2* row_meta;
+    uint32_t* exc_entries;
+    unsigned long long* exc_count;
+    int64_t exc_capacity;
+};
+
+// Walks one read exactly as RegionStateManager.AddAlleleCounts does and hands every entry to the row writer. kFill = false: only the rows are counted
+// (same walk, same row boundaries: the two passes agree by construction).
+template <bool kFill>
+__device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, int n_classes, int32_t* cls_rows, const FillTargets& ft) {
+    const int64_t c0 = rv.cigar_off[r], c1 = rv.cigar_off[r + 1];
+    const int64_t s0 = rv.seq_off[r];
+    const int read_len = (int)(rv.seq_off[r + 1] - s0);
+    const int n_ops = (int)(c1 - c0);
+    if (n_ops == 0) return;
+    const int start_pos = rv.pos0[r] + 1;                                  // Read.Position
+    int ref_span = 0, max_mapped = -1;
+    {
+        int rp = start_pos;
+        for (int i = 0; i < n_ops; i++) {
+            const uint32_t c = rv.cigar[c0 + i];
+            const int op = c & 15, len = (int)(c >> 4);
+            if (pv_ref_span(op)) { ref_span += len; if (pv_read_span(op) && len > 0) max_mapped = rp + len - 1; rp += len; }
+        }
+    }
+    const int end_pos = rv.pos0[r] + ref_span;                             // Read.EndPosition (Read.cs:88-91)
+    if (end_pos < rg.lo || start_pos > rg.hi) {
+        // the read lies outside the staged window - unless a terminal deletion reaches into it (handled by the full walk below)
+        const int last_op0 = (int)(rv.cigar[c1 - 1] & 15);
+        if (last_op0 != 2 && !(n_ops >= 2 && (int)(rv.cigar[c1 - 2] & 15) == 2 && last_op0 == 4)) return;
+    }
+    const bool reverse = (rv.flag[r] & 0x10) != 0;
+    const int cg = (rg.expect_collapsed && rv.collapsed) ? pv_collapsed_group(rv.collapsed[r]) : 0;
+    const uint8_t* bases = rv.bases + s0;
+    const uint8_t* quals = rv.quals + s0;
+    const uint8_t* dirs = rv.base_dirs ? rv.base_dirs + s0 : nullptr;
+    auto dir_at = [&](int i) -> int { return dirs ? min((int)dirs[i], 2) : (reverse ? DIR_R : DIR_F); };
+    auto del_q = [&](int idx) -> int {  // CandidateVariantFinder.CheckDeletionQuality (:294-320): min of the flanking qualities
+        if (read_len == 0) return -1;
+        const int after = idx < read_len ? quals[idx] : quals[idx - 1];
+        const int before = idx > 0 ? quals[idx - 1] : after;
+        return min(before, after);
+    };
+    // terminal deletion bookkeeping (:127-137)
+    const int last_op = (int)(rv.cigar[c1 - 1] & 15);
+    const int prev_op = n_ops >= 2 ? (int)(rv.cigar[c1 - 2] & 15) : -1;
+    const bool ends_in_del = last_op == 2;
+    const bool ends_in_del_before_clip = prev_op == 2 && last_op == 4;
+    int del_len = 0, len_before_del = read_len;
+    if (ends_in_del || ends_in_del_before_clip) {
+        del_len = (int)(ends_in_del_before_clip ? (rv.cigar[c1 - 2] >> 4) : (rv.cigar[c1 - 1] >> 4));
+        len_before_del = ends_in_del_before_clip ? read_len - (int)(rv.cigar[c1 - 1] >> 4) : read_len;
+    }
+    // open-end annotation (:496-553): first / last non-soft-clip operation
+    int first_op = (int)(rv.cigar[c0] & 15);
+    if (first_op == 4 && n_ops >= 2) first_op = (int)(rv.cigar[c0 + 1] & 15);
+    int last_nonclip = last_op;
+    if (last_nonclip == 4 && n_ops >= 2) last_nonclip = prev_op;
+
+    RowState st[2];
+    st[0].key = st[1].key = -1; st[0].widx = st[1].widx = -1; st[0].acc = st[1].acc = 0; st[0].row = st[1].row = 0; st[0].tag = st[1].tag = 0;
+    auto flush_word = [&](RowState& s) {
+        if (kFill && s.widx >= 0 && s.acc != 0) *reinterpret_cast<uint32_t*>(ft.data + s.row * 32 + s.widx * 4) = s.acc;
+        s.widx = -1; s.acc = 0;
+    };
+    // one entry: kind 0 base / 1 deletion; `byte` is the slot value, meta what row_meta gets when the entry opens a row
+    auto put = [&](int kind, int position, int dir, uint32_t byte, int2 meta, int tag) -> int64_t {
+        const int64_t li = pv_locus_index(rg, position);
+        if (li < 0) return -1;
+        const int64_t tile = li >> 5;
+        const int l = (int)(li & 31);
+        const int64_t key = tile * n_classes + pv_class(kind, dir, cg);
+        RowState& s = st[kind];
+        if (key != s.key || tag != s.tag) {
+            flush_word(s);
+            s.key = key;
+            s.tag = tag;
+            if (kFill) {
+                const int cls = pv_class(kind, dir, cg);
+                const int k = atomicAdd(ft.cursor + key, 1);
+                s.row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[tile * n_classes + cls - 1] : 0) + k;
+                ft.row_meta[s.row] = meta;
+            } else {
+                atomicAdd(cls_rows + key, 1);
+            }
+        }
+        if (kFill) {
+            const int w = l >> 2;
+            if (w != s.widx) { flush_word(s); s.widx = w; }
+            s.acc |= byte << (8 * (l & 3));
+        }
+        return li;
+    };
+    auto put_del = [&](int position, int dir, int dq, int anchor) {
+        if (dq < rg.min_bq) return;          // a Deletion entry below the quality bar is never counted (:170-177)
+        put(1, position, dir, (uint32_t)min(max(dq, 1), 63), make_int2(INT32_MIN + anchor, 0), anchor);
+    };
+    const int2 read_meta = make_int2(start_pos, end_pos);
+
+    int read_idx = 0, ref_pos = start_pos, last_position = start_pos - 1;
+    for (int oi = 0; oi < n_ops; oi++) {
+        const uint32_t c = rv.cigar[c0 + oi];
+        const int op = c & 15, len = (int)(c >> 4);
+        const bool rs = pv_read_span(op), fs = pv_ref_span(op);
+        if (rs) {
+            if (!fs && !(ends_in_del_before_clip && read_idx <= len_before_del && len_before_del < read_idx + len)) { read_idx += len; continue; }   // I / S: not mapped
+            for (int k = 0; k < len; k++, read_idx++) {
+                const int dir = dir_at(read_idx);
+                if (ends_in_del_before_clip && read_idx == len_before_del) {      // (:148-159)
+                    const int dq = del_q(read_idx);
+                    for (int j = 1; j < del_len + 1; j++) put_del(j + last_position, dir, dq, kNumAnchors - 1);
+                }
+                if (!fs) continue;
+                const int position = ref_pos++;
+                if (position > last_position + 1) {                              // deletion (or N skip) before this base (:170-177)
+                    const int dq = del_q(read_idx);
+                    if (dq >= rg.min_bq) {
+                        const int an = pv_anchor_type(end_pos, position, start_pos);
+                        for (int j = max(last_position + 1, rg.lo); j < position && j <= rg.hi; j++) put_del(j, dir, dq, an);
+                    }
+                }
+                last_position = position;
+                if (position < rg.lo || position > rg.hi) continue;
+                const uint8_t b = bases[read_idx];
+                const int q = quals[read_idx];
+                const int a2 = pv_allele2(b);
+                const uint32_t byte = a2 < 0 ? 1u : ((uint32_t)a2 << 6) | (uint32_t)min(max(q, 1), 63);
+                const int64_t li = put(0, position, dir, byte, read_meta, 0);
+                if (!kFill || li < 0) continue;
+                // SNV-candidate bookkeeping the counts cannot express (CallMNVs off; CandidateVariantFinder.cs:90-168): only a usable mismatch against an
+                // A/C/G/T reference base can matter; it goes to the segment's side list (the rule of tile_scatter_kernel)
+                if (a2 < 0 || q < rg.min_bq) continue;
+                const bool in_chr = rg.chr == nullptr || position <= rg.chr_len;
+                const uint8_t rb = (rg.chr != nullptr && position >= 1 && position <= rg.chr_len) ? rg.chr[position - 1] : (uint8_t)'N';
+                const int ra2 = pv_allele2(rb);
+                if (ra2 < 0 || ra2 == a2) continue;
+                uint32_t code = 0;
+                if (op != 0 || !in_chr) code |= PB2_ENTRY_NO_CANDIDATE;
+                else {
+                    if (k + 1 < len) {   // open on the right: the next base of this operation exists and is unusable -> FlushVariant(..., openRight = true)
+                        const int nq = quals[read_idx + 1];
+                        const bool nb_n = pv_allele2(bases[read_idx + 1]) < 0;
+                        bool nref_n = false, n_in = true;
+                        if (rg.chr) {
+                            n_in = position + 1 <= rg.chr_len;
+                            if (n_in) nref_n = pv_allele2(rg.chr[position]) < 0;
+                        }
+                        if (n_in && (nq < rg.min_bq || nb_n || nref_n)) code |= PB2_ENTRY_OPEN_RIGHT;
+                    }
+                    if (first_op == 0 && position == start_pos) code |= PB2_ENTRY_OPEN_LEFT;
+                    if (last_nonclip == 0 && position == max_mapped) code |= PB2_ENTRY_OPEN_RIGHT;
+                }
+                if (code) {
+                    const unsigned long long slot = atomicAdd(ft.exc_count, 1ull);
+                    if ((int64_t)slot < ft.exc_capacity) {
+                        const int an = pv_anchor_type(end_pos, position, start_pos);
+                        const int cc = pv_collapsed_code(cg, dir);
+                        ft.exc_entries[2 * slot] = (uint32_t)li;
+                        ft.exc_entries[2 * slot + 1] = (code | (uint32_t)a2 | ((uint32_t)dir << 3)) | ((uint32_t)min(q, 127) << 8) | ((uint32_t)(an | (cc << 4)) << 16);
+                    }
+                }
+            }
+        } else if (fs) {
+            ref_pos += len;
+        }
+    }
+    if (ends_in_del && read_len > 0) {                                           // (:195-210)
+        const int dq = del_q(read_len - 1);
+        const int dir = dir_at(read_len - 1);
+        for (int j = 1; j < del_len + 1; j++) put_del(j + last_position, dir, dq, kNumAnchors - 1);
+    }
+    flush_word(st[0]);
+    flush_word(st[1]);
+}
+
+__global__ void pvert_count_kernel(ReadsView rv, RegionView rg, int n_classes, int32_t* __restrict__ cls_rows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rv.n_reads) return;
+    FillTargets ft{};
+    pv_walk_read<false>(rv, rg, r, n_classes, cls_rows, ft);
+}
+__global__ void pvert_fill_kernel(ReadsView rv, RegionView rg, int n_classes, FillTargets ft) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rv.n_reads) return;
+    pv_walk_read<true>(rv, rg, r, n_classes, nullptr, ft);
+}
+
+// rows per class -> inclusive prefix of the padded (multiple of 32) rows inside the tile; tile_rows[t] = rows of the tile
+__global__ void pvert_layout_kernel(int32_t* __restrict__ cls_rows, int32_t n_tiles, int n_classes, int64_t* __restrict__ tile_rows) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    if (t == n_tiles) { tile_rows[t] = 0; return; }
+    int32_t acc = 0;
+    for (int c = 0; c < n_classes; c++) {
+        acc += (cls_rows[(int64_t)t * n_classes + c] + 31) & ~31;
+        cls_rows[(int64_t)t * n_classes + c] = acc;
+    }
+    tile_rows[t] = acc;
+}
+
+// One warp per 1 KB block, in place: 32 rows x 32 slot bytes -> per lane (= locus) the eight bit planes of its 32 slots.
+constexpr int kTransposeWarps = 8;
+__global__ void __launch_bounds__(32 * kTransposeWarps) pvert_transpose_kernel(uint8_t* __restrict__ data, int64_t n_blocks) {
+    __shared__ __align__(16) uint8_t s_col[kTransposeWarps][32][36];   // [locus][row], padded: 9 words per locus, conflict-free column reads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * kTransposeWarps + warp;
+    if (b >= n_blocks) return;
+    uint8_t* blk = data + b * 1024;
+    // lane = row: its 32 slot bytes
+    const uint4 r0 = *reinterpret_cast<const uint4*>(blk + lane * 32), r1 = *reinterpret_cast<const uint4*>(blk + lane * 32 + 16);
+    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    if (__all_sync(0xffffffffu, (rw[0] | rw[1] | rw[2] | rw[3] | rw[4] | rw[5] | rw[6] | rw[7]) == 0)) return;   // an empty block stays all zero
+#pragma unroll
+    for (int l = 0; l < 32; l++) s_col[warp][l][lane] = (uint8_t)(rw[l >> 2] >> (8 * (l & 3)));
+    __syncwarp();
+    // lane = locus: its column, rows 0..31, eight rows per 64-bit word
+    uint32_t plane[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const uint32_t lo = *reinterpret_cast<const uint32_t*>(&s_col[warp][lane][8 * m]), hi = *reinterpret_cast<const uint32_t*>(&s_col[warp][lane][8 * m + 4]);
+        const unsigned long long t = pv_transpose8x8((unsigned long long)lo | ((unsigned long long)hi << 32));
+#pragma unroll
+        for (int k = 0; k < 8; k++) plane[k] |= (uint32_t)((t >> (8 * k)) & 0xffull) << (8 * m);   // bit k of rows 8m..8m+7
+    }
+    __syncwarp();
+    // slot byte: bit 7 b1, bit 6 b0, bits 5..0 quality.  half 0: B0 B1 Q5 Q4, half 1: Q3 Q2 Q1 Q0
+    *reinterpret_cast<uint4*>(blk + lane * 16) = make_uint4(plane[6], plane[7], plane[5], plane[4]);
+    *reinterpret_cast<uint4*>(blk + 512 + lane * 16) = make_uint4(plane[3], plane[2], plane[1], plane[0]);
+}
+
+__global__ void pvert_ref_bases_kernel(const uint8_t* __restrict__ chr, int64_t chr_len, const int32_t* __restrict__ positions, int32_t first_position, int64_t n_loci,
+                                       uint8_t* __restrict__ ref_base) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_loci) return;
+    const int64_t p = positions ? positions[i] : (int64_t)first_position + i;
+    ref_base[i] = (chr != nullptr && p >= 1 && p <= chr_len) ? chr[p - 1] : (uint8_t)'N';
+}
+
+// One warp per requested locus: lane j takes row 32 g + j of every 32-row group of every class of the locus' tile.
+constexpr int kPvGatherWarps = 4;
+__global__ void __launch_bounds__(32 * kPvGatherWarps)
+pvert_gather_kernel(PvertPileup in, const int32_t* __restrict__ req_locus, int32_t n_req, int32_t* __restrict__ out_counts, int32_t* __restrict__ out_collapsed, int min_bq) {
+    __shared__ int s_hist[kPvGatherWarps][kNumBins + kNumCollapsed];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * kPvGatherWarps + warp;
+    if (r >= n_req) return;
+    int* hist = s_hist[warp];
+    for (int b = lane; b < kNumBins + kNumCollapsed; b += 32) hist[b] = 0;
+    __syncwarp();
+    const int64_t locus = req_locus[r];
+    if (locus >= 0 && locus < in.n_loci) {
+        const int64_t tile = locus >> 5;
+        const int l = (int)(locus & 31);
+        const int32_t position = in.positions ? in.positions[locus] : in.first_position + (int32_t)locus;
+        const int64_t row0 = in.tile_row0[tile];
+        int32_t prev_end = 0;
+        for (int c = 0; c < in.n_classes; c++) {
+            const int32_t end = in.cls_end[tile * in.n_classes + c];
+            const int kind = pv_class_kind(c), dir = pv_class_dir(c), ct = pv_collapsed_code(pv_class_cg(c), dir);
+            for (int32_t g = prev_end; g < end; g += 32) {
+                const uint8_t* blk = in.data + (row0 + g) * 32;
+                const uint4 x = *reinterpret_cast<const uint4*>(blk + l * 16), y = *reinterpret_cast<const uint4*>(blk + 512 + l * 16);
+                const uint32_t b0 = (x.x >> lane) & 1u, b1 = (x.y >> lane) & 1u;
+                const uint32_t q = (((x.z >> lane) & 1u) << 5) | (((x.w >> lane) & 1u) << 4) | (((y.x >> lane) & 1u) << 3) | (((y.y >> lane) & 1u) << 2) |
+                                   (((y.z >> lane) & 1u) << 1) | ((y.w >> lane) & 1u);
+                if ((b0 | b1 | q) == 0) continue;   // empty slot
+                const int2 meta = in.row_meta[row0 + g + lane];
+                int allele, an;
+                if (kind == 1) { allele = AT_DEL; an = meta.x - INT32_MIN; }
+                else { allele = (int)q < min_bq ? AT_N : (int)(b0 | (b1 << 1)); an = pv_anchor_type(meta.y, position, meta.x); }   // RegionStateManager.cs:180-181
+                atomicAdd(&hist[(allele * kNumDirs + dir) * kNumAnchors + an], 1);
+                if (allele != AT_N && ct != 0) {   // CollapsedRegionState.AddCollapsedReadCount (:28-44)
+                    atomicAdd(&hist[kNumBins + ct - 1], 1);
+                    if (ct - 1 == 4 || ct - 1 == 6) atomicAdd(&hist[kNumBins + 2], 1);
+                    else if (ct - 1 == 5 || ct - 1 == 7) atomicAdd(&hist[kNumBins + 3], 1);
+                }
+            }
+            prev_end = end;
+        }
+        __syncwarp();
+    }
+    for (int b = lane; b < kNumBins; b += 32) out_counts[(int64_t)r * kNumBins + b] = hist[b];
+    if (out_collapsed != nullptr && lane < kNumCollapsed) out_collapsed[(int64_t)r * kNumCollapsed + lane] = hist[kNumBins + lane];
+}
+}  // namespace
+
+cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, int n_classes, int32_t* cls_rows, cudaStream_t st) {
+    if (rv.n_reads == 0) return cudaSuccess;
+    pvert_count_kernel<<<(rv.n_reads + 127) / 128, 128, 0, st>>>(rv, rg, n_classes, cls_rows);
+    return cudaGetLastError();
+}
+cudaError_t launch_pvert_layout(int32_t* cls_rows, int32_t n_tiles, int n_classes, int64_t* tile_rows, cudaStream_t st) {
+    pvert_layout_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(cls_rows, n_tiles, n_classes, tile_rows);
+    return cudaGetLastError();
+}
+cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
+                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, cudaStream_t st) {
+    if (rv.n_reads == 0) return cudaSuccess;
+    FillTargets ft{tile_row0, cls_end, cursor, data, row_meta, exc_entries, exc_count, exc_capacity};
+    pvert_fill_kernel<<<(rv.n_reads + 127) / 128, 128, 0, st>>>(rv, rg, n_classes, ft);
+    return cudaGetLastError();
+}
+cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st) {
+    if (n_blocks <= 0) return cudaSuccess;
+    pvert_transpose_kernel<<<(unsigned)((n_blocks + kTransposeWarps - 1) / kTransposeWarps), 32 * kTransposeWarps, 0, st>>>(data, n_blocks);
+    return cudaGetLastError();
+}
+cudaError_t launch_pvert_ref_bases(const uint8_t* chr, int64_t chr_len, const int32_t* positions, int32_t first_position, int64_t n_loci, uint8_t* ref_base, cudaStream_t st) {
+    if (n_loci <= 0) return cudaSuccess;
+    pvert_ref_bases_kernel<<<(unsigned)((n_loci + 255) / 256), 256, 0, st>>>(chr, chr_len, positions, first_position, n_loci, ref_base);
+    return cudaGetLastError();
+}
+cudaError_t launch_pvert_gather(const PvertPileup& in, const int32_t* req_locus, int32_t n_req, int32_t* out_counts, int32_t* out_collapsed, int min_bq, cudaStream_t st) {
+    if (n_req <= 0) return cudaSuccess;
+    pvert_gather_kernel<<<(n_req + kPvGatherWarps - 1) / kPvGatherWarps, 32 * kPvGatherWarps, 0, st>>>(in, req_locus, n_req, out_counts, out_collapsed, min_bq);
+    return cudaGetLastError();
+}
+
+}  // namespace pb2

@@ -234,6 +234,9 @@ __global__ void reads_candidates_kernel(ReadsView rv, int32_t first_read, const 
         rc.type = (uint8_t)type; rc.dir = (uint8_t)d;
         rc.flags = (uint8_t)((open_l ? 1 : 0) | (open_r ? 2 : 0) | (anchor > min(kAnchorK - 1, alt_len - 1) ? 4 : 0));
         rc.collapsed = (uint8_t)collapsed_code(cbyte, d);
+        const int n_from_read = type == CAT_INS ? alt_len - 1 : (type == CAT_DEL ? 0 : alt_len);
+#pragma unroll
+        for (int k = 0; k < 8; k++) rc.read_bases[k] = (k < n_from_read && start_idx + k < read_len) ? bases[start_idx + k] : (uint8_t)0;
         emit_raw(out, count, capacity, rc);
     };
     auto is_n = [](uint8_t b) { return !(b == 'A' || b == 'C' || b == 'G' || b == 'T'); };
@@ -291,6 +294,124 @@ __global__ void reads_candidates_kernel(ReadsView rv, int32_t first_read, const 
         if (op_read_span(op)) read_idx += len;
         if (op_ref_span(op)) ref_idx += len;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ the device read store (pb2_push_reads)
+__global__ void reads_ingest_kernel(ReadsView rv, int32_t first_read, int64_t cigar_base, int64_t seq_base, int64_t* __restrict__ cigar_off, int64_t* __restrict__ seq_off,
+                                    int32_t* __restrict__ end_pos, int32_t prev_key, int2* __restrict__ triggers, int32_t trigger_capacity, IngestStatus* __restrict__ status) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = rv.n_reads - first_read;
+    int lo = INT32_MAX, hi = 0;
+    if (j < nb) {
+        const int r = first_read + j;
+        // offsets as pushed (relative to the batch); the rebased values are written by the thread of the read they start (and thread nb - 1 the last one)
+        const int64_t c0 = cigar_off[r] + (j == 0 ? 0 : cigar_base), c1 = cigar_off[r + 1] + cigar_base;
+        const int64_t s0 = seq_off[r] + (j == 0 ? 0 : seq_base), s1 = seq_off[r + 1] + seq_base;
+        int err = 0;
+        if (c1 < c0 || s1 < s0) err = 4;
+        else if (rv.pos0[r] < 0) err = 3;
+        int64_t rs = 0, fs = 0;
+        if (!err) {
+            for (int64_t k = c0; k < c1; k++) {
+                const uint32_t c = rv.cigar[k];
+                const int op = c & 15;
+                if (op > 8) { err = 1; break; }
+                if (op_read_span(op)) rs += c >> 4;
+                if (op_ref_span(op)) fs += c >> 4;
+            }
+            if (!err && c1 > c0 && rs != s1 - s0) err = 2;
+        }
+        if (err) { if (atomicCAS(&status->error, 0, err) == 0) status->error_read = j; }
+        const int e = rv.pos0[r] + (int)fs;
+        end_pos[r] = e;
+        if (!err) { lo = rv.pos0[r] + 1; hi = e; }
+        const int up_to = rv.pos0[r];
+        const int key = up_to <= 0 ? 0 : (up_to + 999) / 1000;
+        int pk = prev_key;
+        if (j > 0) { const int pp = rv.pos0[r - 1]; pk = pp <= 0 ? 0 : (pp + 999) / 1000; }
+        if (key != pk) {
+            const int slot = atomicAdd(&status->n_triggers, 1);
+            if (slot < trigger_capacity) triggers[slot] = make_int2(r, up_to);
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { if (lo != INT32_MAX) atomicMin(&status->min_start, lo); if (hi > 0) atomicMax(&status->max_end, hi); }
+}
+__global__ void reads_rebase_kernel(int32_t first_read, int32_t nb, int64_t cigar_base, int64_t seq_base, int64_t* __restrict__ cigar_off, int64_t* __restrict__ seq_off) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < 1 || j > nb) return;   // entry `first_read` already holds the absolute start of the batch
+    cigar_off[first_read + j] += cigar_base;
+    seq_off[first_read + j] += seq_base;
+}
+cudaError_t launch_reads_ingest(const ReadsView& rv, int32_t first_read, int64_t cigar_base, int64_t seq_base, int64_t* cigar_off, int64_t* seq_off, int32_t* end_pos,
+                                int32_t prev_key, int2* triggers, int32_t trigger_capacity, IngestStatus* status, cudaStream_t st) {
+    const int nb = rv.n_reads - first_read;
+    if (nb <= 0) return cudaSuccess;
+    reads_ingest_kernel<<<(nb + 127) / 128, 128, 0, st>>>(rv, first_read, cigar_base, seq_base, cigar_off, seq_off, end_pos, prev_key, triggers, trigger_capacity, status);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    reads_rebase_kernel<<<(nb + 1 + 255) / 256, 256, 0, st>>>(first_read, nb, cigar_base, seq_base, cigar_off, seq_off);
+    return cudaGetLastError();
+}
+
+__global__ void reads_keep_flags_kernel(const int32_t* __restrict__ end_pos, int64_t n, int32_t cleared_to, const int64_t* __restrict__ cigar_off,
+                                        const int64_t* __restrict__ seq_off, int64_t* __restrict__ keep_reads, int64_t* __restrict__ keep_cigar, int64_t* __restrict__ keep_seq) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const bool keep = i < n && end_pos[i] > cleared_to;
+    keep_reads[i] = keep ? 1 : 0;
+    keep_cigar[i] = keep ? cigar_off[i + 1] - cigar_off[i] : 0;
+    keep_seq[i] = keep ? seq_off[i + 1] - seq_off[i] : 0;
+}
+cudaError_t launch_reads_keep_flags(const int32_t* end_pos, int64_t n, int32_t cleared_to, const int64_t* cigar_off, const int64_t* seq_off, int64_t* keep_reads,
+                                    int64_t* keep_cigar, int64_t* keep_seq, cudaStream_t st) {
+    reads_keep_flags_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(end_pos, n, cleared_to, cigar_off, seq_off, keep_reads, keep_cigar, keep_seq);
+    return cudaGetLastError();
+}
+// one warp per read: the kept reads move to their new places (exclusive scans of the keep flags / lengths)
+__global__ void reads_compact_kernel(ReadsCompactArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= a.n) return;
+    const int64_t ni = a.new_index[i];
+    if (a.new_index[i + 1] == ni) return;   // dropped
+    const int64_t c0 = a.cigar_off[i], nc = a.cigar_off[i + 1] - c0, s0 = a.seq_off[i], ns = a.seq_off[i + 1] - s0;
+    const int64_t oc = a.new_cigar[i], os = a.new_seq[i];
+    if (lane == 0) {
+        a.o_pos0[ni] = a.pos0[i]; a.o_end_pos[ni] = a.end_pos[i]; a.o_flag[ni] = a.flag[i];
+        a.o_cigar_off[ni] = oc; a.o_seq_off[ni] = os;
+        if (a.collapsed) a.o_collapsed[ni] = a.collapsed[i];
+        if (a.new_index[a.n] == ni + 1) { a.o_cigar_off[ni + 1] = oc + nc; a.o_seq_off[ni + 1] = os + ns; }   // the last kept read closes the offset arrays
+    }
+    for (int64_t k = lane; k < nc; k += 32) a.o_cigar[oc + k] = a.cigar[c0 + k];
+    for (int64_t k = lane; k < ns; k += 32) {
+        a.o_bases[os + k] = a.bases[s0 + k];
+        a.o_quals[os + k] = a.quals[s0 + k];
+        if (a.base_dirs) a.o_base_dirs[os + k] = a.base_dirs[s0 + k];
+    }
+}
+cudaError_t launch_reads_compact(const ReadsCompactArgs& a, cudaStream_t st) {
+    if (a.n <= 0) return cudaSuccess;
+    reads_compact_kernel<<<(unsigned)((a.n * 32 + 255) / 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+__global__ void reads_block_bitmap_kernel(const int32_t* __restrict__ pos0, const int32_t* __restrict__ end_pos, int64_t n, int32_t cleared_through, int32_t key0,
+                                          int32_t n_keys, uint32_t* __restrict__ bitmap) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = max(pos0[i] + 1, cleared_through + 1), e = end_pos[i];
+    if (a > e) return;
+    for (int k = (a + 999) / 1000; k <= (e + 999) / 1000; k++) {
+        const int b = k - key0;
+        if (b >= 0 && b < n_keys) atomicOr(bitmap + (b >> 5), 1u << (b & 31));
+    }
+}
+cudaError_t launch_reads_block_bitmap(const int32_t* pos0, const int32_t* end_pos, int64_t n, int32_t cleared_through, int32_t key0, int32_t n_keys, uint32_t* bitmap,
+                                      cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    reads_block_bitmap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos0, end_pos, n, cleared_through, key0, n_keys, bitmap);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_reads_candidates(const ReadsView& rv, int32_t first_read, const uint8_t* chr, int64_t chr_len, int min_bq, int call_mnvs, int max_mnv, int max_gap,

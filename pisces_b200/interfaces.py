@@ -389,6 +389,10 @@ class GpuStateManager:
         buf = (C.c_char * (96 * n.value)).from_address(out.value)
         return np.frombuffer(buf, dtype=N.RECORD_DTYPE).copy()
 
+    def StageReads(self):
+        """pb2_stage_reads: everything pushed through AddAlleleCounts / AddReadBatch becomes one device-resident segment for call_resident."""
+        self._chk(self._L.pb2_stage_reads(self._h))
+
     def call_resident(self):
         n = C.c_int64()
         self._chk(self._L.pb2_call_resident(self._h, C.byref(n)))
