@@ -1,12 +1,15 @@
 #!/usr/bin/env python
-"""bench.py — candidate loci scored per second on synthetic pileups of the BASELINE.json shape.
+"""bench.py — candidate loci scored per second on synthetic READ sets of the BASELINE.json shapes.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--loci L] [--depth D] [--gvcf 0|1]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5] [--loci L] [--depth D]
 
-A step = one pass of the hot path (pileup count + score + record compaction) over one batch of `loci` synthetic pileup columns per GPU.
-Default workload = BASELINE.json configs[1]: 1 M loci x depth ~Poisson(500), SNV (1 % of loci) + 1-3 bp insertions / deletions (0.1 % of loci,
-explicit candidates with spanning coverage), flat Poisson noise model NL 20, gVCF off, one B200. N>1 (torchrun): loci are sharded by interval across ranks (weak scaling: `loci` per GPU), no data-path
-collective; each step ends with the single all-gather of the per-rank call records (NCCL).
+The input is reads (struct of arrays, as IStateManager.AddAlleleCounts(Read) receives them): the pileup is built on the device.
+  value  a step = one pass of the hot path (pileup count + score + explicit candidates + record compaction) over the `loci` of this GPU, the staged
+         pileup resident in HBM (pb2_stage_reads once, then pb2_call_resident per step);
+  e2e    the same through the C ABI from HOST buffers: pb2_push_reads (pinned H2D of the reads), device staging, pb2_flush (records back on the host).
+Default workload = BASELINE.json configs[1] (c2): 1 M loci x depth ~Poisson(500) (3.57 M reads of 140 bases), SNV (1 % of loci) + 1-3 bp insertions /
+deletions (0.1 % of loci), flat Poisson noise model NL 20, gVCF off, one B200. N>1 (torchrun): loci are sharded by interval across ranks (weak scaling:
+`loci` per GPU), no data-path collective; the job ends with the single all-gather of the per-rank call records (NCCL).
 """
 import argparse
 import json
@@ -23,21 +26,38 @@ METRIC = "candidate loci scored/sec"
 UNIT = "loci/s"
 
 
+# BASELINE.json configs[1..4]: generator arguments (pisces_b200.synth.make_reads), caller options, per-GPU size. configs[2..4] name
+# whole-job sizes of 10 M / 50 M / 200 M loci on 1 / 4 / 8 GPUs; a bench step covers `loci` per GPU (stated in config.workload), larger jobs are more steps.
+CONFIGS = {
+    "c2": dict(loci=1_000_000, depth=500, seed=2, gen=dict(indel_rate=0.001), cfg=dict(output_gvcf=0),
+               what="SNV 1% + indel 0.1%, Poisson noise model NL20, gvcf=0 (BASELINE.json configs[1] shape and size)"),
+    "c3": dict(loci=1_000_000, depth=1000, seed=3, gen=dict(indel_rate=0.0, snv_rate=0.005), cfg=dict(output_gvcf=1),
+               what="SNV 0.5%, gVCF mode: every locus emits a reference record (BASELINE.json configs[2] shape; 10 M loci = 10 such steps)"),
+    "c4": dict(loci=500_000, depth=2000, seed=4, gen=dict(indel_rate=0.0, mnv_pair_rate=0.002, strand_skew_frac=0.1),
+               cfg=dict(output_gvcf=0, call_mnvs=1, max_size_mnv=3, max_gap_mnv=1),
+               what="CallMNVs (MaxSizeMNV 3, gap 1), adjacent-SNV pairs 0.2%, strand skew on 10% of variants (BASELINE.json configs[3] shape; 50 M loci / 4 GPUs = 25 such steps per GPU)"),
+    "c5": dict(loci=1_000_000, depth=300, seed=5, gen=dict(indel_rate=0.001, mnv_pair_rate=0.001, collapsed_frac=0.5, stitched_frac=0.5),
+               cfg=dict(output_gvcf=0, call_mnvs=1, expect_collapsed=1, expect_stitched=1),
+               what="SNV/MNV/indel, 50% collapsed reads (duplex 20%), 50% stitched reads (BASELINE.json configs[4] shape; 200 M loci / 8 GPUs = 25 such steps per GPU)"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--loci", type=int, default=1_000_000, help="loci per GPU")
-    ap.add_argument("--depth", type=int, default=500)
-    ap.add_argument("--depth-dist", default="poisson", choices=["poisson", "fixed"])
-    ap.add_argument("--gvcf", type=int, default=0)
-    ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--indel-rate", type=float, default=0.001)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configs[1..4] shapes")
+    ap.add_argument("--loci", type=int, default=0, help="loci per GPU (0: the config's)")
+    ap.add_argument("--depth", type=int, default=0, help="mean depth (0: the config's)")
+    ap.add_argument("--gvcf", type=int, default=-1, help="override the config's gVCF mode")
+    ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--tune-ctas", type=int, default=0, help="hot-kernel CTAs per SM (tuning experiments)")
-    ap.add_argument("--tune-prefetch", type=int, default=0, help="hot-kernel L2 prefetch distance (tuning experiments)")
-    ap.add_argument("--cpu-sample-loci", type=int, default=200_000)
+    ap.add_argument("--tune-prefetch", type=int, default=0, help="tuning experiments (9: PTILE32 staging instead of PVERT)")
+    ap.add_argument("--cpu-sample-loci", type=int, default=100_000)
+    ap.add_argument("--cpu-repeats", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -110,83 +130,110 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def resolve(a):
+    c = CONFIGS[a.config]
+    a.loci = a.loci or c["loci"]
+    a.depth = a.depth or c["depth"]
+    a.seed = a.seed or c["seed"]
+    a.gen = dict(c["gen"])
+    a.cfg = dict(c["cfg"])
+    if a.gvcf >= 0:
+        a.cfg["output_gvcf"] = a.gvcf
+    return a
+
+
 def workload_name(a):
-    return (f"synthetic {a.loci} loci x depth {'~Poisson' if a.depth_dist == 'poisson' else '='}({a.depth}) per GPU, SNV 1% + indel {100 * a.indel_rate:g}%, "
-            f"Poisson noise model NL20, gvcf={a.gvcf} (BASELINE.json configs[1] shape)")
+    return f"{a.config}: synthetic reads (length 140) over {a.loci} loci x depth ~Poisson({a.depth}) per GPU; {CONFIGS[a.config]['what']}"
 
 
-def oracle_config(a):
+def oracle_caller(a, ref):
     from oracle import binding as ob
-    return ob.default_config(output_gvcf=a.gvcf, collapse=1)
+    kw = dict(a.cfg)
+    if "expect_stitched" in kw:
+        kw["source_is_stitched"] = kw.pop("expect_stitched")
+    if "expect_collapsed" in kw:
+        kw["source_is_collapsed"] = kw.pop("expect_collapsed")
+    return ob.Caller(ob.default_config(collapse=1, **kw), "chr1", ref)
 
 
-def run_oracle_slices(a, d, n_threads, loci_per_thread):
-    """Times the CPU restatement (count + call, no I/O) on n_threads disjoint slices, one thread each. Returns (seconds, loci)."""
+def reads_window(d, lo, hi):
+    """The reads whose start lies in [lo, hi) (0-based) as views, their positions rebased to the window, + the window's reference."""
     import numpy as np
-    from oracle import binding as ob
-    off = d["offsets"].cpu().numpy()
-    slices = []
-    for t in range(n_threads):
-        l0, l1 = t * loci_per_thread, (t + 1) * loci_per_thread
-        e0, e1 = int(off[l0]), int(off[l1])
-        ref = bytes(d["ref_bases"][l0:l1].cpu().numpy()).decode()
-        cands = []
-        if d.get("candidates") is not None:
-            arena = d["arena"]
-            for c in d["candidates"]:
-                p = int(c["position"])
-                if l0 + 1 <= p and p + int(c["ref_len"]) + 1 <= l1:
-                    o, rl, al = int(c["allele_offset"]), int(c["ref_len"]), int(c["alt_len"])
-                    cands.append((int(c["type"]), p - l0, arena[o:o + rl].decode(), arena[o + rl:o + rl + al].decode(), [int(x) for x in c["support"]],
-                                  [int(x) for x in c["well_anchored"]]))
-        slices.append((ob.Caller(oracle_config(a), "chr1", ref), (off[l0:l1 + 1] - e0).astype(np.int64), d["code"][e0:e1].cpu().numpy(),
-                       d["qual"][e0:e1].cpu().numpy(), d["anchor"][e0:e1].cpu().numpy(), cands))
+    r0, r1 = int(np.searchsorted(d["pos0"], lo, "left")), int(np.searchsorted(d["pos0"], hi, "left"))
+    L = d["read_len"]
+    end = min(len(d["ref"]), hi + L + 8)
+    out = dict(pos0=d["pos0"][r0:r1] - lo, flag=d["flag"][r0:r1], cigar_off=d["cigar_off"][r0:r1 + 1] - d["cigar_off"][r0], seq_off=d["seq_off"][r0:r1 + 1] - d["seq_off"][r0],
+               cigar=d["cigar"][d["cigar_off"][r0]:d["cigar_off"][r1]], bases=d["bases"][d["seq_off"][r0]:d["seq_off"][r1]],
+               quals=d["quals"][d["seq_off"][r0]:d["seq_off"][r1]], ref=bytes(d["ref"][lo:end]).decode(),
+               collapsed=None if d.get("collapsed") is None else d["collapsed"][r0:r1], xd_runs=None if d.get("xd_runs") is None else d["xd_runs"][r0:r1])
+    return out
 
-    def work(s):
-        c, o, co, q, an, cands = s
-        for t, p, r, al, sup, wa in cands:
-            c.add_candidate(t, p, r, al, sup, wa)
-        c.add_pileup(o, co, q, an, 1, call_every=1)
-        c.finish()
-    ths = [threading.Thread(target=work, args=(s,)) for s in slices]
+
+def run_oracle(a, w):
+    """The CPU restatement over one window of reads: SmallVariantCaller.Execute's per-read loop (find candidates, count, call). Returns (seconds, caller)."""
+    oc = oracle_caller(a, w["ref"])
     t0 = time.perf_counter()
-    for th in ths:
-        th.start()
-    for th in ths:
-        th.join()
-    return time.perf_counter() - t0, n_threads * loci_per_thread
+    oc.add_reads_soa(w["pos0"], w["flag"], w["cigar_off"], w["cigar"], w["seq_off"], w["bases"], w["quals"], w.get("collapsed"), w.get("xd_runs"))
+    oc.finish()
+    return time.perf_counter() - t0, oc
 
 
 def main_reference(a):
     """Reference arm: the reference's CPU implementation of the path. The C# cannot run here (no dotnet runtime in the image), so this is
-    the oracle port (oracle/) on all host threads, each step a bounded sample of the same workload."""
+    the oracle port (oracle/) on all host threads, each step a bounded sample of the same workload: every thread runs the reference's per-read loop
+    over its own window of the read set."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     from pisces_b200 import synth
     cores = os.cpu_count() or 1
-    per_thread = max(1000, min(20_000, a.loci // cores))
+    per_thread = max(1000, min(8_000, a.loci // cores))
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    d = synth.make_pileup(cores * per_thread, a.depth, seed=a.seed, device=dev, depth_dist=a.depth_dist, indel_rate=a.indel_rate)
-    d = {k: (v.cpu() if hasattr(v, "cpu") else v) for k, v in d.items()}
+    d = synth.make_reads(cores * per_thread + 200, a.depth, seed=a.seed, device=dev, **a.gen)
+    wins = [reads_window(d, t * per_thread, (t + 1) * per_thread) for t in range(cores)]
     times = []
     for i in range(a.warmup + a.steps):
-        dt, loci = run_oracle_slices(a, d, cores, per_thread)
+        ths = [threading.Thread(target=run_oracle, args=(a, w)) for w in wins]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
         if i >= a.warmup:
-            times.append(dt)
+            times.append(time.perf_counter() - t0)
     total = sum(times)
     value = a.steps * cores * per_thread / total
-    sample = f"{cores} threads x {per_thread} loci per step ({cores * per_thread} loci, depth {a.depth}) of the same synthetic workload"
+    sample = f"{cores} threads x {per_thread} loci per step ({cores * per_thread} loci, depth {a.depth}) of the same synthetic read set"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "note": "oracle port of the C# path (dotnet runtime absent); count+call only, no I/O"},
+        "config": {"workload": workload_name(a), "loci_per_gpu": a.loci,
+                   "note": "oracle port of the C# path (dotnet runtime absent): SmallVariantCaller.Execute's per-read loop, no I/O"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def compare_with_oracle(orecs, precs, arena, limit):
+    """Records of the oracle run on a sample window against the product's records of the same positions (<= limit). Returns (compared, mismatches)."""
+    mism = 0
+    o = [r for r in orecs if r.pos <= limit]
+    p = [r for r in precs if int(r["position"]) <= limit]
+    if len(o) != len(p):
+        return max(len(o), len(p)), abs(len(o) - len(p)) + 1
+    for x, y in zip(o, p):
+        rl, al, ab = int(y["ref_len"]), int(y["alt_len"]), int(y["allele_bytes"])
+        raw = ab.to_bytes(4, "little") if rl + al <= 4 else bytes(arena[ab:ab + rl + al])
+        ok = (x.pos == int(y["position"]) and x.type == int(y["type"]) and raw[:rl].decode() == x.ref and raw[rl:rl + al].decode() == x.alt and
+              x.total_coverage == int(y["total_coverage"]) and x.allele_support == int(y["allele_support"]) and x.ref_support == int(y["reference_support"]) and
+              x.vq == int(y["variant_qscore"]) and x.gq == int(y["genotype_qscore"]) and x.genotype == int(y["genotype"]) and x.filter_mask == int(y["filters"]) and
+              list(x.cov) == list(y["coverage_by_direction"]) and list(x.support) == list(y["support_by_direction"]) and x.num_no_calls == int(y["num_no_calls"]))
+        mism += 0 if ok else 1
+    return len(o), mism
+
+
 def main_ours(a):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import pisces_b200 as pb
@@ -202,21 +249,32 @@ def main_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = f"cuda:{local}"
 
-    # ---- synthetic shard for this rank, resident in HBM (interval shard `rank` of `world`)
-    d = synth.make_pileup(a.loci, a.depth, seed=a.seed + 1000 * rank, device=dev, depth_dist=a.depth_dist, indel_rate=a.indel_rate)
+    # ---- synthetic read set of this rank (interval shard `rank` of `world`), generated on the device, kept on the host in pinned memory
+    d = synth.make_reads(a.loci, a.depth, seed=a.seed + 1000 * rank, device=dev, **a.gen)
+    torch.cuda.empty_cache()
     n_entries = d["n_entries"]
-    ref = bytes(d["ref_bases"].cpu().numpy())
-    cfg = pb.make_config(device=local, output_gvcf=a.gvcf)
+    ref = bytes(d["ref"]).decode()
+    keys = ["pos0", "flag", "cigar_off", "cigar", "seq_off", "bases", "quals"] + [k for k in ("base_dirs", "collapsed") if d.get(k) is not None]
+    view = {"flag": np.int16, "cigar": np.int32}
+    pinned = {k: torch.from_numpy(d[k].view(view[k]) if k in view else d[k]).pin_memory() for k in keys}
+    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in pinned.values())
+    cfg = pb.make_config(device=local, **a.cfg)
     cfg.reserved[0] = a.tune_ctas
     cfg.reserved[1] = a.tune_prefetch
     sm = pb.GpuStateManager(cfg, "chr1", ref)
-    sm.AddPileup(d["offsets"], d["code"], d["qual"], d["anchor"], first_position=1, ref_bases=d["ref_bases"], device=True)
-    if d.get("candidates") is not None:
-        sm.AddCandidates(d["candidates"], d["arena"])
+    sm.AddReadsSoA(pinned)
+    sm.StageReads()
+    stage = sm.stage_stats()
+    # the whole job from device-resident reads (candidates found again, pileup staged again, called): reported beside the staged-pileup step
+    sm.flush_resident()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        sm.flush_resident()
+    from_reads_ms = 1e3 * (time.perf_counter() - t0) / 2
+    sm.StageReads()
     torch.cuda.synchronize()
 
     import ctypes as C
-    from pisces_b200 import _native as N
 
     class DevBuf:   # torch view of a device buffer owned by the library
         def __init__(self, ptr, nbytes):
@@ -227,7 +285,7 @@ def main_ours(a):
     # once); when the K steps are done the ranks exchange [K int64 counts | K x fixed-capacity record blocks] in ONE all_gather, inside the timed region.
     job_buf = gather_out = var_view = counts_pinned = None
     n_slots = max(1, a.steps)
-    if world > 1:
+    if world > 1 and resident_ok:
         n0 = sm.call_resident()
         n0_all = torch.tensor([n0], dtype=torch.int64, device=dev)
         dist.all_reduce(n0_all, op=dist.ReduceOp.MAX)    # the ranks' shards differ: the block capacity (hence the gathered size) must be the same on all
@@ -240,9 +298,15 @@ def main_ours(a):
         gather_out = torch.zeros(world * job_buf.numel(), dtype=torch.uint8, device=dev)
         counts_pinned = torch.zeros(n_slots, dtype=torch.int64).pin_memory()
 
+    # configurations whose SNV / MNV candidates come from the candidate finder (CallMNVs) need the collapser / MNV reallocator of pb2_flush: their step is
+    # the whole job from the device-resident reads (pb2_flush_resident); the others run the resident staged-pileup step (pb2_call_resident)
+    resident_ok = not a.cfg.get("call_mnvs")
+
     def step(k=0):
+        if not resident_ok:
+            return len(sm.flush_resident())
         n = sm.call_resident()   # returns after the step's counters are on the host: the library's stream is idle, the variant stream complete
-        if world > 1:
+        if world > 1 and resident_ok:
             slot = k % n_slots
             counts_pinned[slot] = min(n, cap_records)
             o = 8 * n_slots + slot * cap_records * 96
@@ -250,7 +314,7 @@ def main_ours(a):
         return n
 
     def gather_job():
-        if world > 1:
+        if world > 1 and resident_ok:
             job_buf[:8 * n_slots].copy_(counts_pinned.view(torch.uint8), non_blocking=True)
             dist.all_gather_into_tensor(gather_out, job_buf)
 
@@ -290,11 +354,9 @@ def main_ours(a):
     dt = float(tmax.item())
     value = world * a.loci * a.steps / dt
 
-    # ---- roofline of the dominant (only) kernel: algorithmic bytes / CUDA-event duration on the launching stream
-    n_ref_records = a.loci if a.gvcf else 0
-    # point alleles (SNV / reference) never read the anchor/collapsed byte: without collapsed-read tracking the hot kernel skips that plane,
-    # and the algorithmic bytes are SURVEY 8d's 2*D + 8 + 96*E form
-    third_byte = bool(cfg.expect_collapsed)
+    # ---- roofline of the dominant kernel: algorithmic bytes (B = 2 D + 8 + 96 E per locus; 3 D with collapsed-read tracking) / CUDA-event duration
+    n_ref_records = a.loci if a.cfg.get("output_gvcf") else 0
+    third_byte = bool(a.cfg.get("expect_collapsed"))
     algo_bytes = synth.algorithmic_bytes(a.loci, n_entries, n_records + n_ref_records, third_byte=third_byte)
     hot_ms = st["hot_ms"] / max(1, st["hot_launches"])
     achieved = algo_bytes / (hot_ms * 1e-3) / 1e9
@@ -304,73 +366,76 @@ def main_ours(a):
         peak_src = "measured"
     except Exception:
         pass
-    # which hot kernel ran: the PNIB16 one (direction-split, nibble-packed pileup: 1.5 staged bytes per entry) unless collapsed-read tracking / quality
-    # sums are on or it is switched off for comparison (--tune-prefetch 9 -> the PTILE32 vertical-counter kernel, 2 staged bytes per entry)
-    nib = not cfg.expect_collapsed and not cfg.want_sum_base_quality and cfg.noise_model != 1 and a.tune_prefetch != 9
-    kernel_name = "pileup_nib_score_kernel" if nib else "pileup_vcount_score_kernel"
+    pvert = a.tune_prefetch != 9
+    kernel_name = "pileup_pvert_score_kernel" if pvert else "pileup_nib_score_kernel"
     traffic = None
-    try:   # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture of this command (default workload only)
-        if a.loci == 1_000_000 and a.depth == 500 and a.indel_rate == 0.001 and (nib or not a.gvcf):
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[kernel_name + ("_gvcf" if a.gvcf else "")]["dram_bytes_per_launch"]
+    try:   # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture of this command
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[kernel_name + "_" + a.config]["dram_bytes_per_launch"]
+        if a.loci != CONFIGS[a.config]["loci"] or a.depth != CONFIGS[a.config]["depth"]:
+            traffic = None
     except Exception:
         pass
-
+    staged_bytes = stage["staged_bytes"] + 96 * (n_records + n_ref_records)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": 1e3 * dt / a.steps, "wall_ms_per_step": 1e3 * dt_wall / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "loci_per_gpu": a.loci, "entries_per_gpu": n_entries, "records_per_step": n_records + n_ref_records,
-                       "l2": "staged input of the hot kernel (%.2f GB per GPU) larger than L2, no flush needed" % ((1.5 if nib else 2) * n_entries / 1e9), "parallelism": f"interval-sharded x{world}"},
+            "config": {"workload": workload_name(a), "loci_per_gpu": a.loci, "reads_per_gpu": d["n_reads"], "entries_per_gpu": n_entries,
+                       "records_per_step": n_records + n_ref_records,
+                       "l2": "staged input of the hot kernel (%.2f GB per GPU) larger than L2, no flush needed" % (stage["staged_bytes"] / 1e9), "parallelism": f"interval-sharded x{world}"},
             "gpu_launches": st["total_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": kernel_name, "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_entry": 3 if third_byte else 2,
-                         "staged_bytes_per_entry": 1.5 if nib else (3 if third_byte else 2),
+                         # what the kernel physically reads: the staged (PVERT) form is one byte per slot, denser than the model's 2-3 bytes per entry, so `frac`
+                         # can exceed the DRAM rate; frac_staged = staged bytes / kernel time / peak is the physical fraction of the HBM roofline
+                         "staged_bytes_per_launch": staged_bytes, "staged_bytes_per_entry": stage["staged_bytes"] / max(1, n_entries),
+                         "frac_staged": staged_bytes / (hot_ms * 1e-3) / 1e9 / peak,
                          "dram_frac": (traffic / (hot_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                         "kernel_ms": hot_ms,
-                         # the same kernel over blocks of 10 timed steps: on this pool the kernel runs at one of two plateaus (x1.0 / x1.5) that
-                         # switch on a seconds scale with no clock change or throttle reason reported (profiles/r1_summary.md, "machine state")
+                         "kernel_ms": hot_ms, "staging_ms": stage["stage_ms"],
+                         "from_resident_reads": {"ms_per_step": from_reads_ms, "value": a.loci / (from_reads_ms * 1e-3), "unit": UNIT,
+                                                 "what": "find candidates + stage + call from reads resident in HBM (pb2_flush_resident), one GPU"},
+                         "value_step": "pb2_call_resident (staged pileup resident)" if resident_ok else "pb2_flush_resident (reads resident; CallMNVs needs the host collapser / reallocator)",
                          "kernel_ms_blocks": {"min": per_block[0], "median": per_block[len(per_block) // 2], "max": per_block[-1]}},
             "clocks": sampler.summary()}
 
-    # ---- end to end through the C ABI with HOST buffers: pinned H2D of the step's pileup, tile staging, call, D2H of the records
+    # ---- end to end through the C ABI with HOST buffers: pinned H2D of the step's reads, device staging, call, D2H of the records
+    precs = arena = None
     if not a.no_e2e:
-        # host buffers in PB2_LAYOUT_PACKED2 (2 bytes per entry + the sparse candidate flags): what a host behind a PCIe link hands to pb2_push_pileup
-        pc, pq, fi, fb = pb.GpuStateManager.pack_pileup(d["code"].cpu().numpy(), d["qual"].cpu().numpy(), d["anchor"].cpu().numpy(), d["offsets"].cpu().numpy(),
-                                                        d["ref_bases"].cpu().numpy())
-        h = {"offsets": d["offsets"].cpu().pin_memory(), "ref_bases": d["ref_bases"].cpu().pin_memory(), "pcode": torch.from_numpy(pc).pin_memory(),
-             "pqual": torch.from_numpy(pq).pin_memory(), "flag_index": torch.from_numpy(fi).pin_memory(), "flag_bits": torch.from_numpy(fb).pin_memory()}
-        del pc, pq
         sm2 = pb.GpuStateManager(cfg, "chr1", ref)
         caller = pb.GpuAlleleCaller()
-        e2e_steps = max(2, min(a.steps, 4))
+        e2e_steps = max(2, min(a.steps, a.e2e_steps))
 
         def e2e_step():
-            sm2.AddPileupPacked(h["offsets"].numpy(), h["pcode"].numpy(), h["pqual"].numpy(), h["flag_index"].numpy(), h["flag_bits"].numpy(), first_position=1,
-                                ref_bases=h["ref_bases"].numpy())
-            if d.get("candidates") is not None:
-                sm2.AddCandidates(d["candidates"], d["arena"])
+            sm2.AddReadsSoA(pinned)
             recs = caller.Call(sm2, raw=True)
-            sm2.DoneProcessing()
-            return len(recs)
-        e2e_step()
+            return recs
+        precs = e2e_step()
+        arena = sm2.AlleleArena()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            nrec = e2e_step()
+            nrec = len(e2e_step())
         barrier()
         edt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(edt, op=dist.ReduceOp.MAX)
-        line["e2e"] = {"value": world * a.loci * e2e_steps / float(edt.item()), "unit": UNIT, "h2d_bytes_per_step": 2 * n_entries + 8 * (a.loci + 1) + a.loci + 9 * int(h["flag_index"].numel()),
-                       "d2h_bytes_per_step": 96 * nrec, "steps": e2e_steps}
+        line["e2e"] = {"value": world * a.loci * e2e_steps / float(edt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 96 * nrec,
+                       "steps": e2e_steps, "ms_per_step": 1e3 * float(edt.item()) / e2e_steps, "input": "reads (struct of arrays, 2 B per base + 18 B per read), pinned host memory"}
         sm2.close()
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample, single thread like one Pisces (BAM x chr) job
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample, single thread like one Pisces (BAM x chr) job; the same run
+    # verifies the records of the timed workload on the sample's positions
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         s_loci = min(a.cpu_sample_loci, a.loci)
-        dd = {k: (v[: int(d["offsets"][s_loci]) if k in ("code", "qual", "anchor") else s_loci + 1 if k == "offsets" else s_loci].cpu() if hasattr(v, "cpu") else v)
-              for k, v in d.items()}
-        cdt, cl = run_oracle_slices(a, dd, 1, s_loci)
-        line["cpu_baseline"] = {"value": cl / cdt, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"first {s_loci} loci of the same workload, single thread (count + call, no I/O)"}
+        w = reads_window(d, 0, s_loci)
+        best, oc = None, None
+        for _ in range(max(1, a.cpu_repeats)):
+            cdt, oc = run_oracle(a, w)
+            best = cdt if best is None else min(best, cdt)
+        line["cpu_baseline"] = {"value": s_loci / best, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"reads starting in the first {s_loci} loci of the same workload, single thread, best of {max(1, a.cpu_repeats)} "
+                                          "(find candidates + count + call, no I/O)"}
+        if precs is not None:
+            n_cmp, n_bad = compare_with_oracle(oc.records(), precs, arena, s_loci - d["read_len"] - 8)
+            line["verified"] = {"records_compared_with_oracle": n_cmp, "mismatches": n_bad, "positions": f"1..{s_loci - d['read_len'] - 8}"}
     sm.close()
     if rank == 0:
         print(json.dumps(line))
@@ -379,7 +444,7 @@ def main_ours(a):
 
 
 if __name__ == "__main__":
-    args = parse()
+    args = resolve(parse())
     if args.impl == "reference":
         main_reference(args)
     else:

@@ -244,6 +244,9 @@ int pb2_resident_results(pb2_handle* h, const pb2_call_record** ref_records, con
 /* IAlleleCaller.Call for everything staged up to up_to_position (-1 = all): runs pb2_call_resident if needed, copies the
  * records to the host ordered by (position, ref, alt) as AlleleCaller.cs:96-140,172-176 orders them. */
 int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n);
+/* pb2_flush(-1) for everything pushed through pb2_push_reads with the reads kept on the device: candidates are found again in the stored reads, the
+ * batches replayed, nothing is consumed - the whole job from device-resident reads, repeatable. */
+int pb2_flush_resident(pb2_handle* h, const pb2_call_record** out, int64_t* n);
 /* The pb2_call_record_ext rows of the records the last pb2_flush returned (valid until the next flush). */
 int pb2_flush_ext(pb2_handle* h, const pb2_call_record_ext** out, int64_t* n);
 /* Parity hook = IAlleleSource.GetAlleleCount over a position range: out[n][6][3][11] int32 (RegionState._alleleCounts). */
@@ -304,6 +307,9 @@ int pb2_totals(pb2_handle* h, int64_t* total_collapsed);
 /* Timing/diagnostics for bench.py: kernel launches and device milliseconds of the hot kernel since the last call, measured with
  * CUDA events on the handle's stream. */
 int pb2_stats(pb2_handle* h, int64_t* hot_kernel_launches, double* hot_kernel_ms, int64_t* total_kernel_launches);
+/* The last reads -> device pileup staging (pb2_stage_reads / pb2_flush): bytes of the staged form the hot kernel reads, its rows, and the device time of
+ * the staging kernels (CUDA events on the handle's stream). */
+int pb2_stage_stats(pb2_handle* h, int64_t* staged_bytes, int64_t* rows, double* stage_ms);
 /* The handle's cudaStream_t (as void*) so the host can order its own work against it. */
 void* pb2_stream(pb2_handle* h);
 

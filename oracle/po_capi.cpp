@@ -84,6 +84,36 @@ int po_caller_add_read_candidates_only(void* h, const po_read* r) {
     auto* s = (SmallVariantCaller*)h;
     GUARD(s->state->AddCandidates(s->finder->FindCandidates(ToRead(r), s->chrSeq, s->chrName)))
 }
+// A struct of arrays of reads (the layout of pb2_read_batch) through SmallVariantCaller.Execute's per-read loop (SmallVariantCaller.cs:88-104): the bulk form
+// of po_caller_add_read for large synthetic read sets (bench.py's CPU baseline / reference arm, full-size parity tests). collapsed: optional per-read
+// summary byte (bit0 XV/XW present, bit1 duplex, bits 2-3 pair direction 1 FR / 2 RF / 0 other) turned back into the tags the reference reads;
+// xd_runs: optional [n][3] lengths of the F / S / R runs of the XD direction string over the CIGAR-expanded alignment (all zero: no XD tag).
+int po_caller_add_reads_soa(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
+                            const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs) {
+    auto* s = (SmallVariantCaller*)h;
+    try {
+        for (int32_t i = 0; i < n; i++) {
+            po_read r;
+            memset(&r, 0, sizeof(r));
+            r.pos0 = pos0[i]; r.flag = flag[i]; r.mapq = 60;
+            r.n_cigar = (int32_t)(cigar_off[i + 1] - cigar_off[i]); r.cigar = cigar + cigar_off[i];
+            r.l_seq = (int32_t)(seq_off[i + 1] - seq_off[i]); r.seq = (const char*)bases + seq_off[i]; r.qual = quals + seq_off[i];
+            std::string xd;
+            if (xd_runs && (xd_runs[3 * i] | xd_runs[3 * i + 1] | xd_runs[3 * i + 2])) {
+                static const char d[3] = {'F', 'S', 'R'};
+                for (int k = 0; k < 3; k++) if (xd_runs[3 * i + k] > 0) xd += std::to_string(xd_runs[3 * i + k]) + d[k];
+                r.has_tags = 1; r.xd = xd.c_str();
+            }
+            if (collapsed && (collapsed[i] & 1)) {
+                r.has_tags = 1; r.has_xv = 1; r.xv = 1; r.has_xw = 1; r.xw = (collapsed[i] & 2) ? 1 : 0;
+                const int pd = (collapsed[i] >> 2) & 3;
+                r.xr = pd == 1 ? "FR" : (pd == 2 ? "RF" : "FF");
+            }
+            s->ProcessRead(ToRead(&r));
+        }
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 // Locus-major pileup entries (the staging format of include/pisces_b200.h, pb2_pileup_csr) pushed through the SAME per-base operations
 // the reference performs in RegionStateManager.AddAlleleCounts (:161-192) and CandidateVariantFinder (SNV candidates, CallMNVs=false),
 // followed by Call(upTo) as positions clear. Used for parity of the locus-major path and as the CPU baseline of bench.py.

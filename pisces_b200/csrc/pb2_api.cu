@@ -157,6 +157,8 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->ev_stage0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->ev_stage1)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (int i = 0; i < 2; i++) {
         if ((e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -242,6 +244,8 @@ extern "C" void pb2_destroy(pb2_handle* h) {
     if (h->d_gq_tail) cudaFree(h->d_gq_tail);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_stage0) cudaEventDestroy(h->ev_stage0);
+    if (h->ev_stage1) cudaEventDestroy(h->ev_stage1);
     for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_scattered[i]) cudaEventDestroy(h->ev_scattered[i]); }
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -834,6 +838,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
         return PB2_OK;
     }
     // ---- PVERT: rows per (tile, class), layout, fill, bit transposition
+    CU(h, cudaEventRecord(h->ev_stage0, st));
     const int nc = h->cfg.expect_collapsed ? kPvClassesCollapsed : kPvClassesPlain;
     s.pv_classes = nc;
     int32_t* d_cursor = nullptr;
@@ -866,8 +871,12 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     CU(h, launch_pvert_transpose(s.pv_data, s.pv_rows / 32, st));
     CU(h, pool_alloc_t(h, &s.ref_base, (size_t)n_loci));
     CU(h, launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, s.ref_base, st));
+    CU(h, cudaEventRecord(h->ev_stage1, st));
     h->total_launches += 6;
     s.n_entries = R.n_seq;
+    h->last_stage_bytes = (int64_t)s.pv_rows * 32 + (int64_t)n_cls * 4 + ((int64_t)s.n_tiles + 1) * 8 + n_loci;
+    h->last_stage_rows = s.pv_rows;
+    h->have_stage_events = true;
     const int rc = alloc_segment_outputs(h, s);
     pool_free(h, d_cursor); pool_free(h, tile_rows); pool_free(h, temp); pool_free(h, d_index);
     if (rc != PB2_OK) return rc;
@@ -1421,9 +1430,30 @@ static int compact_reads(pb2_handle* h, int32_t cleared_to) {
     return PB2_OK;
 }
 
-extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n) {
+static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n, bool keep_reads);
+extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n) { return flush_impl(h, up_to_position, out, n, false); }
+// IAlleleCaller.Call for everything staged through pb2_push_reads, the reads staying on the device: the candidates are found again in the stored reads
+// (CandidateVariantFinder.FindCandidates), the batches of SmallVariantCaller.Execute replayed again, and nothing is consumed - the whole job from
+// device-resident reads, repeatable (bench.py, and hosts that re-call a chromosome with other options' worth of candidates).
+extern "C" int pb2_flush_resident(pb2_handle* h, const pb2_call_record** out, int64_t* n) {
+    if (!h || !out || !n) return fail(h, PB2_ERR_ARG, "pb2_flush_resident: null argument");
+    if (h->cleared_through != 0) return fail(h, PB2_ERR_STATE, "pb2_flush_resident: positions were already cleared by a partial pb2_flush");
+    CU(h, cudaSetDevice(h->device));
+    const std::vector<int32_t> triggers = h->triggers;
+    const int32_t push_last_key = h->push_last_key;
+    h->cands.clear(); h->cand_by_pos.clear(); h->block_max_endpoint.clear(); h->gapped_ref.clear(); h->snv_explicit_ranges.clear();
+    h->last_trigger_key = 0;
+    rearm_forced(h);
+    int rc = explicit_find_candidates(h, 0, nullptr);
+    if (rc == PB2_OK) rc = flush_impl(h, -1, out, n, true);
+    h->triggers = triggers;
+    h->push_last_key = push_last_key;
+    return rc;
+}
+static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n, bool keep_reads) {
     if (!h || !out || !n) return fail(h, PB2_ERR_ARG, "pb2_flush: null argument");
     CU(h, cudaSetDevice(h->device));
+    nvtx_range nv("pb2_flush");
     Trace tr("flush");
     h->h_out.clear();
     h->arena.clear();
@@ -1608,7 +1638,8 @@ extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_r
     }
     h->cands.erase(std::remove_if(h->cands.begin(), h->cands.end(), [](const HostCand& c) { return !c.alive; }), h->cands.end());
     explicit_reindex(h);
-    if (up_to_position < 0) { free_reads(h); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; h->snv_explicit_ranges.clear(); rearm_forced(h); }
+    if (up_to_position < 0 && keep_reads) { h->cleared_through = 0; h->gapped_ref.clear(); h->last_trigger_key = 0; h->snv_explicit_ranges.clear(); }
+    else if (up_to_position < 0) { free_reads(h); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; h->snv_explicit_ranges.clear(); rearm_forced(h); }
     else if (reads_path && cleared_to > h->cleared_through) {
         const int rc = compact_reads(h, cleared_to);
         if (rc != PB2_OK) return rc;
@@ -1742,6 +1773,23 @@ extern "C" int pb2_get_counts(pb2_handle* h, int32_t position0, int32_t n, int32
     }
     for (size_t i = 0; i < h->segs.size();) {
         if (h->segs[i].temporary) { free_segment(h, h->segs[i]); h->segs.erase(h->segs.begin() + (long)i); } else i++;
+    }
+    return PB2_OK;
+}
+
+extern "C" int pb2_stage_stats(pb2_handle* h, int64_t* staged_bytes, int64_t* rows, double* stage_ms) {
+    if (!h) return PB2_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (staged_bytes) *staged_bytes = h->last_stage_bytes;
+    if (rows) *rows = h->last_stage_rows;
+    if (stage_ms) {
+        *stage_ms = 0;
+        if (h->have_stage_events) {
+            float ms = 0;
+            CU(h, cudaEventSynchronize(h->ev_stage1));
+            CU(h, cudaEventElapsedTime(&ms, h->ev_stage0, h->ev_stage1));
+            *stage_ms = ms;
+        }
     }
     return PB2_OK;
 }

@@ -178,6 +178,9 @@ struct pb2_handle {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_scattered[2] = {nullptr, nullptr};
     cudaMemPool_t pool = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_stage0 = nullptr, ev_stage1 = nullptr;   // around the last reads -> PVERT staging
+    bool have_stage_events = false;
+    int64_t last_stage_bytes = 0, last_stage_rows = 0;
     std::string error;
     std::string chr_name;
     uint8_t* d_chr = nullptr;

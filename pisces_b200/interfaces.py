@@ -286,6 +286,23 @@ class GpuStateManager:
         self._keep = [offsets, pcode, pqual, fi, fb, positions, ref_bases]
         self._chk(self._L.pb2_push_pileup(self._h, C.byref(p)))
 
+    def AddReadsSoA(self, d):
+        """pb2_push_reads with a struct of arrays (dict of numpy arrays / pinned torch tensors: pos0 int32, flag uint16, cigar_off int64, cigar uint32,
+        seq_off int64, bases, quals[, base_dirs, collapsed]): IStateManager.AddAlleleCounts + FindCandidates for every read of the batch."""
+        def ptr(a, dt):
+            if a is None:
+                return None
+            if hasattr(a, "data_ptr"):       # torch tensor (pinned host memory)
+                return a.data_ptr()
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data
+        keep = []
+        b = N.ReadBatch(int(len(d["pos0"])), ptr(d["pos0"], np.int32), ptr(d["flag"], np.uint16), ptr(d["cigar_off"], np.int64), ptr(d["cigar"], np.uint32),
+                        ptr(d["seq_off"], np.int64), ptr(d["bases"], np.uint8), ptr(d["quals"], np.uint8), ptr(d.get("base_dirs"), np.uint8),
+                        ptr(d.get("collapsed"), np.uint8))
+        self._chk(self._L.pb2_push_reads(self._h, C.byref(b)))
+
     def AddReadBatch(self, batch):
         """pb2_push_reads with a ready pb2_read_batch (e.g. from BamReadStager): IStateManager.AddAlleleCounts + FindCandidates for each read."""
         self._chk(self._L.pb2_push_reads(self._h, C.byref(batch)))
@@ -392,6 +409,20 @@ class GpuStateManager:
     def StageReads(self):
         """pb2_stage_reads: everything pushed through AddAlleleCounts / AddReadBatch becomes one device-resident segment for call_resident."""
         self._chk(self._L.pb2_stage_reads(self._h))
+
+    def stage_stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_double()
+        self._chk(self._L.pb2_stage_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(staged_bytes=a.value, rows=b.value, stage_ms=c.value)
+
+    def flush_resident(self):
+        """pb2_flush_resident: the whole job from the device-resident reads (find candidates, stage, call), nothing consumed. Returns raw records."""
+        out = C.c_void_p()
+        n = C.c_int64()
+        self._chk(self._L.pb2_flush_resident(self._h, C.byref(out), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=N.RECORD_DTYPE)
+        return np.frombuffer((C.c_char * (96 * n.value)).from_address(out.value), dtype=N.RECORD_DTYPE).copy()
 
     def call_resident(self):
         n = C.c_int64()

@@ -168,3 +168,148 @@ def algorithmic_bytes(n_loci, n_entries, n_records, third_byte=True):
     """B(D,E) summed over loci: 3 B per entry + 8 B per locus + 96 B per emitted record; 2 B per entry when the
     anchor/collapsed byte is not needed by the configuration (the hot kernel then never reads that plane)."""
     return (3 if third_byte else 2) * n_entries + 8 * n_loci + 96 * n_records
+
+
+def make_reads(n_loci, mean_depth, seed=2, device="cpu", read_len=READ_LEN, snv_rate=0.01, vaf=(0.01, 0.5), indel_rate=0.001, mnv_pair_rate=0.0,
+               strand_skew_frac=0.0, collapsed_frac=0.0, stitched_frac=0.0, chunk_reads=1 << 17):
+    """Seeded synthetic READS of the BASELINE.json shapes: n_loci * mean_depth / read_len reads of length read_len whose start is uniform over
+    the chromosome (so the depth is ~Poisson(mean_depth) away from the two ends), sorted by position like a BAM, as the struct of arrays pb2_push_reads
+    takes. The chromosome is n_loci bases, uniform over ACGT. Base quality from the example_S1-like histogram of make_pileup; a base is mis-called with
+    probability 10^(-q/10); SNV loci (snv_rate) carry an alternate base at VAF ~ U[vaf]; 1-3 bp insertions / deletions at indel_rate of the loci
+    (>= 12 loci apart), carried at VAF ~ U[0.03, 0.43] by the reads that cover the site with at least 10 aligned bases on either side (CIGAR aM kI bM / aM kD bM).
+    mnv_pair_rate: adjacent SNV pairs carried by the same reads (CallMNVs workloads); strand_skew_frac: fraction of the SNV loci whose alternate allele sits
+    9:1 on the forward strand; collapsed_frac: reads tagged as collapsed (duplex 20 %, simplex FR / RF 40 % each; `collapsed` summary bytes);
+    stitched_frac: reads (without indels) whose bases run Forward / Stitched / Reverse (`base_dirs` + `xd_runs`, the XD tag's three run lengths).
+    Returns a dict of CPU numpy arrays (pos0, flag, cigar_off, cigar, seq_off, bases, quals[, collapsed, base_dirs, xd_runs]) + ref (ASCII bytes) + sizes."""
+    import numpy as np
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    L = int(read_len)
+    n_reads = max(1, int(round(n_loci * float(mean_depth) / L)))
+    hi_start = max(1, n_loci - L - 4 + 1)                         # deletions reach up to 3 bases further
+    starts = torch.sort(torch.randint(1, hi_start + 1, (n_reads,), device=dev, generator=g, dtype=torch.int64)).values
+    ref_idx = torch.randint(0, 4, (n_loci + 8,), device=dev, generator=g)
+    is_snv = torch.rand(n_loci + 8, device=dev, generator=g) < snv_rate
+    alt_idx = (ref_idx + torch.randint(1, 4, (n_loci + 8,), device=dev, generator=g)) % 4
+    locus_vaf = vaf[0] + (vaf[1] - vaf[0]) * torch.rand(n_loci + 8, device=dev, generator=g)
+    linked = torch.zeros(n_loci + 8, dtype=torch.bool, device=dev)
+    if mnv_pair_rate > 0:
+        first = torch.nonzero(torch.rand(n_loci, device=dev, generator=g) < mnv_pair_rate).flatten()
+        first = first[first < n_loci - 2]
+        is_snv[first] = True
+        is_snv[first + 1] = True
+        locus_vaf[first + 1] = locus_vaf[first]
+        linked[first] = True
+        linked[first + 1] = True
+    locus_vaf = torch.where(is_snv, locus_vaf, torch.zeros_like(locus_vaf)).to(torch.float32)
+    skew = (torch.rand(n_loci + 8, device=dev, generator=g) < strand_skew_frac) & is_snv
+    # indel sites: p = the base before the event (1-based position p <-> index p - 1)
+    n_sites = 0
+    site_pos = torch.zeros(0, dtype=torch.int64, device=dev)
+    if indel_rate > 0:
+        cand = torch.nonzero(torch.rand(n_loci, device=dev, generator=g) < indel_rate).flatten() + 1
+        cand = cand[(cand >= 2) & (cand < n_loci - 12)]
+        if cand.numel() > 1:
+            keep = torch.ones_like(cand, dtype=torch.bool)
+            keep[1:] = (cand[1:] - cand[:-1]) >= 12
+            cand = cand[keep]
+        site_pos = cand
+        n_sites = int(cand.numel())
+    site_len = torch.randint(1, 4, (max(n_sites, 1),), device=dev, generator=g)
+    site_ins = torch.rand(max(n_sites, 1), device=dev, generator=g) < 0.5
+    site_vaf = 0.03 + 0.4 * torch.rand(max(n_sites, 1), device=dev, generator=g)
+    site_bases = torch.randint(0, 4, (max(n_sites, 1), 3), device=dev, generator=g)
+    qcdf = _quality_table().to(dev)
+    ascii_acgt = _ASCII_ACGT.to(dev)
+    ar = torch.arange(L, device=dev, dtype=torch.int64)[None, :]
+
+    out_bases, out_quals, out_dirs = [], [], []
+    flags = torch.empty(n_reads, dtype=torch.int32, device=dev)
+    n_ops = torch.ones(n_reads, dtype=torch.int64, device=dev)
+    ev_a = torch.zeros(n_reads, dtype=torch.int64, device=dev)      # aligned bases before the event
+    ev_k = torch.zeros(n_reads, dtype=torch.int64, device=dev)      # event length, > 0 insertion, < 0 deletion, 0 none
+    collapsed = torch.zeros(n_reads, dtype=torch.uint8, device=dev) if collapsed_frac > 0 else None
+    xd_runs = torch.zeros((n_reads, 3), dtype=torch.int32, device=dev) if stitched_frac > 0 else None
+    for r0 in range(0, n_reads, chunk_reads):
+        r1 = min(n_reads, r0 + chunk_reads)
+        n = r1 - r0
+        s = starts[r0:r1]
+        reverse = torch.rand(n, device=dev, generator=g) < 0.5
+        first_mate = torch.rand(n, device=dev, generator=g) < 0.5
+        flags[r0:r1] = (0x1 | 0x2 | torch.where(reverse, 0x10, 0x20) | torch.where(first_mate, 0x40, 0x80)).to(torch.int32)
+        k = torch.zeros(n, dtype=torch.int64, device=dev)
+        a = torch.zeros(n, dtype=torch.int64, device=dev)
+        ins_b = torch.zeros((n, 3), dtype=torch.int64, device=dev)
+        if n_sites:
+            idx = torch.searchsorted(site_pos, s + 10).clamp_(max=n_sites - 1)
+            p = site_pos[idx]
+            kk = site_len[idx]
+            ins = site_ins[idx]
+            room = torch.where(ins, p + 1 + 10, p + kk + 1 + 10)       # >= 10 aligned bases after the event
+            ok = (p >= s + 10) & (room <= s + L - 1 - torch.where(ins, kk, torch.zeros_like(kk)))
+            carry = ok & (torch.rand(n, device=dev, generator=g) < site_vaf[idx])
+            k = torch.where(carry, torch.where(ins, kk, -kk), k)
+            a = torch.where(carry, p - s + 1, a)
+            ins_b = site_bases[idx]
+        ev_a[r0:r1] = a
+        ev_k[r0:r1] = k
+        n_ops[r0:r1] = torch.where(k != 0, 3, 1)
+        kpos, kneg = k.clamp(min=0)[:, None], (-k).clamp(min=0)[:, None]
+        a2 = a[:, None]
+        inserted = (k[:, None] > 0) & (ar >= a2) & (ar < a2 + kpos)
+        refoff = torch.where((k[:, None] > 0) & (ar >= a2 + kpos), ar - kpos, torch.where((k[:, None] < 0) & (ar >= a2), ar + kneg, ar.expand(n, L)))
+        refpos = (s[:, None] + refoff).clamp_(max=n_loci + 7)          # 1-based; meaningless where inserted
+        ri = refpos - 1
+        u = torch.rand((n, L), device=dev, generator=g)
+        q = torch.searchsorted(qcdf, u.to(torch.float64)).clamp_(0, 63)
+        u_base = torch.rand((n, L), device=dev, generator=g)
+        u_read = torch.rand((n, 1), device=dev, generator=g).expand(n, L)
+        v = locus_vaf[ri]
+        if strand_skew_frac > 0:
+            v = torch.where(skew[ri], v * torch.where(reverse, 0.2, 1.8)[:, None], v)
+        is_alt = torch.where(linked[ri], u_read, u_base) < v
+        base = torch.where(is_alt, alt_idx[ri], ref_idx[ri])
+        perr = torch.pow(10.0, -q.to(torch.float32) / 10.0)
+        is_err = torch.rand((n, L), device=dev, generator=g) < perr
+        base = torch.where(is_err, (base + torch.randint(1, 4, (n, L), device=dev, generator=g)) % 4, base)
+        if n_sites:
+            j = (ar - a2).clamp_(0, 2).expand(n, L)
+            base = torch.where(inserted, torch.gather(ins_b, 1, j), base)
+        out_bases.append(ascii_acgt[base].reshape(-1).cpu())
+        out_quals.append(q.to(torch.uint8).reshape(-1).cpu())
+        if collapsed is not None:
+            is_c = torch.rand(n, device=dev, generator=g) < collapsed_frac
+            duplex = torch.rand(n, device=dev, generator=g) < 0.2
+            fr = torch.rand(n, device=dev, generator=g) < 0.5
+            collapsed[r0:r1] = torch.where(is_c, 1 | torch.where(duplex, 2, 0) | torch.where(fr, 1 << 2, 2 << 2), 0).to(torch.uint8)
+        if xd_runs is not None:
+            st = (torch.rand(n, device=dev, generator=g) < stitched_frac) & (k == 0)
+            fa = torch.randint(10, L // 2, (n,), device=dev, generator=g)
+            fb = torch.randint(10, L // 3, (n,), device=dev, generator=g)
+            runs = torch.stack([fa, fb, L - fa - fb], 1).to(torch.int32)
+            xd_runs[r0:r1] = torch.where(st[:, None], runs, torch.zeros_like(runs))
+            d_plain = torch.where(reverse, 1, 0)[:, None].expand(n, L)
+            d_st = torch.where(ar < fa[:, None], 0, torch.where(ar < (fa + fb)[:, None], 2, 1))
+            out_dirs.append(torch.where(st[:, None], d_st, d_plain).to(torch.uint8).reshape(-1).cpu())
+    # CIGARs: L M | a M, k I, (L - a - k) M | a M, k D, (L - a) M
+    cigar_off = torch.zeros(n_reads + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(n_ops, 0, out=cigar_off[1:])
+    cigar = torch.empty(int(cigar_off[-1]), dtype=torch.int64, device=dev)
+    plain = ev_k == 0
+    cigar[cigar_off[:-1][plain]] = (L << 4) | 0
+    ev = ~plain
+    o = cigar_off[:-1][ev]
+    ka, kk = ev_a[ev], ev_k[ev]
+    cigar[o] = (ka << 4) | 0
+    cigar[o + 1] = torch.where(kk > 0, (kk << 4) | 1, ((-kk) << 4) | 2)
+    cigar[o + 2] = (torch.where(kk > 0, L - ka - kk, L - ka) << 4) | 0
+    seq_off = torch.arange(n_reads + 1, dtype=torch.int64) * L
+    ref = ascii_acgt[ref_idx[:n_loci]].cpu().numpy()
+    n_entries = int(n_reads) * L - int(ev_k.clamp(min=0).sum()) + int((-ev_k).clamp(min=0).sum())
+    d = dict(n_reads=n_reads, read_len=L, n_loci=n_loci, ref=ref, pos0=(starts - 1).to(torch.int32).cpu().numpy(), flag=flags.to(torch.int16).cpu().numpy().view(np.uint16),
+             cigar_off=cigar_off.cpu().numpy(), cigar=cigar.to(torch.int32).cpu().numpy().view(np.uint32), seq_off=seq_off.numpy(),
+             bases=torch.cat(out_bases).numpy(), quals=torch.cat(out_quals).numpy(), n_entries=n_entries, snv_loci=int(is_snv[:n_loci].sum()), indel_loci=n_sites,
+             collapsed=None if collapsed is None else collapsed.cpu().numpy(), xd_runs=None if xd_runs is None else xd_runs.cpu().numpy(),
+             base_dirs=torch.cat(out_dirs).numpy() if out_dirs else None)
+    return d

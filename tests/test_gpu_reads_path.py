@@ -1,0 +1,123 @@
+"""The reads path end to end on synthetic read sets of the BASELINE.json shapes: struct-of-arrays reads -> device read store -> PVERT pileup (built on the
+device) -> hot kernel + explicit candidates, against the CPU oracle fed the same reads through the reference's per-read loop. Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from pisces_b200 import synth
+from tests.test_gpu_explicit import _resident_records, compare_records
+
+pytestmark = pytest.mark.gpu
+
+
+def _pb():
+    import pisces_b200 as pb
+    return pb
+
+
+def _oracle(d, **kw):
+    okw = dict(kw)
+    if "expect_stitched" in okw:
+        okw["source_is_stitched"] = okw.pop("expect_stitched")
+    if "expect_collapsed" in okw:
+        okw["source_is_collapsed"] = okw.pop("expect_collapsed")
+    oc = ob.Caller(ob.default_config(**okw), "chr1", bytes(d["ref"]).decode())
+    oc.add_reads_soa(d["pos0"], d["flag"], d["cigar_off"], d["cigar"], d["seq_off"], d["bases"], d["quals"], d.get("collapsed"), d.get("xd_runs"))
+    return oc
+
+
+CONFIGS = {
+    # BASELINE.json configs[1]: SNV + indel, Poisson model, VCF only
+    "c2": (dict(indel_rate=0.002), dict(output_gvcf=0, collapse=1)),
+    # configs[2]: gVCF mode
+    "c3": (dict(indel_rate=0.0, snv_rate=0.005), dict(output_gvcf=1, collapse=1)),
+    # configs[3]: MNV phasing + strand-bias filter
+    "c4": (dict(indel_rate=0.0, mnv_pair_rate=0.002, strand_skew_frac=0.1), dict(output_gvcf=0, collapse=1, call_mnvs=1, max_size_mnv=3, max_gap_mnv=1)),
+    # configs[4]: SNV / MNV / indel + collapsed-read model, stitched reads
+    "c5": (dict(indel_rate=0.001, mnv_pair_rate=0.001, collapsed_frac=0.5, stitched_frac=0.5),
+           dict(output_gvcf=0, collapse=1, call_mnvs=1, expect_collapsed=1, expect_stitched=1)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_synthetic_reads_records_match_the_oracle(name):
+    pb = _pb()
+    gen, cfg = CONFIGS[name]
+    d = synth.make_reads(12000, 120, seed=11, **gen)
+    oc = _oracle(d, **cfg)
+    oc.finish()
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode())
+    sm.AddReadsSoA(d)
+    precs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    arena = sm.AlleleArena()
+    ext = sm.AlleleExt()
+    sm.close()
+    orecs = oc.records()
+    assert len(orecs) > 50
+    compare_records(orecs, precs, arena)
+    if cfg.get("expect_collapsed"):
+        for o, e in zip(orecs, ext):
+            assert list(o.collapsed_total) == list(e["collapsed_total"]) and list(o.collapsed_mut) == list(e["collapsed_mut"]), o.pos
+
+
+@pytest.mark.parametrize("name", ["c2", "c5"])
+def test_counts_of_synthetic_reads_bit_exact(name):
+    pb = _pb()
+    gen, cfg = CONFIGS[name]
+    d = synth.make_reads(3000, 80, seed=5, **gen)
+    oc = _oracle(d, **cfg)
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode())
+    sm.AddReadsSoA(d)
+    got = sm.GetAlleleCounts(1, 3000)
+    sm.close()
+    np.testing.assert_array_equal(got, oc.dump_counts(1, 3000))
+
+
+@pytest.mark.parametrize("batch", [1, 7, 1000])
+def test_batched_pushes_equal_one_push(batch):
+    """The store appends batch after batch (offsets rebased on the device); a batch may be a window of larger arrays."""
+    pb = _pb()
+    gen, cfg = CONFIGS["c2"]
+    d = synth.make_reads(4000, 60, seed=9, **gen)
+    ref = bytes(d["ref"]).decode()
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", ref)
+    sm.AddReadsSoA(d)
+    want = pb.GpuAlleleCaller().Call(sm, raw=True)
+    sm.close()
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", ref)
+    n = d["n_reads"]
+    for r0 in range(0, n, batch):
+        r1 = min(n, r0 + batch)
+        sm.AddReadsSoA(dict(pos0=d["pos0"][r0:r1], flag=d["flag"][r0:r1], cigar_off=d["cigar_off"][r0:r1 + 1], cigar=d["cigar"], seq_off=d["seq_off"][r0:r1 + 1],
+                            bases=d["bases"], quals=d["quals"]))
+    got = pb.GpuAlleleCaller().Call(sm, raw=True)
+    sm.close()
+    assert len(want) > 20 and want.tobytes() == got.tobytes()
+
+
+def test_staged_reads_resident_step_equals_flush():
+    """pb2_stage_reads + pb2_call_resident (the bench's device-resident step) emits the records pb2_flush returns."""
+    pb = _pb()
+    gen, cfg = CONFIGS["c2"]
+    d = synth.make_reads(20000, 100, seed=3, **gen)
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode())
+    sm.AddReadsSoA(d)
+    sm.StageReads()
+    n1 = sm.call_resident()
+    assert sm.call_resident() == n1 and sm.call_resident() == n1   # plan-building call, then replays
+    res = _resident_records(sm)
+    precs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    sm.close()
+    short = lambda recs: sorted(bytes(r.tobytes()) for r in recs if int(r["ref_len"]) + int(r["alt_len"]) <= 4)   # longer alleles point into per-call arenas
+    assert len(precs) > 100 and len(res) == len(precs)
+    assert short(res) == short(precs)
+
+
+def test_invalid_reads_are_rejected_as_the_reference_does():
+    pb = _pb()
+    sm = pb.GpuStateManager(pb.make_config(), "chr1", "ACGT" * 50)
+    with pytest.raises(pb.PiscesB200Error, match="Invalid cigar"):
+        sm.AddAlleleCounts(pb.Read(5, "ACGTACGT", "5M", [30] * 8))
+    sm.AddAlleleCounts(pb.Read(5, "ACGTACGT", "8M", [30] * 8))   # the handle stays usable
+    assert len(pb.GpuAlleleCaller().Call(sm, raw=True)) > 0
+    sm.close()
