@@ -36,9 +36,9 @@ CONFIGS = {
     "c4": dict(loci=500_000, depth=2000, seed=4, gen=dict(indel_rate=0.0, mnv_pair_rate=0.002, strand_skew_frac=0.1),
                cfg=dict(output_gvcf=0, call_mnvs=1, max_size_mnv=3, max_gap_mnv=1),
                what="CallMNVs (MaxSizeMNV 3, gap 1), adjacent-SNV pairs 0.2%, strand skew on 10% of variants (BASELINE.json configs[3] shape; 50 M loci / 4 GPUs = 25 such steps per GPU)"),
-    "c5": dict(loci=1_000_000, depth=300, seed=5, gen=dict(indel_rate=0.001, mnv_pair_rate=0.001, collapsed_frac=0.5, stitched_frac=0.5),
+    "c5": dict(loci=1_000_000, depth=300, seed=5, gen=dict(indel_rate=0.001, mnv_pair_rate=0.001, collapsed_frac=1.0, stitched_frac=0.5),
                cfg=dict(output_gvcf=0, call_mnvs=1, expect_collapsed=1, expect_stitched=1),
-               what="SNV/MNV/indel, 50% collapsed reads (duplex 20%), 50% stitched reads (BASELINE.json configs[4] shape; 200 M loci / 8 GPUs = 25 such steps per GPU)"),
+               what="SNV/MNV/indel, collapsed reads (duplex 20%, simplex 80%), 50% stitched reads (BASELINE.json configs[4] shape; 200 M loci / 8 GPUs = 25 such steps per GPU)"),
 }
 
 

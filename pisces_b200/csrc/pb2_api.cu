@@ -652,7 +652,7 @@ extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
     R.n = first + nb;
     R.has_dirs = want_dirs; R.has_collapsed = want_coll;
     ReadsView rv = R.view();
-    CU(h, launch_reads_ingest(rv, (int32_t)first, R.n_cigar - c_lo, R.n_seq - s_lo, R.cigar_off.p, R.seq_off.p, R.end_pos.p, h->push_last_key, d_trig, trig_cap, d_status, st));
+    CU(h, launch_reads_ingest(rv, (int32_t)first, R.n_cigar - c_lo, R.n_seq - s_lo, R.cigar_off.p, R.seq_off.p, R.end_pos.p, h->push_last_key, d_trig, trig_cap, d_status, h->cfg.expect_collapsed, st));
     if (want_dirs && !b->base_dirs) dirs_from_flags_kernel<<<(unsigned)nb, 64, 0, st>>>(R.flag.p, R.seq_off.p, first, first + nb, R.base_dirs.p);
     h->total_launches += 2;
     IngestStatus status;
@@ -666,6 +666,7 @@ extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
             case 1: return fail(h, PB2_ERR_ARG, "pb2_push_reads: bad CIGAR operation");
             case 2: return fail(h, PB2_ERR_ARG, "Invalid cigar: does not match length of read");   // Read.cs:603-605
             case 3: return fail(h, PB2_ERR_ARG, "Position must be greater than 0.");               // RegionStateManager.cs:363-364
+            case 5: return fail(h, PB2_ERR_ARG, "The input is collapsed BAM, but a read is not a collapsed read.");   // CollapedRegionStateManager.cs:40-43
             default: return fail(h, PB2_ERR_ARG, "pb2_push_reads: offsets not monotone");
         }
     }
@@ -1173,6 +1174,21 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
         std::sort(keys.begin(), keys.end());
         keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
     }
+    // the alive candidates in position order, computed once and again only when a batch returned candidates to the state
+    std::vector<size_t> order = all_alive_sorted();
+    size_t order_cands = h->cands.size(), cursor = 0;
+    auto refresh_order = [&]() {
+        if (h->cands.size() != order_cands) { order = all_alive_sorted(); order_cands = h->cands.size(); cursor = 0; }
+    };
+    const bool can_defer = h->forced.empty() && h->forced_positions.empty() && h->forced_pending.empty();
+    std::vector<size_t> deferred;
+    auto flush_deferred = [&]() -> int {
+        if (deferred.empty()) return PB2_OK;
+        std::vector<size_t> none;
+        const int rc = explicit_call_batch(h, deferred, -1, 0, INT32_MAX, called, called_ext, &none);
+        deferred.clear();
+        return rc;
+    };
     std::vector<int32_t> fire;   // upTo values in call order; -1 = the final Call(null)
     {
         size_t used = 0;
@@ -1210,7 +1226,25 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
             if (rc != PB2_OK) return rc;
         }
         std::vector<size_t> batch, kill;
-        for (size_t i : all_alive_sorted()) if (h->cands[i].position > *cleared_out && h->cands[i].position <= max_end) { batch.push_back(i); kill.push_back(i); }
+        refresh_order();
+        while (cursor < order.size() && h->cands[order[cursor]].position <= *cleared_out) cursor++;
+        for (size_t k = cursor; k < order.size() && h->cands[order[k]].position <= max_end; k++)
+            if (h->cands[order[k]].alive) { batch.push_back(order[k]); kill.push_back(order[k]); }
+        if (!pull_collapsable && can_defer) {
+            // A batch of fully anchored insertions / deletions only: every allele is scored on its own (no collapsing, no MNV reallocation, no
+            // gapped-MNV reference counts, nothing returns to the state), so consecutive batches of this kind are scored in one device pass
+            bool boring = true;
+            for (size_t i : batch) {
+                const HostCand& c = h->cands[i];
+                if ((c.type != CAT_INS && c.type != CAT_DEL) || (h->cfg.collapse && (c.open_left || c.open_right))) { boring = false; break; }
+            }
+            if (boring) {
+                for (size_t i : batch) { h->cands[i].alive = false; deferred.push_back(i); }
+                *cleared_out = t >= 0 ? max_end : INT32_MAX;
+                continue;
+            }
+        }
+        { const int rcd = flush_deferred(); if (rcd != PB2_OK) return rcd; }
         if (pull_collapsable) {
             // ExtractCollapsable(upTo) of the blocks that start after max_end and at or before upTo (RegionState.cs:470-490), position by position; each
             // collapsable goes to the batch, and List.Remove takes the FIRST candidate of the position's list that Equals it out of the state
@@ -1241,7 +1275,7 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
         if (rc != PB2_OK) return rc;
         *cleared_out = t >= 0 ? max_end : INT32_MAX;
     }
-    return PB2_OK;
+    return flush_deferred();
 }
 
 // The per-locus part of AlleleCaller.ComputeGenotypeAndFilterAllele (:143-177) for the germline genotypers, over the records of one flush (already

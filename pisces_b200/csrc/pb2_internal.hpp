@@ -56,14 +56,15 @@ cudaError_t launch_reads_candidates(const ReadsView& rv, int32_t first_read, con
 // rebased, Read.EndPosition computed, and the positions where SmallVariantCaller.Execute would have called a batch collected
 // (SmallVariantCaller.cs:99-104: Call(read.Position - 1) whenever that enters a new 1000-bp block key).
 struct IngestStatus {
-    int32_t error;            // 0 ok, 1 bad CIGAR operation, 2 CIGAR does not match the read length, 3 negative position, 4 offsets not monotone
+    int32_t error;            // 0 ok, 1 bad CIGAR operation, 2 CIGAR does not match the read length, 3 negative position, 4 offsets not monotone,
+                              // 5 a read without XV / XW in a collapsed BAM
     int32_t error_read;
     int32_t n_triggers;
     int32_t min_start, max_end;   // 1-based first / last reference position covered by the new reads
     int32_t pad_[3];
 };
 cudaError_t launch_reads_ingest(const ReadsView& rv, int32_t first_read, int64_t cigar_base, int64_t seq_base, int64_t* cigar_off, int64_t* seq_off, int32_t* end_pos,
-                                int32_t prev_pos0, int2* triggers, int32_t trigger_capacity, IngestStatus* status, cudaStream_t st);
+                                int32_t prev_key, int2* triggers, int32_t trigger_capacity, IngestStatus* status, int expect_collapsed, cudaStream_t st);
 // keep[i] = read i ends after `cleared_to`; compaction of the store after a partial flush (exclusive scans of the flags / lengths by the caller)
 cudaError_t launch_reads_keep_flags(const int32_t* end_pos, int64_t n, int32_t cleared_to, const int64_t* cigar_off, const int64_t* seq_off, int64_t* keep_reads,
                                     int64_t* keep_cigar, int64_t* keep_seq, cudaStream_t st);

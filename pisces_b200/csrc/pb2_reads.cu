@@ -298,7 +298,8 @@ __global__ void reads_candidates_kernel(ReadsView rv, int32_t first_read, const 
 
 // ------------------------------------------------------------------------------------------------ the device read store (pb2_push_reads)
 __global__ void reads_ingest_kernel(ReadsView rv, int32_t first_read, int64_t cigar_base, int64_t seq_base, int64_t* __restrict__ cigar_off, int64_t* __restrict__ seq_off,
-                                    int32_t* __restrict__ end_pos, int32_t prev_key, int2* __restrict__ triggers, int32_t trigger_capacity, IngestStatus* __restrict__ status) {
+                                    int32_t* __restrict__ end_pos, int32_t prev_key, int2* __restrict__ triggers, int32_t trigger_capacity, IngestStatus* __restrict__ status,
+                                    int expect_collapsed) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int nb = rv.n_reads - first_read;
     int lo = INT32_MAX, hi = 0;
@@ -320,6 +321,8 @@ __global__ void reads_ingest_kernel(ReadsView rv, int32_t first_read, int64_t ci
                 if (op_ref_span(op)) fs += c >> 4;
             }
             if (!err && c1 > c0 && rs != s1 - s0) err = 2;
+            // CollapsedRegionStateManager.AddCollapsedReadCount (CollapedRegionStateManager.cs:40-43) throws on the first counted base of a read without XV / XW
+            if (!err && expect_collapsed && c1 > c0 && fs > 0 && !(rv.collapsed != nullptr && (rv.collapsed[r] & 1))) err = 5;
         }
         if (err) { if (atomicCAS(&status->error, 0, err) == 0) status->error_read = j; }
         const int e = rv.pos0[r] + (int)fs;
@@ -345,10 +348,11 @@ __global__ void reads_rebase_kernel(int32_t first_read, int32_t nb, int64_t ciga
     seq_off[first_read + j] += seq_base;
 }
 cudaError_t launch_reads_ingest(const ReadsView& rv, int32_t first_read, int64_t cigar_base, int64_t seq_base, int64_t* cigar_off, int64_t* seq_off, int32_t* end_pos,
-                                int32_t prev_key, int2* triggers, int32_t trigger_capacity, IngestStatus* status, cudaStream_t st) {
+                                int32_t prev_key, int2* triggers, int32_t trigger_capacity, IngestStatus* status, int expect_collapsed, cudaStream_t st) {
     const int nb = rv.n_reads - first_read;
     if (nb <= 0) return cudaSuccess;
-    reads_ingest_kernel<<<(nb + 127) / 128, 128, 0, st>>>(rv, first_read, cigar_base, seq_base, cigar_off, seq_off, end_pos, prev_key, triggers, trigger_capacity, status);
+    reads_ingest_kernel<<<(nb + 127) / 128, 128, 0, st>>>(rv, first_read, cigar_base, seq_base, cigar_off, seq_off, end_pos, prev_key, triggers, trigger_capacity, status,
+                                                         expect_collapsed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     reads_rebase_kernel<<<(nb + 1 + 255) / 256, 256, 0, st>>>(first_read, nb, cigar_base, seq_base, cigar_off, seq_off);

@@ -34,7 +34,7 @@ CONFIGS = {
     # configs[3]: MNV phasing + strand-bias filter
     "c4": (dict(indel_rate=0.0, mnv_pair_rate=0.002, strand_skew_frac=0.1), dict(output_gvcf=0, collapse=1, call_mnvs=1, max_size_mnv=3, max_gap_mnv=1)),
     # configs[4]: SNV / MNV / indel + collapsed-read model, stitched reads
-    "c5": (dict(indel_rate=0.001, mnv_pair_rate=0.001, collapsed_frac=0.5, stitched_frac=0.5),
+    "c5": (dict(indel_rate=0.001, mnv_pair_rate=0.001, collapsed_frac=1.0, stitched_frac=0.5),
            dict(output_gvcf=0, collapse=1, call_mnvs=1, expect_collapsed=1, expect_stitched=1)),
 }
 
