@@ -1566,9 +1566,11 @@ static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_reco
             return (k >= 0 && k < s.n_loci) ? k : -1;
         };
         auto with_totals = [&](OutRec o) {   // CollapsedCoverageCalculator (:18-37): the counts at the allele's position / spanning start point
+            const int times = o.e.collapsed_total[0] == kCollapsedTotalTwice ? 2 : 1;   // MNV candidates: see explicit_call_batch
+            if (times == 2) o.e.collapsed_total[0] = 0;
             if (!collapsed.empty()) {
                 const int64_t l = locus_of(o.r.type == CAT_DEL ? o.r.position + 1 : o.r.position);
-                if (l >= 0) for (int t = 0; t < kNumCollapsed; t++) o.e.collapsed_total[t] = collapsed[(size_t)l * kNumCollapsed + t];
+                if (l >= 0) for (int t = 0; t < kNumCollapsed; t++) o.e.collapsed_total[t] = times * collapsed[(size_t)l * kNumCollapsed + t];
             }
             return o;
         };
@@ -1656,7 +1658,12 @@ static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_reco
         for (size_t k = 0; k < explicit_called.size(); k++) any_rest |= !explicit_used[k];
         if (any_rest) {
             for (size_t k = 0; k < h->h_out.size(); k++) all.push_back(OutRec{h->h_out[k], h->h_out_ext[k]});
-            for (size_t k = 0; k < explicit_called.size(); k++) if (!explicit_used[k]) all.push_back(OutRec{explicit_called[k], explicit_ext[k]});
+            for (size_t k = 0; k < explicit_called.size(); k++)
+                if (!explicit_used[k]) {
+                    OutRec o{explicit_called[k], explicit_ext[k]};
+                    if (o.e.collapsed_total[0] == kCollapsedTotalTwice) o.e.collapsed_total[0] = 0;   // no staged position: no totals to double
+                    all.push_back(o);
+                }
             std::stable_sort(all.begin(), all.end(), [&](const OutRec& a, const OutRec& b) {
                 return a.r.position != b.r.position ? a.r.position < b.r.position : (h->forced.empty() ? false : record_less_arena(a.r, b.r, h->arena));
             });

@@ -658,6 +658,10 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
             memset(&e, 0, sizeof(e));
             for (int k = 0; k < 8; k++) e.collapsed_mut[k] = callable[i]->collapsed_mut[k];
             for (int k = 0; k < 3; k++) e.well_anchored_support[k] = callable[i]->wa[k];
+            // An MNV candidate goes through ProcessVariant twice (AlleleCaller.cs:62-75, then :96-106 with every callable allele), and
+            // CollapsedCoverageCalculator ADDS to ReadCollapsedCountTotal each time (CollapsedCoverageCalculator.cs:18-37): its totals come out doubled.
+            // Marked here, applied where pb2_flush fills the totals in.
+            if (callable[i]->from_candidate && callable[i]->type == CAT_MNV) e.collapsed_total[0] = kCollapsedTotalTwice;
             called_ext.push_back(e);
         }
     }
@@ -778,7 +782,8 @@ static int find_candidates_impl(pb2_handle* h, size_t first_read, const BatchHos
         CUX(h, d_raw.reserve((size_t)capacity, st, false, h));
         CUX(h, cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), st));
         CUX(h, launch_reads_candidates(rv, (int32_t)first_read, h->d_chr, h->chr_len, h->dcfg.min_bq, snv_only ? 1 : h->cfg.call_mnvs, snv_only ? 0 : h->cfg.max_size_mnv,
-                                       snv_only ? 0 : h->cfg.max_gap_mnv, h->cfg.expect_collapsed, d_raw.p, d_count.p, capacity, st));
+                                       snv_only ? 0 : h->cfg.max_gap_mnv, h->cfg.expect_collapsed, d_raw.p, d_count.p, capacity, snv_only ? snv_lo : std::max(h->cleared_through, 0),
+                                       snv_only ? snv_hi : INT32_MAX, snv_only ? 1 : 0, R.end_pos.p, st));
         h->total_launches += 1;
         CUX(h, cudaMemcpyAsync(&cnt, d_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         CUX(h, cudaStreamSynchronize(st));

@@ -50,7 +50,8 @@ struct RawCand {
 };
 static_assert(sizeof(RawCand) == 32, "RawCand layout");
 cudaError_t launch_reads_candidates(const ReadsView& rv, int32_t first_read, const uint8_t* chr, int64_t chr_len, int min_bq, int call_mnvs, int max_mnv, int max_gap,
-                                    int expect_collapsed, RawCand* out, unsigned long long* count, int64_t capacity, cudaStream_t st);
+                                    int expect_collapsed, RawCand* out, unsigned long long* count, int64_t capacity, int32_t pos_lo, int32_t pos_hi, int snv_only,
+                                    const int32_t* end_pos, cudaStream_t st);
 
 // pb2_push_reads on the device: the new reads [first, n) of the store are validated (Read.cs:603-605, RegionStateManager.cs:363-364), their offsets
 // rebased, Read.EndPosition computed, and the positions where SmallVariantCaller.Execute would have called a batch collected
@@ -225,6 +226,7 @@ struct pb2_handle {
     std::string vcf_text;                             // pb2_vcf_format's output
 };
 
+constexpr int32_t kCollapsedTotalTwice = INT32_MIN;   // marker in pb2_call_record_ext.collapsed_total[0] between explicit_call_batch and pb2_flush
 // pb2_explicit.cu
 int pb2_fail(pb2_handle* h, int code, const std::string& msg);
 // RegionState.AddCandidate (:94-174): merge into the table (summing counts) or append; tracks MaxAlleleEndpoint of the block.

@@ -47,11 +47,12 @@ struct FillTargets {
 
 // Walks one read exactly as RegionStateManager.AddAlleleCounts does and hands every entry to the row writer. kFill = false: only the rows are counted
 // (same walk, same row boundaries: the two passes agree by construction).
+// bases / quals / dirs: the read's own sequence (global memory, or the CTA's shared-memory copy of it).
 template <bool kFill>
-__device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, int n_classes, int32_t* cls_rows, const FillTargets& ft) {
+__device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, int n_classes, int32_t* cls_rows, const FillTargets& ft, const uint8_t* bases,
+                             const uint8_t* quals, const uint8_t* dirs) {
     const int64_t c0 = rv.cigar_off[r], c1 = rv.cigar_off[r + 1];
-    const int64_t s0 = rv.seq_off[r];
-    const int read_len = (int)(rv.seq_off[r + 1] - s0);
+    const int read_len = (int)(rv.seq_off[r + 1] - rv.seq_off[r]);
     const int n_ops = (int)(c1 - c0);
     if (n_ops == 0) return;
     const int start_pos = rv.pos0[r] + 1;                                  // Read.Position
@@ -72,9 +73,6 @@ __device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, i
     }
     const bool reverse = (rv.flag[r] & 0x10) != 0;
     const int cg = (rg.expect_collapsed && rv.collapsed) ? pv_collapsed_group(rv.collapsed[r]) : 0;
-    const uint8_t* bases = rv.bases + s0;
-    const uint8_t* quals = rv.quals + s0;
-    const uint8_t* dirs = rv.base_dirs ? rv.base_dirs + s0 : nullptr;
     auto dir_at = [&](int i) -> int { return dirs ? min((int)dirs[i], 2) : (reverse ? DIR_R : DIR_F); };
     auto del_q = [&](int idx) -> int {  // CandidateVariantFinder.CheckDeletionQuality (:294-320): min of the flanking qualities
         if (read_len == 0) return -1;
@@ -214,16 +212,55 @@ __device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, i
     flush_word(st[1]);
 }
 
-__global__ void pvert_count_kernel(ReadsView rv, RegionView rg, int n_classes, int32_t* __restrict__ cls_rows) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// The reads of a CTA lie back to back in the store: their bases / qualities (/ directions) are copied into shared memory with coalesced loads and each
+// thread then walks its own read out of shared memory (a read is 35 words long: the per-thread strides are conflict free). A CTA whose reads do not fit
+// (very long reads) walks global memory instead.
+constexpr int kWalkThreads = 128;
+constexpr int kWalkSmem = 20 * 1024;   // bytes per plane (128 reads of 140 bases: 17.5 KB)
+template <bool kFill>
+__global__ void __launch_bounds__(kWalkThreads) pvert_walk_kernel(ReadsView rv, RegionView rg, int n_classes, int32_t* __restrict__ cls_rows, FillTargets ft) {
+    extern __shared__ __align__(16) uint8_t s_seq[];   // bases | quals [| dirs], kWalkSmem each
+    uint8_t* const s_bases = s_seq;
+    uint8_t* const s_quals = s_seq + kWalkSmem;
+    uint8_t* const s_dirs = s_seq + 2 * kWalkSmem;
+    const int r_first = blockIdx.x * kWalkThreads;
+    const int r_last = min(r_first + kWalkThreads, rv.n_reads);
+    const int64_t a = rv.seq_off[r_first], b = rv.seq_off[r_last];
+    const int64_t a16 = a & ~(int64_t)15;   // 16-byte loads from the aligned start of the range
+    const bool staged = b - a16 <= kWalkSmem;
+    if (staged) {
+        const int n16 = (int)((b - a16 + 15) >> 4);
+        for (int i = threadIdx.x; i < n16; i += kWalkThreads) {
+            const int64_t g = a16 + (int64_t)i * 16;
+            if (g + 16 <= b) {
+                *reinterpret_cast<uint4*>(s_bases + i * 16) = *reinterpret_cast<const uint4*>(rv.bases + g);
+                *reinterpret_cast<uint4*>(s_quals + i * 16) = *reinterpret_cast<const uint4*>(rv.quals + g);
+                if (rv.base_dirs) *reinterpret_cast<uint4*>(s_dirs + i * 16) = *reinterpret_cast<const uint4*>(rv.base_dirs + g);
+            } else {
+                for (int k = 0; k < 16 && g + k < b; k++) {
+                    s_bases[i * 16 + k] = rv.bases[g + k];
+                    s_quals[i * 16 + k] = rv.quals[g + k];
+                    if (rv.base_dirs) s_dirs[i * 16 + k] = rv.base_dirs[g + k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int r = r_first + threadIdx.x;
     if (r >= rv.n_reads) return;
-    FillTargets ft{};
-    pv_walk_read<false>(rv, rg, r, n_classes, cls_rows, ft);
+    const int64_t s0 = rv.seq_off[r];
+    const uint8_t* bases = staged ? s_bases + (s0 - a16) : rv.bases + s0;
+    const uint8_t* quals = staged ? s_quals + (s0 - a16) : rv.quals + s0;
+    const uint8_t* dirs = rv.base_dirs ? (staged ? s_dirs + (s0 - a16) : rv.base_dirs + s0) : nullptr;
+    pv_walk_read<kFill>(rv, rg, r, n_classes, cls_rows, ft, bases, quals, dirs);
 }
-__global__ void pvert_fill_kernel(ReadsView rv, RegionView rg, int n_classes, FillTargets ft) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rv.n_reads) return;
-    pv_walk_read<true>(rv, rg, r, n_classes, nullptr, ft);
+template <bool kFill>
+static cudaError_t launch_walk(const ReadsView& rv, const RegionView& rg, int n_classes, int32_t* cls_rows, const FillTargets& ft, cudaStream_t st) {
+    const size_t smem = (size_t)kWalkSmem * (rv.base_dirs ? 3 : 2);
+    cudaError_t e = cudaFuncSetAttribute(pvert_walk_kernel<kFill>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pvert_walk_kernel<kFill><<<(rv.n_reads + kWalkThreads - 1) / kWalkThreads, kWalkThreads, smem, st>>>(rv, rg, n_classes, cls_rows, ft);
+    return cudaGetLastError();
 }
 
 // rows per class -> inclusive prefix of the padded (multiple of 32) rows inside the tile; tile_rows[t] = rows of the tile
@@ -327,8 +364,8 @@ pvert_gather_kernel(PvertPileup in, const int32_t* __restrict__ req_locus, int32
 
 cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, int n_classes, int32_t* cls_rows, cudaStream_t st) {
     if (rv.n_reads == 0) return cudaSuccess;
-    pvert_count_kernel<<<(rv.n_reads + 127) / 128, 128, 0, st>>>(rv, rg, n_classes, cls_rows);
-    return cudaGetLastError();
+    FillTargets ft{};
+    return launch_walk<false>(rv, rg, n_classes, cls_rows, ft, st);
 }
 cudaError_t launch_pvert_layout(int32_t* cls_rows, int32_t n_tiles, int n_classes, int64_t* tile_rows, cudaStream_t st) {
     pvert_layout_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(cls_rows, n_tiles, n_classes, tile_rows);
@@ -338,8 +375,7 @@ cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, int n_c
                               int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, cudaStream_t st) {
     if (rv.n_reads == 0) return cudaSuccess;
     FillTargets ft{tile_row0, cls_end, cursor, data, row_meta, exc_entries, exc_count, exc_capacity};
-    pvert_fill_kernel<<<(rv.n_reads + 127) / 128, 128, 0, st>>>(rv, rg, n_classes, ft);
-    return cudaGetLastError();
+    return launch_walk<true>(rv, rg, n_classes, nullptr, ft, st);
 }
 cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st) {
     if (n_blocks <= 0) return cudaSuccess;

@@ -174,9 +174,12 @@ __device__ __forceinline__ void emit_raw(RawCand* out, unsigned long long* count
 }
 
 __global__ void reads_candidates_kernel(ReadsView rv, int32_t first_read, const uint8_t* __restrict__ chr, int64_t chr_len, int min_bq, int call_mnvs, int max_mnv,
-                                        int max_gap, int expect_collapsed, RawCand* __restrict__ out, unsigned long long* __restrict__ count, int64_t capacity) {
+                                        int max_gap, int expect_collapsed, RawCand* __restrict__ out, unsigned long long* __restrict__ count, int64_t capacity,
+                                        int32_t pos_lo, int32_t pos_hi, int snv_only, const int32_t* __restrict__ end_pos_of) {
     const int r = first_read + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rv.n_reads) return;
+    // only candidates at positions in (pos_lo, pos_hi] are wanted: reads that cannot hold one are skipped (an insertion before the first base sits at Position - 1)
+    if (rv.pos0[r] > pos_hi || (end_pos_of != nullptr && end_pos_of[r] < pos_lo)) return;
     const int64_t c0 = rv.cigar_off[r], c1 = rv.cigar_off[r + 1];
     const int64_t s0 = rv.seq_off[r];
     const int read_len = (int)(rv.seq_off[r + 1] - s0);
@@ -234,6 +237,7 @@ __global__ void reads_candidates_kernel(ReadsView rv, int32_t first_read, const 
         rc.type = (uint8_t)type; rc.dir = (uint8_t)d;
         rc.flags = (uint8_t)((open_l ? 1 : 0) | (open_r ? 2 : 0) | (anchor > min(kAnchorK - 1, alt_len - 1) ? 4 : 0));
         rc.collapsed = (uint8_t)collapsed_code(cbyte, d);
+        if (position <= pos_lo || position > pos_hi || (snv_only && type != CAT_SNV)) return;
         const int n_from_read = type == CAT_INS ? alt_len - 1 : (type == CAT_DEL ? 0 : alt_len);
 #pragma unroll
         for (int k = 0; k < 8; k++) rc.read_bases[k] = (k < n_from_read && start_idx + k < read_len) ? bases[start_idx + k] : (uint8_t)0;
@@ -419,10 +423,12 @@ cudaError_t launch_reads_block_bitmap(const int32_t* pos0, const int32_t* end_po
 }
 
 cudaError_t launch_reads_candidates(const ReadsView& rv, int32_t first_read, const uint8_t* chr, int64_t chr_len, int min_bq, int call_mnvs, int max_mnv, int max_gap,
-                                    int expect_collapsed, RawCand* out, unsigned long long* count, int64_t capacity, cudaStream_t st) {
+                                    int expect_collapsed, RawCand* out, unsigned long long* count, int64_t capacity, int32_t pos_lo, int32_t pos_hi, int snv_only,
+                                    const int32_t* end_pos, cudaStream_t st) {
     const int n = rv.n_reads - first_read;
     if (n <= 0) return cudaSuccess;
-    reads_candidates_kernel<<<(n + 127) / 128, 128, 0, st>>>(rv, first_read, chr, chr_len, min_bq, call_mnvs, max_mnv, max_gap, expect_collapsed, out, count, capacity);
+    reads_candidates_kernel<<<(n + 127) / 128, 128, 0, st>>>(rv, first_read, chr, chr_len, min_bq, call_mnvs, max_mnv, max_gap, expect_collapsed, out, count, capacity, pos_lo,
+                                                            pos_hi, snv_only, end_pos);
     return cudaGetLastError();
 }
 
