@@ -73,6 +73,7 @@ def lib():
         for f in ("po_caller_add_read", "po_caller_add_read_counts_only", "po_caller_add_read_candidates_only"):
             getattr(L, f).argtypes = [C.c_void_p, C.POINTER(ReadStruct)]
         L.po_caller_add_reads_soa.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 9
+        L.po_caller_add_reads_soa_counts_only.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 9
         L.po_caller_add_pileup.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.po_caller_add_candidate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
                                               C.POINTER(C.c_int32)]
@@ -222,7 +223,7 @@ class Caller:
              "candidates": self.L.po_caller_add_read_candidates_only}[mode]
         self._chk(f(self.h, C.byref(st)))
 
-    def add_reads_soa(self, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed=None, xd_runs=None):
+    def add_reads_soa(self, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed=None, xd_runs=None, counts_only=False):
         """A struct of arrays of reads (pb2_read_batch layout) through the reference's per-read loop."""
         import numpy as np
         arrs = [np.ascontiguousarray(pos0, dtype=np.int32), np.ascontiguousarray(flag, dtype=np.uint16), np.ascontiguousarray(cigar_off, dtype=np.int64),
@@ -230,7 +231,8 @@ class Caller:
                 np.ascontiguousarray(quals, dtype=np.uint8)]
         coll = None if collapsed is None else np.ascontiguousarray(collapsed, dtype=np.uint8)
         xd = None if xd_runs is None else np.ascontiguousarray(xd_runs, dtype=np.int32)
-        self._chk(self.L.po_caller_add_reads_soa(self.h, len(arrs[0]), *[a.ctypes.data for a in arrs], None if coll is None else coll.ctypes.data,
+        f = self.L.po_caller_add_reads_soa_counts_only if counts_only else self.L.po_caller_add_reads_soa
+        self._chk(f(self.h, len(arrs[0]), *[a.ctypes.data for a in arrs], None if coll is None else coll.ctypes.data,
                                                  None if xd is None else xd.ctypes.data))
 
     def add_pileup(self, offsets, code, qual, anchor, first_position=1, call_every=1):

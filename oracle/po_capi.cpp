@@ -88,8 +88,19 @@ int po_caller_add_read_candidates_only(void* h, const po_read* r) {
 // of po_caller_add_read for large synthetic read sets (bench.py's CPU baseline / reference arm, full-size parity tests). collapsed: optional per-read
 // summary byte (bit0 XV/XW present, bit1 duplex, bits 2-3 pair direction 1 FR / 2 RF / 0 other) turned back into the tags the reference reads;
 // xd_runs: optional [n][3] lengths of the F / S / R runs of the XD direction string over the CIGAR-expanded alignment (all zero: no XD tag).
+static int add_reads_soa_impl(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
+                              const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs, bool counts_only);
 int po_caller_add_reads_soa(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
                             const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs) {
+    return add_reads_soa_impl(h, n, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed, xd_runs, false);
+}
+// RegionStateManager.AddAlleleCounts only (nothing is called, no block is cleared): for po_dump_counts
+int po_caller_add_reads_soa_counts_only(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
+                                        const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs) {
+    return add_reads_soa_impl(h, n, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed, xd_runs, true);
+}
+static int add_reads_soa_impl(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
+                              const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs, bool counts_only) {
     auto* s = (SmallVariantCaller*)h;
     try {
         for (int32_t i = 0; i < n; i++) {
@@ -109,7 +120,7 @@ int po_caller_add_reads_soa(void* h, int32_t n, const int32_t* pos0, const uint1
                 const int pd = (collapsed[i] >> 2) & 3;
                 r.xr = pd == 1 ? "FR" : (pd == 2 ? "RF" : "FF");
             }
-            s->ProcessRead(ToRead(&r));
+            if (counts_only) s->state->AddAlleleCounts(ToRead(&r)); else s->ProcessRead(ToRead(&r));
         }
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }

@@ -67,6 +67,8 @@ int po_caller_add_read_counts_only(void* h, const po_read* r); /* RegionStateMan
 int po_caller_add_read_candidates_only(void* h, const po_read* r); /* FindCandidates + AddCandidates only */
 int po_caller_add_reads_soa(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
                             const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed /* or NULL */, const int32_t* xd_runs /* [n][3] or NULL */);
+int po_caller_add_reads_soa_counts_only(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
+                                        const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs);
 int po_caller_add_pileup(void* h, int64_t n_loci, int32_t first_pos, const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int32_t call_every);
 /* IAlleleSource.AddCandidates with one hand-built candidate (explicit candidates of the locus-major path) */
 int po_caller_add_candidate(void* h, int32_t type, int32_t pos, const char* ref, const char* alt, const int32_t support[3], const int32_t well_anchored[3],

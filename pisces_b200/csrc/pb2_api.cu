@@ -778,7 +778,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
         if (positions.empty()) return PB2_OK;
     }
     const int64_t n_loci = h->have_intervals ? (int64_t)positions.size() : span;
-    int32_t* d_index = nullptr;
+    int32_t *d_index = nullptr, *d_index_ge = nullptr;
     Segment s;
     s.n_loci = n_loci;
     s.n_tiles = (int32_t)((n_loci + kTileLoci - 1) / kTileLoci);
@@ -788,12 +788,18 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     if (h->have_intervals) {
         CU(h, pool_alloc_t(h, &d_index, index_of_pos.size()));
         CU(h, cudaMemcpyAsync(d_index, index_of_pos.data(), sizeof(int32_t) * index_of_pos.size(), cudaMemcpyHostToDevice, st));
+        std::vector<int32_t> index_ge((size_t)span + 1);
+        index_ge[(size_t)span] = (int32_t)positions.size();
+        for (int64_t k = span - 1; k >= 0; k--) index_ge[(size_t)k] = index_of_pos[(size_t)k] >= 0 ? index_of_pos[(size_t)k] : index_ge[(size_t)k + 1];
+        CU(h, pool_alloc_t(h, &d_index_ge, index_ge.size()));
+        CU(h, cudaMemcpyAsync(d_index_ge, index_ge.data(), sizeof(int32_t) * index_ge.size(), cudaMemcpyHostToDevice, st));
+        CU(h, cudaStreamSynchronize(st));   // index_ge is a local
         CU(h, pool_alloc_t(h, &s.positions, positions.size()));
         CU(h, cudaMemcpyAsync(s.positions, positions.data(), sizeof(int32_t) * positions.size(), cudaMemcpyHostToDevice, st));
         s.h_positions = positions;
     }
     ReadsView rv = R.view();
-    RegionView rg{lo, hi, d_index, h->d_chr, h->chr_len, h->dcfg.min_bq, h->cfg.expect_collapsed};
+    RegionView rg{lo, hi, d_index, h->d_chr, h->chr_len, h->dcfg.min_bq, h->cfg.expect_collapsed, d_index_ge, s.positions, n_loci};
     if (!pvert_eligible(h)) {
         // quality sums / unusual quality bars: the PTILE32 form, through the locus-major entry list (reads_count / reads_emit -> push_common)
         unsigned int *d_depth = nullptr, *d_cursor = nullptr;
@@ -801,7 +807,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
         uint8_t *d_code = nullptr, *d_qual = nullptr, *d_anch = nullptr, *d_ref = nullptr;
         void* temp = nullptr;
         auto cleanup = [&]() {
-            void* ptrs[] = {d_depth, d_cursor, d_off, d_depth64, d_code, d_qual, d_anch, d_ref, temp, d_index, s.positions};
+            void* ptrs[] = {d_depth, d_cursor, d_off, d_depth64, d_code, d_qual, d_anch, d_ref, temp, d_index, d_index_ge, s.positions};
             for (void* p : ptrs) pool_free(h, p);
         };
 #define CUC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->error = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return PB2_ERR_CUDA; } } while (0)
@@ -852,7 +858,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     CU(h, pool_alloc_t(h, &s.pv_tile_row0, (size_t)s.n_tiles + 1));
     CU(h, cudaMemsetAsync(s.pv_cls_end, 0, sizeof(int32_t) * n_cls, st));
     CU(h, cudaMemsetAsync(d_cursor, 0, sizeof(int32_t) * n_cls, st));
-    CU(h, launch_pvert_count(rv, rg, nc, s.pv_cls_end, st));
+    CU(h, launch_pvert_count(rv, rg, R.end_pos.p, nc, s.pv_cls_end, st));
     CU(h, launch_pvert_layout(s.pv_cls_end, s.n_tiles, nc, tile_rows, st));
     size_t tb = 0;
     CU(h, exclusive_scan_i64(tile_rows, s.pv_tile_row0, s.n_tiles + 1, nullptr, 0, &tb, st));
@@ -868,7 +874,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     CU(h, pool_alloc_t(h, &s.exc_entries, 2 * (size_t)s.exc_capacity));
     CU(h, pool_alloc_t(h, &s.counters, 4));
     CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
-    CU(h, launch_pvert_fill(rv, rg, nc, s.pv_tile_row0, s.pv_cls_end, d_cursor, s.pv_data, s.pv_row_meta, s.exc_entries, s.counters + 3, s.exc_capacity, st));
+    CU(h, launch_pvert_fill(rv, rg, R.end_pos.p, nc, s.pv_tile_row0, s.pv_cls_end, d_cursor, s.pv_data, s.pv_row_meta, s.exc_entries, s.counters + 3, s.exc_capacity, st));
     CU(h, launch_pvert_transpose(s.pv_data, s.pv_rows / 32, st));
     CU(h, pool_alloc_t(h, &s.ref_base, (size_t)n_loci));
     CU(h, launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, s.ref_base, st));
@@ -879,7 +885,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     h->last_stage_rows = s.pv_rows;
     h->have_stage_events = true;
     const int rc = alloc_segment_outputs(h, s);
-    pool_free(h, d_cursor); pool_free(h, tile_rows); pool_free(h, temp); pool_free(h, d_index);
+    pool_free(h, d_cursor); pool_free(h, tile_rows); pool_free(h, temp); pool_free(h, d_index); pool_free(h, d_index_ge);
     if (rc != PB2_OK) return rc;
     h->segs.push_back(std::move(s));
     return PB2_OK;
@@ -1026,8 +1032,9 @@ static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std:
         const int32_t pos = s.has_positions ? s.h_positions[locus] : s.first_position + (int32_t)locus;
         return ((uint64_t)(uint32_t)pos << 8) | (uint8_t)base_of[allele & 3];
     };
-    // one byte per locus: which alleles were called there (the flagged entries are many, the called alleles few: no hashing per entry)
-    std::vector<uint8_t> called_mask((size_t)s.n_loci, 0);
+    // one slot per locus with a called SNV (the flagged entries are many, the called alleles few: no hashing, no sorting per entry)
+    std::vector<int32_t> slot_of((size_t)s.n_loci, -1);
+    int32_t n_slots = 0;
     for (auto& v : vars) {
         if (v.type != CAT_SNV) continue;
         int64_t l = -1;
@@ -1036,29 +1043,30 @@ static int reconcile_flagged_entries(pb2_handle* h, const Segment& s, const std:
             if (it != s.h_positions.end() && *it == v.position) l = it - s.h_positions.begin();
         } else l = (int64_t)v.position - s.first_position;
         if (l < 0 || l >= s.n_loci) continue;
-        const char alt = (char)((v.allele_bytes >> 8) & 0xff);
-        for (int a = 0; a < 4; a++) if (base_of[a] == alt) called_mask[(size_t)l] |= (uint8_t)(1u << a);
+        if (slot_of[(size_t)l] < 0) slot_of[(size_t)l] = n_slots++;
+    }
+    std::vector<Acc> accs((size_t)n_slots * 4);
+    std::vector<uint8_t> touched((size_t)n_slots * 4, 0);
+    std::vector<uint32_t> slot_locus((size_t)n_slots, 0);
+    for (size_t i = 0; i + 1 < exc.size(); i += 2) {
+        const int allele = (int)(exc[i + 1] & 7);
+        if (allele > 3 || exc[i] >= (uint32_t)s.n_loci) continue;
+        const int32_t sl = slot_of[exc[i]];
+        if (sl < 0) continue;
+        Acc& a = accs[(size_t)sl * 4 + (size_t)allele];
+        touched[(size_t)sl * 4 + (size_t)allele] = 1;
+        slot_locus[(size_t)sl] = exc[i];
+        const uint32_t f = exc[i + 1] & 0xffu;
+        const bool l = f & PB2_ENTRY_OPEN_LEFT, r = f & PB2_ENTRY_OPEN_RIGHT;
+        if (f & PB2_ENTRY_NO_CANDIDATE) a.nocand++;
+        else if (l && r) a.open_lr++;
+        else if (l) a.open_l++;
+        else if (r) a.open_r++;
     }
     std::vector<std::pair<Key, Acc>> groups;
-    {
-        std::vector<std::pair<Key, uint32_t>> items;
-        for (size_t i = 0; i + 1 < exc.size(); i += 2) {
-            const int allele = (int)(exc[i + 1] & 7);
-            if (allele > 3) continue;
-            if (exc[i] >= (uint32_t)s.n_loci || !((called_mask[exc[i]] >> allele) & 1)) continue;
-            items.push_back({Key{exc[i], allele}, exc[i + 1] & 0xffu});
-        }
-        std::sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-        for (auto& it : items) {
-            if (groups.empty() || groups.back().first < it.first) groups.push_back({it.first, Acc()});
-            Acc& a = groups.back().second;
-            const bool l = it.second & PB2_ENTRY_OPEN_LEFT, r = it.second & PB2_ENTRY_OPEN_RIGHT;
-            if (it.second & PB2_ENTRY_NO_CANDIDATE) a.nocand++;
-            else if (l && r) a.open_lr++;
-            else if (l) a.open_l++;
-            else if (r) a.open_r++;
-        }
-    }
+    for (int32_t sl = 0; sl < n_slots; sl++)
+        for (int allele = 0; allele < 4; allele++)
+            if (touched[(size_t)sl * 4 + (size_t)allele]) groups.push_back({Key{slot_locus[(size_t)sl], allele}, accs[(size_t)sl * 4 + (size_t)allele]});
     for (auto& g : groups) {
         auto it = index.find(key_of(g.first.locus, g.first.allele));
         if (it != index.end()) {
@@ -1189,6 +1197,8 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
         deferred.clear();
         return rc;
     };
+    Trace tr("explicit_batches");
+    tr.mark("keys");
     std::vector<int32_t> fire;   // upTo values in call order; -1 = the final Call(null)
     {
         size_t used = 0;
@@ -1275,7 +1285,10 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
         if (rc != PB2_OK) return rc;
         *cleared_out = t >= 0 ? max_end : INT32_MAX;
     }
-    return flush_deferred();
+    tr.mark("loop");
+    const int rcf = flush_deferred();
+    tr.mark("deferred");
+    return rcf;
 }
 
 // The per-locus part of AlleleCaller.ComputeGenotypeAndFilterAllele (:143-177) for the germline genotypers, over the records of one flush (already
@@ -1557,6 +1570,7 @@ static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_reco
         pool_free(h, d_collapsed);
         tr.mark("hot+d2h");
         if (!exc.empty() && !h->cfg.call_mnvs) { const int rc = reconcile_flagged_entries(h, s, exc, hot_vars); if (rc != PB2_OK) return rc; }
+        tr.mark("reconcile");
         auto locus_of = [&](int32_t pos) -> int64_t {
             if (s.has_positions) {
                 auto it = std::lower_bound(s.h_positions.begin(), s.h_positions.end(), pos);
@@ -1689,6 +1703,7 @@ static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_reco
         h->snv_explicit_ranges.erase(std::remove_if(h->snv_explicit_ranges.begin(), h->snv_explicit_ranges.end(),
                                                     [&](const std::pair<int32_t, int32_t>& r) { return r.second <= cleared_to; }), h->snv_explicit_ranges.end());
     }
+    tr.mark("cleanup");
     *out = h->h_out.data();
     *n = (int64_t)h->h_out.size();
     return PB2_OK;

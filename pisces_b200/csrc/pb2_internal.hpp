@@ -25,11 +25,14 @@ struct ReadsView {
 };
 struct RegionView {
     int32_t lo, hi;
-    const int32_t* index_of_pos;
+    const int32_t* index_of_pos;   // [hi - lo + 1] locus of a position, -1 = not staged; nullptr: locus = position - lo
     const uint8_t* chr;
     int64_t chr_len;
     int min_bq;
     int expect_collapsed;
+    const int32_t* index_ge = nullptr;    // [hi - lo + 2] first locus at or after a position (with index_of_pos; n_loci past the last)
+    const int32_t* positions = nullptr;   // [n_loci] position of a locus (with index_of_pos)
+    int64_t n_loci = 0;
 };
 cudaError_t launch_reads_count(const ReadsView& rv, const RegionView& rg, unsigned int* depth, cudaStream_t st);
 cudaError_t launch_reads_emit(const ReadsView& rv, const RegionView& rg, const int64_t* offsets, unsigned int* cursor, uint8_t* code, uint8_t* qual, uint8_t* anch,

@@ -45,34 +45,23 @@ struct FillTargets {
     int64_t exc_capacity;
 };
 
-// Walks one read exactly as RegionStateManager.AddAlleleCounts does and hands every entry to the row writer. kFill = false: only the rows are counted
-// (same walk, same row boundaries: the two passes agree by construction).
-// bases / quals / dirs: the read's own sequence (global memory, or the CTA's shared-memory copy of it).
+// Walks one read exactly as RegionStateManager.AddAlleleCounts does, restricted to the reference positions [w_lo, w_hi] of ONE tile, and hands every entry
+// there to the row writer: operations before the window are skipped whole, an aligned operation is walked over its bases inside the window only. One
+// thread per (read, tile) piece: every thread does the same amount of work (at most 32 bases), whatever the phase of its read against the tile grid.
+// kFill = false: only the rows are counted (same walk, same row boundaries: the two passes agree by construction).
 template <bool kFill>
-__device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, int n_classes, int32_t* cls_rows, const FillTargets& ft, const uint8_t* bases,
-                             const uint8_t* quals, const uint8_t* dirs) {
+__device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, int end_pos, int w_lo, int w_hi, int n_classes, int32_t* cls_rows, const FillTargets& ft) {
     const int64_t c0 = rv.cigar_off[r], c1 = rv.cigar_off[r + 1];
-    const int read_len = (int)(rv.seq_off[r + 1] - rv.seq_off[r]);
+    const int64_t s0 = rv.seq_off[r];
+    const int read_len = (int)(rv.seq_off[r + 1] - s0);
     const int n_ops = (int)(c1 - c0);
     if (n_ops == 0) return;
-    const int start_pos = rv.pos0[r] + 1;                                  // Read.Position
-    int ref_span = 0, max_mapped = -1;
-    {
-        int rp = start_pos;
-        for (int i = 0; i < n_ops; i++) {
-            const uint32_t c = rv.cigar[c0 + i];
-            const int op = c & 15, len = (int)(c >> 4);
-            if (pv_ref_span(op)) { ref_span += len; if (pv_read_span(op) && len > 0) max_mapped = rp + len - 1; rp += len; }
-        }
-    }
-    const int end_pos = rv.pos0[r] + ref_span;                             // Read.EndPosition (Read.cs:88-91)
-    if (end_pos < rg.lo || start_pos > rg.hi) {
-        // the read lies outside the staged window - unless a terminal deletion reaches into it (handled by the full walk below)
-        const int last_op0 = (int)(rv.cigar[c1 - 1] & 15);
-        if (last_op0 != 2 && !(n_ops >= 2 && (int)(rv.cigar[c1 - 2] & 15) == 2 && last_op0 == 4)) return;
-    }
+    const int start_pos = rv.pos0[r] + 1;                                  // Read.Position; end_pos = Read.EndPosition (Read.cs:88-91)
     const bool reverse = (rv.flag[r] & 0x10) != 0;
     const int cg = (rg.expect_collapsed && rv.collapsed) ? pv_collapsed_group(rv.collapsed[r]) : 0;
+    const uint8_t* __restrict__ bases = rv.bases + s0;
+    const uint8_t* __restrict__ quals = rv.quals + s0;
+    const uint8_t* __restrict__ dirs = rv.base_dirs ? rv.base_dirs + s0 : nullptr;
     auto dir_at = [&](int i) -> int { return dirs ? min((int)dirs[i], 2) : (reverse ? DIR_R : DIR_F); };
     auto del_q = [&](int idx) -> int {  // CandidateVariantFinder.CheckDeletionQuality (:294-320): min of the flanking qualities
         if (read_len == 0) return -1;
@@ -90,11 +79,20 @@ __device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, i
         del_len = (int)(ends_in_del_before_clip ? (rv.cigar[c1 - 2] >> 4) : (rv.cigar[c1 - 1] >> 4));
         len_before_del = ends_in_del_before_clip ? read_len - (int)(rv.cigar[c1 - 1] >> 4) : read_len;
     }
-    // open-end annotation (:496-553): first / last non-soft-clip operation
+    // open-end annotation (:496-553): first / last non-soft-clip operation, the last mapped position
     int first_op = (int)(rv.cigar[c0] & 15);
     if (first_op == 4 && n_ops >= 2) first_op = (int)(rv.cigar[c0 + 1] & 15);
     int last_nonclip = last_op;
     if (last_nonclip == 4 && n_ops >= 2) last_nonclip = prev_op;
+    int max_mapped = -1;
+    if (kFill) {
+        int rp = start_pos;
+        for (int i = 0; i < n_ops; i++) {
+            const uint32_t c = rv.cigar[c0 + i];
+            const int op = c & 15, len = (int)(c >> 4);
+            if (pv_ref_span(op)) { if (pv_read_span(op) && len > 0) max_mapped = rp + len - 1; rp += len; }
+        }
+    }
 
     RowState st[2];
     st[0].key = st[1].key = -1; st[0].widx = st[1].widx = -1; st[0].acc = st[1].acc = 0; st[0].row = st[1].row = 0; st[0].tag = st[1].tag = 0;
@@ -108,14 +106,14 @@ __device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, i
         if (li < 0) return -1;
         const int64_t tile = li >> 5;
         const int l = (int)(li & 31);
-        const int64_t key = tile * n_classes + pv_class(kind, dir, cg);
+        const int cls = pv_class(kind, dir, cg);
+        const int64_t key = tile * n_classes + cls;
         RowState& s = st[kind];
         if (key != s.key || tag != s.tag) {
             flush_word(s);
             s.key = key;
             s.tag = tag;
             if (kFill) {
-                const int cls = pv_class(kind, dir, cg);
                 const int k = atomicAdd(ft.cursor + key, 1);
                 s.row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[tile * n_classes + cls - 1] : 0) + k;
                 ft.row_meta[s.row] = meta;
@@ -130,9 +128,10 @@ __device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, i
         }
         return li;
     };
-    auto put_del = [&](int position, int dir, int dq, int anchor) {
-        if (dq < rg.min_bq) return;          // a Deletion entry below the quality bar is never counted (:170-177)
-        put(1, position, dir, (uint32_t)min(max(dq, 1), 63), make_int2(INT32_MIN + anchor, 0), anchor);
+    // Deletion entries at positions [a, b] clipped to the window; a Deletion entry below the quality bar is never counted (:170-177)
+    auto put_dels = [&](int a, int b, int dir, int dq, int anchor) {
+        if (dq < rg.min_bq) return;
+        for (int j = max(a, w_lo); j <= min(b, w_hi); j++) put(1, j, dir, (uint32_t)min(max(dq, 1), 63), make_int2(INT32_MIN + anchor, 0), anchor);
     };
     const int2 read_meta = make_int2(start_pos, end_pos);
 
@@ -141,125 +140,97 @@ __device__ void pv_walk_read(const ReadsView& rv, const RegionView& rg, int r, i
         const uint32_t c = rv.cigar[c0 + oi];
         const int op = c & 15, len = (int)(c >> 4);
         const bool rs = pv_read_span(op), fs = pv_ref_span(op);
-        if (rs) {
-            if (!fs && !(ends_in_del_before_clip && read_idx <= len_before_del && len_before_del < read_idx + len)) { read_idx += len; continue; }   // I / S: not mapped
-            for (int k = 0; k < len; k++, read_idx++) {
-                const int dir = dir_at(read_idx);
-                if (ends_in_del_before_clip && read_idx == len_before_del) {      // (:148-159)
-                    const int dq = del_q(read_idx);
-                    for (int j = 1; j < del_len + 1; j++) put_del(j + last_position, dir, dq, kNumAnchors - 1);
-                }
-                if (!fs) continue;
-                const int position = ref_pos++;
-                if (position > last_position + 1) {                              // deletion (or N skip) before this base (:170-177)
-                    const int dq = del_q(read_idx);
-                    if (dq >= rg.min_bq) {
-                        const int an = pv_anchor_type(end_pos, position, start_pos);
-                        for (int j = max(last_position + 1, rg.lo); j < position && j <= rg.hi; j++) put_del(j, dir, dq, an);
-                    }
-                }
-                last_position = position;
-                if (position < rg.lo || position > rg.hi) continue;
-                const uint8_t b = bases[read_idx];
-                const int q = quals[read_idx];
-                const int a2 = pv_allele2(b);
-                const uint32_t byte = a2 < 0 ? 1u : ((uint32_t)a2 << 6) | (uint32_t)min(max(q, 1), 63);
-                const int64_t li = put(0, position, dir, byte, read_meta, 0);
-                if (!kFill || li < 0) continue;
-                // SNV-candidate bookkeeping the counts cannot express (CallMNVs off; CandidateVariantFinder.cs:90-168): only a usable mismatch against an
-                // A/C/G/T reference base can matter; it goes to the segment's side list (the rule of tile_scatter_kernel)
-                if (a2 < 0 || q < rg.min_bq) continue;
-                const bool in_chr = rg.chr == nullptr || position <= rg.chr_len;
-                const uint8_t rb = (rg.chr != nullptr && position >= 1 && position <= rg.chr_len) ? rg.chr[position - 1] : (uint8_t)'N';
-                const int ra2 = pv_allele2(rb);
-                if (ra2 < 0 || ra2 == a2) continue;
-                uint32_t code = 0;
-                if (op != 0 || !in_chr) code |= PB2_ENTRY_NO_CANDIDATE;
-                else {
-                    if (k + 1 < len) {   // open on the right: the next base of this operation exists and is unusable -> FlushVariant(..., openRight = true)
-                        const int nq = quals[read_idx + 1];
-                        const bool nb_n = pv_allele2(bases[read_idx + 1]) < 0;
-                        bool nref_n = false, n_in = true;
-                        if (rg.chr) {
-                            n_in = position + 1 <= rg.chr_len;
-                            if (n_in) nref_n = pv_allele2(rg.chr[position]) < 0;
+        if (rs && !fs) {                                                          // I / S: not mapped to the reference
+            if (ends_in_del_before_clip && read_idx <= len_before_del && len_before_del < read_idx + len)   // (:148-159): at the first clipped base
+                put_dels(last_position + 1, last_position + del_len, dir_at(len_before_del), del_q(len_before_del), kNumAnchors - 1);
+            read_idx += len;
+        } else if (rs && fs) {
+            if (len > 0) {
+                if (ref_pos > last_position + 1 && ref_pos - 1 >= w_lo && last_position + 1 <= w_hi)       // deletion (or N skip) before this base (:170-177)
+                    put_dels(last_position + 1, ref_pos - 1, dir_at(read_idx), del_q(read_idx), pv_anchor_type(end_pos, ref_pos, start_pos));
+                const int k0 = max(0, w_lo - ref_pos), k1 = min(len, w_hi - ref_pos + 1);
+                for (int k = k0; k < k1; k++) {
+                    const int ri = read_idx + k, position = ref_pos + k;
+                    const int dir = dir_at(ri);
+                    const uint8_t b = bases[ri];
+                    const int q = quals[ri];
+                    const int a2 = pv_allele2(b);
+                    const uint32_t byte = a2 < 0 ? 1u : ((uint32_t)a2 << 6) | (uint32_t)min(max(q, 1), 63);
+                    const int64_t li = put(0, position, dir, byte, read_meta, 0);
+                    if (!kFill || li < 0) continue;
+                    // SNV-candidate bookkeeping the counts cannot express (CallMNVs off; CandidateVariantFinder.cs:90-168): only a usable mismatch against
+                    // an A/C/G/T reference base can matter; it goes to the segment's side list (the rule of tile_scatter_kernel)
+                    if (a2 < 0 || q < rg.min_bq) continue;
+                    const bool in_chr = rg.chr == nullptr || position <= rg.chr_len;
+                    const uint8_t rb = (rg.chr != nullptr && position >= 1 && position <= rg.chr_len) ? rg.chr[position - 1] : (uint8_t)'N';
+                    const int ra2 = pv_allele2(rb);
+                    if (ra2 < 0 || ra2 == a2) continue;
+                    uint32_t code = 0;
+                    if (op != 0 || !in_chr) code |= PB2_ENTRY_NO_CANDIDATE;
+                    else {
+                        if (k + 1 < len) {   // open on the right: the next base of this operation exists and is unusable -> FlushVariant(..., openRight = true)
+                            const int nq = quals[ri + 1];
+                            const bool nb_n = pv_allele2(bases[ri + 1]) < 0;
+                            bool nref_n = false, n_in = true;
+                            if (rg.chr) {
+                                n_in = position + 1 <= rg.chr_len;
+                                if (n_in) nref_n = pv_allele2(rg.chr[position]) < 0;
+                            }
+                            if (n_in && (nq < rg.min_bq || nb_n || nref_n)) code |= PB2_ENTRY_OPEN_RIGHT;
                         }
-                        if (n_in && (nq < rg.min_bq || nb_n || nref_n)) code |= PB2_ENTRY_OPEN_RIGHT;
+                        if (first_op == 0 && position == start_pos) code |= PB2_ENTRY_OPEN_LEFT;
+                        if (last_nonclip == 0 && position == max_mapped) code |= PB2_ENTRY_OPEN_RIGHT;
                     }
-                    if (first_op == 0 && position == start_pos) code |= PB2_ENTRY_OPEN_LEFT;
-                    if (last_nonclip == 0 && position == max_mapped) code |= PB2_ENTRY_OPEN_RIGHT;
-                }
-                if (code) {
-                    const unsigned long long slot = atomicAdd(ft.exc_count, 1ull);
-                    if ((int64_t)slot < ft.exc_capacity) {
-                        const int an = pv_anchor_type(end_pos, position, start_pos);
-                        const int cc = pv_collapsed_code(cg, dir);
-                        ft.exc_entries[2 * slot] = (uint32_t)li;
-                        ft.exc_entries[2 * slot + 1] = (code | (uint32_t)a2 | ((uint32_t)dir << 3)) | ((uint32_t)min(q, 127) << 8) | ((uint32_t)(an | (cc << 4)) << 16);
+                    if (code) {
+                        const unsigned long long slot = atomicAdd(ft.exc_count, 1ull);
+                        if ((int64_t)slot < ft.exc_capacity) {
+                            const int an = pv_anchor_type(end_pos, position, start_pos);
+                            const int cc = pv_collapsed_code(cg, dir);
+                            ft.exc_entries[2 * slot] = (uint32_t)li;
+                            ft.exc_entries[2 * slot + 1] = (code | (uint32_t)a2 | ((uint32_t)dir << 3)) | ((uint32_t)min(q, 127) << 8) | ((uint32_t)(an | (cc << 4)) << 16);
+                        }
                     }
                 }
+                last_position = ref_pos + len - 1;
             }
+            read_idx += len;
+            ref_pos += len;
+            if (ref_pos > w_hi + 1 && !ends_in_del && !ends_in_del_before_clip) break;   // everything further lies behind the window
         } else if (fs) {
             ref_pos += len;
         }
     }
-    if (ends_in_del && read_len > 0) {                                           // (:195-210)
-        const int dq = del_q(read_len - 1);
-        const int dir = dir_at(read_len - 1);
-        for (int j = 1; j < del_len + 1; j++) put_del(j + last_position, dir, dq, kNumAnchors - 1);
-    }
+    if (ends_in_del && read_len > 0)                                              // (:195-210)
+        put_dels(last_position + 1, last_position + del_len, dir_at(read_len - 1), del_q(read_len - 1), kNumAnchors - 1);
     flush_word(st[0]);
     flush_word(st[1]);
 }
 
-// The reads of a CTA lie back to back in the store: their bases / qualities (/ directions) are copied into shared memory with coalesced loads and each
-// thread then walks its own read out of shared memory (a read is 35 words long: the per-thread strides are conflict free). A CTA whose reads do not fit
-// (very long reads) walks global memory instead.
-constexpr int kWalkThreads = 128;
-constexpr int kWalkSmem = 20 * 1024;   // bytes per plane (128 reads of 140 bases: 17.5 KB)
+// One thread per (read, tile) piece: thread t takes read t / kWalkPieces and, of the tiles the read touches, the (t % kWalkPieces)-th, (+ kWalkPieces)-th, ...
+constexpr int kWalkPieces = 8;
 template <bool kFill>
-__global__ void __launch_bounds__(kWalkThreads) pvert_walk_kernel(ReadsView rv, RegionView rg, int n_classes, int32_t* __restrict__ cls_rows, FillTargets ft) {
-    extern __shared__ __align__(16) uint8_t s_seq[];   // bases | quals [| dirs], kWalkSmem each
-    uint8_t* const s_bases = s_seq;
-    uint8_t* const s_quals = s_seq + kWalkSmem;
-    uint8_t* const s_dirs = s_seq + 2 * kWalkSmem;
-    const int r_first = blockIdx.x * kWalkThreads;
-    const int r_last = min(r_first + kWalkThreads, rv.n_reads);
-    const int64_t a = rv.seq_off[r_first], b = rv.seq_off[r_last];
-    const int64_t a16 = a & ~(int64_t)15;   // 16-byte loads from the aligned start of the range
-    const bool staged = b - a16 <= kWalkSmem;
-    if (staged) {
-        const int n16 = (int)((b - a16 + 15) >> 4);
-        for (int i = threadIdx.x; i < n16; i += kWalkThreads) {
-            const int64_t g = a16 + (int64_t)i * 16;
-            if (g + 16 <= b) {
-                *reinterpret_cast<uint4*>(s_bases + i * 16) = *reinterpret_cast<const uint4*>(rv.bases + g);
-                *reinterpret_cast<uint4*>(s_quals + i * 16) = *reinterpret_cast<const uint4*>(rv.quals + g);
-                if (rv.base_dirs) *reinterpret_cast<uint4*>(s_dirs + i * 16) = *reinterpret_cast<const uint4*>(rv.base_dirs + g);
-            } else {
-                for (int k = 0; k < 16 && g + k < b; k++) {
-                    s_bases[i * 16 + k] = rv.bases[g + k];
-                    s_quals[i * 16 + k] = rv.quals[g + k];
-                    if (rv.base_dirs) s_dirs[i * 16 + k] = rv.base_dirs[g + k];
-                }
-            }
-        }
-        __syncthreads();
-    }
-    const int r = r_first + threadIdx.x;
+__global__ void __launch_bounds__(256) pvert_walk_kernel(ReadsView rv, RegionView rg, const int32_t* __restrict__ end_pos_of, int n_classes, int32_t* __restrict__ cls_rows,
+                                                        FillTargets ft) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(t / kWalkPieces), k = (int)(t % kWalkPieces);
     if (r >= rv.n_reads) return;
-    const int64_t s0 = rv.seq_off[r];
-    const uint8_t* bases = staged ? s_bases + (s0 - a16) : rv.bases + s0;
-    const uint8_t* quals = staged ? s_quals + (s0 - a16) : rv.quals + s0;
-    const uint8_t* dirs = rv.base_dirs ? (staged ? s_dirs + (s0 - a16) : rv.base_dirs + s0) : nullptr;
-    pv_walk_read<kFill>(rv, rg, r, n_classes, cls_rows, ft, bases, quals, dirs);
+    const int start_pos = rv.pos0[r] + 1, end_pos = end_pos_of[r];
+    const int a = max(start_pos, rg.lo), e = min(end_pos, rg.hi);
+    if (a > e) return;
+    // loci of the staged window the read touches: [l0, l1]
+    const int64_t l0 = rg.index_ge ? rg.index_ge[a - rg.lo] : (int64_t)(a - rg.lo);
+    const int64_t l1 = (rg.index_ge ? (int64_t)rg.index_ge[e - rg.lo + 1] : (int64_t)(e - rg.lo + 1)) - 1;
+    if (l0 > l1) return;
+    for (int64_t tile = (l0 >> 5) + k; tile <= (l1 >> 5); tile += kWalkPieces) {
+        const int64_t f = tile << 5, g = min(f + 31, rg.n_loci - 1);
+        const int w_lo = rg.positions ? rg.positions[f] : rg.lo + (int)f, w_hi = rg.positions ? rg.positions[g] : rg.lo + (int)g;
+        pv_walk_piece<kFill>(rv, rg, r, end_pos, max(w_lo, a), min(w_hi, e), n_classes, cls_rows, ft);
+    }
 }
 template <bool kFill>
-static cudaError_t launch_walk(const ReadsView& rv, const RegionView& rg, int n_classes, int32_t* cls_rows, const FillTargets& ft, cudaStream_t st) {
-    const size_t smem = (size_t)kWalkSmem * (rv.base_dirs ? 3 : 2);
-    cudaError_t e = cudaFuncSetAttribute(pvert_walk_kernel<kFill>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    pvert_walk_kernel<kFill><<<(rv.n_reads + kWalkThreads - 1) / kWalkThreads, kWalkThreads, smem, st>>>(rv, rg, n_classes, cls_rows, ft);
+static cudaError_t launch_walk(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, const FillTargets& ft, cudaStream_t st) {
+    const int64_t threads = (int64_t)rv.n_reads * kWalkPieces;
+    pvert_walk_kernel<kFill><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rv, rg, end_pos, n_classes, cls_rows, ft);
     return cudaGetLastError();
 }
 
@@ -362,20 +333,20 @@ pvert_gather_kernel(PvertPileup in, const int32_t* __restrict__ req_locus, int32
 }
 }  // namespace
 
-cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, int n_classes, int32_t* cls_rows, cudaStream_t st) {
+cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, cudaStream_t st) {
     if (rv.n_reads == 0) return cudaSuccess;
     FillTargets ft{};
-    return launch_walk<false>(rv, rg, n_classes, cls_rows, ft, st);
+    return launch_walk<false>(rv, rg, end_pos, n_classes, cls_rows, ft, st);
 }
 cudaError_t launch_pvert_layout(int32_t* cls_rows, int32_t n_tiles, int n_classes, int64_t* tile_rows, cudaStream_t st) {
     pvert_layout_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(cls_rows, n_tiles, n_classes, tile_rows);
     return cudaGetLastError();
 }
-cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
+cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
                               int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, cudaStream_t st) {
     if (rv.n_reads == 0) return cudaSuccess;
     FillTargets ft{tile_row0, cls_end, cursor, data, row_meta, exc_entries, exc_count, exc_capacity};
-    return launch_walk<true>(rv, rg, n_classes, nullptr, ft, st);
+    return launch_walk<true>(rv, rg, end_pos, n_classes, nullptr, ft, st);
 }
 cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st) {
     if (n_blocks <= 0) return cudaSuccess;

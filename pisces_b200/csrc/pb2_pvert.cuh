@@ -66,9 +66,9 @@ __host__ __device__ inline unsigned long long pv_transpose8x8(unsigned long long
 struct ReadsView;
 struct RegionView;
 // reads -> rows: count rows per (tile, class); layout (pad, prefix); fill (rows + row_meta + flagged-entry side list); bit transposition in place
-cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, int n_classes, int32_t* cls_rows, cudaStream_t st);
+cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, cudaStream_t st);
 cudaError_t launch_pvert_layout(int32_t* cls_rows /* in: rows per class; out: inclusive padded prefix */, int32_t n_tiles, int n_classes, int64_t* tile_rows, cudaStream_t st);
-cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
+cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
                               int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, cudaStream_t st);
 cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st);
 cudaError_t launch_pvert_ref_bases(const uint8_t* chr, int64_t chr_len, const int32_t* positions, int32_t first_position, int64_t n_loci, uint8_t* ref_base, cudaStream_t st);

@@ -412,7 +412,8 @@ __global__ void reads_block_bitmap_kernel(const int32_t* __restrict__ pos0, cons
     if (a > e) return;
     for (int k = (a + 999) / 1000; k <= (e + 999) / 1000; k++) {
         const int b = k - key0;
-        if (b >= 0 && b < n_keys) atomicOr(bitmap + (b >> 5), 1u << (b & 31));
+        // reads arrive in position order: nearly every read finds its block's bit already set (a stale view only costs a redundant atomic)
+        if (b >= 0 && b < n_keys && !((*reinterpret_cast<volatile uint32_t*>(bitmap + (b >> 5)) >> (b & 31)) & 1u)) atomicOr(bitmap + (b >> 5), 1u << (b & 31));
     }
 }
 cudaError_t launch_reads_block_bitmap(const int32_t* pos0, const int32_t* end_pos, int64_t n, int32_t cleared_through, int32_t key0, int32_t n_keys, uint32_t* bitmap,

@@ -15,14 +15,14 @@ def _pb():
     return pb
 
 
-def _oracle(d, **kw):
+def _oracle(d, counts_only=False, **kw):
     okw = dict(kw)
     if "expect_stitched" in okw:
         okw["source_is_stitched"] = okw.pop("expect_stitched")
     if "expect_collapsed" in okw:
         okw["source_is_collapsed"] = okw.pop("expect_collapsed")
     oc = ob.Caller(ob.default_config(**okw), "chr1", bytes(d["ref"]).decode())
-    oc.add_reads_soa(d["pos0"], d["flag"], d["cigar_off"], d["cigar"], d["seq_off"], d["bases"], d["quals"], d.get("collapsed"), d.get("xd_runs"))
+    oc.add_reads_soa(d["pos0"], d["flag"], d["cigar_off"], d["cigar"], d["seq_off"], d["bases"], d["quals"], d.get("collapsed"), d.get("xd_runs"), counts_only=counts_only)
     return oc
 
 
@@ -65,7 +65,7 @@ def test_counts_of_synthetic_reads_bit_exact(name):
     pb = _pb()
     gen, cfg = CONFIGS[name]
     d = synth.make_reads(3000, 80, seed=5, **gen)
-    oc = _oracle(d, **cfg)
+    oc = _oracle(d, counts_only=True, **cfg)
     sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode())
     sm.AddReadsSoA(d)
     got = sm.GetAlleleCounts(1, 3000)
