@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample-loci", type=int, default=100_000)
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-input", default="packed", choices=["packed", "soa"], help="host form of the reads: one packed byte per base, or bases + qualities")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -257,7 +258,13 @@ def main_ours(a):
     keys = ["pos0", "flag", "cigar_off", "cigar", "seq_off", "bases", "quals"] + [k for k in ("base_dirs", "collapsed") if d.get(k) is not None]
     view = {"flag": np.int16, "cigar": np.int32}
     pinned = {k: torch.from_numpy(d[k].view(view[k]) if k in view else d[k]).pin_memory() for k in keys}
-    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in pinned.values())
+    # the e2e input: the same reads packed to one byte per base (pb2_pack_reads: lossless, exceptions listed), as a host behind a PCIe link would hold them
+    if a.e2e_input == "packed" and not a.no_e2e:
+        pk = pb.GpuStateManager.pack_reads(d)
+        e2e_in = {k: torch.from_numpy(np.ascontiguousarray(v).view(view[k]) if k in view else np.ascontiguousarray(v)).pin_memory() for k, v in pk.items() if v is not None}
+    else:
+        e2e_in = pinned
+    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in e2e_in.values())
     cfg = pb.make_config(device=local, **a.cfg)
     cfg.reserved[0] = a.tune_ctas
     cfg.reserved[1] = a.tune_prefetch
@@ -404,7 +411,10 @@ def main_ours(a):
         e2e_steps = max(2, min(a.steps, a.e2e_steps))
 
         def e2e_step():
-            sm2.AddReadsSoA(pinned)
+            if a.e2e_input == "packed":
+                sm2.AddReadsPacked(e2e_in)
+            else:
+                sm2.AddReadsSoA(pinned)
             recs = caller.Call(sm2, raw=True)
             return recs
         precs = e2e_step()
@@ -418,7 +428,7 @@ def main_ours(a):
         if world > 1:
             dist.all_reduce(edt, op=dist.ReduceOp.MAX)
         line["e2e"] = {"value": world * a.loci * e2e_steps / float(edt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 96 * nrec,
-                       "steps": e2e_steps, "ms_per_step": 1e3 * float(edt.item()) / e2e_steps, "input": "reads (struct of arrays, 2 B per base + 18 B per read), pinned host memory"}
+                       "steps": e2e_steps, "ms_per_step": 1e3 * float(edt.item()) / e2e_steps, "input": ("reads, one packed byte per base (pb2_push_reads_packed) + 26 B per read" if a.e2e_input == "packed" else "reads, bases + qualities (pb2_push_reads) + 26 B per read") + ", pinned host memory"}
         sm2.close()
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample, single thread like one Pisces (BAM x chr) job; the same run

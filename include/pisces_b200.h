@@ -111,6 +111,26 @@ typedef struct pb2_read_batch {
     const uint8_t*  collapsed;   /* optional [n]: bit0 IsCollapsedRead (XV/XW present), bit1 IsDuplex, bits2-3 ReadPairDirection 1=FR 2=RF 0=other (Read.cs:17-71,311-349) */
 } pb2_read_batch;
 
+/* The same reads for hosts behind a PCIe link: one byte per base instead of two. seq[i] = allele2 << 6 | quality with allele2 = A 0, G 1, C 2, T 3
+ * (the reference's AlleleType order) and quality <= 63. A base that is not A/C/G/T, a quality above 63, and an A of quality 0 (whose byte would be 0) are
+ * EXCEPTIONS: their seq byte is 0 and exc_index[] (indices into seq, increasing) / exc_base[] (ASCII) / exc_qual[] carry the real values, so the form is
+ * lossless. pb2_pack_reads builds it from bases + qualities. The device unpacks into the same read store pb2_push_reads fills. */
+typedef struct pb2_packed_read_batch {
+    int32_t n_reads;
+    const int32_t*  pos0;
+    const uint16_t* flag;
+    const int64_t*  cigar_off;
+    const uint32_t* cigar;
+    const int64_t*  seq_off;
+    const uint8_t*  seq;
+    int64_t n_exceptions;
+    const int64_t*  exc_index;
+    const uint8_t*  exc_base;
+    const uint8_t*  exc_qual;
+    const uint8_t*  base_dirs;   /* optional, one byte per base as in pb2_read_batch */
+    const uint8_t*  collapsed;   /* optional */
+} pb2_packed_read_batch;
+
 /* Locus-major pileup ("pileup columns") in CSR form: locus i covers reference position first_position + i (or positions[i]),
  * its entries are [offsets[i], offsets[i+1]) in the three byte planes. One entry = one call to RegionState.AddAlleleCount
  * (RegionStateManager.cs:155,174,183,206) before minimum-base-quality is applied:
@@ -215,6 +235,10 @@ int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p);
  * positions they cover; the pileup is built on the device (read expansion, bucketing to loci, tile interleave). */
 int pb2_push_reads(pb2_handle* h, const pb2_read_batch* batch);
 
+int pb2_push_reads_packed(pb2_handle* h, const pb2_packed_read_batch* batch);
+/* Host helper (no device work): packs n bases + qualities into seq[n] and lists the exceptions. Returns the number of exceptions; when it exceeds
+ * exc_capacity only the first exc_capacity were stored (call again with larger arrays). */
+int64_t pb2_pack_reads(const uint8_t* bases, const uint8_t* quals, int64_t n, uint8_t* seq, int64_t* exc_index, uint8_t* exc_base, uint8_t* exc_qual, int64_t exc_capacity);
 /* Stages everything pushed through pb2_push_reads so far as one device-resident segment (the pileup is built on the device from the reads the handle
  * keeps there), so that pb2_call_resident / pb2_resident_results run on it: the whole-chromosome form of IStateManager for hosts that push all reads
  * first (bench.py, multi-GPU shards). The reads stay staged; a later pb2_flush re-stages what it needs and supersedes this segment. */

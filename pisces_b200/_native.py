@@ -35,6 +35,12 @@ class ReadBatch(C.Structure):
                 ("seq_off", C.c_void_p), ("bases", C.c_void_p), ("quals", C.c_void_p), ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p)]
 
 
+class PackedReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("pos0", C.c_void_p), ("flag", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("seq_off", C.c_void_p),
+                ("seq", C.c_void_p), ("n_exceptions", C.c_int64), ("exc_index", C.c_void_p), ("exc_base", C.c_void_p), ("exc_qual", C.c_void_p),
+                ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p)]
+
+
 class Candidate(C.Structure):
     _fields_ = [("position", C.c_int32), ("type", C.c_uint8), ("open_flags", C.c_uint8), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16),
                 ("reserved", C.c_uint16), ("allele_offset", C.c_uint32), ("support", C.c_int32 * 3), ("well_anchored", C.c_int32 * 3),
@@ -67,7 +73,7 @@ RECORD_DTYPE = [("position", "<i4"), ("type", "u1"), ("genotype", "u1"), ("sb_fl
 RECORD_EXT_DTYPE = [("collapsed_mut", "<i4", (8,)), ("collapsed_total", "<i4", (8,)), ("well_anchored_support", "<i4", (3,)), ("phase_set_index", "<i4")]
 
 EXPORTS = ["pb2_default_config", "pb2_create", "pb2_destroy", "pb2_last_error", "pb2_device_count", "pb2_set_reference", "pb2_set_intervals",
-           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_stage_reads", "pb2_push_candidates", "pb2_set_forced_alleles", "pb2_allele_arena", "pb2_call_resident", "pb2_resident_results", "pb2_flush", "pb2_flush_resident", "pb2_flush_ext",
+           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_reads_packed", "pb2_pack_reads", "pb2_stage_reads", "pb2_push_candidates", "pb2_set_forced_alleles", "pb2_allele_arena", "pb2_call_resident", "pb2_resident_results", "pb2_flush", "pb2_flush_resident", "pb2_flush_ext",
            "pb2_get_counts", "pb2_reset", "pb2_stats", "pb2_stage_stats", "pb2_stream", "pb2_totals", "pb2_vcf_format",
            "pb2_bam_open", "pb2_bam_close", "pb2_bam_last_error", "pb2_bam_header", "pb2_bam_next_batch", "pb2_bam_batch_amplicons",
            "pb2_bam_amplicon_names"]
@@ -96,6 +102,9 @@ def load():
     L.pb2_push_pileup.argtypes = [H, C.POINTER(PileupCsr)]
     L.pb2_push_pileup_device.argtypes = [H, C.POINTER(PileupCsr)]
     L.pb2_push_reads.argtypes = [H, C.POINTER(ReadBatch)]
+    L.pb2_push_reads_packed.argtypes = [H, C.POINTER(PackedReadBatch)]
+    L.pb2_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.pb2_pack_reads.restype = C.c_int64
     L.pb2_stage_reads.argtypes = [H]
     L.pb2_push_candidates.argtypes = [H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     L.pb2_set_forced_alleles.argtypes = [H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]

@@ -590,10 +590,32 @@ __global__ static void dirs_from_flags_kernel(const uint16_t* __restrict__ flag,
     for (int64_t k = seq_off[r] + threadIdx.x; k < seq_off[r + 1]; k += blockDim.x) dirs[k] = d;
 }
 
-extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
+// PB2 packed sequence bytes -> the store's ASCII bases + qualities; then the exceptions (bases that are not A/C/G/T, qualities the byte cannot hold)
+__global__ static void unpack_seq_kernel(const uint8_t* __restrict__ seq, int64_t n, uint8_t* __restrict__ bases, uint8_t* __restrict__ quals) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    const uint32_t lut = 'A' | ('G' << 8) | ('C' << 16) | ((uint32_t)'T' << 24);   // allele2: AlleleType order A G C T
+    for (int k = 0; k < 4 && i + k < n; k++) {
+        const uint32_t b = seq[i + k];
+        bases[i + k] = (uint8_t)(lut >> (8 * (b >> 6)));
+        quals[i + k] = (uint8_t)(b & 63u);
+    }
+}
+__global__ static void apply_seq_exceptions_kernel(const int64_t* __restrict__ index, const uint8_t* __restrict__ eb, const uint8_t* __restrict__ eq, int64_t n_exc, int64_t lo,
+                                                   int64_t hi, uint8_t* __restrict__ bases, uint8_t* __restrict__ quals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_exc) return;
+    const int64_t k = index[i];
+    if (k >= lo && k < hi) { bases[k] = eb[i]; quals[k] = eq[i]; }
+}
+
+// seq / exc_*: the packed form of pb2_push_reads_packed (then b->bases / b->quals are NULL), else nullptr
+static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t* seq, int64_t n_exc, const int64_t* exc_index, const uint8_t* exc_base,
+                           const uint8_t* exc_qual) {
     if (!h || !b || b->n_reads < 0) return fail(h, PB2_ERR_ARG, "pb2_push_reads: bad argument");
     if (b->n_reads == 0) return PB2_OK;
-    if (!b->pos0 || !b->flag || !b->cigar_off || !b->cigar || !b->seq_off || !b->bases || !b->quals) return fail(h, PB2_ERR_ARG, "pb2_push_reads: null array");
+    if (!b->pos0 || !b->flag || !b->cigar_off || !b->cigar || !b->seq_off || (!seq && (!b->bases || !b->quals))) return fail(h, PB2_ERR_ARG, "pb2_push_reads: null array");
+    if (seq && (n_exc < 0 || (n_exc > 0 && (!exc_index || !exc_base || !exc_qual)))) return fail(h, PB2_ERR_ARG, "pb2_push_reads_packed: bad exception list");
     CU(h, cudaSetDevice(h->device));
     nvtx_range nv("pb2_push_reads");
     Trace tr("push_reads");
@@ -630,9 +652,28 @@ extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
     CU(h, cudaMemcpyAsync(R.cigar_off.p + first + 1, b->cigar_off + 1, sizeof(int64_t) * (size_t)nb, k, st));
     CU(h, cudaMemcpyAsync(R.seq_off.p + first + 1, b->seq_off + 1, sizeof(int64_t) * (size_t)nb, k, st));
     if (ncig) CU(h, cudaMemcpyAsync(R.cigar.p + R.n_cigar, b->cigar + c_lo, sizeof(uint32_t) * (size_t)ncig, k, st));
+    uint8_t* d_seq = nullptr;
+    int64_t* d_exc_index = nullptr;
+    uint8_t *d_exc_base = nullptr, *d_exc_qual = nullptr;
     if (nseq) {
-        CU(h, cudaMemcpyAsync(R.bases.p + R.n_seq, b->bases + s_lo, (size_t)nseq, k, st));
-        CU(h, cudaMemcpyAsync(R.quals.p + R.n_seq, b->quals + s_lo, (size_t)nseq, k, st));
+        if (seq) {
+            CU(h, pool_alloc(h, (void**)&d_seq, (size_t)nseq));
+            CU(h, cudaMemcpyAsync(d_seq, seq + s_lo, (size_t)nseq, k, st));
+            unpack_seq_kernel<<<(unsigned)(((nseq + 3) / 4 + 255) / 256), 256, 0, st>>>(d_seq, nseq, R.bases.p + R.n_seq, R.quals.p + R.n_seq);
+            if (n_exc > 0) {
+                CU(h, pool_alloc_t(h, &d_exc_index, (size_t)n_exc)); CU(h, pool_alloc_t(h, &d_exc_base, (size_t)n_exc)); CU(h, pool_alloc_t(h, &d_exc_qual, (size_t)n_exc));
+                CU(h, cudaMemcpyAsync(d_exc_index, exc_index, sizeof(int64_t) * (size_t)n_exc, k, st));
+                CU(h, cudaMemcpyAsync(d_exc_base, exc_base, (size_t)n_exc, k, st));
+                CU(h, cudaMemcpyAsync(d_exc_qual, exc_qual, (size_t)n_exc, k, st));
+                // exception indices address the batch's seq array: rebased to the window [s_lo, s_hi) by the pointer arithmetic below
+                apply_seq_exceptions_kernel<<<(unsigned)((n_exc + 255) / 256), 256, 0, st>>>(d_exc_index, d_exc_base, d_exc_qual, n_exc, s_lo, s_hi, R.bases.p + R.n_seq - s_lo,
+                                                                                             R.quals.p + R.n_seq - s_lo);
+            }
+            h->total_launches += 2;
+        } else {
+            CU(h, cudaMemcpyAsync(R.bases.p + R.n_seq, b->bases + s_lo, (size_t)nseq, k, st));
+            CU(h, cudaMemcpyAsync(R.quals.p + R.n_seq, b->quals + s_lo, (size_t)nseq, k, st));
+        }
         if (b->base_dirs) CU(h, cudaMemcpyAsync(R.base_dirs.p + R.n_seq, b->base_dirs + s_lo, (size_t)nseq, k, st));
     }
     if (want_coll) {
@@ -659,6 +700,7 @@ extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
     CU(h, cudaMemcpyAsync(&status, d_status, sizeof(status), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));   // the caller's buffers are consumed
     tr.mark("h2d+ingest");
+    pool_free(h, d_seq); pool_free(h, d_exc_index); pool_free(h, d_exc_base); pool_free(h, d_exc_qual);
     auto rollback = [&]() { R.n = first; pool_free(h, d_status); pool_free(h, d_trig); };
     if (status.error) {
         rollback();
@@ -686,10 +728,39 @@ extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) {
     R.n_cigar += ncig; R.n_seq += nseq;
     R.min_start = std::min(R.min_start, status.min_start);
     R.max_end = std::max(R.max_end, status.max_end);
-    BatchHostView hv{b->bases + s_lo, b->seq_off, s_lo};
-    const int rc = explicit_find_candidates(h, (size_t)first, &hv);
+    BatchHostView hv{seq ? nullptr : b->bases + s_lo, b->seq_off, s_lo};
+    const int rc = explicit_find_candidates(h, (size_t)first, seq ? nullptr : &hv);
     tr.mark("candidates");
     return rc;
+}
+
+extern "C" int pb2_push_reads(pb2_handle* h, const pb2_read_batch* b) { return push_reads_impl(h, b, nullptr, 0, nullptr, nullptr, nullptr); }
+extern "C" int pb2_push_reads_packed(pb2_handle* h, const pb2_packed_read_batch* p) {
+    if (!h || !p) return fail(h, PB2_ERR_ARG, "pb2_push_reads_packed: bad argument");
+    pb2_read_batch b;
+    memset(&b, 0, sizeof(b));
+    b.n_reads = p->n_reads; b.pos0 = p->pos0; b.flag = p->flag; b.cigar_off = p->cigar_off; b.cigar = p->cigar; b.seq_off = p->seq_off;
+    b.base_dirs = p->base_dirs; b.collapsed = p->collapsed;
+    if (p->n_reads > 0 && !p->seq) return fail(h, PB2_ERR_ARG, "pb2_push_reads_packed: null array");
+    return push_reads_impl(h, &b, p->seq, p->n_exceptions, p->exc_index, p->exc_base, p->exc_qual);
+}
+// Host helper: bases + qualities -> the packed bytes of pb2_push_reads_packed and their exception list. Returns the number of exceptions (which may
+// exceed exc_capacity: then only the first exc_capacity were stored and the caller retries with larger arrays), or < 0 on a bad argument.
+extern "C" int64_t pb2_pack_reads(const uint8_t* bases, const uint8_t* quals, int64_t n, uint8_t* seq, int64_t* exc_index, uint8_t* exc_base, uint8_t* exc_qual,
+                                  int64_t exc_capacity) {
+    if (n < 0 || (n > 0 && (!bases || !quals || !seq))) return PB2_ERR_ARG;
+    int64_t n_exc = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const uint8_t b = bases[i], q = quals[i];
+        const int a2 = b == 'A' ? 0 : b == 'G' ? 1 : b == 'C' ? 2 : b == 'T' ? 3 : -1;
+        const uint8_t v = (a2 < 0 || q > 63) ? 0 : (uint8_t)((a2 << 6) | q);
+        seq[i] = v;
+        if (v == 0) {
+            if (n_exc < exc_capacity && exc_index && exc_base && exc_qual) { exc_index[n_exc] = i; exc_base[n_exc] = b; exc_qual[n_exc] = q; }
+            n_exc++;
+        }
+    }
+    return n_exc;
 }
 
 extern "C" int pb2_totals(pb2_handle* h, int64_t* total_collapsed) {

@@ -94,21 +94,21 @@ __device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, 
         }
     }
 
-    RowState st[2];
-    st[0].key = st[1].key = -1; st[0].widx = st[1].widx = -1; st[0].acc = st[1].acc = 0; st[0].row = st[1].row = 0; st[0].tag = st[1].tag = 0;
+    // two rows in flight, one per entry kind (separate variables: they stay in registers)
+    RowState sb, sd;
+    sb.key = sd.key = -1; sb.widx = sd.widx = -1; sb.acc = sd.acc = 0; sb.row = sd.row = 0; sb.tag = sd.tag = 0;
     auto flush_word = [&](RowState& s) {
-        if (kFill && s.widx >= 0 && s.acc != 0) *reinterpret_cast<uint32_t*>(ft.data + s.row * 32 + s.widx * 4) = s.acc;
+        if (kFill && s.widx >= 0 && s.acc != 0) *reinterpret_cast<uint32_t*>(ft.data + s.row * 32 + s.widx * 4) |= s.acc;
         s.widx = -1; s.acc = 0;
     };
-    // one entry: kind 0 base / 1 deletion; `byte` is the slot value, meta what row_meta gets when the entry opens a row
-    auto put = [&](int kind, int position, int dir, uint32_t byte, int2 meta, int tag) -> int64_t {
+    // one entry into the row of its kind: `byte` is the slot value, meta what row_meta gets when the entry opens a row
+    auto put_into = [&](RowState& s, int kind, int position, int dir, uint32_t byte, int2 meta, int tag) -> int64_t {
         const int64_t li = pv_locus_index(rg, position);
         if (li < 0) return -1;
         const int64_t tile = li >> 5;
         const int l = (int)(li & 31);
         const int cls = pv_class(kind, dir, cg);
         const int64_t key = tile * n_classes + cls;
-        RowState& s = st[kind];
         if (key != s.key || tag != s.tag) {
             flush_word(s);
             s.key = key;
@@ -131,7 +131,7 @@ __device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, 
     // Deletion entries at positions [a, b] clipped to the window; a Deletion entry below the quality bar is never counted (:170-177)
     auto put_dels = [&](int a, int b, int dir, int dq, int anchor) {
         if (dq < rg.min_bq) return;
-        for (int j = max(a, w_lo); j <= min(b, w_hi); j++) put(1, j, dir, (uint32_t)min(max(dq, 1), 63), make_int2(INT32_MIN + anchor, 0), anchor);
+        for (int j = max(a, w_lo); j <= min(b, w_hi); j++) put_into(sd, 1, j, dir, (uint32_t)min(max(dq, 1), 63), make_int2(INT32_MIN + anchor, 0), anchor);
     };
     const int2 read_meta = make_int2(start_pos, end_pos);
 
@@ -149,22 +149,15 @@ __device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, 
                 if (ref_pos > last_position + 1 && ref_pos - 1 >= w_lo && last_position + 1 <= w_hi)       // deletion (or N skip) before this base (:170-177)
                     put_dels(last_position + 1, ref_pos - 1, dir_at(read_idx), del_q(read_idx), pv_anchor_type(end_pos, ref_pos, start_pos));
                 const int k0 = max(0, w_lo - ref_pos), k1 = min(len, w_hi - ref_pos + 1);
-                for (int k = k0; k < k1; k++) {
-                    const int ri = read_idx + k, position = ref_pos + k;
-                    const int dir = dir_at(ri);
-                    const uint8_t b = bases[ri];
-                    const int q = quals[ri];
-                    const int a2 = pv_allele2(b);
-                    const uint32_t byte = a2 < 0 ? 1u : ((uint32_t)a2 << 6) | (uint32_t)min(max(q, 1), 63);
-                    const int64_t li = put(0, position, dir, byte, read_meta, 0);
-                    if (!kFill || li < 0) continue;
-                    // SNV-candidate bookkeeping the counts cannot express (CallMNVs off; CandidateVariantFinder.cs:90-168): only a usable mismatch against
-                    // an A/C/G/T reference base can matter; it goes to the segment's side list (the rule of tile_scatter_kernel)
-                    if (a2 < 0 || q < rg.min_bq) continue;
+                // the flagged-entry test of one counted base (fill pass): SNV-candidate bookkeeping the counts cannot express (CallMNVs off;
+                // CandidateVariantFinder.cs:90-168). Only a usable mismatch against an A/C/G/T reference base can matter; it goes to the segment's side list
+                // (the rule of tile_scatter_kernel)
+                auto flag_entry = [&](int k, int ri, int position, int dir, int a2, int q, int64_t li) {
+                    if (a2 < 0 || q < rg.min_bq) return;
                     const bool in_chr = rg.chr == nullptr || position <= rg.chr_len;
                     const uint8_t rb = (rg.chr != nullptr && position >= 1 && position <= rg.chr_len) ? rg.chr[position - 1] : (uint8_t)'N';
                     const int ra2 = pv_allele2(rb);
-                    if (ra2 < 0 || ra2 == a2) continue;
+                    if (ra2 < 0 || ra2 == a2) return;
                     uint32_t code = 0;
                     if (op != 0 || !in_chr) code |= PB2_ENTRY_NO_CANDIDATE;
                     else {
@@ -190,6 +183,60 @@ __device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, 
                             ft.exc_entries[2 * slot + 1] = (code | (uint32_t)a2 | ((uint32_t)dir << 3)) | ((uint32_t)min(q, 127) << 8) | ((uint32_t)(an | (cc << 4)) << 16);
                         }
                     }
+                };
+                // the common case: every position is a locus (no interval gaps) and the bases of the stretch share one direction. The stretch is one row
+                // of its tile: the row is opened once and written word by word - all threads of a warp run the same eight iterations over the tile's words
+                bool fast = k0 < k1 && rg.index_of_pos == nullptr;
+                const int dir0 = fast ? dir_at(read_idx + k0) : 0;
+                if (fast && dirs != nullptr) for (int k = k0 + 1; k < k1; k++) fast = fast && dir_at(read_idx + k) == dir0;
+                if (fast) {
+                    const int64_t tile = (int64_t)(w_lo - rg.lo) >> 5;
+                    const int cls = pv_class(0, dir0, cg);
+                    const int64_t key = tile * n_classes + cls;
+                    if (key != sb.key || sb.tag != 0) {
+                        flush_word(sb);
+                        sb.key = key; sb.tag = 0;
+                        if (kFill) {
+                            const int kk = atomicAdd(ft.cursor + key, 1);
+                            sb.row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[tile * n_classes + cls - 1] : 0) + kk;
+                            ft.row_meta[sb.row] = read_meta;
+                        } else {
+                            atomicAdd(cls_rows + key, 1);
+                        }
+                    }
+                    if (kFill) {
+                        flush_word(sb);
+                        const int tp = rg.lo + (int)(tile << 5);                       // position of the tile's locus 0
+                        const int la = ref_pos + k0 - tp, lb = ref_pos + k1 - 1 - tp;   // loci of the stretch inside the tile
+                        uint32_t* const rowp = reinterpret_cast<uint32_t*>(ft.data + sb.row * 32);
+#pragma unroll 1
+                        for (int w = 0; w < 8; w++) {
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int l = 4 * w + j;
+                                if (l < la || l > lb) continue;
+                                const int position = tp + l, k = position - ref_pos, ri = read_idx + k;
+                                const uint8_t b = bases[ri];
+                                const int q = quals[ri];
+                                const int a2 = pv_allele2(b);
+                                acc |= (a2 < 0 ? 1u : ((uint32_t)a2 << 6) | (uint32_t)min(max(q, 1), 63)) << (8 * j);
+                                flag_entry(k, ri, position, dir0, a2, q, (int64_t)(position - rg.lo));
+                            }
+                            if (acc) rowp[w] |= acc;   // the row is this thread's own and starts out zero: a word may be completed by a later stretch
+                        }
+                    }
+                } else
+                for (int k = k0; k < k1; k++) {
+                    const int ri = read_idx + k, position = ref_pos + k;
+                    const int dir = dir_at(ri);
+                    const uint8_t b = bases[ri];
+                    const int q = quals[ri];
+                    const int a2 = pv_allele2(b);
+                    const uint32_t byte = a2 < 0 ? 1u : ((uint32_t)a2 << 6) | (uint32_t)min(max(q, 1), 63);
+                    const int64_t li = put_into(sb, 0, position, dir, byte, read_meta, 0);
+                    if (!kFill || li < 0) continue;
+                    flag_entry(k, ri, position, dir, a2, q, li);
                 }
                 last_position = ref_pos + len - 1;
             }
@@ -202,8 +249,8 @@ __device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, 
     }
     if (ends_in_del && read_len > 0)                                              // (:195-210)
         put_dels(last_position + 1, last_position + del_len, dir_at(read_len - 1), del_q(read_len - 1), kNumAnchors - 1);
-    flush_word(st[0]);
-    flush_word(st[1]);
+    flush_word(sb);
+    flush_word(sd);
 }
 
 // One thread per (read, tile) piece: thread t takes read t / kWalkPieces and, of the tiles the read touches, the (t % kWalkPieces)-th, (+ kWalkPieces)-th, ...

@@ -303,6 +303,43 @@ class GpuStateManager:
                         ptr(d.get("collapsed"), np.uint8))
         self._chk(self._L.pb2_push_reads(self._h, C.byref(b)))
 
+    @staticmethod
+    def pack_reads(d):
+        """pb2_pack_reads: the struct of arrays of AddReadsSoA with bases + quals replaced by one packed byte per base (+ the exception list)."""
+        L = N.load()
+        bases, quals = np.ascontiguousarray(d["bases"], dtype=np.uint8), np.ascontiguousarray(d["quals"], dtype=np.uint8)
+        n = len(bases)
+        seq = np.empty(n, dtype=np.uint8)
+        cap = max(1024, n // 64)
+        while True:
+            ei, eb, eq = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.uint8), np.empty(cap, dtype=np.uint8)
+            ne = L.pb2_pack_reads(bases.ctypes.data, quals.ctypes.data, n, seq.ctypes.data, ei.ctypes.data, eb.ctypes.data, eq.ctypes.data, cap)
+            if ne < 0:
+                raise PiscesB200Error(int(ne), "pb2_pack_reads")
+            if ne <= cap:
+                break
+            cap = int(ne)
+        out = {k: d[k] for k in ("pos0", "flag", "cigar_off", "cigar", "seq_off")}
+        out.update(seq=seq, exc_index=ei[:ne].copy(), exc_base=eb[:ne].copy(), exc_qual=eq[:ne].copy(), base_dirs=d.get("base_dirs"), collapsed=d.get("collapsed"))
+        return out
+
+    def AddReadsPacked(self, d):
+        """pb2_push_reads_packed with the dict pack_reads returns (numpy arrays or pinned torch tensors)."""
+        keep = []
+
+        def ptr(a, dt):
+            if a is None:
+                return None
+            if hasattr(a, "data_ptr"):
+                return a.data_ptr()
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data if len(a) else None
+        b = N.PackedReadBatch(int(len(d["pos0"])), ptr(d["pos0"], np.int32), ptr(d["flag"], np.uint16), ptr(d["cigar_off"], np.int64), ptr(d["cigar"], np.uint32),
+                              ptr(d["seq_off"], np.int64), ptr(d["seq"], np.uint8), int(len(d["exc_index"])), ptr(d["exc_index"], np.int64), ptr(d["exc_base"], np.uint8),
+                              ptr(d["exc_qual"], np.uint8), ptr(d.get("base_dirs"), np.uint8), ptr(d.get("collapsed"), np.uint8))
+        self._chk(self._L.pb2_push_reads_packed(self._h, C.byref(b)))
+
     def AddReadBatch(self, batch):
         """pb2_push_reads with a ready pb2_read_batch (e.g. from BamReadStager): IStateManager.AddAlleleCounts + FindCandidates for each read."""
         self._chk(self._L.pb2_push_reads(self._h, C.byref(batch)))

@@ -95,6 +95,34 @@ def test_batched_pushes_equal_one_push(batch):
     assert len(want) > 20 and want.tobytes() == got.tobytes()
 
 
+def test_packed_reads_equal_plain_reads():
+    """pb2_push_reads_packed (one byte per base + exceptions) fills the same read store: N bases, qualities 0 and > 63 go through the exception list."""
+    pb = _pb()
+    gen, cfg = CONFIGS["c2"]
+    d = synth.make_reads(6000, 80, seed=13, **gen)
+    rng = np.random.default_rng(3)
+    bases, quals = d["bases"].copy(), d["quals"].copy()
+    bases[rng.random(len(bases)) < 0.004] = ord("N")
+    quals[rng.random(len(quals)) < 0.002] = 0
+    quals[rng.random(len(quals)) < 0.002] = 70
+    d = dict(d, bases=bases, quals=quals)
+    ref = bytes(d["ref"]).decode()
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", ref)
+    sm.AddReadsSoA(d)
+    want = pb.GpuAlleleCaller().Call(sm, raw=True)
+    sm.close()
+    packed = pb.GpuStateManager.pack_reads(d)
+    assert len(packed["exc_index"]) > 100
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", ref)
+    sm.AddReadsPacked(packed)
+    got = pb.GpuAlleleCaller().Call(sm, raw=True)
+    sm.close()
+    assert len(want) > 50 and want.tobytes() == got.tobytes()
+    oc = _oracle(d, **cfg)
+    oc.finish()
+    compare_records(oc.records(), got, b"")
+
+
 def test_staged_reads_resident_step_equals_flush():
     """pb2_stage_reads + pb2_call_resident (the bench's device-resident step) emits the records pb2_flush returns."""
     pb = _pb()
