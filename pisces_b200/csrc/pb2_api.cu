@@ -265,7 +265,8 @@ extern "C" int pb2_set_reference(pb2_handle* h, const char* chr_name, const uint
     if (h->d_chr) { cudaFree(h->d_chr); h->d_chr = nullptr; }
     h->chr_len = len;
     if (len > 0) {
-        CU(h, cudaMalloc(&h->d_chr, (size_t)len));
+        CU(h, cudaMalloc(&h->d_chr, (size_t)len + 16));   // slack: kernels read the chromosome a word at a time
+        CU(h, cudaMemsetAsync(h->d_chr + len, 'N', 16, h->stream));
         CU(h, cudaMemcpyAsync(h->d_chr, h->h_chr.data(), (size_t)len, cudaMemcpyHostToDevice, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
     }
@@ -578,7 +579,7 @@ static cudaError_t grow(pb2_handle* h, GrowBuf<T>& b, size_t need, size_t keep) 
 }
 static void free_reads(pb2_handle* h) {
     DeviceReads& R = h->reads;
-    void* ptrs[] = {R.pos0.p, R.end_pos.p, R.flag.p, R.cigar_off.p, R.seq_off.p, R.cigar.p, R.bases.p, R.quals.p, R.base_dirs.p, R.collapsed.p};
+    void* ptrs[] = {R.pos0.p, R.end_pos.p, R.flag.p, R.cigar_off.p, R.seq_off.p, R.cigar.p, R.bases.p, R.quals.p, R.base_dirs.p, R.collapsed.p, R.slots.p};
     for (void* p : ptrs) pool_free(h, p);
     h->reads = DeviceReads();
 }
@@ -637,6 +638,7 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
     CU(h, grow(h, R.cigar, (size_t)(R.n_cigar + ncig), (size_t)R.n_cigar));
     CU(h, grow(h, R.bases, (size_t)(R.n_seq + nseq), (size_t)R.n_seq));
     CU(h, grow(h, R.quals, (size_t)(R.n_seq + nseq), (size_t)R.n_seq));
+    CU(h, grow(h, R.slots, (size_t)(R.n_seq + nseq) + 32, R.n_seq ? (size_t)R.n_seq + 16 : 0));
     if (want_dirs) {
         CU(h, grow(h, R.base_dirs, (size_t)(R.n_seq + nseq), R.has_dirs ? (size_t)R.n_seq : 0));
         if (!R.has_dirs && first > 0) dirs_from_flags_kernel<<<(unsigned)first, 64, 0, st>>>(R.flag.p, R.seq_off.p, 0, first, R.base_dirs.p);
@@ -676,6 +678,7 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
         }
         if (b->base_dirs) CU(h, cudaMemcpyAsync(R.base_dirs.p + R.n_seq, b->base_dirs + s_lo, (size_t)nseq, k, st));
     }
+    if (nseq) { CU(h, launch_reads_slots(R.bases.p + R.n_seq, R.quals.p + R.n_seq, nseq, R.slots.p + 16 + R.n_seq, st)); h->total_launches += 1; }
     if (want_coll) {
         if (b->collapsed) CU(h, cudaMemcpyAsync(R.collapsed.p + first, b->collapsed, (size_t)nb, k, st));
         else CU(h, cudaMemsetAsync(R.collapsed.p + first, 0, (size_t)nb, st));
@@ -902,7 +905,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
         CUC(pool_alloc(h, (void**)&d_anch, (size_t)std::max<int64_t>(n_entries, 1)));
         CUC(launch_reads_emit(rv, rg, d_off, d_cursor, d_code, d_qual, d_anch, st));
         CUC(pool_alloc(h, (void**)&d_ref, (size_t)n_loci));
-        CUC(launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, d_ref, st));
+        CUC(launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, d_ref, nullptr, st));
         h->total_launches += 6;
         pb2_pileup_csr csr;
         memset(&csr, 0, sizeof(csr));
@@ -945,10 +948,14 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     CU(h, pool_alloc_t(h, &s.exc_entries, 2 * (size_t)s.exc_capacity));
     CU(h, pool_alloc_t(h, &s.counters, 4));
     CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
-    CU(h, launch_pvert_fill(rv, rg, R.end_pos.p, nc, s.pv_tile_row0, s.pv_cls_end, d_cursor, s.pv_data, s.pv_row_meta, s.exc_entries, s.counters + 3, s.exc_capacity, st));
-    CU(h, launch_pvert_transpose(s.pv_data, s.pv_rows / 32, st));
+    uint8_t* d_ref_slot = nullptr;
     CU(h, pool_alloc_t(h, &s.ref_base, (size_t)n_loci));
-    CU(h, launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, s.ref_base, st));
+    CU(h, pool_alloc_t(h, &d_ref_slot, (size_t)s.n_tiles * 32));
+    CU(h, launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, s.ref_base, d_ref_slot, st));
+    CU(h, launch_pvert_fill(rv, rg, R.end_pos.p, nc, s.pv_tile_row0, s.pv_cls_end, d_cursor, s.pv_data, s.pv_row_meta, s.exc_entries, s.counters + 3, s.exc_capacity, d_ref_slot,
+                            st));
+    CU(h, launch_pvert_transpose(s.pv_data, s.pv_rows / 32, st));
+    pool_free(h, d_ref_slot);
     CU(h, cudaEventRecord(h->ev_stage1, st));
     h->total_launches += 6;
     s.n_entries = R.n_seq;
@@ -1530,12 +1537,14 @@ static int compact_reads(pb2_handle* h, int32_t cleared_to) {
         CU(h, grow(h, K.cigar, std::max<size_t>(kc, 1), 0)); CU(h, grow(h, K.bases, std::max<size_t>(ks, 1), 0)); CU(h, grow(h, K.quals, std::max<size_t>(ks, 1), 0));
         if (R.has_dirs) CU(h, grow(h, K.base_dirs, std::max<size_t>(ks, 1), 0));
         if (R.has_collapsed) CU(h, grow(h, K.collapsed, kn, 0));
+        CU(h, grow(h, K.slots, ks + 32, 0));
         ReadsCompactArgs a;
         a.n = R.n; a.new_index = ni; a.new_cigar = nc; a.new_seq = ns;
         a.pos0 = R.pos0.p; a.end_pos = R.end_pos.p; a.flag = R.flag.p; a.cigar_off = R.cigar_off.p; a.cigar = R.cigar.p; a.seq_off = R.seq_off.p;
         a.bases = R.bases.p; a.quals = R.quals.p; a.base_dirs = R.has_dirs ? R.base_dirs.p : nullptr; a.collapsed = R.has_collapsed ? R.collapsed.p : nullptr;
         a.o_pos0 = K.pos0.p; a.o_end_pos = K.end_pos.p; a.o_flag = K.flag.p; a.o_cigar_off = K.cigar_off.p; a.o_cigar = K.cigar.p; a.o_seq_off = K.seq_off.p;
         a.o_bases = K.bases.p; a.o_quals = K.quals.p; a.o_base_dirs = K.base_dirs.p; a.o_collapsed = K.collapsed.p;
+        a.slots = R.slots.p + 16; a.o_slots = K.slots.p + 16;
         CU(h, launch_reads_compact(a, st));
         K.n = totals[0]; K.n_cigar = totals[1]; K.n_seq = totals[2];
         K.min_start = R.min_start; K.max_end = R.max_end; K.last_pos0 = R.last_pos0;

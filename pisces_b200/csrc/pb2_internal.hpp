@@ -22,6 +22,7 @@ struct ReadsView {
     const uint8_t* quals;
     const uint8_t* base_dirs;
     const uint8_t* collapsed;
+    const uint8_t* slots = nullptr;   // PVERT slot byte of every read base (pb2_pvert.cuh), derived at ingest; 16 bytes of slack on either side
 };
 struct RegionView {
     int32_t lo, hi;
@@ -79,7 +80,10 @@ struct ReadsCompactArgs {
     const uint8_t *bases, *quals, *base_dirs, *collapsed;
     int32_t* o_pos0; int32_t* o_end_pos; uint16_t* o_flag; int64_t* o_cigar_off; uint32_t* o_cigar; int64_t* o_seq_off;
     uint8_t *o_bases, *o_quals, *o_base_dirs, *o_collapsed;
+    const uint8_t* slots; uint8_t* o_slots;   // (already offset by the leading slack)
 };
+// slot bytes (pb2_pvert.cuh) of the bases [first, first + n) of the store
+cudaError_t launch_reads_slots(const uint8_t* bases, const uint8_t* quals, int64_t n, uint8_t* slots, cudaStream_t st);
 cudaError_t launch_reads_compact(const ReadsCompactArgs& a, cudaStream_t st);
 // 1000-bp blocks touched by the reads at positions > cleared_through: bit (key - key0) of the bitmap
 cudaError_t launch_reads_block_bitmap(const int32_t* pos0, const int32_t* end_pos, int64_t n, int32_t cleared_through, int32_t key0, int32_t n_keys, uint32_t* bitmap,
@@ -101,13 +105,14 @@ struct DeviceReads {
     GrowBuf<int64_t> cigar_off, seq_off;   // [n + 1]
     GrowBuf<uint32_t> cigar;
     GrowBuf<uint8_t> bases, quals, base_dirs, collapsed;
+    GrowBuf<uint8_t> slots;   // [16 + n_seq + 16]
     bool has_dirs = false, has_collapsed = false;
     int32_t min_start = INT32_MAX, max_end = 0;   // extent of the stored reads (1-based positions)
     int32_t last_pos0 = -1;                       // Position of the read pushed last (-1: none yet)
     size_t size() const { return (size_t)n; }
     pb2::ReadsView view() const {
         return pb2::ReadsView{(int32_t)n, pos0.p, flag.p, cigar_off.p, cigar.p, seq_off.p, bases.p, quals.p, has_dirs ? base_dirs.p : nullptr,
-                              has_collapsed ? collapsed.p : nullptr};
+                              has_collapsed ? collapsed.p : nullptr, slots.p ? slots.p + 16 : nullptr};
     }
 };
 

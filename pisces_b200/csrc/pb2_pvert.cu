@@ -43,6 +43,7 @@ struct FillTargets {
     uint32_t* exc_entries;
     unsigned long long* exc_count;
     int64_t exc_capacity;
+    const uint32_t* ref_slot_words;   // per locus one byte, allele2 << 6 of the reference base (1 where it is not A/C/G/T), four loci per word
 };
 
 // Walks one read exactly as RegionStateManager.AddAlleleCounts does, restricted to the reference positions [w_lo, w_hi] of ONE tile, and hands every entry
@@ -208,22 +209,31 @@ __device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, 
                         flush_word(sb);
                         const int tp = rg.lo + (int)(tile << 5);                       // position of the tile's locus 0
                         const int la = ref_pos + k0 - tp, lb = ref_pos + k1 - 1 - tp;   // loci of the stretch inside the tile
+                        const int delta = read_idx - ref_pos + tp;                      // read index of the base at locus l: l + delta
                         uint32_t* const rowp = reinterpret_cast<uint32_t*>(ft.data + sb.row * 32);
+                        const uint8_t* const sl = rv.slots + s0;                        // the read's slot bytes (16 bytes of slack around the plane)
+                        const uint32_t* const refw = ft.ref_slot_words + (tile << 3);
 #pragma unroll 1
                         for (int w = 0; w < 8; w++) {
-                            uint32_t acc = 0;
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const int l = 4 * w + j;
-                                if (l < la || l > lb) continue;
-                                const int position = tp + l, k = position - ref_pos, ri = read_idx + k;
-                                const uint8_t b = bases[ri];
-                                const int q = quals[ri];
-                                const int a2 = pv_allele2(b);
-                                acc |= (a2 < 0 ? 1u : ((uint32_t)a2 << 6) | (uint32_t)min(max(q, 1), 63)) << (8 * j);
-                                flag_entry(k, ri, position, dir0, a2, q, (int64_t)(position - rg.lo));
+                            const int l4 = 4 * w;
+                            if (l4 + 3 < la || l4 > lb) continue;
+                            // four slot bytes from an arbitrary byte address: two aligned words and a funnel shift
+                            const uintptr_t a = reinterpret_cast<uintptr_t>(sl + (l4 + delta));
+                            const uint32_t* const aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+                            uint32_t v = __funnelshift_r(aw[0], aw[1], (unsigned)(a & 3u) * 8u);
+                            const int c0 = max(la - l4, 0), c1 = min(lb - l4, 3);       // bytes of the word inside the stretch
+                            const uint32_t m = (0xffffffffu << (8 * c0)) & (0xffffffffu >> (8 * (3 - c1)));
+                            v &= m;
+                            // candidate flags: only a base whose allele differs from the reference allele can need one
+                            uint32_t x = rg.chr != nullptr ? ((v ^ refw[w]) & 0xc0c0c0c0u & m) : 0u;
+                            while (x) {
+                                const int j = (__ffs((int)x) - 1) >> 3;
+                                x &= ~(0xffu << (8 * j));
+                                const int l = l4 + j, position = tp + l, k = position - ref_pos, ri = read_idx + k;
+                                flag_entry(k, ri, position, dir0, pv_allele2(bases[ri]), quals[ri], (int64_t)(position - rg.lo));
                             }
-                            if (acc) rowp[w] |= acc;   // the row is this thread's own and starts out zero: a word may be completed by a later stretch
+                            if (c0 == 0 && c1 == 3) rowp[w] = v;   // a whole word of this stretch
+                            else if (v) rowp[w] |= v;              // the row is this thread's own and starts out zero: a later stretch may complete the word
                         }
                     }
                 } else
@@ -325,11 +335,16 @@ __global__ void __launch_bounds__(32 * kTransposeWarps) pvert_transpose_kernel(u
 }
 
 __global__ void pvert_ref_bases_kernel(const uint8_t* __restrict__ chr, int64_t chr_len, const int32_t* __restrict__ positions, int32_t first_position, int64_t n_loci,
-                                       uint8_t* __restrict__ ref_base) {
+                                       uint8_t* __restrict__ ref_base, uint8_t* __restrict__ ref_slot, int64_t n_padded) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_loci) return;
-    const int64_t p = positions ? positions[i] : (int64_t)first_position + i;
-    ref_base[i] = (chr != nullptr && p >= 1 && p <= chr_len) ? chr[p - 1] : (uint8_t)'N';
+    if (i >= n_padded) return;
+    uint8_t b = 'N';
+    if (i < n_loci) {
+        const int64_t p = positions ? positions[i] : (int64_t)first_position + i;
+        if (chr != nullptr && p >= 1 && p <= chr_len) b = chr[p - 1];
+        ref_base[i] = b;
+    }
+    if (ref_slot != nullptr) { const int a2 = pv_allele2(b); ref_slot[i] = a2 < 0 ? (uint8_t)1 : (uint8_t)(a2 << 6); }
 }
 
 // One warp per requested locus: lane j takes row 32 g + j of every 32-row group of every class of the locus' tile.
@@ -390,9 +405,9 @@ cudaError_t launch_pvert_layout(int32_t* cls_rows, int32_t n_tiles, int n_classe
     return cudaGetLastError();
 }
 cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
-                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, cudaStream_t st) {
+                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, const uint8_t* ref_slot, cudaStream_t st) {
     if (rv.n_reads == 0) return cudaSuccess;
-    FillTargets ft{tile_row0, cls_end, cursor, data, row_meta, exc_entries, exc_count, exc_capacity};
+    FillTargets ft{tile_row0, cls_end, cursor, data, row_meta, exc_entries, exc_count, exc_capacity, reinterpret_cast<const uint32_t*>(ref_slot)};
     return launch_walk<true>(rv, rg, end_pos, n_classes, nullptr, ft, st);
 }
 cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st) {
@@ -400,9 +415,11 @@ cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t
     pvert_transpose_kernel<<<(unsigned)((n_blocks + kTransposeWarps - 1) / kTransposeWarps), 32 * kTransposeWarps, 0, st>>>(data, n_blocks);
     return cudaGetLastError();
 }
-cudaError_t launch_pvert_ref_bases(const uint8_t* chr, int64_t chr_len, const int32_t* positions, int32_t first_position, int64_t n_loci, uint8_t* ref_base, cudaStream_t st) {
+cudaError_t launch_pvert_ref_bases(const uint8_t* chr, int64_t chr_len, const int32_t* positions, int32_t first_position, int64_t n_loci, uint8_t* ref_base, uint8_t* ref_slot,
+                                   cudaStream_t st) {
     if (n_loci <= 0) return cudaSuccess;
-    pvert_ref_bases_kernel<<<(unsigned)((n_loci + 255) / 256), 256, 0, st>>>(chr, chr_len, positions, first_position, n_loci, ref_base);
+    const int64_t n_padded = ref_slot ? (n_loci + 31) / 32 * 32 : n_loci;
+    pvert_ref_bases_kernel<<<(unsigned)((n_padded + 255) / 256), 256, 0, st>>>(chr, chr_len, positions, first_position, n_loci, ref_base, ref_slot, n_padded);
     return cudaGetLastError();
 }
 cudaError_t launch_pvert_gather(const PvertPileup& in, const int32_t* req_locus, int32_t n_req, int32_t* out_counts, int32_t* out_collapsed, int min_bq, cudaStream_t st) {

@@ -69,9 +69,11 @@ struct RegionView;
 cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, cudaStream_t st);
 cudaError_t launch_pvert_layout(int32_t* cls_rows /* in: rows per class; out: inclusive padded prefix */, int32_t n_tiles, int n_classes, int64_t* tile_rows, cudaStream_t st);
 cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
-                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, cudaStream_t st);
+                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, const uint8_t* ref_slot, cudaStream_t st);
 cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st);
-cudaError_t launch_pvert_ref_bases(const uint8_t* chr, int64_t chr_len, const int32_t* positions, int32_t first_position, int64_t n_loci, uint8_t* ref_base, cudaStream_t st);
+// ref_base[n_loci] ASCII; ref_slot (optional, [n_loci rounded up to 32]): allele2 << 6 of the reference base, 1 where it is not A/C/G/T
+cudaError_t launch_pvert_ref_bases(const uint8_t* chr, int64_t chr_len, const int32_t* positions, int32_t first_position, int64_t n_loci, uint8_t* ref_base, uint8_t* ref_slot,
+                                   cudaStream_t st);
 // 198-bin counts (+ collapsed-read counts) of requested loci straight from the blocks: same outputs as launch_gather_locus_counts
 cudaError_t launch_pvert_gather(const PvertPileup& in, const int32_t* req_locus, int32_t n_req, int32_t* out_counts, int32_t* out_collapsed, int min_bq, cudaStream_t st);
 // the hot kernel over PVERT (pb2_kernels.cu)

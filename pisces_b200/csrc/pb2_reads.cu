@@ -363,6 +363,22 @@ cudaError_t launch_reads_ingest(const ReadsView& rv, int32_t first_read, int64_t
     return cudaGetLastError();
 }
 
+// slot = allele2 << 6 | quality clamped to [1, 63]; a base that is not A/C/G/T is (0, quality 1): counted, never an allele (pb2_pvert.cuh)
+__global__ void reads_slots_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, int64_t n, uint8_t* __restrict__ slots) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = bases[i], q = quals[i];
+    const uint32_t d = b - 65u;                                                     // 'A'
+    const bool valid = d < 20u && ((0x80045u >> d) & 1u);                           // A C G T
+    const uint32_t a2 = (0x78u >> (2u * ((b >> 1) & 3u))) & 3u;                     // A 0, C 2, G 1, T 3 (AlleleType order A G C T)
+    slots[i] = (uint8_t)(valid ? ((a2 << 6) | min(max(q, 1u), 63u)) : 1u);
+}
+cudaError_t launch_reads_slots(const uint8_t* bases, const uint8_t* quals, int64_t n, uint8_t* slots, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    reads_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bases, quals, n, slots);
+    return cudaGetLastError();
+}
+
 __global__ void reads_keep_flags_kernel(const int32_t* __restrict__ end_pos, int64_t n, int32_t cleared_to, const int64_t* __restrict__ cigar_off,
                                         const int64_t* __restrict__ seq_off, int64_t* __restrict__ keep_reads, int64_t* __restrict__ keep_cigar, int64_t* __restrict__ keep_seq) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,6 +413,7 @@ __global__ void reads_compact_kernel(ReadsCompactArgs a) {
         a.o_bases[os + k] = a.bases[s0 + k];
         a.o_quals[os + k] = a.quals[s0 + k];
         if (a.base_dirs) a.o_base_dirs[os + k] = a.base_dirs[s0 + k];
+        if (a.slots) a.o_slots[os + k] = a.slots[s0 + k];
     }
 }
 cudaError_t launch_reads_compact(const ReadsCompactArgs& a, cudaStream_t st) {

@@ -116,11 +116,12 @@ def test_packed_reads_equal_plain_reads():
     sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", ref)
     sm.AddReadsPacked(packed)
     got = pb.GpuAlleleCaller().Call(sm, raw=True)
+    arena = sm.AlleleArena()
     sm.close()
     assert len(want) > 50 and want.tobytes() == got.tobytes()
     oc = _oracle(d, **cfg)
     oc.finish()
-    compare_records(oc.records(), got, b"")
+    compare_records(oc.records(), got, arena)
 
 
 def test_staged_reads_resident_step_equals_flush():
