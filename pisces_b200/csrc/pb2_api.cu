@@ -198,8 +198,46 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
 
 // Device memory of a handle comes from its own stream-ordered pool (cudaMallocFromPoolAsync on the handle's stream) that never returns memory to
 // the driver while the handle lives: after the first push every staging buffer is a pool hit, so a push costs no cudaMalloc / cudaFree.
-static cudaError_t pool_alloc(pb2_handle* h, void** p, size_t bytes) { return cudaMallocFromPoolAsync(p, std::max<size_t>(bytes, 256), h->pool, h->stream); }
-static void pool_free(pb2_handle* h, void* p, size_t = 0) { if (p) cudaFreeAsync(p, h->stream); }
+// On top of the pool sits a small block cache: a freed block is kept by the handle and handed out again to the next request of about its size (within
+// 25 %), so a host that repeats the same push / flush cycle makes no allocator call at all in steady state (growing the pool by gigabytes costs tens to
+// hundreds of milliseconds and showed up as a x3 spread of the end-to-end step). All users are ordered on the handle's stream (the copy / side stream
+// work is joined by events before a block is freed), so a block is reused in stream order like a pool allocation.
+cudaError_t pb2_dev_alloc(pb2_handle* h, void** p, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 256) + 255) & ~(size_t)255;
+    long best = -1;
+    for (size_t i = 0; i < h->blocks.size(); i++) {
+        const DevBlock& b = h->blocks[i];
+        if (!b.used && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 + 4096 && (best < 0 || b.bytes < h->blocks[(size_t)best].bytes)) best = (long)i;
+    }
+    if (best >= 0) { h->blocks[(size_t)best].used = true; *p = h->blocks[(size_t)best].p; h->cached_free_bytes -= h->blocks[(size_t)best].bytes; return cudaSuccess; }
+    const cudaError_t e = cudaMallocFromPoolAsync(p, bytes, h->pool, h->stream);
+    if (e == cudaSuccess) h->blocks.push_back(DevBlock{*p, bytes, true});
+    return e;
+}
+void pb2_dev_free(pb2_handle* h, void* p) {
+    if (!p) return;
+    for (size_t i = 0; i < h->blocks.size(); i++)
+        if (h->blocks[i].p == p) {
+            h->blocks[i].used = false;
+            h->cached_free_bytes += h->blocks[i].bytes;
+            // bound what the cache holds back: beyond 64 idle blocks or 24 GB the oldest idle blocks return to the pool
+            size_t idle = 0;
+            for (auto& b : h->blocks) idle += b.used ? 0 : 1;
+            for (size_t k = 0; k < h->blocks.size() && (idle > 64 || h->cached_free_bytes > ((size_t)24 << 30));) {
+                if (!h->blocks[k].used) { cudaFreeAsync(h->blocks[k].p, h->stream); h->cached_free_bytes -= h->blocks[k].bytes; h->blocks.erase(h->blocks.begin() + (long)k); idle--; }
+                else k++;
+            }
+            return;
+        }
+    cudaFreeAsync(p, h->stream);   // not one of ours (allocated before the cache existed)
+}
+static void release_block_cache(pb2_handle* h) {
+    for (auto& b : h->blocks) if (!b.used) cudaFreeAsync(b.p, h->stream);
+    h->blocks.erase(std::remove_if(h->blocks.begin(), h->blocks.end(), [](const DevBlock& b) { return !b.used; }), h->blocks.end());
+    h->cached_free_bytes = 0;
+}
+static cudaError_t pool_alloc(pb2_handle* h, void** p, size_t bytes) { return pb2_dev_alloc(h, p, bytes); }
+static void pool_free(pb2_handle* h, void* p, size_t = 0) { pb2_dev_free(h, p); }
 template <class T>
 static cudaError_t pool_alloc_t(pb2_handle* h, T** p, size_t count) { return pool_alloc(h, reinterpret_cast<void**>(p), count * sizeof(T)); }
 
@@ -247,6 +285,7 @@ extern "C" void pb2_destroy(pb2_handle* h) {
     if (h->ev_stage0) cudaEventDestroy(h->ev_stage0);
     if (h->ev_stage1) cudaEventDestroy(h->ev_stage1);
     for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_scattered[i]) cudaEventDestroy(h->ev_scattered[i]); }
+    release_block_cache(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -576,6 +615,13 @@ static cudaError_t grow(pb2_handle* h, GrowBuf<T>& b, size_t need, size_t keep) 
     pool_free(h, b.p);
     b.p = np; b.cap = ncap;
     return e;
+}
+// the reads leave the store, its buffers stay for the next push (pb2_reset / pb2_destroy release them)
+static void clear_reads(pb2_handle* h) {
+    DeviceReads& R = h->reads;
+    R.n = R.n_cigar = R.n_seq = 0;
+    R.has_dirs = R.has_collapsed = false;
+    R.min_start = INT32_MAX; R.max_end = 0; R.last_pos0 = -1;
 }
 static void free_reads(pb2_handle* h) {
     DeviceReads& R = h->reads;
@@ -1774,7 +1820,7 @@ static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_reco
     h->cands.erase(std::remove_if(h->cands.begin(), h->cands.end(), [](const HostCand& c) { return !c.alive; }), h->cands.end());
     explicit_reindex(h);
     if (up_to_position < 0 && keep_reads) { h->cleared_through = 0; h->gapped_ref.clear(); h->last_trigger_key = 0; h->snv_explicit_ranges.clear(); }
-    else if (up_to_position < 0) { free_reads(h); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; h->snv_explicit_ranges.clear(); rearm_forced(h); }
+    else if (up_to_position < 0) { clear_reads(h); h->cleared_through = 0; h->gapped_ref.clear(); h->triggers.clear(); h->last_trigger_key = 0; h->push_last_key = 0; h->snv_explicit_ranges.clear(); rearm_forced(h); }
     else if (reads_path && cleared_to > h->cleared_through) {
         const int rc = compact_reads(h, cleared_to);
         if (rc != PB2_OK) return rc;

@@ -68,15 +68,15 @@ struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
     pb2_handle* owner = nullptr;
-    ~DevBuf() { if (p) { if (owner) cudaFreeAsync(p, owner->stream); else cudaFree(p); } }
+    ~DevBuf() { if (p) { if (owner) pb2_dev_free(owner, p); else cudaFree(p); } }
     cudaError_t reserve(size_t n, cudaStream_t st, bool keep = false, pb2_handle* h = nullptr) {
         if (n <= cap) return cudaSuccess;
         const size_t ncap = std::max<size_t>(n, cap * 2 + 64);
         T* np = nullptr;
-        cudaError_t e = h ? cudaMallocFromPoolAsync(reinterpret_cast<void**>(&np), ncap * sizeof(T), h->pool, st) : cudaMalloc(&np, ncap * sizeof(T));
+        cudaError_t e = h ? pb2_dev_alloc(h, reinterpret_cast<void**>(&np), ncap * sizeof(T)) : cudaMalloc(&np, ncap * sizeof(T));
         if (e != cudaSuccess) return e;
         if (keep && p && cap) e = cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
-        if (p) { if (owner) cudaFreeAsync(p, st); else { cudaStreamSynchronize(st); cudaFree(p); } }
+        if (p) { if (owner) pb2_dev_free(owner, p); else { cudaStreamSynchronize(st); cudaFree(p); } }
         p = np; cap = ncap; owner = h;
         return e;
     }
@@ -774,7 +774,8 @@ static int find_candidates_impl(pb2_handle* h, size_t first_read, const BatchHos
     // real data, so the buffer starts smaller and the kernel is run again with the exact size if it did not fit
     const bool per_base = h->cfg.call_mnvs || snv_only;
     const int64_t n_cig = R.n_cigar, n_seq = R.n_seq;
-    int64_t capacity = n_cig + (per_base ? std::min<int64_t>(n_seq, std::max<int64_t>(1 << 20, n_seq / 16)) : 0) + 16;
+    // (a position-limited search - explicit_materialize_snvs - touches a few hundred positions)
+    int64_t capacity = (snv_only ? 0 : n_cig) + (per_base ? std::min<int64_t>(n_seq, snv_only ? (1 << 18) : std::max<int64_t>(1 << 20, n_seq / 16)) : 0) + 16;
     CUX(h, d_count.reserve(1, st, false, h));
     const ReadsView rv = R.view();
     unsigned long long cnt = 0;

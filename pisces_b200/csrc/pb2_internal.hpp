@@ -179,8 +179,11 @@ struct Segment {   // one staged pileup (pb2_push_pileup*)
     unsigned long long h_var_count = 0, h_exc_count = 0;
 };
 
+struct DevBlock { void* p; size_t bytes; bool used; };
 struct pb2_handle {
     pb2_config cfg;
+    std::vector<DevBlock> blocks;   // device blocks handed out by pb2_dev_alloc: in use, or idle and waiting for the next request of their size
+    size_t cached_free_bytes = 0;
     pb2::DeviceConfig dcfg;
     int device = 0;
     int num_sms = 0;
@@ -235,6 +238,9 @@ struct pb2_handle {
 };
 
 constexpr int32_t kCollapsedTotalTwice = INT32_MIN;   // marker in pb2_call_record_ext.collapsed_total[0] between explicit_call_batch and pb2_flush
+// pb2_api.cu: device memory of a handle (pool + block cache, stream-ordered on the handle's stream)
+cudaError_t pb2_dev_alloc(pb2_handle* h, void** p, size_t bytes);
+void pb2_dev_free(pb2_handle* h, void* p);
 // pb2_explicit.cu
 int pb2_fail(pb2_handle* h, int code, const std::string& msg);
 // RegionState.AddCandidate (:94-174): merge into the table (summing counts) or append; tracks MaxAlleleEndpoint of the block.

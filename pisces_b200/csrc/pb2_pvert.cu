@@ -265,12 +265,19 @@ __device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, 
 
 // One thread per (read, tile) piece: thread t takes read t / kWalkPieces and, of the tiles the read touches, the (t % kWalkPieces)-th, (+ kWalkPieces)-th, ...
 constexpr int kWalkPieces = 8;
+// A SIMPLE read: one 'M' operation, its own direction for every base, every position a locus. Its pieces are written by pvert_fill_simple_kernel.
+__device__ __forceinline__ bool pv_simple_read(const ReadsView& rv, const RegionView& rg, int r) {
+    if (rv.base_dirs != nullptr || rg.index_of_pos != nullptr) return false;
+    const int64_t c0 = rv.cigar_off[r];
+    return rv.cigar_off[r + 1] - c0 == 1 && (rv.cigar[c0] & 15u) == 0;
+}
 template <bool kFill>
 __global__ void __launch_bounds__(256) pvert_walk_kernel(ReadsView rv, RegionView rg, const int32_t* __restrict__ end_pos_of, int n_classes, int32_t* __restrict__ cls_rows,
-                                                        FillTargets ft) {
+                                                        FillTargets ft, int skip_simple) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = (int)(t / kWalkPieces), k = (int)(t % kWalkPieces);
     if (r >= rv.n_reads) return;
+    if (skip_simple && pv_simple_read(rv, rg, r)) return;
     const int start_pos = rv.pos0[r] + 1, end_pos = end_pos_of[r];
     const int a = max(start_pos, rg.lo), e = min(end_pos, rg.hi);
     if (a > e) return;
@@ -284,10 +291,102 @@ __global__ void __launch_bounds__(256) pvert_walk_kernel(ReadsView rv, RegionVie
         pv_walk_piece<kFill>(rv, rg, r, end_pos, max(w_lo, a), min(w_hi, e), n_classes, cls_rows, ft);
     }
 }
+// The candidate-flag test of one counted base of a simple read (see flag_entry in pv_walk_piece), out of line: it runs for the few bases whose allele
+// differs from the reference allele.
+__device__ __noinline__ void pv_flag_simple(const uint8_t* __restrict__ rbases, const uint8_t* __restrict__ rquals, const uint8_t* __restrict__ chr, int64_t chr_len, int min_bq,
+                                            int region_lo, uint32_t* __restrict__ exc_entries, unsigned long long* __restrict__ exc_count, int64_t exc_capacity, int ri,
+                                            int position, int dir, int cg, int start_pos, int end_pos, int len) {
+    const int a2 = pv_allele2(rbases[ri]);
+    const int q = rquals[ri];
+    if (a2 < 0 || q < min_bq) return;
+    const bool in_chr = position <= chr_len;
+    const uint8_t rb = (position >= 1 && position <= chr_len) ? chr[position - 1] : (uint8_t)'N';
+    const int ra2 = pv_allele2(rb);
+    if (ra2 < 0 || ra2 == a2) return;
+    uint32_t code = 0;
+    if (!in_chr) code |= PB2_ENTRY_NO_CANDIDATE;
+    else {
+        if (ri + 1 < len) {   // open on the right: the next base of the operation exists and is unusable -> FlushVariant(..., openRight = true)
+            const int nq = rquals[ri + 1];
+            const bool nb_n = pv_allele2(rbases[ri + 1]) < 0;
+            const bool n_in = position + 1 <= chr_len;
+            const bool nref_n = n_in && pv_allele2(chr[position]) < 0;
+            if (n_in && (nq < min_bq || nb_n || nref_n)) code |= PB2_ENTRY_OPEN_RIGHT;
+        }
+        if (position == start_pos) code |= PB2_ENTRY_OPEN_LEFT;
+        if (position == end_pos) code |= PB2_ENTRY_OPEN_RIGHT;
+    }
+    if (!code) return;
+    const unsigned long long slot = atomicAdd(exc_count, 1ull);
+    if ((int64_t)slot < exc_capacity) {
+        const int an = pv_anchor_type(end_pos, position, start_pos);
+        const int cc = pv_collapsed_code(cg, dir);
+        exc_entries[2 * slot] = (uint32_t)(position - region_lo);
+        exc_entries[2 * slot + 1] = (code | (uint32_t)a2 | ((uint32_t)dir << 3)) | ((uint32_t)min(q, 127) << 8) | ((uint32_t)(an | (cc << 4)) << 16);
+    }
+}
+
+// The pieces of simple reads (the bulk of any read set): a piece is one row, copied out of the read's slot bytes a word at a time - the nine source
+// words are requested together, so a thread waits for memory once per piece. Few registers: many pieces in flight per SM.
+__global__ void __launch_bounds__(256) pvert_fill_simple_kernel(ReadsView rv, RegionView rg, int n_classes, FillTargets ft) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(t / kWalkPieces), k = (int)(t % kWalkPieces);
+    if (r >= rv.n_reads || !pv_simple_read(rv, rg, r)) return;
+    const int len = (int)(rv.cigar[rv.cigar_off[r]] >> 4);
+    const int start_pos = rv.pos0[r] + 1, end_pos = rv.pos0[r] + len;
+    const int a = max(start_pos, rg.lo), e = min(end_pos, rg.hi);
+    if (a > e || len == 0) return;
+    const int64_t s0 = rv.seq_off[r];
+    const int dir = (rv.flag[r] & 0x10) ? DIR_R : DIR_F;
+    const int cg = (rg.expect_collapsed && rv.collapsed) ? pv_collapsed_group(rv.collapsed[r]) : 0;
+    const int cls = pv_class(0, dir, cg);
+    for (int tile = ((a - rg.lo) >> 5) + k; tile <= ((e - rg.lo) >> 5); tile += kWalkPieces) {
+        const int tp = rg.lo + (tile << 5);
+        const int la = max(a - tp, 0), lb = min(e - tp, 31);
+        const int64_t key = (int64_t)tile * n_classes + cls;
+        const int kk = atomicAdd(ft.cursor + key, 1);
+        // the source words while the row number is on its way
+        const int delta = tp - start_pos;                                         // read index of the base at locus l: l + delta
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(rv.slots + s0 + delta);   // address of the slot byte of locus 0 (may lie before the read: never loaded)
+        const uint32_t* const aw = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
+        const unsigned sh = (unsigned)(a0 & 3u) * 8u;
+        const int wa = la >> 2, wb = lb >> 2;
+        uint32_t src[9];
+#pragma unroll
+        for (int w = 0; w < 9; w++) src[w] = (w >= wa && w <= wb + 1) ? aw[w] : 0u;
+        const int64_t row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[(int64_t)tile * n_classes + cls - 1] : 0) + kk;
+        ft.row_meta[row] = make_int2(start_pos, end_pos);
+        uint32_t* const rowp = reinterpret_cast<uint32_t*>(ft.data + row * 32);
+        const uint32_t* const refw = ft.ref_slot_words + ((int64_t)tile << 3);
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            if (w < wa || w > wb) continue;
+            const int c0 = max(la - 4 * w, 0), c1 = min(lb - 4 * w, 3);            // bytes of the word inside the read
+            const uint32_t m = (0xffffffffu << (8 * c0)) & (0xffffffffu >> (8 * (3 - c1)));
+            const uint32_t v = __funnelshift_r(src[w], src[w + 1], sh) & m;
+            uint32_t x = rg.chr != nullptr ? ((v ^ refw[w]) & 0xc0c0c0c0u & m) : 0u;  // only a base whose allele differs from the reference allele can need a flag
+            while (x) {
+                const int j = (__ffs((int)x) - 1) >> 3;
+                x &= ~(0xffu << (8 * j));
+                const int l = 4 * w + j;
+                pv_flag_simple(rv.bases + s0, rv.quals + s0, rg.chr, rg.chr_len, rg.min_bq, rg.lo, ft.exc_entries, ft.exc_count, ft.exc_capacity, l + delta, tp + l, dir, cg,
+                               start_pos, end_pos, len);
+            }
+            rowp[w] = v;
+        }
+    }
+}
+
 template <bool kFill>
 static cudaError_t launch_walk(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, const FillTargets& ft, cudaStream_t st) {
     const int64_t threads = (int64_t)rv.n_reads * kWalkPieces;
-    pvert_walk_kernel<kFill><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rv, rg, end_pos, n_classes, cls_rows, ft);
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    if (kFill) {
+        pvert_fill_simple_kernel<<<grid, 256, 0, st>>>(rv, rg, n_classes, ft);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    pvert_walk_kernel<kFill><<<grid, 256, 0, st>>>(rv, rg, end_pos, n_classes, cls_rows, ft, kFill ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -364,18 +364,33 @@ cudaError_t launch_reads_ingest(const ReadsView& rv, int32_t first_read, int64_t
 }
 
 // slot = allele2 << 6 | quality clamped to [1, 63]; a base that is not A/C/G/T is (0, quality 1): counted, never an allele (pb2_pvert.cuh)
+__device__ __forceinline__ uint32_t slots_of_word(uint32_t b4, uint32_t q4) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t b = (b4 >> (8 * k)) & 0xffu, q = (q4 >> (8 * k)) & 0xffu;
+        const uint32_t d = b - 65u;                                                     // 'A'
+        const bool valid = d < 20u && ((0x80045u >> d) & 1u);                           // A C G T
+        const uint32_t a2 = (0x78u >> (2u * ((b >> 1) & 3u))) & 3u;                     // A 0, C 2, G 1, T 3 (AlleleType order A G C T)
+        out |= (valid ? ((a2 << 6) | min(max(q, 1u), 63u)) : 1u) << (8 * k);
+    }
+    return out;
+}
 __global__ void reads_slots_kernel(const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals, int64_t n, uint8_t* __restrict__ slots) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // 16 bytes per thread where the three pointers allow it (they share their offset into 256-byte aligned planes, the slot plane 16 bytes further)
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (i >= n) return;
-    const uint32_t b = bases[i], q = quals[i];
-    const uint32_t d = b - 65u;                                                     // 'A'
-    const bool valid = d < 20u && ((0x80045u >> d) & 1u);                           // A C G T
-    const uint32_t a2 = (0x78u >> (2u * ((b >> 1) & 3u))) & 3u;                     // A 0, C 2, G 1, T 3 (AlleleType order A G C T)
-    slots[i] = (uint8_t)(valid ? ((a2 << 6) | min(max(q, 1u), 63u)) : 1u);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(bases + i) | reinterpret_cast<uintptr_t>(quals + i) | reinterpret_cast<uintptr_t>(slots + i)) & 15u) == 0;
+    if (aligned && i + 16 <= n) {
+        const uint4 b = *reinterpret_cast<const uint4*>(bases + i), q = *reinterpret_cast<const uint4*>(quals + i);
+        *reinterpret_cast<uint4*>(slots + i) = make_uint4(slots_of_word(b.x, q.x), slots_of_word(b.y, q.y), slots_of_word(b.z, q.z), slots_of_word(b.w, q.w));
+    } else {
+        for (int64_t k = i; k < n && k < i + 16; k++) slots[k] = (uint8_t)slots_of_word(bases[k], quals[k]);
+    }
 }
 cudaError_t launch_reads_slots(const uint8_t* bases, const uint8_t* quals, int64_t n, uint8_t* slots, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    reads_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bases, quals, n, slots);
+    reads_slots_kernel<<<(unsigned)(((n + 15) / 16 + 255) / 256), 256, 0, st>>>(bases, quals, n, slots);
     return cudaGetLastError();
 }
 
