@@ -793,10 +793,47 @@ static int find_candidates_impl(pb2_handle* h, size_t first_read, const BatchHos
         capacity = (int64_t)cnt + 16;
     }
     if (cnt == 0) return PB2_OK;
-    std::vector<RawCand> raw((size_t)cnt);
-    CUX(h, cudaMemcpy(raw.data(), d_raw.p, sizeof(RawCand) * (size_t)cnt, cudaMemcpyDeviceToHost));
-    // FindCandidates' own order: read by read, operation by operation
-    std::sort(raw.begin(), raw.end(), [](const RawCand& a, const RawCand& b) { return a.read != b.read ? a.read < b.read : a.order < b.order; });
+    // Many occurrences, few distinct candidates: reduce by key on the device and bring back one row per distinct candidate (with the place of its first
+    // occurrence). Small sets, and sets with alleles longer than RawCand::read_bases or a hash collision, take the one-by-one path below.
+    std::vector<RawCand> raw;
+    std::vector<CandGroup> groups;
+    if (cnt >= 2048) {
+        const int64_t n = (int64_t)cnt;
+        DevBuf<unsigned long long> k0, k1; DevBuf<uint32_t> i0, i1; DevBuf<int32_t> head, gof, flg; DevBuf<uint8_t> tmp; DevBuf<CandGroup> dg;
+        size_t tb = 0;
+        CUX(h, cand_reduce_temp_bytes(n, &tb));
+        CUX(h, k0.reserve((size_t)n, st, false, h)); CUX(h, k1.reserve((size_t)n, st, false, h)); CUX(h, i0.reserve((size_t)n, st, false, h)); CUX(h, i1.reserve((size_t)n, st, false, h));
+        CUX(h, head.reserve((size_t)n, st, false, h)); CUX(h, gof.reserve((size_t)n, st, false, h)); CUX(h, flg.reserve(1, st, false, h)); CUX(h, tmp.reserve(tb + 16, st, false, h));
+        CUX(h, cudaMemsetAsync(flg.p, 0, sizeof(int32_t), st));
+        CUX(h, launch_cand_group(d_raw.p, n, k0.p, k1.p, i0.p, i1.p, head.p, gof.p, tmp.p, tb + 16, flg.p, st));
+        int32_t n_groups = 0, flags = 0;
+        CUX(h, cudaMemcpyAsync(&n_groups, gof.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUX(h, cudaMemcpyAsync(&flags, flg.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUX(h, cudaStreamSynchronize(st));
+        h->total_launches += 5;
+        if (flags == 0 && n_groups > 0) {
+            CUX(h, dg.reserve((size_t)n_groups, st, false, h));
+            CUX(h, launch_cand_reduce(d_raw.p, i1.p, gof.p, n, dg.p, n_groups, st));
+            h->total_launches += 2;
+            groups.resize((size_t)n_groups);
+            CUX(h, cudaMemcpyAsync(groups.data(), dg.p, sizeof(CandGroup) * groups.size(), cudaMemcpyDeviceToHost, st));
+            CUX(h, cudaStreamSynchronize(st));
+            std::sort(groups.begin(), groups.end(), [](const CandGroup& a, const CandGroup& b) { return a.first_seen < b.first_seen; });
+            // the head candidates themselves: gathered on the host side from the raw list (one small copy per group would be slower than the list)
+            raw.resize((size_t)cnt);
+            CUX(h, cudaMemcpy(raw.data(), d_raw.p, sizeof(RawCand) * (size_t)cnt, cudaMemcpyDeviceToHost));
+            std::vector<RawCand> heads;
+            heads.reserve(groups.size());
+            for (auto& g : groups) heads.push_back(raw[g.first_index]);
+            raw.swap(heads);
+        }
+    }
+    if (groups.empty()) {
+        raw.resize((size_t)cnt);
+        CUX(h, cudaMemcpy(raw.data(), d_raw.p, sizeof(RawCand) * (size_t)cnt, cudaMemcpyDeviceToHost));
+        // FindCandidates' own order: read by read, operation by operation
+        std::sort(raw.begin(), raw.end(), [](const RawCand& a, const RawCand& b) { return a.read != b.read ? a.read < b.read : a.order < b.order; });
+    }
     // alleles longer than RawCand::read_bases whose read is not in the caller's batch: fetched from the device store
     std::vector<uint8_t> fetched;
     auto read_bases_of = [&](const RawCand& rc, int n_from_read, std::string& out) -> int {
@@ -814,7 +851,8 @@ static int find_candidates_impl(pb2_handle* h, size_t first_read, const BatchHos
         return PB2_OK;
     };
     const char* chr = reinterpret_cast<const char*>(h->h_chr.data());
-    for (const RawCand& rc : raw) {
+    for (size_t ci = 0; ci < raw.size(); ci++) {
+        const RawCand& rc = raw[ci];
         if (rc.position <= h->cleared_through || rc.position < 1) continue;
         if (snv_only && (rc.type != CAT_SNV || rc.position <= snv_lo || rc.position > snv_hi)) continue;
         if ((int64_t)rc.position - 1 + rc.ref_len > h->chr_len) continue;   // Substring past the chromosome end throws in the reference
@@ -827,13 +865,19 @@ static int find_candidates_impl(pb2_handle* h, size_t first_read, const BatchHos
         else if (rc.type == CAT_DEL) c.alt.assign(1, chr[rc.position - 1]);
         else rcode = read_bases_of(rc, (int)rc.alt_len, c.alt);
         if (rcode != PB2_OK) return rcode;
-        c.support[rc.dir] = 1;
-        if (rc.flags & 4) c.well_anchored[rc.dir] = 1;
-        if (rc.collapsed) {   // CandidateVariantFinder.Create (:352-384)
-            const int t = rc.collapsed - 1;
-            c.collapsed_mut[t]++;
-            if (t == 4 || t == 6) c.collapsed_mut[2]++;
-            else if (t == 5 || t == 7) c.collapsed_mut[3]++;
+        if (!groups.empty()) {   // one row per distinct candidate, its occurrences already summed
+            const CandGroup& g = groups[ci];
+            for (int k = 0; k < 3; k++) { c.support[k] = g.support[k]; c.well_anchored[k] = g.well_anchored[k]; }
+            for (int k = 0; k < 8; k++) c.collapsed_mut[k] = g.collapsed_mut[k];
+        } else {
+            c.support[rc.dir] = 1;
+            if (rc.flags & 4) c.well_anchored[rc.dir] = 1;
+            if (rc.collapsed) {   // CandidateVariantFinder.Create (:352-384)
+                const int t = rc.collapsed - 1;
+                c.collapsed_mut[t]++;
+                if (t == 4 || t == 6) c.collapsed_mut[2]++;
+                else if (t == 5 || t == 7) c.collapsed_mut[3]++;
+            }
         }
         explicit_add_candidate(h, c);
     }

@@ -57,6 +57,19 @@ cudaError_t launch_reads_candidates(const ReadsView& rv, int32_t first_read, con
                                     int expect_collapsed, RawCand* out, unsigned long long* count, int64_t capacity, int32_t pos_lo, int32_t pos_hi, int snv_only,
                                     const int32_t* end_pos, cudaStream_t st);
 
+// One distinct candidate of a read set after the device-side reduce by key (RegionState.AddCandidate): the counts of all its occurrences and where it
+// was raised first.
+struct CandGroup {
+    int32_t support[3], well_anchored[3], collapsed_mut[8];
+    uint32_t first_index;            // index of (one of) its raw candidates
+    uint32_t pad_;
+    unsigned long long first_seen;   // (read << 32) | order of its first occurrence: FindCandidates' emission order
+};
+cudaError_t cand_reduce_temp_bytes(int64_t n, size_t* bytes);
+cudaError_t launch_cand_group(const RawCand* raw, int64_t n, unsigned long long* keys_in, unsigned long long* keys_out, uint32_t* idx_in, uint32_t* idx_out, int32_t* head,
+                              int32_t* group_of, void* temp, size_t temp_bytes, int32_t* flags, cudaStream_t st);
+cudaError_t launch_cand_reduce(const RawCand* raw, const uint32_t* idx, const int32_t* group_of, int64_t n, CandGroup* groups, int64_t n_groups, cudaStream_t st);
+
 // pb2_push_reads on the device: the new reads [first, n) of the store are validated (Read.cs:603-605, RegionStateManager.cs:363-364), their offsets
 // rebased, Read.EndPosition computed, and the positions where SmallVariantCaller.Execute would have called a batch collected
 // (SmallVariantCaller.cs:99-104: Call(read.Position - 1) whenever that enters a new 1000-bp block key).

@@ -356,10 +356,11 @@ __global__ void __launch_bounds__(256) pvert_fill_simple_kernel(ReadsView rv, Re
         for (int w = 0; w < 9; w++) src[w] = (w >= wa && w <= wb + 1) ? aw[w] : 0u;
         const int64_t row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[(int64_t)tile * n_classes + cls - 1] : 0) + kk;
         ft.row_meta[row] = make_int2(start_pos, end_pos);
-        uint32_t* const rowp = reinterpret_cast<uint32_t*>(ft.data + row * 32);
         const uint32_t* const refw = ft.ref_slot_words + ((int64_t)tile << 3);
+        uint32_t out[8];
 #pragma unroll
         for (int w = 0; w < 8; w++) {
+            out[w] = 0;
             if (w < wa || w > wb) continue;
             const int c0 = max(la - 4 * w, 0), c1 = min(lb - 4 * w, 3);            // bytes of the word inside the read
             const uint32_t m = (0xffffffffu << (8 * c0)) & (0xffffffffu >> (8 * (3 - c1)));
@@ -372,8 +373,12 @@ __global__ void __launch_bounds__(256) pvert_fill_simple_kernel(ReadsView rv, Re
                 pv_flag_simple(rv.bases + s0, rv.quals + s0, rg.chr, rg.chr_len, rg.min_bq, rg.lo, ft.exc_entries, ft.exc_count, ft.exc_capacity, l + delta, tp + l, dir, cg,
                                start_pos, end_pos, len);
             }
-            rowp[w] = v;
+            out[w] = v;
         }
+        // the whole row in two 16-byte stores (empty slots are zero: whole sectors are written, nothing is read back)
+        uint4* const rowq = reinterpret_cast<uint4*>(ft.data + row * 32);
+        rowq[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        rowq[1] = make_uint4(out[4], out[5], out[6], out[7]);
     }
 }
 

@@ -2,6 +2,8 @@
 // One thread walks one read's CIGAR exactly as RegionStateManager.AddAlleleCounts does
 // (src/lib/Pisces.Processing/RegionState/RegionStateManager.cs:118-220) and produces one entry per AddAlleleCount call; the SNV
 // candidate flags follow CandidateVariantFinder (src/lib/Pisces.Domain/Logic/CandidateVariantFinder.cs:90-203,496-553) for CallMNVs=false.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "pb2_internal.hpp"
 
 namespace pb2 {
@@ -438,20 +440,125 @@ cudaError_t launch_reads_compact(const ReadsCompactArgs& a, cudaStream_t st) {
 }
 __global__ void reads_block_bitmap_kernel(const int32_t* __restrict__ pos0, const int32_t* __restrict__ end_pos, int64_t n, int32_t cleared_through, int32_t key0,
                                           int32_t n_keys, uint32_t* __restrict__ bitmap) {
+    // reads arrive in position order: the 32 reads of a warp touch a handful of neighbouring blocks. The warp's key range is reduced first and its
+    // lanes then set the bits of that range (usually one bit, set by one lane)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int a = max(pos0[i] + 1, cleared_through + 1), e = end_pos[i];
-    if (a > e) return;
-    for (int k = (a + 999) / 1000; k <= (e + 999) / 1000; k++) {
-        const int b = k - key0;
-        // reads arrive in position order: nearly every read finds its block's bit already set (a stale view only costs a redundant atomic)
-        if (b >= 0 && b < n_keys && !((*reinterpret_cast<volatile uint32_t*>(bitmap + (b >> 5)) >> (b & 31)) & 1u)) atomicOr(bitmap + (b >> 5), 1u << (b & 31));
+    int k_lo = INT32_MAX, k_hi = INT32_MIN;
+    if (i < n) {
+        const int a = max(pos0[i] + 1, cleared_through + 1), e = end_pos[i];
+        if (a <= e) { k_lo = (a + 999) / 1000; k_hi = (e + 999) / 1000; }
+    }
+    k_lo = __reduce_min_sync(0xffffffffu, k_lo);
+    k_hi = __reduce_max_sync(0xffffffffu, k_hi);
+    if (k_lo > k_hi) return;
+    // (a warp whose reads are far apart would mark blocks between them that no read touches: only when the range is one every read of the warp
+    // overlaps - the common case - is it used; otherwise every lane marks its own blocks)
+    const int lane = threadIdx.x & 31;
+    bool mine = false;
+    int m_lo = 0, m_hi = -1;
+    if (i < n) {
+        const int a = max(pos0[i] + 1, cleared_through + 1), e = end_pos[i];
+        if (a <= e) { m_lo = (a + 999) / 1000; m_hi = (e + 999) / 1000; mine = true; }
+    }
+    const bool same = !mine || (m_lo == k_lo && m_hi == k_hi);
+    if (__all_sync(0xffffffffu, same)) {
+        for (int k = k_lo + lane; k <= k_hi; k += 32) { const int b = k - key0; if (b >= 0 && b < n_keys) atomicOr(bitmap + (b >> 5), 1u << (b & 31)); }
+    } else {
+        for (int k = m_lo; k <= m_hi; k++) { const int b = k - key0; if (b >= 0 && b < n_keys) atomicOr(bitmap + (b >> 5), 1u << (b & 31)); }
     }
 }
 cudaError_t launch_reads_block_bitmap(const int32_t* pos0, const int32_t* end_pos, int64_t n, int32_t cleared_through, int32_t key0, int32_t n_keys, uint32_t* bitmap,
                                       cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     reads_block_bitmap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos0, end_pos, n, cleared_through, key0, n_keys, bitmap);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ RegionState.AddCandidate on the device (reduce by key)
+// The candidates a read set raises are many (every read that carries an indel raises it again) and few distinct. They are grouped here: sorted by
+// (position, hash of the allele), equal neighbours merged with their counts summed - what RegionState.AddCandidate (RegionState.cs:94-174) does one
+// candidate at a time - and the host receives one row per distinct candidate with the (read, order) of its first occurrence, which is all it needs to
+// insert them in the reference's order. Two different candidates that share position and hash would be merged wrongly: the head test compares all
+// fields and raises `collision`, and the host then takes the one-by-one path instead.
+__device__ __forceinline__ bool raw_same(const RawCand& a, const RawCand& b) {
+    if (a.position != b.position || a.type != b.type || (a.flags & 3) != (b.flags & 3) || a.ref_len != b.ref_len || a.alt_len != b.alt_len) return false;
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (a.read_bases[k] != b.read_bases[k]) return false;
+    return true;
+}
+__global__ void cand_keys_kernel(const RawCand* __restrict__ raw, int64_t n, unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx, int32_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RawCand c = raw[i];
+    uint32_t hsh = 2166136261u;
+    auto mix = [&](uint32_t v) { hsh = (hsh ^ v) * 16777619u; };
+    mix(c.type); mix(c.flags & 3u); mix(c.ref_len); mix(c.alt_len);
+#pragma unroll
+    for (int k = 0; k < 8; k++) mix(c.read_bases[k]);
+    keys[i] = ((unsigned long long)(uint32_t)c.position << 32) | hsh;
+    idx[i] = (uint32_t)i;
+    const int n_from_read = c.type == CAT_INS ? (int)c.alt_len - 1 : (c.type == CAT_DEL ? 0 : (int)c.alt_len);
+    if (n_from_read > 8) atomicOr(flags, 1);   // alleles longer than RawCand::read_bases cannot be compared here
+}
+__global__ void cand_heads_kernel(const RawCand* __restrict__ raw, const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx, int64_t n,
+                                  int32_t* __restrict__ head, int32_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int hd = 1;
+    if (i > 0 && keys[i] == keys[i - 1]) {
+        hd = 0;
+        if (!raw_same(raw[idx[i]], raw[idx[i - 1]])) atomicOr(flags, 2);
+    }
+    head[i] = hd;
+}
+__global__ void cand_reduce_kernel(const RawCand* __restrict__ raw, const uint32_t* __restrict__ idx, const int32_t* __restrict__ group_of /* inclusive scan of head */,
+                                   int64_t n, CandGroup* __restrict__ groups) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RawCand c = raw[idx[i]];
+    CandGroup& g = groups[group_of[i] - 1];
+    atomicAdd(&g.support[c.dir], 1);
+    if (c.flags & 4) atomicAdd(&g.well_anchored[c.dir], 1);
+    if (c.collapsed) {   // CandidateVariantFinder.Create (:352-384)
+        const int t = c.collapsed - 1;
+        atomicAdd(&g.collapsed_mut[t], 1);
+        if (t == 4 || t == 6) atomicAdd(&g.collapsed_mut[2], 1);
+        else if (t == 5 || t == 7) atomicAdd(&g.collapsed_mut[3], 1);
+    }
+    const unsigned long long seen = ((unsigned long long)(uint32_t)c.read << 32) | (uint32_t)c.order;
+    const unsigned long long old = atomicMin(&g.first_seen, seen);
+    if (seen < old) g.first_index = idx[i];   // (racy among equal candidates only in which of them is kept: they are equal in every field that is read)
+}
+__global__ void cand_groups_init_kernel(CandGroup* __restrict__ groups, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CandGroup g;
+    memset(&g, 0, sizeof(g));
+    g.first_seen = ~0ull;
+    groups[i] = g;
+}
+cudaError_t cand_reduce_temp_bytes(int64_t n, size_t* bytes) {
+    size_t a = 0, b = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceScan::InclusiveSum(nullptr, b, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+    *bytes = std::max(a, b);
+    return e;
+}
+cudaError_t launch_cand_group(const RawCand* raw, int64_t n, unsigned long long* keys_in, unsigned long long* keys_out, uint32_t* idx_in, uint32_t* idx_out, int32_t* head,
+                              int32_t* group_of, void* temp, size_t temp_bytes, int32_t* flags, cudaStream_t st) {
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    cand_keys_kernel<<<grid, 256, 0, st>>>(raw, n, keys_in, idx_in, flags);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, 64, st);
+    if (e != cudaSuccess) return e;
+    cand_heads_kernel<<<grid, 256, 0, st>>>(raw, keys_out, idx_out, n, head, flags);
+    e = cub::DeviceScan::InclusiveSum(temp, temp_bytes, head, group_of, (int)n, st);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+cudaError_t launch_cand_reduce(const RawCand* raw, const uint32_t* idx, const int32_t* group_of, int64_t n, CandGroup* groups, int64_t n_groups, cudaStream_t st) {
+    cand_groups_init_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(groups, n_groups);
+    cand_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, idx, group_of, n, groups);
     return cudaGetLastError();
 }
 
