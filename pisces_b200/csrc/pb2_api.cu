@@ -1233,11 +1233,15 @@ static bool record_less_arena(const pb2_call_record& a, const pb2_call_record& b
 }
 
 // Per-locus gapped-MNV reference counts of a segment (RegionState._gappedMnvReferenceCounts), or nullptr when there are none.
+__global__ static void scatter_pairs_kernel(const int2* __restrict__ pairs, int32_t n, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicOr(out + pairs[i].x, pairs[i].y);
+}
+// The few loci that carry a gapped-MNV reference count or the suppress bit are scattered into a zeroed device array (no per-locus host work).
 static int upload_gapped(pb2_handle* h, const Segment& s, int32_t** d_out) {
     *d_out = nullptr;
     if (h->gapped_ref.empty() && h->snv_explicit_ranges.empty()) return PB2_OK;
-    std::vector<int32_t> g((size_t)s.n_loci, 0);
-    bool any = false;
+    std::vector<int2> pairs;
     auto locus_of = [&](int32_t pos) -> int64_t {
         if (s.has_positions) {
             auto it = std::lower_bound(s.h_positions.begin(), s.h_positions.end(), pos);
@@ -1248,18 +1252,29 @@ static int upload_gapped(pb2_handle* h, const Segment& s, int32_t** d_out) {
     };
     for (auto& kv : h->gapped_ref) {
         const int64_t l = locus_of(kv.first);
-        if (l >= 0) { g[(size_t)l] = kv.second & (kSuppressCountSnvs - 1); any = true; }
+        if (l >= 0) pairs.push_back(make_int2((int)l, kv.second & (kSuppressCountSnvs - 1)));
     }
     // positions whose SNV candidates are explicit (explicit_materialize_snvs): the hot kernel must not derive SNVs from the counts there
-    for (auto& r : h->snv_explicit_ranges)
-        for (int64_t i = 0; i < s.n_loci; i++) {
-            const int32_t pos = s.has_positions ? s.h_positions[(size_t)i] : s.first_position + (int32_t)i;
-            if (pos > r.first && pos <= r.second) { g[(size_t)i] |= kSuppressCountSnvs; any = true; }
+    for (auto& r : h->snv_explicit_ranges) {
+        int64_t i0, i1;   // loci with position in (r.first, r.second]
+        if (s.has_positions) {
+            i0 = std::upper_bound(s.h_positions.begin(), s.h_positions.end(), r.first) - s.h_positions.begin();
+            i1 = std::upper_bound(s.h_positions.begin(), s.h_positions.end(), r.second) - s.h_positions.begin();
+        } else {
+            i0 = std::max<int64_t>(0, (int64_t)r.first + 1 - s.first_position);
+            i1 = std::min<int64_t>(s.n_loci, (int64_t)r.second + 1 - s.first_position);
         }
-    if (!any) return PB2_OK;
-    CU(h, cudaMalloc(d_out, sizeof(int32_t) * g.size()));
-    CU(h, cudaMemcpyAsync(*d_out, g.data(), sizeof(int32_t) * g.size(), cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
+        for (int64_t i = i0; i < i1; i++) pairs.push_back(make_int2((int)i, kSuppressCountSnvs));
+    }
+    if (pairs.empty()) return PB2_OK;
+    int2* d_pairs = nullptr;
+    CU(h, pool_alloc_t(h, d_out, (size_t)s.n_loci));
+    CU(h, pool_alloc_t(h, &d_pairs, pairs.size()));
+    CU(h, cudaMemsetAsync(*d_out, 0, sizeof(int32_t) * (size_t)s.n_loci, h->stream));
+    CU(h, cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(int2) * pairs.size(), cudaMemcpyHostToDevice, h->stream));
+    scatter_pairs_kernel<<<(unsigned)((pairs.size() + 255) / 256), 256, 0, h->stream>>>(d_pairs, (int32_t)pairs.size(), *d_out);
+    CU(h, cudaStreamSynchronize(h->stream));   // pairs is a local
+    pool_free(h, d_pairs);
     return PB2_OK;
 }
 
@@ -1673,7 +1688,7 @@ static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_reco
             int32_t* d_gapped = nullptr;
             int rc = upload_gapped(h, s, &d_gapped);
             if (rc == PB2_OK) rc = run_segment(h, s, nullptr, d_collapsed, d_gapped);
-            if (d_gapped) cudaFree(d_gapped);
+            pool_free(h, d_gapped);
             if (rc != PB2_OK) return rc;
         }
         std::vector<pb2_call_record> hot_vars((size_t)s.h_var_count);

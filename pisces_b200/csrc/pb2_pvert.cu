@@ -328,57 +328,97 @@ __device__ __noinline__ void pv_flag_simple(const uint8_t* __restrict__ rbases, 
 
 // The pieces of simple reads (the bulk of any read set): a piece is one row, copied out of the read's slot bytes a word at a time - the nine source
 // words are requested together, so a thread waits for memory once per piece. Few registers: many pieces in flight per SM.
+// Thread mapping: blockIdx.y = which of its pieces, blockIdx.x * 256 + threadIdx.x = which read: the 32 reads of a warp are neighbours in position order,
+// their k-th pieces fall into one or two tiles, and the warp takes its rows from a tile's cursor with ONE atomic per (tile, class) instead of 32 (the
+// reads being sorted, every tile's cursor is hammered by the few thousand threads in flight around it: the same-address atomics were the kernel's time).
 __global__ void __launch_bounds__(256) pvert_fill_simple_kernel(ReadsView rv, RegionView rg, int n_classes, FillTargets ft) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = (int)(t / kWalkPieces), k = (int)(t % kWalkPieces);
-    if (r >= rv.n_reads || !pv_simple_read(rv, rg, r)) return;
-    const int len = (int)(rv.cigar[rv.cigar_off[r]] >> 4);
-    const int start_pos = rv.pos0[r] + 1, end_pos = rv.pos0[r] + len;
-    const int a = max(start_pos, rg.lo), e = min(end_pos, rg.hi);
-    if (a > e || len == 0) return;
-    const int64_t s0 = rv.seq_off[r];
-    const int dir = (rv.flag[r] & 0x10) ? DIR_R : DIR_F;
-    const int cg = (rg.expect_collapsed && rv.collapsed) ? pv_collapsed_group(rv.collapsed[r]) : 0;
+    const int r = blockIdx.x * 256 + threadIdx.x, k = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const bool mine = r < rv.n_reads && pv_simple_read(rv, rg, r);
+    int len = 0, start_pos = 0, end_pos = 0, a = 1, e = 0, dir = 0, cg = 0;
+    int64_t s0 = 0;
+    if (mine) {
+        len = (int)(rv.cigar[rv.cigar_off[r]] >> 4);
+        start_pos = rv.pos0[r] + 1; end_pos = rv.pos0[r] + len;
+        a = max(start_pos, rg.lo); e = min(end_pos, rg.hi);
+        if (len == 0) e = a - 1;
+        s0 = rv.seq_off[r];
+        dir = (rv.flag[r] & 0x10) ? DIR_R : DIR_F;
+        cg = (rg.expect_collapsed && rv.collapsed) ? pv_collapsed_group(rv.collapsed[r]) : 0;
+    }
     const int cls = pv_class(0, dir, cg);
-    for (int tile = ((a - rg.lo) >> 5) + k; tile <= ((e - rg.lo) >> 5); tile += kWalkPieces) {
-        const int tp = rg.lo + (tile << 5);
-        const int la = max(a - tp, 0), lb = min(e - tp, 31);
-        const int64_t key = (int64_t)tile * n_classes + cls;
-        const int kk = atomicAdd(ft.cursor + key, 1);
-        // the source words while the row number is on its way
-        const int delta = tp - start_pos;                                         // read index of the base at locus l: l + delta
-        const uintptr_t a0 = reinterpret_cast<uintptr_t>(rv.slots + s0 + delta);   // address of the slot byte of locus 0 (may lie before the read: never loaded)
-        const uint32_t* const aw = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
-        const unsigned sh = (unsigned)(a0 & 3u) * 8u;
-        const int wa = la >> 2, wb = lb >> 2;
-        uint32_t src[9];
+    int tile = mine && a <= e ? ((a - rg.lo) >> 5) + k : 1;
+    const int tile_last = mine && a <= e ? ((e - rg.lo) >> 5) : 0;
+    while (__any_sync(0xffffffffu, tile <= tile_last)) {
+        const bool work = tile <= tile_last;
+        const long long key = work ? (long long)tile * n_classes + cls : -1 - lane;   // idle lanes: keys of their own
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        int kk = 0;
+        if (work) {
+            const int leader = __ffs((int)peers) - 1;
+            if (lane == leader) kk = atomicAdd(ft.cursor + key, __popc(peers));
+            kk = __shfl_sync(peers, kk, leader) + __popc(peers & ((1u << lane) - 1u));
+            const int tp = rg.lo + (tile << 5);
+            const int la = max(a - tp, 0), lb = min(e - tp, 31);
+            const int delta = tp - start_pos;                                         // read index of the base at locus l: l + delta
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(rv.slots + s0 + delta);   // address of the slot byte of locus 0 (may lie before the read: never loaded)
+            const uint32_t* const aw = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
+            const unsigned sh = (unsigned)(a0 & 3u) * 8u;
+            const int wa = la >> 2, wb = lb >> 2;
+            uint32_t src[9];
 #pragma unroll
-        for (int w = 0; w < 9; w++) src[w] = (w >= wa && w <= wb + 1) ? aw[w] : 0u;
-        const int64_t row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[(int64_t)tile * n_classes + cls - 1] : 0) + kk;
-        ft.row_meta[row] = make_int2(start_pos, end_pos);
-        const uint32_t* const refw = ft.ref_slot_words + ((int64_t)tile << 3);
-        uint32_t out[8];
+            for (int w = 0; w < 9; w++) src[w] = (w >= wa && w <= wb + 1) ? aw[w] : 0u;
+            const int64_t row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[(int64_t)tile * n_classes + cls - 1] : 0) + kk;
+            ft.row_meta[row] = make_int2(start_pos, end_pos);
+            const uint32_t* const refw = ft.ref_slot_words + ((int64_t)tile << 3);
+            uint32_t out[8];
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
-            out[w] = 0;
-            if (w < wa || w > wb) continue;
-            const int c0 = max(la - 4 * w, 0), c1 = min(lb - 4 * w, 3);            // bytes of the word inside the read
-            const uint32_t m = (0xffffffffu << (8 * c0)) & (0xffffffffu >> (8 * (3 - c1)));
-            const uint32_t v = __funnelshift_r(src[w], src[w + 1], sh) & m;
-            uint32_t x = rg.chr != nullptr ? ((v ^ refw[w]) & 0xc0c0c0c0u & m) : 0u;  // only a base whose allele differs from the reference allele can need a flag
-            while (x) {
-                const int j = (__ffs((int)x) - 1) >> 3;
-                x &= ~(0xffu << (8 * j));
-                const int l = 4 * w + j;
-                pv_flag_simple(rv.bases + s0, rv.quals + s0, rg.chr, rg.chr_len, rg.min_bq, rg.lo, ft.exc_entries, ft.exc_count, ft.exc_capacity, l + delta, tp + l, dir, cg,
-                               start_pos, end_pos, len);
+            for (int w = 0; w < 8; w++) {
+                out[w] = 0;
+                if (w < wa || w > wb) continue;
+                const int c0 = max(la - 4 * w, 0), c1 = min(lb - 4 * w, 3);            // bytes of the word inside the read
+                const uint32_t m = (0xffffffffu << (8 * c0)) & (0xffffffffu >> (8 * (3 - c1)));
+                const uint32_t v = __funnelshift_r(src[w], src[w + 1], sh) & m;
+                uint32_t x = rg.chr != nullptr ? ((v ^ refw[w]) & 0xc0c0c0c0u & m) : 0u;  // only a base whose allele differs from the reference allele can need a flag
+                while (x) {
+                    const int j = (__ffs((int)x) - 1) >> 3;
+                    x &= ~(0xffu << (8 * j));
+                    const int l = 4 * w + j;
+                    pv_flag_simple(rv.bases + s0, rv.quals + s0, rg.chr, rg.chr_len, rg.min_bq, rg.lo, ft.exc_entries, ft.exc_count, ft.exc_capacity, l + delta, tp + l, dir, cg,
+                                   start_pos, end_pos, len);
+                }
+                out[w] = v;
             }
-            out[w] = v;
+            // the whole row in two 16-byte stores (empty slots are zero: whole sectors are written, nothing is read back)
+            uint4* const rowq = reinterpret_cast<uint4*>(ft.data + row * 32);
+            rowq[0] = make_uint4(out[0], out[1], out[2], out[3]);
+            rowq[1] = make_uint4(out[4], out[5], out[6], out[7]);
         }
-        // the whole row in two 16-byte stores (empty slots are zero: whole sectors are written, nothing is read back)
-        uint4* const rowq = reinterpret_cast<uint4*>(ft.data + row * 32);
-        rowq[0] = make_uint4(out[0], out[1], out[2], out[3]);
-        rowq[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        tile += kWalkPieces;
+    }
+}
+
+// the rows simple reads will take, same mapping and the same one-atomic-per-group trick
+__global__ void __launch_bounds__(256) pvert_count_simple_kernel(ReadsView rv, RegionView rg, int n_classes, int32_t* __restrict__ cls_rows) {
+    const int r = blockIdx.x * 256 + threadIdx.x, k = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const bool mine = r < rv.n_reads && pv_simple_read(rv, rg, r);
+    int a = 1, e = 0, cls = 0;
+    if (mine) {
+        const int len = (int)(rv.cigar[rv.cigar_off[r]] >> 4);
+        a = max(rv.pos0[r] + 1, rg.lo); e = min(rv.pos0[r] + len, rg.hi);
+        if (len == 0) e = a - 1;
+        const int cg = (rg.expect_collapsed && rv.collapsed) ? pv_collapsed_group(rv.collapsed[r]) : 0;
+        cls = pv_class(0, (rv.flag[r] & 0x10) ? DIR_R : DIR_F, cg);
+    }
+    int tile = mine && a <= e ? ((a - rg.lo) >> 5) + k : 1;
+    const int tile_last = mine && a <= e ? ((e - rg.lo) >> 5) : 0;
+    while (__any_sync(0xffffffffu, tile <= tile_last)) {
+        const bool work = tile <= tile_last;
+        const long long key = work ? (long long)tile * n_classes + cls : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (work && lane == __ffs((int)peers) - 1) atomicAdd(cls_rows + key, __popc(peers));
+        tile += kWalkPieces;
     }
 }
 
@@ -386,12 +426,12 @@ template <bool kFill>
 static cudaError_t launch_walk(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, const FillTargets& ft, cudaStream_t st) {
     const int64_t threads = (int64_t)rv.n_reads * kWalkPieces;
     const unsigned grid = (unsigned)((threads + 255) / 256);
-    if (kFill) {
-        pvert_fill_simple_kernel<<<grid, 256, 0, st>>>(rv, rg, n_classes, ft);
-        const cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    pvert_walk_kernel<kFill><<<grid, 256, 0, st>>>(rv, rg, end_pos, n_classes, cls_rows, ft, kFill ? 1 : 0);
+    const dim3 sgrid((unsigned)((rv.n_reads + 255) / 256), kWalkPieces);
+    if (kFill) pvert_fill_simple_kernel<<<sgrid, 256, 0, st>>>(rv, rg, n_classes, ft);
+    else pvert_count_simple_kernel<<<sgrid, 256, 0, st>>>(rv, rg, n_classes, cls_rows);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    pvert_walk_kernel<kFill><<<grid, 256, 0, st>>>(rv, rg, end_pos, n_classes, cls_rows, ft, 1);
     return cudaGetLastError();
 }
 
