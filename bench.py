@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample-loci", type=int, default=100_000)
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-jobs", type=int, default=3, help="concurrent (BAM x chromosome) jobs of the end-to-end leg: one handle + one host thread each, as Pisces -t N runs them")
     ap.add_argument("--e2e-input", default="packed", choices=["packed", "soa"], help="host form of the reads: one packed byte per base, or bases + qualities")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -406,30 +407,51 @@ def main_ours(a):
     # ---- end to end through the C ABI with HOST buffers: pinned H2D of the step's reads, device staging, call, D2H of the records
     precs = arena = None
     if not a.no_e2e:
-        sm2 = pb.GpuStateManager(cfg, "chr1", ref)
-        caller = pb.GpuAlleleCaller()
+        # One handle + one host thread per job, as the reference runs its (BAM x chromosome) jobs (-t N: JobManager, SURVEY 8b "Threading"): while one job's
+        # reads cross the PCIe link another job's pileup is staged and called, so the link stays busy. Every job processes the same `loci` per step.
+        n_jobs = max(1, a.e2e_jobs)
         e2e_steps = max(2, min(a.steps, a.e2e_steps))
+        sms = [pb.GpuStateManager(cfg, "chr1", ref) for _ in range(n_jobs)]
+        caller = pb.GpuAlleleCaller()
 
-        def e2e_step():
+        def e2e_step(sm2):
             if a.e2e_input == "packed":
                 sm2.AddReadsPacked(e2e_in)
             else:
                 sm2.AddReadsSoA(pinned)
-            recs = caller.Call(sm2, raw=True)
-            return recs
-        precs = e2e_step()
-        arena = sm2.AlleleArena()
+            return caller.Call(sm2, raw=True)
+        for sm2 in sms:   # warm-up (allocations, block cache), and the records the oracle check below compares
+            precs = e2e_step(sm2)
+            arena = sm2.AlleleArena()
+            e2e_step(sm2)
+        counts = [0] * n_jobs
+
+        def job(j):
+            for _ in range(e2e_steps):
+                counts[j] = len(e2e_step(sms[j]))
         barrier()
+        ths = [threading.Thread(target=job, args=(j,)) for j in range(n_jobs)]
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            nrec = len(e2e_step())
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
         barrier()
         edt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(edt, op=dist.ReduceOp.MAX)
-        line["e2e"] = {"value": world * a.loci * e2e_steps / float(edt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 96 * nrec,
-                       "steps": e2e_steps, "ms_per_step": 1e3 * float(edt.item()) / e2e_steps, "input": ("reads, one packed byte per base (pb2_push_reads_packed) + 26 B per read" if a.e2e_input == "packed" else "reads, bases + qualities (pb2_push_reads) + 26 B per read") + ", pinned host memory"}
-        sm2.close()
+        nrec = counts[0]
+        # one job alone (no overlap): the latency of a step
+        t1 = time.perf_counter()
+        for _ in range(2):
+            e2e_step(sms[0])
+        single_ms = 1e3 * (time.perf_counter() - t1) / 2
+        line["e2e"] = {"value": world * n_jobs * a.loci * e2e_steps / float(edt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 96 * nrec,
+                       "steps": e2e_steps, "jobs": n_jobs, "ms_per_step": 1e3 * float(edt.item()) / (e2e_steps * n_jobs), "single_job_ms_per_step": single_ms,
+                       "single_job_value": world * a.loci / (single_ms * 1e-3),
+                       "input": ("reads, one packed byte per base (pb2_push_reads_packed) + 26 B per read" if a.e2e_input == "packed" else "reads, bases + qualities (pb2_push_reads) + 26 B per read") + ", pinned host memory"}
+        for sm2 in sms:
+            sm2.close()
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample, single thread like one Pisces (BAM x chr) job; the same run
     # verifies the records of the timed workload on the sample's positions

@@ -978,13 +978,18 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     CU(h, pool_alloc_t(h, &s.pv_tile_row0, (size_t)s.n_tiles + 1));
     CU(h, cudaMemsetAsync(s.pv_cls_end, 0, sizeof(int32_t) * n_cls, st));
     CU(h, cudaMemsetAsync(d_cursor, 0, sizeof(int32_t) * n_cls, st));
-    CU(h, launch_pvert_count(rv, rg, R.end_pos.p, nc, s.pv_cls_end, st));
+    int32_t* d_complex = nullptr;
+    CU(h, pool_alloc_t(h, &d_complex, (size_t)R.n + 1));
+    CU(h, cudaMemsetAsync(d_complex, 0, sizeof(int32_t), st));
+    CU(h, launch_pvert_count(rv, rg, R.end_pos.p, nc, s.pv_cls_end, d_complex, st));
     CU(h, launch_pvert_layout(s.pv_cls_end, s.n_tiles, nc, tile_rows, st));
     size_t tb = 0;
     CU(h, exclusive_scan_i64(tile_rows, s.pv_tile_row0, s.n_tiles + 1, nullptr, 0, &tb, st));
     CU(h, pool_alloc(h, &temp, std::max<size_t>(tb, 16)));
     CU(h, exclusive_scan_i64(tile_rows, s.pv_tile_row0, s.n_tiles + 1, temp, tb, nullptr, st));
+    int32_t n_complex = 0;
     CU(h, cudaMemcpyAsync(&s.pv_rows, s.pv_tile_row0 + s.n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(&n_complex, d_complex, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     const size_t data_bytes = (size_t)std::max<int64_t>(s.pv_rows, 32) * 32;
     CU(h, pool_alloc(h, (void**)&s.pv_data, data_bytes + 4096));
@@ -999,7 +1004,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     CU(h, pool_alloc_t(h, &d_ref_slot, (size_t)s.n_tiles * 32));
     CU(h, launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, s.ref_base, d_ref_slot, st));
     CU(h, launch_pvert_fill(rv, rg, R.end_pos.p, nc, s.pv_tile_row0, s.pv_cls_end, d_cursor, s.pv_data, s.pv_row_meta, s.exc_entries, s.counters + 3, s.exc_capacity, d_ref_slot,
-                            st));
+                            d_complex, n_complex, st));
     CU(h, launch_pvert_transpose(s.pv_data, s.pv_rows / 32, st));
     pool_free(h, d_ref_slot);
     CU(h, cudaEventRecord(h->ev_stage1, st));
@@ -1009,7 +1014,7 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     h->last_stage_rows = s.pv_rows;
     h->have_stage_events = true;
     const int rc = alloc_segment_outputs(h, s);
-    pool_free(h, d_cursor); pool_free(h, tile_rows); pool_free(h, temp); pool_free(h, d_index); pool_free(h, d_index_ge);
+    pool_free(h, d_cursor); pool_free(h, tile_rows); pool_free(h, temp); pool_free(h, d_index); pool_free(h, d_index_ge); pool_free(h, d_complex);
     if (rc != PB2_OK) return rc;
     h->segs.push_back(std::move(s));
     return PB2_OK;

@@ -271,13 +271,14 @@ __device__ __forceinline__ bool pv_simple_read(const ReadsView& rv, const Region
     const int64_t c0 = rv.cigar_off[r];
     return rv.cigar_off[r + 1] - c0 == 1 && (rv.cigar[c0] & 15u) == 0;
 }
+// complex: the reads that are not simple, listed by pvert_count_simple_kernel (complex[0] = how many, then their indices)
 template <bool kFill>
 __global__ void __launch_bounds__(256) pvert_walk_kernel(ReadsView rv, RegionView rg, const int32_t* __restrict__ end_pos_of, int n_classes, int32_t* __restrict__ cls_rows,
-                                                        FillTargets ft, int skip_simple) {
+                                                        FillTargets ft, const int32_t* __restrict__ complex) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = (int)(t / kWalkPieces), k = (int)(t % kWalkPieces);
-    if (r >= rv.n_reads) return;
-    if (skip_simple && pv_simple_read(rv, rg, r)) return;
+    const int k = (int)(t % kWalkPieces);
+    if (t / kWalkPieces >= complex[0]) return;
+    const int r = complex[1 + t / kWalkPieces];
     const int start_pos = rv.pos0[r] + 1, end_pos = end_pos_of[r];
     const int a = max(start_pos, rg.lo), e = min(end_pos, rg.hi);
     if (a > e) return;
@@ -399,10 +400,19 @@ __global__ void __launch_bounds__(256) pvert_fill_simple_kernel(ReadsView rv, Re
 }
 
 // the rows simple reads will take, same mapping and the same one-atomic-per-group trick
-__global__ void __launch_bounds__(256) pvert_count_simple_kernel(ReadsView rv, RegionView rg, int n_classes, int32_t* __restrict__ cls_rows) {
+__global__ void __launch_bounds__(256) pvert_count_simple_kernel(ReadsView rv, RegionView rg, int n_classes, int32_t* __restrict__ cls_rows, int32_t* __restrict__ complex) {
     const int r = blockIdx.x * 256 + threadIdx.x, k = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const bool mine = r < rv.n_reads && pv_simple_read(rv, rg, r);
+    if (k == 0) {   // the other reads go to the list the general walker works from (one atomic per warp)
+        const unsigned cx = __ballot_sync(0xffffffffu, r < rv.n_reads && !mine);
+        if (cx) {
+            int base = 0;
+            if (lane == __ffs((int)cx) - 1) base = atomicAdd(complex, __popc(cx));
+            base = __shfl_sync(0xffffffffu, base, __ffs((int)cx) - 1);
+            if ((cx >> lane) & 1u) complex[1 + base + __popc(cx & ((1u << lane) - 1u))] = r;
+        }
+    }
     int a = 1, e = 0, cls = 0;
     if (mine) {
         const int len = (int)(rv.cigar[rv.cigar_off[r]] >> 4);
@@ -422,16 +432,18 @@ __global__ void __launch_bounds__(256) pvert_count_simple_kernel(ReadsView rv, R
     }
 }
 
+// complex: [1 + n_reads] ints, complex[0] zeroed by the caller before the count pass; n_complex: how many the count pass listed (fill pass), or -1: not
+// known on the host yet (count pass: the kernel is launched for every read and the surplus threads leave at once)
 template <bool kFill>
-static cudaError_t launch_walk(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, const FillTargets& ft, cudaStream_t st) {
-    const int64_t threads = (int64_t)rv.n_reads * kWalkPieces;
-    const unsigned grid = (unsigned)((threads + 255) / 256);
+static cudaError_t launch_walk(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, const FillTargets& ft, int32_t* complex,
+                               int64_t n_complex, cudaStream_t st) {
     const dim3 sgrid((unsigned)((rv.n_reads + 255) / 256), kWalkPieces);
     if (kFill) pvert_fill_simple_kernel<<<sgrid, 256, 0, st>>>(rv, rg, n_classes, ft);
-    else pvert_count_simple_kernel<<<sgrid, 256, 0, st>>>(rv, rg, n_classes, cls_rows);
+    else pvert_count_simple_kernel<<<sgrid, 256, 0, st>>>(rv, rg, n_classes, cls_rows, complex);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    pvert_walk_kernel<kFill><<<grid, 256, 0, st>>>(rv, rg, end_pos, n_classes, cls_rows, ft, 1);
+    const int64_t threads = (n_complex < 0 ? (int64_t)rv.n_reads : n_complex) * kWalkPieces;
+    if (threads > 0) pvert_walk_kernel<kFill><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rv, rg, end_pos, n_classes, cls_rows, ft, complex);
     return cudaGetLastError();
 }
 
@@ -539,20 +551,21 @@ pvert_gather_kernel(PvertPileup in, const int32_t* __restrict__ req_locus, int32
 }
 }  // namespace
 
-cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, cudaStream_t st) {
+cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, int32_t* complex, cudaStream_t st) {
     if (rv.n_reads == 0) return cudaSuccess;
     FillTargets ft{};
-    return launch_walk<false>(rv, rg, end_pos, n_classes, cls_rows, ft, st);
+    return launch_walk<false>(rv, rg, end_pos, n_classes, cls_rows, ft, complex, -1, st);
 }
 cudaError_t launch_pvert_layout(int32_t* cls_rows, int32_t n_tiles, int n_classes, int64_t* tile_rows, cudaStream_t st) {
     pvert_layout_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(cls_rows, n_tiles, n_classes, tile_rows);
     return cudaGetLastError();
 }
 cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
-                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, const uint8_t* ref_slot, cudaStream_t st) {
+                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, const uint8_t* ref_slot, int32_t* complex,
+                              int64_t n_complex, cudaStream_t st) {
     if (rv.n_reads == 0) return cudaSuccess;
     FillTargets ft{tile_row0, cls_end, cursor, data, row_meta, exc_entries, exc_count, exc_capacity, reinterpret_cast<const uint32_t*>(ref_slot)};
-    return launch_walk<true>(rv, rg, end_pos, n_classes, nullptr, ft, st);
+    return launch_walk<true>(rv, rg, end_pos, n_classes, nullptr, ft, complex, n_complex, st);
 }
 cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st) {
     if (n_blocks <= 0) return cudaSuccess;

@@ -66,10 +66,12 @@ __host__ __device__ inline unsigned long long pv_transpose8x8(unsigned long long
 struct ReadsView;
 struct RegionView;
 // reads -> rows: count rows per (tile, class); layout (pad, prefix); fill (rows + row_meta + flagged-entry side list); bit transposition in place
-cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, cudaStream_t st);
+// complex: [1 + n_reads] ints, complex[0] = 0 before the count pass, which lists there the reads that need the general walker (fill: n_complex of them)
+cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, int32_t* complex, cudaStream_t st);
 cudaError_t launch_pvert_layout(int32_t* cls_rows /* in: rows per class; out: inclusive padded prefix */, int32_t n_tiles, int n_classes, int64_t* tile_rows, cudaStream_t st);
 cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
-                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, const uint8_t* ref_slot, cudaStream_t st);
+                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, const uint8_t* ref_slot, int32_t* complex,
+                              int64_t n_complex, cudaStream_t st);
 cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st);
 // ref_base[n_loci] ASCII; ref_slot (optional, [n_loci rounded up to 32]): allele2 << 6 of the reference base, 1 where it is not A/C/G/T
 cudaError_t launch_pvert_ref_bases(const uint8_t* chr, int64_t chr_len, const int32_t* positions, int32_t first_position, int64_t n_loci, uint8_t* ref_base, uint8_t* ref_slot,
