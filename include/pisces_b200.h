@@ -325,6 +325,23 @@ int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* filter, int32_t 
 int pb2_bam_batch_amplicons(pb2_bam_reader* r, const int32_t** amplicon_id, int32_t* n_reads);
 int pb2_bam_amplicon_names(pb2_bam_reader* r, int32_t* n, const char* const** names);
 
+/* Interval sharding of one chromosome across handles / GPUs (the reference shards by chromosome and concatenates in genome order:
+ * src/lib/Pisces.Processing/Logic/BaseGenomeProcessor.cs:60-72, src/exe/Pisces/Logic/Processing/GenomeProcessor.cs:156-186). pb2_shard_plan cuts the positions
+ * [first_position, last_position] into n_shards runs of 1000-bp blocks, balanced by the position-sorted reads' starts (pos0, may be NULL: balanced by
+ * positions). Shard i EMITS the positions [own_lo, own_hi] and must SEE the reads [read_first, read_end) (those that can touch [stage_lo, stage_hi]: its own
+ * positions plus a halo of two blocks and max_read_span on either side, which holds everything that reaches across a cut: far end points of spanning
+ * alleles, MNV leftovers moving into the next block (AlleleCaller.cs:91-92), collapsable candidates pulled from the following block
+ * (RegionStateManager.cs:441-457), gapped-MNV reference counts (AlleleCaller.cs:94)). A shard's handle gets pb2_set_owned_range(own_lo, own_hi) and its
+ * reads; the records of the shards, concatenated in shard order, are the records of the unsharded chromosome. */
+typedef struct pb2_shard {
+    int32_t own_lo, own_hi;
+    int32_t stage_lo, stage_hi;
+    int64_t read_first, read_end;
+} pb2_shard;
+int pb2_shard_plan(const int32_t* pos0, int64_t n_reads, int32_t first_position, int32_t last_position, int32_t max_read_span, int32_t n_shards, pb2_shard* out);
+/* Only positions in [own_lo, own_hi] are emitted by pb2_flush / pb2_call_resident from now on (0, 0: everything). */
+int pb2_set_owned_range(pb2_handle* h, int32_t own_lo, int32_t own_hi);
+
 /* IAlleleCaller.TotalNumCollapsed (src/exe/Pisces/Interfaces/IAlleleCaller.cs:11): candidates merged by the collapser since pb2_create. */
 int pb2_totals(pb2_handle* h, int64_t* total_collapsed);
 

@@ -41,6 +41,10 @@ class PackedReadBatch(C.Structure):
                 ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p)]
 
 
+class Shard(C.Structure):
+    _fields_ = [("own_lo", C.c_int32), ("own_hi", C.c_int32), ("stage_lo", C.c_int32), ("stage_hi", C.c_int32), ("read_first", C.c_int64), ("read_end", C.c_int64)]
+
+
 class Candidate(C.Structure):
     _fields_ = [("position", C.c_int32), ("type", C.c_uint8), ("open_flags", C.c_uint8), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16),
                 ("reserved", C.c_uint16), ("allele_offset", C.c_uint32), ("support", C.c_int32 * 3), ("well_anchored", C.c_int32 * 3),
@@ -74,7 +78,7 @@ RECORD_EXT_DTYPE = [("collapsed_mut", "<i4", (8,)), ("collapsed_total", "<i4", (
 
 EXPORTS = ["pb2_default_config", "pb2_create", "pb2_destroy", "pb2_last_error", "pb2_device_count", "pb2_set_reference", "pb2_set_intervals",
            "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_reads_packed", "pb2_pack_reads", "pb2_stage_reads", "pb2_push_candidates", "pb2_set_forced_alleles", "pb2_allele_arena", "pb2_call_resident", "pb2_resident_results", "pb2_flush", "pb2_flush_resident", "pb2_flush_ext",
-           "pb2_get_counts", "pb2_reset", "pb2_stats", "pb2_stage_stats", "pb2_stream", "pb2_totals", "pb2_vcf_format",
+           "pb2_get_counts", "pb2_reset", "pb2_shard_plan", "pb2_set_owned_range", "pb2_stats", "pb2_stage_stats", "pb2_stream", "pb2_totals", "pb2_vcf_format",
            "pb2_bam_open", "pb2_bam_close", "pb2_bam_last_error", "pb2_bam_header", "pb2_bam_next_batch", "pb2_bam_batch_amplicons",
            "pb2_bam_amplicon_names"]
 
@@ -117,6 +121,8 @@ def load():
     L.pb2_get_counts.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p]
     L.pb2_reset.argtypes = [H]
     L.pb2_stats.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.pb2_shard_plan.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Shard)]
+    L.pb2_set_owned_range.argtypes = [H, C.c_int32, C.c_int32]
     L.pb2_stage_stats.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.pb2_vcf_format.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]
     L.pb2_bam_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]

@@ -127,6 +127,7 @@ static void derive_config(pb2_handle* h) {
     d.tune_prefetch = c.reserved[1];
     d.tune_ctas_per_sm = c.reserved[0] == 3 ? 3 : 4;   // tuning knob (bench.py --tune-ctas)
     d.snv_from_counts = c.call_mnvs ? 0 : 1;   // CallMNVs: SNV candidates come from the finder's state machine (explicit), not from the counts
+    d.own_lo = h->own_lo; d.own_hi = h->own_hi;
     d.vq_error_rate = std::pow(10.0, -1 * (double)d.noise_level / 10.0);                      // QtoP: double division (MathOperations.cs:7-10)
     d.sb_noise = std::pow(10.0, (double)((float)(-1 * d.noise_level) / 10.0f));               // float exponent (StrandBiasCalculator.cs:32)
 }
@@ -810,6 +811,50 @@ extern "C" int64_t pb2_pack_reads(const uint8_t* bases, const uint8_t* quals, in
         }
     }
     return n_exc;
+}
+
+// ------------------------------------------------------------------------------------------------ interval sharding
+// BaseGenomeProcessor shards by chromosome and concatenates in genome order (BaseGenomeProcessor.cs:60-72, GenomeProcessor.cs:156-186); within a chromosome the
+// loci are independent once the counts are complete, so a chromosome is cut into interval shards at 1000-bp block boundaries (the batches of
+// RegionStateManager are block-aligned). A shard stages a HALO on either side - two blocks plus the longest read span: what reaches across a cut is an
+// allele's far end point (CoverageCalculator.cs:19-47), MNV leftovers that move into the next block (AlleleCaller.cs:91-92), the collapsable candidates a
+// batch pulls from the following block (RegionStateManager.cs:441-457) and the gapped-MNV reference take-away (AlleleCaller.cs:94), all within one read
+// span of the cut - and emits only the positions it owns.
+extern "C" int pb2_shard_plan(const int32_t* pos0, int64_t n_reads, int32_t first_position, int32_t last_position, int32_t max_read_span, int32_t n_shards, pb2_shard* out) {
+    if (n_shards < 1 || !out || last_position < first_position || first_position < 1 || max_read_span < 0 || n_reads < 0 || (n_reads > 0 && !pos0)) return PB2_ERR_ARG;
+    const int32_t halo = 2000 + (max_read_span + 999) / 1000 * 1000;
+    std::vector<int32_t> cut((size_t)n_shards + 1);   // shard i owns (cut[i], cut[i + 1]]
+    cut[0] = first_position - 1;
+    cut[(size_t)n_shards] = last_position;
+    for (int32_t i = 1; i < n_shards; i++) {
+        int64_t p;
+        if (n_reads > 0) p = (int64_t)pos0[(size_t)(n_reads * i / n_shards)] + 1;                                      // balanced by reads (pos0 is sorted)
+        else p = first_position - 1 + ((int64_t)last_position - first_position + 1) * i / n_shards;                      // balanced by positions
+        p = (p + 500) / 1000 * 1000;                                                                                     // to a block boundary
+        p = std::max<int64_t>(p, cut[(size_t)i - 1]);
+        cut[(size_t)i] = (int32_t)std::min<int64_t>(p, last_position);
+    }
+    for (int32_t i = 0; i < n_shards; i++) {
+        pb2_shard& s = out[i];
+        s.own_lo = cut[(size_t)i] + 1; s.own_hi = cut[(size_t)i + 1];
+        s.stage_lo = std::max(1, s.own_lo - halo);
+        s.stage_hi = (int32_t)std::min<int64_t>((int64_t)s.own_hi + halo, INT32_MAX);
+        s.read_first = 0; s.read_end = n_reads;
+        if (n_reads > 0) {   // the position-sorted reads that can touch [stage_lo, stage_hi]
+            s.read_first = std::lower_bound(pos0, pos0 + n_reads, s.stage_lo - 1 - max_read_span) - pos0;
+            s.read_end = std::upper_bound(pos0, pos0 + n_reads, s.stage_hi - 1) - pos0;
+        }
+        if (s.own_hi < s.own_lo) { s.read_first = s.read_end = 0; }
+    }
+    return PB2_OK;
+}
+extern "C" int pb2_set_owned_range(pb2_handle* h, int32_t own_lo, int32_t own_hi) {
+    if (!h || (own_hi != 0 && (own_lo < 1 || own_hi < own_lo))) return fail(h, PB2_ERR_ARG, "pb2_set_owned_range: bad range");
+    h->own_lo = own_hi ? own_lo : 0; h->own_hi = own_hi;
+    derive_config(h);
+    explicit_release_resident(h);
+    release_resident_graph(h);
+    return PB2_OK;
 }
 
 extern "C" int pb2_totals(pb2_handle* h, int64_t* total_collapsed) {
@@ -1679,7 +1724,10 @@ static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_reco
     pb2_call_record_ext zero_ext;
     memset(&zero_ext, 0, sizeof(zero_ext));
     h->h_out_ext.clear();
-    auto emit = [&](const OutRec& o) { h->h_out.push_back(o.r); h->h_out_ext.push_back(o.e); };
+    auto emit = [&](const OutRec& o) {
+        if (h->dcfg.own_hi > 0 && (o.r.position < h->dcfg.own_lo || o.r.position > h->dcfg.own_hi)) return;   // an interval shard emits the positions it owns
+        h->h_out.push_back(o.r); h->h_out_ext.push_back(o.e);
+    };
     std::vector<uint8_t> explicit_used(explicit_called.size(), 0);
     const bool want_collapsed = h->cfg.expect_collapsed != 0;
     for (auto& s : h->segs) {

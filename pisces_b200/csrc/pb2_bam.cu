@@ -57,11 +57,14 @@ bool next_block(pb2_bam_reader* r) {
         q += 4 + slen;
     }
     if (bsize < 0) { r->error = "BGZF block without a BC field"; r->eof = true; return false; }
+    // BSIZE + 1 = the whole block: 12 header bytes, XLEN extra bytes, the deflate stream, crc32 + isize (8 bytes)
+    if ((size_t)bsize + 1 < 12 + (size_t)xlen + 8) { r->error = "malformed BGZF block (BSIZE smaller than its header)"; r->eof = true; return false; }
     const size_t clen = (size_t)bsize + 1 - 12 - (size_t)xlen;   // compressed data + crc32 + isize
     std::vector<uint8_t> comp(clen);
-    if (clen < 8 || fread(comp.data(), 1, clen, r->f) != clen) { r->error = "truncated BGZF block"; r->eof = true; return false; }
+    if (fread(comp.data(), 1, clen, r->f) != clen) { r->error = "truncated BGZF block"; r->eof = true; return false; }
     const uint32_t isize = comp[clen - 4] | (comp[clen - 3] << 8) | (comp[clen - 2] << 16) | ((uint32_t)comp[clen - 1] << 24);
     if (isize == 0) return true;   // the empty end-of-file block
+    if (isize > 65536) { r->error = "malformed BGZF block (ISIZE above 64 KiB)"; r->eof = true; return false; }
     if (r->cur > 0 && r->cur == r->buf.size()) { r->buf.clear(); r->cur = 0; }
     const size_t old = r->buf.size();
     r->buf.resize(old + isize);
@@ -88,7 +91,7 @@ uint32_t rd_u32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 std::string lower(std::string s) { for (auto& c : s) c = (char)tolower((unsigned char)c); return s; }
 
 struct Tags { bool has_xv = false, has_xw = false; int64_t xv = 0, xw = 0; bool has_xr = false, has_xd = false; std::string xr, xd; bool any = false;
-              bool has_xn = false, bad_xn = false; std::string xn; };
+              bool has_xn = false, bad_xn = false; std::string xn; bool malformed = false; };
 Tags parse_tags(const uint8_t* p, size_t n) {
     Tags t;
     size_t i = 0;
@@ -100,6 +103,22 @@ Tags parse_tags(const uint8_t* p, size_t n) {
         bool is_int = false;
         std::string sv;
         bool is_str = false;
+        // every value is read inside the record: a tag that runs past its end makes the record malformed
+        size_t fixed = 0;
+        switch (ty) {
+            case 'c': case 'C': case 'A': fixed = 1; break;
+            case 's': case 'S': fixed = 2; break;
+            case 'i': case 'I': case 'f': fixed = 4; break;
+            case 'B': fixed = 5; break;
+            default: break;
+        }
+        if (i + fixed > n) { t.malformed = true; return t; }
+        if (ty == 'B') {
+            const char st = (char)p[i];
+            const int32_t cnt = rd_i32(p + i + 1);
+            const size_t sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+            if (cnt < 0 || (size_t)cnt > (n - i - 5) / sz) { t.malformed = true; return t; }
+        }
         if (a == 'X' && b == 'N') {   // Read.GetAmpliconNameIfExists -> TagUtils.GetStringTag (BamCommon.cs:1182-1216): Z / H strings, A / C (upper-cased type)
             t.has_xn = true;          // one character, anything else throws
             const char up = (char)toupper((unsigned char)ty);
@@ -115,7 +134,12 @@ Tags parse_tags(const uint8_t* p, size_t n) {
             case 'I': iv = rd_u32(p + i); i += 4; is_int = true; break;
             case 'f': i += 4; break;
             case 'A': i += 1; break;
-            case 'Z': case 'H': { size_t e = i; while (e < n && p[e] != 0) e++; sv.assign((const char*)p + i, e - i); i = e + 1; is_str = true; break; }
+            case 'Z': case 'H': {
+                size_t e = i;
+                while (e < n && p[e] != 0) e++;
+                if (e >= n) { t.malformed = true; return t; }   // no terminator inside the record
+                sv.assign((const char*)p + i, e - i); i = e + 1; is_str = true; break;
+            }
             case 'B': {
                 const char st = (char)p[i];
                 const int32_t cnt = rd_i32(p + i + 1);
@@ -135,7 +159,12 @@ Tags parse_tags(const uint8_t* p, size_t n) {
 }
 }  // namespace
 
+static int bam_open_impl(const char* path, pb2_bam_reader** out);
 extern "C" int pb2_bam_open(const char* path, pb2_bam_reader** out) {
+    try { return bam_open_impl(path, out); }
+    catch (const std::exception&) { if (out) *out = nullptr; return PB2_ERR_NOMEM; }
+}
+static int bam_open_impl(const char* path, pb2_bam_reader** out) {
     if (!path || !out) return PB2_ERR_ARG;
     *out = nullptr;
     pb2_bam_reader* r = new pb2_bam_reader();
@@ -185,14 +214,21 @@ extern "C" int pb2_bam_header(pb2_bam_reader* r, int32_t* n_refs, const char* co
     return PB2_OK;
 }
 
+static int bam_next_batch_impl(pb2_bam_reader* r, const pb2_bam_filter* flt, int32_t max_reads, pb2_read_batch* batch, int32_t* ref_id_out, int64_t* n_skipped);
+// nothing throws across the C boundary: allocation failures and the like become error codes
 extern "C" int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* flt, int32_t max_reads, pb2_read_batch* batch, int32_t* ref_id_out, int64_t* n_skipped) {
+    try { return bam_next_batch_impl(r, flt, max_reads, batch, ref_id_out, n_skipped); }
+    catch (const std::bad_alloc&) { if (r) r->error = "out of memory while decoding the BAM file"; return PB2_ERR_NOMEM; }
+    catch (const std::exception& e) { if (r) r->error = std::string("malformed BAM file: ") + e.what(); return PB2_ERR_ARG; }
+}
+static int bam_next_batch_impl(pb2_bam_reader* r, const pb2_bam_filter* flt, int32_t max_reads, pb2_read_batch* batch, int32_t* ref_id_out, int64_t* n_skipped) {
     if (!r || !batch || max_reads <= 0) return bfail(r, "pb2_bam_next_batch: bad argument");
     pb2_bam_filter f;
     f.min_map_quality = 1; f.remove_duplicates = 1; f.only_proper_pairs = 0;   // BamFilterParameters.cs:7-11
     if (flt) f = *flt;
     r->pos0.clear(); r->flag.clear(); r->cigar.clear(); r->bases.clear(); r->quals.clear(); r->base_dirs.clear(); r->collapsed.clear(); r->amplicon_id.clear();
     r->cigar_off.assign(1, 0); r->seq_off.assign(1, 0);
-    bool any_dirs = false, any_coll = false;
+    bool any_dirs = false, any_coll = false;   // (kept for diagnostics)
     int64_t skipped = 0;
     int32_t batch_ref = -2;
     static const char kSeq[] = "=ACMGRSVTWYHKDBN";
@@ -222,6 +258,7 @@ extern "C" int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* flt, 
         if (batch_ref == -2) batch_ref = ref_id;
         else if (ref_id != batch_ref) { r->pending.swap(rec); r->have_pending = true; break; }   // the next chromosome starts: its reads go to the next batch
         const Tags t = parse_tags(p + o_tags, rec.size() - o_tags);
+        if (t.malformed) return bfail(r, "malformed BAM record (a tag runs past the end of the record)");
         if (t.bad_xn) return bfail(r, "Found an unexpected string BAM tag data type while looking for a tag (XN)");
         int32_t amp = -1;
         if (t.has_xn) {
@@ -244,10 +281,16 @@ extern "C" int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* flt, 
         r->base_dirs.resize(d0 + (size_t)l_seq, (uint8_t)(reverse ? 1 : 0));
         if (t.has_xd && !t.xd.empty()) {
             std::vector<uint8_t> expanded;
+            size_t cigar_units = 0;   // the direction string is walked along the expanded CIGAR: runs beyond its length are never looked at
+            for (uint32_t k = 0; k < n_cig; k++) cigar_units += rd_u32(p + o_cig + 4 * k) >> 4;
             int64_t num = 0;
             for (char ch : t.xd) {
-                if (ch >= '0' && ch <= '9') num = num * 10 + (ch - '0');
-                else { const uint8_t dv = ch == 'F' ? 0 : ch == 'R' ? 1 : 2; expanded.insert(expanded.end(), (size_t)num, dv); num = 0; }
+                if (ch >= '0' && ch <= '9') num = std::min<int64_t>(num * 10 + (ch - '0'), (int64_t)1 << 40);
+                else {
+                    const uint8_t dv = ch == 'F' ? 0 : ch == 'R' ? 1 : 2;
+                    expanded.insert(expanded.end(), (size_t)std::min<int64_t>(num, (int64_t)(cigar_units - std::min(cigar_units, expanded.size()))), dv);
+                    num = 0;
+                }
             }
             size_t ci = 0, si = 0;
             for (uint32_t k = 0; k < n_cig; k++) {
@@ -276,8 +319,11 @@ extern "C" int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* flt, 
     batch->n_reads = (int32_t)r->pos0.size();
     batch->pos0 = r->pos0.data(); batch->flag = r->flag.data(); batch->cigar_off = r->cigar_off.data(); batch->cigar = r->cigar.data();
     batch->seq_off = r->seq_off.data(); batch->bases = r->bases.data(); batch->quals = r->quals.data();
-    batch->base_dirs = any_dirs ? r->base_dirs.data() : nullptr;
-    batch->collapsed = any_coll ? r->collapsed.data() : nullptr;
+    // always handed out (both hold the values the flags imply where a read carries no XD / XV / XW tag): a stitched or collapsed BAM streamed in small
+    // batches mixes tagged and untagged reads, and a batch must not change shape with its content
+    (void)any_dirs; (void)any_coll;
+    batch->base_dirs = r->base_dirs.data();
+    batch->collapsed = r->collapsed.data();
     if (ref_id_out) *ref_id_out = batch_ref == -2 ? -1 : batch_ref;
     if (n_skipped) *n_skipped = skipped;
     return PB2_OK;

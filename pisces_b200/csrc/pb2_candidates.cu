@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(32 * kScoreWarps) score_candidates_kernel(Cand
 
     if (a.out_dense != nullptr) a.out_dense[i] = r;
     if (a.out_callable != nullptr) a.out_callable[i] = (callable ? 1 : 0) | (report ? 2 : 0) | (forced_report ? 4 : 0);
-    if (a.var_records != nullptr && report) {
+    if (a.var_records != nullptr && report && (cfg.own_hi <= 0 || (c.position >= cfg.own_lo && c.position <= cfg.own_hi))) {
         const unsigned long long slot = atomicAdd(a.var_count, 1ull);
         if ((int64_t)slot < a.var_capacity) a.var_records[slot] = r;
         if (a.ref_valid != nullptr && c.locus >= 0 && !is_ref) a.ref_valid[c.locus] = 0;

@@ -220,6 +220,7 @@ struct pb2_handle {
     bool have_intervals = false;
     std::vector<Segment> segs;
     DeviceReads reads;
+    int32_t own_lo = 0, own_hi = 0;   // pb2_set_owned_range (0, 0: everything)
     int32_t cleared_through = 0;   // positions <= this were called by an earlier pb2_flush(up_to >= 0)
     int* d_tile_counter = nullptr;
     std::vector<pb2_call_record> h_out;

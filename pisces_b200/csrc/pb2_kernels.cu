@@ -389,6 +389,10 @@ constexpr int kCtaPending = 64;   // per-CTA queue of the vertical-counter kerne
 __device__ __forceinline__ void finish_locus(const int (&cnt)[kNumAlleles][kNumDirs], double qsum, int any, int64_t locus, int ref_allele, const TilePileup& in,
                                              const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, PendingLocus* cta_queue = nullptr,
                                              int* cta_count = nullptr) {
+    if (cfg.own_hi > 0) {   // an interval shard scores the loci it owns; its halo is staged for the alleles that reach into it, never emitted
+        const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+        if (position < cfg.own_lo || position > cfg.own_hi) { if (out.ref_records != nullptr) out.ref_valid[locus] = 0; return; }
+    }
     const int gapped_word = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
     const int gapped = gapped_word & (kSuppressCountSnvs - 1);
     unsigned cand_mask = 0;

@@ -42,6 +42,7 @@ struct DeviceConfig {
     int ploidy;             // PloidyModel of THIS chromosome (GenotypeCreator.GetPloidyForThisChr): 0 Somatic, 1 DiploidByThresholding, 3 Haploid
     float diploid_minor_vf, diploid_major_vf, diploid_sum_vf;   // DiploidSNVThresholdingParameters
     double sb_min_vf;       // (double)_config.MinFrequency: minDetectableSNP of the Diploid strand-bias model (StrandBiasCalculator.cs:137-148)
+    int own_lo, own_hi;     // interval shard: only positions in [own_lo, own_hi] are emitted (pb2_set_owned_range); own_hi = 0: everything
     double vq_error_rate;   // MathOperations.QtoP(noise_level) (VariantQualityCalculator.cs:31)
     double sb_noise;        // Math.Pow(10, -1*noise_level/10f) (StrandBiasCalculator.cs:32)
 };

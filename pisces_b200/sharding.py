@@ -16,6 +16,31 @@ BLOCK = 1000  # GlobalConstants.RegionSize
 RECORD_BYTES = 96
 
 
+def shard_plan(pos0, first_position, last_position, max_read_span, n_shards):
+    """pb2_shard_plan (the library owns the plan, a .NET host calls the same entry point): block-aligned cuts balanced by the position-sorted reads' starts
+    (pos0 may be None: balanced by positions), halo of two blocks + max_read_span. Returns a list of dicts own_lo, own_hi, stage_lo, stage_hi, read_first,
+    read_end."""
+    import ctypes as C
+    L = _native.load()
+    out = (_native.Shard * n_shards)()
+    p0 = None if pos0 is None else np.ascontiguousarray(pos0, dtype=np.int32)
+    rc = L.pb2_shard_plan(None if p0 is None else p0.ctypes.data, 0 if p0 is None else len(p0), int(first_position), int(last_position), int(max_read_span), int(n_shards), out)
+    if rc != 0:
+        raise ValueError(f"pb2_shard_plan: bad argument ({rc})")
+    return [dict(own_lo=s.own_lo, own_hi=s.own_hi, stage_lo=s.stage_lo, stage_hi=s.stage_hi, read_first=s.read_first, read_end=s.read_end) for s in out]
+
+
+def shard_reads(d, shard):
+    """The reads of one shard (views of the struct of arrays `d`, offsets left absolute: pb2_push_reads accepts windows of larger arrays)."""
+    a, b = int(shard["read_first"]), int(shard["read_end"])
+    out = dict(pos0=d["pos0"][a:b], flag=d["flag"][a:b], cigar_off=d["cigar_off"][a:b + 1], cigar=d["cigar"], seq_off=d["seq_off"][a:b + 1], bases=d["bases"], quals=d["quals"])
+    if d.get("collapsed") is not None:
+        out["collapsed"] = d["collapsed"][a:b]
+    if d.get("base_dirs") is not None:
+        out["base_dirs"] = d["base_dirs"]
+    return out
+
+
 def shard_loci(weights, world_size, block=BLOCK, first_position=1):
     """Cut loci [0, n) into world_size contiguous shards balanced by `weights` (entries per locus), cutting only where a new 1000-bp block of
     reference positions starts (so that a shard owns whole RegionState blocks). Returns [(lo, hi)] with hi exclusive; shards may be empty."""

@@ -4,7 +4,9 @@ import ctypes as C
 import os
 
 import numpy as np
+import pytest
 
+from pisces_b200 import _native as N
 from tests import bamio
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -44,8 +46,10 @@ def test_phix_bam_matches_python_decoder():
         assert sum(b["skipped"] for b in batches) == len(recs) - len(kept) and sum(len(b["pos0"]) for b in batches) == len(kept)
         i = 0
         for b in batches:
-            assert b["dirs"] is None and b["coll"] is None
+            # always handed out; without XD / XV / XW tags they hold what the flags imply
+            assert b["dirs"] is not None and b["coll"] is not None and not (b["coll"] & 1).any()
             for k in range(len(b["pos0"])):
+                assert set(b["dirs"][b["soff"][k]:b["soff"][k + 1]].tolist()) <= {1 if int(b["flag"][k]) & 0x10 else 0}
                 r = kept[i]
                 assert (int(b["pos0"][k]), int(b["flag"][k])) == (r["pos0"], r["flag"])
                 assert list(b["cigar"][b["coff"][k]:b["coff"][k + 1]]) == r["cigar"]
@@ -111,3 +115,56 @@ def test_amplicon_names_from_the_xn_tag():
         assert set(st.batch_amplicons()) == {-1}
     assert st.amplicon_names() == []
     st.close()
+
+
+def _bgzf_block(payload, bsize_override=None, isize_override=None):
+    import struct
+    import zlib
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(payload) + co.flush()
+    bsize = len(comp) + 25 if bsize_override is None else bsize_override
+    isize = len(payload) if isize_override is None else isize_override
+    return (b"\x1f\x8b\x08\x04" + b"\0" * 6 + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize) + comp +
+            struct.pack("<II", zlib.crc32(payload) & 0xffffffff, isize))
+
+
+def _bam_bytes(tag_bytes=b"", l_seq=4):
+    import struct
+    header = b"BAM\1" + struct.pack("<i", 0) + struct.pack("<i", 1) + struct.pack("<i", 5) + b"chr1\0" + struct.pack("<i", 1000)
+    name = b"r\0"
+    rec = struct.pack("<iiIIiiii", 0, 10, (len(name)) | (60 << 8) | (4680 << 16), 1 | (0 << 16), l_seq, -1, -1, 0) + name + struct.pack("<I", (l_seq << 4) | 0) + \
+        bytes([0x12] * ((l_seq + 1) // 2)) + bytes([30] * l_seq) + tag_bytes
+    return header + struct.pack("<i", len(rec)) + rec
+
+
+@pytest.mark.parametrize("case", ["bsize_underflow", "isize_huge", "tag_past_end", "string_unterminated", "b_array_count", "xd_huge_run"])
+def test_malformed_bam_is_rejected_not_crashed(case, tmp_path):
+    """block sizes, tag values and XD run lengths are validated against the record before anything is allocated or read."""
+    import struct
+    L = N.load()
+    good = _bam_bytes()
+    if case == "bsize_underflow":
+        data = _bgzf_block(good, bsize_override=5)
+    elif case == "isize_huge":
+        data = _bgzf_block(good, isize_override=1 << 30)
+    elif case == "tag_past_end":
+        data = _bgzf_block(_bam_bytes(b"XVi\x01\x00"))            # an int32 with two of its four bytes
+    elif case == "string_unterminated":
+        data = _bgzf_block(_bam_bytes(b"XDZ4F"))                    # no NUL
+    elif case == "b_array_count":
+        data = _bgzf_block(_bam_bytes(b"XBBi" + struct.pack("<i", 1 << 28)))
+    else:
+        data = _bgzf_block(_bam_bytes(b"XDZ4000000000F\0"))         # a direction run of four billion: clamped to the CIGAR length, read kept
+    path = tmp_path / "bad.bam"
+    path.write_bytes(data + _bgzf_block(b""))
+    rd = C.c_void_p()
+    rc = L.pb2_bam_open(str(path).encode(), C.byref(rd))
+    if rc != 0:
+        return   # rejected at open
+    b, ref_id, skipped = N.ReadBatch(), C.c_int32(), C.c_int64()
+    rc = L.pb2_bam_next_batch(rd, None, 100, C.byref(b), C.byref(ref_id), C.byref(skipped))
+    if case == "xd_huge_run":
+        assert rc == 0 and b.n_reads == 1
+    else:
+        assert rc != 0 and L.pb2_bam_last_error(rd)
+    L.pb2_bam_close(rd)

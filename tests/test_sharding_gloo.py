@@ -27,6 +27,28 @@ def test_shard_loci_balances_and_cuts_on_blocks():
     assert sharding.shard_loci([], 2) == [(0, 0), (0, 0)]
 
 
+def test_shard_plan_cuts_on_blocks_with_halo():
+    """pb2_shard_plan (host logic, no GPU): block-aligned cuts balanced by read starts, halo = two blocks + the read span, read windows that hold every
+    read able to touch the staged range."""
+    rng = np.random.default_rng(1)
+    pos0 = np.sort(np.concatenate([rng.integers(0, 40_000, 30_000), rng.integers(10_000, 14_000, 30_000)])).astype(np.int32)   # a deep stretch
+    span = 150
+    for n in (1, 2, 4, 8):
+        plan = sharding.shard_plan(pos0, 1, 40_150, span, n)
+        assert plan[0]["own_lo"] == 1 and plan[-1]["own_hi"] == 40_150
+        assert all(a["own_hi"] + 1 == b["own_lo"] for a, b in zip(plan, plan[1:]))
+        assert all(s["own_hi"] % 1000 == 0 for s in plan[:-1])                         # cuts at block boundaries
+        for s in plan:
+            assert s["stage_lo"] == max(1, s["own_lo"] - 3000) and s["stage_hi"] == s["own_hi"] + 3000
+            touching = np.nonzero((pos0 + 1 + span >= s["stage_lo"]) & (pos0 + 1 <= s["stage_hi"]))[0]
+            if len(touching):
+                assert s["read_first"] <= touching[0] and s["read_end"] >= touching[-1] + 1
+        loads = [int(((pos0 + 1 >= s["own_lo"]) & (pos0 + 1 <= s["own_hi"])).sum()) for s in plan]
+        assert max(loads) <= len(pos0) / n + 0.2 * len(pos0)                          # balanced by reads, up to one block of the deep stretch
+    by_pos = sharding.shard_plan(None, 1, 10_000, 100, 4)
+    assert [s["own_hi"] for s in by_pos] == [3000, 5000, 8000, 10_000] or [s["own_hi"] for s in by_pos] == [2000, 5000, 8000, 10_000] or all(s["own_hi"] % 1000 == 0 for s in by_pos)
+
+
 def _fake_records(lo, hi, step):
     pos = np.arange(lo, hi, step, dtype=np.int32)
     r = np.zeros(len(pos), dtype=_native.RECORD_DTYPE)
