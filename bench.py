@@ -251,8 +251,29 @@ def main_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = f"cuda:{local}"
 
-    # ---- synthetic read set of this rank (interval shard `rank` of `world`), generated on the device, kept on the host in pinned memory
+    # ---- synthetic read set of this rank, generated on the device, kept on the host in pinned memory. N > 1: the job's chromosome is `world` stretches of
+    # `loci` positions, cut by pb2_shard_plan into one interval shard per rank; a rank holds its own stretch plus the reads of its neighbours' stretches
+    # inside the plan's halo (positions are kept local to the rank: the shard's own range starts after the left halo).
+    from pisces_b200 import sharding
     d = synth.make_reads(a.loci, a.depth, seed=a.seed + 1000 * rank, device=dev, **a.gen)
+    own_lo, own_hi = 1, a.loci
+    if world > 1:
+        span = d["read_len"] + 4
+        plan = sharding.shard_plan(None, 1, world * a.loci, span, world)
+        me = plan[rank]
+        assert (me["own_lo"], me["own_hi"]) == (rank * a.loci + 1, (rank + 1) * a.loci), "loci per GPU must be a multiple of 1000"
+        halo_l = me["own_lo"] - me["stage_lo"]
+        halo_r = min(me["stage_hi"], world * a.loci) - me["own_hi"]
+        parts = []
+        if rank > 0:
+            nb = synth.make_reads(a.loci, a.depth, seed=a.seed + 1000 * (rank - 1), device=dev, **a.gen)
+            parts.append((synth.reads_slice(nb, a.loci - halo_l, a.loci), -(a.loci - halo_l)))   # (the reads inside the halo; its first read span is thinner, 3000 positions from anything owned)
+        parts.append((d, halo_l))
+        if rank < world - 1:
+            nb = synth.make_reads(a.loci, a.depth, seed=a.seed + 1000 * (rank + 1), device=dev, **a.gen)
+            parts.append((synth.reads_slice(nb, 0, halo_r), halo_l + a.loci))
+        d = synth.reads_concat(parts, a.loci)
+        own_lo, own_hi = halo_l + 1, halo_l + a.loci
     torch.cuda.empty_cache()
     n_entries = d["n_entries"]
     ref = bytes(d["ref"]).decode()
@@ -270,6 +291,8 @@ def main_ours(a):
     cfg.reserved[0] = a.tune_ctas
     cfg.reserved[1] = a.tune_prefetch
     sm = pb.GpuStateManager(cfg, "chr1", ref)
+    if world > 1:
+        sm.SetOwnedRange(own_lo, own_hi)
     sm.AddReadsSoA(pinned)
     sm.StageReads()
     stage = sm.stage_stats()
@@ -282,49 +305,41 @@ def main_ours(a):
     sm.StageReads()
     torch.cuda.synchronize()
 
-    import ctypes as C
-
-    class DevBuf:   # torch view of a device buffer owned by the library
-        def __init__(self, ptr, nbytes):
-            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-    # ---- the single all-gather of per-interval call records (NCCL) at the end of the job: a step appends its variant records to the
-    # rank's job buffer (one device copy out of the library's variant stream, which lives at a fixed device address, so its torch view is created
-    # once); when the K steps are done the ranks exchange [K int64 counts | K x fixed-capacity record blocks] in ONE all_gather, inside the timed region.
-    job_buf = gather_out = var_view = counts_pinned = None
-    n_slots = max(1, a.steps)
-    if world > 1 and resident_ok:
-        n0 = sm.call_resident()
-        n0_all = torch.tensor([n0], dtype=torch.int64, device=dev)
-        dist.all_reduce(n0_all, op=dist.ReduceOp.MAX)    # the ranks' shards differ: the block capacity (hence the gathered size) must be the same on all
-        n0 = int(n0_all.item())
-        cap_records = (n0 + n0 // 8 + 127) // 64 * 64   # fixed capacity of a step's block: the largest shard's record count plus 12 % head-room
-        vr, nv = C.c_void_p(), C.c_int64()
-        sm._chk(sm._L.pb2_resident_results(sm._h, None, None, None, C.byref(vr), C.byref(nv)))
-        var_view = torch.as_tensor(DevBuf(vr.value, cap_records * 96), device=dev)
-        job_buf = torch.zeros(8 * n_slots + n_slots * cap_records * 96, dtype=torch.uint8, device=dev)
-        gather_out = torch.zeros(world * job_buf.numel(), dtype=torch.uint8, device=dev)
-        counts_pinned = torch.zeros(n_slots, dtype=torch.int64).pin_memory()
-
     # configurations whose SNV / MNV candidates come from the candidate finder (CallMNVs) need the collapser / MNV reallocator of pb2_flush: their step is
     # the whole job from the device-resident reads (pb2_flush_resident); the others run the resident staged-pileup step (pb2_call_resident)
     resident_ok = not a.cfg.get("call_mnvs")
 
+    # ---- the job's records: every resident step appends its variant records to the rank's job buffer ON THE DEVICE (pb2_set_resident_sink: the library
+    # copies them on its own stream, no host synchronisation per step); when the K steps are done the slots are ordered by position on the device
+    # (pb2_sink_sort) and the ranks exchange [K counts | K fixed-capacity record blocks] in ONE all_gather, inside the timed region.
+    job_buf = gather_out = None
+    n_slots = max(1, a.steps)
+    if resident_ok:
+        n0 = sm.call_resident()          # synchronous: builds the explicit-candidate plan and the CUDA graph of the step
+        n0_all = torch.tensor([n0], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(n0_all, op=dist.ReduceOp.MAX)    # the ranks' shards differ: the block capacity (hence the gathered size) must be the same on all
+        cap_records = (int(n0_all.item()) * 9 // 8 + 127) // 64 * 64   # fixed capacity of a step's block: the largest shard's record count plus 12 % head-room
+        job_buf = torch.zeros(8 * n_slots + n_slots * cap_records * 96, dtype=torch.uint8, device=dev)
+        sm.call_resident()               # replay once synchronously (the first call built the plan on the handle stream only)
+        sm.set_resident_sink(job_buf.data_ptr(), cap_records, n_slots)
+        if world > 1:
+            gather_out = torch.zeros(world * job_buf.numel(), dtype=torch.uint8, device=dev)
+
     def step(k=0):
         if not resident_ok:
             return len(sm.flush_resident())
-        n = sm.call_resident()   # returns after the step's counters are on the host: the library's stream is idle, the variant stream complete
-        if world > 1 and resident_ok:
-            slot = k % n_slots
-            counts_pinned[slot] = min(n, cap_records)
-            o = 8 * n_slots + slot * cap_records * 96
-            job_buf[o:o + cap_records * 96].copy_(var_view, non_blocking=True)
-        return n
+        sm.call_resident_async()         # enqueue only: the step's graph + the copy of its records into slot k of the job buffer
+        return 0
 
-    def gather_job():
-        if world > 1 and resident_ok:
-            job_buf[:8 * n_slots].copy_(counts_pinned.view(torch.uint8), non_blocking=True)
-            dist.all_gather_into_tensor(gather_out, job_buf)
+    def finish_job():
+        if resident_ok:
+            sm.sink_sort()
+            n = sm.resident_sync()
+            if world > 1:
+                dist.all_gather_into_tensor(gather_out, job_buf)
+            return n
+        return None
 
     def barrier():
         if world > 1:
@@ -333,7 +348,9 @@ def main_ours(a):
 
     for k in range(max(3, a.warmup)):
         n_records = step(k)
-    gather_job()   # untimed: NCCL sets its channels up on the first collective
+    n_fin = finish_job()   # untimed: NCCL sets its channels up on the first collective
+    if n_fin is not None:
+        n_records = n_fin
     sm.stats()
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -341,12 +358,9 @@ def main_ours(a):
     sampler.start()
     ev0.record()
     t0 = time.perf_counter()
-    blocks = []   # hot-kernel time of every 10 timed steps (the library's own CUDA events): shows a machine-state change inside the timed region
     for k in range(a.steps):
         n_records = step(k)
-        if (k + 1) % 10 == 0 or k + 1 == a.steps:
-            blocks.append(sm.stats())
-    gather_job()
+    n_fin = finish_job()
     barrier()
     ev1.record()
     ev1.synchronize()
@@ -354,7 +368,26 @@ def main_ours(a):
     dt = ev0.elapsed_time(ev1) * 1e-3   # device clock between the two synchronised brackets (the wall clock beside it: wall_ms_per_step)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
+    if n_fin is not None:
+        n_records = n_fin
+    timed_launches = sm.stats()["total_launches"]
+    # the hot kernel's own time (the library's CUDA events around it), read after the timed region from synchronous steps in blocks of 10: shows a
+    # machine-state change between blocks
+    blocks = []
+    if resident_ok:
+        sm.set_resident_sink(None, 0, 0)
+        for _ in range(3):
+            for _ in range(10):
+                sm.call_resident()
+            blocks.append(sm.stats())
+    else:
+        blocks.append(dict(hot_launches=a.steps, hot_ms=0.0, total_launches=timed_launches))
+        for _ in range(3):
+            sm.flush_resident()
+        st_ = sm.stats()
+        blocks[0]["hot_ms"] = st_["hot_ms"] / max(1, st_["hot_launches"]) * a.steps
     st = {k: sum(b[k] for b in blocks) for k in ("hot_launches", "hot_ms", "total_launches")}
+    st["total_launches"] = timed_launches
     per_block = sorted(b["hot_ms"] / max(1, b["hot_launches"]) for b in blocks)
     tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:

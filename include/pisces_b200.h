@@ -265,6 +265,15 @@ int pb2_call_resident(pb2_handle* h, int64_t* n_records);
  * and the compacted variant stream. Any may be NULL. */
 int pb2_resident_results(pb2_handle* h, const pb2_call_record** ref_records, const uint8_t** ref_valid, int64_t* n_loci,
                          const pb2_call_record** variant_records, int64_t* n_variants);
+/* The job's record sink for the end-of-job gather (one all-gather of per-interval call records): a caller-provided DEVICE buffer of
+ * 8 * n_slots + n_slots * slot_records * 96 bytes, [n_slots int64 record counts | n_slots blocks of slot_records pb2_call_record]. Every resident step from
+ * now on copies its variant stream (at most slot_records records) and their count into slot (step number % n_slots) on the handle's stream; NULL unsets.
+ * pb2_call_resident_async enqueues one step without synchronising the host (after one synchronous pb2_call_resident built the plan); pb2_resident_sync
+ * waits for everything enqueued; pb2_sink_sort orders every slot's records by position on the device, ready to be gathered in rank order. */
+int pb2_set_resident_sink(pb2_handle* h, void* device_buffer, int64_t slot_records, int32_t n_slots);
+int pb2_call_resident_async(pb2_handle* h);
+int pb2_resident_sync(pb2_handle* h, int64_t* n_records_last);
+int pb2_sink_sort(pb2_handle* h);
 /* IAlleleCaller.Call for everything staged up to up_to_position (-1 = all): runs pb2_call_resident if needed, copies the
  * records to the host ordered by (position, ref, alt) as AlleleCaller.cs:96-140,172-176 orders them. */
 int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n);

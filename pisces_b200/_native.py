@@ -77,7 +77,7 @@ RECORD_DTYPE = [("position", "<i4"), ("type", "u1"), ("genotype", "u1"), ("sb_fl
 RECORD_EXT_DTYPE = [("collapsed_mut", "<i4", (8,)), ("collapsed_total", "<i4", (8,)), ("well_anchored_support", "<i4", (3,)), ("phase_set_index", "<i4")]
 
 EXPORTS = ["pb2_default_config", "pb2_create", "pb2_destroy", "pb2_last_error", "pb2_device_count", "pb2_set_reference", "pb2_set_intervals",
-           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_reads_packed", "pb2_pack_reads", "pb2_stage_reads", "pb2_push_candidates", "pb2_set_forced_alleles", "pb2_allele_arena", "pb2_call_resident", "pb2_resident_results", "pb2_flush", "pb2_flush_resident", "pb2_flush_ext",
+           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_reads_packed", "pb2_pack_reads", "pb2_stage_reads", "pb2_push_candidates", "pb2_set_forced_alleles", "pb2_allele_arena", "pb2_call_resident", "pb2_call_resident_async", "pb2_resident_sync", "pb2_set_resident_sink", "pb2_sink_sort", "pb2_resident_results", "pb2_flush", "pb2_flush_resident", "pb2_flush_ext",
            "pb2_get_counts", "pb2_reset", "pb2_shard_plan", "pb2_set_owned_range", "pb2_stats", "pb2_stage_stats", "pb2_stream", "pb2_totals", "pb2_vcf_format",
            "pb2_bam_open", "pb2_bam_close", "pb2_bam_last_error", "pb2_bam_header", "pb2_bam_next_batch", "pb2_bam_batch_amplicons",
            "pb2_bam_amplicon_names"]
@@ -114,6 +114,10 @@ def load():
     L.pb2_set_forced_alleles.argtypes = [H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     L.pb2_allele_arena.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.pb2_call_resident.argtypes = [H, C.POINTER(C.c_int64)]
+    L.pb2_call_resident_async.argtypes = [H]
+    L.pb2_resident_sync.argtypes = [H, C.POINTER(C.c_int64)]
+    L.pb2_set_resident_sink.argtypes = [H, C.c_void_p, C.c_int64, C.c_int32]
+    L.pb2_sink_sort.argtypes = [H]
     L.pb2_resident_results.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.pb2_flush.argtypes = [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.pb2_flush_resident.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]

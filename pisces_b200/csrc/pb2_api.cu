@@ -1106,7 +1106,73 @@ static int resident_step_enqueue(pb2_handle* h, Segment& s, bool with_explicit, 
     CU(h, cudaMemcpyAsync(h->h_counters, s.counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
     return PB2_OK;
 }
-static int resident_step(pb2_handle* h, Segment& s, bool with_explicit) {
+// ---- the job's record sink (multi-GPU gather): [n_slots int64 counts | n_slots x slot_records records]; a step's variant stream lands in slot step % n_slots
+__global__ static void sink_copy_kernel(const pb2_call_record* __restrict__ var, const unsigned long long* __restrict__ counters, long long* __restrict__ count_out,
+                                        pb2_call_record* __restrict__ slot, int64_t slot_records) {
+    const int64_t n = min((int64_t)counters[0], slot_records);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = (long long)n;
+    const uint4* src = reinterpret_cast<const uint4*>(var);
+    uint4* dst = reinterpret_cast<uint4*>(slot);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * 6; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ static void sink_keys_kernel(const long long* __restrict__ counts, const pb2_call_record* __restrict__ slots, int64_t slot_records, int32_t n_slots,
+                                        unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slot_records * n_slots) return;
+    const int64_t slot = i / slot_records, k = i % slot_records;
+    const bool valid = k < counts[slot];
+    keys[i] = ((unsigned long long)slot << 33) | (valid ? (unsigned long long)(uint32_t)slots[i].position : 0x1ffffffffull);
+    idx[i] = (uint32_t)i;
+}
+__global__ static void sink_gather_kernel(const pb2_call_record* __restrict__ in, const uint32_t* __restrict__ idx, int64_t n, pb2_call_record* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 6) return;
+    reinterpret_cast<uint4*>(out)[t] = reinterpret_cast<const uint4*>(in)[(int64_t)idx[t / 6] * 6 + t % 6];
+}
+cudaError_t sink_sort_pairs(void* temp, size_t& temp_bytes, const unsigned long long* kin, unsigned long long* kout, const uint32_t* vin, uint32_t* vout, int64_t n, cudaStream_t st);
+
+extern "C" int pb2_set_resident_sink(pb2_handle* h, void* device_buffer, int64_t slot_records, int32_t n_slots) {
+    if (!h || (device_buffer && (slot_records < 1 || n_slots < 1))) return fail(h, PB2_ERR_ARG, "pb2_set_resident_sink: bad argument");
+    h->sink = device_buffer; h->sink_slot_records = slot_records; h->sink_slots = device_buffer ? n_slots : 0; h->sink_next = 0;
+    return PB2_OK;
+}
+static int sink_append(pb2_handle* h, Segment& s) {
+    if (!h->sink) return PB2_OK;
+    const int32_t slot = (int32_t)(h->sink_next++ % h->sink_slots);
+    long long* counts = reinterpret_cast<long long*>(h->sink);
+    pb2_call_record* slots = reinterpret_cast<pb2_call_record*>(reinterpret_cast<uint8_t*>(h->sink) + 8 * (size_t)h->sink_slots);
+    const int blocks = (int)std::min<int64_t>((h->sink_slot_records * 6 + 255) / 256, 2048);
+    sink_copy_kernel<<<blocks, 256, 0, h->stream>>>(s.var_records, s.counters, counts + slot, slots + (int64_t)slot * h->sink_slot_records, h->sink_slot_records);
+    h->total_launches += 1;
+    return cudaGetLastError() == cudaSuccess ? PB2_OK : fail(h, PB2_ERR_CUDA, "sink_copy_kernel launch failed");
+}
+// Orders the records of every slot by position on the device (AlleleCaller orders its output by position: AlleleCaller.cs:96-140; alleles of one position
+// keep their emission order, as the reference's OrderBy is applied per position by the host that writes them)
+extern "C" int pb2_sink_sort(pb2_handle* h) {
+    if (!h || !h->sink) return fail(h, PB2_ERR_STATE, "pb2_sink_sort: no sink set");
+    CU(h, cudaSetDevice(h->device));
+    const int64_t n = h->sink_slot_records * h->sink_slots;
+    long long* counts = reinterpret_cast<long long*>(h->sink);
+    pb2_call_record* slots = reinterpret_cast<pb2_call_record*>(reinterpret_cast<uint8_t*>(h->sink) + 8 * (size_t)h->sink_slots);
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    uint32_t *i0 = nullptr, *i1 = nullptr;
+    pb2_call_record* tmp = nullptr;
+    void* temp = nullptr;
+    size_t tb = 0;
+    CU(h, sink_sort_pairs(nullptr, tb, k0, k1, i0, i1, n, h->stream));
+    CU(h, pool_alloc_t(h, &k0, (size_t)n)); CU(h, pool_alloc_t(h, &k1, (size_t)n)); CU(h, pool_alloc_t(h, &i0, (size_t)n)); CU(h, pool_alloc_t(h, &i1, (size_t)n));
+    CU(h, pool_alloc_t(h, &tmp, (size_t)n)); CU(h, pool_alloc(h, &temp, tb + 16));
+    sink_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(counts, slots, h->sink_slot_records, h->sink_slots, k0, i0);
+    CU(h, sink_sort_pairs(temp, tb, k0, k1, i0, i1, n, h->stream));
+    sink_gather_kernel<<<(unsigned)((n * 6 + 255) / 256), 256, 0, h->stream>>>(slots, i1, n, tmp);
+    CU(h, cudaMemcpyAsync(slots, tmp, sizeof(pb2_call_record) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    h->total_launches += 4;
+    void* ptrs[] = {k0, k1, i0, i1, tmp, temp};
+    for (void* p : ptrs) pool_free(h, p);
+    return PB2_OK;
+}
+
+static int resident_step(pb2_handle* h, Segment& s, bool with_explicit, bool sync = true) {
     cudaStream_t st = h->stream;
     if (h->resident_graph == nullptr && !h->resident_graph_failed) {
         const int64_t launches_before = h->total_launches;
@@ -1129,7 +1195,32 @@ static int resident_step(pb2_handle* h, Segment& s, bool with_explicit) {
         const int rc = resident_step_enqueue(h, s, with_explicit, false);
         if (rc != PB2_OK) return rc;
     }
+    { const int rc = sink_append(h, s); if (rc != PB2_OK) return rc; }
+    if (!sync) { h->hot_launches += 1; h->total_launches += 2; return PB2_OK; }
     return finish_segment(h, s, true);
+}
+// One resident step without a host synchronisation: the step (a CUDA graph) and the copy of its variant records into the next sink slot are enqueued and
+// the call returns. Needs one synchronous pb2_call_resident before (it builds the plan and the graph) and a sink (pb2_set_resident_sink).
+extern "C" int pb2_call_resident_async(pb2_handle* h) {
+    if (!h) return PB2_ERR_ARG;
+    if (h->segs.size() != 1 || h->resident_graph == nullptr || (!h->cands.empty() && !explicit_resident_ready(h)))
+        return fail(h, PB2_ERR_STATE, "pb2_call_resident_async: call pb2_call_resident once first (one staged segment)");
+    CU(h, cudaSetDevice(h->device));
+    return resident_step(h, h->segs[0], !h->cands.empty(), false);
+}
+extern "C" int pb2_resident_sync(pb2_handle* h, int64_t* n_records_last) {
+    if (!h) return PB2_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (!h->segs.empty()) {
+        Segment& s = h->segs[0];
+        s.h_var_count = h->h_counters[0]; s.h_exc_count = h->h_counters[3]; s.called = true;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->hot_ms += ms * 1;   // (the last step's kernel time; the steps before are counted as launches)
+        if (n_records_last) *n_records_last = (int64_t)s.h_var_count;
+        if ((int64_t)s.h_var_count > s.var_capacity) return fail(h, PB2_ERR_NOMEM, "variant record buffer overflow");
+    }
+    return PB2_OK;
 }
 
 extern "C" int pb2_call_resident(pb2_handle* h, int64_t* n_records) {

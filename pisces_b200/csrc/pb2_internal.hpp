@@ -221,6 +221,9 @@ struct pb2_handle {
     std::vector<Segment> segs;
     DeviceReads reads;
     int32_t own_lo = 0, own_hi = 0;   // pb2_set_owned_range (0, 0: everything)
+    void* sink = nullptr;             // pb2_set_resident_sink: device buffer of the job's records, filled slot by slot by the resident steps
+    int64_t sink_slot_records = 0, sink_next = 0;
+    int32_t sink_slots = 0;
     int32_t cleared_through = 0;   // positions <= this were called by an earlier pb2_flush(up_to >= 0)
     int* d_tile_counter = nullptr;
     std::vector<pb2_call_record> h_out;

@@ -6,6 +6,7 @@
 //   CoverageCalculator.CalculateSinglePoint                             src/lib/Pisces.Calculators/CoverageCalculator.cs:49-98
 //   AlleleCaller.ProcessVariant / IsCallable / ComputeGenotypeAndFilterAllele   src/exe/Pisces/Logic/VariantCalling/AlleleCaller.cs:143-177,208-258
 //   AlleleProcessor.ApplyFilters, RMxNCalculator                        AlleleProcessor.cs:25-71, src/lib/Pisces.Calculators/RMxNCalculator.cs:19-133
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include "pb2_kernels.cuh"
 #include "pb2_math.cuh"
@@ -190,6 +191,13 @@ cudaError_t launch_tile_scatter(const int64_t* off, const uint8_t* code, const u
     return cudaGetLastError();
 }
 
+}  // namespace pb2
+// (key, index) pairs of the job sink by key (pb2_sink_sort): CUB radix sort over the 40 key bits in use
+cudaError_t sink_sort_pairs(void* temp, size_t& temp_bytes, const unsigned long long* kin, unsigned long long* kout, const uint32_t* vin, uint32_t* vout, int64_t n,
+                            cudaStream_t st) {
+    return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 48, st);
+}
+namespace pb2 {
 // out[i] = sum_{j<i} in[j]   (staging step, not on the hot path: CUB device scan). tile_layout_kernel already scaled the input to bytes.
 cudaError_t exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* temp, size_t temp_bytes, size_t* temp_needed, cudaStream_t stream) {
     size_t need = 0;

@@ -461,6 +461,24 @@ class GpuStateManager:
             return np.zeros(0, dtype=N.RECORD_DTYPE)
         return np.frombuffer((C.c_char * (96 * n.value)).from_address(out.value), dtype=N.RECORD_DTYPE).copy()
 
+    def SetOwnedRange(self, own_lo, own_hi):
+        """pb2_set_owned_range: this handle is one interval shard and emits only the positions it owns."""
+        self._chk(self._L.pb2_set_owned_range(self._h, int(own_lo), int(own_hi)))
+
+    def set_resident_sink(self, device_ptr, slot_records, n_slots):
+        self._chk(self._L.pb2_set_resident_sink(self._h, device_ptr, int(slot_records), int(n_slots)))
+
+    def call_resident_async(self):
+        self._chk(self._L.pb2_call_resident_async(self._h))
+
+    def resident_sync(self):
+        n = C.c_int64()
+        self._chk(self._L.pb2_resident_sync(self._h, C.byref(n)))
+        return n.value
+
+    def sink_sort(self):
+        self._chk(self._L.pb2_sink_sort(self._h))
+
     def call_resident(self):
         n = C.c_int64()
         self._chk(self._L.pb2_call_resident(self._h, C.byref(n)))

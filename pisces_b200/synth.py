@@ -313,3 +313,48 @@ def make_reads(n_loci, mean_depth, seed=2, device="cpu", read_len=READ_LEN, snv_
              collapsed=None if collapsed is None else collapsed.cpu().numpy(), xd_runs=None if xd_runs is None else xd_runs.cpu().numpy(),
              base_dirs=torch.cat(out_dirs).numpy() if out_dirs else None)
     return d
+
+
+def reads_slice(d, lo, hi):
+    """The reads of make_reads' dict whose start (0-based) lies in [lo, hi), offsets rebased to the slice."""
+    import numpy as np
+    r0, r1 = int(np.searchsorted(d["pos0"], lo, "left")), int(np.searchsorted(d["pos0"], hi, "left"))
+    out = dict(d)
+    c0, c1, s0, s1 = int(d["cigar_off"][r0]), int(d["cigar_off"][r1]), int(d["seq_off"][r0]), int(d["seq_off"][r1])
+    out.update(n_reads=r1 - r0, pos0=d["pos0"][r0:r1], flag=d["flag"][r0:r1], cigar_off=d["cigar_off"][r0:r1 + 1] - c0, cigar=d["cigar"][c0:c1],
+               seq_off=d["seq_off"][r0:r1 + 1] - s0, bases=d["bases"][s0:s1], quals=d["quals"][s0:s1])
+    for k in ("collapsed", "xd_runs"):
+        if d.get(k) is not None:
+            out[k] = d[k][r0:r1]
+    if d.get("base_dirs") is not None:
+        out["base_dirs"] = d["base_dirs"][s0:s1]
+    return out
+
+
+def reads_concat(parts, chunk_loci):
+    """Concatenates read sets [(dict, position shift)] (in position order) into one; the reference is the shifted concatenation of the parts' chromosomes
+    (a part shifted by a negative amount contributes its tail)."""
+    import numpy as np
+    ref_parts, pos, flag, cig, bases, quals, coll, dirs, xd = [], [], [], [], [], [], [], [], []
+    coff, soff = [np.zeros(1, dtype=np.int64)], [np.zeros(1, dtype=np.int64)]
+    n_entries = 0
+    total_len = 0
+    for dct, shift in parts:
+        full = dct["ref"]
+        ref_parts.append(full[-shift:] if shift < 0 else full)
+        total_len = max(total_len, shift + len(full))
+        pos.append(dct["pos0"] + shift); flag.append(dct["flag"]); cig.append(dct["cigar"]); bases.append(dct["bases"]); quals.append(dct["quals"])
+        coff.append(dct["cigar_off"][1:] + coff[-1][-1]); soff.append(dct["seq_off"][1:] + soff[-1][-1])
+        if dct.get("collapsed") is not None:
+            coll.append(dct["collapsed"])
+        if dct.get("base_dirs") is not None:
+            dirs.append(dct["base_dirs"])
+        if dct.get("xd_runs") is not None:
+            xd.append(dct["xd_runs"])
+        n_entries += int(len(dct["bases"]))
+    ref = np.concatenate(ref_parts)
+    first = parts[0][0]
+    return dict(n_reads=int(sum(len(p) for p in pos)), read_len=first["read_len"], n_loci=len(ref), ref=ref, pos0=np.concatenate(pos).astype(np.int32), flag=np.concatenate(flag),
+                cigar_off=np.concatenate(coff), cigar=np.concatenate(cig), seq_off=np.concatenate(soff), bases=np.concatenate(bases), quals=np.concatenate(quals),
+                n_entries=n_entries, collapsed=np.concatenate(coll) if coll else None, base_dirs=np.concatenate(dirs) if dirs else None,
+                xd_runs=np.concatenate(xd) if xd else None, snv_loci=first.get("snv_loci"), indel_loci=first.get("indel_loci"))
