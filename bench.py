@@ -29,6 +29,10 @@ UNIT = "loci/s"
 # BASELINE.json configs[1..4]: generator arguments (pisces_b200.synth.make_reads), caller options, per-GPU size. configs[2..4] name
 # whole-job sizes of 10 M / 50 M / 200 M loci on 1 / 4 / 8 GPUs; a bench step covers `loci` per GPU (stated in config.workload), larger jobs are more steps.
 CONFIGS = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case. The hg19 sequence is not available offline, so the reference bases are N:
+    # the step stages the BAM, builds the pileup and scores the reference allele of every interval position (coverage, no-calls, genotype), no variants.
+    "c1": dict(loci=3203, depth=250, seed=1, gen={}, cfg=dict(output_gvcf=1, min_coverage=10),
+               what="tests/golden/example_S1.mapped.bam (the 482 mapped reads of testdata/example_S1.bam) x Intervals_1.picard, SNV-only, min-depth 10 (BASELINE.json configs[0])"),
     "c2": dict(loci=1_000_000, depth=500, seed=2, gen=dict(indel_rate=0.001), cfg=dict(output_gvcf=0),
                what="SNV 1% + indel 0.1%, Poisson noise model NL20, gvcf=0 (BASELINE.json configs[1] shape and size)"),
     "c3": dict(loci=1_000_000, depth=1000, seed=3, gen=dict(indel_rate=0.0, snv_rate=0.005), cfg=dict(output_gvcf=1),
@@ -187,6 +191,30 @@ def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if a.config == "c1":   # the reference's own CPU-runnable case: one job, one thread (the reference runs a BAM x chromosome job on one thread)
+        from oracle import binding as ob
+        from tests import bamio
+        path, iv, n_loci = c1_inputs()
+        _, refs, recs = bamio.read_bam(path)
+        kept = [r for r in recs if not (r["flag"] & 0x4 or r["flag"] & 0x100 or r["flag"] & 0x400 or r["mapq"] < 1 or not r["cigar"] or r["ref_id"] < 0)]
+        times = []
+        for i in range(a.warmup + a.steps):
+            t1 = time.perf_counter()
+            for ref_id in sorted({r["ref_id"] for r in kept}):
+                oc = ob.Caller(ob.default_config(output_gvcf=1, min_coverage=10), refs[ref_id][0], "", intervals=iv.get(refs[ref_id][0], []))
+                for r in kept:
+                    if r["ref_id"] == ref_id:
+                        oc.add_read(ob.SimpleRead(r["pos0"] + 1, r["seq"], r["cigar"], r["qual"], flag=r["flag"], mapq=r["mapq"]))
+                oc.finish()
+            if i >= a.warmup:
+                times.append(time.perf_counter() - t1)
+        value = n_loci * a.steps / sum(times)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": 1e3 * sum(times) / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+                          "data": "reference test data (tests/golden)", "config": {"workload": f"c1: {CONFIGS['c1']['what']}", "loci_per_gpu": n_loci},
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"the {len(kept)} reads through the oracle's per-read loop"},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     import torch
     from pisces_b200 import synth
     cores = os.cpu_count() or 1
@@ -210,8 +238,8 @@ def main_reference(a):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "loci_per_gpu": a.loci,
-                   "note": "oracle port of the C# path (dotnet runtime absent): SmallVariantCaller.Execute's per-read loop, no I/O"},
+        "config": {"workload": workload_name(a), "loci_per_gpu": a.loci},
+        "note": "oracle port of the C# path (dotnet runtime absent): SmallVariantCaller.Execute's per-read loop, no I/O",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -234,7 +262,87 @@ def compare_with_oracle(orecs, precs, arena, limit):
     return len(o), mism
 
 
+def c1_inputs():
+    import collections
+    G = os.path.join(ROOT, "tests", "golden")
+    iv = collections.OrderedDict()
+    for line in open(os.path.join(G, "Intervals_1.picard")):
+        if line.startswith("@") or not line.strip():
+            continue
+        f = line.split("\t")
+        iv.setdefault(f[0], []).append((int(f[1]), int(f[2])))
+    n_loci = sum(len(set(p for a_, b_ in v for p in range(a_, b_ + 1))) for v in iv.values())
+    return os.path.join(G, "example_S1.mapped.bam"), iv, n_loci
+
+
+def main_c1(a):
+    """configs[0]: BAM file -> library stager -> device pileup -> records, one handle per chromosome with its intervals. Host file in, records out: the step
+    IS end to end; the CPU baseline is the oracle's per-read loop over the same reads."""
+    import torch
+    import pisces_b200 as pb
+    from oracle import binding as ob
+    from tests import bamio
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; pisces_b200 has no CPU path")
+    path, iv, n_loci = c1_inputs()
+    cfg = pb.make_config(**a.cfg)
+
+    def step():
+        st = pb.BamReadStager(path)
+        names = [n for n, _ in st.references]
+        sms, n_rec = {}, 0
+        for ref_id, batch, _ in st:
+            if ref_id not in sms:
+                sms[ref_id] = pb.GpuStateManager(cfg, names[ref_id], None, intervals=iv.get(names[ref_id], []))
+            sms[ref_id].AddReadBatch(batch)
+        for sm in sms.values():
+            n_rec += len(pb.GpuAlleleCaller().Call(sm, raw=True))
+            sm.close()
+        st.close()
+        return n_rec
+    for _ in range(max(3, a.warmup)):
+        n_rec = step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        n_rec = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    value = n_loci * a.steps / dt
+    # CPU: the oracle over the same reads (counts + reference calls), single thread
+    _, refs, recs = bamio.read_bam(path)
+    kept = [r for r in recs if not (r["flag"] & 0x4 or r["flag"] & 0x100 or r["flag"] & 0x400 or r["mapq"] < 1 or not r["cigar"] or r["ref_id"] < 0)]
+    best = None
+    for _ in range(max(1, a.cpu_repeats)):
+        t1 = time.perf_counter()
+        for ref_id in sorted({r["ref_id"] for r in kept}):
+            oc = ob.Caller(ob.default_config(output_gvcf=1, min_coverage=10), refs[ref_id][0], "", intervals=iv.get(refs[ref_id][0], []))
+            for r in kept:
+                if r["ref_id"] == ref_id:
+                    oc.add_read(ob.SimpleRead(r["pos0"] + 1, r["seq"], r["cigar"], r["qual"], flag=r["flag"], mapq=r["mapq"]))
+            oc.finish()
+        cdt = time.perf_counter() - t1
+        best = cdt if best is None else min(best, cdt)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "reference test data (tests/golden)",
+            "config": {"workload": f"c1: {CONFIGS['c1']['what']}", "loci_per_gpu": n_loci},
+            "workload_details": {"reads": len(kept), "records_per_step": n_rec,
+                                 "note": "a 482-read job is launch- and host-bound by construction: the number is the latency of one whole job, not a roofline point"},
+            "gpu_launches": None, "roofline": None, "clocks": sampler.summary(),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": sum(len(r["seq"]) * 2 + 26 for r in kept), "d2h_bytes_per_step": 96 * n_rec,
+                    "input": "BAM file on the host (pb2_bam_* stager), records back on the host"},
+            "cpu_baseline": {"value": n_loci / best, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"the same {len(kept)} reads through the oracle's per-read loop (python per-read calls included), best of {max(1, a.cpu_repeats)}"}}
+    print(json.dumps(line))
+
+
 def main_ours(a):
+    if a.config == "c1":
+        return main_c1(a)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -419,9 +527,11 @@ def main_ours(a):
     staged_bytes = stage["staged_bytes"] + 96 * (n_records + n_ref_records)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": 1e3 * dt / a.steps, "wall_ms_per_step": 1e3 * dt_wall / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "loci_per_gpu": a.loci, "reads_per_gpu": d["n_reads"], "entries_per_gpu": n_entries,
-                       "records_per_step": n_records + n_ref_records,
-                       "l2": "staged input of the hot kernel (%.2f GB per GPU) larger than L2, no flush needed" % (stage["staged_bytes"] / 1e9), "parallelism": f"interval-sharded x{world}"},
+            # (the same two keys as the reference arm's line, so that the two arms compare as the same configuration)
+            "config": {"workload": workload_name(a), "loci_per_gpu": a.loci},
+            "workload_details": {"reads_per_gpu": d["n_reads"], "entries_per_gpu": n_entries, "records_per_step": n_records + n_ref_records,
+                                 "l2": "staged input of the hot kernel (%.2f GB per GPU) larger than L2, no flush needed" % (stage["staged_bytes"] / 1e9),
+                                 "parallelism": f"interval shards of one chromosome x{world} (pb2_shard_plan)"},
             "gpu_launches": st["total_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": kernel_name, "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_entry": 3 if third_byte else 2,

@@ -176,6 +176,51 @@ def test_interval_shards_concatenate_to_the_unsharded_records(name, n_shards):
     assert short(got) == short(want)
 
 
+def test_example_s1_bam_counts():
+    """BASELINE.json configs[0] (C1): the mapped reads of the reference's testdata/example_S1.bam (tests/golden/example_S1.mapped.bam: chr1 and chr12
+    amplicon pile-ups, soft clips, insertions, deletions) through the library's BAM stager and the device pileup: the [6][3][11] counts of every covered
+    position equal the oracle's, bit for bit. (The hg19 sequence is not available offline - SURVEY 8c - so C1 pins counts, not calls.)"""
+    import os
+    from tests import bamio
+    pb = _pb()
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    path = os.path.join(G, "example_S1.mapped.bam")
+    _, refs, recs = bamio.read_bam(path)
+    ops = "MIDNSHP=X"
+    by_chr = {}
+    for r in recs:
+        if r["flag"] & 0x4 or r["flag"] & 0x100 or r["flag"] & 0x400 or r["mapq"] < 1 or not r["cigar"] or r["ref_id"] < 0:
+            continue
+        by_chr.setdefault(r["ref_id"], []).append(r)
+    st = pb.BamReadStager(path, max_reads=100)
+    sms = {}
+    for ref_id, batch, _ in st:
+        if ref_id not in sms:
+            sms[ref_id] = pb.GpuStateManager(pb.make_config(min_coverage=10), refs[ref_id][0], None)
+        sms[ref_id].AddReadBatch(batch)
+    st.close()
+    assert sorted(sms) == sorted(by_chr) and len(by_chr) == 2
+    total = 0
+    for ref_id, rr in by_chr.items():
+        lo = min(r["pos0"] + 1 for r in rr)
+        hi = max(r["pos0"] + sum(c >> 4 for c in r["cigar"] if ops[c & 15] in "MDN=X") for r in rr)
+        oc = ob.Caller(ob.default_config(min_coverage=10), refs[ref_id][0], "")
+        for r in rr:
+            oc.add_read(ob.SimpleRead(r["pos0"] + 1, r["seq"], r["cigar"], r["qual"], flag=r["flag"], mapq=r["mapq"]), mode="counts")
+        # the pile-ups are a few hundred positions wide, far apart: compare around every read start
+        starts = sorted({(r["pos0"] // 1000) * 1000 + 1 for r in rr} | {((r["pos0"] + 200) // 1000) * 1000 + 1 for r in rr})
+        for w in starts:
+            if w > hi:
+                continue
+            got = sms[ref_id].GetAlleleCounts(w, 1000)
+            exp = oc.dump_counts(w, 1000)
+            np.testing.assert_array_equal(got, exp)
+            total += int(exp.sum())
+        sms[ref_id].close()
+        assert lo >= 1
+    assert total > 40_000
+
+
 def test_invalid_reads_are_rejected_as_the_reference_does():
     pb = _pb()
     sm = pb.GpuStateManager(pb.make_config(), "chr1", "ACGT" * 50)
