@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--depth", type=int, default=0, help="mean depth (0: the config's)")
     ap.add_argument("--gvcf", type=int, default=-1, help="override the config's gVCF mode")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--gen", dest="gen_json", default="", help="JSON overrides of the config's read-generator arguments (tuning experiments), e.g. '{\"snv_rate\": 0}'")
     ap.add_argument("--tune-ctas", type=int, default=0, help="hot-kernel CTAs per SM (tuning experiments)")
     ap.add_argument("--tune-prefetch", type=int, default=0, help="tuning experiments (9: PTILE32 staging instead of PVERT)")
     ap.add_argument("--cpu-sample-loci", type=int, default=100_000)
@@ -142,6 +143,8 @@ def resolve(a):
     a.depth = a.depth or c["depth"]
     a.seed = a.seed or c["seed"]
     a.gen = dict(c["gen"])
+    if a.gen_json:
+        a.gen.update(json.loads(a.gen_json))
     a.cfg = dict(c["cfg"])
     if a.gvcf >= 0:
         a.cfg["output_gvcf"] = a.gvcf

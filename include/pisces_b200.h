@@ -89,6 +89,8 @@ typedef struct pb2_config {
     float   diploid_major_vf;            /* .MajorVF (0.70) */
     float   diploid_sum_vf_multiallelic; /* .SumVFforMultiAllelicSite (0.80) */
     int32_t is_male;                     /* VariantCallingParameters.IsMale: -1 null, 0 false, 1 true */
+    float   amplicon_bias_filter;        /* VariantCallingParameters.AmpliconBiasFilterThreshold (-abfilter): < 0 = null (default). With a threshold the reads'
+                                            amplicon names are tracked (Factory.ShouldTrackAmpliconCounts, Factory.cs:51-54) and SNVs get the AmpliconBias filter */
     int32_t reserved[2];                 /* tuning knobs of bench.py; 0 in production */
 } pb2_config;
 
@@ -109,6 +111,8 @@ typedef struct pb2_read_batch {
     const uint8_t*  quals;
     const uint8_t*  base_dirs;   /* optional: Read.SequencedBaseDirectionMap per base (XD tag projected, Read.cs:390-421,664-682); NULL -> from flag 0x10 */
     const uint8_t*  collapsed;   /* optional [n]: bit0 IsCollapsedRead (XV/XW present), bit1 IsDuplex, bits2-3 ReadPairDirection 1=FR 2=RF 0=other (Read.cs:17-71,311-349) */
+    const int32_t*  amplicon;    /* optional [n]: Read.GetAmpliconNameIfExists (the XN tag, Read.cs:479-486) as an id >= 0 of the host's name dictionary
+                                    (pb2_bam_batch_amplicons hands these out), -1 = no tag. Read only when amplicon_bias_filter >= 0 */
 } pb2_read_batch;
 
 /* The same reads for hosts behind a PCIe link: one byte per base instead of two. seq[i] = allele2 << 6 | quality with allele2 = A 0, G 1, C 2, T 3
@@ -129,6 +133,7 @@ typedef struct pb2_packed_read_batch {
     const uint8_t*  exc_qual;
     const uint8_t*  base_dirs;   /* optional, one byte per base as in pb2_read_batch */
     const uint8_t*  collapsed;   /* optional */
+    const int32_t*  amplicon;    /* optional, as in pb2_read_batch */
 } pb2_packed_read_batch;
 
 /* Locus-major pileup ("pileup columns") in CSR form: locus i covers reference position first_position + i (or positions[i]),

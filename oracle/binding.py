@@ -28,7 +28,7 @@ class Config(C.Structure):
         [(n, C.c_int32) for n in ("call_mnvs", "max_size_mnv", "max_gap_mnv", "collapse")] + \
         [(n, C.c_float) for n in ("collapse_freq_threshold", "collapse_freq_ratio_threshold")] + \
         [(n, C.c_int32) for n in ("exclude_mnvs_from_collapsing", "tracked_anchor_size", "output_gvcf", "source_is_stitched", "source_is_collapsed", "apply_validation")] + \
-        [(n, C.c_float) for n in ("diploid_minor_vf", "diploid_major_vf", "diploid_sum_vf_multiallelic")] + [("is_male", C.c_int32)]
+        [(n, C.c_float) for n in ("diploid_minor_vf", "diploid_major_vf", "diploid_sum_vf_multiallelic")] + [("is_male", C.c_int32), ("amplicon_bias_filter", C.c_float)]
 
 
 class ReadStruct(C.Structure):
@@ -45,7 +45,10 @@ class Record(C.Structure):
                 ("allele_support", C.c_int32), ("ref_support", C.c_int32), ("num_no_calls", C.c_int32),
                 ("fraction_no_calls", C.c_float), ("frequency", C.c_float), ("bias_score", C.c_double), ("gatk_bias_score", C.c_double),
                 ("bias_acceptable", C.c_int32), ("var_both_strands", C.c_int32), ("cov_both_strands", C.c_int32), ("forced", C.c_int32),
-                ("collapsed_mut", C.c_int32 * 8), ("collapsed_total", C.c_int32 * 8), ("ref_len", C.c_int32), ("alt_len", C.c_int32)]
+                ("collapsed_mut", C.c_int32 * 8), ("collapsed_total", C.c_int32 * 8), ("ref_len", C.c_int32), ("alt_len", C.c_int32),
+                ("has_amplicon_bias", C.c_int32), ("amplicon_bias_detected", C.c_int32),
+                ("n_amp_support", C.c_int32), ("amp_support_names", C.c_int32 * 6), ("amp_support_counts", C.c_int32 * 6),
+                ("n_amp_coverage", C.c_int32), ("amp_coverage_names", C.c_int32 * 6), ("amp_coverage_counts", C.c_int32 * 6)]
 
 
 # enums (src/lib/Pisces.Domain/Types/*.cs)
@@ -73,6 +76,7 @@ def lib():
         for f in ("po_caller_add_read", "po_caller_add_read_counts_only", "po_caller_add_read_candidates_only"):
             getattr(L, f).argtypes = [C.c_void_p, C.POINTER(ReadStruct)]
         L.po_caller_add_reads_soa.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 9
+        L.po_caller_add_reads_soa_amplicons.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 10
         L.po_caller_add_reads_soa_counts_only.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 9
         L.po_caller_add_pileup.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.po_caller_add_candidate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
@@ -223,17 +227,24 @@ class Caller:
              "candidates": self.L.po_caller_add_read_candidates_only}[mode]
         self._chk(f(self.h, C.byref(st)))
 
-    def add_reads_soa(self, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed=None, xd_runs=None, counts_only=False):
-        """A struct of arrays of reads (pb2_read_batch layout) through the reference's per-read loop."""
+    def add_reads_soa(self, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed=None, xd_runs=None, counts_only=False, amplicon=None):
+        """A struct of arrays of reads (pb2_read_batch layout) through the reference's per-read loop. amplicon: per-read XN name ids, -1 = no tag."""
         import numpy as np
         arrs = [np.ascontiguousarray(pos0, dtype=np.int32), np.ascontiguousarray(flag, dtype=np.uint16), np.ascontiguousarray(cigar_off, dtype=np.int64),
                 np.ascontiguousarray(cigar, dtype=np.uint32), np.ascontiguousarray(seq_off, dtype=np.int64), np.ascontiguousarray(bases, dtype=np.uint8),
                 np.ascontiguousarray(quals, dtype=np.uint8)]
         coll = None if collapsed is None else np.ascontiguousarray(collapsed, dtype=np.uint8)
         xd = None if xd_runs is None else np.ascontiguousarray(xd_runs, dtype=np.int32)
-        f = self.L.po_caller_add_reads_soa_counts_only if counts_only else self.L.po_caller_add_reads_soa
+        extra = []
+        if amplicon is not None:
+            assert not counts_only
+            amp = np.ascontiguousarray(amplicon, dtype=np.int32)
+            assert len(amp) == len(arrs[0])
+            f, extra = self.L.po_caller_add_reads_soa_amplicons, [amp.ctypes.data]
+        else:
+            f = self.L.po_caller_add_reads_soa_counts_only if counts_only else self.L.po_caller_add_reads_soa
         self._chk(f(self.h, len(arrs[0]), *[a.ctypes.data for a in arrs], None if coll is None else coll.ctypes.data,
-                                                 None if xd is None else xd.ctypes.data))
+                    None if xd is None else xd.ctypes.data, *extra))
 
     def add_pileup(self, offsets, code, qual, anchor, first_position=1, call_every=1):
         """Locus-major entries (pb2_pileup_csr semantics) through the reference's per-base operations."""

@@ -11,6 +11,7 @@ namespace po {
 struct CoverageCalculator {
     bool considerAnchorInformation;
     bool collapsedCalculator;  // CollapsedCoverageCalculator (Factory.cs:193-199)
+    bool trackAmpliconCoverage = false;   // the reference asks the source for CoverageByAmplicon unconditionally (:52); only a tracking run ever reads the answer
     explicit CoverageCalculator(bool considerAnchor = false, bool collapsed = false) : considerAnchorInformation(considerAnchor), collapsedCalculator(collapsed) {}
 
     void Compute(CalledAllele& allele, IAlleleSource& src) const {  // :19-47 (+ CollapsedCoverageCalculator.cs:18-37)
@@ -25,6 +26,7 @@ struct CoverageCalculator {
         }
     }
     void CalculateSinglePoint(CalledAllele& allele, IAlleleSource& src) const {  // :49-98
+        if (trackAmpliconCoverage) allele.CoverageByAmplicon = src.GetCoverageByAmplicon(allele.ReferencePosition);   // :52, :334-337
         if (collapsedCalculator) {  // CollapsedCoverageCalculator.CalculateSinglePoint :23-31
             for (int t = 0; t < NumReadCollapsedTypes; t++) allele.ReadCollapsedCountTotal[t] += src.GetCollapsedReadCount(allele.ReferencePosition, (ReadCollapsedType)t);
         }

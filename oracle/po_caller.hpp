@@ -75,7 +75,7 @@ inline void AlleleProcessorProcess(CalledAllele& a, const Config& cfg, const std
     if (a.Type != Reference) {
         if (cfg.NoCallFilterThreshold >= 0 && a.FractionNoCalls > cfg.NoCallFilterThreshold) a.AddFilter(F_NoCall);
         if (!a.StrandBiasResults.BiasAcceptable || (cfg.FilterOutVariantsPresentOnlyOneStrand && !a.StrandBiasResults.VarPresentOnBothStrands)) a.AddFilter(F_StrandBias);
-        // AmpliconBias: out of scope (needs XN amplicon names; AmpliconBiasResults stays null without them)
+        if (a.HasAmpliconBiasResults && a.AmpliconBiasDetected && cfg.AmpliconBiasFilterThreshold >= 0) a.AddFilter(F_AmpliconBias);   // :49-50
         if (cfg.IndelRepeatFilter > 0) {
             if (cfg.IndelRepeatFilter <= ComputeIndelRepeatLength(a, chrSeq)) a.AddFilter(F_IndelRepeatLength);
         }
@@ -362,6 +362,7 @@ struct AlleleCaller {
     AlleleCaller(const Config& c, const std::string& chr, const std::string* seq, ChrIntervalSet* iv)
         : cfg(c), chrName(chr), chrSeq(seq), intervalSet(iv),
           coverage(c.TrackedAnchorSize > 0, c.SourceIsCollapsed && c.SourceIsStitched) {  // Factory.cs:193-199
+        coverage.trackAmpliconCoverage = c.TrackAmpliconCounts();
         if (cfg.Collapse) collapser = std::make_unique<VariantCollapser>(&coverage, cfg.CollapseFreqThreshold, cfg.CollapseFreqRatioThreshold, cfg.ExcludeMNVsFromCollapsing);
         chrPloidy = GetPloidyForThisChr(cfg.ploidy, cfg.IsMale, chrName);
         if (chrPloidy == PM_DiploidByAdaptiveGT) throw std::runtime_error("DiploidByAdaptiveGT genotyper is out of scope (SURVEY 8f rank 4)");
@@ -380,6 +381,19 @@ struct AlleleCaller {
             // _config.MinFrequency = genotypeCalculator.MinVarFrequency (Factory.cs:140,160)
             v.StrandBiasResults = CalculateStrandBiasResults(v.EstimatedCoverageByDirection.data(), v.SupportByDirection.data(), NL, minFrequency,
                                                              cfg.StrandBiasAcceptanceCriteria, cfg.strandBiasModel);
+            // AmpliconBiasCalculator.Compute (AmpliconBiasCalculator.cs:20-31): SNVs only, only with a threshold
+            if (cfg.AmpliconBiasFilterThreshold >= 0 && v.Type == Snv) {
+                int sn[MaxNumOverlappingAmplicons], sc[MaxNumOverlappingAmplicons], cn[MaxNumOverlappingAmplicons], cc[MaxNumOverlappingAmplicons];
+                int nc = 0;
+                for (int i = 0; i < MaxNumOverlappingAmplicons; i++) {
+                    sn[i] = v.SupportByAmplicon.names[(size_t)i]; sc[i] = v.SupportByAmplicon.counts[(size_t)i];
+                    if (!v.CoverageByAmplicon.isNull && v.CoverageByAmplicon.names[(size_t)i] >= 0) { cn[nc] = v.CoverageByAmplicon.names[(size_t)i]; cc[nc] = v.CoverageByAmplicon.counts[(size_t)i]; nc++; }
+                }
+                const AmpliconBiasResults r = CalculateAmpliconBias(sn, sc, v.SupportByAmplicon.isNull ? -1 : MaxNumOverlappingAmplicons, cn, cc, nc,
+                                                                    cfg.AmpliconBiasFilterThreshold, cfg.MaximumVariantQScore);
+                v.HasAmpliconBiasResults = !r.isNull;
+                v.AmpliconBiasDetected = !r.isNull && r.biasDetected;
+            }
         }
         AlleleProcessorProcess(v, cfg, *chrSeq, source.ExpectStitchedReads(), variantFreqFilter);
     }
@@ -491,8 +505,8 @@ struct SmallVariantCaller {
         if (ivs) { intervals = std::make_unique<ChrIntervalSet>(); intervals->Intervals = *ivs; intervals->SortAndCollapse(); }  // Factory.cs:229-245
         // Factory.CreateStateManager :209-227
         state = std::make_unique<RegionStateManager>(cfg.OutputGvcfFile, cfg.MinimumBaseCallQuality, cfg.SourceIsStitched, intervals.get(), 1000, cfg.Collapse,
-                                                     cfg.TrackedAnchorSize, cfg.SourceIsStitched && cfg.SourceIsCollapsed);
-        finder = std::make_unique<CandidateVariantFinder>(cfg.MinimumBaseCallQuality, cfg.MaxSizeMNV, cfg.MaxGapBetweenMNV, cfg.CallMNVs);  // Factory.cs:123-126
+                                                     cfg.TrackedAnchorSize, cfg.SourceIsStitched && cfg.SourceIsCollapsed, cfg.TrackAmpliconCounts());
+        finder = std::make_unique<CandidateVariantFinder>(cfg.MinimumBaseCallQuality, cfg.MaxSizeMNV, cfg.MaxGapBetweenMNV, cfg.CallMNVs, 5, cfg.TrackAmpliconCounts());  // Factory.cs:123-126
         caller = std::make_unique<AlleleCaller>(cfg, chrName, &chrSeq, intervals.get());
     }
     void AddForcedAllele(int pos, const std::string& ref, const std::string& alt) {  // SmallVariantCaller.cs:48-77 + Factory.SelectForcedAllele

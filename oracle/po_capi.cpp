@@ -27,6 +27,7 @@ void po_default_config(po_config* c) {
     c->exclude_mnvs_from_collapsing = d.ExcludeMNVsFromCollapsing; c->tracked_anchor_size = d.TrackedAnchorSize; c->output_gvcf = d.OutputGvcfFile;
     c->source_is_stitched = d.SourceIsStitched; c->source_is_collapsed = d.SourceIsCollapsed; c->apply_validation = 1;
     c->diploid_minor_vf = d.DiploidMinorVF; c->diploid_major_vf = d.DiploidMajorVF; c->diploid_sum_vf_multiallelic = d.DiploidSumVFforMultiAllelicSite; c->is_male = d.IsMale;
+    c->amplicon_bias_filter = d.AmpliconBiasFilterThreshold;
 }
 static Config FromC(const po_config* c) {
     Config d;
@@ -42,6 +43,7 @@ static Config FromC(const po_config* c) {
     d.ExcludeMNVsFromCollapsing = c->exclude_mnvs_from_collapsing; d.TrackedAnchorSize = c->tracked_anchor_size; d.OutputGvcfFile = c->output_gvcf;
     d.SourceIsStitched = c->source_is_stitched; d.SourceIsCollapsed = c->source_is_collapsed; d.ApplyValidation = c->apply_validation != 0;
     d.DiploidMinorVF = c->diploid_minor_vf; d.DiploidMajorVF = c->diploid_major_vf; d.DiploidSumVFforMultiAllelicSite = c->diploid_sum_vf_multiallelic; d.IsMale = c->is_male;
+    d.AmpliconBiasFilterThreshold = c->amplicon_bias_filter;
     return d;
 }
 static Read ToRead(const po_read* r) {
@@ -89,18 +91,22 @@ int po_caller_add_read_candidates_only(void* h, const po_read* r) {
 // summary byte (bit0 XV/XW present, bit1 duplex, bits 2-3 pair direction 1 FR / 2 RF / 0 other) turned back into the tags the reference reads;
 // xd_runs: optional [n][3] lengths of the F / S / R runs of the XD direction string over the CIGAR-expanded alignment (all zero: no XD tag).
 static int add_reads_soa_impl(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
-                              const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs, bool counts_only);
+                              const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs, bool counts_only, const int32_t* amplicon);
 int po_caller_add_reads_soa(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
                             const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs) {
-    return add_reads_soa_impl(h, n, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed, xd_runs, false);
+    return add_reads_soa_impl(h, n, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed, xd_runs, false, nullptr);
+}
+int po_caller_add_reads_soa_amplicons(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
+                                      const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs, const int32_t* amplicon) {
+    return add_reads_soa_impl(h, n, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed, xd_runs, false, amplicon);
 }
 // RegionStateManager.AddAlleleCounts only (nothing is called, no block is cleared): for po_dump_counts
 int po_caller_add_reads_soa_counts_only(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
                                         const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs) {
-    return add_reads_soa_impl(h, n, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed, xd_runs, true);
+    return add_reads_soa_impl(h, n, pos0, flag, cigar_off, cigar, seq_off, bases, quals, collapsed, xd_runs, true, nullptr);
 }
 static int add_reads_soa_impl(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
-                              const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs, bool counts_only) {
+                              const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs, bool counts_only, const int32_t* amplicon) {
     auto* s = (SmallVariantCaller*)h;
     try {
         for (int32_t i = 0; i < n; i++) {
@@ -120,7 +126,9 @@ static int add_reads_soa_impl(void* h, int32_t n, const int32_t* pos0, const uin
                 const int pd = (collapsed[i] >> 2) & 3;
                 r.xr = pd == 1 ? "FR" : (pd == 2 ? "RF" : "FF");
             }
-            if (counts_only) s->state->AddAlleleCounts(ToRead(&r)); else s->ProcessRead(ToRead(&r));
+            Read rd = ToRead(&r);
+            if (amplicon) rd.AmpliconName = amplicon[i];
+            if (counts_only) s->state->AddAlleleCounts(rd); else s->ProcessRead(rd);
         }
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
@@ -195,6 +203,14 @@ static void Fill(const CalledAllele& a, po_record* o) {
     o->cov_both_strands = a.StrandBiasResults.CovPresentOnBothStrands; o->forced = a.IsForcedToReport;
     for (int i = 0; i < 8; i++) { o->collapsed_mut[i] = a.ReadCollapsedCountsMut[i]; o->collapsed_total[i] = a.ReadCollapsedCountTotal[i]; }
     o->ref_len = (int)a.ReferenceAllele.size(); o->alt_len = (int)a.AlternateAllele.size();
+    o->has_amplicon_bias = a.HasAmpliconBiasResults; o->amplicon_bias_detected = a.AmpliconBiasDetected;
+    auto amp = [](const AmpliconCounts& c, int32_t* n, int32_t* names, int32_t* counts) {
+        *n = c.isNull ? -1 : 0;
+        for (int i = 0; i < MaxNumOverlappingAmplicons && !c.isNull; i++)
+            if (c.names[(size_t)i] >= 0) { names[*n] = c.names[(size_t)i]; counts[*n] = c.counts[(size_t)i]; (*n)++; }
+    };
+    amp(a.SupportByAmplicon, &o->n_amp_support, o->amp_support_names, o->amp_support_counts);
+    amp(a.CoverageByAmplicon, &o->n_amp_coverage, o->amp_coverage_names, o->amp_coverage_counts);
 }
 int po_caller_get_record(void* h, int32_t i, po_record* out) { GUARD(Fill(*((SmallVariantCaller*)h)->output.at((size_t)i), out)) }
 const char* po_caller_record_ref(void* h, int32_t i) { return ((SmallVariantCaller*)h)->output.at((size_t)i)->ReferenceAllele.c_str(); }

@@ -23,6 +23,7 @@ typedef struct po_config {
     int32_t apply_validation;   /* 1: VariantCallingParameters.Validate() derived values (what Program.Main does); 0: raw options as some reference tests build them */
     float diploid_minor_vf, diploid_major_vf, diploid_sum_vf_multiallelic;   /* DiploidSNVThresholdingParameters (VariantCallingParameters.cs:84) */
     int32_t is_male;            /* bool? IsMale: -1 = null (GenotypeCreator.GetPloidyForThisChr) */
+    float amplicon_bias_filter; /* float? AmpliconBiasFilterThreshold (-abfilter): < 0 = null; amplicon tracking follows it (Factory.ShouldTrackAmpliconCounts) */
 } po_config;
 
 typedef struct po_read {
@@ -53,6 +54,9 @@ typedef struct po_record {
     int32_t bias_acceptable, var_both_strands, cov_both_strands, forced;
     int32_t collapsed_mut[8], collapsed_total[8];
     int32_t ref_len, alt_len;
+    int32_t has_amplicon_bias, amplicon_bias_detected;   /* AmpliconBiasResults != null, .BiasDetected */
+    int32_t n_amp_support, amp_support_names[6], amp_support_counts[6];      /* SupportByAmplicon: filled slots in slot order (-1 arrays null) */
+    int32_t n_amp_coverage, amp_coverage_names[6], amp_coverage_counts[6];   /* CoverageByAmplicon */
 } po_record;
 
 void po_default_config(po_config* c);
@@ -69,6 +73,9 @@ int po_caller_add_reads_soa(void* h, int32_t n, const int32_t* pos0, const uint1
                             const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed /* or NULL */, const int32_t* xd_runs /* [n][3] or NULL */);
 int po_caller_add_reads_soa_counts_only(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
                                         const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs);
+/* as po_caller_add_reads_soa, plus the reads' amplicon names (XN tag) as ids, -1 = no tag */
+int po_caller_add_reads_soa_amplicons(void* h, int32_t n, const int32_t* pos0, const uint16_t* flag, const int64_t* cigar_off, const uint32_t* cigar, const int64_t* seq_off,
+                                      const uint8_t* bases, const uint8_t* quals, const uint8_t* collapsed, const int32_t* xd_runs, const int32_t* amplicon);
 int po_caller_add_pileup(void* h, int64_t n_loci, int32_t first_pos, const int64_t* off, const uint8_t* code, const uint8_t* qual, const uint8_t* anch, int32_t call_every);
 /* IAlleleSource.AddCandidates with one hand-built candidate (explicit candidates of the locus-major path) */
 int po_caller_add_candidate(void* h, int32_t type, int32_t pos, const char* ref, const char* alt, const int32_t support[3], const int32_t well_anchored[3],

@@ -9,8 +9,10 @@ struct CandidateVariantFinder {
     int minimumBaseCallQuality, maxLengthMnv, maxLengthInterveningRef;
     bool callMnvs;
     int wellAnchoredAnchorSize;
-    CandidateVariantFinder(int qualityCutoff, int maxMnv, int maxGap, bool mnvs, int wellAnchored = 5)
-        : minimumBaseCallQuality(qualityCutoff), maxLengthMnv(maxMnv), maxLengthInterveningRef(maxGap), callMnvs(mnvs), wellAnchoredAnchorSize(wellAnchored) {}
+    bool trackAmpliconCounts;   // :19-28
+    CandidateVariantFinder(int qualityCutoff, int maxMnv, int maxGap, bool mnvs, int wellAnchored = 5, bool trackAmplicons = false)
+        : minimumBaseCallQuality(qualityCutoff), maxLengthMnv(maxMnv), maxLengthInterveningRef(maxGap), callMnvs(mnvs), wellAnchoredAnchorSize(wellAnchored),
+          trackAmpliconCounts(trackAmplicons) {}
 
     // GetSupportDirection :396-445 (+ GetDeletionDirectionForStitchedRead :462-488)
     static DirectionType GetSupportDirection(const CandidateAllele& c, const Read& r, int startIndexInRead) {
@@ -94,6 +96,11 @@ struct CandidateVariantFinder {
             std::string readBases = r.Sequence.substr(variantStartIndexInRead, variantLengthSoFar);
             auto c = Create(referenceBases.size() > 1 ? Mnv : Snv, chrName, variantStartIndexInReference + 1, referenceBases, readBases, r,
                             variantStartIndexInRead, wellAnchoredAnchorSize);
+            if (trackAmpliconCounts && r.AmpliconName >= 0) {   // CreateMnvSnv -> SetAmpliconName :205-232 (SNVs and MNVs only; the indel calls are commented out :256,288)
+                c->SupportByAmplicon = AmpliconCounts::Empty();
+                c->SupportByAmplicon.names[0] = r.AmpliconName;
+                c->SupportByAmplicon.counts[0] = 1;
+            }
             c->OpenOnLeft = openLeft;
             c->OpenOnRight = openRight;
             out.push_back(c);

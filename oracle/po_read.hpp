@@ -30,6 +30,7 @@ struct Read {
     bool hasTagData = false;
     std::optional<std::string> XD, XR;
     std::optional<int> XV, XW;
+    int AmpliconName = -1;   // Read.GetAmpliconNameIfExists (Read.cs:483-486): the XN tag as an index into the caller's name dictionary, -1 = no tag
 
     int Position() const { return BamPosition + 1; }  // Read.cs:81
     uint32_t ReferenceSpan() const { uint32_t l = 0; for (auto& o : CigarData) if (o.IsReferenceSpan()) l += o.Length; return l; }

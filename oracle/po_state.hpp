@@ -96,6 +96,7 @@ struct IAlleleSource {
     virtual void AddGappedMnvRefCount(const std::map<int, int>& lookup) = 0;
     virtual int GetGappedMnvRefCount(int position) = 0;
     virtual bool ExpectStitchedReads() const = 0;
+    virtual AmpliconCounts GetCoverageByAmplicon(int position) = 0;   // IAlleleSource.cs:23
 };
 
 // RegionState.cs
@@ -107,6 +108,7 @@ struct RegionState {
     std::vector<int> gapped;            // [size]
     std::vector<std::vector<CandPtr>> cands;  // [size]
     std::vector<int> collapsed;         // [size][8]  (CollapsedRegionState)
+    std::vector<AmpliconCounts> amplicons;   // [size] _ampliconNamesPerPos / _ampliconCountsPerPos (:269-307)
     int MaxAlleleEndpoint = 0;          // survives Reset() — Initialize() never clears it (RegionState.cs:31,54-78)
 
     RegionState(int s, int e, int k) : StartPosition(s), EndPosition(e), K(k), NA(2 * k + 1) { Initialize(); }
@@ -118,6 +120,22 @@ struct RegionState {
         gapped.assign(n, 0);
         cands.assign(n, {});
         collapsed.assign(n * 8, 0);
+        amplicons.assign(n, AmpliconCounts());
+    }
+    void AddAmpliconCount(int p, int name) {   // :269-307
+        if (name < 0 || !IsPositionInRegion(p)) return;
+        AmpliconCounts& a = amplicons[(size_t)(p - StartPosition)];
+        if (a.isNull) a = AmpliconCounts::Empty();
+        a.Add(name, 1);
+    }
+    AmpliconCounts GetCountsByAmpliconForPosition(int p) const {   // :325-352: the filled slots, in slot order
+        if (!IsPositionInRegion(p)) throw std::invalid_argument("Position is not in region");
+        const AmpliconCounts& a = amplicons[(size_t)(p - StartPosition)];
+        AmpliconCounts out = AmpliconCounts::Empty();
+        int k = 0;
+        for (int i = 0; i < MaxNumOverlappingAmplicons; i++)
+            if (!a.isNull && a.names[(size_t)i] >= 0) { out.names[(size_t)k] = a.names[(size_t)i]; out.counts[(size_t)k] = a.counts[(size_t)i]; k++; }
+        return out;
     }
     void Reset(int s, int e) { StartPosition = s; EndPosition = e; Initialize(); }  // :73-78
     bool IsPositionInRegion(int p) const { return p >= StartPosition && p <= EndPosition; }
@@ -152,7 +170,7 @@ struct RegionState {
         }
         if (otherEnd > MaxAlleleEndpoint) MaxAlleleEndpoint = otherEnd;
     }
-    void AddCandidate(const CandPtr& nc, bool trackOpenEnded) {  // :94-174
+    void AddCandidate(const CandPtr& nc, bool trackOpenEnded, bool trackAmplicon = false) {  // :94-174
         if (nc->Type == Reference) throw std::invalid_argument("reference candidates are not tracked");
         if (!IsPositionInRegion(nc->ReferencePosition)) throw std::invalid_argument("Unable to add candidate to region");
         auto& existing = cands[nc->ReferencePosition - StartPosition];
@@ -165,6 +183,18 @@ struct RegionState {
             for (int i = 0; i < 3; i++) found->SupportByDirection[i] += nc->SupportByDirection[i];
             for (int i = 0; i < 3; i++) found->WellAnchoredSupportByDirection[i] += nc->WellAnchoredSupportByDirection[i];
             for (int i = 0; i < 8; i++) found->ReadCollapsedCountsMut[i] += nc->ReadCollapsedCountsMut[i];
+            if (trackAmplicon && !nc->SupportByAmplicon.isNull) {   // :138-170 (every merged occurrence counts 1, whatever the new candidate's own count says)
+                for (int i = 0; i < MaxNumOverlappingAmplicons; i++) {
+                    const int name = nc->SupportByAmplicon.names[(size_t)i];
+                    if (name < 0) continue;
+                    if (found->SupportByAmplicon.isNull) found->SupportByAmplicon = AmpliconCounts::Empty();
+                    auto ix = found->SupportByAmplicon.Index(name);
+                    if (ix.first == -1) {
+                        if (ix.second < 0) throw std::out_of_range("Index was outside the bounds of the array.");
+                        found->SupportByAmplicon.names[(size_t)ix.second] = name; found->SupportByAmplicon.counts[(size_t)ix.second] = 1;
+                    } else found->SupportByAmplicon.counts[(size_t)ix.first]++;
+                }
+            }
         }
         UpdateMaxPosition(*nc);
     }
@@ -242,11 +272,17 @@ struct RegionStateManager : IAlleleSource {
     bool trackOpenEnded;
     int numAnchorTypes;
     bool expectStitched, expectCollapsed;
+    bool trackAmpliconCounts = false;   // RegionStateManager.cs:25,40,52
 
     RegionStateManager(bool includeRef, int minBQ, bool expectStitchedReads, ChrIntervalSet* intervals, int blockSize, bool trackOpen,
-                       int anchorTypes, bool expectCollapsedReads)
+                       int anchorTypes, bool expectCollapsedReads, bool trackAmplicons = false)
         : regionSize(blockSize), minBasecallQuality(minBQ), includeRefAlleles(includeRef), intervalSet(intervals), trackOpenEnded(trackOpen),
-          numAnchorTypes(anchorTypes), expectStitched(expectStitchedReads), expectCollapsed(expectCollapsedReads) {}
+          numAnchorTypes(anchorTypes), expectStitched(expectStitchedReads), expectCollapsed(expectCollapsedReads), trackAmpliconCounts(trackAmplicons) {}
+    AmpliconCounts GetCoverageByAmplicon(int position) override {   // :228-232 (a position without a block dereferences null in the reference)
+        RegionState* region = GetBlock(position, false);
+        if (!region) throw std::runtime_error("Object reference not set to an instance of an object.");
+        return region->GetCountsByAmpliconForPosition(position);
+    }
     int WellAnchoredIndex() const { return numAnchorTypes; }
     int NumAnchorIndexes() const { return numAnchorTypes * 2 + 1; }
     bool ExpectStitchedReads() const override { return expectStitched; }
@@ -269,7 +305,7 @@ struct RegionStateManager : IAlleleSource {
         return lastAccessedBlock;
     }
     void AddCandidates(const std::vector<CandPtr>& cs) override {  // :55-66
-        for (auto& c : cs) GetBlock(c->ReferencePosition)->AddCandidate(c, trackOpenEnded);
+        for (auto& c : cs) GetBlock(c->ReferencePosition)->AddCandidate(c, trackOpenEnded, trackAmpliconCounts);
     }
     int GetAnchorType(int alignmentEndPosition, int basePosition, int alignmentStartPosition) const {  // :83-116
         int leftAnchor = basePosition - alignmentStartPosition;
@@ -329,7 +365,10 @@ struct RegionStateManager : IAlleleSource {
             AlleleType alleleType = GetAlleleType(alignment.Sequence[i]);
             if (alignment.Qualities[i] < minBasecallQuality) alleleType = AT_N;
             GetBlock(position)->AddAlleleCount(position, alleleType, directionType, anchorType);
-            if (alleleType != AT_N) AddCollapsedReadCount(position, alignment, directionType);
+            if (alleleType != AT_N) {
+                AddCollapsedReadCount(position, alignment, directionType);
+                if (trackAmpliconCounts) GetBlock(position)->AddAmpliconCount(position, alignment.AmpliconName);   // :188, :407-416
+            }
             // Math.Pow(10, -1 * (int)q / 10f): int / float -> float exponent (:191)
             float expo = (float)(-1 * (int)alignment.Qualities[i]) / 10.0f;
             GetBlock(position)->AddBaseQualites(position, alleleType, directionType, std::pow(10.0, (double)expo), anchorType);

@@ -69,6 +69,33 @@ struct BiasResults {
 };
 
 // Models/Alleles/CandidateAllele.cs
+// AmpliconCounts (src/lib/Pisces.Domain/Models/AmpliconCounts.cs:34-110): names are small integers (the XN dictionary), -1 = null slot; isNull: the
+// AmpliconNames array itself is null. Slots are filled in first-seen order, Constants.MaxNumOverlappingAmplicons = 6 of them (Constants.cs:54-62).
+constexpr int MaxNumOverlappingAmplicons = 6;
+struct AmpliconCounts {
+    bool isNull = true;
+    std::array<int, MaxNumOverlappingAmplicons> names{{-1, -1, -1, -1, -1, -1}};
+    std::array<int, MaxNumOverlappingAmplicons> counts{{0, 0, 0, 0, 0, 0}};
+    static AmpliconCounts Empty() { AmpliconCounts a; a.isNull = false; return a; }
+    // GetAmpliconNameIndex (:48-66): (index of the name, first empty slot), -1 where there is none
+    std::pair<int, int> Index(int name) const {
+        int firstEmpty = -1;
+        for (int i = 0; i < MaxNumOverlappingAmplicons; i++) {
+            if (names[(size_t)i] == name) return {i, -1};
+            if (names[(size_t)i] < 0 && firstEmpty == -1) firstEmpty = i;
+        }
+        return {-1, firstEmpty};
+    }
+    void Add(int name, int count) {   // the merge of RegionState.AddCandidate (:138-170) / CandidateAllele.AddSupport (:82-103) / RegionState.AddAmpliconCount (:269-307)
+        auto ix = Index(name);
+        if (ix.first > -1) counts[(size_t)ix.first] += count;
+        else {
+            if (ix.second < 0) throw std::out_of_range("Index was outside the bounds of the array.");   // more than 6 overlapping amplicons: the reference throws
+            names[(size_t)ix.second] = name; counts[(size_t)ix.second] += count;
+        }
+    }
+};
+
 struct CandidateAllele {
     std::string Chromosome;
     int ReferencePosition = 0;
@@ -79,6 +106,7 @@ struct CandidateAllele {
     std::array<int, 8> ReadCollapsedCountsMut{{0, 0, 0, 0, 0, 0, 0, 0}};
     bool OpenOnRight = false, OpenOnLeft = false, IsKnown = false, IsForcedAllele = false;
     float Frequency = 0;
+    AmpliconCounts SupportByAmplicon;   // CandidateAllele.cs:23
     CandidateAllele() {}
     CandidateAllele(const std::string& chr, int coord, const std::string& ref, const std::string& alt, AlleleCategory t)
         : Chromosome(chr), ReferencePosition(coord), ReferenceAllele(ref), AlternateAllele(alt), Type(t) {
@@ -96,9 +124,15 @@ struct CandidateAllele {
                o.Chromosome == Chromosome && o.ReferenceAllele == ReferenceAllele;
     }
     int Length() const;  // BaseAllele.Length
-    void AddSupport(const CandidateAllele& from) {  // :74-79 (amplicon part out of scope)
+    void AddSupport(const CandidateAllele& from) {  // :74-106
         for (int i = 0; i < 3; i++) SupportByDirection[i] += from.SupportByDirection[i];
         for (int i = 0; i < 3; i++) WellAnchoredSupportByDirection[i] += from.WellAnchoredSupportByDirection[i];
+        if (!from.SupportByAmplicon.isNull) {
+            if (SupportByAmplicon.isNull) SupportByAmplicon = AmpliconCounts::Empty();
+            // (:89-103 walks all six slots of the source, null names included: a null name "matches" the first empty slot of the target and adds 0)
+            for (int i = 0; i < MaxNumOverlappingAmplicons; i++)
+                if (from.SupportByAmplicon.names[(size_t)i] >= 0) SupportByAmplicon.Add(from.SupportByAmplicon.names[(size_t)i], from.SupportByAmplicon.counts[(size_t)i]);
+        }
     }
 };
 inline int AlleleLength(AlleleCategory t, const std::string& ref, const std::string& alt) {  // BaseAllele.cs:24-43
@@ -137,6 +171,8 @@ struct CalledAllele {
     int WellAnchoredSupport = 0;
     double UnanchoredCoverageWeight = 0;
     int ReferenceSupport = 0;
+    AmpliconCounts SupportByAmplicon, CoverageByAmplicon;   // CalledAllele.cs:35-36
+    bool AmpliconBiasDetected = false, HasAmpliconBiasResults = false;   // AmpliconBiasResults != null / .BiasDetected (CalledAllele.cs:20)
 
     CalledAllele() {}
     explicit CalledAllele(AlleleCategory t) : Type(t) { genotype = (t == Reference) ? HomozygousRef : HeterozygousAltRef; }  // :148-161
@@ -177,6 +213,7 @@ inline CalledAllele MapToCalled(const CandidateAllele& c) {
     a.SupportByDirection = c.SupportByDirection;
     a.WellAnchoredSupportByDirection = c.WellAnchoredSupportByDirection;
     if (c.Type != Reference) a.ReadCollapsedCountsMut = c.ReadCollapsedCountsMut;
+    if (!c.SupportByAmplicon.isNull) a.SupportByAmplicon = c.SupportByAmplicon;   // AlleleHelper.Map :72-82
     return a;
 }
 inline CandidateAllele MapToCandidate(const CalledAllele& a) {
@@ -212,6 +249,8 @@ struct Config {
     int ploidy = PM_Somatic;
     float DiploidMinorVF = 0.20f, DiploidMajorVF = 0.70f, DiploidSumVFforMultiAllelicSite = 0.80f;   // DiploidSNVThresholdingParameters (:84)
     int IsMale = -1;                    // bool? IsMale: -1 = null
+    float AmpliconBiasFilterThreshold = -1;   // float? (VariantCallingParameters.cs:102-107): < 0 = null; tracking follows it (Factory.ShouldTrackAmpliconCounts :51-54)
+    bool TrackAmpliconCounts() const { return AmpliconBiasFilterThreshold >= 0; }
     int ForcedNoiseLevel = -1;          // NL = ForcedNoiseLevel == -1 ? MinimumBaseCallQuality : ForcedNoiseLevel  (:109-118)
     int noiseModel = NM_Flat;
     float StrandBiasAcceptanceCriteria = 0.5f;

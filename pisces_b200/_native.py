@@ -21,7 +21,7 @@ class Config(C.Structure):
         ("max_size_mnv", C.c_int32), ("max_gap_mnv", C.c_int32), ("collapse_freq_threshold", C.c_float),
         ("collapse_freq_ratio_threshold", C.c_float), ("exclude_mnvs_from_collapsing", C.c_int32), ("skip_validation", C.c_int32),
         ("diploid_minor_vf", C.c_float), ("diploid_major_vf", C.c_float), ("diploid_sum_vf_multiallelic", C.c_float), ("is_male", C.c_int32),
-        ("reserved", C.c_int32 * 2)]
+        ("amplicon_bias_filter", C.c_float), ("reserved", C.c_int32 * 2)]
 
 
 class PileupCsr(C.Structure):
@@ -32,13 +32,14 @@ class PileupCsr(C.Structure):
 
 class ReadBatch(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("pos0", C.c_void_p), ("flag", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p),
-                ("seq_off", C.c_void_p), ("bases", C.c_void_p), ("quals", C.c_void_p), ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p)]
+                ("seq_off", C.c_void_p), ("bases", C.c_void_p), ("quals", C.c_void_p), ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p),
+                ("amplicon", C.c_void_p)]
 
 
 class PackedReadBatch(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("pos0", C.c_void_p), ("flag", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("seq_off", C.c_void_p),
                 ("seq", C.c_void_p), ("n_exceptions", C.c_int64), ("exc_index", C.c_void_p), ("exc_base", C.c_void_p), ("exc_qual", C.c_void_p),
-                ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p)]
+                ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p), ("amplicon", C.c_void_p)]
 
 
 class Shard(C.Structure):

@@ -77,6 +77,7 @@ extern "C" void pb2_default_config(pb2_config* c) {
     c->collapse_freq_threshold = 0.0f; c->collapse_freq_ratio_threshold = 0.5f; c->exclude_mnvs_from_collapsing = 0;
     c->diploid_minor_vf = 0.20f; c->diploid_major_vf = 0.70f; c->diploid_sum_vf_multiallelic = 0.80f;   // VariantCallingParameters.cs:84
     c->is_male = -1;
+    c->amplicon_bias_filter = -1.0f;
 }
 
 extern "C" int pb2_device_count(void) {
@@ -177,7 +178,7 @@ extern "C" int pb2_create(const pb2_config* cfg, pb2_handle** out) {
         if ((e = cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return bail("cudaMemPoolSetAttribute", e);
     }
     if ((e = cudaMalloc(&h->d_tile_counter, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaHostAlloc(&h->h_counters, sizeof(unsigned long long) * 4, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc(&h->h_counters, sizeof(unsigned long long) * 5, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
     {
         h->q_table_max = std::min(std::max(cfg->max_variant_qscore, 0), 1023);
         std::vector<double> t((size_t)h->q_table_max + 1);
@@ -249,7 +250,7 @@ static void release_resident_graph(pb2_handle* h) {
 
 static void free_segment(pb2_handle* h, Segment& s) {
     void* ptrs[] = {s.code, s.anch, s.ref_records, s.var_records, s.pending, s.depth, s.pad, s.tile_base, s.ref_base, s.positions, s.ref_valid, s.exc_entries, s.counters,
-                    s.nib, s.nib_tile_base, s.nib_store, s.nib_depth, s.pv_data, s.pv_row_meta, s.pv_tile_row0, s.pv_cls_end};
+                    s.nib, s.nib_tile_base, s.nib_store, s.nib_depth, s.pv_data, s.pv_row_meta, s.pv_tile_row0, s.pv_cls_end, s.pv_row_amp};
     for (void* p : ptrs) pool_free(h, p);
     s = Segment();
 }
@@ -409,8 +410,8 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
     // the side list of flagged entries is filled by the scatter below (counters[3]; counters[0..2] are reset by every run)
     s.exc_capacity = 1 << 20;
     CU(h, pool_alloc_t(h, &s.exc_entries, 2 * (size_t)s.exc_capacity));
-    CU(h, pool_alloc_t(h, &s.counters, 4));
-    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
+    CU(h, pool_alloc_t(h, &s.counters, 5));   // variants, -, pending, flagged entries, amplicon status
+    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 5, st));
     h->total_launches += 3;
 
     // the interleaving scatter
@@ -557,6 +558,16 @@ static int push_common(pb2_handle* h, const pb2_pileup_csr* p, bool device_ptrs)
 extern "C" int pb2_push_pileup(pb2_handle* h, const pb2_pileup_csr* p) { return push_common(h, p, false); }
 extern "C" int pb2_push_pileup_device(pb2_handle* h, const pb2_pileup_csr* p) { return push_common(h, p, true); }
 
+static const char* const kTooManyAmplicons = "Index was outside the bounds of the array.";   // a seventh amplicon name at one position (RegionState.cs:293-297)
+// AmpliconBiasCalculator.Compute over the segment's variant stream (count-based SNVs, and explicit ones appended by the resident explicit pass)
+static int amplicon_pass(pb2_handle* h, Segment& s, cudaStream_t st) {
+    if (s.pv_row_amp == nullptr || h->cfg.amplicon_bias_filter < 0) return PB2_OK;
+    CU(h, cudaMemsetAsync(s.counters + 4, 0, sizeof(unsigned long long), st));
+    CU(h, launch_pvert_amplicon_bias(pvert_view(s), s.pv_row_amp, s.var_records, s.counters, 0, s.var_capacity, nullptr, h->cfg.amplicon_bias_filter, h->dcfg.min_bq,
+                                     reinterpret_cast<int*>(s.counters + 4), h->num_sms, st));
+    h->total_launches += 1;
+    return PB2_OK;
+}
 // enqueue: counters reset, hot kernel (+ overflow scorer) between the timing events. finish: counters back, one synchronize, bookkeeping.
 static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out, const int32_t* d_gapped, bool reset_counters = true,
                            bool capturing = false) {
@@ -584,7 +595,7 @@ static int enqueue_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32
 static int finish_segment(pb2_handle* h, Segment& s, bool counters_already_copied = false) {
     cudaStream_t st = h->stream;
     unsigned long long* cnt4 = h->h_counters;
-    if (!counters_already_copied) CU(h, cudaMemcpyAsync(cnt4, s.counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    if (!counters_already_copied) CU(h, cudaMemcpyAsync(cnt4, s.counters, sizeof(unsigned long long) * 5, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     float ms = 0;
     CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -597,10 +608,12 @@ static int finish_segment(pb2_handle* h, Segment& s, bool counters_already_copie
     s.called = true;
     if ((int64_t)cnt[0] > s.var_capacity) return fail(h, PB2_ERR_NOMEM, "variant record buffer overflow");
     if ((int64_t)cnt[1] > s.exc_capacity) return fail(h, PB2_ERR_NOMEM, "open-ended candidate side list overflow");
+    if (s.pv_row_amp != nullptr && cnt4[4] != 0) return fail(h, PB2_ERR_ARG, kTooManyAmplicons);
     return PB2_OK;
 }
 static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out, const int32_t* d_gapped = nullptr) {
-    const int rc = enqueue_segment(h, s, counts_out, collapsed_out, d_gapped);
+    int rc = enqueue_segment(h, s, counts_out, collapsed_out, d_gapped);
+    if (rc == PB2_OK) rc = amplicon_pass(h, s, h->stream);
     return rc != PB2_OK ? rc : finish_segment(h, s);
 }
 
@@ -621,12 +634,12 @@ static cudaError_t grow(pb2_handle* h, GrowBuf<T>& b, size_t need, size_t keep) 
 static void clear_reads(pb2_handle* h) {
     DeviceReads& R = h->reads;
     R.n = R.n_cigar = R.n_seq = 0;
-    R.has_dirs = R.has_collapsed = false;
+    R.has_dirs = R.has_collapsed = R.has_amplicon = false;
     R.min_start = INT32_MAX; R.max_end = 0; R.last_pos0 = -1;
 }
 static void free_reads(pb2_handle* h) {
     DeviceReads& R = h->reads;
-    void* ptrs[] = {R.pos0.p, R.end_pos.p, R.flag.p, R.cigar_off.p, R.seq_off.p, R.cigar.p, R.bases.p, R.quals.p, R.base_dirs.p, R.collapsed.p, R.slots.p};
+    void* ptrs[] = {R.pos0.p, R.end_pos.p, R.flag.p, R.cigar_off.p, R.seq_off.p, R.cigar.p, R.bases.p, R.quals.p, R.base_dirs.p, R.collapsed.p, R.slots.p, R.amplicon.p};
     for (void* p : ptrs) pool_free(h, p);
     h->reads = DeviceReads();
 }
@@ -677,6 +690,10 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
     // per-base directions / collapsed summaries: optional per batch. Once any batch carried them the store holds them for every read (a stitched or
     // collapsed BAM streamed in small batches mixes tagged and untagged reads): reads pushed without get the flag-derived defaults.
     const bool want_dirs = R.has_dirs || b->base_dirs != nullptr, want_coll = R.has_collapsed || b->collapsed != nullptr;
+    // amplicon names: tracked only with a threshold (Factory.ShouldTrackAmpliconCounts); reads pushed without ids have no XN tag (-1)
+    const bool want_amp = h->cfg.amplicon_bias_filter >= 0 && (R.has_amplicon || b->amplicon != nullptr);
+    if (want_amp && h->cfg.call_mnvs && b->amplicon != nullptr)
+        return fail(h, PB2_ERR_UNSUPPORTED, "amplicon names together with call_mnvs: SupportByAmplicon of MNV-derived SNVs is not built (DESIGN.md 9)");
     CU(h, grow(h, R.pos0, (size_t)(first + nb), (size_t)first));
     CU(h, grow(h, R.end_pos, (size_t)(first + nb), (size_t)first));
     CU(h, grow(h, R.flag, (size_t)(first + nb), (size_t)first));
@@ -693,6 +710,10 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
     if (want_coll) {
         CU(h, grow(h, R.collapsed, (size_t)(first + nb), R.has_collapsed ? (size_t)first : 0));
         if (!R.has_collapsed && first > 0) CU(h, cudaMemsetAsync(R.collapsed.p, 0, (size_t)first, st));
+    }
+    if (want_amp) {
+        CU(h, grow(h, R.amplicon, (size_t)(first + nb), R.has_amplicon ? (size_t)first : 0));
+        if (!R.has_amplicon && first > 0) CU(h, cudaMemsetAsync(R.amplicon.p, 0xff, sizeof(int32_t) * (size_t)first, st));
     }
     if (first == 0) { CU(h, cudaMemsetAsync(R.cigar_off.p, 0, sizeof(int64_t), st)); CU(h, cudaMemsetAsync(R.seq_off.p, 0, sizeof(int64_t), st)); }
     const cudaMemcpyKind k = cudaMemcpyHostToDevice;
@@ -730,6 +751,10 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
         if (b->collapsed) CU(h, cudaMemcpyAsync(R.collapsed.p + first, b->collapsed, (size_t)nb, k, st));
         else CU(h, cudaMemsetAsync(R.collapsed.p + first, 0, (size_t)nb, st));
     }
+    if (want_amp) {
+        if (b->amplicon) CU(h, cudaMemcpyAsync(R.amplicon.p + first, b->amplicon, sizeof(int32_t) * (size_t)nb, k, st));
+        else CU(h, cudaMemsetAsync(R.amplicon.p + first, 0xff, sizeof(int32_t) * (size_t)nb, st));
+    }
     // ingest: offsets rebased, Read.EndPosition, validation, the batch triggers of SmallVariantCaller.Execute
     IngestStatus* d_status = nullptr;
     int2* d_trig = nullptr;
@@ -741,7 +766,8 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
     init.min_start = INT32_MAX;
     CU(h, cudaMemcpyAsync(d_status, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     R.n = first + nb;
-    R.has_dirs = want_dirs; R.has_collapsed = want_coll;
+    const bool had_amp = R.has_amplicon;
+    R.has_dirs = want_dirs; R.has_collapsed = want_coll; R.has_amplicon = want_amp;
     ReadsView rv = R.view();
     CU(h, launch_reads_ingest(rv, (int32_t)first, R.n_cigar - c_lo, R.n_seq - s_lo, R.cigar_off.p, R.seq_off.p, R.end_pos.p, h->push_last_key, d_trig, trig_cap, d_status, h->cfg.expect_collapsed, st));
     if (want_dirs && !b->base_dirs) dirs_from_flags_kernel<<<(unsigned)nb, 64, 0, st>>>(R.flag.p, R.seq_off.p, first, first + nb, R.base_dirs.p);
@@ -751,7 +777,7 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
     CU(h, cudaStreamSynchronize(st));   // the caller's buffers are consumed
     tr.mark("h2d+ingest");
     pool_free(h, d_seq); pool_free(h, d_exc_index); pool_free(h, d_exc_base); pool_free(h, d_exc_qual);
-    auto rollback = [&]() { R.n = first; pool_free(h, d_status); pool_free(h, d_trig); };
+    auto rollback = [&]() { R.n = first; R.has_amplicon = had_amp && first > 0; pool_free(h, d_status); pool_free(h, d_trig); };
     if (status.error) {
         rollback();
         switch (status.error) {
@@ -790,7 +816,7 @@ extern "C" int pb2_push_reads_packed(pb2_handle* h, const pb2_packed_read_batch*
     pb2_read_batch b;
     memset(&b, 0, sizeof(b));
     b.n_reads = p->n_reads; b.pos0 = p->pos0; b.flag = p->flag; b.cigar_off = p->cigar_off; b.cigar = p->cigar; b.seq_off = p->seq_off;
-    b.base_dirs = p->base_dirs; b.collapsed = p->collapsed;
+    b.base_dirs = p->base_dirs; b.collapsed = p->collapsed; b.amplicon = p->amplicon;
     if (p->n_reads > 0 && !p->seq) return fail(h, PB2_ERR_ARG, "pb2_push_reads_packed: null array");
     return push_reads_impl(h, &b, p->seq, p->n_exceptions, p->exc_index, p->exc_base, p->exc_qual);
 }
@@ -966,6 +992,10 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     ReadsView rv = R.view();
     RegionView rg{lo, hi, d_index, h->d_chr, h->chr_len, h->dcfg.min_bq, h->cfg.expect_collapsed, d_index_ge, s.positions, n_loci};
     if (!pvert_eligible(h)) {
+        if (rv.amplicon != nullptr) {
+            pool_free(h, d_index); pool_free(h, d_index_ge); pool_free(h, s.positions);
+            return fail(h, PB2_ERR_UNSUPPORTED, "amplicon names need the PVERT pileup: minimum base-call quality in [2, 63], flat noise model, no quality sums");
+        }
         // quality sums / unusual quality bars: the PTILE32 form, through the locus-major entry list (reads_count / reads_emit -> push_common)
         unsigned int *d_depth = nullptr, *d_cursor = nullptr;
         int64_t *d_off = nullptr, *d_depth64 = nullptr;
@@ -1039,16 +1069,20 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     const size_t data_bytes = (size_t)std::max<int64_t>(s.pv_rows, 32) * 32;
     CU(h, pool_alloc(h, (void**)&s.pv_data, data_bytes + 4096));
     CU(h, pool_alloc_t(h, &s.pv_row_meta, (size_t)std::max<int64_t>(s.pv_rows, 32)));
+    if (rv.amplicon != nullptr) {   // amplicon tracking: the name id of every row's read (padding rows: none)
+        CU(h, pool_alloc_t(h, &s.pv_row_amp, (size_t)std::max<int64_t>(s.pv_rows, 32)));
+        CU(h, cudaMemsetAsync(s.pv_row_amp, 0xff, sizeof(int32_t) * (size_t)std::max<int64_t>(s.pv_rows, 32), st));
+    }
     CU(h, cudaMemsetAsync(s.pv_data, 0, data_bytes + 4096, st));
     s.exc_capacity = std::max<int64_t>(1 << 20, R.n_seq / 128);
     CU(h, pool_alloc_t(h, &s.exc_entries, 2 * (size_t)s.exc_capacity));
-    CU(h, pool_alloc_t(h, &s.counters, 4));
-    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 4, st));
+    CU(h, pool_alloc_t(h, &s.counters, 5));   // variants, -, pending, flagged entries, amplicon status
+    CU(h, cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * 5, st));
     uint8_t* d_ref_slot = nullptr;
     CU(h, pool_alloc_t(h, &s.ref_base, (size_t)n_loci));
     CU(h, pool_alloc_t(h, &d_ref_slot, (size_t)s.n_tiles * 32));
     CU(h, launch_pvert_ref_bases(h->d_chr, h->chr_len, s.positions, lo, n_loci, s.ref_base, d_ref_slot, st));
-    CU(h, launch_pvert_fill(rv, rg, R.end_pos.p, nc, s.pv_tile_row0, s.pv_cls_end, d_cursor, s.pv_data, s.pv_row_meta, s.exc_entries, s.counters + 3, s.exc_capacity, d_ref_slot,
+    CU(h, launch_pvert_fill(rv, rg, R.end_pos.p, nc, s.pv_tile_row0, s.pv_cls_end, d_cursor, s.pv_data, s.pv_row_meta, s.pv_row_amp, s.exc_entries, s.counters + 3, s.exc_capacity, d_ref_slot,
                             d_complex, n_complex, st));
     CU(h, launch_pvert_transpose(s.pv_data, s.pv_rows / 32, st));
     pool_free(h, d_ref_slot);
@@ -1103,7 +1137,8 @@ static int resident_step_enqueue(pb2_handle* h, Segment& s, bool with_explicit, 
         const int rc2 = explicit_prune_resident(h, s);
         if (rc2 != PB2_OK) return rc2;
     }
-    CU(h, cudaMemcpyAsync(h->h_counters, s.counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    { const int rc3 = amplicon_pass(h, s, st); if (rc3 != PB2_OK) return rc3; }
+    CU(h, cudaMemcpyAsync(h->h_counters, s.counters, sizeof(unsigned long long) * 5, cudaMemcpyDeviceToHost, st));
     return PB2_OK;
 }
 // ---- the job's record sink (multi-GPU gather): [n_slots int64 counts | n_slots x slot_records records]; a step's variant stream lands in slot step % n_slots
@@ -1219,6 +1254,7 @@ extern "C" int pb2_resident_sync(pb2_handle* h, int64_t* n_records_last) {
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->hot_ms += ms * 1;   // (the last step's kernel time; the steps before are counted as launches)
         if (n_records_last) *n_records_last = (int64_t)s.h_var_count;
         if ((int64_t)s.h_var_count > s.var_capacity) return fail(h, PB2_ERR_NOMEM, "variant record buffer overflow");
+        if (s.pv_row_amp != nullptr && h->h_counters[4] != 0) return fail(h, PB2_ERR_ARG, kTooManyAmplicons);
     }
     return PB2_OK;
 }
@@ -1238,6 +1274,7 @@ extern "C" int pb2_call_resident(pb2_handle* h, int64_t* n_records) {
         if (!explicit_resident_ready(h)) {   // first call: plan building, everything in order on the handle stream
             rc = enqueue_segment(h, s, nullptr, nullptr, nullptr);
             if (rc == PB2_OK) rc = explicit_call_resident(h, s, h->stream);
+            if (rc == PB2_OK) rc = amplicon_pass(h, s, h->stream);
         } else {
             rc = resident_step(h, s, true);
             if (rc != PB2_OK) return rc;
@@ -1732,13 +1769,14 @@ static int compact_reads(pb2_handle* h, int32_t cleared_to) {
         h->reads.last_pos0 = last;
     } else if (totals[0] < R.n) {
         DeviceReads K;
-        K.has_dirs = R.has_dirs; K.has_collapsed = R.has_collapsed;
+        K.has_dirs = R.has_dirs; K.has_collapsed = R.has_collapsed; K.has_amplicon = R.has_amplicon;
         const size_t kn = (size_t)totals[0], kc = (size_t)totals[1], ks = (size_t)totals[2];
         CU(h, grow(h, K.pos0, kn, 0)); CU(h, grow(h, K.end_pos, kn, 0)); CU(h, grow(h, K.flag, kn, 0));
         CU(h, grow(h, K.cigar_off, kn + 1, 0)); CU(h, grow(h, K.seq_off, kn + 1, 0));
         CU(h, grow(h, K.cigar, std::max<size_t>(kc, 1), 0)); CU(h, grow(h, K.bases, std::max<size_t>(ks, 1), 0)); CU(h, grow(h, K.quals, std::max<size_t>(ks, 1), 0));
         if (R.has_dirs) CU(h, grow(h, K.base_dirs, std::max<size_t>(ks, 1), 0));
         if (R.has_collapsed) CU(h, grow(h, K.collapsed, kn, 0));
+        if (R.has_amplicon) CU(h, grow(h, K.amplicon, kn, 0));
         CU(h, grow(h, K.slots, ks + 32, 0));
         ReadsCompactArgs a;
         a.n = R.n; a.new_index = ni; a.new_cigar = nc; a.new_seq = ns;
@@ -1747,6 +1785,7 @@ static int compact_reads(pb2_handle* h, int32_t cleared_to) {
         a.o_pos0 = K.pos0.p; a.o_end_pos = K.end_pos.p; a.o_flag = K.flag.p; a.o_cigar_off = K.cigar_off.p; a.o_cigar = K.cigar.p; a.o_seq_off = K.seq_off.p;
         a.o_bases = K.bases.p; a.o_quals = K.quals.p; a.o_base_dirs = K.base_dirs.p; a.o_collapsed = K.collapsed.p;
         a.slots = R.slots.p + 16; a.o_slots = K.slots.p + 16;
+        a.amplicon = R.has_amplicon ? R.amplicon.p : nullptr; a.o_amplicon = K.amplicon.p;
         CU(h, launch_reads_compact(a, st));
         K.n = totals[0]; K.n_cigar = totals[1]; K.n_seq = totals[2];
         K.min_start = R.min_start; K.max_end = R.max_end; K.last_pos0 = R.last_pos0;

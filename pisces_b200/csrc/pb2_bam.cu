@@ -324,6 +324,8 @@ static int bam_next_batch_impl(pb2_bam_reader* r, const pb2_bam_filter* flt, int
     (void)any_dirs; (void)any_coll;
     batch->base_dirs = r->base_dirs.data();
     batch->collapsed = r->collapsed.data();
+    // amplicon name ids once the file has shown an XN tag (a file without the tag never asks the caller to track amplicons)
+    batch->amplicon = r->amplicon_names.empty() ? nullptr : r->amplicon_id.data();
     if (ref_id_out) *ref_id_out = batch_ref == -2 ? -1 : batch_ref;
     if (n_skipped) *n_skipped = skipped;
     return PB2_OK;

@@ -259,6 +259,24 @@ int score_pieces(BatchCtx& ctx, const std::vector<Piece*>& pieces, std::vector<u
     }
     CUX(h, launch_score_candidates(a, h->dcfg, st));
     h->total_launches += 1;
+    // AmpliconBiasCalculator.Compute for the SNV candidates among them (positions whose SNVs were made explicit): per-amplicon tallies from the pileup of
+    // the segment that holds the position. (In append mode the pass over the segment's variant stream covers them: amplicon_pass, pb2_api.cu.)
+    int amp_status = 0;
+    if (!append_seg && h->cfg.amplicon_bias_filter >= 0) {
+        for (auto& seg : h->segs) {
+            if (seg.pv_row_amp == nullptr) continue;
+            int* d_status = reinterpret_cast<int*>(seg.counters + 4);
+            CUX(h, cudaMemsetAsync(d_status, 0, sizeof(int), st));
+            CUX(h, launch_pvert_amplicon_bias(pvert_view(seg), seg.pv_row_amp, ctx.d_out.p, nullptr, (int64_t)n, (int64_t)n, nullptr, h->cfg.amplicon_bias_filter, h->dcfg.min_bq, d_status,
+                                              h->num_sms, st));
+            int one = 0;
+            CUX(h, cudaMemcpyAsync(&one, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUX(h, cudaStreamSynchronize(st));
+            amp_status |= one;
+            h->total_launches += 1;
+        }
+    }
+    if (amp_status) { h->error = "Index was outside the bounds of the array."; return PB2_ERR_ARG; }
     if (!append_seg) {
         if (out_records) { out_records->resize(n); CUX(h, cudaMemcpyAsync(out_records->data(), ctx.d_out.p, n * sizeof(pb2_call_record), cudaMemcpyDeviceToHost, st)); }
         if (out_flags) { out_flags->resize(n); CUX(h, cudaMemcpyAsync(out_flags->data(), ctx.d_flags.p, n, cudaMemcpyDeviceToHost, st)); }

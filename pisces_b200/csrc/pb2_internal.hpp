@@ -23,6 +23,7 @@ struct ReadsView {
     const uint8_t* base_dirs;
     const uint8_t* collapsed;
     const uint8_t* slots = nullptr;   // PVERT slot byte of every read base (pb2_pvert.cuh), derived at ingest; 16 bytes of slack on either side
+    const int32_t* amplicon = nullptr;   // [n] amplicon name id of a read (-1 none); only with amplicon tracking
 };
 struct RegionView {
     int32_t lo, hi;
@@ -91,6 +92,7 @@ struct ReadsCompactArgs {
     const int64_t *new_index, *new_cigar, *new_seq;   // exclusive scans, [n + 1]
     const int32_t* pos0; const int32_t* end_pos; const uint16_t* flag; const int64_t* cigar_off; const uint32_t* cigar; const int64_t* seq_off;
     const uint8_t *bases, *quals, *base_dirs, *collapsed;
+    const int32_t* amplicon = nullptr; int32_t* o_amplicon = nullptr;
     int32_t* o_pos0; int32_t* o_end_pos; uint16_t* o_flag; int64_t* o_cigar_off; uint32_t* o_cigar; int64_t* o_seq_off;
     uint8_t *o_bases, *o_quals, *o_base_dirs, *o_collapsed;
     const uint8_t* slots; uint8_t* o_slots;   // (already offset by the leading slack)
@@ -119,13 +121,14 @@ struct DeviceReads {
     GrowBuf<uint32_t> cigar;
     GrowBuf<uint8_t> bases, quals, base_dirs, collapsed;
     GrowBuf<uint8_t> slots;   // [16 + n_seq + 16]
-    bool has_dirs = false, has_collapsed = false;
+    GrowBuf<int32_t> amplicon;   // [n] with amplicon tracking (pb2_config.amplicon_bias_filter >= 0), else unused
+    bool has_dirs = false, has_collapsed = false, has_amplicon = false;
     int32_t min_start = INT32_MAX, max_end = 0;   // extent of the stored reads (1-based positions)
     int32_t last_pos0 = -1;                       // Position of the read pushed last (-1: none yet)
     size_t size() const { return (size_t)n; }
     pb2::ReadsView view() const {
         return pb2::ReadsView{(int32_t)n, pos0.p, flag.p, cigar_off.p, cigar.p, seq_off.p, bases.p, quals.p, has_dirs ? base_dirs.p : nullptr,
-                              has_collapsed ? collapsed.p : nullptr, slots.p ? slots.p + 16 : nullptr};
+                              has_collapsed ? collapsed.p : nullptr, slots.p ? slots.p + 16 : nullptr, has_amplicon ? amplicon.p : nullptr};
     }
 };
 
@@ -165,6 +168,7 @@ struct Segment {   // one staged pileup (pb2_push_pileup*)
     // PVERT form (pb2_pvert.cuh; segments built from pushed reads): pv_data != nullptr, and none of the PTILE32 / PNIB16 planes exist
     uint8_t* pv_data = nullptr;
     int2* pv_row_meta = nullptr;
+    int32_t* pv_row_amp = nullptr;   // [n_rows] amplicon id of the row's read (base rows; -1 none), with amplicon tracking only
     int64_t* pv_tile_row0 = nullptr;
     int32_t* pv_cls_end = nullptr;
     int32_t pv_classes = 0;

@@ -281,49 +281,59 @@ __device__ __forceinline__ int count_of(const int (&c)[kNumAlleles][kNumDirs], i
 // One point allele (SNV or Reference) of a locus: coverage, q-score, strand bias, filters, genotype, record. kRefOnly: the allele is known at compile
 // time to be the locus' reference allele (the per-locus Reference candidate of gVCF mode) - that instance is inlined into the hot kernel, its counts
 // and its record living in registers; the general one sits behind the out-of-line score_point_allele below.
-template <bool kRefOnly>
-__device__ __forceinline__ bool score_point_allele_impl(const int (&c)[kNumAlleles][kNumDirs], double qsum, int position, int ref_allele,
-                                                        int alt_allele /* == ref_allele for Reference */, int gapped, const DeviceConfig& cfg,
-                                                        const HotInputsExtra& ex, pb2_call_record& r) {
-    const uint8_t* __restrict__ chr_seq = ex.chr_seq;
-    const int64_t chr_len = ex.chr_len;
-    const bool is_ref = kRefOnly || alt_allele == ref_allele;
+// The stages of one point allele, separable so that the queued-locus scorer can spread the independent FP64 chains (the q-score and the three sets of
+// strand-bias statistics) over the four lanes of its group: (1) coverage and support out of the counts + the cheap callability bars, (2) q-score and
+// strand bias, (3) filters, genotype, record.
+struct PointPrep {
     int cov[3], sup[3];
-    int total = 0, nocalls = 0, ref_support = 0;
+    int total, nocalls, ref_support, allele_support;
+    float freq;
+    bool is_ref;
+};
+template <bool kRefOnly>
+__device__ __forceinline__ bool point_allele_prepare(const int (&c)[kNumAlleles][kNumDirs], int ref_allele, int alt_allele, int gapped, const DeviceConfig& cfg, PointPrep& p) {
+    p.is_ref = kRefOnly || alt_allele == ref_allele;
+    p.total = 0; p.nocalls = 0; p.ref_support = 0;
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-        cov[d] = c[AT_A][d] + c[AT_C][d] + c[AT_G][d] + c[AT_T][d] + c[AT_DEL][d];
-        total += cov[d];
-        nocalls += c[AT_N][d];
-        sup[d] = count_of(c, alt_allele, d);
-        if (ref_allele != AT_N) ref_support += kRefOnly ? sup[d] : count_of(c, ref_allele, d);
+        p.cov[d] = c[AT_A][d] + c[AT_C][d] + c[AT_G][d] + c[AT_T][d] + c[AT_DEL][d];
+        p.total += p.cov[d];
+        p.nocalls += c[AT_N][d];
+        p.sup[d] = count_of(c, alt_allele, d);
+        if (ref_allele != AT_N) p.ref_support += kRefOnly ? p.sup[d] : count_of(c, ref_allele, d);
     }
-    int allele_support = sup[0] + sup[1] + sup[2];
-    if (is_ref) allele_support = max(0, allele_support - gapped);  // CoverageCalculator.cs:94-97
-    else ref_support = max(0, ref_support - gapped);               // :90-93
-    const float freq = allele_frequency(allele_support, total);
-
+    p.allele_support = p.sup[0] + p.sup[1] + p.sup[2];
+    if (p.is_ref) p.allele_support = max(0, p.allele_support - gapped);  // CoverageCalculator.cs:94-97
+    else p.ref_support = max(0, p.ref_support - gapped);                 // :90-93
+    p.freq = allele_frequency(p.allele_support, p.total);
     // cheap callability tests first (same outcome as evaluating Q/SB first, AlleleCaller.cs:236-258)
-    if (!is_ref) {
-        if (total < cfg.min_coverage && !cfg.output_gvcf) return false;
-        if (total != 0 && freq < cfg.min_frequency) return false;
+    if (!p.is_ref) {
+        if (p.total < cfg.min_coverage && !cfg.output_gvcf) return false;
+        if (p.total != 0 && p.freq < cfg.min_frequency) return false;
     }
-    int vq = 0, nl_applied = 0;
-    SbResult sb;
-    sb.bias = 0; sb.gatk = 0; sb.acceptable = false; sb.var_both = false; sb.cov_both = false;   // new BiasResults()
-    if (allele_support > 0) {
-        int nl = cfg.noise_level;
-        double error_rate = cfg.vq_error_rate;
-        if (cfg.noise_model == 1) {   // NoiseModel.Window (AlleleCaller.cs:215-218)
-            nl = (int)(-10 * log10(qsum / total));
-            error_rate = q_to_p((double)nl);
-        }
-        nl_applied = nl;
-        vq = (total == 0) ? 0 : poisson_qscore(allele_support, total, error_rate, cfg.max_vq);
+    return true;
+}
+__device__ __forceinline__ int point_allele_vq(const PointPrep& p, double qsum, const DeviceConfig& cfg, int& nl_applied) {
+    nl_applied = 0;
+    if (p.allele_support <= 0) return 0;
+    int nl = cfg.noise_level;
+    double error_rate = cfg.vq_error_rate;
+    if (cfg.noise_model == 1) {   // NoiseModel.Window (AlleleCaller.cs:215-218)
+        nl = (int)(-10 * log10(qsum / p.total));
+        error_rate = q_to_p((double)nl);
     }
-    if (!is_ref && vq < cfg.min_vq) return false;
-    if (allele_support > 0) sb = strand_bias(cov, sup, cfg.sb_noise, (double)cfg.sb_acceptance, cfg.sb_model, cfg.sb_min_vf);
-
+    nl_applied = nl;
+    return (p.total == 0) ? 0 : poisson_qscore(p.allele_support, p.total, error_rate, cfg.max_vq);
+}
+// RMxNCalculator.ShouldFilter of a point allele (reference alleles are never filtered, AlleleProcessor.cs:44-66): reads the chromosome, nothing else
+__device__ __forceinline__ bool point_allele_rmxn(const PointPrep& p, int position, int ref_allele, int alt_allele, const DeviceConfig& cfg, const HotInputsExtra& ex) {
+    return !p.is_ref && rmxn_should_filter_snv(position, base_of_allele(ref_allele), base_of_allele(alt_allele), p.freq, cfg, ex.chr_seq, ex.chr_len);
+}
+__device__ __forceinline__ void point_allele_finish(const PointPrep& p, int vq, int nl_applied, const SbResult& sb, bool rmxn_hit, double qsum, int position, int ref_allele,
+                                                    int alt_allele, const DeviceConfig& cfg, const HotInputsExtra& ex, pb2_call_record& r) {
+    const bool is_ref = p.is_ref;
+    const int total = p.total, nocalls = p.nocalls, allele_support = p.allele_support, ref_support = p.ref_support;
+    const float freq = p.freq;
     // AlleleProcessor.Process / ApplyFilters
     const float all_reads = (float)(total + nocalls);
     const float frac_nc = all_reads == 0 ? 0.0f : ((float)nocalls / all_reads);
@@ -333,7 +343,7 @@ __device__ __forceinline__ bool score_point_allele_impl(const int (&c)[kNumAllel
     if (!is_ref) {
         if (cfg.no_call_filter >= 0 && frac_nc > cfg.no_call_filter) filters |= 1u << FLT_NO_CALL;
         if (!sb.acceptable || (cfg.filter_single_strand && !sb.var_both)) filters |= 1u << FLT_STRAND_BIAS;
-        if (rmxn_should_filter_snv(position, base_of_allele(ref_allele), base_of_allele(alt_allele), freq, cfg, chr_seq, chr_len)) filters |= 1u << FLT_RMXN;
+        if (rmxn_hit) filters |= 1u << FLT_RMXN;
         if (freq < cfg.variant_freq_filter) filters |= 1u << FLT_LOW_VF;
     }
     // SomaticGenotyper + GQ (per allele). Germline ploidy: exact for a locus whose only allele is this reference allele; the alleles of a locus
@@ -361,7 +371,7 @@ __device__ __forceinline__ bool score_point_allele_impl(const int (&c)[kNumAllel
     r.genotype_qscore = gq;
     r.total_coverage = total;
 #pragma unroll
-    for (int d = 0; d < 3; d++) { r.coverage_by_direction[d] = cov[d]; r.support_by_direction[d] = sup[d]; }
+    for (int d = 0; d < 3; d++) { r.coverage_by_direction[d] = p.cov[d]; r.support_by_direction[d] = p.sup[d]; }
     r.allele_support = allele_support;
     r.reference_support = ref_support;
     r.num_no_calls = nocalls;
@@ -372,6 +382,20 @@ __device__ __forceinline__ bool score_point_allele_impl(const int (&c)[kNumAllel
     r.sum_base_quality = qsum;
     r.bias_score = sb.bias;
     r.gatk_bias_score = sb.gatk;
+}
+template <bool kRefOnly>
+__device__ __forceinline__ bool score_point_allele_impl(const int (&c)[kNumAlleles][kNumDirs], double qsum, int position, int ref_allele,
+                                                        int alt_allele /* == ref_allele for Reference */, int gapped, const DeviceConfig& cfg,
+                                                        const HotInputsExtra& ex, pb2_call_record& r) {
+    PointPrep p;
+    if (!point_allele_prepare<kRefOnly>(c, ref_allele, alt_allele, gapped, cfg, p)) return false;
+    int nl_applied;
+    const int vq = point_allele_vq(p, qsum, cfg, nl_applied);
+    if (!p.is_ref && vq < cfg.min_vq) return false;
+    SbResult sb;
+    sb.bias = 0; sb.gatk = 0; sb.acceptable = false; sb.var_both = false; sb.cov_both = false;   // new BiasResults()
+    if (p.allele_support > 0) sb = strand_bias(p.cov, p.sup, cfg.sb_noise, (double)cfg.sb_acceptance, cfg.sb_model, cfg.sb_min_vf);
+    point_allele_finish(p, vq, nl_applied, sb, point_allele_rmxn(p, position, ref_allele, alt_allele, cfg, ex), qsum, position, ref_allele, alt_allele, cfg, ex, r);
     return true;
 }
 
@@ -394,12 +418,15 @@ constexpr int kCtaPending = 64;   // per-CTA queue of the vertical-counter kerne
 
 // The counts arrive as a plain array indexed with compile-time constants only, so they stay in registers: LocusCounts (whose address the out-of-line
 // scorer takes) is built inside the branches that need it, not for every locus (that cost 129 MB of local-memory stores per million loci).
+// kRefStream = false: an instance for VCF-only runs (no dense reference stream): the inlined reference-allele scorer is not even compiled in, which is
+// what lets the counting loop of the PVERT kernel live in 40 registers (more warps, deeper loads in flight).
+template <bool kRefStream = true>
 __device__ __forceinline__ void finish_locus(const int (&cnt)[kNumAlleles][kNumDirs], double qsum, int any, int64_t locus, int ref_allele, const TilePileup& in,
                                              const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, PendingLocus* cta_queue = nullptr,
-                                             int* cta_count = nullptr) {
+                                             int* cta_count = nullptr, int cta_capacity = kCtaPending) {
     if (cfg.own_hi > 0) {   // an interval shard scores the loci it owns; its halo is staged for the alleles that reach into it, never emitted
         const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
-        if (position < cfg.own_lo || position > cfg.own_hi) { if (out.ref_records != nullptr) out.ref_valid[locus] = 0; return; }
+        if (position < cfg.own_lo || position > cfg.own_hi) { if (kRefStream && out.ref_records != nullptr) out.ref_valid[locus] = 0; return; }
     }
     const int gapped_word = ex.gapped_ref ? ex.gapped_ref[locus] : 0;
     const int gapped = gapped_word & (kSuppressCountSnvs - 1);
@@ -422,7 +449,7 @@ __device__ __forceinline__ void finish_locus(const int (&cnt)[kNumAlleles][kNumD
         PendingLocus* dst = nullptr;
         if (cta_queue != nullptr) {
             const int s = atomicAdd(cta_count, 1);
-            if (s < kCtaPending) dst = cta_queue + s;
+            if (s < cta_capacity) dst = cta_queue + s;
         }
         if (dst == nullptr) {   // no CTA queue (198-bin kernel) or it is full: the global queue, scored by score_pending_kernel
             const unsigned long long slot = atomicAdd(out.pending_count, 1ull);
@@ -444,8 +471,8 @@ __device__ __forceinline__ void finish_locus(const int (&cnt)[kNumAlleles][kNumD
 #pragma unroll
             for (int i = 0; i < (int)(sizeof(PendingLocus) / 16); i++) dp[i] = sp[i];
         }
-        if (out.ref_records != nullptr) out.ref_valid[locus] = 0;   // decided when the queued locus is scored
-    } else if (out.ref_records != nullptr) {
+        if (kRefStream && out.ref_records != nullptr) out.ref_valid[locus] = 0;   // decided when the queued locus is scored
+    } else if (kRefStream && out.ref_records != nullptr) {
         // RegionState.GetAllCandidates: a Reference candidate per position when gVCF; zero-coverage positions only with intervals (:446)
         // ... and never past the chromosome end (:411-412)
         const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
@@ -643,38 +670,142 @@ pileup_count_score_kernel(const __grid_constant__ TilePileup in, const __grid_co
 
 // A queued locus scored by 4 adjacent lanes: lane j takes alternate allele j of (A, C, G, T) (the (ref, alt) order of AlleleCaller.cs:172-176 is
 // restored when the records are sorted), then lane 0 the reference allele if nothing was called there (:146-147). Must be called by full warps.
-__device__ __forceinline__ void score_queued_locus(const PendingLocus* item /* nullptr: idle group */, int j, const TilePileup& in, const HotInputsExtra& ex,
-                                                   const HotOutputs& out, const DeviceConfig& cfg) {
+__device__ __noinline__ void score_queued_locus(const PendingLocus* item /* nullptr: idle group */, int j, const TilePileup& in, const HotInputsExtra& ex,
+                                                const HotOutputs& out, const DeviceConfig& cfg) {
+    // A group of four lanes per queued locus, the whole warp in lockstep. Pass i scores the i-th SNV candidate of every locus of the warp (nearly always
+    // the only one); in it the independent FP64 chains run side by side - lane 0 of a group the Poisson q-score, lanes 1..3 the overall / forward /
+    // reverse strand-bias statistics (one instruction stream for all three) - and lane 0 finishes the record. The time of a pass is that of the longest
+    // chain, not of their sum: it runs after the CTA's last tile, when there is nothing left to hide it behind. Every shuffle is a full-warp one at a
+    // warp-uniform point: with per-group masks the groups lose their convergence in the first data-dependent loop and run one after the other.
     const int lane = threadIdx.x & 31;
-    bool called = false;
+    const int lead = lane & ~3;
     LocusCounts lc;
-    int64_t locus = 0;
-    int ref_allele = AT_N, position = 0, cand_mask = 0, gapped = 0;
-    if (item != nullptr) {
 #pragma unroll
-        for (int a = 0; a < kNumAlleles; a++)
+    for (int a = 0; a < kNumAlleles; a++)
 #pragma unroll
-            for (int d = 0; d < kNumDirs; d++) lc.c[a][d] = item->c[a * kNumDirs + d];
-        lc.qsum = item->qsum;
-        locus = item->locus;
-        cand_mask = item->cand_mask;
-        gapped = item->gapped;
-        ref_allele = allele_of_base(in.ref_base[locus]);
-        position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
-        const int order[4] = {AT_A, AT_C, AT_G, AT_T};
-        const int alt = order[j];
-        if ((cand_mask >> alt) & 1) {
+        for (int d = 0; d < kNumDirs; d++) lc.c[a][d] = item ? item->c[a * kNumDirs + d] : 0;
+    lc.qsum = item ? item->qsum : 0.0;
+    const int64_t locus = item ? item->locus : 0;
+    const int cand_mask = item ? item->cand_mask : 0, gapped = item ? item->gapped : 0;
+    const int ref_allele = item ? allele_of_base(in.ref_base[locus]) : AT_N;
+    const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+    bool called = false;
+    unsigned rem = (unsigned)cand_mask & 0xfu;
+    const int passes = __reduce_max_sync(0xffffffffu, __popc(rem));
+#pragma unroll 1
+    for (int pass = 0; pass < passes; pass++) {
+        const int alt = rem ? __ffs((int)rem) - 1 : 0;
+        const bool have = rem != 0;
+        rem &= rem - 1;
+        PointPrep p;
+        const bool ok = point_allele_prepare<false>(lc.c, ref_allele, alt, gapped, cfg, p) && have;   // the same on the four lanes of a group
+        int vq = 0, nl_applied = 0;
+        SbStats st;
+        st.fn = st.fp = st.vg = st.coverage = st.support = 0;
+        if (ok) {
+            if (j == 0) vq = point_allele_vq(p, lc.qsum, cfg, nl_applied);
+            else if (p.allele_support > 0) st = sb_stats_of(j - 1, p.cov, p.sup, cfg.sb_noise, cfg.sb_model, cfg.sb_min_vf);
+        }
+        SbStats o, f, r;
+        o.vg = __shfl_sync(0xffffffffu, st.vg, lead + 1); o.fp = __shfl_sync(0xffffffffu, st.fp, lead + 1);
+        o.coverage = __shfl_sync(0xffffffffu, st.coverage, lead + 1); o.support = __shfl_sync(0xffffffffu, st.support, lead + 1);
+        f.vg = __shfl_sync(0xffffffffu, st.vg, lead + 2); f.fp = __shfl_sync(0xffffffffu, st.fp, lead + 2);
+        f.coverage = __shfl_sync(0xffffffffu, st.coverage, lead + 2); f.support = __shfl_sync(0xffffffffu, st.support, lead + 2);
+        r.vg = __shfl_sync(0xffffffffu, st.vg, lead + 3); r.fp = __shfl_sync(0xffffffffu, st.fp, lead + 3);
+        r.coverage = __shfl_sync(0xffffffffu, st.coverage, lead + 3); r.support = __shfl_sync(0xffffffffu, st.support, lead + 3);
+        o.fn = f.fn = r.fn = 0;
+        if (ok && j == 0 && vq >= cfg.min_vq) {   // AlleleCaller.IsCallable
+            SbResult sb;
+            sb.bias = 0; sb.gatk = 0; sb.acceptable = false; sb.var_both = false; sb.cov_both = false;   // new BiasResults()
+            if (p.allele_support > 0) sb = strand_bias_combine(o, f, r, (double)cfg.sb_acceptance);
+            pb2_call_record rec;
+            point_allele_finish(p, vq, nl_applied, sb, point_allele_rmxn(p, position, ref_allele, alt, cfg, ex), lc.qsum, position, ref_allele, alt, cfg, ex, rec);
+            called = true;
+            const unsigned long long slot = atomicAdd(out.var_count, 1ull);
+            if ((int64_t)slot < out.var_capacity) store_record(out.var_records + slot, rec);
+        }
+        __syncwarp();
+    }
+    if (item != nullptr && j == 0 && out.ref_records != nullptr) {
+        const bool variant_called = ((cand_mask & 0x100) != 0) || called;
+        const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (cand_mask & 0x200)) && (ex.chr_len == 0 || position <= ex.chr_len);
+        if (emit) {
             pb2_call_record r;
-            if (score_point_allele(lc, position, ref_allele, alt, gapped, cfg, ex, r)) {
-                called = true;
-                const unsigned long long slot = atomicAdd(out.var_count, 1ull);
-                if ((int64_t)slot < out.var_capacity) store_record(out.var_records + slot, r);
+            score_point_allele(lc, position, ref_allele, ref_allele, gapped, cfg, ex, r);
+            store_record(out.ref_records + locus, r);
+        }
+        out.ref_valid[locus] = emit ? 1 : 0;
+    }
+}
+
+// The same queue scored by the whole CTA (256 threads) with one TASK per thread instead of one locus per group of lanes: of a queue of up to 51 loci,
+// threads 0..50 take the Poisson q-score of locus t, threads 51..203 one of the three sets of strand-bias statistics of locus (t - 51) / 3, threads
+// 204..254 the RMxN scan of the chromosome around locus t - 204. A warp then holds (nearly) one kind of task - no divergent instruction streams to
+// serialise - and the independent chains of a locus run on different warps at the same time; the results meet in shared memory, and thread t finishes
+// the record of locus t. This pass runs after the CTA's last tile with nothing to hide behind: its time is that of the slowest single chain.
+constexpr int kCtaTaskLoci = 51;
+struct QueueScratch {
+    double vg[kCtaTaskLoci][3], fp[kCtaTaskLoci][3];
+    uint8_t rmxn[kCtaTaskLoci];
+};
+__device__ __noinline__ void score_cta_queue(const PendingLocus* q, int n, QueueScratch& sc, const TilePileup& in, const HotInputsExtra& ex, const HotOutputs& out,
+                                             const DeviceConfig& cfg) {
+    const int t = threadIdx.x;
+    const bool lead = t < kCtaTaskLoci;
+    const bool scan = t >= 4 * kCtaTaskLoci && t < 5 * kCtaTaskLoci;
+    const int item = lead ? t : (scan ? t - 4 * kCtaTaskLoci : (t - kCtaTaskLoci) / 3);
+    const int which = (lead || scan) ? 0 : (t - kCtaTaskLoci) % 3;
+    const bool have_item = item < n && t < 5 * kCtaTaskLoci;
+    LocusCounts lc;
+#pragma unroll
+    for (int a = 0; a < kNumAlleles; a++)
+#pragma unroll
+        for (int d = 0; d < kNumDirs; d++) lc.c[a][d] = have_item ? q[item].c[a * kNumDirs + d] : 0;
+    lc.qsum = have_item ? q[item].qsum : 0.0;
+    const int64_t locus = have_item ? q[item].locus : 0;
+    const int cand_mask = have_item ? q[item].cand_mask : 0, gapped = have_item ? q[item].gapped : 0;
+    const int ref_allele = have_item ? allele_of_base(in.ref_base[locus]) : AT_N;
+    const int position = in.positions ? in.positions[locus] : in.first_position + (int)locus;
+    bool called = false;
+    unsigned rem = (unsigned)cand_mask & 0xfu;
+    while (__syncthreads_or(rem != 0)) {   // pass i: the i-th SNV candidate of every queued locus (nearly always the only one)
+        const int alt = rem ? __ffs((int)rem) - 1 : 0;
+        const bool have = rem != 0;
+        rem &= rem - 1;
+        PointPrep p;
+        const bool ok = point_allele_prepare<false>(lc.c, ref_allele, alt, gapped, cfg, p) && have;
+        int vq = 0, nl_applied = 0;
+        if (ok) {
+            if (lead) vq = point_allele_vq(p, lc.qsum, cfg, nl_applied);
+            else if (scan) sc.rmxn[item] = point_allele_rmxn(p, position, ref_allele, alt, cfg, ex) ? 1 : 0;
+            else if (p.allele_support > 0) {
+                const SbStats st = sb_stats_of(which, p.cov, p.sup, cfg.sb_noise, cfg.sb_model, cfg.sb_min_vf);
+                sc.vg[item][which] = st.vg; sc.fp[item][which] = st.fp;
             }
         }
+        __syncthreads();
+        if (ok && lead && vq >= cfg.min_vq) {   // AlleleCaller.IsCallable
+            SbResult sb;
+            sb.bias = 0; sb.gatk = 0; sb.acceptable = false; sb.var_both = false; sb.cov_both = false;   // new BiasResults()
+            if (p.allele_support > 0) {
+                SbStats s3[3];
+#pragma unroll
+                for (int w = 0; w < 3; w++) {
+                    int s_, c_;
+                    sb_inputs_of(w, p.cov, p.sup, s_, c_);
+                    s3[w].support = s_; s3[w].coverage = c_; s3[w].vg = sc.vg[item][w]; s3[w].fp = sc.fp[item][w]; s3[w].fn = 0;
+                }
+                sb = strand_bias_combine(s3[0], s3[1], s3[2], (double)cfg.sb_acceptance);
+            }
+            pb2_call_record rec;
+            point_allele_finish(p, vq, nl_applied, sb, sc.rmxn[item] != 0, lc.qsum, position, ref_allele, alt, cfg, ex, rec);
+            called = true;
+            const unsigned long long slot = atomicAdd(out.var_count, 1ull);
+            if ((int64_t)slot < out.var_capacity) store_record(out.var_records + slot, rec);
+        }
     }
-    const unsigned b = __ballot_sync(0xffffffffu, called);
-    if (item != nullptr && j == 0 && out.ref_records != nullptr) {
-        const bool variant_called = ((cand_mask & 0x100) != 0) || (((b >> (lane & ~3)) & 0xfu) != 0);
+    if (have_item && lead && out.ref_records != nullptr) {
+        const bool variant_called = ((cand_mask & 0x100) != 0) || called;
         const bool emit = cfg.output_gvcf && !variant_called && (cfg.have_intervals || (cand_mask & 0x200)) && (ex.chr_len == 0 || position <= ex.chr_len);
         if (emit) {
             pb2_call_record r;
@@ -1449,11 +1580,14 @@ cudaError_t launch_hot_kernel(const TilePileup& in, const HotInputsExtra& ex, co
 // bit-serial comparison of the six quality planes against the bits of minBQ (one LOP3 per plane), the four allele indicators are one LOP3 each, and a
 // count is a POPC: about 30 instructions per 32 entries, no counters to read out. Direction, collapsed-read category and entry kind are properties of
 // the block's class, so stitched and collapsed-read data run through the same loop at the same byte per entry.
-template <bool kCollapsed>
-__global__ void __launch_bounds__(256, 4)
+// kRefStream: the run has a dense reference stream (gVCF) - the per-locus tail then holds the inlined reference-allele scorer and the kernel keeps the
+// 64-register / 4-CTA shape; without it the kernel runs 6 CTAs per SM. kAhead: blocks requested ahead of the one being counted.
+template <bool kCollapsed, bool kRefStream, int kCtas, int kAhead>
+__global__ void __launch_bounds__(256, kCtas)
 pileup_pvert_score_kernel(const __grid_constant__ PvertPileup pv, const __grid_constant__ HotInputsExtra ex, const __grid_constant__ HotOutputs out,
                           const __grid_constant__ DeviceConfig cfg, int* __restrict__ tile_counter) {
     __shared__ __align__(16) PendingLocus s_pend[kCtaPending];
+    __shared__ QueueScratch s_scratch;
     __shared__ int s_pend_n;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_pend_n = 0;
@@ -1487,10 +1621,13 @@ pileup_pvert_score_kernel(const __grid_constant__ PvertPileup pv, const __grid_c
 #pragma unroll
         for (int t = 0; t < kNumCollapsed; t++) coll[t] = 0;
 
-        // blocks of all classes sit back to back: the loads run one block ahead of the counting, across class boundaries
-        uint4 nx = make_uint4(0, 0, 0, 0), ny = nx, nx2 = nx, ny2 = nx;
-        if (total > 0) { nx = ldg_stream(p); ny = ldg_stream(p + 512); }
-        if (total > 32) { nx2 = ldg_stream(p + 1024); ny2 = ldg_stream(p + 1536); }
+        // blocks of all classes sit back to back: the loads run kAhead blocks ahead of the counting, across class boundaries (a ring of registers)
+        uint4 rx[kAhead], ry[kAhead];
+#pragma unroll
+        for (int j = 0; j < kAhead; j++) {
+            rx[j] = make_uint4(0, 0, 0, 0); ry[j] = rx[j];
+            if (32 * j < total) { rx[j] = ldg_stream(p + 1024 * j); ry[j] = ldg_stream(p + 1024 * j + 512); }
+        }
         int row = 0;
 #pragma unroll 1
         for (int c = 0; c < nc; c++) {
@@ -1499,9 +1636,10 @@ pileup_pvert_score_kernel(const __grid_constant__ PvertPileup pv, const __grid_c
             int a0 = 0, a1 = 0, a2 = 0, a3 = 0, pres = 0;
 #pragma unroll 1
             for (; row < end; row += 32) {
-                const uint4 x = nx, y = ny;
-                nx = nx2; ny = ny2;
-                if (row + 64 < total) { nx2 = ldg_stream(p + 2048); ny2 = ldg_stream(p + 2560); }
+                const uint4 x = rx[0], y = ry[0];
+#pragma unroll
+                for (int j = 0; j + 1 < kAhead; j++) { rx[j] = rx[j + 1]; ry[j] = ry[j + 1]; }
+                if (row + 32 * kAhead < total) { rx[kAhead - 1] = ldg_stream(p + 1024 * kAhead); ry[kAhead - 1] = ldg_stream(p + 1024 * kAhead + 512); }
                 p += 1024;
                 // q >= minBQ, least significant plane first: ge_i = m_i ? (Q_i & ge) : (Q_i | ge)
                 uint32_t ge = y.w | ~M[0];
@@ -1547,15 +1685,11 @@ pileup_pvert_score_kernel(const __grid_constant__ PvertPileup pv, const __grid_c
 #pragma unroll
             for (int d = 0; d < kNumDirs; d++) any += cnt[a][d];
         const int ref_allele = allele_of_base(pv.ref_base[locus]);
-        finish_locus(cnt, 0.0, any, locus, ref_allele, in, ex, out, cfg, s_pend, &s_pend_n);
+        finish_locus<kRefStream>(cnt, 0.0, any, locus, ref_allele, in, ex, out, cfg, s_pend, &s_pend_n, kCtaTaskLoci);
     }
 
     __syncthreads();
-    {
-        const int n = min(s_pend_n, kCtaPending);
-        const int item = threadIdx.x >> 2;
-        score_queued_locus(item < n ? &s_pend[item] : nullptr, threadIdx.x & 3, in, ex, out, cfg);
-    }
+    score_cta_queue(s_pend, min(s_pend_n, kCtaTaskLoci), s_scratch, in, ex, out, cfg);
 }
 
 cudaError_t launch_pvert_hot_kernel(const PvertPileup& pv, const HotInputsExtra& ex, const HotOutputs& out, const DeviceConfig& cfg, int num_sms, int* tile_counter,
@@ -1563,9 +1697,16 @@ cudaError_t launch_pvert_hot_kernel(const PvertPileup& pv, const HotInputsExtra&
     if (pv.n_tiles == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
+    // the tuning runs of round 2 (profiles/r2_summary.md): 4 CTAs x 2 blocks ahead beat 2, 3, 5 and 6 CTAs per SM, 3 and 4 blocks ahead, and an L2 prefetch of
+    // the next tile's head, for both instances
     const int grid = max(1, min(num_sms * 4, (pv.n_tiles + 7) / 8));
-    if (cfg.expect_collapsed) pileup_pvert_score_kernel<true><<<grid, 256, 0, stream>>>(pv, ex, out, cfg, tile_counter);
-    else pileup_pvert_score_kernel<false><<<grid, 256, 0, stream>>>(pv, ex, out, cfg, tile_counter);
+    if (out.ref_records != nullptr) {
+        if (cfg.expect_collapsed) pileup_pvert_score_kernel<true, true, 4, 2><<<grid, 256, 0, stream>>>(pv, ex, out, cfg, tile_counter);
+        else pileup_pvert_score_kernel<false, true, 4, 2><<<grid, 256, 0, stream>>>(pv, ex, out, cfg, tile_counter);
+    } else {
+        if (cfg.expect_collapsed) pileup_pvert_score_kernel<true, false, 4, 2><<<grid, 256, 0, stream>>>(pv, ex, out, cfg, tile_counter);
+        else pileup_pvert_score_kernel<false, false, 4, 2><<<grid, 256, 0, stream>>>(pv, ex, out, cfg, tile_counter);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     TilePileup in;

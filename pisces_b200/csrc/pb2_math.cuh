@@ -284,10 +284,19 @@ __device__ __forceinline__ SbStats sb_create_stats(double support, double covera
 struct SbResult { double bias, gatk; bool acceptable, var_both, cov_both; };
 
 // noise = Math.Pow(10, -1*qNoise/10f) (float exponent, :32): a per-run constant, computed once on the host
-__device__ __forceinline__ SbResult strand_bias(const int cov[3], const int sup[3], double noise, double acceptance, int model, double min_vf) {  // :21-72,89-105
-    const SbStats o = sb_create_stats(sup[0] + sup[1] + sup[2], cov[0] + cov[1] + cov[2], noise, model, min_vf);
-    const SbStats f = sb_create_stats(sup[0] + sup[2] / 2, cov[0] + cov[2] / 2, noise, model, min_vf);
-    const SbStats r = sb_create_stats(sup[1] + sup[2] / 2, cov[1] + cov[2] / 2, noise, model, min_vf);
+// The three sets of statistics of StrandBiasCalculator.CalculateStrandBiasResults (:21-72): which = 0 overall, 1 forward, 2 reverse (stitched reads
+// count half to each strand, integer halves as the reference's int arithmetic gives them)
+__device__ __forceinline__ void sb_inputs_of(int which, const int cov[3], const int sup[3], int& s, int& c) {
+    s = which == 0 ? sup[0] + sup[1] + sup[2] : (which == 1 ? sup[0] : sup[1]) + sup[2] / 2;
+    c = which == 0 ? cov[0] + cov[1] + cov[2] : (which == 1 ? cov[0] : cov[1]) + cov[2] / 2;
+}
+__device__ __forceinline__ SbStats sb_stats_of(int which, const int cov[3], const int sup[3], double noise, int model, double min_vf) {
+    // one call site: threads that compute different sets run the same instructions
+    int s, c;
+    sb_inputs_of(which, cov, sup, s, c);
+    return sb_create_stats(s, c, noise, model, min_vf);
+}
+__device__ __forceinline__ SbResult strand_bias_combine(const SbStats& o, const SbStats& f, const SbStats& r, double acceptance) {  // :40-72,89-105
     double fb = (f.vg * r.fp) / o.vg;
     double rb = (r.vg * f.fp) / o.vg;
     if (o.vg == 0) { fb = 1; rb = 1; }
@@ -300,6 +309,13 @@ __device__ __forceinline__ SbResult strand_bias(const int cov[3], const int sup[
     if (!res.cov_both) { res.bias = 0; res.gatk = -INFINITY; }
     res.acceptable = res.bias < acceptance;
     return res;
+}
+// noise = Math.Pow(10, -1*qNoise/10f) (float exponent, :32): a per-run constant, computed once on the host
+__device__ __forceinline__ SbResult strand_bias(const int cov[3], const int sup[3], double noise, double acceptance, int model, double min_vf) {  // :21-72,89-105
+    const SbStats o = sb_stats_of(0, cov, sup, noise, model, min_vf);
+    const SbStats f = sb_stats_of(1, cov, sup, noise, model, min_vf);
+    const SbStats r = sb_stats_of(2, cov, sup, noise, model, min_vf);
+    return strand_bias_combine(o, f, r, acceptance);
 }
 
 // ---------------------------------------------------------------- CalledAllele.Frequency / RefFrequency (CalledAllele.cs:49-52,123-126): float

@@ -40,6 +40,7 @@ struct FillTargets {
     int32_t* cursor;
     uint8_t* data;
     int2* row_meta;
+    int32_t* row_amp;   // optional: amplicon id of the row's read (base rows)
     uint32_t* exc_entries;
     unsigned long long* exc_count;
     int64_t exc_capacity;
@@ -118,6 +119,7 @@ __device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, 
                 const int k = atomicAdd(ft.cursor + key, 1);
                 s.row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[tile * n_classes + cls - 1] : 0) + k;
                 ft.row_meta[s.row] = meta;
+                if (ft.row_amp != nullptr && kind == 0) ft.row_amp[s.row] = rv.amplicon ? rv.amplicon[r] : -1;
             } else {
                 atomicAdd(cls_rows + key, 1);
             }
@@ -201,6 +203,7 @@ __device__ void pv_walk_piece(const ReadsView& rv, const RegionView& rg, int r, 
                             const int kk = atomicAdd(ft.cursor + key, 1);
                             sb.row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[tile * n_classes + cls - 1] : 0) + kk;
                             ft.row_meta[sb.row] = read_meta;
+                            if (ft.row_amp != nullptr) ft.row_amp[sb.row] = rv.amplicon ? rv.amplicon[r] : -1;
                         } else {
                             atomicAdd(cls_rows + key, 1);
                         }
@@ -371,6 +374,7 @@ __global__ void __launch_bounds__(256) pvert_fill_simple_kernel(ReadsView rv, Re
             for (int w = 0; w < 9; w++) src[w] = (w >= wa && w <= wb + 1) ? aw[w] : 0u;
             const int64_t row = ft.tile_row0[tile] + (cls > 0 ? ft.cls_end[(int64_t)tile * n_classes + cls - 1] : 0) + kk;
             ft.row_meta[row] = make_int2(start_pos, end_pos);
+            if (ft.row_amp != nullptr) ft.row_amp[row] = rv.amplicon ? rv.amplicon[r] : -1;
             const uint32_t* const refw = ft.ref_slot_words + ((int64_t)tile << 3);
             uint32_t out[8];
 #pragma unroll
@@ -549,6 +553,104 @@ pvert_gather_kernel(PvertPileup in, const int32_t* __restrict__ req_locus, int32
     for (int b = lane; b < kNumBins; b += 32) out_counts[(int64_t)r * kNumBins + b] = hist[b];
     if (out_collapsed != nullptr && lane < kNumCollapsed) out_collapsed[(int64_t)r * kNumCollapsed + lane] = hist[kNumBins + lane];
 }
+
+// AmpliconBiasCalculator (src/lib/Pisces.Calculators/AmpliconBiasCalculator.cs:20-133) for the SNV records of a record stream. One warp per record: it
+// walks the base rows of the record's tile exactly as the gather above, tallying per amplicon name the usable bases of the locus (CoverageByAmplicon:
+// RegionState.AddAmpliconCount from RegionStateManager.cs:188, every base counted as A/C/G/T) and those equal to the alternate base (SupportByAmplicon:
+// the SNV candidates of CandidateVariantFinder.cs:205-232 merged by RegionState.AddCandidate :138-170 - for count-based SNVs the same reads), in at
+// most Constants.MaxNumOverlappingAmplicons = 6 slots. The verdict BiasDetected is an OR over the amplicons, so the reference's first-seen slot order
+// does not matter; a seventh name at a called SNV is the reference's IndexOutOfRangeException (status 1).
+constexpr int kAmpSlots = 6;
+constexpr int kAmpWarps = 4;
+__global__ void __launch_bounds__(32 * kAmpWarps)
+pvert_amplicon_bias_kernel(PvertPileup in, const int32_t* __restrict__ row_amp, pb2_call_record* __restrict__ records, const unsigned long long* __restrict__ n_dev, int64_t n_host,
+                           int64_t capacity, const uint8_t* __restrict__ valid, float acceptance, int min_bq, int* __restrict__ status) {
+    __shared__ int s_name[kAmpWarps][kAmpSlots], s_cov[kAmpWarps][kAmpSlots], s_sup[kAmpWarps][kAmpSlots], s_n[kAmpWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+    if (n > capacity) n = capacity;
+    for (int64_t i = (int64_t)blockIdx.x * kAmpWarps + warp; i < n; i += (int64_t)gridDim.x * kAmpWarps) {
+        const pb2_call_record& rec = records[i];
+        if (valid != nullptr && !(valid[i] & 1)) continue;
+        if (rec.type != CAT_SNV || rec.allele_support <= 0 || rec.ref_len != 1 || rec.alt_len != 1) continue;   // Compute :20-31 (AlleleCaller.cs:217-228)
+        const int alt2 = pv_allele2((uint8_t)(rec.allele_bytes >> 8));
+        int64_t locus = -1;
+        if (in.positions == nullptr) locus = (int64_t)rec.position - in.first_position;
+        else {
+            int64_t lo = 0, hi = in.n_loci;
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (in.positions[mid] < rec.position) lo = mid + 1; else hi = mid; }
+            if (lo < in.n_loci && in.positions[lo] == rec.position) locus = lo;
+        }
+        if (locus < 0 || locus >= in.n_loci || alt2 < 0) continue;
+        if (lane == 0) s_n[warp] = 0;
+        __syncwarp();
+        const int64_t tile = locus >> 5;
+        const int l = (int)(locus & 31);
+        const int64_t row0 = in.tile_row0[tile];
+        int32_t prev_end = 0;
+        bool overflow = false;
+        for (int c = 0; c < in.n_classes; c++) {
+            const int32_t end = in.cls_end[tile * in.n_classes + c];
+            if (pv_class_kind(c) == 0) {
+                for (int32_t g = prev_end; g < end; g += 32) {
+                    const uint8_t* blk = in.data + (row0 + g) * 32;
+                    const uint4 x = *reinterpret_cast<const uint4*>(blk + l * 16), y = *reinterpret_cast<const uint4*>(blk + 512 + l * 16);
+                    const uint32_t b0 = (x.x >> lane) & 1u, b1 = (x.y >> lane) & 1u;
+                    const uint32_t q = (((x.z >> lane) & 1u) << 5) | (((x.w >> lane) & 1u) << 4) | (((y.x >> lane) & 1u) << 3) | (((y.y >> lane) & 1u) << 2) |
+                                       (((y.z >> lane) & 1u) << 1) | ((y.w >> lane) & 1u);
+                    const int amp = row_amp[row0 + g + lane];
+                    const bool usable = (int)q >= min_bq && amp >= 0;      // an N base is (0, q = 1) and min_bq >= 2; empty slots have q = 0
+                    const bool is_alt = usable && (int)(b0 | (b1 << 1)) == alt2;
+                    unsigned todo = __ballot_sync(0xffffffffu, usable);
+                    const unsigned alts = __ballot_sync(0xffffffffu, is_alt);
+                    while (todo) {
+                        const int leader = __ffs((int)todo) - 1;
+                        const int name = __shfl_sync(0xffffffffu, amp, leader);
+                        const unsigned same = __ballot_sync(0xffffffffu, usable && amp == name);
+                        todo &= ~same;
+                        if (lane == 0) {
+                            int k = 0;
+                            const int cnt = s_n[warp];
+                            while (k < cnt && s_name[warp][k] != name) k++;
+                            if (k == cnt) {
+                                if (cnt == kAmpSlots) overflow = true;
+                                else { s_name[warp][k] = name; s_cov[warp][k] = 0; s_sup[warp][k] = 0; s_n[warp] = cnt + 1; }
+                            }
+                            if (k < kAmpSlots) { s_cov[warp][k] += __popc(same); s_sup[warp][k] += __popc(same & alts); }
+                        }
+                    }
+                }
+            }
+            prev_end = end;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (overflow) { atomicExch(status, 1); continue; }
+            const int cnt = s_n[warp];
+            bool any_support = false;
+            for (int k = 0; k < cnt; k++) any_support |= s_sup[warp][k] > 0;
+            if (!any_support || cnt < 2) continue;                  // CalculateAmpliconBias :50-59: no verdict
+            double max_freq = 0.0;
+            for (int k = 0; k < cnt; k++) {                         // :64-82
+                const double freq = (double)s_sup[warp][k] / (double)s_cov[warp][k];
+                if (freq >= max_freq) max_freq = freq;
+            }
+            bool bias = false;
+            for (int k = 0; k < cnt; k++) {                         // :84-129
+                const double coverage = s_cov[warp][k], support = s_sup[warp][k];
+                const double freq = support / coverage;
+                const double expected = max_freq * coverage;
+                double chance = 1.0;
+                if (expected < 5.0) {}                               // Constants.MinNumObservations
+                else if (expected <= support || freq > 0.1) {}       // Constants.FreePassObservationFreq
+                else chance = fmax(0.0, pisces_poisson_cdf(support, expected));
+                if (chance < (double)acceptance) bias = true;
+            }
+            if (bias) records[i].filters |= (uint16_t)(1u << FLT_AMPLICON_BIAS);
+        }
+        __syncwarp();
+    }
+}
 }  // namespace
 
 cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, int32_t* complex, cudaStream_t st) {
@@ -561,10 +663,10 @@ cudaError_t launch_pvert_layout(int32_t* cls_rows, int32_t n_tiles, int n_classe
     return cudaGetLastError();
 }
 cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
-                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, const uint8_t* ref_slot, int32_t* complex,
-                              int64_t n_complex, cudaStream_t st) {
+                              int2* row_meta, int32_t* row_amp, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, const uint8_t* ref_slot,
+                              int32_t* complex, int64_t n_complex, cudaStream_t st) {
     if (rv.n_reads == 0) return cudaSuccess;
-    FillTargets ft{tile_row0, cls_end, cursor, data, row_meta, exc_entries, exc_count, exc_capacity, reinterpret_cast<const uint32_t*>(ref_slot)};
+    FillTargets ft{tile_row0, cls_end, cursor, data, row_meta, row_amp, exc_entries, exc_count, exc_capacity, reinterpret_cast<const uint32_t*>(ref_slot)};
     return launch_walk<true>(rv, rg, end_pos, n_classes, nullptr, ft, complex, n_complex, st);
 }
 cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st) {
@@ -582,6 +684,14 @@ cudaError_t launch_pvert_ref_bases(const uint8_t* chr, int64_t chr_len, const in
 cudaError_t launch_pvert_gather(const PvertPileup& in, const int32_t* req_locus, int32_t n_req, int32_t* out_counts, int32_t* out_collapsed, int min_bq, cudaStream_t st) {
     if (n_req <= 0) return cudaSuccess;
     pvert_gather_kernel<<<(n_req + kPvGatherWarps - 1) / kPvGatherWarps, 32 * kPvGatherWarps, 0, st>>>(in, req_locus, n_req, out_counts, out_collapsed, min_bq);
+    return cudaGetLastError();
+}
+cudaError_t launch_pvert_amplicon_bias(const PvertPileup& in, const int32_t* row_amp, pb2_call_record* records, const unsigned long long* n_dev, int64_t n_host, int64_t capacity,
+                                       const uint8_t* valid, float acceptance, int min_bq, int* status, int num_sms, cudaStream_t st) {
+    if (row_amp == nullptr || (n_dev == nullptr && n_host <= 0)) return cudaSuccess;
+    const int64_t want = n_dev ? (int64_t)num_sms * 4 : (n_host + kAmpWarps - 1) / kAmpWarps;
+    pvert_amplicon_bias_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms * 8)), 32 * kAmpWarps, 0, st>>>(in, row_amp, records, n_dev, n_host, capacity, valid,
+                                                                                                                                      acceptance, min_bq, status);
     return cudaGetLastError();
 }
 

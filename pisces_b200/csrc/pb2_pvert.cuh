@@ -70,8 +70,12 @@ struct RegionView;
 cudaError_t launch_pvert_count(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, int32_t* cls_rows, int32_t* complex, cudaStream_t st);
 cudaError_t launch_pvert_layout(int32_t* cls_rows /* in: rows per class; out: inclusive padded prefix */, int32_t n_tiles, int n_classes, int64_t* tile_rows, cudaStream_t st);
 cudaError_t launch_pvert_fill(const ReadsView& rv, const RegionView& rg, const int32_t* end_pos, int n_classes, const int64_t* tile_row0, const int32_t* cls_end, int32_t* cursor, uint8_t* data,
-                              int2* row_meta, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity, const uint8_t* ref_slot, int32_t* complex,
-                              int64_t n_complex, cudaStream_t st);
+                              int2* row_meta, int32_t* row_amp /* optional: amplicon id per base row */, uint32_t* exc_entries, unsigned long long* exc_count, int64_t exc_capacity,
+                              const uint8_t* ref_slot, int32_t* complex, int64_t n_complex, cudaStream_t st);
+// AmpliconBiasCalculator.Compute over a stream of records (n_dev: device counter, else n_host; valid: optional per-record flag byte, bit 0): sets the
+// AmpliconBias filter bit of the SNV records it detects bias for; *status = 1 when a called SNV's position holds more than six amplicon names
+cudaError_t launch_pvert_amplicon_bias(const PvertPileup& in, const int32_t* row_amp, pb2_call_record* records, const unsigned long long* n_dev, int64_t n_host, int64_t capacity,
+                                       const uint8_t* valid, float acceptance, int min_bq, int* status, int num_sms, cudaStream_t st);
 cudaError_t launch_pvert_transpose(uint8_t* data, int64_t n_blocks, cudaStream_t st);
 // ref_base[n_loci] ASCII; ref_slot (optional, [n_loci rounded up to 32]): allele2 << 6 of the reference base, 1 where it is not A/C/G/T
 cudaError_t launch_pvert_ref_bases(const uint8_t* chr, int64_t chr_len, const int32_t* positions, int32_t first_position, int64_t n_loci, uint8_t* ref_base, uint8_t* ref_slot,

@@ -423,6 +423,7 @@ __global__ void reads_compact_kernel(ReadsCompactArgs a) {
         a.o_pos0[ni] = a.pos0[i]; a.o_end_pos[ni] = a.end_pos[i]; a.o_flag[ni] = a.flag[i];
         a.o_cigar_off[ni] = oc; a.o_seq_off[ni] = os;
         if (a.collapsed) a.o_collapsed[ni] = a.collapsed[i];
+        if (a.amplicon) a.o_amplicon[ni] = a.amplicon[i];
         if (a.new_index[a.n] == ni + 1) { a.o_cigar_off[ni + 1] = oc + nc; a.o_seq_off[ni + 1] = os + ns; }   // the last kept read closes the offset arrays
     }
     for (int64_t k = lane; k < nc; k += 32) a.o_cigar[oc + k] = a.cigar[c0 + k];

@@ -288,7 +288,7 @@ class GpuStateManager:
 
     def AddReadsSoA(self, d):
         """pb2_push_reads with a struct of arrays (dict of numpy arrays / pinned torch tensors: pos0 int32, flag uint16, cigar_off int64, cigar uint32,
-        seq_off int64, bases, quals[, base_dirs, collapsed]): IStateManager.AddAlleleCounts + FindCandidates for every read of the batch."""
+        seq_off int64, bases, quals[, base_dirs, collapsed, amplicon int32]): IStateManager.AddAlleleCounts + FindCandidates for every read of the batch."""
         def ptr(a, dt):
             if a is None:
                 return None
@@ -300,7 +300,7 @@ class GpuStateManager:
         keep = []
         b = N.ReadBatch(int(len(d["pos0"])), ptr(d["pos0"], np.int32), ptr(d["flag"], np.uint16), ptr(d["cigar_off"], np.int64), ptr(d["cigar"], np.uint32),
                         ptr(d["seq_off"], np.int64), ptr(d["bases"], np.uint8), ptr(d["quals"], np.uint8), ptr(d.get("base_dirs"), np.uint8),
-                        ptr(d.get("collapsed"), np.uint8))
+                        ptr(d.get("collapsed"), np.uint8), ptr(d.get("amplicon"), np.int32))
         self._chk(self._L.pb2_push_reads(self._h, C.byref(b)))
 
     @staticmethod
@@ -320,7 +320,7 @@ class GpuStateManager:
                 break
             cap = int(ne)
         out = {k: d[k] for k in ("pos0", "flag", "cigar_off", "cigar", "seq_off")}
-        out.update(seq=seq, exc_index=ei[:ne].copy(), exc_base=eb[:ne].copy(), exc_qual=eq[:ne].copy(), base_dirs=d.get("base_dirs"), collapsed=d.get("collapsed"))
+        out.update(seq=seq, exc_index=ei[:ne].copy(), exc_base=eb[:ne].copy(), exc_qual=eq[:ne].copy(), base_dirs=d.get("base_dirs"), collapsed=d.get("collapsed"), amplicon=d.get("amplicon"))
         return out
 
     def AddReadsPacked(self, d):
@@ -337,7 +337,7 @@ class GpuStateManager:
             return a.ctypes.data if len(a) else None
         b = N.PackedReadBatch(int(len(d["pos0"])), ptr(d["pos0"], np.int32), ptr(d["flag"], np.uint16), ptr(d["cigar_off"], np.int64), ptr(d["cigar"], np.uint32),
                               ptr(d["seq_off"], np.int64), ptr(d["seq"], np.uint8), int(len(d["exc_index"])), ptr(d["exc_index"], np.int64), ptr(d["exc_base"], np.uint8),
-                              ptr(d["exc_qual"], np.uint8), ptr(d.get("base_dirs"), np.uint8), ptr(d.get("collapsed"), np.uint8))
+                              ptr(d["exc_qual"], np.uint8), ptr(d.get("base_dirs"), np.uint8), ptr(d.get("collapsed"), np.uint8), ptr(d.get("amplicon"), np.int32))
         self._chk(self._L.pb2_push_reads_packed(self._h, C.byref(b)))
 
     def AddReadBatch(self, batch):

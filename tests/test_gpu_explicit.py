@@ -367,7 +367,8 @@ def test_collapsed_stitched_full_text_golden_through_cuda_path():
     reads = json.load(open(os.path.join(G, "collapsed_stitched_reads.json")))
     seq = "N" * (9770498 - 1) + ("GAAGTAACAACGCAGGATGCCCCCTGGGGTGGACTGCCCCATGGAATTCTGGACCAAGGAGGAGAATCAGAGCGTTGTGGTTGACTTCCTGCTGCCCACAGGGGTCTACCTGAACTTCCCTGTGTCCCGCAATGCCAACCTC"
                                  "AGCACCATCAAGCAGGTATGGCCTCCATC")
-    pkw = dict(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, expect_stitched=1, expect_collapsed=1, skip_validation=1)
+    # AmpliconBiasFilterThreshold = 0.01F as the reference's test sets it (:719): tracking is on, the file has no XN tag, nothing is filtered
+    pkw = dict(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, expect_stitched=1, expect_collapsed=1, skip_validation=1, amplicon_bias_filter=0.01)
 
     def base_dirs(r):   # Read.SequencedBaseDirectionMap: the XD runs projected onto the read bases (Read.cs:390-421,664-682)
         exp, num = [], ""
@@ -432,7 +433,8 @@ def test_bam_file_to_vcf_text_through_the_library():
     want = [l.rstrip("\n") for l in open(os.path.join(G, "collapsed_stitched.records.vcf"))]
     for max_reads in (65536, 3, 1):   # streamed in tiny batches too: tagged and untagged reads mix, every batch has the same shape
         st = pb.BamReadStager(os.path.join(G, "collapsed.test.stitched.bam"), max_reads=max_reads)
-        sm = pb.GpuStateManager(pb.make_config(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, expect_stitched=1, expect_collapsed=1, skip_validation=1), "chr1", seq)
+        sm = pb.GpuStateManager(pb.make_config(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, expect_stitched=1, expect_collapsed=1, skip_validation=1, amplicon_bias_filter=0.01),
+                                "chr1", seq)
         for _, batch, _ in st:
             sm.AddReadBatch(batch)
         recs = pb.GpuAlleleCaller().Call(sm, raw=True)

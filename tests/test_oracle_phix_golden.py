@@ -57,7 +57,7 @@ def test_collapsed_stitched_full_text_golden():
     reads = json.load(open(os.path.join(G, "collapsed_stitched_reads.json")))
     seq = "N" * (9770498 - 1) + ("GAAGTAACAACGCAGGATGCCCCCTGGGGTGGACTGCCCCATGGAATTCTGGACCAAGGAGGAGAATCAGAGCGTTGTGGTTGACTTCCTGCTGCCCACAGGGGTCTACCTGAACTTCCCTGTGTCCCGCAATGCCAACCTC"
                                  "AGCACCATCAAGCAGGTATGGCCTCCATC")
-    kw = dict(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, source_is_stitched=1, source_is_collapsed=1, apply_validation=0)
+    kw = dict(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, source_is_stitched=1, source_is_collapsed=1, apply_validation=0, amplicon_bias_filter=0.01)   # :719
     c = ob.Caller(ob.default_config(**kw), "chr1", seq)
     for r in reads:
         c.add_read(ob.SimpleRead(r["pos0"] + 1, r["seq"], r["cigar"], r["qual"], flag=r["flag"], mapq=r["mapq"], has_tags=True, xd=r["xd"], xr=r["xr"],

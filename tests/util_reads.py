@@ -139,3 +139,58 @@ def to_product(rd):
 def oracle_cfg_from(**kw):
     """Oracle config with the same knobs the product config takes (names of po_config)."""
     return ob.default_config(**kw)
+
+
+def make_amplicon_reads(seed=0, n_amp=4, per_amp=200, read_len=140, stride=100, untagged=30, jitter=2, variants=None):
+    """Amplicon-shaped reads as a struct of arrays (pb2_read_batch layout + "amplicon", the XN name as an id, -1 = no tag): amplicon a covers about
+    [20 + a * stride, +read_len), neighbours overlap by read_len - stride. All reads are one 'M' run. variants: list of (position 1-based, {amplicon id: vaf})
+    (key -1: the untagged reads); the alt base is the reference base's successor in ACGT. Reads come out sorted by position, amplicons interleaved."""
+    rng = np.random.default_rng(seed)
+    L = 20 + (n_amp - 1) * stride + read_len + jitter + 40
+    ref = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)].copy()
+    starts, names = [], []
+    for a in range(n_amp):
+        starts.append(20 + a * stride + rng.integers(0, jitter + 1, per_amp))
+        names.append(np.full(per_amp, a))
+    if untagged:
+        starts.append(rng.integers(20, L - read_len - 1, untagged))
+        names.append(np.full(untagged, -1))
+    starts = np.concatenate(starts).astype(np.int32)
+    names = np.concatenate(names).astype(np.int32)
+    order = np.argsort(starts, kind="stable")
+    starts, names = starts[order], names[order]
+    n = len(starts)
+    idx = starts[:, None] + np.arange(read_len)[None, :]          # 0-based reference index of every base
+    bases = ref[idx].copy()
+    nxt = np.zeros(256, dtype=np.uint8)
+    for x, y in zip(b"ACGT", b"CGTA"):
+        nxt[x] = y
+    for pos, vafs in (variants or []):
+        col = pos - 1 - starts
+        for name, vaf in vafs.items():
+            hit = (names == name) & (col >= 0) & (col < read_len) & (rng.random(n) < vaf)
+            rows = np.nonzero(hit)[0]
+            bases[rows, col[rows]] = nxt[ref[pos - 1]]
+    quals = rng.integers(30, 41, size=bases.shape).astype(np.uint8)
+    low = rng.random(bases.shape) < 0.06
+    quals[low] = rng.integers(2, 20, size=int(low.sum()))
+    err = rng.random(bases.shape) < 0.002
+    bases[err] = nxt[bases[err]]
+    flag = np.where(rng.random(n) < 0.5, 0x10, 0).astype(np.uint16)
+    return dict(ref=ref, pos0=starts, flag=flag, cigar_off=np.arange(n + 1, dtype=np.int64), cigar=np.full(n, (read_len << 4) | 0, dtype=np.uint32),
+                seq_off=np.arange(n + 1, dtype=np.int64) * read_len, bases=bases.reshape(-1), quals=quals.reshape(-1), amplicon=names, n_loci=L)
+
+
+def amplicon_counts_at(d, pos, min_bq=20, alt=None):
+    """Per-amplicon (name -> count) of the reads' usable bases at 1-based pos (RegionState.AddAmpliconCount: every base counted as A/C/G/T at quality >=
+    min_bq), in first-seen order; with alt: only the bases equal to it (the support of the SNV candidate)."""
+    L = int(d["seq_off"][1] - d["seq_off"][0])
+    col = pos - 1 - d["pos0"]
+    out = {}
+    for r in np.nonzero((col >= 0) & (col < L))[0]:
+        k = int(d["seq_off"][r]) + int(col[r])
+        b, q, a = int(d["bases"][k]), int(d["quals"][k]), int(d["amplicon"][r])
+        if a < 0 or q < min_bq or b not in b"ACGT" or (alt is not None and b != alt):
+            continue
+        out[a] = out.get(a, 0) + 1
+    return out
