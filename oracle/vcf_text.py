@@ -7,6 +7,8 @@ reference's full-text goldens can be compared line by line:
 """
 from decimal import ROUND_HALF_UP, Decimal
 
+import numpy as np
+
 GT_STR = {"HomozygousAlt": "1/1", "HomozygousRef": "0/0", "HeterozygousAltRef": "0/1", "HeterozygousAlt1Alt2": "1/2", "RefLikeNoCall": "./.",
           "AltLikeNoCall": "./.", "RefAndNoCall": "0/.", "AltAndNoCall": "1/.", "HemizygousAlt": "1", "HemizygousNoCall": ".", "HemizygousRef": "0",
           "Others": "2/2"}
@@ -29,9 +31,10 @@ def _float_tostring(x):
     return s
 
 
-def _fixed(x, decimals):
-    """Custom numeric format "0.000…": .NET rounds the shortest-15-digit decimal half away from zero."""
-    d = Decimal(repr(float(x)))
+def _fixed(x, decimals, single=False):
+    """Custom numeric format "0.000…": .NET rounds the shortest-15-digit decimal half away from zero. single: the value is a C# float, which
+    float.ToString (netcoreapp2.0, Number.FormatSingle) first reduces to 7 significant digits."""
+    d = Decimal("%.6e" % float(np.float32(x))) if single else Decimal(repr(float(x)))
     q = Decimal(1).scaleb(-decimals)
     s = str(d.quantize(q, rounding=ROUND_HALF_UP))
     return s
@@ -78,7 +81,7 @@ class VcfText:
             vf = np.float32(0) if rec.total_coverage == 0 else np.float32(1) - freq
         else:
             vf = freq
-        fmt, sample = "GT:GQ:AD:DP:VF", f"{GT_STR[gt]}:{rec.gq}:{ad}:{depth}:{_fixed(float(vf), self.vf_decimals)}"
+        fmt, sample = "GT:GQ:AD:DP:VF", f"{GT_STR[gt]}:{rec.gq}:{ad}:{depth}:{_fixed(float(vf), self.vf_decimals, single=True)}"
         if self.out_sb:
             sb = min(max(-100.0, rec.gatk_bias_score), 0.0)
             fmt += ":NL:SB"
@@ -133,17 +136,21 @@ class VcfText:
         freq = np.float32(first.frequency)                                                          # GetFrequencyString (:329-358)
         if is_ref:
             vf = float(np.float32(0) if first.total_coverage == 0 else np.float32(1) - freq)
+        vf_is_double = False
+        if is_ref:
+            pass
         elif gt in ("HeterozygousAlt1Alt2", "Alt12LikeNoCall"):
             vf = sum(float(r.allele_support) / float(depth) for r in recs)
+            vf_is_double = True
         else:
             vf = float(freq)
-        fmt, sample = "GT:GQ:AD:DP:VF", f"{GT_STR[gt]}:{gq}:{ad}:{depth}:{_fixed(vf, self.vf_decimals)}"
+        fmt, sample = "GT:GQ:AD:DP:VF", f"{GT_STR[gt]}:{gq}:{ad}:{depth}:{_fixed(vf, self.vf_decimals, single=not vf_is_double)}"
         if self.out_sb:
             fmt += ":NL:SB"
             sample += f":{first.noise_level}:{_fixed(min(max(-100.0, first.gatk_bias_score), 0.0), 4)}"
         if self.nc:
             fmt += ":NC"
-            sample += ":" + _fixed(float(np.float32(first.fraction_no_calls)), 4)
+            sample += ":" + _fixed(float(np.float32(first.fraction_no_calls)), 4, single=True)
         return "\t".join([chrom, str(first.pos), ".", ref, alt, str(vq), ";".join(names) if names else "PASS", f"DP={depth}", fmt, sample])
 
 

@@ -614,7 +614,21 @@ static int finish_segment(pb2_handle* h, Segment& s, bool counters_already_copie
 static int run_segment(pb2_handle* h, Segment& s, int32_t* counts_out, int32_t* collapsed_out, const int32_t* d_gapped = nullptr) {
     int rc = enqueue_segment(h, s, counts_out, collapsed_out, d_gapped);
     if (rc == PB2_OK) rc = amplicon_pass(h, s, h->stream);
-    return rc != PB2_OK ? rc : finish_segment(h, s);
+    if (rc == PB2_OK) rc = finish_segment(h, s);
+    if (rc == PB2_ERR_NOMEM && (int64_t)h->h_counters[0] > s.var_capacity) {
+        // up to three SNV alleles per locus can be callable (permissive thresholds on deep, noisy data): the stream is sized for one per locus, the
+        // counter holds the exact need - grow and run the segment again
+        const int64_t need = (int64_t)h->h_counters[0];
+        pool_free(h, s.var_records);
+        s.var_records = nullptr;
+        s.var_capacity = need + 1024;
+        s.alloc_var = sizeof(pb2_call_record) * (size_t)s.var_capacity;
+        CU(h, pool_alloc(h, (void**)&s.var_records, s.alloc_var));
+        rc = enqueue_segment(h, s, counts_out, collapsed_out, d_gapped);
+        if (rc == PB2_OK) rc = amplicon_pass(h, s, h->stream);
+        if (rc == PB2_OK) rc = finish_segment(h, s);
+    }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ the device read store
@@ -785,6 +799,7 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
             case 2: return fail(h, PB2_ERR_ARG, "Invalid cigar: does not match length of read");   // Read.cs:603-605
             case 3: return fail(h, PB2_ERR_ARG, "Position must be greater than 0.");               // RegionStateManager.cs:363-364
             case 5: return fail(h, PB2_ERR_ARG, "The input is collapsed BAM, but a read is not a collapsed read.");   // CollapedRegionStateManager.cs:40-43
+            case 6: return fail(h, PB2_ERR_UNSUPPORTED, "pb2_push_reads: an insertion or deletion longer than 65534 bases");
             default: return fail(h, PB2_ERR_ARG, "pb2_push_reads: offsets not monotone");
         }
     }

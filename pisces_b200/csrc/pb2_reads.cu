@@ -323,6 +323,7 @@ __global__ void reads_ingest_kernel(ReadsView rv, int32_t first_read, int64_t ci
                 const uint32_t c = rv.cigar[k];
                 const int op = c & 15;
                 if (op > 8) { err = 1; break; }
+                if ((op == 1 || op == 2) && (c >> 4) > 65534u) { err = 6; break; }   // candidate allele lengths travel as 16-bit fields
                 if (op_read_span(op)) rs += c >> 4;
                 if (op_ref_span(op)) fs += c >> 4;
             }

@@ -60,6 +60,37 @@ std::string fixed_half_up(double x, int decimals) {
     if (decimals > 0) out += "." + digits.substr(il);
     return out;
 }
+// The same custom format on a C# float (CalledAllele.Frequency, FractionNoCalls): float.ToString of netcoreapp2.0 first reduces the value to 7
+// significant digits (Number.FormatSingle: FLOAT_PRECISION) and rounds THAT decimal half away from zero - 21/2000 = 0.0105f is 0.01049999986 as a
+// double but "0.0105" in 7 digits, and prints 0.011 at three places.
+std::string fixed_half_up_f32(float x, int decimals) {
+    if (!std::isfinite(x)) return fixed_half_up((double)x, decimals);
+    char e[40];
+    snprintf(e, sizeof(e), "%.6e", (double)std::fabs(x));   // d.dddddde+XX: 7 significant digits, correctly rounded
+    std::string mant;
+    mant.push_back(e[0]);
+    mant.append(e + 2, 6);
+    const int exp10 = atoi(e + 9);
+    // value = 0.mant x 10^(exp10 + 1): spell it as integer part + fraction digits, then round at `decimals`
+    std::string ip, fp;
+    const int point = exp10 + 1;
+    if (point <= 0) { ip = "0"; fp = std::string((size_t)(-point), '0') + mant; }
+    else if (point >= (int)mant.size()) { ip = mant + std::string((size_t)(point - (int)mant.size()), '0'); }
+    else { ip = mant.substr(0, (size_t)point); fp = mant.substr((size_t)point); }
+    while ((int)fp.size() < decimals + 1) fp.push_back('0');
+    const bool up = fp[(size_t)decimals] >= '5';
+    std::string digits = ip + fp.substr(0, (size_t)decimals);
+    if (up) {
+        int i = (int)digits.size() - 1;
+        while (i >= 0) { if (digits[(size_t)i] == '9') { digits[(size_t)i] = '0'; i--; } else { digits[(size_t)i]++; break; } }
+        if (i < 0) digits.insert(digits.begin(), '1');
+    }
+    const size_t il = digits.size() - (size_t)decimals;
+    std::string body = digits.substr(0, il);
+    if (decimals > 0) body += "." + digits.substr(il);
+    const bool neg = std::signbit(x) && body.find_first_not_of("0.") != std::string::npos;
+    return (neg ? "-" : "") + body;
+}
 const char* genotype_string(int gt) {   // VcfFormatter.MapGenotype (:184-215)
     switch (gt) {
         case GT_HOM_ALT: return "1/1";
@@ -188,13 +219,17 @@ extern "C" int pb2_vcf_format(pb2_handle* h, const pb2_call_record* recs, const 
         } else ad = std::to_string(r.reference_support) + "," + std::to_string(r.allele_support);
         // VF (:329-358): SumMultipleVF for 1/2 and Alt12LikeNoCall (a double sum), else the first allele's float Frequency
         const float freq = r.total_coverage == 0 ? 0.0f : std::min((float)r.allele_support / (float)r.total_coverage, 1.0f);
-        double vf = is_ref ? (double)(r.total_coverage == 0 ? 0.0f : 1.0f - freq) : (double)freq;
+        const float vf32 = is_ref ? (r.total_coverage == 0 ? 0.0f : 1.0f - freq) : freq;
+        double vf = (double)vf32;
+        bool vf_is_double = false;
         if (!is_ref && (gt == GT_HET_ALT12 || gt == GT_ALT12_NOCALL)) {
             vf = 0;
+            vf_is_double = true;
             for (size_t k = 0; k < nv; k++) vf += (double)v[k]->allele_support / (double)depth;
         }
         std::string fmt = "GT:GQ:AD:DP:VF";
-        std::string sample = std::string(genotype_string(gt)) + ":" + std::to_string(gq) + ":" + ad + ":" + std::to_string(depth) + ":" + fixed_half_up(vf, vf_decimals);
+        std::string sample = std::string(genotype_string(gt)) + ":" + std::to_string(gq) + ":" + ad + ":" + std::to_string(depth) + ":" +
+                             (vf_is_double ? fixed_half_up(vf, vf_decimals) : fixed_half_up_f32(vf32, vf_decimals));
         if (out_sb) {
             double sb = r.gatk_bias_score > -100.0 ? r.gatk_bias_score : -100.0;   // [-100, 0] (VcfWritingParameters.cs:14-15)
             sb = sb < 0.0 ? sb : 0.0;
@@ -203,7 +238,7 @@ extern "C" int pb2_vcf_format(pb2_handle* h, const pb2_call_record* recs, const 
         }
         if (o.report_no_calls) {   // NC (:257-263)
             fmt += ":NC";
-            sample += ":" + fixed_half_up((double)r.fraction_no_calls, 4);
+            sample += ":" + fixed_half_up_f32(r.fraction_no_calls, 4);
         }
         if (o.report_rc_counts) {   // US (:283-316)
             static const int with_ts[6] = {0, 1, 4, 5, 6, 7}, without_ts[4] = {0, 1, 2, 3};

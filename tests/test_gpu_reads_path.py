@@ -229,3 +229,30 @@ def test_invalid_reads_are_rejected_as_the_reference_does():
     sm.AddAlleleCounts(pb.Read(5, "ACGTACGT", "8M", [30] * 8))   # the handle stays usable
     assert len(pb.GpuAlleleCaller().Call(sm, raw=True)) > 0
     sm.close()
+
+
+def test_oversized_indel_is_refused():
+    pb = _pb()
+    sm = pb.GpuStateManager(pb.make_config(), "chr1", "ACGT" * 50)
+    with pytest.raises(pb.PiscesB200Error, match="65534"):
+        sm.AddAlleleCounts(pb.Read(5, "ACGTACGT", "4M70000D4M", [30] * 8))
+    sm.close()
+
+
+def test_variant_stream_larger_than_one_record_per_locus():
+    """Permissive thresholds on deep noisy data: up to three SNV alleles per locus are callable, more records than the one-per-locus stream the segment starts
+    with - the flush grows the stream to the counter's exact need and runs the segment again (no PB2_ERR_NOMEM), records equal to the oracle's."""
+    pb = _pb()
+    cfg = dict(output_gvcf=0, min_frequency=0.0002, min_frequency_filter=0.0002, min_variant_qscore=0, variant_qscore_filter=0, min_coverage=1, forced_noise_level=60)
+    d = synth.make_reads(1000, 6000, seed=21, indel_rate=0.0, snv_rate=0.3)
+    okw = dict(output_gvcf=0, min_frequency=0.0002, min_frequency_filter=0.0002, min_vq=0, vq_filter=0, min_coverage=1, forced_noise_level=60)
+    oc = _oracle(d, **okw)
+    oc.finish()
+    orecs = oc.records()
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode())
+    sm.AddReadsSoA(d)
+    precs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    arena = sm.AlleleArena()
+    sm.close()
+    assert len(orecs) > 1024 and len(orecs) > len(d["ref"])   # more than one per staged locus
+    compare_records(orecs, precs, arena)

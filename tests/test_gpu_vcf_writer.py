@@ -73,3 +73,17 @@ def test_uncrushed_somatic_line():
     got = sm.FormatVcf(_records([r]), report_no_calls=True)
     sm.close()
     assert got == ["chr4\t55141055\t.\tA\tG\t0\tPASS\tDP=5394\tGT:GQ:AD:DP:VF:NL:SB:NC\t1/1:0:7,5387:5394:0.9987:23:0.0000:0.0000"]
+
+
+def test_float_fields_round_from_seven_significant_digits():
+    """VF and NC are C# floats formatted from their 7-significant-digit decimal (float.ToString, netcoreapp2.0): 21/2000 prints 0.011, not the 0.010 the
+    float widened to double would give. Same cases as tests/test_oracle_vcf_writer.py."""
+    import pisces_b200 as pb
+    sm = pb.GpuStateManager(pb.make_config(min_frequency=0.01, min_frequency_filter=0.01), "chr4", "ACGTACGT")   # three VF decimals
+    for support, coverage, want in ((21, 2000, "0.011"), (1, 400, "0.003"), (29, 2000, "0.015"), (1, 3, "0.333"), (1, 8, "0.125"), (2, 3, "0.667")):
+        r = _allele(100, SNV, "A", "G", support, 2)   # HeterozygousAltRef
+        r["total_coverage"], r["reference_support"] = coverage, coverage - support
+        r["fraction_no_calls"] = np.float32(0.00105)
+        sample = sm.FormatVcf(_records([r]), report_no_calls=True)[0].split("\t")[-1].split(":")
+        assert sample[4] == want and sample[-1] == "0.0011", (support, coverage, sample)
+    sm.close()

@@ -3,6 +3,8 @@ own writer golden and literal asserts (src/test/Pisces.IO.Tests/UnitTests/VcfFil
 import os
 from types import SimpleNamespace
 
+import numpy as np
+
 from oracle import binding as ob
 from oracle.vcf_text import VcfText, pad_positions
 
@@ -53,3 +55,19 @@ def test_padding_walk():
     assert pad_positions([(2, 3), (4, 4), (9, 10)], [3, 7, 10]) == [("pad", 2), ("call", 3), ("pad", 4), ("call", 7), ("pad", 9), ("call", 10)]
     assert pad_positions([(5, 6)], [], write_remaining=True) == [("pad", 5), ("pad", 6)]
     assert pad_positions([(5, 6)], [1], write_remaining=False) == [("call", 1)]
+
+
+def test_float_fields_round_from_seven_significant_digits():
+    """VF and NC are C# floats: float.ToString("0.000") of netcoreapp2.0 reduces the value to 7 significant digits first (Number.FormatSingle) and rounds
+    that decimal half away from zero. 21/2000 = 0.0105f is 0.01049999986 as a double but prints 0.011; 1/400 and 29/2000 are ties of the same kind."""
+    vt = VcfText(ob.default_config(min_frequency=0.01, min_frequency_filter=0.01), ob.FILTERS, ob.GENOTYPES)   # three VF decimals
+    vt.nc = True
+    for support, coverage, want in ((21, 2000, "0.011"), (1, 400, "0.003"), (29, 2000, "0.015"), (1, 3, "0.333"), (1, 8, "0.125"), (2, 3, "0.667")):
+        a = _allele(100, SNV, "A", "G", support, "HeterozygousAltRef", coverage=coverage, ref_support=coverage - support)
+        a.fraction_no_calls = float(np.float32(support) / np.float32(coverage + support))
+        sample = vt.crushed_line("chr4", [a]).split("\t")[-1].split(":")
+        assert sample[4] == want, (support, coverage, sample)
+        assert vt.line("chr4", a).split("\t")[-1].split(":")[4] == want
+    a = _allele(100, SNV, "A", "G", 21, "HeterozygousAltRef", coverage=2000, ref_support=1979)
+    a.fraction_no_calls = float(np.float32(0.00105))
+    assert vt.crushed_line("chr4", [a]).split("\t")[-1].split(":")[-1] == "0.0011"
