@@ -960,7 +960,11 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
     // loci: the whole span, or — with intervals — the interval positions inside 1000-bp blocks some read touched
     // (reference candidates are only generated for existing blocks: RegionStateManager.cs:295-314, RegionState.cs:393-399)
     std::vector<int32_t> positions, index_of_pos;
-    if (h->have_intervals) {
+    // without intervals the reads of one flush can still lie far apart (an amplicon panel run without an interval file): past a million positions of
+    // span the touched blocks are looked at, and if they are the smaller half only their positions are staged (the reference only ever creates the
+    // blocks reads touch, RegionStateManager.cs:361-383) - through the same positions[] / index_of_pos indirection as interval runs
+    bool listed = h->have_intervals;
+    if (h->have_intervals || span > (1 << 20)) {
         const int b0 = (lo - 1) / 1000, nbk = (hi - 1) / 1000 - b0 + 1;
         std::vector<uint32_t> bits((size_t)(nbk + 31) / 32, 0);
         uint32_t* d_bits = nullptr;
@@ -972,26 +976,34 @@ static int stage_reads_segment(pb2_handle* h, int32_t cleared_end, int32_t clear
         CU(h, cudaStreamSynchronize(st));
         pool_free(h, d_bits);
         auto touched = [&](int64_t p) { const int k = (int)((p - 1) / 1000) - b0; return k >= 0 && k < nbk && ((bits[(size_t)k >> 5] >> (k & 31)) & 1u); };
-        index_of_pos.assign((size_t)span, -1);
-        std::vector<std::pair<int32_t, int32_t>> iv;
-        for (size_t i = 0; i < h->iv_start.size(); i++) iv.push_back({h->iv_start[i], h->iv_end[i]});
-        std::sort(iv.begin(), iv.end());
-        for (auto& v : iv)
-            for (int64_t p = std::max<int64_t>(v.first, lo); p <= std::min<int64_t>(v.second, hi); p++)
-                if (index_of_pos[(size_t)(p - lo)] < 0 && touched(p)) index_of_pos[(size_t)(p - lo)] = 0;
-        for (int64_t k = 0; k < span; k++)
-            if (index_of_pos[(size_t)k] == 0) { index_of_pos[(size_t)k] = (int32_t)positions.size(); positions.push_back((int32_t)(lo + k)); }
-        if (positions.empty()) return PB2_OK;
+        if (!h->have_intervals) {
+            int64_t n_touched = 0;
+            for (uint32_t w : bits) n_touched += __builtin_popcount(w);
+            listed = n_touched * 1000 * 2 < span;
+        }
+        if (listed) {
+            index_of_pos.assign((size_t)span, -1);
+            std::vector<std::pair<int32_t, int32_t>> iv;
+            if (h->have_intervals) for (size_t i = 0; i < h->iv_start.size(); i++) iv.push_back({h->iv_start[i], h->iv_end[i]});
+            else iv.push_back({lo, hi});
+            std::sort(iv.begin(), iv.end());
+            for (auto& v : iv)
+                for (int64_t p = std::max<int64_t>(v.first, lo); p <= std::min<int64_t>(v.second, hi); p++)
+                    if (index_of_pos[(size_t)(p - lo)] < 0 && touched(p)) index_of_pos[(size_t)(p - lo)] = 0;
+            for (int64_t k = 0; k < span; k++)
+                if (index_of_pos[(size_t)k] == 0) { index_of_pos[(size_t)k] = (int32_t)positions.size(); positions.push_back((int32_t)(lo + k)); }
+            if (positions.empty()) return PB2_OK;
+        }
     }
-    const int64_t n_loci = h->have_intervals ? (int64_t)positions.size() : span;
+    const int64_t n_loci = listed ? (int64_t)positions.size() : span;
     int32_t *d_index = nullptr, *d_index_ge = nullptr;
     Segment s;
     s.n_loci = n_loci;
     s.n_tiles = (int32_t)((n_loci + kTileLoci - 1) / kTileLoci);
     s.first_position = lo;
-    s.has_positions = h->have_intervals;
+    s.has_positions = listed;
     s.temporary = temporary;
-    if (h->have_intervals) {
+    if (listed) {
         CU(h, pool_alloc_t(h, &d_index, index_of_pos.size()));
         CU(h, cudaMemcpyAsync(d_index, index_of_pos.data(), sizeof(int32_t) * index_of_pos.size(), cudaMemcpyHostToDevice, st));
         std::vector<int32_t> index_ge((size_t)span + 1);

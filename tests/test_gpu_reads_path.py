@@ -256,3 +256,35 @@ def test_variant_stream_larger_than_one_record_per_locus():
     sm.close()
     assert len(orecs) > 1024 and len(orecs) > len(d["ref"])   # more than one per staged locus
     compare_records(orecs, precs, arena)
+
+
+@pytest.mark.parametrize("gvcf", [0, 1])
+def test_reads_far_apart_without_intervals_stage_only_touched_blocks(gvcf):
+    """Two read clusters 3 Mbp apart in one flush, no interval file: only the positions of the 1000-bp blocks reads touch are staged (the reference only
+    creates those blocks, RegionStateManager.cs:361-383), records equal to the oracle's."""
+    pb = _pb()
+    d = synth.make_reads(3000, 80, seed=31, indel_rate=0.002)
+    far = 3_000_000
+    n = len(d["pos0"])
+    ref = np.frombuffer(b"ACGT", dtype=np.uint8)[np.random.default_rng(1).integers(0, 4, far + len(d["ref"]) + 10)].copy()
+    ref[: len(d["ref"])] = d["ref"]
+    ref[far: far + len(d["ref"])] = d["ref"]
+    both = dict(ref=ref, pos0=np.concatenate([d["pos0"], d["pos0"] + far]), flag=np.concatenate([d["flag"], d["flag"]]),
+                cigar_off=np.concatenate([d["cigar_off"], d["cigar_off"][1:] + d["cigar_off"][-1]]), cigar=np.concatenate([d["cigar"], d["cigar"]]),
+                seq_off=np.concatenate([d["seq_off"], d["seq_off"][1:] + d["seq_off"][-1]]), bases=np.concatenate([d["bases"], d["bases"]]),
+                quals=np.concatenate([d["quals"], d["quals"]]))
+    assert len(both["pos0"]) == 2 * n
+    cfg = dict(output_gvcf=gvcf, collapse=1)
+    oc = _oracle(both, **cfg)
+    oc.finish()
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(ref).decode())
+    sm.AddReadsSoA(both)
+    sm.StageReads()
+    st = sm.stage_stats()
+    assert st["staged_bytes"] < st["rows"] * 32 + 1_000_000   # the rows of two clusters + their few tiles' tables, not three million empty loci
+    precs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    arena = sm.AlleleArena()
+    sm.close()
+    orecs = oc.records()
+    assert len(orecs) > 40 and any(o.pos > far for o in orecs)
+    compare_records(orecs, precs, arena)
