@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-jobs", type=int, default=3, help="concurrent (BAM x chromosome) jobs of the end-to-end leg: one handle + one host thread each, as Pisces -t N runs them")
     ap.add_argument("--e2e-input", default="packed", choices=["packed", "soa"], help="host form of the reads: one packed byte per base, or bases + qualities")
+    ap.add_argument("--gather", default="all", choices=["all", "root"], help="end-of-job exchange of the ranks' call records: all_gather, or gather to rank 0 (the writer)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -463,7 +464,7 @@ def main_ours(a):
         job_buf = torch.zeros(8 * n_slots + n_slots * cap_records * 96, dtype=torch.uint8, device=dev)
         sm.call_resident()               # replay once synchronously (the first call built the plan on the handle stream only)
         sm.set_resident_sink(job_buf.data_ptr(), cap_records, n_slots)
-        if world > 1:
+        if world > 1 and (a.gather == "all" or rank == 0):
             gather_out = torch.zeros(world * job_buf.numel(), dtype=torch.uint8, device=dev)
 
     def step(k=0):
@@ -478,8 +479,10 @@ def main_ours(a):
         if resident_ok:
             sm.sink_sort()
             n = sm.resident_sync()
-            if world > 1:
+            if world > 1 and a.gather == "all":
                 dist.all_gather_into_tensor(gather_out, job_buf)
+            elif world > 1:
+                dist.gather(job_buf, list(gather_out.view(world, -1).unbind(0)) if rank == 0 else None, dst=0)
             return n
         return None
 
