@@ -305,7 +305,7 @@ def main_c1(a):
                 sms[ref_id].DoneProcessing()
             sms[ref_id].AddReadBatch(batch)
         for ref_id in used:
-            n_rec += len(pb.GpuAlleleCaller().Call(sms[ref_id], raw=True))
+            n_rec += len(pb.GpuAlleleCaller().Call(sms[ref_id], raw=True, copy=False))
         st.close()
         return n_rec
     for _ in range(max(3, a.warmup)):
@@ -437,10 +437,10 @@ def main_ours(a):
     sm.AddReadsSoA(pinned)
     sm.StageReads()
     # the whole job from device-resident reads (candidates found again, pileup staged again, called): reported beside the staged-pileup step
-    sm.flush_resident()
+    sm.flush_resident(copy=False)
     t0 = time.perf_counter()
     for _ in range(2):
-        sm.flush_resident()
+        sm.flush_resident(copy=False)
     from_reads_ms = 1e3 * (time.perf_counter() - t0) / 2
     sm.StageReads()
     torch.cuda.synchronize()
@@ -469,7 +469,7 @@ def main_ours(a):
 
     def step(k=0):
         if not resident_ok:
-            return len(sm.flush_resident())
+            return len(sm.flush_resident(copy=False))
         sm.call_resident_async()         # enqueue only: the step's graph + the copy of its records into slot k of the job buffer
         return 0
 
@@ -528,7 +528,7 @@ def main_ours(a):
     else:
         blocks.append(dict(hot_launches=a.steps, hot_ms=0.0, total_launches=timed_launches))
         for _ in range(3):
-            sm.flush_resident()
+            sm.flush_resident(copy=False)
         st_ = sm.stats()
         blocks[0]["hot_ms"] = st_["hot_ms"] / max(1, st_["hot_launches"]) * a.steps
     st = {k: sum(b[k] for b in blocks) for k in ("hot_launches", "hot_ms", "total_launches")}
@@ -599,9 +599,9 @@ def main_ours(a):
                 sm2.AddReadsPacked(e2e_in)
             else:
                 sm2.AddReadsSoA(pinned)
-            return caller.Call(sm2, raw=True)
+            return caller.Call(sm2, raw=True, copy=False)   # the records, on the host, in the library's buffer (read in place, as a P/Invoke host would)
         for sm2 in sms:   # warm-up (allocations, block cache), and the records the oracle check below compares
-            precs = e2e_step(sm2)
+            precs = e2e_step(sm2).copy()
             arena = sm2.AlleleArena()
             e2e_step(sm2)
         counts = [0] * n_jobs

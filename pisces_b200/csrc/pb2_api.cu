@@ -7,6 +7,7 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <thread>
 #include "pb2_internal.hpp"
 
 using namespace pb2;
@@ -280,6 +281,8 @@ extern "C" void pb2_destroy(pb2_handle* h) {
     if (h->d_chr) cudaFree(h->d_chr);
     if (h->d_tile_counter) cudaFree(h->d_tile_counter);
     if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->pin_refs) cudaFreeHost(h->pin_refs);
+    if (h->pin_valid) cudaFreeHost(h->pin_valid);
     if (h->d_q_to_p) cudaFree(h->d_q_to_p);
     if (h->d_gq_tail) cudaFree(h->d_gq_tail);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1173,9 +1176,10 @@ __global__ static void sink_copy_kernel(const pb2_call_record* __restrict__ var,
                                         pb2_call_record* __restrict__ slot, int64_t slot_records) {
     const int64_t n = min((int64_t)counters[0], slot_records);
     if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = (long long)n;
-    const uint4* src = reinterpret_cast<const uint4*>(var);
-    uint4* dst = reinterpret_cast<uint4*>(slot);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * 6; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    // 8-byte words: the record blocks start 8 * n_slots bytes into the caller's buffer, which is 16-byte aligned only for an even number of slots
+    const uint2* src = reinterpret_cast<const uint2*>(var);
+    uint2* dst = reinterpret_cast<uint2*>(slot);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * 12; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 __global__ static void sink_keys_kernel(const long long* __restrict__ counts, const pb2_call_record* __restrict__ slots, int64_t slot_records, int32_t n_slots,
                                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx) {
@@ -1188,13 +1192,14 @@ __global__ static void sink_keys_kernel(const long long* __restrict__ counts, co
 }
 __global__ static void sink_gather_kernel(const pb2_call_record* __restrict__ in, const uint32_t* __restrict__ idx, int64_t n, pb2_call_record* __restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * 6) return;
-    reinterpret_cast<uint4*>(out)[t] = reinterpret_cast<const uint4*>(in)[(int64_t)idx[t / 6] * 6 + t % 6];
+    if (t >= n * 12) return;
+    reinterpret_cast<uint2*>(out)[t] = reinterpret_cast<const uint2*>(in)[(int64_t)idx[t / 12] * 12 + t % 12];
 }
 cudaError_t sink_sort_pairs(void* temp, size_t& temp_bytes, const unsigned long long* kin, unsigned long long* kout, const uint32_t* vin, uint32_t* vout, int64_t n, cudaStream_t st);
 
 extern "C" int pb2_set_resident_sink(pb2_handle* h, void* device_buffer, int64_t slot_records, int32_t n_slots) {
-    if (!h || (device_buffer && (slot_records < 1 || n_slots < 1))) return fail(h, PB2_ERR_ARG, "pb2_set_resident_sink: bad argument");
+    if (!h || (device_buffer && (slot_records < 1 || n_slots < 1 || (reinterpret_cast<uintptr_t>(device_buffer) & 7))))
+        return fail(h, PB2_ERR_ARG, "pb2_set_resident_sink: bad argument (the buffer must be 8-byte aligned)");
     h->sink = device_buffer; h->sink_slot_records = slot_records; h->sink_slots = device_buffer ? n_slots : 0; h->sink_next = 0;
     return PB2_OK;
 }
@@ -1203,7 +1208,7 @@ static int sink_append(pb2_handle* h, Segment& s) {
     const int32_t slot = (int32_t)(h->sink_next++ % h->sink_slots);
     long long* counts = reinterpret_cast<long long*>(h->sink);
     pb2_call_record* slots = reinterpret_cast<pb2_call_record*>(reinterpret_cast<uint8_t*>(h->sink) + 8 * (size_t)h->sink_slots);
-    const int blocks = (int)std::min<int64_t>((h->sink_slot_records * 6 + 255) / 256, 2048);
+    const int blocks = (int)std::min<int64_t>((h->sink_slot_records * 12 + 255) / 256, 2048);
     sink_copy_kernel<<<blocks, 256, 0, h->stream>>>(s.var_records, s.counters, counts + slot, slots + (int64_t)slot * h->sink_slot_records, h->sink_slot_records);
     h->total_launches += 1;
     return cudaGetLastError() == cudaSuccess ? PB2_OK : fail(h, PB2_ERR_CUDA, "sink_copy_kernel launch failed");
@@ -1226,7 +1231,7 @@ extern "C" int pb2_sink_sort(pb2_handle* h) {
     CU(h, pool_alloc_t(h, &tmp, (size_t)n)); CU(h, pool_alloc(h, &temp, tb + 16));
     sink_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(counts, slots, h->sink_slot_records, h->sink_slots, k0, i0);
     CU(h, sink_sort_pairs(temp, tb, k0, k1, i0, i1, n, h->stream));
-    sink_gather_kernel<<<(unsigned)((n * 6 + 255) / 256), 256, 0, h->stream>>>(slots, i1, n, tmp);
+    sink_gather_kernel<<<(unsigned)((n * 12 + 255) / 256), 256, 0, h->stream>>>(slots, i1, n, tmp);
     CU(h, cudaMemcpyAsync(slots, tmp, sizeof(pb2_call_record) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
     h->total_launches += 4;
     void* ptrs[] = {k0, k1, i0, i1, tmp, temp};
@@ -1644,8 +1649,8 @@ static void germline_locus_pass(pb2_handle* h) {
     const bool germline = d.ploidy != PLOIDY_SOMATIC;
     const bool locus_processor = h->cfg.ploidy == PLOIDY_DIPLOID;   // follows the SAMPLE ploidy (Factory.cs:145-147)
     if (!germline && !locus_processor) return;
-    std::vector<pb2_call_record>& R = h->h_out;
-    std::vector<pb2_call_record_ext>& E = h->h_out_ext;
+    auto& R = h->h_out;
+    auto& E = h->h_out_ext;
     auto freq_of = [](int support, int total) { return total == 0 ? 0.0f : std::min((float)support / (float)total, 1.0f); };
     std::vector<uint8_t> drop(R.size(), 0);
     bool any_drop = false;
@@ -1825,6 +1830,13 @@ static int compact_reads(pb2_handle* h, int32_t cleared_to) {
     return PB2_OK;
 }
 
+template <class T>
+struct HostSpan {
+    T* p = nullptr;
+    size_t n = 0;
+    bool empty() const { return n == 0; }
+    T& operator[](size_t i) const { return p[i]; }
+};
 static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n, bool keep_reads);
 extern "C" int pb2_flush(pb2_handle* h, int32_t up_to_position, const pb2_call_record** out, int64_t* n) { return flush_impl(h, up_to_position, out, n, false); }
 // IAlleleCaller.Call for everything staged through pb2_push_reads, the reads staying on the device: the candidates are found again in the stored reads
@@ -1905,13 +1917,25 @@ static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_reco
         std::vector<uint32_t> exc((size_t)s.h_exc_count * 2);
         if (!exc.empty()) CU(h, cudaMemcpyAsync(exc.data(), s.exc_entries, sizeof(uint32_t) * exc.size(), cudaMemcpyDeviceToHost, h->stream));
         if (!hot_vars.empty()) CU(h, cudaMemcpyAsync(hot_vars.data(), s.var_records, sizeof(pb2_call_record) * hot_vars.size(), cudaMemcpyDeviceToHost, h->stream));
-        std::vector<pb2_call_record> refs;
-        std::vector<uint8_t> valid;
+        // the dense reference stream lands in pinned memory the handle keeps (96 MB per million loci: a pageable vector made this copy the flush's
+        // largest item, at a tenth of the link's rate and with a page fault per 4 KB)
+        HostSpan<pb2_call_record> refs;
+        HostSpan<uint8_t> valid;
         if (s.ref_records) {
-            refs.resize((size_t)s.n_loci);
-            valid.resize((size_t)s.n_loci);
-            CU(h, cudaMemcpyAsync(refs.data(), s.ref_records, sizeof(pb2_call_record) * refs.size(), cudaMemcpyDeviceToHost, h->stream));
-            CU(h, cudaMemcpyAsync(valid.data(), s.ref_valid, valid.size(), cudaMemcpyDeviceToHost, h->stream));
+            auto pinned = [&](void*& p, size_t& have, size_t need) -> cudaError_t {
+                if (need <= have) return cudaSuccess;
+                if (p) cudaFreeHost(p);
+                p = nullptr; have = 0;
+                const cudaError_t e = cudaHostAlloc(&p, need + need / 4, cudaHostAllocDefault);
+                if (e == cudaSuccess) have = need + need / 4;
+                return e;
+            };
+            CU(h, pinned(h->pin_refs, h->pin_refs_bytes, sizeof(pb2_call_record) * (size_t)s.n_loci));
+            CU(h, pinned(h->pin_valid, h->pin_valid_bytes, (size_t)s.n_loci));
+            refs = HostSpan<pb2_call_record>{static_cast<pb2_call_record*>(h->pin_refs), (size_t)s.n_loci};
+            valid = HostSpan<uint8_t>{static_cast<uint8_t*>(h->pin_valid), (size_t)s.n_loci};
+            CU(h, cudaMemcpyAsync(refs.p, s.ref_records, sizeof(pb2_call_record) * refs.n, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaMemcpyAsync(valid.p, s.ref_valid, valid.n, cudaMemcpyDeviceToHost, h->stream));
         }
         if (d_collapsed) {
             collapsed.resize((size_t)s.n_loci * kNumCollapsed);
@@ -2004,18 +2028,59 @@ static int flush_impl(pb2_handle* h, int32_t up_to_position, const pb2_call_reco
             while (vi < vars.size() && vars[vi].r.position <= cleared_to) emit(vars[vi++]);
             continue;
         }
-        for (int64_t i = 0; i < s.n_loci; i++) {
-            const int32_t pos = s.has_positions ? s.h_positions[(size_t)i] : s.first_position + (int32_t)i;
-            if (pos > cleared_to) break;
-            while (vi < vars.size() && vars[vi].r.position < pos) emit(vars[vi++]);
-            bool variant_here = false;
-            while (vi < vars.size() && vars[vi].r.position == pos) { emit(vars[vi++]); variant_here = true; }
-            if (!refs.empty() && valid[(size_t)i] && !variant_here) {
-                auto ov = ref_override.find(pos);
-                emit(ov == ref_override.end() ? with_totals(OutRec{refs[(size_t)i], zero_ext}) : ov->second);
+        // Two passes: the walk decides what goes where (a 4-byte plan entry per output record: reference locus i, or variant k), the fill copies the
+        // 96 + 80 bytes per record with a few host threads - a gVCF chromosome is a million reference records per million loci, and one thread
+        // writes them at ~6 GB/s.
+        {
+            const bool owned = h->dcfg.own_hi > 0;
+            auto mine = [&](int32_t pos) { return !owned || (pos >= h->dcfg.own_lo && pos <= h->dcfg.own_hi); };
+            constexpr uint32_t kVar = 0x80000000u;
+            std::vector<uint32_t> plan;
+            plan.reserve((size_t)s.n_loci + vars.size());
+            std::vector<OutRec> overrides;   // reference records replaced by a reallocated MNV's (rare): planned as variants appended to `vars`
+            auto plan_var = [&](size_t k) { if (mine(vars[k].r.position)) plan.push_back(kVar | (uint32_t)k); };
+            const size_t n_vars = vars.size();
+            for (int64_t i = 0; i < s.n_loci; i++) {
+                const int32_t pos = s.has_positions ? s.h_positions[(size_t)i] : s.first_position + (int32_t)i;
+                if (pos > cleared_to) break;
+                while (vi < n_vars && vars[vi].r.position < pos) plan_var(vi++);
+                bool variant_here = false;
+                while (vi < n_vars && vars[vi].r.position == pos) { plan_var(vi++); variant_here = true; }
+                if (!refs.empty() && valid[(size_t)i] && !variant_here && mine(pos)) {
+                    auto ov = ref_override.empty() ? ref_override.end() : ref_override.find(pos);
+                    if (ov == ref_override.end()) plan.push_back((uint32_t)i);
+                    else { plan.push_back(kVar | (uint32_t)(n_vars + overrides.size())); overrides.push_back(ov->second); }
+                }
+            }
+            while (vi < n_vars && vars[vi].r.position <= cleared_to) plan_var(vi++);
+            const size_t base = h->h_out.size();
+            h->h_out.resize(base + plan.size());
+            h->h_out_ext.resize(base + plan.size());
+            pb2_call_record* out_r = h->h_out.data() + base;
+            pb2_call_record_ext* out_e = h->h_out_ext.data() + base;
+            auto fill = [&](size_t a, size_t b) {
+                for (size_t j = a; j < b; j++) {
+                    const uint32_t e = plan[j];
+                    if (e & kVar) {
+                        const size_t k = e & ~kVar;
+                        const OutRec& o = k < n_vars ? vars[k] : overrides[k - n_vars];
+                        out_r[j] = o.r; out_e[j] = o.e;
+                    } else if (collapsed.empty()) {
+                        out_r[j] = refs[e]; out_e[j] = zero_ext;
+                    } else {
+                        const OutRec o = with_totals(OutRec{refs[e], zero_ext});
+                        out_r[j] = o.r; out_e[j] = o.e;
+                    }
+                }
+            };
+            const size_t n_threads = plan.size() < (1u << 16) ? 1 : std::min<size_t>(8, std::max<unsigned>(1, std::thread::hardware_concurrency() / 4));
+            if (n_threads <= 1) fill(0, plan.size());
+            else {
+                std::vector<std::thread> pool;
+                for (size_t t = 0; t < n_threads; t++) pool.emplace_back(fill, plan.size() * t / n_threads, plan.size() * (t + 1) / n_threads);
+                for (auto& t : pool) t.join();
             }
         }
-        while (vi < vars.size() && vars[vi].r.position <= cleared_to) emit(vars[vi++]);
     }
     {   // explicit alleles at positions no segment stages (e.g. an insertion before the first covered base)
         std::vector<OutRec> all;

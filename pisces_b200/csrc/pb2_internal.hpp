@@ -108,6 +108,18 @@ cudaError_t launch_reads_block_bitmap(const int32_t* pos0, const int32_t* end_po
 
 // Reads staged by pb2_push_reads: a struct of arrays in device memory (the handle's pool), kept until a flush clears the positions they cover. The host
 // keeps no per-read state: what the host-side replay of SmallVariantCaller.Execute needs (batch triggers, touched blocks, extent) is computed by kernels.
+// std::allocator whose value-less construct() default-initialises (no zero fill for PODs)
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+    DefaultInitAllocator() = default;
+    template <class U> DefaultInitAllocator(const DefaultInitAllocator<U>&) {}
+    template <class U, class... Args>
+    void construct(U* p, Args&&... args) {
+        if constexpr (sizeof...(Args) == 0) ::new ((void*)p) U;
+        else ::new ((void*)p) U(std::forward<Args>(args)...);
+    }
+};
 template <class T>
 struct GrowBuf {
     T* p = nullptr;
@@ -230,8 +242,9 @@ struct pb2_handle {
     int32_t sink_slots = 0;
     int32_t cleared_through = 0;   // positions <= this were called by an earlier pb2_flush(up_to >= 0)
     int* d_tile_counter = nullptr;
-    std::vector<pb2_call_record> h_out;
-    std::vector<pb2_call_record_ext> h_out_ext;   // parallel to h_out
+    // (resize() of these does not zero-fill: a gVCF flush sizes them for a million records and then writes every byte from several threads)
+    std::vector<pb2_call_record, DefaultInitAllocator<pb2_call_record>> h_out;
+    std::vector<pb2_call_record_ext, DefaultInitAllocator<pb2_call_record_ext>> h_out_ext;   // parallel to h_out
     int64_t hot_launches = 0, total_launches = 0;
     double hot_ms = 0;
     // ---- explicit candidates (pb2_explicit.cu)
@@ -247,6 +260,8 @@ struct pb2_handle {
     bool resident_graph_failed = false;
     int64_t resident_graph_launches = 0;              // kernels inside the graph
     unsigned long long* h_counters = nullptr;         // pinned: the segment's counters after a step
+    void* pin_refs = nullptr; size_t pin_refs_bytes = 0;     // pinned landing area of a flush's dense reference stream (gVCF: 96 B per locus) ...
+    void* pin_valid = nullptr; size_t pin_valid_bytes = 0;   // ... and its validity bytes; grow-only, released by pb2_destroy
     std::vector<uint8_t> arena;                       // allele bytes the last flush's records point into
     std::vector<std::pair<int32_t, int32_t>> snv_explicit_ranges;   // (lo, hi] positions whose SNV candidates were made explicit (explicit_materialize_snvs)
     // ---- forced-genotyping alleles (pb2_set_forced_alleles)

@@ -434,14 +434,15 @@ class GpuStateManager:
         self._chk(self._L.pb2_reset(self._h))
 
     # -- used by GpuAlleleCaller
-    def _flush(self, up_to):
+    def _flush(self, up_to, copy=True):
         out = C.c_void_p()
         n = C.c_int64()
         self._chk(self._L.pb2_flush(self._h, -1 if up_to is None else int(up_to), C.byref(out), C.byref(n)))
         if n.value == 0:
             return np.zeros(0, dtype=N.RECORD_DTYPE)
         buf = (C.c_char * (96 * n.value)).from_address(out.value)
-        return np.frombuffer(buf, dtype=N.RECORD_DTYPE).copy()
+        view = np.frombuffer(buf, dtype=N.RECORD_DTYPE)
+        return view.copy() if copy else view   # the view is the library's own host buffer: valid until the next flush / reset / close of this handle
 
     def StageReads(self):
         """pb2_stage_reads: everything pushed through AddAlleleCounts / AddReadBatch becomes one device-resident segment for call_resident."""
@@ -452,14 +453,16 @@ class GpuStateManager:
         self._chk(self._L.pb2_stage_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(staged_bytes=a.value, rows=b.value, stage_ms=c.value)
 
-    def flush_resident(self):
-        """pb2_flush_resident: the whole job from the device-resident reads (find candidates, stage, call), nothing consumed. Returns raw records."""
+    def flush_resident(self, copy=True):
+        """pb2_flush_resident: the whole job from the device-resident reads (find candidates, stage, call), nothing consumed. Returns raw records
+        (copy=False: a view of the library's host buffer, valid until the next flush)."""
         out = C.c_void_p()
         n = C.c_int64()
         self._chk(self._L.pb2_flush_resident(self._h, C.byref(out), C.byref(n)))
         if n.value == 0:
             return np.zeros(0, dtype=N.RECORD_DTYPE)
-        return np.frombuffer((C.c_char * (96 * n.value)).from_address(out.value), dtype=N.RECORD_DTYPE).copy()
+        view = np.frombuffer((C.c_char * (96 * n.value)).from_address(out.value), dtype=N.RECORD_DTYPE)
+        return view.copy() if copy else view
 
     def SetOwnedRange(self, own_lo, own_hi):
         """pb2_set_owned_range: this handle is one interval shard and emits only the positions it owns."""
@@ -551,8 +554,10 @@ class GpuAlleleCaller:
         self.TotalNumCalled = 0
         self.TotalNumCollapsed = 0
 
-    def Call(self, source, upToPosition=None, raw=False):
-        recs = source._flush(upToPosition)
+    def Call(self, source, upToPosition=None, raw=False, copy=True):
+        """raw: the pb2_call_record array instead of CalledAllele objects; with copy=False a view of the library's host buffer (what a P/Invoke host
+        reads in place), valid until the handle's next flush."""
+        recs = source._flush(upToPosition, copy=copy or not raw)
         self.TotalNumCalled += len(recs)
         if raw:
             return recs

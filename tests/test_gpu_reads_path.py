@@ -288,3 +288,39 @@ def test_reads_far_apart_without_intervals_stage_only_touched_blocks(gvcf):
     orecs = oc.records()
     assert len(orecs) > 40 and any(o.pos > far for o in orecs)
     compare_records(orecs, precs, arena)
+
+
+@pytest.mark.parametrize("n_slots", [3, 4])
+def test_resident_sink_holds_every_steps_records_in_position_order(n_slots):
+    """pb2_set_resident_sink + pb2_call_resident_async + pb2_sink_sort + pb2_resident_sync (the job buffer of the multi-GPU gather): every slot of
+    [n_slots counts | n_slots record blocks] holds one step's variant records, ordered by position, equal to the flush's records. An odd slot count puts
+    the record blocks at an address that is only 8-byte aligned."""
+    import torch
+    from pisces_b200 import _native as N
+    pb = _pb()
+    gen, cfg = CONFIGS["c2"]
+    d = synth.make_reads(20000, 100, seed=5, **gen)
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode())
+    sm.AddReadsSoA(d)
+    sm.StageReads()
+    n0 = sm.call_resident()
+    assert sm.call_resident() == n0
+    cap = n0 + 7
+    buf = torch.zeros(8 * n_slots + n_slots * cap * 96, dtype=torch.uint8, device="cuda")
+    sm.set_resident_sink(buf.data_ptr(), cap, n_slots)
+    for _ in range(n_slots + 2):      # wraps around: slot = step % n_slots
+        sm.call_resident_async()
+    sm.sink_sort()
+    assert sm.resident_sync() == n0
+    host = buf.cpu().numpy()
+    counts = host[: 8 * n_slots].view(np.int64)
+    assert list(counts) == [n0] * n_slots
+    sm.set_resident_sink(None, 0, 0)
+    precs = pb.GpuAlleleCaller().Call(sm, raw=True)
+    sm.close()
+    want = sorted(bytes(r.tobytes()) for r in precs if int(r["ref_len"]) + int(r["alt_len"]) <= 4)
+    for k in range(n_slots):
+        recs = np.frombuffer(host[8 * n_slots + k * cap * 96: 8 * n_slots + (k * cap + n0) * 96].tobytes(), dtype=N.RECORD_DTYPE)
+        pos = recs["position"].astype(np.int64)
+        assert (np.diff(pos) >= 0).all()
+        assert sorted(bytes(r.tobytes()) for r in recs if int(r["ref_len"]) + int(r["alt_len"]) <= 4) == want
