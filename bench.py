@@ -63,7 +63,8 @@ def parse():
     ap.add_argument("--cpu-sample-loci", type=int, default=100_000)
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=4)
-    ap.add_argument("--e2e-jobs", type=int, default=3, help="concurrent (BAM x chromosome) jobs of the end-to-end leg: one handle + one host thread each, as Pisces -t N runs them")
+    ap.add_argument("--e2e-jobs", type=int, default=0, help="concurrent (BAM x chromosome) jobs of the end-to-end leg: one handle + one host thread each, as Pisces -t N runs them "
+                    "(0: host cores / (2 x ranks), between 2 and 6 - measured at N = 1: 2 jobs 57.8, 3 61.2, 4 65.2, 6 68.3 M loci/s)")
     ap.add_argument("--e2e-input", default="packed", choices=["packed", "soa"], help="host form of the reads: one packed byte per base, or bases + qualities")
     ap.add_argument("--gather", default="all", choices=["all", "root"], help="end-of-job exchange of the ranks' call records: all_gather, or gather to rank 0 (the writer)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -423,11 +424,13 @@ def main_ours(a):
     pinned = {k: torch.from_numpy(d[k].view(view[k]) if k in view else d[k]).pin_memory() for k in keys}
     # the e2e input: the same reads packed to one byte per base (pb2_pack_reads: lossless, exceptions listed), as a host behind a PCIe link would hold them
     if a.e2e_input == "packed" and not a.no_e2e:
-        pk = pb.GpuStateManager.pack_reads(d)
-        e2e_in = {k: torch.from_numpy(np.ascontiguousarray(v).view(view[k]) if k in view else np.ascontiguousarray(v)).pin_memory() for k, v in pk.items() if v is not None}
+        # + compact offsets: one byte of CIGAR-operation count per read instead of two 8-byte offsets (built on the device)
+        pk = pb.GpuStateManager.pack_reads(d, compact=bool(np.diff(d["cigar_off"]).max() <= 255))
+        e2e_in = {k: (v if isinstance(v, int) else torch.from_numpy(np.ascontiguousarray(v).view(view[k]) if k in view else np.ascontiguousarray(v)).pin_memory())
+                  for k, v in pk.items() if v is not None}
     else:
         e2e_in = pinned
-    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in e2e_in.values())
+    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in e2e_in.values() if not isinstance(t, int))
     cfg = pb.make_config(device=local, **a.cfg)
     cfg.reserved[0] = a.tune_ctas
     cfg.reserved[1] = a.tune_prefetch
@@ -589,7 +592,7 @@ def main_ours(a):
     if not a.no_e2e:
         # One handle + one host thread per job, as the reference runs its (BAM x chromosome) jobs (-t N: JobManager, SURVEY 8b "Threading"): while one job's
         # reads cross the PCIe link another job's pileup is staged and called, so the link stays busy. Every job processes the same `loci` per step.
-        n_jobs = max(1, a.e2e_jobs)
+        n_jobs = a.e2e_jobs if a.e2e_jobs > 0 else max(2, min(6, (os.cpu_count() or 8) // (2 * world)))
         e2e_steps = max(2, min(a.steps, a.e2e_steps))
         sms = [pb.GpuStateManager(cfg, "chr1", ref) for _ in range(n_jobs)]
         caller = pb.GpuAlleleCaller()
@@ -629,7 +632,8 @@ def main_ours(a):
         line["e2e"] = {"value": world * n_jobs * a.loci * e2e_steps / float(edt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 96 * nrec,
                        "steps": e2e_steps, "jobs": n_jobs, "ms_per_step": 1e3 * float(edt.item()) / (e2e_steps * n_jobs), "single_job_ms_per_step": single_ms,
                        "single_job_value": world * a.loci / (single_ms * 1e-3),
-                       "input": ("reads, one packed byte per base (pb2_push_reads_packed) + 26 B per read" if a.e2e_input == "packed" else "reads, bases + qualities (pb2_push_reads) + 26 B per read") + ", pinned host memory"}
+                       "input": ("reads, one packed byte per base (pb2_push_reads_packed)" if a.e2e_input == "packed" else "reads, bases + qualities (pb2_push_reads)")
+                                + " + %.0f B of metadata per read, pinned host memory" % ((h2d_bytes - (1 if a.e2e_input == "packed" else 2) * len(d["bases"])) / max(1, d["n_reads"]))}
         for sm2 in sms:
             sm2.close()
 

@@ -39,7 +39,8 @@ class ReadBatch(C.Structure):
 class PackedReadBatch(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("pos0", C.c_void_p), ("flag", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("seq_off", C.c_void_p),
                 ("seq", C.c_void_p), ("n_exceptions", C.c_int64), ("exc_index", C.c_void_p), ("exc_base", C.c_void_p), ("exc_qual", C.c_void_p),
-                ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p), ("amplicon", C.c_void_p)]
+                ("base_dirs", C.c_void_p), ("collapsed", C.c_void_p), ("amplicon", C.c_void_p), ("cigar_ops", C.c_void_p), ("n_cigar_total", C.c_int64),
+                ("n_seq_total", C.c_int64)]
 
 
 class Shard(C.Structure):

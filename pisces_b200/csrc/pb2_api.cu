@@ -687,12 +687,34 @@ __global__ static void apply_seq_exceptions_kernel(const int64_t* __restrict__ i
     if (k >= lo && k < hi) { bases[k] = eb[i]; quals[k] = eq[i]; }
 }
 
-// seq / exc_*: the packed form of pb2_push_reads_packed (then b->bases / b->quals are NULL), else nullptr
+// compact offsets of pb2_packed_read_batch: operations per read -> batch-relative cigar_off / seq_off, on the device
+__global__ static void widen_ops_kernel(const uint8_t* __restrict__ ops, int64_t n, int64_t* __restrict__ out /* [n + 1] */) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = i < n ? ops[i] : 0;
+}
+__global__ static void read_spans_kernel(const uint32_t* __restrict__ cigar, int64_t n_cigar, const int64_t* __restrict__ coff /* [n + 1], batch-relative */, int64_t n,
+                                         int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int64_t span = 0;
+    if (i < n)
+        for (int64_t k = coff[i]; k < min(coff[i + 1], n_cigar); k++) {   // (counts that overrun the batch's cigar[] fail the totals check; never read past it)
+            const uint32_t c = cigar[k];
+            const int op = c & 15;
+            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) span += c >> 4;   // M I S = X consume read bases
+        }
+    out[i] = span;
+}
+
+// seq / exc_*: the packed form of pb2_push_reads_packed (then b->bases / b->quals are NULL), else nullptr. cigar_ops: its compact-offsets form (then
+// b->cigar_off / b->seq_off are NULL and ncig_total / nseq_total size the batch)
 static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t* seq, int64_t n_exc, const int64_t* exc_index, const uint8_t* exc_base,
-                           const uint8_t* exc_qual) {
+                           const uint8_t* exc_qual, const uint8_t* cigar_ops = nullptr, int64_t ncig_total = 0, int64_t nseq_total = 0) {
     if (!h || !b || b->n_reads < 0) return fail(h, PB2_ERR_ARG, "pb2_push_reads: bad argument");
     if (b->n_reads == 0) return PB2_OK;
-    if (!b->pos0 || !b->flag || !b->cigar_off || !b->cigar || !b->seq_off || (!seq && (!b->bases || !b->quals))) return fail(h, PB2_ERR_ARG, "pb2_push_reads: null array");
+    const bool compact = cigar_ops != nullptr;
+    if (compact && (b->cigar_off || b->seq_off || !seq || ncig_total < 0 || nseq_total < 0)) return fail(h, PB2_ERR_ARG, "pb2_push_reads_packed: cigar_ops goes with NULL cigar_off / seq_off");
+    if (!b->pos0 || !b->flag || (!compact && (!b->cigar_off || !b->seq_off)) || !b->cigar || (!seq && (!b->bases || !b->quals))) return fail(h, PB2_ERR_ARG, "pb2_push_reads: null array");
     if (seq && (n_exc < 0 || (n_exc > 0 && (!exc_index || !exc_base || !exc_qual)))) return fail(h, PB2_ERR_ARG, "pb2_push_reads_packed: bad exception list");
     CU(h, cudaSetDevice(h->device));
     nvtx_range nv("pb2_push_reads");
@@ -700,7 +722,7 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
     DeviceReads& R = h->reads;
     cudaStream_t st = h->stream;
     const int64_t nb = b->n_reads;
-    const int64_t c_lo = b->cigar_off[0], c_hi = b->cigar_off[nb], s_lo = b->seq_off[0], s_hi = b->seq_off[nb];
+    const int64_t c_lo = compact ? 0 : b->cigar_off[0], c_hi = compact ? ncig_total : b->cigar_off[nb], s_lo = compact ? 0 : b->seq_off[0], s_hi = compact ? nseq_total : b->seq_off[nb];
     if (c_hi < c_lo || s_hi < s_lo) return fail(h, PB2_ERR_ARG, "pb2_push_reads: offsets not monotone");
     if (R.n + nb > INT32_MAX) return fail(h, PB2_ERR_ARG, "pb2_push_reads: more than 2^31 reads staged");
     const int64_t first = R.n, ncig = c_hi - c_lo, nseq = s_hi - s_lo;
@@ -736,9 +758,34 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
     const cudaMemcpyKind k = cudaMemcpyHostToDevice;
     CU(h, cudaMemcpyAsync(R.pos0.p + first, b->pos0, sizeof(int32_t) * (size_t)nb, k, st));
     CU(h, cudaMemcpyAsync(R.flag.p + first, b->flag, sizeof(uint16_t) * (size_t)nb, k, st));
-    CU(h, cudaMemcpyAsync(R.cigar_off.p + first + 1, b->cigar_off + 1, sizeof(int64_t) * (size_t)nb, k, st));
-    CU(h, cudaMemcpyAsync(R.seq_off.p + first + 1, b->seq_off + 1, sizeof(int64_t) * (size_t)nb, k, st));
+    if (!compact) {
+        CU(h, cudaMemcpyAsync(R.cigar_off.p + first + 1, b->cigar_off + 1, sizeof(int64_t) * (size_t)nb, k, st));
+        CU(h, cudaMemcpyAsync(R.seq_off.p + first + 1, b->seq_off + 1, sizeof(int64_t) * (size_t)nb, k, st));
+    }
     if (ncig) CU(h, cudaMemcpyAsync(R.cigar.p + R.n_cigar, b->cigar + c_lo, sizeof(uint32_t) * (size_t)ncig, k, st));
+    int64_t compact_totals[2] = {ncig_total, nseq_total};
+    if (compact) {   // batch-relative offsets out of the operation counts: two scans, the second over the read spans the first one's offsets delimit
+        uint8_t* d_ops = nullptr;
+        int64_t *d_in = nullptr, *d_coff = nullptr, *d_soff = nullptr;
+        void* temp = nullptr;
+        size_t tb = 0;
+        CU(h, pool_alloc_t(h, &d_ops, (size_t)nb)); CU(h, pool_alloc_t(h, &d_in, (size_t)nb + 1)); CU(h, pool_alloc_t(h, &d_coff, (size_t)nb + 1)); CU(h, pool_alloc_t(h, &d_soff, (size_t)nb + 1));
+        CU(h, exclusive_scan_i64(d_in, d_coff, nb + 1, nullptr, 0, &tb, st));
+        CU(h, pool_alloc(h, &temp, tb + 16));
+        CU(h, cudaMemcpyAsync(d_ops, cigar_ops, (size_t)nb, k, st));
+        const unsigned grid = (unsigned)((nb + 1 + 255) / 256);
+        widen_ops_kernel<<<grid, 256, 0, st>>>(d_ops, nb, d_in);
+        CU(h, exclusive_scan_i64(d_in, d_coff, nb + 1, temp, tb, nullptr, st));
+        read_spans_kernel<<<grid, 256, 0, st>>>(R.cigar.p + R.n_cigar, ncig, d_coff, nb, d_in);
+        CU(h, exclusive_scan_i64(d_in, d_soff, nb + 1, temp, tb, nullptr, st));
+        CU(h, cudaMemcpyAsync(R.cigar_off.p + first + 1, d_coff + 1, sizeof(int64_t) * (size_t)nb, cudaMemcpyDeviceToDevice, st));
+        CU(h, cudaMemcpyAsync(R.seq_off.p + first + 1, d_soff + 1, sizeof(int64_t) * (size_t)nb, cudaMemcpyDeviceToDevice, st));
+        CU(h, cudaMemcpyAsync(&compact_totals[0], d_coff + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(&compact_totals[1], d_soff + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        h->total_launches += 4;
+        void* ptrs[] = {d_ops, d_in, d_coff, d_soff, temp};
+        for (void* p : ptrs) pool_free(h, p);
+    }
     uint8_t* d_seq = nullptr;
     int64_t* d_exc_index = nullptr;
     uint8_t *d_exc_base = nullptr, *d_exc_qual = nullptr;
@@ -795,6 +842,10 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
     tr.mark("h2d+ingest");
     pool_free(h, d_seq); pool_free(h, d_exc_index); pool_free(h, d_exc_base); pool_free(h, d_exc_qual);
     auto rollback = [&]() { R.n = first; R.has_amplicon = had_amp && first > 0; pool_free(h, d_status); pool_free(h, d_trig); };
+    if (compact && (compact_totals[0] != ncig_total || compact_totals[1] != nseq_total)) {
+        rollback();
+        return fail(h, PB2_ERR_ARG, "pb2_push_reads_packed: cigar_ops do not add up to n_cigar_total / the CIGARs' read spans to n_seq_total");
+    }
     if (status.error) {
         rollback();
         switch (status.error) {
@@ -822,7 +873,7 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
     R.n_cigar += ncig; R.n_seq += nseq;
     R.min_start = std::min(R.min_start, status.min_start);
     R.max_end = std::max(R.max_end, status.max_end);
-    BatchHostView hv{seq ? nullptr : b->bases + s_lo, b->seq_off, s_lo};
+    BatchHostView hv{seq ? nullptr : b->bases + s_lo, compact ? nullptr : b->seq_off, s_lo};
     const int rc = explicit_find_candidates(h, (size_t)first, seq ? nullptr : &hv);
     tr.mark("candidates");
     return rc;
@@ -836,6 +887,7 @@ extern "C" int pb2_push_reads_packed(pb2_handle* h, const pb2_packed_read_batch*
     b.n_reads = p->n_reads; b.pos0 = p->pos0; b.flag = p->flag; b.cigar_off = p->cigar_off; b.cigar = p->cigar; b.seq_off = p->seq_off;
     b.base_dirs = p->base_dirs; b.collapsed = p->collapsed; b.amplicon = p->amplicon;
     if (p->n_reads > 0 && !p->seq) return fail(h, PB2_ERR_ARG, "pb2_push_reads_packed: null array");
+    if (p->cigar_ops != nullptr) return push_reads_impl(h, &b, p->seq, p->n_exceptions, p->exc_index, p->exc_base, p->exc_qual, p->cigar_ops, p->n_cigar_total, p->n_seq_total);
     return push_reads_impl(h, &b, p->seq, p->n_exceptions, p->exc_index, p->exc_base, p->exc_qual);
 }
 // Host helper: bases + qualities -> the packed bytes of pb2_push_reads_packed and their exception list. Returns the number of exceptions (which may

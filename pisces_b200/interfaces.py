@@ -304,9 +304,17 @@ class GpuStateManager:
         self._chk(self._L.pb2_push_reads(self._h, C.byref(b)))
 
     @staticmethod
-    def pack_reads(d):
-        """pb2_pack_reads: the struct of arrays of AddReadsSoA with bases + quals replaced by one packed byte per base (+ the exception list)."""
+    def pack_reads(d, compact=False):
+        """pb2_pack_reads: the struct of arrays of AddReadsSoA with bases + quals replaced by one packed byte per base (+ the exception list).
+        compact: also the compact-offsets form (one byte of operation count per read instead of two 8-byte offsets; the offsets are built on the device)."""
         L = N.load()
+        if compact:
+            co, so = np.asarray(d["cigar_off"], dtype=np.int64), np.asarray(d["seq_off"], dtype=np.int64)
+            ops = np.diff(co)
+            if len(ops) and ops.max() > 255:
+                raise ValueError("compact offsets need at most 255 CIGAR operations per read")
+            d = dict(d, cigar=np.asarray(d["cigar"])[co[0]:co[-1]], bases=np.asarray(d["bases"])[so[0]:so[-1]], quals=np.asarray(d["quals"])[so[0]:so[-1]],
+                     base_dirs=None if d.get("base_dirs") is None else np.asarray(d["base_dirs"])[so[0]:so[-1]])
         bases, quals = np.ascontiguousarray(d["bases"], dtype=np.uint8), np.ascontiguousarray(d["quals"], dtype=np.uint8)
         n = len(bases)
         seq = np.empty(n, dtype=np.uint8)
@@ -320,6 +328,8 @@ class GpuStateManager:
                 break
             cap = int(ne)
         out = {k: d[k] for k in ("pos0", "flag", "cigar_off", "cigar", "seq_off")}
+        if compact:
+            out.update(cigar_off=None, seq_off=None, cigar_ops=ops.astype(np.uint8), n_cigar_total=int(len(d["cigar"])), n_seq_total=int(n))
         out.update(seq=seq, exc_index=ei[:ne].copy(), exc_base=eb[:ne].copy(), exc_qual=eq[:ne].copy(), base_dirs=d.get("base_dirs"), collapsed=d.get("collapsed"), amplicon=d.get("amplicon"))
         return out
 
@@ -335,9 +345,10 @@ class GpuStateManager:
             a = np.ascontiguousarray(a, dtype=dt)
             keep.append(a)
             return a.ctypes.data if len(a) else None
-        b = N.PackedReadBatch(int(len(d["pos0"])), ptr(d["pos0"], np.int32), ptr(d["flag"], np.uint16), ptr(d["cigar_off"], np.int64), ptr(d["cigar"], np.uint32),
-                              ptr(d["seq_off"], np.int64), ptr(d["seq"], np.uint8), int(len(d["exc_index"])), ptr(d["exc_index"], np.int64), ptr(d["exc_base"], np.uint8),
-                              ptr(d["exc_qual"], np.uint8), ptr(d.get("base_dirs"), np.uint8), ptr(d.get("collapsed"), np.uint8), ptr(d.get("amplicon"), np.int32))
+        b = N.PackedReadBatch(int(len(d["pos0"])), ptr(d["pos0"], np.int32), ptr(d["flag"], np.uint16), ptr(d.get("cigar_off"), np.int64), ptr(d["cigar"], np.uint32),
+                              ptr(d.get("seq_off"), np.int64), ptr(d["seq"], np.uint8), int(len(d["exc_index"])), ptr(d["exc_index"], np.int64), ptr(d["exc_base"], np.uint8),
+                              ptr(d["exc_qual"], np.uint8), ptr(d.get("base_dirs"), np.uint8), ptr(d.get("collapsed"), np.uint8), ptr(d.get("amplicon"), np.int32),
+                              ptr(d.get("cigar_ops"), np.uint8), int(d.get("n_cigar_total") or 0), int(d.get("n_seq_total") or 0))
         self._chk(self._L.pb2_push_reads_packed(self._h, C.byref(b)))
 
     def AddReadBatch(self, batch):

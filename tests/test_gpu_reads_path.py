@@ -324,3 +324,31 @@ def test_resident_sink_holds_every_steps_records_in_position_order(n_slots):
         pos = recs["position"].astype(np.int64)
         assert (np.diff(pos) >= 0).all()
         assert sorted(bytes(r.tobytes()) for r in recs if int(r["ref_len"]) + int(r["alt_len"]) <= 4) == want
+
+
+def test_compact_offsets_equal_plain_push():
+    """pb2_packed_read_batch with cigar_ops (one byte of operation count per read, offsets built on the device) stages the same reads as the offset
+    arrays: records identical, over several batches cut out of larger arrays; operation counts that do not add up are refused."""
+    pb = _pb()
+    gen, cfg = CONFIGS["c2"]
+    d = synth.make_reads(15000, 90, seed=17, **gen)
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode())
+    sm.AddReadsSoA(d)
+    want = pb.GpuAlleleCaller().Call(sm, raw=True)
+    n = len(d["pos0"])
+    cuts = [0, n // 3, n // 3 + 1, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = dict(pos0=d["pos0"][a:b], flag=d["flag"][a:b], cigar_off=d["cigar_off"][a:b + 1], cigar=d["cigar"], seq_off=d["seq_off"][a:b + 1], bases=d["bases"], quals=d["quals"])
+        pk = pb.GpuStateManager.pack_reads(part, compact=True)
+        assert pk["cigar_off"] is None and len(pk["cigar_ops"]) == b - a
+        sm.AddReadsPacked(pk)
+    got = pb.GpuAlleleCaller().Call(sm, raw=True)
+    assert len(want) > 100 and [bytes(r.tobytes()) for r in got if int(r["ref_len"]) + int(r["alt_len"]) <= 4] == \
+        [bytes(r.tobytes()) for r in want if int(r["ref_len"]) + int(r["alt_len"]) <= 4]
+    bad = pb.GpuStateManager.pack_reads(dict(pos0=d["pos0"][:50], flag=d["flag"][:50], cigar_off=d["cigar_off"][:51], cigar=d["cigar"], seq_off=d["seq_off"][:51],
+                                             bases=d["bases"], quals=d["quals"]), compact=True)
+    bad["cigar_ops"] = bad["cigar_ops"].copy()
+    bad["cigar_ops"][7] += 1
+    with pytest.raises(pb.PiscesB200Error, match="add up"):
+        sm.AddReadsPacked(bad)
+    sm.close()
