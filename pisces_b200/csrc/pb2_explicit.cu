@@ -436,10 +436,25 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
             if (a.open_left != b.open_left) return !a.open_left;
             return false;
         });
+        // A target can only take a candidate that starts or ends where it does (can_collapse compares one of the two, by type and open end), so the
+        // targets are indexed by both positions once per batch: with CallMNVs every sequencing error is a candidate, thousands per block, and the
+        // all-pairs scan was the flush's largest item
+        auto end_of = [](const HostCand& c) { return c.position + (int32_t)(c.type == CAT_DEL ? c.ref.size() : c.alt.size()) - 1; };
+        std::unordered_map<int32_t, std::vector<size_t>> by_start, by_end;
+        by_start.reserve(targets.size()); by_end.reserve(targets.size());
+        for (size_t t : targets) { by_start[cs[t].position].push_back(t); by_end[end_of(cs[t])].push_back(t); }
+        std::vector<size_t> near;
         for (size_t vi : to_collapse) {
             HostCand& v = cs[vi];
+            near.clear();
+            auto a = by_start.find(v.position);
+            if (a != by_start.end()) near.insert(near.end(), a->second.begin(), a->second.end());
+            auto b = by_end.find(end_of(v));
+            if (b != by_end.end()) near.insert(near.end(), b->second.begin(), b->second.end());
+            std::sort(near.begin(), near.end());   // the order of `targets` (= candidate order), each target once
+            near.erase(std::unique(near.begin(), near.end()), near.end());
             std::vector<size_t> pms;
-            for (size_t t : targets) if (t != vi && cs[t].alive && can_collapse(v, cs[t])) pms.push_back(t);
+            for (size_t t : near) if (t != vi && cs[t].alive && can_collapse(v, cs[t])) pms.push_back(t);
             if (pms.empty()) continue;
             for (size_t t : pms) cs[t].frequency = candidate_frequency(h, cs[t], ingr[t], recs[t].total_coverage);
             const float tcf = candidate_frequency(h, v, ingr[vi], recs[vi].total_coverage);
