@@ -249,6 +249,13 @@ int pb2_push_reads_packed(pb2_handle* h, const pb2_packed_read_batch* batch);
 /* Host helper (no device work): packs n bases + qualities into seq[n] and lists the exceptions. Returns the number of exceptions; when it exceeds
  * exc_capacity only the first exc_capacity were stored (call again with larger arrays). */
 int64_t pb2_pack_reads(const uint8_t* bases, const uint8_t* quals, int64_t n, uint8_t* seq, int64_t* exc_index, uint8_t* exc_base, uint8_t* exc_qual, int64_t exc_capacity);
+/* Host helper of the locus-major path (no device work): code / qual / anchor planes of a pb2_pileup_csr -> PB2_LAYOUT_PACKED2 (pcode, pqual: two bytes per
+ * entry) + the sparse list of flagged entries (flag_index increasing, flag_bits = code & 0xe0). offsets [n_loci + 1] + ref_bases [n_loci] are optional:
+ * with them, flags on entries that show the reference base of their locus are dropped (they raise no SNV candidate, CandidateVariantFinder.cs:112-141).
+ * Returns the number of flagged entries (> flag_capacity: call again with larger arrays), PB2_ERR_UNSUPPORTED when an anchor byte carries a collapsed-read
+ * type (bits 4-7). */
+int64_t pb2_pack_pileup(const uint8_t* code, const uint8_t* qual, const uint8_t* anchor, int64_t n_entries, const int64_t* offsets, const uint8_t* ref_bases, int64_t n_loci,
+                        uint8_t* pcode, uint8_t* pqual, int64_t* flag_index, uint8_t* flag_bits, int64_t flag_capacity);
 /* Stages everything pushed through pb2_push_reads so far as one device-resident segment (the pileup is built on the device from the reads the handle
  * keeps there), so that pb2_call_resident / pb2_resident_results run on it: the whole-chromosome form of IStateManager for hosts that push all reads
  * first (bench.py, multi-GPU shards). The reads stay staged; a later pb2_flush re-stages what it needs and supersedes this segment. */

@@ -79,7 +79,7 @@ RECORD_DTYPE = [("position", "<i4"), ("type", "u1"), ("genotype", "u1"), ("sb_fl
 RECORD_EXT_DTYPE = [("collapsed_mut", "<i4", (8,)), ("collapsed_total", "<i4", (8,)), ("well_anchored_support", "<i4", (3,)), ("phase_set_index", "<i4")]
 
 EXPORTS = ["pb2_default_config", "pb2_create", "pb2_destroy", "pb2_last_error", "pb2_device_count", "pb2_set_reference", "pb2_set_intervals",
-           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_reads_packed", "pb2_pack_reads", "pb2_stage_reads", "pb2_push_candidates", "pb2_set_forced_alleles", "pb2_allele_arena", "pb2_call_resident", "pb2_call_resident_async", "pb2_resident_sync", "pb2_set_resident_sink", "pb2_sink_sort", "pb2_resident_results", "pb2_flush", "pb2_flush_resident", "pb2_flush_ext",
+           "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_reads_packed", "pb2_pack_reads", "pb2_pack_pileup", "pb2_stage_reads", "pb2_push_candidates", "pb2_set_forced_alleles", "pb2_allele_arena", "pb2_call_resident", "pb2_call_resident_async", "pb2_resident_sync", "pb2_set_resident_sink", "pb2_sink_sort", "pb2_resident_results", "pb2_flush", "pb2_flush_resident", "pb2_flush_ext",
            "pb2_get_counts", "pb2_reset", "pb2_shard_plan", "pb2_set_owned_range", "pb2_stats", "pb2_stage_stats", "pb2_stream", "pb2_totals", "pb2_vcf_format",
            "pb2_bam_open", "pb2_bam_close", "pb2_bam_last_error", "pb2_bam_header", "pb2_bam_next_batch", "pb2_bam_batch_amplicons",
            "pb2_bam_amplicon_names"]
@@ -111,6 +111,8 @@ def load():
     L.pb2_push_reads_packed.argtypes = [H, C.POINTER(PackedReadBatch)]
     L.pb2_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.pb2_pack_reads.restype = C.c_int64
+    L.pb2_pack_pileup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.pb2_pack_pileup.restype = C.c_int64
     L.pb2_stage_reads.argtypes = [H]
     L.pb2_push_candidates.argtypes = [H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     L.pb2_set_forced_alleles.argtypes = [H, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]

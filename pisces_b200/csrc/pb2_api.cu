@@ -909,6 +909,39 @@ extern "C" int64_t pb2_pack_reads(const uint8_t* bases, const uint8_t* quals, in
     return n_exc;
 }
 
+// Host helper of the locus-major path: the three planes of pb2_pileup_csr -> PB2_LAYOUT_PACKED2 (two bytes per entry: the anchor bin rides in the spare bits of
+// the code and quality bytes) plus the sparse list of entries that carry candidate flags (code bits 5-7). With offsets + ref_bases, flags on entries whose
+// base is the reference base of their locus are left out: such a base raises no SNV candidate (CandidateVariantFinder.cs:112-141), its open-end flags say
+// nothing (staging clears them as well). Returns the number of flagged entries (which may exceed flag_capacity: then only the first flag_capacity were
+// stored), PB2_ERR_ARG for a bad argument, PB2_ERR_UNSUPPORTED when an anchor byte carries a collapsed-read type (bits 4-7: the packed form has no room).
+extern "C" int64_t pb2_pack_pileup(const uint8_t* code, const uint8_t* qual, const uint8_t* anchor, int64_t n_entries, const int64_t* offsets, const uint8_t* ref_bases,
+                                   int64_t n_loci, uint8_t* pcode, uint8_t* pqual, int64_t* flag_index, uint8_t* flag_bits, int64_t flag_capacity) {
+    if (n_entries < 0 || (n_entries > 0 && (!code || !qual || !anchor || !pcode || !pqual)) || flag_capacity < 0) return PB2_ERR_ARG;
+    const bool by_locus = offsets != nullptr && ref_bases != nullptr && n_loci > 0;
+    if (by_locus && offsets[n_loci] != n_entries) return PB2_ERR_ARG;
+    int64_t n_flags = 0, locus = 0;
+    for (int64_t i = 0; i < n_entries; i++) {
+        const uint8_t c = code[i], q = qual[i], a = anchor[i];
+        if (a >> 4) return PB2_ERR_UNSUPPORTED;
+        pcode[i] = (uint8_t)((c & 0x1f) | ((a & 7) << 5));
+        pqual[i] = (uint8_t)((q & 0x7f) | ((a >> 3) << 7));
+        if (c & 0xe0) {
+            bool keep = true;
+            if (by_locus) {
+                while (locus + 1 <= n_loci && offsets[locus + 1] <= i) locus++;
+                const uint8_t rb = ref_bases[locus];
+                const int ref_allele = rb == 'A' ? 0 : rb == 'G' ? 1 : rb == 'C' ? 2 : rb == 'T' ? 3 : 4;
+                keep = (c & 7) != ref_allele;
+            }
+            if (keep) {
+                if (n_flags < flag_capacity && flag_index && flag_bits) { flag_index[n_flags] = i; flag_bits[n_flags] = (uint8_t)(c & 0xe0); }
+                n_flags++;
+            }
+        }
+    }
+    return n_flags;
+}
+
 // ------------------------------------------------------------------------------------------------ interval sharding
 // BaseGenomeProcessor shards by chromosome and concatenates in genome order (BaseGenomeProcessor.cs:60-72, GenomeProcessor.cs:156-186); within a chromosome the
 // loci are independent once the counts are complete, so a chromosome is cut into interval shards at 1000-bp block boundaries (the batches of
@@ -1600,6 +1633,15 @@ static int run_explicit_batches(pb2_handle* h, int32_t up_to, bool reads_path, s
     };
     Trace tr("explicit_batches");
     tr.mark("keys");
+    extern double g_batch_phase_ms[8];
+    for (double& v : g_batch_phase_ms) v = 0;
+    struct PhaseReport {
+        ~PhaseReport() {
+            if (!trace_on()) return;
+            fprintf(stderr, "[pb2] batch phases: copy=%.1f collapse_score=%.1f collapse=%.1f mnv_score=%.1f refs=%.1f realloc=%.1f final_score=%.1f emit=%.1f ms\n", g_batch_phase_ms[0],
+                    g_batch_phase_ms[1], g_batch_phase_ms[2], g_batch_phase_ms[3], g_batch_phase_ms[4], g_batch_phase_ms[5], g_batch_phase_ms[6], g_batch_phase_ms[7]);
+        }
+    } phase_report;
     std::vector<int32_t> fire;   // upTo values in call order; -1 = the final Call(null)
     {
         size_t used = 0;

@@ -15,6 +15,7 @@
 #include <memory>
 #include <set>
 #include <unordered_map>
+#include <chrono>
 #include "pb2_internal.hpp"
 
 using namespace pb2;
@@ -357,9 +358,22 @@ int explicit_add_forced_candidates(pb2_handle* h, int32_t up_to) {   // SmallVar
 }
 
 // ------------------------------------------------------------------------------------------------ AlleleCaller.Call, explicit part
+// PB2_TRACE: where the time of the batches goes (host phases of explicit_call_batch, summed over the batches of a flush)
+double g_batch_phase_ms[8];
+static bool batch_trace() { static const bool on = getenv("PB2_TRACE") != nullptr; return on; }
+struct PhaseClock {
+    std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    void mark(int phase) {
+        if (!batch_trace()) return;
+        const auto now = std::chrono::steady_clock::now();
+        g_batch_phase_ms[phase] += std::chrono::duration<double, std::milli>(now - last).count();
+        last = now;
+    }
+};
 int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t max_cleared, int32_t ref_lo, int32_t ref_hi, std::vector<pb2_call_record>& called,
                         std::vector<pb2_call_record_ext>& called_ext, const std::vector<size_t>* kill) {
     if (batch.empty()) return PB2_OK;
+    PhaseClock pc_;
     std::vector<HostCand> cs;
     cs.reserve(batch.size());
     for (size_t idx : batch) { cs.push_back(h->cands[idx]); cs.back().alive = true; }
@@ -406,6 +420,7 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
         }
     }
 
+    pc_.mark(0);
     // ---- VariantCollapser.Collapse (:31-113)
     const bool any_open = std::any_of(cs.begin(), cs.end(), [](const HostCand& c) { return c.open_left || c.open_right; });
     if (h->cfg.collapse && any_open) {
@@ -418,6 +433,7 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
         std::vector<uint8_t> scratch_arena;
         rc = score_pieces(ctx, ps, scratch_arena, &recs, nullptr, &ingr, nullptr);
         if (rc != PB2_OK) return rc;
+        pc_.mark(1);
         std::vector<size_t> targets;
         for (size_t i = 0; i < cs.size(); i++) if (!(h->cfg.exclude_mnvs_from_collapsing && cs[i].type == CAT_MNV)) targets.push_back(i);
         std::vector<size_t> to_collapse;
@@ -474,6 +490,7 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
             v.alive = false;
         }
     }
+    pc_.mark(2);
     if (h->cfg.collapse && max_cleared >= 0) {   // candidates beyond the cleared positions go back to the state (:100-112)
         for (auto& c : cs)
             if (c.alive && c.position > max_cleared) { c.alive = false; HostCand back = c; back.alive = true; explicit_add_candidate(h, back); }
@@ -503,6 +520,7 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
             else callable.push_back(p);
         }
     }
+    pc_.mark(3);
     {
         // Reference candidates of the batch (RegionState.GetAllCandidates :393-449). With reference calls on there is one per position and the
         // reallocator treats them like any callable allele (IsPotentialOverlap :262): a failed gapped MNV hands its support to the reference allele at a
@@ -557,6 +575,7 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
             for (int32_t pos : forced_pos) add_ref(pos, true);
         }
     }
+    pc_.mark(4);
     if (!failed.empty()) {
         // ---- MnvReallocator.ReallocateFailedMnvs (:12-98)
         auto create = [&](int32_t pos, int allele_support, const std::string& alt, const std::string& ref, const int32_t* sup) -> Piece* {   // CreateVariant (:156-173)
@@ -665,6 +684,7 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
             explicit_add_candidate(h, c);
         }
     }
+    pc_.mark(5);
     // ---- GetRefSupportFromGappedMnvs (:186-206) -> RegionState.AddGappedMnvRefCount
     for (Piece* a : callable) {
         if (a->type != CAT_MNV) continue;
@@ -684,6 +704,7 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
         std::vector<uint8_t> flags;
         rc = score_pieces(ctx, callable, arena, &recs, &flags, nullptr, nullptr);
         if (rc != PB2_OK) return rc;
+        pc_.mark(6);
         for (size_t i = 0; i < recs.size(); i++) {
             if (!(flags[i] & (2 | 4))) continue;   // IsCallable && ShouldReport, or a forced allele (:108-118)
             called.push_back(recs[i]);
@@ -698,6 +719,7 @@ int explicit_call_batch(pb2_handle* h, const std::vector<size_t>& batch, int32_t
             called_ext.push_back(e);
         }
     }
+    pc_.mark(7);
     return PB2_OK;
 }
 

@@ -255,20 +255,26 @@ class GpuStateManager:
         """Host planes (code, qual, anchor) -> PB2_LAYOUT_PACKED2: two bytes per entry plus the sparse list of candidate flags. With offsets and
         ref_bases given, flags on entries whose base is the reference base of their locus are left out: such a base raises no SNV candidate
         (CandidateVariantFinder.cs:112-141), so its open-end flags say nothing (staging clears them as well)."""
+        L = N.load()   # pb2_pack_pileup: the packing is library code (a .NET host calls the same entry point)
         code, qual, anchor = (np.ascontiguousarray(x, dtype=np.uint8) for x in (code, qual, anchor))
-        if (anchor >> 4).any():
-            raise ValueError("PB2_LAYOUT_PACKED2 cannot carry the collapsed-read type (anchor bits 4-7)")
-        flag_index = np.flatnonzero(code & 0xe0).astype(np.int64)
-        if offsets is not None and ref_bases is not None and len(flag_index):
-            locus = np.searchsorted(np.asarray(offsets, dtype=np.int64), flag_index, side="right") - 1
-            ref_allele = np.full(256, 4, dtype=np.uint8)
-            ref_allele[[ord("A"), ord("G"), ord("C"), ord("T")]] = [0, 1, 2, 3]
-            keep = (code[flag_index] & 7) != ref_allele[np.asarray(ref_bases, dtype=np.uint8)[locus]]
-            flag_index = flag_index[keep]
-        flag_bits = (code[flag_index] & 0xe0).astype(np.uint8)
-        pcode = (code & 0x1f) | ((anchor & 7) << 5)
-        pqual = (qual & 0x7f) | ((anchor >> 3) << 7)
-        return pcode.astype(np.uint8), pqual.astype(np.uint8), flag_index, flag_bits
+        n = len(code)
+        by_locus = offsets is not None and ref_bases is not None
+        off = np.ascontiguousarray(offsets, dtype=np.int64) if by_locus else None
+        rb = np.ascontiguousarray(ref_bases, dtype=np.uint8) if by_locus else None
+        pcode, pqual = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+        cap = max(1024, n // 64)
+        while True:
+            fi, fb = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.uint8)
+            nf = L.pb2_pack_pileup(code.ctypes.data, qual.ctypes.data, anchor.ctypes.data, n, off.ctypes.data if by_locus else None, rb.ctypes.data if by_locus else None,
+                                   len(off) - 1 if by_locus else 0, pcode.ctypes.data, pqual.ctypes.data, fi.ctypes.data, fb.ctypes.data, cap)
+            if nf == N_ERR_UNSUPPORTED:
+                raise ValueError("PB2_LAYOUT_PACKED2 cannot carry the collapsed-read type (anchor bits 4-7)")
+            if nf < 0:
+                raise PiscesB200Error(int(nf), "pb2_pack_pileup")
+            if nf <= cap:
+                break
+            cap = int(nf)
+        return pcode, pqual, fi[:nf].copy(), fb[:nf].copy()
 
     def AddPileupPacked(self, offsets, pcode, pqual, flag_index=None, flag_bits=None, first_position=1, positions=None, ref_bases=None):
         """pb2_push_pileup with PB2_LAYOUT_PACKED2 host buffers (see pack_pileup): 2 bytes per entry cross the PCIe link instead of 3."""
@@ -505,6 +511,7 @@ class GpuStateManager:
 
 
 N_ERR_ARG = -1
+N_ERR_UNSUPPORTED = -5
 
 
 class BamReadStager:
