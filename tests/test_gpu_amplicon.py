@@ -12,16 +12,16 @@ from tests.util_reads import make_amplicon_reads
 pytestmark = pytest.mark.gpu
 
 
-def _oracle(d, **cfg):
-    oc = ob.Caller(ob.default_config(**cfg), "chr1", bytes(d["ref"]).decode())
+def _oracle(d, intervals=None, **cfg):
+    oc = ob.Caller(ob.default_config(**cfg), "chr1", bytes(d["ref"]).decode(), intervals=intervals)
     oc.add_reads_soa(d["pos0"], d["flag"], d["cigar_off"], d["cigar"], d["seq_off"], d["bases"], d["quals"], amplicon=d["amplicon"])
     oc.finish()
     return oc.records()
 
 
-def _product(d, packed=False, batches=1, resident=False, **cfg):
+def _product(d, packed=False, batches=1, resident=False, intervals=None, **cfg):
     import pisces_b200 as pb
-    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode())
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode(), intervals=intervals)
     n = len(d["pos0"])
     cuts = np.linspace(0, n, batches + 1).astype(int)
     for a, b in zip(cuts[:-1], cuts[1:]):
@@ -60,6 +60,19 @@ def test_amplicon_bias_filter_matches_the_oracle(gvcf, mode):
     flagged = sorted(int(r["position"]) for r in precs if (int(r["filters"]) >> AB) & 1)
     assert flagged == sorted(r.pos for r in orecs if (r.filter_mask >> AB) & 1)
     assert {130, 230, 330} <= set(flagged) and not {60, 145, 245} & set(flagged)
+
+
+@pytest.mark.parametrize("gvcf", [0, 1])
+def test_with_an_interval_file(gvcf):
+    """Interval runs stage listed positions (positions[] / index_of_pos): the amplicon kernel finds a record's locus by binary search."""
+    d = make_amplicon_reads(seed=5, variants=VARIANTS)
+    iv = [(100, 150), (220, 340)]
+    cfg = dict(output_gvcf=gvcf, amplicon_bias_filter=0.01)
+    orecs = _oracle(d, intervals=iv, **cfg)
+    precs, arena = _product(d, intervals=iv, **cfg)
+    compare_records(orecs, precs, arena)
+    flagged = sorted(int(r["position"]) for r in precs if (int(r["filters"]) >> AB) & 1)
+    assert {130, 230, 330} <= set(flagged) and 60 not in {int(r["position"]) for r in precs}
 
 
 def test_many_seeds_and_shapes():

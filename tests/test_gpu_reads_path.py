@@ -142,7 +142,7 @@ def test_staged_reads_resident_step_equals_flush():
     assert short(res) == short(precs)
 
 
-@pytest.mark.parametrize("name,n_shards", [("c2", 2), ("c2", 4), ("c4", 3), ("c5", 2)])
+@pytest.mark.parametrize("name,n_shards", [("c2", 2), ("c2", 4), ("c3", 2), ("c4", 3), ("c5", 2)])
 def test_interval_shards_concatenate_to_the_unsharded_records(name, n_shards):
     """pb2_shard_plan + pb2_set_owned_range: every shard sees its reads (own positions + halo) and emits only what it owns; the shards' records in shard
     order are the unsharded chromosome's records, byte for byte - with reads spanning every cut (depth 100 everywhere), indels, MNVs and collapsing."""
