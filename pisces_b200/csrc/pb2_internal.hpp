@@ -218,6 +218,7 @@ struct pb2_handle {
     int num_sms = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_scattered[2] = {nullptr, nullptr};
+    cudaEvent_t ev_piece[4] = {nullptr, nullptr, nullptr, nullptr};   // pacing of large host-to-device copies (h2d_in_pieces)
     cudaMemPool_t pool = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_stage0 = nullptr, ev_stage1 = nullptr;   // around the last reads -> PVERT staging
