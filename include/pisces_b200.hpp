@@ -29,6 +29,7 @@ struct Read {
     std::vector<uint8_t> Qualities;
     std::vector<uint8_t> SequencedBaseDirectionMap;   // optional (stitched reads)
     int CollapsedSummary = -1;             // optional, see pb2_read_batch.collapsed
+    int32_t AmpliconId = -1;               // optional: Read.GetAmpliconNameIfExists as an id of the host's dictionary (pb2_read_batch.amplicon), -1 = no XN tag
 };
 
 class GpuStateManager {
@@ -86,7 +87,8 @@ public:
         if (buffer_.empty()) return;
         std::vector<int32_t> pos0; std::vector<uint16_t> flag; std::vector<int64_t> coff{0}, soff{0};
         std::vector<uint32_t> cigar; std::vector<uint8_t> bases, quals, dirs, coll;
-        bool anyDirs = false, anyColl = false;
+        std::vector<int32_t> amp;
+        bool anyDirs = false, anyColl = false, anyAmp = false;
         for (auto& r : buffer_) { anyDirs |= !r.SequencedBaseDirectionMap.empty(); anyColl |= r.CollapsedSummary >= 0; }
         for (auto& r : buffer_) {
             pos0.push_back(r.Position - 1); flag.push_back(r.Flag);
@@ -98,10 +100,12 @@ public:
                 else dirs.insert(dirs.end(), r.Sequence.size(), (uint8_t)((r.Flag & 0x10) ? 1 : 0));
             }
             if (anyColl) coll.push_back((uint8_t)(r.CollapsedSummary < 0 ? 0 : r.CollapsedSummary));
+            amp.push_back(r.AmpliconId);
+            anyAmp = anyAmp || r.AmpliconId >= 0;
             soff.push_back((int64_t)bases.size());
         }
         pb2_read_batch b{(int32_t)buffer_.size(), pos0.data(), flag.data(), coff.data(), cigar.data(), soff.data(), bases.data(), quals.data(),
-                         anyDirs ? dirs.data() : nullptr, anyColl ? coll.data() : nullptr};
+                         anyDirs ? dirs.data() : nullptr, anyColl ? coll.data() : nullptr, anyAmp ? amp.data() : nullptr};
         check(pb2_push_reads(h_, &b));
         buffer_.clear();
     }
