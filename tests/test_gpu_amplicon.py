@@ -110,3 +110,28 @@ def test_amplicon_names_with_call_mnvs_are_refused():
     d = make_amplicon_reads(seed=5, variants=VARIANTS)
     with pytest.raises(pb.PiscesB200Error, match="call_mnvs"):
         _product(d, output_gvcf=0, amplicon_bias_filter=0.01, call_mnvs=1)
+
+
+def test_streamed_batches_with_partial_flushes():
+    """Reads pushed batch by batch with pb2_flush(up_to) in between (the reads that end inside the cleared positions leave the store by a device compaction,
+    their amplicon ids with them): the concatenated records equal the oracle's, filter included. Twelve amplicons over two 1000-bp blocks."""
+    import pisces_b200 as pb
+    rng = np.random.default_rng(3)
+    variants = [(int(p), {int(a): float(rng.choice([0.0, 0.05, 0.3, 0.5])) for a in range(12)}) for p in rng.integers(40, 1250, 60)]
+    d = make_amplicon_reads(seed=21, n_amp=12, per_amp=150, stride=100, untagged=40, variants=variants)
+    cfg = dict(output_gvcf=0, amplicon_bias_filter=0.01)
+    orecs = _oracle(d, **cfg)
+    sm = pb.GpuStateManager(pb.make_config(**cfg), "chr1", bytes(d["ref"]).decode())
+    n = len(d["pos0"])
+    cuts = [0, n // 4, n // 2, 3 * n // 4, n]
+    got = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sm.AddReadsSoA(dict(pos0=d["pos0"][a:b], flag=d["flag"][a:b], cigar_off=d["cigar_off"][a:b + 1], cigar=d["cigar"], seq_off=d["seq_off"][a:b + 1], bases=d["bases"],
+                            quals=d["quals"], amplicon=d["amplicon"][a:b]))
+        up_to = None if b == n else int(d["pos0"][b])        # Call(read.Position - 1) of the next read (0-based pos0 = Position - 1)
+        got.append(pb.GpuAlleleCaller().Call(sm, upToPosition=up_to, raw=True))
+    arena = sm.AlleleArena()
+    sm.close()
+    precs = np.concatenate(got)
+    assert max(o.pos for o in orecs) > 1000 and sum((o.filter_mask >> AB) & 1 for o in orecs) >= 3
+    compare_records(orecs, precs, arena)
