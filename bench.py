@@ -295,7 +295,7 @@ def main_c1(a):
     sms = {}   # one handle per chromosome, kept across jobs as a worker thread of the host would (pb2_reset between jobs; intervals stay set)
 
     def step():
-        st = pb.BamReadStager(path)
+        st = pb.BamReadStager(path, packed=True)   # pb2_bam_next_batch_packed: the stager's batches in the one-byte-per-base form
         names = [n for n, _ in st.references]
         n_rec, used = 0, []
         for ref_id, batch, _ in st:

@@ -344,6 +344,9 @@ void pb2_bam_close(pb2_bam_reader* r);
 const char* pb2_bam_last_error(pb2_bam_reader* r);
 int pb2_bam_header(pb2_bam_reader* r, int32_t* n_refs, const char* const** names, const int32_t** lengths, int32_t* is_stitched, int32_t* is_collapsed);
 int pb2_bam_next_batch(pb2_bam_reader* r, const pb2_bam_filter* filter, int32_t max_reads, pb2_read_batch* batch, int32_t* ref_id, int64_t* n_skipped);
+/* The same, as the packed batch of pb2_push_reads_packed (one byte per base + exceptions, compact offsets, per-base directions / collapsed summaries only
+ * when a read of the batch carries the tags): what a host behind a PCIe link should push. Same lifetime rules as pb2_bam_next_batch. */
+int pb2_bam_next_batch_packed(pb2_bam_reader* r, const pb2_bam_filter* filter, int32_t max_reads, pb2_packed_read_batch* batch, int32_t* ref_id, int64_t* n_skipped);
 /* Amplicon names of the reads: Read.GetAmpliconNameIfExists (src/lib/Pisces.Domain/Models/Read.cs:479-486), the XN tag through TagUtils.GetStringTag
  * (src/lib/Alignment.Domain/BamCommon.cs:1182-1216). amplicon_id[i] of read i of the batch handed out last indexes the reader's name dictionary
  * (first-seen order over the kept reads of the file so far), -1 without the tag. Host-side input of the amplicon-bias filter (whose

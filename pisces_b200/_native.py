@@ -81,7 +81,7 @@ RECORD_EXT_DTYPE = [("collapsed_mut", "<i4", (8,)), ("collapsed_total", "<i4", (
 EXPORTS = ["pb2_default_config", "pb2_create", "pb2_destroy", "pb2_last_error", "pb2_device_count", "pb2_set_reference", "pb2_set_intervals",
            "pb2_push_pileup", "pb2_push_pileup_device", "pb2_push_reads", "pb2_push_reads_packed", "pb2_pack_reads", "pb2_pack_pileup", "pb2_stage_reads", "pb2_push_candidates", "pb2_set_forced_alleles", "pb2_allele_arena", "pb2_call_resident", "pb2_call_resident_async", "pb2_resident_sync", "pb2_set_resident_sink", "pb2_sink_sort", "pb2_resident_results", "pb2_flush", "pb2_flush_resident", "pb2_flush_ext",
            "pb2_get_counts", "pb2_reset", "pb2_shard_plan", "pb2_set_owned_range", "pb2_stats", "pb2_stage_stats", "pb2_stream", "pb2_totals", "pb2_vcf_format",
-           "pb2_bam_open", "pb2_bam_close", "pb2_bam_last_error", "pb2_bam_header", "pb2_bam_next_batch", "pb2_bam_batch_amplicons",
+           "pb2_bam_open", "pb2_bam_close", "pb2_bam_last_error", "pb2_bam_header", "pb2_bam_next_batch", "pb2_bam_next_batch_packed", "pb2_bam_batch_amplicons",
            "pb2_bam_amplicon_names"]
 
 _lib = None
@@ -141,6 +141,7 @@ def load():
     L.pb2_bam_header.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_char_p)), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int32)]
     L.pb2_bam_next_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(ReadBatch), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    L.pb2_bam_next_batch_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(PackedReadBatch), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     L.pb2_bam_batch_amplicons.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
     L.pb2_bam_amplicon_names.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_char_p))]
     L.pb2_totals.argtypes = [H, C.POINTER(C.c_int64)]

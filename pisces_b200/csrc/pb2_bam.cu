@@ -30,6 +30,10 @@ struct pb2_bam_reader {
     std::vector<int64_t> cigar_off, seq_off;
     std::vector<uint32_t> cigar;
     std::vector<uint8_t> bases, quals, base_dirs, collapsed;
+    // the packed form of the batch handed out last (pb2_bam_next_batch_packed)
+    std::vector<uint8_t> packed_seq, exc_base, exc_qual, cigar_ops;
+    std::vector<int64_t> exc_index;
+    bool batch_any_dirs = false, batch_any_coll = false;
     std::vector<int32_t> amplicon_id;                    // per read of the batch: index into amplicon_names, -1 without an XN tag
     std::vector<std::string> amplicon_names;             // the file's amplicon names in first-seen order (kept reads only)
     std::vector<const char*> amplicon_name_ptrs;
@@ -321,7 +325,7 @@ static int bam_next_batch_impl(pb2_bam_reader* r, const pb2_bam_filter* flt, int
     batch->seq_off = r->seq_off.data(); batch->bases = r->bases.data(); batch->quals = r->quals.data();
     // always handed out (both hold the values the flags imply where a read carries no XD / XV / XW tag): a stitched or collapsed BAM streamed in small
     // batches mixes tagged and untagged reads, and a batch must not change shape with its content
-    (void)any_dirs; (void)any_coll;
+    r->batch_any_dirs = any_dirs; r->batch_any_coll = any_coll;
     batch->base_dirs = r->base_dirs.data();
     batch->collapsed = r->collapsed.data();
     // amplicon name ids once the file has shown an XN tag (a file without the tag never asks the caller to track amplicons)
@@ -329,6 +333,48 @@ static int bam_next_batch_impl(pb2_bam_reader* r, const pb2_bam_filter* flt, int
     if (ref_id_out) *ref_id_out = batch_ref == -2 ? -1 : batch_ref;
     if (n_skipped) *n_skipped = skipped;
     return PB2_OK;
+}
+
+// The same batch in the packed form of pb2_push_reads_packed: one byte per base + the exception list, compact offsets (operation counts) when every read
+// has at most 255 CIGAR operations, per-base directions only when a read of the batch carried an XD tag and collapsed summaries only when one carried
+// XV / XW (pb2_push_reads_packed gives the other reads their flag-derived defaults): 1.1 bytes per base cross the PCIe link instead of 3.
+extern "C" int pb2_bam_next_batch_packed(pb2_bam_reader* r, const pb2_bam_filter* flt, int32_t max_reads, pb2_packed_read_batch* out, int32_t* ref_id_out, int64_t* n_skipped) {
+    if (!r || !out) return PB2_ERR_ARG;
+    try {
+        pb2_read_batch b;
+        const int rc = bam_next_batch_impl(r, flt, max_reads, &b, ref_id_out, n_skipped);
+        if (rc != PB2_OK) return rc;
+        memset(out, 0, sizeof(*out));
+        out->n_reads = b.n_reads;
+        if (b.n_reads == 0) return PB2_OK;
+        const int64_t n_seq = (int64_t)r->bases.size();
+        r->packed_seq.resize((size_t)n_seq);
+        int64_t cap = std::max<int64_t>(1024, n_seq / 64);
+        for (;;) {
+            r->exc_index.resize((size_t)cap); r->exc_base.resize((size_t)cap); r->exc_qual.resize((size_t)cap);
+            const int64_t ne = pb2_pack_reads(r->bases.data(), r->quals.data(), n_seq, r->packed_seq.data(), r->exc_index.data(), r->exc_base.data(), r->exc_qual.data(), cap);
+            if (ne < 0) return bfail(r, "pb2_pack_reads failed");
+            if (ne <= cap) { out->n_exceptions = ne; break; }
+            cap = ne;
+        }
+        bool compact = true;
+        r->cigar_ops.resize((size_t)b.n_reads);
+        for (int32_t i = 0; i < b.n_reads; i++) {
+            const int64_t ops = r->cigar_off[(size_t)i + 1] - r->cigar_off[(size_t)i];
+            if (ops > 255) { compact = false; break; }
+            r->cigar_ops[(size_t)i] = (uint8_t)ops;
+        }
+        out->pos0 = b.pos0; out->flag = b.flag; out->cigar = b.cigar; out->seq = r->packed_seq.data();
+        out->exc_index = r->exc_index.data(); out->exc_base = r->exc_base.data(); out->exc_qual = r->exc_qual.data();
+        if (compact) { out->cigar_ops = r->cigar_ops.data(); out->n_cigar_total = (int64_t)r->cigar.size(); out->n_seq_total = n_seq; }
+        else { out->cigar_off = b.cigar_off; out->seq_off = b.seq_off; }
+        out->base_dirs = r->batch_any_dirs ? b.base_dirs : nullptr;
+        out->collapsed = r->batch_any_coll ? b.collapsed : nullptr;
+        out->amplicon = b.amplicon;
+        return PB2_OK;
+    }
+    catch (const std::bad_alloc&) { r->error = "out of memory while decoding the BAM file"; return PB2_ERR_NOMEM; }
+    catch (const std::exception& e) { r->error = std::string("malformed BAM file: ") + e.what(); return PB2_ERR_ARG; }
 }
 
 // Amplicon names of the reads (the XN tag, Read.GetAmpliconNameIfExists, src/lib/Pisces.Domain/Models/Read.cs:479-486): ids of the reads of the batch

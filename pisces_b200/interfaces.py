@@ -358,8 +358,10 @@ class GpuStateManager:
         self._chk(self._L.pb2_push_reads_packed(self._h, C.byref(b)))
 
     def AddReadBatch(self, batch):
-        """pb2_push_reads with a ready pb2_read_batch (e.g. from BamReadStager): IStateManager.AddAlleleCounts + FindCandidates for each read."""
-        self._chk(self._L.pb2_push_reads(self._h, C.byref(batch)))
+        """pb2_push_reads / pb2_push_reads_packed with a ready batch struct (e.g. from BamReadStager): IStateManager.AddAlleleCounts + FindCandidates for
+        each read."""
+        push = self._L.pb2_push_reads_packed if isinstance(batch, N.PackedReadBatch) else self._L.pb2_push_reads
+        self._chk(push(self._h, C.byref(batch)))
 
     def AddCandidates(self, candidates, arena=None):
         """IAlleleSource.AddCandidates (pb2_push_candidates). Either a list of dicts (type, pos, ref, alt, support[3], well_anchored[3], open_left,
@@ -518,8 +520,9 @@ class BamReadStager:
     """pb2_bam_*: BAM file -> pb2_read_batch batches (BGZF inflate, record decode, AlignmentSource.ShouldSkipRead, XD / XV / XW / XR), all in the library.
     Iterating yields (ref_id, ReadBatch struct, n_skipped); a batch is only valid until the next one is fetched."""
 
-    def __init__(self, path, min_map_quality=1, remove_duplicates=True, only_proper_pairs=False, max_reads=65536):
+    def __init__(self, path, min_map_quality=1, remove_duplicates=True, only_proper_pairs=False, max_reads=65536, packed=False):
         self._L = N.load()
+        self.packed = packed   # hand out pb2_packed_read_batch (pb2_bam_next_batch_packed: one byte per base, compact offsets) instead of pb2_read_batch
         self._r = C.c_void_p()
         if self._L.pb2_bam_open(os.fsencode(path), C.byref(self._r)) != 0:
             raise PiscesB200Error(N_ERR_ARG, f"pb2_bam_open({path}) failed")
@@ -532,8 +535,9 @@ class BamReadStager:
 
     def __iter__(self):
         while True:
-            b, ref_id, skipped = N.ReadBatch(), C.c_int32(), C.c_int64()
-            if self._L.pb2_bam_next_batch(self._r, self._flt, self.max_reads, C.byref(b), C.byref(ref_id), C.byref(skipped)) != 0:
+            b, ref_id, skipped = (N.PackedReadBatch() if self.packed else N.ReadBatch()), C.c_int32(), C.c_int64()
+            nxt = self._L.pb2_bam_next_batch_packed if self.packed else self._L.pb2_bam_next_batch
+            if nxt(self._r, self._flt, self.max_reads, C.byref(b), C.byref(ref_id), C.byref(skipped)) != 0:
                 raise PiscesB200Error(N_ERR_ARG, self._L.pb2_bam_last_error(self._r).decode())
             if b.n_reads == 0:
                 return

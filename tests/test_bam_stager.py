@@ -168,3 +168,40 @@ def test_malformed_bam_is_rejected_not_crashed(case, tmp_path):
     else:
         assert rc != 0 and L.pb2_bam_last_error(rd)
     L.pb2_bam_close(rd)
+
+
+def test_packed_batches_hold_the_same_reads():
+    """pb2_bam_next_batch_packed against pb2_bam_next_batch on the reference's BAM fixtures (CPU: no device work): the packed bytes + exception list unpack
+    to the same bases and qualities, the operation counts are the offsets' differences, direction / collapsed planes come only with tagged reads."""
+    import ctypes as C
+    import pisces_b200 as pb
+    lut = np.frombuffer(b"AGCT", dtype=np.uint8)
+
+    def arr(ptr, n, dt):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(dt)), shape=(n,)).copy() if ptr and n else np.zeros(0, dtype=dt)
+    for name in ("PhiX_S3.bam", "collapsed.test.stitched.bam", "example_S1.mapped.bam"):
+        path = os.path.join(G, name)
+        plain = pb.BamReadStager(path, max_reads=97)
+        packed = pb.BamReadStager(path, max_reads=97, packed=True)
+        n_batches = 0
+        for (ra, a, sa), (rb, b, sb) in zip(plain, packed):
+            n = a.n_reads
+            assert (ra, sa, n) == (rb, sb, b.n_reads)
+            coff, soff = arr(a.cigar_off, n + 1, C.c_int64), arr(a.seq_off, n + 1, C.c_int64)
+            nseq, ncig = int(soff[-1]), int(coff[-1])
+            assert np.array_equal(arr(a.pos0, n, C.c_int32), arr(b.pos0, n, C.c_int32)) and np.array_equal(arr(a.flag, n, C.c_uint16), arr(b.flag, n, C.c_uint16))
+            assert np.array_equal(arr(a.cigar, ncig, C.c_uint32), arr(b.cigar, ncig, C.c_uint32))
+            assert not b.cigar_off and not b.seq_off and (b.n_cigar_total, b.n_seq_total) == (ncig, nseq)
+            assert np.array_equal(arr(b.cigar_ops, n, C.c_uint8), np.diff(coff).astype(np.uint8))
+            seq = arr(b.seq, nseq, C.c_uint8)
+            bases, quals = lut[seq >> 6].copy(), (seq & 63).copy()
+            ei = arr(b.exc_index, b.n_exceptions, C.c_int64)
+            bases[ei], quals[ei] = arr(b.exc_base, b.n_exceptions, C.c_uint8), arr(b.exc_qual, b.n_exceptions, C.c_uint8)
+            assert np.array_equal(bases, arr(a.bases, nseq, C.c_uint8)) and np.array_equal(quals, arr(a.quals, nseq, C.c_uint8))
+            tagged = name.startswith("collapsed")
+            assert bool(b.base_dirs) == tagged and bool(b.collapsed) == tagged
+            if tagged:
+                assert np.array_equal(arr(a.base_dirs, nseq, C.c_uint8), arr(b.base_dirs, nseq, C.c_uint8))
+            n_batches += 1
+        assert n_batches >= 1
+        plain.close(); packed.close()

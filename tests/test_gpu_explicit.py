@@ -405,16 +405,18 @@ def test_collapsed_stitched_full_text_golden_through_cuda_path():
         assert a == b
 
 
-def test_bam_file_to_vcf_text_through_the_library():
+@pytest.mark.parametrize("packed", [False, True])
+def test_bam_file_to_vcf_text_through_the_library(packed):
     """The whole path from the library's own entry points: PhiX_S3.bam -> pb2_bam_* (decode, read filter) -> pb2_push_reads -> pb2_flush, streamed
     block by block -> pb2_vcf_format == PhiX_S3.noisy.vcf, line by line; and collapsed.test.stitched.bam (XD / XV / XW / XR from the tags)
-    -> test_truth.stitched.genome.vcf."""
+    -> test_truth.stitched.genome.vcf. packed: the stager hands out pb2_packed_read_batch (one byte per base, compact offsets, tag planes only with
+    tagged reads) and the reads go through pb2_push_reads_packed."""
     import ctypes as C
     import os
     pb = _pb()
     G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     genome = open(os.path.join(G, "phix_genome.txt")).read().strip()
-    st = pb.BamReadStager(os.path.join(G, "PhiX_S3.bam"), max_reads=50)
+    st = pb.BamReadStager(os.path.join(G, "PhiX_S3.bam"), max_reads=50, packed=packed)
     sm = pb.GpuStateManager(pb.make_config(min_coverage=2, min_base_call_quality=10, min_variant_qscore=1, min_frequency=0.00001, forced_noise_level=40, call_mnvs=1,
                                            max_size_mnv=10, max_gap_mnv=5, no_call_filter=1.0, expect_stitched=int(st.is_stitched)), st.references[0][0], genome)
     caller = pb.GpuAlleleCaller()
@@ -432,7 +434,7 @@ def test_bam_file_to_vcf_text_through_the_library():
                                  "AGCACCATCAAGCAGGTATGGCCTCCATC")
     want = [l.rstrip("\n") for l in open(os.path.join(G, "collapsed_stitched.records.vcf"))]
     for max_reads in (65536, 3, 1):   # streamed in tiny batches too: tagged and untagged reads mix, every batch has the same shape
-        st = pb.BamReadStager(os.path.join(G, "collapsed.test.stitched.bam"), max_reads=max_reads)
+        st = pb.BamReadStager(os.path.join(G, "collapsed.test.stitched.bam"), max_reads=max_reads, packed=packed)
         sm = pb.GpuStateManager(pb.make_config(call_mnvs=1, max_size_mnv=100, max_gap_mnv=10, expect_stitched=1, expect_collapsed=1, skip_validation=1, amplicon_bias_filter=0.01),
                                 "chr1", seq)
         for _, batch, _ in st:
