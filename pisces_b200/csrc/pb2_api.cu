@@ -673,13 +673,32 @@ __global__ static void dirs_from_flags_kernel(const uint16_t* __restrict__ flag,
 
 // PB2 packed sequence bytes -> the store's ASCII bases + qualities; then the exceptions (bases that are not A/C/G/T, qualities the byte cannot hold)
 __global__ static void unpack_seq_kernel(const uint8_t* __restrict__ seq, int64_t n, uint8_t* __restrict__ bases, uint8_t* __restrict__ quals) {
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= n) return;
+    // sixteen packed bytes per thread: one 16-byte load, two 16-byte stores (the vector path needs the three pointers 16-byte aligned; the head of a
+    // push that appends at an odd offset and the tail go byte by byte)
     const uint32_t lut = 'A' | ('G' << 8) | ('C' << 16) | ((uint32_t)'T' << 24);   // allele2: AlleleType order A G C T
-    for (int k = 0; k < 4 && i + k < n; k++) {
-        const uint32_t b = seq[i + k];
-        bases[i + k] = (uint8_t)(lut >> (8 * (b >> 6)));
-        quals[i + k] = (uint8_t)(b & 63u);
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i >= n) return;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(seq) | reinterpret_cast<uintptr_t>(bases) | reinterpret_cast<uintptr_t>(quals)) & 15) == 0;
+    if (aligned && i + 16 <= n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(seq + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t b[4], q[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            q[k] = w[k] & 0x3f3f3f3fu;
+            uint32_t o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) o |= ((lut >> (8 * ((w[k] >> (8 * j + 6)) & 3u))) & 0xffu) << (8 * j);
+            b[k] = o;
+        }
+        *reinterpret_cast<uint4*>(bases + i) = make_uint4(b[0], b[1], b[2], b[3]);
+        *reinterpret_cast<uint4*>(quals + i) = make_uint4(q[0], q[1], q[2], q[3]);
+        return;
+    }
+    for (int k = 0; k < 16 && i + k < n; k++) {
+        const uint32_t v = seq[i + k];
+        bases[i + k] = (uint8_t)(lut >> (8 * (v >> 6)));
+        quals[i + k] = (uint8_t)(v & 63u);
     }
 }
 __global__ static void apply_seq_exceptions_kernel(const int64_t* __restrict__ index, const uint8_t* __restrict__ eb, const uint8_t* __restrict__ eq, int64_t n_exc, int64_t lo,
@@ -813,7 +832,7 @@ static int push_reads_impl(pb2_handle* h, const pb2_read_batch* b, const uint8_t
         if (seq) {
             CU(h, pool_alloc(h, (void**)&d_seq, (size_t)nseq));
             CU(h, h2d_in_pieces(h, d_seq, seq + s_lo, (size_t)nseq, st));
-            unpack_seq_kernel<<<(unsigned)(((nseq + 3) / 4 + 255) / 256), 256, 0, st>>>(d_seq, nseq, R.bases.p + R.n_seq, R.quals.p + R.n_seq);
+            unpack_seq_kernel<<<(unsigned)(((nseq + 15) / 16 + 255) / 256), 256, 0, st>>>(d_seq, nseq, R.bases.p + R.n_seq, R.quals.p + R.n_seq);
             if (n_exc > 0) {
                 CU(h, pool_alloc_t(h, &d_exc_index, (size_t)n_exc)); CU(h, pool_alloc_t(h, &d_exc_base, (size_t)n_exc)); CU(h, pool_alloc_t(h, &d_exc_qual, (size_t)n_exc));
                 CU(h, cudaMemcpyAsync(d_exc_index, exc_index, sizeof(int64_t) * (size_t)n_exc, k, st));
