@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--tune-ctas", type=int, default=0, help="hot-kernel CTAs per SM (tuning experiments)")
     ap.add_argument("--tune-prefetch", type=int, default=0, help="tuning experiments (9: PTILE32 staging instead of PVERT)")
     ap.add_argument("--cpu-sample-loci", type=int, default=100_000)
-    ap.add_argument("--cpu-repeats", type=int, default=3)
+    ap.add_argument("--cpu-repeats", type=int, default=5, help="cpu_baseline: best of this many runs of the sample (SURVEY 8d)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-jobs", type=int, default=0, help="concurrent (BAM x chromosome) jobs of the end-to-end leg: one handle + one host thread each, as Pisces -t N runs them "
                     "(0: host cores / (2 x ranks), between 2 and 6 - measured at N = 1: 2 jobs 57.8, 3 61.2, 4 65.2, 6 68.3 M loci/s)")
