@@ -50,3 +50,15 @@ def test_no_cpu_fallback():
     with pytest.raises(pb.PiscesB200Error) as e:
         pb.GpuStateManager()
     assert e.value.code == -2 and "no CPU path" in str(e.value)
+
+
+def test_integration_doc_binds_every_entry_point():
+    """INTEGRATION.md shows the reference-side binding (P/Invoke stubs): every function include/pisces_b200.h declares appears there."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "pisces_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    funcs = sorted(set(re.findall(r"\b(pb2_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(funcs) > 40
+    assert [f for f in funcs if f not in doc] == []
